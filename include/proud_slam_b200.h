@@ -1,0 +1,244 @@
+/*
+ * proud_slam_b200.h -- C ABI of libproud_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the Proud-SLAM mapping/tracking render path.  Every
+ * entry point takes plain device pointers, sizes and a CUDA stream
+ * (cudaStream_t passed as void*); no torch types cross this boundary.  Each
+ * declaration cites the reference interface it replaces (paths relative to the
+ * reference repository).  Conventions:
+ *
+ *   - return value: 0 = ok, <0 = bad argument (PSLAM_E_*), >0 = cudaError_t of
+ *     the failing launch.  Nothing aborts or exit()s (the reference's
+ *     CUDA_CHECK_ERRORS does, sparse_voxels/include/cuda_utils.h:37-48);
+ *     pslam_last_error() returns a thread-local message for the last failure.
+ *   - all launches are asynchronous on `stream`; the library keeps no global
+ *     mutable state and retains no pointer after return.
+ *   - outputs and workspaces are caller-allocated (the reference allocates
+ *     inside C++, intersect.cpp:98-106 / sample.cpp:80-89; the Python shim
+ *     proud_slam_b200/grid.py does that allocation instead).
+ *   - tensors are dense row-major fp32 / int32 unless stated.
+ */
+#ifndef PROUD_SLAM_B200_H
+#define PROUD_SLAM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSLAM_ABI_VERSION 1
+#define PSLAM_E_ARG (-1)      /* null pointer / non-positive size */
+#define PSLAM_E_RANGE (-2)    /* size outside what the kernels support */
+#define PSLAM_E_ALIGN (-3)    /* pointer not 16-byte aligned where required */
+
+typedef void *pslam_stream_t; /* cudaStream_t */
+
+int pslam_abi_version(void);
+const char *pslam_last_error(void);
+/* Device properties the host side sizes grids with: out[0]=SM count,
+ * out[1]=compute capability*10, out[2]=max opt-in smem per block. */
+int pslam_device_info(int *out3);
+
+/* ------------------------------------------------------------------------
+ * `grid` module, third_party/sparse_voxels/src/binding.cpp:12-20
+ * ---------------------------------------------------------------------- */
+
+/* svo_intersect, include/intersect.h:14-15, src/intersect.cpp:83-112,
+ * kernel src/intersect_gpu.cu:191-270.  ray_start/ray_dir [b,m,3], points
+ * [b,n,3], children [b,n,9] -> idx [b,m,n_max] (-1 padded), min_depth /
+ * max_depth [b,m,n_max] (0 padded).  Hits are in the reference's DFS order. */
+int pslam_svo_intersect(int b, int n, int m, float voxelsize, int n_max,
+                        const float *ray_start, const float *ray_dir,
+                        const float *points, const int *children,
+                        int *idx, float *min_depth, float *max_depth,
+                        pslam_stream_t stream);
+
+/* aabb_intersect, include/intersect.h:12-13, src/intersect.cpp:49-76, kernel :142-189. */
+int pslam_aabb_intersect(int b, int n, int m, float voxelsize, int n_max,
+                         const float *ray_start, const float *ray_dir,
+                         const float *points,
+                         int *idx, float *min_depth, float *max_depth,
+                         pslam_stream_t stream);
+
+/* ball_intersect, include/intersect.h:10-11, src/intersect.cpp:15-42, kernel :13-73. */
+int pslam_ball_intersect(int b, int n, int m, float radius, int n_max,
+                         const float *ray_start, const float *ray_dir,
+                         const float *points,
+                         int *idx, float *min_depth, float *max_depth,
+                         pslam_stream_t stream);
+
+/* triangle_intersect, include/intersect.h:16-17, src/intersect.cpp:119-146,
+ * kernel :272-387.  face_points [b,n,9] -> idx [b,m,n_max], depth
+ * [b,m,n_max,3], uv [b,m,n_max,2]. */
+int pslam_triangle_intersect(int b, int n, int m, float cagesize, float blur, int n_max,
+                             const float *ray_start, const float *ray_dir,
+                             const float *face_points,
+                             int *idx, float *depth, float *uv,
+                             pslam_stream_t stream);
+
+/* inverse_cdf_sampling, include/sample.h:13-15, src/sample.cpp:56-95, kernel
+ * src/sample_gpu.cu:133-239.  pts_idx/min_depth/max_depth/probs
+ * [b,num_rays,max_hits], steps [b,num_rays], uniform_noise and the three
+ * outputs [b,num_rays,max_steps] (outputs are fully initialised: idx=-1,
+ * depth=dists=0).  Reproduces the reference's tail-loop behaviour (SURVEY
+ * Appendix A-Q7) bit for bit. */
+int pslam_inverse_cdf_sampling(int b, int num_rays, int max_hits, int max_steps,
+                               float fixed_step_size,
+                               const int *pts_idx, const float *min_depth,
+                               const float *max_depth, const float *uniform_noise,
+                               const float *probs, const float *steps,
+                               int *sampled_idx, float *sampled_depth,
+                               float *sampled_dists, pslam_stream_t stream);
+
+/* uniform_ray_sampling, include/sample.h:10-12, src/sample.cpp:21-54, kernel :13-131. */
+int pslam_uniform_ray_sampling(int b, int num_rays, int max_hits, int max_steps,
+                               float step_size,
+                               const int *pts_idx, const float *min_depth,
+                               const float *max_depth, const float *uniform_noise,
+                               int *sampled_idx, float *sampled_depth,
+                               float *sampled_dists, pslam_stream_t stream);
+
+/* Test helper: out[i] = __fdividef(1.0f, in[i]) -- the device reciprocal the
+ * slab test uses (intersect_gpu.cu:91-101), so a CPU oracle can be compared
+ * bit for bit. */
+int pslam_debug_rcp(const float *in, float *out, int n, pslam_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Torch-level stages of render_rays (src/variations/render_helpers.py)
+ * ---------------------------------------------------------------------- */
+
+/* Decoder parameters in the reference's own layout (nn.Linear weight [out,in],
+ * src/variations/nrgbd.py:106-113; depth=2, skips=[], embedder "none",
+ * sdf_dim=128, in_dim=16).  width is 128 (Replica) or 256 (ScanNet/ARKit). */
+typedef struct {
+    int width;
+    const float *W1, *b1;   /* [w,16], [w]        */
+    const float *W2, *b2;   /* [w,w], [w]         */
+    const float *W3, *b3;   /* [129,w], [129]     */
+    const float *W4, *b4;   /* [w,144], [w]       */
+    const float *W5, *b5;   /* [3,w], [3]         */
+} pslam_decoder_t;
+
+/* Gradients, same shapes; accumulated into (+=).  Any pointer may be NULL only
+ * if all are (decoder gradients disabled). */
+typedef struct {
+    float *W1, *b1, *W2, *b2, *W3, *b3, *W4, *b4, *W5, *b5;
+} pslam_decoder_grad_t;
+
+/* get_features_vox + get_embeddings_vox + trilinear_interp,
+ * render_helpers.py:105-156, 87-99, 47-59.  xyz [p,3], vox_idx [p] (row ids
+ * into centres/vertex_idx), centres [N,3], vertex_idx [N,8], emb [E,16]
+ * -> feat [p,16]. */
+int pslam_trilinear_fwd(int p, const float *xyz, const int *vox_idx,
+                        const float *centres, const int *vertex_idx, const float *emb,
+                        float voxel_size, float *feat, pslam_stream_t stream);
+/* Backward of the above: g_feat [p,16] -> g_emb [E,16] (+=, atomics) and
+ * g_xyz [p,3] (either may be NULL). */
+int pslam_trilinear_bwd(int p, const float *xyz, const int *vox_idx,
+                        const float *centres, const int *vertex_idx, const float *emb,
+                        float voxel_size, const float *g_feat,
+                        float *g_emb, float *g_xyz, pslam_stream_t stream);
+
+/* Decoder.get_values, nrgbd.py:116-135: feat [p,16] -> out [p,4] = (r,g,b,sdf). */
+int pslam_decoder_fwd(int p, const pslam_decoder_t *dec, const float *feat,
+                      float *out, pslam_stream_t stream);
+/* Backward: g_out [p,4] -> g_feat [p,16] (may be NULL) and parameter
+ * gradients (grad may be NULL).  Activations are recomputed, not stored. */
+int pslam_decoder_bwd(int p, const pslam_decoder_t *dec, const float *feat,
+                      const float *g_out, float *g_feat,
+                      const pslam_decoder_grad_t *grad, pslam_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Fused render + loss + backward (one mapping / tracking iteration):
+ * render_rays (render_helpers.py:351-556) + Criterion.forward
+ * (src/criterion.py:16-116) + loss.backward(), with zero host syncs.
+ * ---------------------------------------------------------------------- */
+#define PSLAM_F_TRACKING   1   /* median-gated depth loss (criterion.py:45-49) */
+#define PSLAM_F_GRAD_EMB   2
+#define PSLAM_F_GRAD_DEC   4
+#define PSLAM_F_GRAD_RAYS  8
+#define PSLAM_F_FORWARD_ONLY 16
+
+/* device-side counters written by the pipeline (int32 each) */
+enum {
+    PSLAM_C_RH = 0,       /* rays that hit (R_h) */
+    PSLAM_C_P = 1,        /* max hits per ray after trimming (P / H) */
+    PSLAM_C_NSAMP = 2,    /* total valid samples */
+    PSLAM_C_S = 3,        /* max samples per ray (S) */
+    PSLAM_C_OVERFLOW = 4, /* !=0: sample_cap too small or DFS stack overflow */
+    PSLAM_C_TILE = 5,     /* internal work counters */
+    PSLAM_C_TILE2 = 6,
+    PSLAM_C_COUNT = 16
+};
+
+/* loss block written by the pipeline (fp32 each) */
+enum {
+    PSLAM_L_TOTAL = 0, PSLAM_L_COLOR = 1, PSLAM_L_DEPTH = 2, PSLAM_L_FS = 3, PSLAM_L_SDF = 4,
+    PSLAM_L_COUNT = 16
+};
+
+typedef struct {
+    /* sizes */
+    int R;              /* rays in the batch */
+    int N;              /* octree rows */
+    int E;              /* embedding rows */
+    int n_max;          /* hit cap per ray (reference hard-codes 50, voxel_helpers.py:561) */
+    int sample_cap;     /* capacity (samples) of the CSR sample arrays */
+    int flags;          /* PSLAM_F_* */
+    float voxel_size, step_size, truncation, max_distance, max_depth;
+    float w_rgb, w_depth, w_fs, w_sdf;
+    /* inputs */
+    const float *rays_o, *rays_d;          /* [R,3] */
+    const float *target_rgb;               /* [R,3] */
+    const float *target_depth;             /* [R]   */
+    const float *centres;                  /* [N,3] voxel_center_xyz */
+    const int *structure;                  /* [N,9] voxel_structure  */
+    const int *vertex_idx;                 /* [N,8] voxel_vertex_idx */
+    const float *emb;                      /* [E,16] voxel_vertex_emb */
+    pslam_decoder_t dec;
+    const float *noise;                    /* [>=R_h, noise_stride] uniform(0.001,0.999) or NULL */
+    int noise_stride;
+    uint64_t seed;                         /* counter-based noise when noise==NULL */
+    /* intermediates (caller-allocated; readable by tests / the drop-in API) */
+    int *hit_idx;                          /* [n_max,R] slot-major, sorted by entry depth */
+    float *hit_min, *hit_max;              /* [n_max,R] */
+    int *hit_count;                        /* [R] valid hits per ray after trimming */
+    int *hit_ray;                          /* [R] rank -> ray id (first R_h valid) */
+    int *ray_rank;                         /* [R] ray id -> rank or -1 */
+    int *samp_off;                         /* [R+1] CSR offsets by rank */
+    int *samp_vox;                         /* [sample_cap] voxel row id */
+    int *samp_ray;                         /* [sample_cap] rank of the owning ray */
+    float *samp_z;                         /* [sample_cap] depth (segment mid-point) */
+    float *samp_dist;                      /* [sample_cap] segment length */
+    float *samp_out;                       /* [sample_cap,4] (r,g,b,sdf) from the decoder */
+    float *samp_gout;                      /* [sample_cap,4] dL/d(r,g,b,sdf) */
+    float *ray_out;                        /* [R,8] by rank: r,g,b,depth,z_min,U,|dd|/sqrt(var),gate */
+    int *scratch_i;                        /* [4*ceil(R/128)+64] block partials for the scans */
+    float *scratch_f;                      /* [16*ceil(R/4)+64] block partials for the loss sums... see api.cu */
+    int *counters;                         /* [PSLAM_C_COUNT] */
+    /* outputs */
+    float *loss;                           /* [PSLAM_L_COUNT] */
+    float *g_emb;                          /* [E,16] += */
+    pslam_decoder_grad_t g_dec;            /* += */
+    float *g_rays_o, *g_rays_d;            /* [R,3] by ray id, overwritten */
+} pslam_render_t;
+
+/* Bytes the caller must provide for scratch_i / scratch_f for a batch of R rays. */
+int64_t pslam_render_scratch_i_count(int R);
+int64_t pslam_render_scratch_f_count(int R);
+
+/* Stage 1: intersection, sort/trim, compaction, sampling (kernels 1-2 + a4-a6).
+ * Fills hit_*, samp_* and counters.  No host sync. */
+int pslam_render_sample(const pslam_render_t *p, pslam_stream_t stream);
+/* Stage 2: trilinear lookup + decoder + compositing + loss (kernels 3-5 forward). */
+int pslam_render_forward(const pslam_render_t *p, pslam_stream_t stream);
+/* Stage 3: backward of stage 2 into g_emb / g_dec / g_rays_*. */
+int pslam_render_backward(const pslam_render_t *p, pslam_stream_t stream);
+/* All three stages back to back. */
+int pslam_render_step(const pslam_render_t *p, pslam_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PROUD_SLAM_B200_H */

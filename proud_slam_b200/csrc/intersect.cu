@@ -1,0 +1,430 @@
+// Kernel 1: ray vs sparse-voxel-octree intersection (+ the other `grid`
+// intersectors kept for API completeness).
+//
+// Semantics follow the reference kernel
+// third_party/sparse_voxels/src/intersect_gpu.cu:75-140 (slab test) and
+// :191-270 (DFS): root is row 0, a node is a leaf iff children[k,8]==1, the box
+// half-size is 0.5*voxelsize*children[k,8], children are pushed 0..7 so child 7
+// is popped first, hits are appended in that DFS order up to n_max.  The slab
+// arithmetic keeps the reference's operation order and its __fdividef
+// reciprocal so depths are bit-identical.
+//
+// What is different (B200-first): one thread per ray over a flat grid sized to
+// the ray count instead of 256 blocks x <=32 threads over a 256x replicated
+// octree; the ray, its reciprocal direction and the traversal stack live in
+// registers / shared memory (stack[level][thread], conflict-free) instead of a
+// zero-filled 1 KB local array with the ray re-read from global per node; the
+// octree is read once through the read-only path and stays L1/L2 resident.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace pslam {
+
+constexpr int kSmemStack = 64;    // 7*L+1 entries cover L <= 9 levels (grid_dim <= 512)
+constexpr int kSpillStack = 192;  // beyond that: local memory, total 256 as intersect_gpu.cu:229
+constexpr int kIntersectThreads = 128;
+
+struct Ray {
+    float o[3], inv[3];
+};
+
+__device__ __forceinline__ Ray load_ray(const float *__restrict__ ray_start, const float *__restrict__ ray_dir, int64_t r)
+{
+    Ray ray;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        ray.o[a] = __ldg(ray_start + r * 3 + a);
+        ray.inv[a] = __fdividef(1.0f, __ldg(ray_dir + r * 3 + a));  // intersect_gpu.cu:91-101
+    }
+    return ray;
+}
+
+// intersect_gpu.cu:75-140.  Explicit _rn intrinsics pin the reference's
+// (c -/+ h - o) * inv evaluation order (no FMA contraction is possible there
+// either: SASS of the reference shows FADD,FADD,FMUL).
+__device__ __forceinline__ bool slab(const Ray &ray, float cx, float cy, float cz, float half, float &t_lo, float &t_hi)
+{
+    float lo = 0.0f, hi = 100000.0f;
+    const float c[3] = {cx, cy, cz};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float d_lo = __fmul_rn(__fsub_rn(__fsub_rn(c[a], half), ray.o[a]), ray.inv[a]);
+        float d_hi = __fmul_rn(__fsub_rn(__fadd_rn(c[a], half), ray.o[a]), ray.inv[a]);
+        if (d_hi < d_lo) { float t = d_lo; d_lo = d_hi; d_hi = t; }
+        if (d_hi < lo) return false;
+        if (d_lo > hi) return false;
+        lo = (d_lo > lo) ? d_lo : lo;
+        hi = (d_hi < hi) ? d_hi : hi;
+        if (lo > hi) return false;
+    }
+    t_lo = lo; t_hi = hi;
+    return lo > -1.0f;  // "depths.x > -1.0f", intersect_gpu.cu:247
+}
+
+// DFS over the flattened octree.  `emit(cnt, k, lo, hi)` stores hit number cnt.
+// Returns the hit count, or -1-count when the stack overflowed 256 entries (the
+// reference asserts there, intersect_gpu.cu:235).
+template <class Emit>
+__device__ __forceinline__ int dfs(const Ray &ray, const float *__restrict__ points, const int *__restrict__ children,
+                                   float half_voxel, int n_max, int *s_stack, Emit emit)
+{
+    int spill[kSpillStack];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    int top = 0, cnt = 0;
+    s_stack[tid] = 0;  // root = row 0, intersect_gpu.cu:232
+    while (top > -1 && cnt < n_max) {
+        const int k = (top < kSmemStack) ? s_stack[top * nthr + tid] : spill[top - kSmemStack];
+        --top;
+        const int *ch = children + (int64_t)k * 9;
+        const int side = __ldg(ch + 8);
+        float lo, hi;
+        if (!slab(ray, __ldg(points + (int64_t)k * 3), __ldg(points + (int64_t)k * 3 + 1), __ldg(points + (int64_t)k * 3 + 2),
+                  __fmul_rn(half_voxel, (float)side), lo, hi))
+            continue;
+        if (side == 1) {  // terminal node, intersect_gpu.cu:250
+            emit(cnt, k, lo, hi);
+            ++cnt;
+            continue;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int c = __ldg(ch + u);
+            if (c > -1) {
+                ++top;
+                if (top < kSmemStack) s_stack[top * nthr + tid] = c;
+                else if (top < kSmemStack + kSpillStack) spill[top - kSmemStack] = c;
+                else return -1 - cnt;
+            }
+        }
+    }
+    return cnt;
+}
+
+// ---- reference layout (grid.svo_intersect) --------------------------------------------------
+__global__ void __launch_bounds__(kIntersectThreads)
+k_svo_intersect_ref(int b, int n, int m, float half_voxel, int n_max, const float *__restrict__ ray_start,
+                    const float *__restrict__ ray_dir, const float *__restrict__ points,
+                    const int *__restrict__ children, int *__restrict__ idx, float *__restrict__ min_depth,
+                    float *__restrict__ max_depth)
+{
+    extern __shared__ int s_stack[];
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= (int64_t)b * m) return;
+    const int bi = (int)(r / m);
+    const Ray ray = load_ray(ray_start, ray_dir, r);
+    int *oi = idx + r * n_max;
+    float *omin = min_depth + r * n_max, *omax = max_depth + r * n_max;
+    int cnt = dfs(ray, points + (int64_t)bi * n * 3, children + (int64_t)bi * n * 9, half_voxel, n_max, s_stack,
+                  [&](int c, int k, float lo, float hi) { oi[c] = k; omin[c] = lo; omax[c] = hi; });
+    if (cnt < 0) cnt = -1 - cnt;
+    for (int l = cnt; l < n_max; ++l) { oi[l] = -1; omin[l] = 0.0f; omax[l] = 0.0f; }  // intersect.cpp:98-106
+}
+
+// ---- fused layout: slot-major [n_max, R], sorted by entry depth, trimmed at max_distance ------
+// Does the work of voxel_helpers.py:571-588 (fill/sort/gather/trim) per ray in
+// the same kernel: a stable insertion sort over the (mean ~3.6) hits.
+__global__ void __launch_bounds__(kIntersectThreads)
+k_intersect_fused(int R, float half_voxel, int n_max, float max_distance, const float *__restrict__ ray_start,
+                  const float *__restrict__ ray_dir, const float *__restrict__ points,
+                  const int *__restrict__ children, int *__restrict__ hit_idx, float *__restrict__ hit_min,
+                  float *__restrict__ hit_max, int *__restrict__ hit_count, int *__restrict__ block_hits,
+                  int *__restrict__ counters)
+{
+    extern __shared__ int s_stack[];
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    int count = 0;
+    bool overflow = false;
+    if (r < R) {
+        const Ray ray = load_ray(ray_start, ray_dir, r);
+        int cnt = dfs(ray, points, children, half_voxel, n_max, s_stack, [&](int c, int k, float lo, float hi) {
+            const int64_t at = (int64_t)c * R + r;
+            hit_idx[at] = k; hit_min[at] = lo; hit_max[at] = hi;
+        });
+        if (cnt < 0) { overflow = true; cnt = -1 - cnt; }
+        // stable insertion sort by entry depth: ties keep DFS order (SURVEY A-Q3)
+        for (int i = 1; i < cnt; ++i) {
+            const int64_t ai = (int64_t)i * R + r;
+            const float kmin = hit_min[ai], kmax = hit_max[ai];
+            const int kidx = hit_idx[ai];
+            int j = i - 1;
+            while (j >= 0 && hit_min[(int64_t)j * R + r] > kmin) {
+                const int64_t from = (int64_t)j * R + r, to = from + R;
+                hit_min[to] = hit_min[from]; hit_max[to] = hit_max[from]; hit_idx[to] = hit_idx[from];
+                --j;
+            }
+            const int64_t to = (int64_t)(j + 1) * R + r;
+            hit_min[to] = kmin; hit_max[to] = kmax; hit_idx[to] = kidx;
+        }
+        // drop hits that start beyond max_distance (voxel_helpers.py:578)
+        while (count < cnt && !(hit_min[(int64_t)count * R + r] > max_distance)) ++count;
+        hit_count[r] = count;
+    }
+    const int nhit = __syncthreads_count(count > 0);
+    const int wmax = warp_max_i(count);
+    if ((threadIdx.x & 31) == 0 && wmax > 0) atomicMax(counters + PSLAM_C_P, wmax);
+    if (overflow) atomicOr(counters + PSLAM_C_OVERFLOW, 2);
+    if (threadIdx.x == 0) block_hits[blockIdx.x] = nhit;
+}
+
+// Exclusive scan of `nb` block partials by one block; total -> *total_out.
+__global__ void __launch_bounds__(1024) k_scan_partials(int *__restrict__ partials, int nb, int *__restrict__ total_out)
+{
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nb; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = (i < nb) ? partials[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int w = s_warp[threadIdx.x];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, w, o);
+                if (threadIdx.x >= o) w += y;
+            }
+            s_warp[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const int warp_excl = (threadIdx.x >> 5) ? s_warp[(threadIdx.x >> 5) - 1] : 0;
+        const int carry = s_carry;
+        if (i < nb) partials[i] = carry + warp_excl + x - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + warp_excl + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_out = s_carry;
+}
+
+// rank of every hit ray (order-preserving compaction, render_helpers.py:390-398).
+__global__ void __launch_bounds__(kIntersectThreads)
+k_compact_rays(int R, const int *__restrict__ hit_count, const int *__restrict__ block_base, int *__restrict__ hit_ray,
+               int *__restrict__ ray_rank)
+{
+    __shared__ int s_warp[kIntersectThreads / 32];
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool hit = (r < R) && hit_count[r] > 0;
+    const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_warp[warp] = __popc(ballot);
+    __syncthreads();
+    int base = block_base[blockIdx.x];
+    for (int w = 0; w < warp; ++w) base += s_warp[w];
+    const int rank = base + __popc(ballot & ((1u << lane) - 1u));
+    if (r < R) ray_rank[r] = hit ? rank : -1;
+    if (hit) hit_ray[rank] = r;
+}
+
+// ---- API-surface kernels (not perf targets) ---------------------------------------------------
+__global__ void k_aabb_intersect_ref(int b, int n, int m, float half_voxel, int n_max,
+                                     const float *__restrict__ ray_start, const float *__restrict__ ray_dir,
+                                     const float *__restrict__ points, int *__restrict__ idx,
+                                     float *__restrict__ min_depth, float *__restrict__ max_depth)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= (int64_t)b * m) return;
+    const float *pts = points + (int64_t)(r / m) * n * 3;
+    const Ray ray = load_ray(ray_start, ray_dir, r);
+    int *oi = idx + r * n_max;
+    float *omin = min_depth + r * n_max, *omax = max_depth + r * n_max;
+    int cnt = 0;
+    for (int k = 0; k < n && cnt < n_max; ++k) {  // intersect_gpu.cu:172-187
+        float lo, hi;
+        if (slab(ray, __ldg(pts + k * 3), __ldg(pts + k * 3 + 1), __ldg(pts + k * 3 + 2), half_voxel, lo, hi)) {
+            oi[cnt] = k; omin[cnt] = lo; omax[cnt] = hi; ++cnt;
+        }
+    }
+    for (int l = cnt; l < n_max; ++l) { oi[l] = -1; omin[l] = 0.0f; omax[l] = 0.0f; }
+}
+
+__global__ void k_ball_intersect_ref(int b, int n, int m, float radius, int n_max,
+                                     const float *__restrict__ ray_start, const float *__restrict__ ray_dir,
+                                     const float *__restrict__ points, int *__restrict__ idx,
+                                     float *__restrict__ min_depth, float *__restrict__ max_depth)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= (int64_t)b * m) return;
+    const float *pts = points + (int64_t)(r / m) * n * 3;
+    const float x0 = ray_start[r * 3], y0 = ray_start[r * 3 + 1], z0 = ray_start[r * 3 + 2];
+    const float xw = ray_dir[r * 3], yw = ray_dir[r * 3 + 1], zw = ray_dir[r * 3 + 2];
+    const float radius2 = radius * radius;
+    int *oi = idx + r * n_max;
+    float *omin = min_depth + r * n_max, *omax = max_depth + r * n_max;
+    int cnt = 0;
+    for (int k = 0; k < n && cnt < n_max; ++k) {  // intersect_gpu.cu:51-71
+        const float x = pts[k * 3] - x0, y = pts[k * 3 + 1] - y0, z = pts[k * 3 + 2] - z0;
+        const float d2 = x * x + y * y + z * z;
+        const float proj = x * xw + y * yw + z * zw;
+        const float d2_proj = proj * proj;  // pow(., 2)
+        const float r2 = d2 - d2_proj;
+        if (r2 < radius2) {
+            const float depth = sqrtf(d2_proj), blur = sqrtf(radius2 - r2);
+            oi[cnt] = k; omin[cnt] = depth - blur; omax[cnt] = depth + blur; ++cnt;
+        }
+    }
+    for (int l = cnt; l < n_max; ++l) { oi[l] = -1; omin[l] = 0.0f; omax[l] = 0.0f; }
+}
+
+struct F3 { float x, y, z; };
+__device__ __forceinline__ F3 sub3(F3 a, F3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ F3 cross3(F3 a, F3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+__device__ __forceinline__ float dot3(F3 a, F3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+__global__ void k_triangle_intersect_ref(int b, int n, int m, float cagesize, float blur, int n_max,
+                                         const float *__restrict__ ray_start, const float *__restrict__ ray_dir,
+                                         const float *__restrict__ face_points, int *__restrict__ idx,
+                                         float *__restrict__ depth, float *__restrict__ uv)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= (int64_t)b * m) return;
+    const float *fp = face_points + (int64_t)(r / m) * n * 9;
+    const F3 ori = {ray_start[r * 3], ray_start[r * 3 + 1], ray_start[r * 3 + 2]};
+    const F3 dir = {ray_dir[r * 3], ray_dir[r * 3 + 1], ray_dir[r * 3 + 2]};
+    int *oi = idx + r * n_max;
+    float *od = depth + r * n_max * 3, *ouv = uv + r * n_max * 2;
+    for (int l = 0; l < n_max; ++l) { oi[l] = -1; od[l * 3] = od[l * 3 + 1] = od[l * 3 + 2] = 0.0f; ouv[l * 2] = ouv[l * 2 + 1] = 0.0f; }
+    int cnt = 0;
+    for (int k = 0; k < n && cnt < n_max; ++k) {
+        // Moeller-Trumbore, intersect_gpu.cu:272-303
+        const F3 v0 = {fp[k * 9], fp[k * 9 + 1], fp[k * 9 + 2]};
+        const F3 v0v1 = sub3({fp[k * 9 + 3], fp[k * 9 + 4], fp[k * 9 + 5]}, v0);
+        const F3 v0v2 = sub3({fp[k * 9 + 6], fp[k * 9 + 7], fp[k * 9 + 8]}, v0);
+        const F3 v0O = sub3(ori, v0);
+        const F3 dxe = cross3(dir, v0v2);
+        const float det = __fdividef(1.0f, dot3(v0v1, dxe));
+        float u = dot3(v0O, dxe) * det;
+        if (u < 0.0f - blur || u > 1.0f + blur) continue;
+        const F3 oxe = cross3(v0O, v0v1);
+        float v = dot3(dir, oxe) * det;
+        if (v < 0.0f - blur || v > 1.0f + blur) continue;
+        if ((u + v) < 0.0f - blur || (u + v) > 1.0f + blur) continue;
+        float d = dot3(v0v2, oxe) * det;
+        if (!(d > 0)) continue;
+        int ki = k;
+        for (int l = 0; l < cnt; ++l)  // insertion by depth, intersect_gpu.cu:356-365
+            if (d < od[l * 3]) {
+                int ti = oi[l]; oi[l] = ki; ki = ti;
+                float t = od[l * 3]; od[l * 3] = d; d = t;
+                t = ouv[l * 2]; ouv[l * 2] = u; u = t;
+                t = ouv[l * 2 + 1]; ouv[l * 2 + 1] = v; v = t;
+            }
+        oi[cnt] = ki; od[cnt * 3] = d; ouv[cnt * 2] = u; ouv[cnt * 2 + 1] = v; ++cnt;
+    }
+    for (int l = 0; l < cnt; ++l) {  // :373-386
+        od[l * 3 + 1] = (l == 0) ? -cagesize : -fminf(cagesize, 0.5f * (od[l * 3] - od[l * 3 - 3]));
+        od[l * 3 + 2] = (l == cnt - 1) ? cagesize : fminf(cagesize, 0.5f * (od[l * 3 + 3] - od[l * 3]));
+    }
+}
+
+__global__ void k_debug_rcp(const float *__restrict__ in, float *__restrict__ out, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __fdividef(1.0f, in[i]);
+}
+
+}  // namespace pslam
+
+using namespace pslam;
+
+static int check_grouped(int b, int n, int m, int n_max, const void *a, const void *c, const void *d, const void *e)
+{
+    PSLAM_CHECK_ARG(b > 0 && n > 0 && m > 0 && n_max > 0, PSLAM_E_ARG, "sizes must be positive (b=%d n=%d m=%d n_max=%d)", b, n, m, n_max);
+    PSLAM_CHECK_ARG(a && c && d && e, PSLAM_E_ARG, "null pointer argument");
+    PSLAM_CHECK_ARG((int64_t)b * m * n_max < (int64_t)1 << 40, PSLAM_E_RANGE, "batch too large");
+    return 0;
+}
+
+extern "C" int pslam_svo_intersect(int b, int n, int m, float voxelsize, int n_max, const float *ray_start,
+                                   const float *ray_dir, const float *points, const int *children, int *idx,
+                                   float *min_depth, float *max_depth, pslam_stream_t stream)
+{
+    if (int rc = check_grouped(b, n, m, n_max, ray_start, ray_dir, points, children)) return rc;
+    PSLAM_CHECK_ARG(idx && min_depth && max_depth, PSLAM_E_ARG, "null output pointer");
+    const int64_t rays = (int64_t)b * m;
+    const int blocks = (int)ceil_div64(rays, kIntersectThreads);
+    const size_t smem = sizeof(int) * kSmemStack * kIntersectThreads;
+    k_svo_intersect_ref<<<blocks, kIntersectThreads, smem, (cudaStream_t)stream>>>(
+        b, n, m, (float)(voxelsize * 0.5), n_max, ray_start, ray_dir, points, children, idx, min_depth, max_depth);
+    PSLAM_CHECK_LAUNCH("svo_intersect");
+    return 0;
+}
+
+extern "C" int pslam_aabb_intersect(int b, int n, int m, float voxelsize, int n_max, const float *ray_start,
+                                    const float *ray_dir, const float *points, int *idx, float *min_depth,
+                                    float *max_depth, pslam_stream_t stream)
+{
+    if (int rc = check_grouped(b, n, m, n_max, ray_start, ray_dir, points, idx)) return rc;
+    PSLAM_CHECK_ARG(min_depth && max_depth, PSLAM_E_ARG, "null output pointer");
+    const int blocks = (int)ceil_div64((int64_t)b * m, 128);
+    k_aabb_intersect_ref<<<blocks, 128, 0, (cudaStream_t)stream>>>(b, n, m, (float)(voxelsize * 0.5), n_max, ray_start,
+                                                                   ray_dir, points, idx, min_depth, max_depth);
+    PSLAM_CHECK_LAUNCH("aabb_intersect");
+    return 0;
+}
+
+extern "C" int pslam_ball_intersect(int b, int n, int m, float radius, int n_max, const float *ray_start,
+                                    const float *ray_dir, const float *points, int *idx, float *min_depth,
+                                    float *max_depth, pslam_stream_t stream)
+{
+    if (int rc = check_grouped(b, n, m, n_max, ray_start, ray_dir, points, idx)) return rc;
+    PSLAM_CHECK_ARG(min_depth && max_depth, PSLAM_E_ARG, "null output pointer");
+    const int blocks = (int)ceil_div64((int64_t)b * m, 128);
+    k_ball_intersect_ref<<<blocks, 128, 0, (cudaStream_t)stream>>>(b, n, m, radius, n_max, ray_start, ray_dir, points, idx,
+                                                                   min_depth, max_depth);
+    PSLAM_CHECK_LAUNCH("ball_intersect");
+    return 0;
+}
+
+extern "C" int pslam_triangle_intersect(int b, int n, int m, float cagesize, float blur, int n_max,
+                                        const float *ray_start, const float *ray_dir, const float *face_points,
+                                        int *idx, float *depth, float *uv, pslam_stream_t stream)
+{
+    if (int rc = check_grouped(b, n, m, n_max, ray_start, ray_dir, face_points, idx)) return rc;
+    PSLAM_CHECK_ARG(depth && uv, PSLAM_E_ARG, "null output pointer");
+    const int blocks = (int)ceil_div64((int64_t)b * m, 128);
+    k_triangle_intersect_ref<<<blocks, 128, 0, (cudaStream_t)stream>>>(b, n, m, cagesize, blur, n_max, ray_start, ray_dir,
+                                                                       face_points, idx, depth, uv);
+    PSLAM_CHECK_LAUNCH("triangle_intersect");
+    return 0;
+}
+
+extern "C" int pslam_debug_rcp(const float *in, float *out, int n, pslam_stream_t stream)
+{
+    PSLAM_CHECK_ARG(in && out && n > 0, PSLAM_E_ARG, "bad argument");
+    k_debug_rcp<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, n);
+    PSLAM_CHECK_LAUNCH("debug_rcp");
+    return 0;
+}
+
+// Stage-1a of the fused pipeline.
+namespace pslam {
+int scan_partials(int *partials, int nb, int *total_out, cudaStream_t st)
+{
+    k_scan_partials<<<1, 1024, 0, st>>>(partials, nb, total_out);
+    PSLAM_CHECK_LAUNCH("scan_partials");
+    return 0;
+}
+
+int launch_intersect_fused(const pslam_render_t *p, cudaStream_t st)
+{
+    const int nb = ceil_div(p->R, kIntersectThreads);
+    int *block_hits = p->scratch_i;  // [nb]
+    const size_t smem = sizeof(int) * kSmemStack * kIntersectThreads;
+    k_intersect_fused<<<nb, kIntersectThreads, smem, st>>>(p->R, (float)(p->voxel_size * 0.5), p->n_max, p->max_distance,
+                                                          p->rays_o, p->rays_d, p->centres, p->structure, p->hit_idx,
+                                                          p->hit_min, p->hit_max, p->hit_count, block_hits, p->counters);
+    PSLAM_CHECK_LAUNCH("intersect_fused");
+    if (int rc = scan_partials(block_hits, nb, p->counters + PSLAM_C_RH, st)) return rc;
+    k_compact_rays<<<nb, kIntersectThreads, 0, st>>>(p->R, p->hit_count, block_hits, p->hit_ray, p->ray_rank);
+    PSLAM_CHECK_LAUNCH("compact_rays");
+    return 0;
+}
+}  // namespace pslam

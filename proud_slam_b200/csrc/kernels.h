@@ -1,0 +1,21 @@
+// Internal launch entry points shared between the .cu files of libproud_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/proud_slam_b200.h"
+
+namespace pslam {
+
+// intersect.cu
+int scan_partials(int *partials, int nb, int *total_out, cudaStream_t st);
+int launch_intersect_fused(const pslam_render_t *p, cudaStream_t st);
+// sample.cu
+int launch_sample_fused(const pslam_render_t *p, cudaStream_t st);
+// field.cu (trilinear lookup + decoder MLP)
+int launch_field_forward(const pslam_render_t *p, cudaStream_t st);
+int launch_field_backward(const pslam_render_t *p, cudaStream_t st);
+// composite.cu (SDF->weights compositing + loss)
+int launch_composite_forward(const pslam_render_t *p, cudaStream_t st);
+int launch_composite_backward(const pslam_render_t *p, cudaStream_t st);
+
+}  // namespace pslam

@@ -1,0 +1,365 @@
+// Kernel 2: stratified inverse-CDF sampling inside the hit voxels.
+//
+// Semantics follow third_party/sparse_voxels/src/sample_gpu.cu:133-239 exactly,
+// including the tail loop's indexing quirk: whether a
+// ray gets its closing samples depends on its position j inside its group
+// ("num_rays > j*P + curr_bin"), the break test reads the hit table of the
+// group's FIRST ray, and after the main loop ran out of bins one more sample is
+// emitted whose voxel id is read one slot past the ray's hits (-1, or the next
+// ray's first voxel when the ray filled all P slots).  Arithmetic is pinned
+// with _rn intrinsics: IEEE division, and the one FMA nvcc contracts in the
+// reference (z = min + u*(max-min), SURVEY A-Q8).
+//
+// One `sample_ray` routine serves both layouts through two small policies:
+//   * HitView  -- how hit (ray-in-group j', bin) is read (reference [b,n,P]
+//                 tensors, or the fused pipeline's slot-major tables addressed
+//                 through the rank -> ray map, emulating the reference's
+//                 G=200 grouping and 800-ray chunks without materialising them)
+//   * Sink     -- where samples go (padded [.., max_steps] rows, a CSR segment,
+//                 or nowhere for the counting pass)
+#include "common.cuh"
+#include "kernels.h"
+
+namespace pslam {
+
+constexpr int kSampleThreads = 128;
+constexpr int kGroups = 200;      // voxel_helpers.py:300
+constexpr int kChunkRays = 800;   // voxel_helpers.py:331 (4*G)
+
+// The sampling loop for ray j of a group with `num_rays` rays and P hit slots.
+template <class HitView, class Noise, class Sink>
+__device__ __forceinline__ int sample_ray(const HitView &hv, const Noise &noise, Sink &sink, int j, int num_rays, int P,
+                                          float prob0, float steps, float fixed_step_size)
+{
+    int bin = 0, s = 0;
+    float lo_d = hv.tmin(j, 0), hi_d = hv.tmax(j, 0);
+    float lo_c = 0.0f, hi_c = prob0;
+    float step_size = __fdiv_rn(1.0f, steps);  // (float)(1.0/steps): double rounding is innocuous here
+    float z_low = lo_d;
+    const int total_steps = (int)ceilf(steps);
+    bool done = false;
+    if (fixed_step_size > 0.0f) step_size = fixed_step_size;
+
+    for (int step = 0; step < total_steps; ++step) {
+        const float cdf = __fmul_rn(__fadd_rn((float)step, noise(step)), step_size);
+        while (cdf > hi_c) {
+            sink(s, hv.idx(j, bin), __fsub_rn(hi_d, z_low), __fmul_rn(__fadd_rn(hi_d, z_low), 0.5f));
+            ++bin; ++s;
+            if (bin >= P || hv.idx(j, bin) == -1) { done = true; break; }
+            lo_d = hv.tmin(j, bin); hi_d = hv.tmax(j, bin);
+            lo_c = hi_c; hi_c = __fadd_rn(hi_c, hv.prob(j, bin));
+            z_low = lo_d;
+        }
+        if (done) break;
+        const float u = __fdiv_rn(__fsub_rn(cdf, lo_c), __fsub_rn(hi_c, lo_c));
+        const float z = __fmaf_rn(u, __fsub_rn(hi_d, lo_d), lo_d);
+        sink(s, hv.idx(j, bin), __fsub_rn(z, z_low), __fmul_rn(__fadd_rn(z, z_low), 0.5f));
+        z_low = z; ++s;
+    }
+    // tail, sample_gpu.cu:224-237 (`~done` is always true)
+    while (z_low < hi_d && num_rays > j * P + bin) {
+        sink(s, hv.flat_idx(j * P + bin), __fsub_rn(hi_d, z_low), __fmul_rn(__fadd_rn(hi_d, z_low), 0.5f));
+        ++bin; ++s;
+        if (bin >= P || hv.flat_idx(bin) == -1) break;
+        lo_d = hv.tmin(j, bin); hi_d = hv.tmax(j, bin);
+        z_low = lo_d;
+    }
+    return s;
+}
+
+// ---- reference layout ---------------------------------------------------------------------
+struct RefHits {
+    const int *idx_; const float *min_, *max_, *prob_;  // group base pointers
+    int P;
+    __device__ __forceinline__ int idx(int j, int b) const { return __ldg(idx_ + j * P + b); }
+    __device__ __forceinline__ int flat_idx(int f) const { return __ldg(idx_ + f); }
+    __device__ __forceinline__ float tmin(int j, int b) const { return __ldg(min_ + j * P + b); }
+    __device__ __forceinline__ float tmax(int j, int b) const { return __ldg(max_ + j * P + b); }
+    __device__ __forceinline__ float prob(int j, int b) const { return __ldg(prob_ + j * P + b); }
+};
+struct RefNoise {
+    const float *row; int max_steps;
+    __device__ __forceinline__ float operator()(int step) const { return step < max_steps ? __ldg(row + step) : 0.5f; }
+};
+struct PaddedSink {
+    int *idx; float *depth, *dist; int max_steps;
+    __device__ __forceinline__ void operator()(int s, int vox, float d, float z)
+    {
+        if (s < max_steps) { idx[s] = vox; dist[s] = d; depth[s] = z; }
+    }
+};
+
+__global__ void __launch_bounds__(kSampleThreads)
+k_inverse_cdf_ref(int b, int num_rays, int P, int max_steps, float fixed_step_size, const int *__restrict__ pts_idx,
+                  const float *__restrict__ min_depth, const float *__restrict__ max_depth,
+                  const float *__restrict__ noise, const float *__restrict__ probs, const float *__restrict__ steps,
+                  int *__restrict__ sampled_idx, float *__restrict__ sampled_depth, float *__restrict__ sampled_dists)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= (int64_t)b * num_rays) return;
+    const int g = (int)(r / num_rays), j = (int)(r % num_rays);
+    const int64_t hb = (int64_t)g * num_rays * P;
+    RefHits hv{pts_idx + hb, min_depth + hb, max_depth + hb, probs + hb, P};
+    RefNoise nz{noise + r * max_steps, max_steps};
+    PaddedSink sink{sampled_idx + r * max_steps, sampled_depth + r * max_steps, sampled_dists + r * max_steps, max_steps};
+    int s = sample_ray(hv, nz, sink, j, num_rays, P, hv.prob(j, 0), __ldg(steps + r), fixed_step_size);
+    s = min(s, max_steps);
+    for (int k = s; k < max_steps; ++k) { sink.idx[k] = -1; sink.depth[k] = 0.0f; sink.dist[k] = 0.0f; }  // sample.cpp:80-89
+}
+
+// ---- fused layout ---------------------------------------------------------------------------
+// Ray of rank q lives in group g = q / n, position jf = q % n (n = ceil(R_h/200)),
+// chunk c = jf / 800, j = jf % 800 inside a chunk of nc = min(800, n - 800c) rays
+// (voxel_helpers.py:300-343).  Ranks >= R_h are padding = copies of rank 0 (:302-311).
+struct FusedHits {
+    const int *hit_idx; const float *hit_min, *hit_max; const int *hit_count, *hit_ray;
+    int R, Rh, P, chunk_base_rank;  // rank of (g, 800c + 0)
+    float total;                    // sum of this ray's segment lengths
+    float max_distance;             // value the reference reads in padded slots (voxel_helpers.py:579-580)
+    __device__ __forceinline__ int ray_of(int j) const
+    {
+        int q = chunk_base_rank + j;
+        if (q >= Rh) q = 0;
+        return __ldg(hit_ray + q);
+    }
+    __device__ __forceinline__ int idx_r(int r, int b) const
+    {
+        return (b < __ldg(hit_count + r)) ? __ldg(hit_idx + (int64_t)b * R + r) : -1;
+    }
+    __device__ __forceinline__ int idx(int j, int b) const { return idx_r(ray_of(j), b); }
+    __device__ __forceinline__ int flat_idx(int f) const { return idx_r(ray_of(f / P), f % P); }
+    __device__ __forceinline__ float tmin(int j, int b) const
+    {
+        const int r = ray_of(j);
+        return (b < __ldg(hit_count + r)) ? __ldg(hit_min + (int64_t)b * R + r) : max_distance;
+    }
+    __device__ __forceinline__ float tmax(int j, int b) const
+    {
+        const int r = ray_of(j);
+        return (b < __ldg(hit_count + r)) ? __ldg(hit_max + (int64_t)b * R + r) : max_distance;
+    }
+    __device__ __forceinline__ float prob(int j, int b) const
+    {
+        return __fdiv_rn(__fsub_rn(tmax(j, b), tmin(j, b)), total);  // voxel_helpers.py:639-643
+    }
+};
+
+// Counter-based uniform noise for production runs (no noise tensor in HBM):
+// a 2-round multiply-xorshift hash of (seed, rank, step) -> (0.001, 0.999) like
+// voxel_helpers.py:328's clamp.  Parity tests pass an explicit tensor instead.
+struct HashNoise {
+    uint64_t key;
+    __device__ __forceinline__ float operator()(int step) const
+    {
+        uint64_t x = key + (uint64_t)step * 0x9E3779B97F4A7C15ull;
+        x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+        x ^= x >> 27; x *= 0x94D049BB133111EBull;
+        x ^= x >> 31;
+        const float u = (float)(x >> 40) * (1.0f / 16777216.0f);
+        return fminf(fmaxf(u, 0.001f), 0.999f);
+    }
+};
+struct TensorNoise {
+    const float *row; int stride;
+    __device__ __forceinline__ float operator()(int step) const { return step < stride ? __ldg(row + step) : 0.5f; }
+};
+struct CountSink {
+    int last;
+    __device__ __forceinline__ void operator()(int, int v, float, float) { last = v; }
+};
+struct CsrSink {
+    int *vox; float *z, *dist; int *ray; int rank; int room;
+    __device__ __forceinline__ void operator()(int s, int v, float d, float zz)
+    {
+        // a trailing -1 id (A-Q7/A-Q9) is not a sample; it can only be the last emission
+        if (v != -1 && s < room) { vox[s] = v; z[s] = zz; dist[s] = fmaxf(d, 0.0f); ray[s] = rank; }
+    }
+};
+
+template <bool WRITE>
+__global__ void __launch_bounds__(kSampleThreads)
+k_sample_fused(pslam_render_t p, int *__restrict__ block_counts)
+{
+    const int Rh = p.counters[PSLAM_C_RH];
+    const int P = p.counters[PSLAM_C_P];
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    int nsamp = 0;
+    if (q < Rh) {
+        const int n = (Rh + kGroups - 1) / kGroups;
+        const int g = q / n, jf = q % n;
+        const int c = jf / kChunkRays, j = jf % kChunkRays;
+        const int nc = min(kChunkRays, n - c * kChunkRays);
+        const int r = __ldg(p.hit_ray + q);
+        const int cnt = __ldg(p.hit_count + r);
+        // a5: dists, their sum (left-to-right fp32), probs and steps (voxel_helpers.py:639-644)
+        float total = 0.0f;
+        for (int b = 0; b < cnt; ++b)
+            total = __fadd_rn(total, __fsub_rn(__ldg(p.hit_max + (int64_t)b * p.R + r), __ldg(p.hit_min + (int64_t)b * p.R + r)));
+        const float steps = __fdiv_rn(total, p.step_size);
+        FusedHits hv;
+        hv.hit_idx = p.hit_idx; hv.hit_min = p.hit_min; hv.hit_max = p.hit_max;
+        hv.hit_count = p.hit_count; hv.hit_ray = p.hit_ray;
+        hv.R = p.R; hv.Rh = Rh; hv.P = P; hv.chunk_base_rank = g * n + c * kChunkRays;
+        hv.total = total; hv.max_distance = p.max_distance;
+        const float prob0 = hv.prob(j, 0);
+        int room = 0, off = 0;
+        if (WRITE) {
+            off = min(p.samp_off[q], p.sample_cap);
+            room = max(0, min(p.samp_off[q + 1], p.sample_cap) - off);
+        }
+        CsrSink csr{p.samp_vox + off, p.samp_z + off, p.samp_dist + off, p.samp_ray + off, q, room};
+        CountSink cs{0};
+        int s;
+        if (p.noise) {
+            TensorNoise nz{p.noise + (int64_t)q * p.noise_stride, p.noise_stride};
+            s = WRITE ? sample_ray(hv, nz, csr, j, nc, P, prob0, steps, -1.0f)
+                      : sample_ray(hv, nz, cs, j, nc, P, prob0, steps, -1.0f);
+        } else {
+            HashNoise nz{p.seed ^ ((uint64_t)(uint32_t)q * 0xD1B54A32D192ED03ull)};
+            s = WRITE ? sample_ray(hv, nz, csr, j, nc, P, prob0, steps, -1.0f)
+                      : sample_ray(hv, nz, cs, j, nc, P, prob0, steps, -1.0f);
+        }
+        if (!WRITE) {
+            // a trailing -1 id (A-Q7) is not a sample and can only be the last emission
+            nsamp = (s > 0 && cs.last == -1) ? s - 1 : s;
+            p.samp_off[q] = nsamp;  // counts now; turned into offsets by k_sample_offsets
+        }
+    }
+    if (!WRITE) {
+        __shared__ int s_sum[kSampleThreads / 32];
+        const int wsum = warp_sum_i(nsamp), wmax = warp_max_i(nsamp);
+        if ((threadIdx.x & 31) == 0) {
+            s_sum[threadIdx.x >> 5] = wsum;
+            if (wmax > 0) atomicMax(p.counters + PSLAM_C_S, wmax);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < kSampleThreads / 32; ++w) t += s_sum[w];
+            block_counts[blockIdx.x] = t;
+        }
+    }
+}
+
+// counts -> exclusive offsets (block-local scan + scanned block bases); also writes off[R_h].
+__global__ void __launch_bounds__(kSampleThreads)
+k_sample_offsets(pslam_render_t p, const int *__restrict__ block_base)
+{
+    __shared__ int s_warp[kSampleThreads / 32];
+    const int Rh = p.counters[PSLAM_C_RH];
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = (q < Rh) ? p.samp_off[q] : 0;
+    int x = v;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    int base = block_base[blockIdx.x];
+    for (int w = 0; w < warp; ++w) base += s_warp[w];
+    if (q < Rh) p.samp_off[q] = base + x - v;
+    if (q == Rh - 1) {
+        const int total = base + x;
+        p.samp_off[Rh] = total;
+        p.counters[PSLAM_C_NSAMP] = min(total, p.sample_cap);
+        if (total > p.sample_cap) atomicOr(p.counters + PSLAM_C_OVERFLOW, 1);
+    }
+}
+
+int launch_sample_fused(const pslam_render_t *p, cudaStream_t st)
+{
+    const int nb = ceil_div(p->R, kSampleThreads);
+    int *block_counts = p->scratch_i + ceil_div(p->R, 128) + 8;  // after intersect's block_hits
+    k_sample_fused<false><<<nb, kSampleThreads, 0, st>>>(*p, block_counts);
+    PSLAM_CHECK_LAUNCH("sample_count");
+    if (int rc = scan_partials(block_counts, nb, p->counters + PSLAM_C_TILE2, st)) return rc;
+    k_sample_offsets<<<nb, kSampleThreads, 0, st>>>(*p, block_counts);
+    PSLAM_CHECK_LAUNCH("sample_offsets");
+    k_sample_fused<true><<<nb, kSampleThreads, 0, st>>>(*p, nullptr);
+    PSLAM_CHECK_LAUNCH("sample_write");
+    return 0;
+}
+
+// ---- uniform_ray_sampling (API surface), sample_gpu.cu:13-131 ---------------------------------
+__global__ void k_uniform_sampling_ref(int b, int num_rays, int max_hits, int max_steps, float step_size,
+                                       const int *__restrict__ pts_idx, const float *__restrict__ min_depth,
+                                       const float *__restrict__ max_depth, const float *__restrict__ noise,
+                                       int *__restrict__ sampled_idx, float *__restrict__ sampled_depth,
+                                       float *__restrict__ sampled_dists)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= (int64_t)b * num_rays) return;
+    const int *pi = pts_idx + r * max_hits;
+    const float *mn = min_depth + r * max_hits, *mx = max_depth + r * max_hits, *nz = noise + r * max_steps;
+    int *oi = sampled_idx + r * max_steps;
+    float *od = sampled_depth + r * max_steps, *os = sampled_dists + r * max_steps;
+    for (int k = 0; k < max_steps; ++k) { oi[k] = -1; od[k] = 0.0f; os[k] = 0.0f; }
+    int s = 0, ucur = 0, umin = 0, umax = 0;
+    float last_min = 0.f, last_max = 0.f, curr = 0.f;
+    // merge segment boundaries with the marching samples, :45-95
+    while (true) {
+        if (umax == max_hits || ucur == max_steps || pi[umax] == -1) break;
+        last_min = (umin < max_hits) ? mn[umin] : 10000.0f;
+        last_max = (umax < max_hits) ? mx[umax] : 10000.0f;
+        if (ucur < max_steps) curr = mn[0] + ((float)ucur + nz[ucur]) * step_size;
+        if (s >= max_steps) break;  // the reference would write out of bounds here
+        if (last_max <= curr && last_max <= last_min) { od[s] = last_max; oi[s] = pi[umax]; ++umax; ++s; continue; }
+        if (curr <= last_min && curr <= last_max) { od[s] = curr; oi[s] = (umin > 0) ? pi[umin - 1] : -1; ++ucur; ++s; continue; }
+        if (last_min <= curr && last_min <= last_max) { od[s] = last_min; oi[s] = pi[umin]; ++umin; ++s; continue; }
+        break;  // NaN input: none of the three orderings holds (the reference would spin)
+    }
+    int step = 0;
+    umin = 0; umax = 0;
+    for (ucur = 0; ucur < max_steps - 1; ++ucur) {  // :97-123
+        if (oi[ucur + 1] == -1) break;
+        const float l = od[ucur], rr = od[ucur + 1];
+        od[ucur] = (l + rr) * 0.5f;
+        os[ucur] = rr - l;
+        if (umin < max_hits && od[ucur] >= mn[umin] && pi[umin] > -1) ++umin;
+        if (umax < max_hits && od[ucur] >= mx[umax] && pi[umax] > -1) ++umax;
+        if (umax == max_hits || pi[umax] == -1) break;
+        if (umin - 1 == umax && os[ucur] > 0) { od[step] = od[ucur]; os[step] = os[ucur]; oi[step] = oi[ucur]; ++step; }
+    }
+    for (int k = step; k < max_steps; ++k) oi[k] = -1;
+}
+
+}  // namespace pslam
+
+using namespace pslam;
+
+extern "C" int pslam_inverse_cdf_sampling(int b, int num_rays, int max_hits, int max_steps, float fixed_step_size,
+                                          const int *pts_idx, const float *min_depth, const float *max_depth,
+                                          const float *uniform_noise, const float *probs, const float *steps,
+                                          int *sampled_idx, float *sampled_depth, float *sampled_dists,
+                                          pslam_stream_t stream)
+{
+    PSLAM_CHECK_ARG(b > 0 && num_rays > 0 && max_hits > 0 && max_steps > 0, PSLAM_E_ARG,
+                    "sizes must be positive (b=%d num_rays=%d max_hits=%d max_steps=%d)", b, num_rays, max_hits, max_steps);
+    PSLAM_CHECK_ARG(pts_idx && min_depth && max_depth && uniform_noise && probs && steps, PSLAM_E_ARG, "null input pointer");
+    PSLAM_CHECK_ARG(sampled_idx && sampled_depth && sampled_dists, PSLAM_E_ARG, "null output pointer");
+    const int blocks = (int)ceil_div64((int64_t)b * num_rays, kSampleThreads);
+    k_inverse_cdf_ref<<<blocks, kSampleThreads, 0, (cudaStream_t)stream>>>(
+        b, num_rays, max_hits, max_steps, fixed_step_size, pts_idx, min_depth, max_depth, uniform_noise, probs, steps,
+        sampled_idx, sampled_depth, sampled_dists);
+    PSLAM_CHECK_LAUNCH("inverse_cdf_sampling");
+    return 0;
+}
+
+extern "C" int pslam_uniform_ray_sampling(int b, int num_rays, int max_hits, int max_steps, float step_size,
+                                          const int *pts_idx, const float *min_depth, const float *max_depth,
+                                          const float *uniform_noise, int *sampled_idx, float *sampled_depth,
+                                          float *sampled_dists, pslam_stream_t stream)
+{
+    PSLAM_CHECK_ARG(b > 0 && num_rays > 0 && max_hits > 0 && max_steps > 0, PSLAM_E_ARG, "sizes must be positive");
+    PSLAM_CHECK_ARG(pts_idx && min_depth && max_depth && uniform_noise && sampled_idx && sampled_depth && sampled_dists,
+                    PSLAM_E_ARG, "null pointer argument");
+    const int blocks = (int)ceil_div64((int64_t)b * num_rays, 128);
+    k_uniform_sampling_ref<<<blocks, 128, 0, (cudaStream_t)stream>>>(b, num_rays, max_hits, max_steps, step_size, pts_idx,
+                                                                     min_depth, max_depth, uniform_noise, sampled_idx,
+                                                                     sampled_depth, sampled_dists);
+    PSLAM_CHECK_LAUNCH("uniform_ray_sampling");
+    return 0;
+}
