@@ -140,13 +140,18 @@ int pslam_trilinear_bwd(int p, const float *xyz, const int *vox_idx,
                         float voxel_size, const float *g_feat,
                         float *g_emb, float *g_xyz, pslam_stream_t stream);
 
-/* Decoder.get_values, nrgbd.py:116-135: feat [p,16] -> out [p,4] = (r,g,b,sdf). */
+/* Floats of workspace the decoder kernels need for `width` (repacked weights;
+ * rewritten by every call, so it may be shared by calls on one stream). */
+int64_t pslam_decoder_ws_count(int width);
+
+/* Decoder.get_values, nrgbd.py:116-135: feat [p,16] -> out [p,4] = (r,g,b,sdf).
+ * ws: pslam_decoder_ws_count(width) floats, 16-byte aligned. */
 int pslam_decoder_fwd(int p, const pslam_decoder_t *dec, const float *feat,
-                      float *out, pslam_stream_t stream);
+                      float *ws, float *out, pslam_stream_t stream);
 /* Backward: g_out [p,4] -> g_feat [p,16] (may be NULL) and parameter
  * gradients (grad may be NULL).  Activations are recomputed, not stored. */
 int pslam_decoder_bwd(int p, const pslam_decoder_t *dec, const float *feat,
-                      const float *g_out, float *g_feat,
+                      float *ws, const float *g_out, float *g_feat,
                       const pslam_decoder_grad_t *grad, pslam_stream_t stream);
 
 /* ------------------------------------------------------------------------
@@ -197,6 +202,7 @@ typedef struct {
     const int *vertex_idx;                 /* [N,8] voxel_vertex_idx */
     const float *emb;                      /* [E,16] voxel_vertex_emb */
     pslam_decoder_t dec;
+    float *dec_ws;                         /* [pslam_decoder_ws_count(dec.width)] repacked weights */
     const float *noise;                    /* [>=R_h, noise_stride] uniform(0.001,0.999) or NULL */
     int noise_stride;
     uint64_t seed;                         /* counter-based noise when noise==NULL */
@@ -212,10 +218,11 @@ typedef struct {
     float *samp_z;                         /* [sample_cap] depth (segment mid-point) */
     float *samp_dist;                      /* [sample_cap] segment length */
     float *samp_out;                       /* [sample_cap,4] (r,g,b,sdf) from the decoder */
+    float *samp_w;                         /* [sample_cap] compositing weight per sample (may be NULL) */
     float *samp_gout;                      /* [sample_cap,4] dL/d(r,g,b,sdf) */
     float *ray_out;                        /* [R,8] by rank: r,g,b,depth,z_min,U,|dd|/sqrt(var),gate */
-    int *scratch_i;                        /* [4*ceil(R/128)+64] block partials for the scans */
-    float *scratch_f;                      /* [16*ceil(R/4)+64] block partials for the loss sums... see api.cu */
+    int *scratch_i;                        /* [pslam_render_scratch_i_count(R)] block partials (scans, loss counts) */
+    float *scratch_f;                      /* [pslam_render_scratch_f_count(R)] block partials (loss sums) */
     int *counters;                         /* [PSLAM_C_COUNT] */
     /* outputs */
     float *loss;                           /* [PSLAM_L_COUNT] */
@@ -224,7 +231,11 @@ typedef struct {
     float *g_rays_o, *g_rays_d;            /* [R,3] by ray id, overwritten */
 } pslam_render_t;
 
-/* Bytes the caller must provide for scratch_i / scratch_f for a batch of R rays. */
+/* sizeof(pslam_render_t) and offsetof(.., loss): lets a binding check its mirror of the struct. */
+int pslam_render_sizeof(void);
+int pslam_render_offsetof_loss(void);
+
+/* Elements the caller must provide for scratch_i / scratch_f for a batch of R rays. */
 int64_t pslam_render_scratch_i_count(int R);
 int64_t pslam_render_scratch_f_count(int R);
 
@@ -237,6 +248,22 @@ int pslam_render_forward(const pslam_render_t *p, pslam_stream_t stream);
 int pslam_render_backward(const pslam_render_t *p, pslam_stream_t stream);
 /* All three stages back to back. */
 int pslam_render_step(const pslam_render_t *p, pslam_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Host-side octree: torch.classes.svo.Octree,
+ * third_party/sparse_octree/src/bindings.cpp:11-35 (init / insert /
+ * get_centres_and_children / has_voxel / count_nodes / count_leaf_nodes /
+ * get_leaf_voxels).  Plain host pointers; the producer of `map_states`.
+ * ---------------------------------------------------------------------- */
+void *pslam_octree_new(int grid_dim);                       /* Octree::init, octree.cpp:46-60 */
+void pslam_octree_free(void *tree);
+int pslam_octree_count(void *tree);                         /* count_nodes */
+int pslam_octree_count_leaves(void *tree);                  /* count_leaf_nodes (SURFACE voxels) */
+int pslam_octree_insert(void *tree, const int *vox, int m); /* Octree::insert, octree.cpp:104-294; vox [m,3] */
+int pslam_octree_has_voxel(void *tree, int x, int y, int z);
+/* get_centres_and_children, octree.cpp:561-687: voxels [N,4] f32, children [N,8] f32, features [N,8] i32 */
+int pslam_octree_flatten(void *tree, float *voxels, float *children, int *features);
+int pslam_octree_leaf_voxels(void *tree, int *out_xyz, int cap);
 
 #ifdef __cplusplus
 }

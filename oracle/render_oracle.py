@@ -31,8 +31,8 @@ def ray_intersect_vox(ray_start, ray_dir, centres, children, voxel_size, max_hit
     + :558-595 (sort by entry depth, drop beyond max_distance, trim)."""
     R = ray_start.shape[1]
     idx, tmin, tmax = _c_intersect(
-        ray_start.reshape(1, R, 3).numpy(), ray_dir.reshape(1, R, 3).numpy(),
-        centres.reshape(1, -1, 3).numpy(), children.reshape(1, -1, 9).numpy(),
+        ray_start.detach().reshape(1, R, 3).numpy(), ray_dir.detach().reshape(1, R, 3).numpy(),
+        centres.detach().reshape(1, -1, 3).numpy(), children.reshape(1, -1, 9).numpy(),
         float(voxel_size), N_MAX_HITS,
         None if inv_dir is None else np.asarray(inv_dir).reshape(1, R, 3))
     pts_idx = torch.from_numpy(idx)

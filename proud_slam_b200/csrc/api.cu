@@ -1,0 +1,138 @@
+// libproud_b200.so: error reporting, device queries and the three-stage driver
+// of the fused render path (include/proud_slam_b200.h).
+#include <stdarg.h>
+#include <stddef.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace pslam {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int num_sms()
+{
+    static int cached[64] = {0};  // per device, written idempotently
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+static int check_render(const pslam_render_t *p)
+{
+    PSLAM_CHECK_ARG(p, PSLAM_E_ARG, "null pslam_render_t");
+    PSLAM_CHECK_ARG(p->R > 0 && p->N > 0 && p->E > 0 && p->n_max > 0 && p->sample_cap > 0, PSLAM_E_ARG,
+                    "sizes must be positive (R=%d N=%d E=%d n_max=%d sample_cap=%d)", p->R, p->N, p->E, p->n_max, p->sample_cap);
+    PSLAM_CHECK_ARG(p->R <= (1 << 26), PSLAM_E_RANGE, "R=%d too large", p->R);
+    PSLAM_CHECK_ARG(p->voxel_size > 0.0f && p->step_size > 0.0f && p->truncation > 0.0f, PSLAM_E_ARG, "voxel_size, step_size and truncation must be > 0");
+    PSLAM_CHECK_ARG(p->rays_o && p->rays_d && p->centres && p->structure && p->vertex_idx && p->emb, PSLAM_E_ARG, "null input pointer");
+    PSLAM_CHECK_ARG(p->hit_idx && p->hit_min && p->hit_max && p->hit_count && p->hit_ray && p->ray_rank && p->samp_off && p->samp_vox &&
+                        p->samp_ray && p->samp_z && p->samp_dist && p->scratch_i && p->scratch_f && p->counters,
+                    PSLAM_E_ARG, "null intermediate buffer");
+    PSLAM_CHECK_ARG(p->noise == nullptr || p->noise_stride > 0, PSLAM_E_ARG, "noise_stride must be > 0 with an explicit noise tensor");
+    return 0;
+}
+
+static int check_render_field(const pslam_render_t *p, bool backward)
+{
+    PSLAM_CHECK_ARG(p->dec.width == 128 || p->dec.width == 256, PSLAM_E_RANGE, "decoder width %d not supported (128 or 256)", p->dec.width);
+    PSLAM_CHECK_ARG(p->dec.W1 && p->dec.b1 && p->dec.W2 && p->dec.b2 && p->dec.W3 && p->dec.b3 && p->dec.W4 && p->dec.b4 && p->dec.W5 && p->dec.b5,
+                    PSLAM_E_ARG, "null decoder parameter");
+    PSLAM_CHECK_ARG(p->dec_ws && p->samp_out && p->ray_out && p->loss, PSLAM_E_ARG, "null forward buffer");
+    PSLAM_CHECK_ARG((p->target_rgb == nullptr) == (p->target_depth == nullptr), PSLAM_E_ARG, "target_rgb and target_depth go together");
+    if (backward) PSLAM_CHECK_ARG(p->target_rgb && p->target_depth, PSLAM_E_ARG, "backward needs the Criterion targets");
+    PSLAM_CHECK_ARG(((uintptr_t)p->dec.W1 | (uintptr_t)p->dec.W2 | (uintptr_t)p->dec.W3 | (uintptr_t)p->dec.W4 | (uintptr_t)p->dec_ws |
+                     (uintptr_t)p->samp_out | (uintptr_t)p->emb) % 16 == 0,
+                    PSLAM_E_ALIGN, "decoder weights, dec_ws, samp_out and emb must be 16-byte aligned");
+    if (backward) {
+        PSLAM_CHECK_ARG(p->samp_gout && ((uintptr_t)p->samp_gout % 16 == 0), PSLAM_E_ARG, "samp_gout missing or misaligned");
+        if (p->flags & PSLAM_F_GRAD_EMB) PSLAM_CHECK_ARG(p->g_emb && ((uintptr_t)p->g_emb % 16 == 0), PSLAM_E_ARG, "g_emb missing or misaligned");
+        if (p->flags & PSLAM_F_GRAD_RAYS) PSLAM_CHECK_ARG(p->g_rays_o && p->g_rays_d, PSLAM_E_ARG, "g_rays_o/g_rays_d missing");
+        if (p->flags & PSLAM_F_GRAD_DEC)
+            PSLAM_CHECK_ARG(p->g_dec.W1 && p->g_dec.b1 && p->g_dec.W2 && p->g_dec.b2 && p->g_dec.W3 && p->g_dec.b3 && p->g_dec.W4 &&
+                                p->g_dec.b4 && p->g_dec.W5 && p->g_dec.b5,
+                            PSLAM_E_ARG, "null decoder gradient pointer");
+    }
+    return 0;
+}
+
+}  // namespace pslam
+
+using namespace pslam;
+
+extern "C" int pslam_abi_version(void) { return PSLAM_ABI_VERSION; }
+extern "C" const char *pslam_last_error(void) { return g_error; }
+
+extern "C" int pslam_device_info(int *out3)
+{
+    PSLAM_CHECK_ARG(out3, PSLAM_E_ARG, "null output");
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { set_error("cudaGetDevice: %s", cudaGetErrorString(e)); return (int)e; }
+    int major = 0, minor = 0, smem = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    out3[0] = num_sms(); out3[1] = major * 10 + minor; out3[2] = smem;
+    return 0;
+}
+
+extern "C" int64_t pslam_render_scratch_i_count(int R)
+{
+    return 2 * ((int64_t)ceil_div(R, 128) + 8) + 2 * (int64_t)ceil_div(R, 8) + 64;
+}
+extern "C" int64_t pslam_render_scratch_f_count(int R) { return 4 * (int64_t)ceil_div(R, 8) + 64; }
+
+extern "C" int pslam_render_sample(const pslam_render_t *p, pslam_stream_t stream)
+{
+    if (int rc = check_render(p)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(p->counters, 0, sizeof(int) * PSLAM_C_COUNT, st);
+    if (e != cudaSuccess) { set_error("memset counters: %s", cudaGetErrorString(e)); return (int)e; }
+    if (int rc = launch_intersect_fused(p, st)) return rc;
+    return launch_sample_fused(p, st);
+}
+
+extern "C" int pslam_render_forward(const pslam_render_t *p, pslam_stream_t stream)
+{
+    if (int rc = check_render(p)) return rc;
+    if (int rc = check_render_field(p, false)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = launch_field_forward(p, st)) return rc;
+    return launch_composite_forward(p, st);
+}
+
+extern "C" int pslam_render_backward(const pslam_render_t *p, pslam_stream_t stream)
+{
+    if (int rc = check_render(p)) return rc;
+    if (int rc = check_render_field(p, true)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = launch_composite_backward(p, st)) return rc;
+    return launch_field_backward(p, st);
+}
+
+extern "C" int pslam_render_step(const pslam_render_t *p, pslam_stream_t stream)
+{
+    if (int rc = pslam_render_sample(p, stream)) return rc;
+    if (int rc = pslam_render_forward(p, stream)) return rc;
+    if (p->flags & PSLAM_F_FORWARD_ONLY) return 0;
+    return pslam_render_backward(p, stream);
+}
+
+/* sizeof / field offsets so that language bindings can verify their struct mirrors */
+extern "C" int pslam_render_sizeof(void) { return (int)sizeof(pslam_render_t); }
+extern "C" int pslam_render_offsetof_loss(void) { return (int)offsetof(pslam_render_t, loss); }

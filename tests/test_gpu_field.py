@@ -1,0 +1,89 @@
+"""Kernels 3 and 4 in isolation through the C ABI: trilinear lookup and the decoder MLP,
+forward and backward, against the oracle's torch restatement (fp32, 1e-4 relative)."""
+import pytest
+import torch
+
+from oracle import render_oracle as ro
+from proud_slam_b200 import _lib
+from tests import util
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _dec_struct(params):
+    from proud_slam_b200.pipeline import _decoder_struct
+    return _decoder_struct(params)
+
+
+@pytest.mark.parametrize("width,n", [(128, 1), (128, 64), (128, 1000), (256, 333), (128, 20000)])
+def test_decoder_forward_backward(width, n, device):
+    from proud_slam_b200.pipeline import DecoderGradT, _decoder_struct
+    import ctypes as C
+    lib = _lib.lib()
+    dec = ro.decoder_params(width=width, seed=2)
+    g = torch.Generator().manual_seed(n)
+    feat = (torch.randn(n, 16, generator=g) * 0.05).requires_grad_(True)
+    rgb, sdf = ro.decoder_forward(dec, feat)
+    g_out = torch.randn(n, 4, generator=g)
+    (torch.cat([rgb, sdf[:, None]], 1) * g_out).sum().backward()
+
+    decd = [p.detach().to(device) for p in dec]
+    featd = feat.detach().to(device)
+    ws = torch.empty(int(lib.pslam_decoder_ws_count(width)), device=device)
+    out = torch.empty(n, 4, device=device)
+    ds = _decoder_struct(decd)
+    _lib.check(lib.pslam_decoder_fwd(n, C.byref(ds), _lib.ptr(featd), _lib.ptr(ws), _lib.ptr(out), _lib.stream_ptr(device)), "fwd")
+    assert rel_err(out[:, :3], rgb.detach()) < TOL
+    assert rel_err(out[:, 3], sdf.detach()) < TOL
+
+    gd = [torch.zeros_like(p) for p in decd]
+    gs = _decoder_struct(gd, DecoderGradT)
+    g_feat = torch.empty(n, 16, device=device)
+    g_outd = g_out.to(device)
+    _lib.check(lib.pslam_decoder_bwd(n, C.byref(ds), _lib.ptr(featd), _lib.ptr(ws), _lib.ptr(g_outd), _lib.ptr(g_feat),
+                                     C.byref(gs), _lib.stream_ptr(device)), "bwd")
+    torch.cuda.synchronize()
+    assert rel_err(g_feat, feat.grad) < TOL
+    for i in range(10):
+        assert rel_err(gd[i], dec[i].grad) < TOL, f"param {i}"
+
+
+def test_decoder_rejects_bad_width(device):
+    import ctypes as C
+    from proud_slam_b200.pipeline import DecoderT
+    ds = DecoderT()
+    ds.width = 64
+    rc = _lib.lib().pslam_decoder_fwd(4, C.byref(ds), None, None, None, None)
+    assert rc < 0
+    assert b"width" in _lib.lib().pslam_last_error()
+
+
+@pytest.mark.parametrize("n", [1, 777, 50000])
+def test_trilinear_forward_backward(n, device):
+    lib = _lib.lib()
+    s, ms = util.build_scene("tiny", emb_scale=0.5)
+    leaf = torch.nonzero((ms["voxel_vertex_idx"] >= 0).all(-1)).view(-1)
+    g = torch.Generator().manual_seed(n)
+    vox = leaf[torch.randint(0, leaf.numel(), (n,), generator=g)]
+    xyz = (ms["voxel_center_xyz"].detach()[vox] + (torch.rand(n, 3, generator=g) - 0.5) * s.voxel_size).requires_grad_(True)
+    f = ro.get_features_vox(xyz, vox, ms, s.voxel_size)
+    g_f = torch.randn(n, 16, generator=g)
+    (f * g_f).sum().backward()
+
+    d = lambda t: t.detach().to(device).contiguous()
+    feat = torch.empty(n, 16, device=device)
+    args = (n, _lib.ptr(d(xyz)), _lib.ptr(d(vox.int())), _lib.ptr(d(ms["voxel_center_xyz"])), _lib.ptr(d(ms["voxel_vertex_idx"])),
+            _lib.ptr(d(ms["voxel_vertex_emb"])), float(s.voxel_size))
+    keep = [d(xyz), d(vox.int()), d(ms["voxel_center_xyz"]), d(ms["voxel_vertex_idx"]), d(ms["voxel_vertex_emb"])]
+    args = (n,) + tuple(_lib.ptr(t) for t in keep) + (float(s.voxel_size),)
+    _lib.check(lib.pslam_trilinear_fwd(*args, _lib.ptr(feat), _lib.stream_ptr(device)), "tri fwd")
+    assert rel_err(feat, f.detach()) < TOL
+    g_emb = torch.zeros_like(keep[4])
+    g_xyz = torch.empty(n, 3, device=device)
+    g_fd = g_f.to(device)
+    _lib.check(lib.pslam_trilinear_bwd(*args, _lib.ptr(g_fd), _lib.ptr(g_emb), _lib.ptr(g_xyz), _lib.stream_ptr(device)), "tri bwd")
+    torch.cuda.synchronize()
+    assert rel_err(g_emb, ms["voxel_vertex_emb"].grad) < TOL
+    assert rel_err(g_xyz, xyz.grad) < TOL
