@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""Benchmark of the mapping render path (BASELINE.json: rays/s per mapping iteration, fwd+bwd).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one mapping iteration of the reference's BA loop on one ray batch
+(render_rays + Criterion + backward, ``src/variations/render_helpers.py:609-676``): gradient
+buffers zeroed, ``pslam_render_step`` (intersection, sampling, trilinear lookup, decoder,
+compositing, loss, full backward), and for N > 1 the cross-rank loss closure + gradient all-reduce.
+
+Workload at N=1: BASELINE.json configs[1] -- synthetic Replica-shaped scene (1200x680 camera,
+0.2 m voxels, ~20k octants), 8 keyframes x 1024 rays = 8192 rays per iteration.  For N > 1 every
+rank renders its own 8192-ray batch of the same replicated map (weak scaling; ray batches and
+keyframes shard, the octree/embeddings/decoder are replicated).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "rays/sec per mapping iter (fwd+bwd)"
+UNIT = "rays/s"
+SCENE = "replica_20k"
+KEYFRAMES = 8
+RAYS_PER_FRAME = 1024
+CRIT_W = (0.5, 1.0, 10.0, 5000.0)      # rgb, depth, fs, sdf (configs/replica/replica.yaml:6-11)
+WIDTH = 128
+
+
+def macs_per_sample(w):
+    return 16 * w + w * w + w * 129 + 144 * w + w * 3      # nrgbd.py:106-113
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def build_workload(rank, rays_per_frame=RAYS_PER_FRAME, keyframes=KEYFRAMES, scene_kind=SCENE):
+    """Scene + map (product octree, no oracle) + this rank's ray batch, on CPU."""
+    from proud_slam_b200 import scene as sc, svo
+    s = sc.make_scene(scene_kind, pixel_stride=2)
+    tree = svo.Octree()
+    tree.init(s.grid_dim, 16, s.voxel_size, 8)
+    tree.insert(torch.from_numpy(s.voxels))
+    n_oct = tree.count_nodes()
+    ms = svo.build_map_states(tree, s.voxel_size, num_embeddings=max(20000, n_oct), device="cpu", seed=0)
+    frames = [(rank * keyframes + i) % len(s.frames) for i in range(keyframes)]
+    rays_o, rays_d, rgb, depth = sc.sample_batch(s, frames, rays_per_frame, seed=100 + rank)
+    return s, ms, (rays_o[0].contiguous(), rays_d[0].contiguous(), rgb[0].contiguous(), depth[0].contiguous()), n_oct, tree.count_leaf_nodes()
+
+
+def decoder_params(width, device):
+    torch.manual_seed(0)
+    shapes = [(width, 16), (width, width), (129, width), (width, 144), (3, width)]
+    out = []
+    for o, i in shapes:     # nn.Linear default init
+        b = 1.0 / (i ** 0.5)
+        out += [(torch.rand(o, i) * 2 - 1) * b, (torch.rand(o) * 2 - 1) * b]
+    return [p.to(device).contiguous() for p in out]
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def run_reference(args):
+    """`--impl reference`: the reference's CPU path for this workload.  /root/reference cannot travel
+    to the GPU box and its two native kernels have no CPU build, so this is the oracle PORT
+    (oracle/: C restatement of the kernels + the torch stages on CPU tensors), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle  # noqa: F401  (test infrastructure; allowed here as the CPU baseline)
+    from tests import util
+    from oracle import render_oracle as ro
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    s, ms, (rays_o, rays_d, rgb, depth), n_oct, n_vox = build_workload(0)
+    ms["voxel_vertex_emb"].requires_grad_(True)
+    dec = [p.requires_grad_(True) for p in decoder_params(WIDTH, "cpu")]
+    R = rays_o.shape[0]
+    ro_, rd_ = rays_o[None].clone().requires_grad_(True), rays_d[None].clone().requires_grad_(True)
+    gen = torch.Generator().manual_seed(0)
+
+    def one():
+        util.oracle_step(ro_, rd_, rgb[None], depth[None], ms, dec, voxel_size=s.voxel_size, generator=gen)
+
+    for _ in range(args.warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = R / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{SCENE}: {KEYFRAMES} keyframes x {RAYS_PER_FRAME} rays = {R} rays/iter, {n_oct} octants "
+                               f"({n_vox} voxels) at 0.2 m, decoder width {WIDTH}, mapping fwd+bwd on CPU tensors"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} full iterations of the {R}-ray workload (oracle port, torch CPU + OpenMP C kernels)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch.distributed as dist
+    from proud_slam_b200 import _lib
+    from proud_slam_b200.pipeline import RenderPipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the render path has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    s, ms_cpu, batch_cpu, n_oct, n_vox = build_workload(rank)
+    ms = {k: v.to(device).contiguous() for k, v in ms_cpu.items()}
+    dec = decoder_params(WIDTH, device)
+    R = batch_cpu[0].shape[0]
+    E = ms["voxel_vertex_emb"].shape[0]
+    # one flat gradient buffer [E*16 | decoder]: the kernels scatter straight into what NCCL reduces
+    n_dec = sum(p.numel() for p in dec)
+    flat = torch.zeros(E * 16 + n_dec, device=device)
+    g_emb = flat[: E * 16].view(E, 16)
+    g_dec, off = [], E * 16
+    for p in dec:
+        g_dec.append(flat[off: off + p.numel()].view_as(p))
+        off += p.numel()
+    host = [t.pin_memory() for t in batch_cpu]                        # e2e: inputs start in pinned host memory
+    dev_in = [torch.empty_like(t, device=device) for t in batch_cpu]
+    for d, h in zip(dev_in, host):
+        d.copy_(h)
+    pipe = RenderPipeline(R, device, samples_per_ray=64)
+    pipe.bind(dev_in[0], dev_in[1], ms, dec, voxel_size=s.voxel_size, step_size=0.1 * s.voxel_size, truncation=0.1,
+              max_distance=10.0, max_depth=10.0, target_rgb=dev_in[2], target_depth=dev_in[3], noise=None, seed=1,
+              weights=CRIT_W, g_emb=g_emb, g_dec=g_dec, grad_rays=True, defer_loss=(world > 1))
+    rows = torch.zeros(world, 16, dtype=torch.float64, device=device)
+    loss_host = torch.empty(16, pin_memory=True)
+    flush = torch.empty(192 * 1024 * 1024 // 4, device=device)       # 192 MiB > 126 MB L2
+
+    def step(seed):
+        pipe.args.seed = seed
+        flat.zero_()
+        if world == 1:
+            pipe.step()
+        else:
+            pipe.sample()
+            pipe.forward()                                            # stops at this rank's raw loss sums
+            dist.all_gather_into_tensor(rows, pipe.loss_raw)
+            pipe.finalize_loss(rows)
+            pipe.backward()
+            dist.all_reduce(flat)
+
+    def timed(fn, n):
+        """n steps, each bracketed by events on the launching stream, L2 flushed in between."""
+        total = 0.0
+        evs = []
+        for i in range(n):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn(i)
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        for a, b in evs:
+            total += a.elapsed_time(b)
+        return total / n
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(1000 + i)
+    barrier()
+    counts = pipe.counts()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    ms_step = timed(lambda i: step(i + 1), args.steps)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # end to end through the public call with HOST buffers: H2D of the step's inputs, D2H of the loss
+    def e2e_step(i):
+        for d, h in zip(dev_in, host):
+            d.copy_(h, non_blocking=True)
+        step(i + 1)
+        loss_host.copy_(pipe.loss, non_blocking=True)
+
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    ms_e2e = timed(e2e_step, args.steps)
+    barrier()
+    loss_val = float(loss_host[0])
+
+    # dominant kernel alone (field backward = decoder dgrad+wgrad + embedding scatter), events around it
+    prof = {}
+    if rank == 0:
+        pipe.args.flags = pipe.args.flags & ~_lib.F_DEFER_LOSS
+        stage_ms = []
+        for stage_id in range(6):
+            reps = []
+            for it in range(max(3, min(args.steps, 10))):
+                flat.zero_()
+                for k in range(stage_id):        # bring the pipeline to this stage
+                    pipe.stage(k)
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                pipe.stage(stage_id)
+                b.record()
+                torch.cuda.synchronize()
+                reps.append(a.elapsed_time(b))
+            stage_ms.append(sum(reps[1:]) / max(len(reps) - 1, 1))
+        prof = dict(zip(["intersect", "sample", "field_fwd", "composite_fwd", "composite_bwd", "field_bwd"], stage_ms))
+
+    if world > 1:
+        t = torch.tensor([ms_step, ms_e2e], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step, ms_e2e = t.tolist()
+        ns = torch.tensor([float(counts["n_samples"])], device=device, dtype=torch.float64)
+        dist.all_reduce(ns)
+        total_samples = int(ns.item())
+    else:
+        total_samples = counts["n_samples"]
+
+    if rank == 0:
+        peaks = measured_peaks()
+        P = counts["n_samples"]
+        flops_bwd = 4.0 * macs_per_sample(WIDTH) * P              # dgrad + wgrad; recompute not counted
+        t_k = prof["field_bwd"] * 1e-3
+        achieved = flops_bwd / t_k / 1e12
+        value = world * R / (ms_step * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"{SCENE}: {KEYFRAMES} keyframes x {RAYS_PER_FRAME} rays = {R} rays/iter per GPU, {n_oct} octants "
+                                   f"({n_vox} voxels) at 0.2 m, {E}x16 embeddings, decoder width {WIDTH}, mapping fwd+bwd",
+                       "rays_per_gpu": R, "hit_rays": counts["R_h"], "samples_per_iter_per_gpu": P, "max_samples_per_ray": counts["S"],
+                       "total_samples_all_gpus": total_samples, "l2": "flushed (192 MiB write) between timed iterations",
+                       "parallelism": f"dp{world} (rays sharded, map replicated, grads all-reduced)" if world > 1 else "single GPU",
+                       "loss": loss_val},
+            "e2e": {"value": world * R / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(sum(t.numel() * 4 for t in host)), "d2h_bytes_per_step": 64},
+            "gpu_launches": args.steps * 15,
+            "clocks": clocks,
+            "roofline": {"kernel": "k_field<128,bwd> (decoder dgrad+wgrad, fused trilinear backward)", "bound": "tensor",
+                         "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
+                         "traffic": None, "peak_source": peaks["source"] + ", bf16 burst; kernel math is fp32 SIMT in this round",
+                         "algorithmic_flops_per_launch": flops_bwd, "kernel_ms": prof["field_bwd"]},
+            "stage_ms": prof,
+        }
+        line["cpu_baseline"] = cpu_baseline(s, ms_cpu)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(s, ms_cpu):
+    """Oracle port timed on the host cores on a bounded sample: BASELINE.json configs[0]-sized batches
+    (2048 rays) of the same scene, fwd + loss + bwd."""
+    import oracle  # noqa: F401
+    from proud_slam_b200 import scene as sc
+    from tests import util
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    ms = {k: v.clone() for k, v in ms_cpu.items()}
+    ms["voxel_vertex_emb"].requires_grad_(True)
+    dec = [p.requires_grad_(True) for p in decoder_params(WIDTH, "cpu")]
+    rays_o, rays_d, rgb, depth = sc.sample_batch(s, [0, 1], 1024, seed=7)
+    rays_o.requires_grad_(True)
+    rays_d.requires_grad_(True)
+    gen = torch.Generator().manual_seed(0)
+    one = lambda: util.oracle_step(rays_o, rays_d, rgb, depth, ms, dec, voxel_size=s.voxel_size, generator=gen)
+    one()
+    n, t0 = 0, time.perf_counter()
+    while n < 3 or (time.perf_counter() - t0 < 10.0 and n < 50):
+        one()
+        n += 1
+    dt = (time.perf_counter() - t0) / n
+    return {"value": 2048 / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} iterations x 2048 rays (2 keyframes x 1024) of the same scene, fwd+loss+bwd, {dt * 1e3:.1f} ms each"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

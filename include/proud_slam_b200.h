@@ -164,6 +164,8 @@ int pslam_decoder_bwd(int p, const pslam_decoder_t *dec, const float *feat,
 #define PSLAM_F_GRAD_DEC   4
 #define PSLAM_F_GRAD_RAYS  8
 #define PSLAM_F_FORWARD_ONLY 16
+#define PSLAM_F_DEFER_LOSS 32   /* forward stops at this rank's raw loss sums (loss_raw); the
+                                  caller exchanges them and calls pslam_loss_finalize */
 
 /* device-side counters written by the pipeline (int32 each) */
 enum {
@@ -225,6 +227,7 @@ typedef struct {
     float *scratch_f;                      /* [pslam_render_scratch_f_count(R)] block partials (loss sums) */
     int *counters;                         /* [PSLAM_C_COUNT] */
     /* outputs */
+    double *loss_raw;                      /* [16] this rank's raw loss sums (see composite.cu RAW_*) */
     float *loss;                           /* [PSLAM_L_COUNT] */
     float *g_emb;                          /* [E,16] += */
     pslam_decoder_grad_t g_dec;            /* += */
@@ -244,10 +247,17 @@ int64_t pslam_render_scratch_f_count(int R);
 int pslam_render_sample(const pslam_render_t *p, pslam_stream_t stream);
 /* Stage 2: trilinear lookup + decoder + compositing + loss (kernels 3-5 forward). */
 int pslam_render_forward(const pslam_render_t *p, pslam_stream_t stream);
+/* Multi-GPU: closes the loss from the raw sums of all ranks (rows [nrows,16],
+ * e.g. an all-gather of every rank's loss_raw): sums add, S is the maximum
+ * (criterion.py:70-112 couples all rays through global means and counts). */
+int pslam_loss_finalize(const pslam_render_t *p, const double *rows, int nrows, pslam_stream_t stream);
 /* Stage 3: backward of stage 2 into g_emb / g_dec / g_rays_*. */
 int pslam_render_backward(const pslam_render_t *p, pslam_stream_t stream);
 /* All three stages back to back. */
 int pslam_render_step(const pslam_render_t *p, pslam_stream_t stream);
+/* Profiling hook: one stage of the step (0 intersect, 1 sampling, 2 field fwd, 3 composite fwd + loss,
+ * 4 composite bwd, 5 field bwd) so a benchmark can bracket a single kernel with events. */
+int pslam_render_stage(const pslam_render_t *p, int stage, pslam_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * Host-side octree: torch.classes.svo.Octree,

@@ -38,13 +38,13 @@ class RenderT(C.Structure):
         + [(n, C.c_void_p) for n in ("hit_idx", "hit_min", "hit_max", "hit_count", "hit_ray", "ray_rank",
                                      "samp_off", "samp_vox", "samp_ray", "samp_z", "samp_dist", "samp_out",
                                      "samp_w", "samp_gout", "ray_out", "scratch_i", "scratch_f", "counters")]
-        + [("loss", C.c_void_p), ("g_emb", C.c_void_p), ("g_dec", DecoderGradT),
+        + [("loss_raw", C.c_void_p), ("loss", C.c_void_p), ("g_emb", C.c_void_p), ("g_dec", DecoderGradT),
            ("g_rays_o", C.c_void_p), ("g_rays_d", C.c_void_p)]
     )
 
 
 # flags / counter slots / loss slots (include/proud_slam_b200.h)
-F_TRACKING, F_GRAD_EMB, F_GRAD_DEC, F_GRAD_RAYS, F_FORWARD_ONLY = 1, 2, 4, 8, 16
+F_TRACKING, F_GRAD_EMB, F_GRAD_DEC, F_GRAD_RAYS, F_FORWARD_ONLY, F_DEFER_LOSS = 1, 2, 4, 8, 16, 32
 C_RH, C_P, C_NSAMP, C_S, C_OVERFLOW, C_COUNT = 0, 1, 2, 3, 4, 16
 L_TOTAL, L_COLOR, L_DEPTH, L_FS, L_SDF, L_COUNT = 0, 1, 2, 3, 4, 16
 
@@ -72,7 +72,9 @@ _PROTOTYPES = {
     "pslam_render_sample": (C.c_int, [C.POINTER(RenderT), _S]),
     "pslam_render_forward": (C.c_int, [C.POINTER(RenderT), _S]),
     "pslam_render_backward": (C.c_int, [C.POINTER(RenderT), _S]),
+    "pslam_loss_finalize": (C.c_int, [C.POINTER(RenderT), _P, _I, _S]),
     "pslam_render_step": (C.c_int, [C.POINTER(RenderT), _S]),
+    "pslam_render_stage": (C.c_int, [C.POINTER(RenderT), _I, _S]),
     "pslam_octree_new": (C.c_void_p, [_I]),
     "pslam_octree_free": (None, [_P]),
     "pslam_octree_count": (C.c_int, [_P]),

@@ -52,7 +52,7 @@ static int check_render_field(const pslam_render_t *p, bool backward)
     PSLAM_CHECK_ARG(p->dec.width == 128 || p->dec.width == 256, PSLAM_E_RANGE, "decoder width %d not supported (128 or 256)", p->dec.width);
     PSLAM_CHECK_ARG(p->dec.W1 && p->dec.b1 && p->dec.W2 && p->dec.b2 && p->dec.W3 && p->dec.b3 && p->dec.W4 && p->dec.b4 && p->dec.W5 && p->dec.b5,
                     PSLAM_E_ARG, "null decoder parameter");
-    PSLAM_CHECK_ARG(p->dec_ws && p->samp_out && p->ray_out && p->loss, PSLAM_E_ARG, "null forward buffer");
+    PSLAM_CHECK_ARG(p->dec_ws && p->samp_out && p->ray_out && p->loss && p->loss_raw, PSLAM_E_ARG, "null forward buffer");
     PSLAM_CHECK_ARG((p->target_rgb == nullptr) == (p->target_depth == nullptr), PSLAM_E_ARG, "target_rgb and target_depth go together");
     if (backward) PSLAM_CHECK_ARG(p->target_rgb && p->target_depth, PSLAM_E_ARG, "backward needs the Criterion targets");
     PSLAM_CHECK_ARG(((uintptr_t)p->dec.W1 | (uintptr_t)p->dec.W2 | (uintptr_t)p->dec.W3 | (uintptr_t)p->dec.W4 | (uintptr_t)p->dec_ws |
@@ -93,9 +93,9 @@ extern "C" int pslam_device_info(int *out3)
 
 extern "C" int64_t pslam_render_scratch_i_count(int R)
 {
-    return 2 * ((int64_t)ceil_div(R, 128) + 8) + 2 * (int64_t)ceil_div(R, 8) + 64;
+    return 2 * ((int64_t)ceil_div(R, 128) + 8) + 8 * (int64_t)ceil_div(R, 8) + 64;
 }
-extern "C" int64_t pslam_render_scratch_f_count(int R) { return 4 * (int64_t)ceil_div(R, 8) + 64; }
+extern "C" int64_t pslam_render_scratch_f_count(int R) { return 8 * (int64_t)ceil_div(R, 8) + 64; }
 
 extern "C" int pslam_render_sample(const pslam_render_t *p, pslam_stream_t stream)
 {
@@ -116,6 +116,13 @@ extern "C" int pslam_render_forward(const pslam_render_t *p, pslam_stream_t stre
     return launch_composite_forward(p, st);
 }
 
+extern "C" int pslam_loss_finalize(const pslam_render_t *p, const double *rows, int nrows, pslam_stream_t stream)
+{
+    if (int rc = check_render(p)) return rc;
+    PSLAM_CHECK_ARG(rows && nrows > 0 && p->loss, PSLAM_E_ARG, "loss_finalize: bad argument");
+    return launch_loss_coeffs(p, rows, nrows, (cudaStream_t)stream);
+}
+
 extern "C" int pslam_render_backward(const pslam_render_t *p, pslam_stream_t stream)
 {
     if (int rc = check_render(p)) return rc;
@@ -129,10 +136,33 @@ extern "C" int pslam_render_step(const pslam_render_t *p, pslam_stream_t stream)
 {
     if (int rc = pslam_render_sample(p, stream)) return rc;
     if (int rc = pslam_render_forward(p, stream)) return rc;
-    if (p->flags & PSLAM_F_FORWARD_ONLY) return 0;
+    if (p->flags & (PSLAM_F_FORWARD_ONLY | PSLAM_F_DEFER_LOSS)) return 0;
     return pslam_render_backward(p, stream);
 }
 
 /* sizeof / field offsets so that language bindings can verify their struct mirrors */
 extern "C" int pslam_render_sizeof(void) { return (int)sizeof(pslam_render_t); }
 extern "C" int pslam_render_offsetof_loss(void) { return (int)offsetof(pslam_render_t, loss); }
+
+/* Profiling hook: launches ONE stage of the step so that a benchmark can bracket a single kernel
+ * with events.  0 intersect(+compaction) 1 sampling 2 field fwd 3 composite fwd(+loss) 4 composite bwd
+ * 5 field bwd.  The preceding stages must have run on the same argument block. */
+extern "C" int pslam_render_stage(const pslam_render_t *p, int stage, pslam_stream_t stream)
+{
+    if (int rc = check_render(p)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (stage) {
+        case 0: {
+            cudaError_t e = cudaMemsetAsync(p->counters, 0, sizeof(int) * PSLAM_C_COUNT, st);
+            if (e != cudaSuccess) { set_error("memset counters: %s", cudaGetErrorString(e)); return (int)e; }
+            return launch_intersect_fused(p, st);
+        }
+        case 1: return launch_sample_fused(p, st);
+        case 2: if (int rc = check_render_field(p, false)) return rc; return launch_field_forward(p, st);
+        case 3: if (int rc = check_render_field(p, false)) return rc; return launch_composite_forward(p, st);
+        case 4: if (int rc = check_render_field(p, true)) return rc; return launch_composite_backward(p, st);
+        case 5: if (int rc = check_render_field(p, true)) return rc; return launch_field_backward(p, st);
+    }
+    set_error("unknown stage %d", stage);
+    return PSLAM_E_ARG;
+}

@@ -30,13 +30,6 @@ enum { L_THRESH = 5, L_CDEPTH = 6, L_CFS = 7, L_CSDF = 8, L_CCOLOR = 9, L_NVALID
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-struct RaySeg {
-    int beg, cnt;   // CSR segment
-    int ray;        // ray id
-    int ind;        // index of the first sign change (0 if none)
-    float z_min;
-};
-
 // first k with s_k*s_{k+1} < 0 over the reference's padded row of width S
 __device__ __forceinline__ int first_sign_change(const float *__restrict__ out, int beg, int cnt, int S, int lane)
 {
@@ -57,14 +50,18 @@ __device__ __forceinline__ int first_sign_change(const float *__restrict__ out, 
 __global__ void __launch_bounds__(kCompThreads)
 k_composite_fwd(pslam_render_t p, float *__restrict__ part_f, int *__restrict__ part_i)
 {
-    __shared__ float s_f[kCompWarps][3];
-    __shared__ int s_i[kCompWarps][2];
+    __shared__ float s_f[kCompWarps][5];
+    __shared__ int s_i[kCompWarps][6];
     const int Rh = p.counters[PSLAM_C_RH];
     const int S = p.counters[PSLAM_C_S];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = blockIdx.x * kCompWarps + warp;
     float sum_color = 0.f, sum_fs = 0.f, sum_sdf = 0.f;
     int n_fs = 0, n_sdf = 0;
+    // pad terms, linear in S so that they can be closed after a cross-rank max of S:
+    //   pads of a ray = (S - cnt) copies of (z=10, sdf=1)  ->  S*x0 - x1 with x1 = x0*cnt
+    float pad_d0 = 0.f, pad_d1 = 0.f;           // sum over rays of [sdf-mask pad] d^2 (and * cnt)
+    int pad_f0 = 0, pad_f1 = 0, pad_m0 = 0, pad_m1 = 0;
     if (q < Rh) {
         const int beg = p.samp_off[q], cnt = min(p.samp_off[q + 1], p.sample_cap) - beg;
         const int ray = p.hit_ray[q];
@@ -116,12 +113,14 @@ k_composite_fwd(pslam_render_t p, float *__restrict__ part_f, int *__restrict__ 
         }
         if (lane == 0) {
             // the (S - cnt) pads of this row: z = 10, sdf = 1
-            const int npad = S - cnt;
-            if (npad > 0 && has_tgt) {
+            if (has_tgt) {
                 const bool front = kPadZ < __fsub_rn(gt, tau), back = kPadZ > __fadd_rn(gt, tau);
                 const bool sm = !front && !back && gt > 0.0f && gt < p.max_depth;
-                if (front) n_fs += npad;   // (1*1 - 1)^2 = 0 adds nothing to the sum
-                if (sm) { n_sdf += npad; const float d = (kPadZ + kPadSdf * tau) - gt; sum_sdf += (float)npad * d * d; }
+                if (front) { pad_f0 = 1; pad_f1 = cnt; }   // (1*1 - 1)^2 = 0 adds nothing to the fs sum
+                if (sm) {
+                    const float d = (kPadZ + kPadSdf * tau) - gt;
+                    pad_m0 = 1; pad_m1 = cnt; pad_d0 = d * d; pad_d1 = d * d * (float)cnt;
+                }
             }
             float *ro = p.ray_out + (size_t)q * 8;
             ro[0] = r; ro[1] = g; ro[2] = b; ro[3] = dep; ro[4] = z_min; ro[5] = U;
@@ -138,66 +137,62 @@ k_composite_fwd(pslam_render_t p, float *__restrict__ part_f, int *__restrict__ 
         n_fs = warp_sum_i(n_fs); n_sdf = warp_sum_i(n_sdf);
     }
     if (lane == 0) {
-        s_f[warp][0] = sum_color; s_f[warp][1] = sum_fs; s_f[warp][2] = sum_sdf;
-        s_i[warp][0] = n_fs; s_i[warp][1] = n_sdf;
+        s_f[warp][0] = sum_color; s_f[warp][1] = sum_fs; s_f[warp][2] = sum_sdf; s_f[warp][3] = pad_d0; s_f[warp][4] = pad_d1;
+        s_i[warp][0] = n_fs; s_i[warp][1] = n_sdf; s_i[warp][2] = pad_f0; s_i[warp][3] = pad_f1;
+        s_i[warp][4] = pad_m0; s_i[warp][5] = pad_m1;
     }
     __syncthreads();
-    if (threadIdx.x < 3) {
+    if (threadIdx.x < 5) {
         float t = 0.0f;
         for (int w = 0; w < kCompWarps; ++w) t += s_f[w][threadIdx.x];
-        part_f[(size_t)blockIdx.x * 4 + threadIdx.x] = t;
-    } else if (threadIdx.x < 5) {
+        part_f[(size_t)blockIdx.x * 8 + threadIdx.x] = t;
+    } else if (threadIdx.x >= 8 && threadIdx.x < 14) {
         int t = 0;
-        for (int w = 0; w < kCompWarps; ++w) t += s_i[w][threadIdx.x - 3];
-        part_i[(size_t)blockIdx.x * 2 + threadIdx.x - 3] = t;
+        for (int w = 0; w < kCompWarps; ++w) t += s_i[w][threadIdx.x - 8];
+        part_i[(size_t)blockIdx.x * 8 + threadIdx.x - 8] = t;
     }
 }
 
-// block-wide sums (1024 threads), deterministic order
-__device__ __forceinline__ float block_sum_f(float v, float *s_buf)
-{
-    v = warp_sum(v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) s_buf[threadIdx.x >> 5] = v;
-    __syncthreads();
-    float t = 0.0f;
-    for (int w = 0; w < 32; ++w) t += s_buf[w];
-    return t;
-}
-__device__ __forceinline__ long long block_sum_ll(long long v, long long *s_buf)
+// block-wide sum (1024 threads) in double, deterministic order
+__device__ __forceinline__ double block_sum_d(double v, double *s_buf)
 {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     __syncthreads();
     if ((threadIdx.x & 31) == 0) s_buf[threadIdx.x >> 5] = v;
     __syncthreads();
-    long long t = 0;
+    double t = 0.0;
     for (int w = 0; w < 32; ++w) t += s_buf[w];
     return t;
 }
 
+// Stage A of the loss: this rank's raw sums -> raw[16] (double).  Slots: see RAW_* below.
+enum { RAW_COLOR = 0, RAW_FS, RAW_SDF, RAW_D0, RAW_D1, RAW_NFS, RAW_F0, RAW_F1, RAW_NSDF, RAW_M0, RAW_M1, RAW_RH,
+       RAW_DEPTH, RAW_NVALID, RAW_S, RAW_THRESH };
+
 __global__ void __launch_bounds__(1024)
-k_loss_finalize(pslam_render_t p, const float *__restrict__ part_f, const int *__restrict__ part_i, int nblocks)
+k_loss_reduce(pslam_render_t p, const float *__restrict__ part_f, const int *__restrict__ part_i, int nblocks)
 {
-    __shared__ float s_f[32];
-    __shared__ long long s_ll[32];
+    __shared__ double s_d[32];
     __shared__ unsigned s_hist[256];
     __shared__ unsigned s_prefix, s_rank;
     const int Rh = p.counters[PSLAM_C_RH];
-    const int S = p.counters[PSLAM_C_S];
     const int tid = threadIdx.x;
-    float c = 0.f, fs = 0.f, sd = 0.f;
-    long long nfs = 0, nsdf = 0;
+    double f[5] = {0, 0, 0, 0, 0}, n[6] = {0, 0, 0, 0, 0, 0};
     for (int b = tid; b < nblocks; b += 1024) {
-        c += part_f[(size_t)b * 4]; fs += part_f[(size_t)b * 4 + 1]; sd += part_f[(size_t)b * 4 + 2];
-        nfs += part_i[(size_t)b * 2]; nsdf += part_i[(size_t)b * 2 + 1];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) f[k] += (double)part_f[(size_t)b * 8 + k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) n[k] += (double)part_i[(size_t)b * 8 + k];
     }
-    c = block_sum_f(c, s_f); fs = block_sum_f(fs, s_f); sd = block_sum_f(sd, s_f);
-    nfs = block_sum_ll(nfs, s_ll); nsdf = block_sum_ll(nsdf, s_ll);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) f[k] = block_sum_d(f[k], s_d);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) n[k] = block_sum_d(n[k], s_d);
 
     // tracking: lower median of tmp = |dd|/sqrt(var) over the hit rays (torch.median), by
     // 4 x 8-bit radix select on the float bit patterns (all values are >= 0)
-    float thresh = __int_as_float(0x7f800000), median = 0.0f;
+    float thresh = __int_as_float(0x7f800000);
     if ((p.flags & PSLAM_F_TRACKING) && Rh > 0) {
         if (tid == 0) { s_prefix = 0u; s_rank = (unsigned)((Rh - 1) / 2); }
         for (int pass = 0; pass < 4; ++pass) {
@@ -223,36 +218,60 @@ k_loss_finalize(pslam_render_t p, const float *__restrict__ part_f, const int *_
             }
             __syncthreads();
         }
-        median = __uint_as_float(s_prefix);
-        thresh = 10.0f * median;
+        thresh = 10.0f * __uint_as_float(s_prefix);
     }
     // depth loss over valid (and gated) rays, criterion.py:41-50
-    float dsum = 0.0f;
-    long long nvalid = 0;
+    double dsum = 0.0, nvalid = 0.0;
     for (int q = tid; q < Rh; q += 1024) {
         const float *ro = p.ray_out + (size_t)q * 8;
         const bool ok = ro[7] != 0.0f && (!(p.flags & PSLAM_F_TRACKING) || ro[6] < thresh);
-        if (ok) { dsum += fabsf(__ldg(p.target_depth + p.hit_ray[q]) - ro[3]); ++nvalid; }
+        if (ok) { dsum += (double)fabsf(__ldg(p.target_depth + p.hit_ray[q]) - ro[3]); nvalid += 1.0; }
     }
-    dsum = block_sum_f(dsum, s_f);
-    nvalid = block_sum_ll(nvalid, s_ll);
+    dsum = block_sum_d(dsum, s_d);
+    nvalid = block_sum_d(nvalid, s_d);
     if (tid == 0) {
-        const float n = (float)Rh * (float)S;     // elements of the reference's padded [R_h,S] tensors
-        const float fnfs = (float)nfs, fnsdf = (float)nsdf;
-        const float fs_w = 1.0f - fnfs / (fnfs + fnsdf), sdf_w = 1.0f - fnsdf / (fnfs + fnsdf);
-        const float color = c / (3.0f * (float)Rh);
-        const float depth = dsum / (float)nvalid;
-        const float fs_loss = (fs / n) * fs_w, sdf_loss = (sd / n) * sdf_w;
-        p.loss[PSLAM_L_COLOR] = color; p.loss[PSLAM_L_DEPTH] = depth;
-        p.loss[PSLAM_L_FS] = fs_loss; p.loss[PSLAM_L_SDF] = sdf_loss;
-        p.loss[PSLAM_L_TOTAL] = p.w_rgb * color + p.w_depth * depth + p.w_fs * fs_loss + p.w_sdf * sdf_loss;
-        p.loss[L_THRESH] = thresh;
-        p.loss[L_CDEPTH] = p.w_depth / (float)nvalid;
-        p.loss[L_CFS] = p.w_fs * fs_w * 2.0f / n;
-        p.loss[L_CSDF] = p.w_sdf * sdf_w * 2.0f * p.truncation / n;
-        p.loss[L_CCOLOR] = p.w_rgb / (3.0f * (float)Rh);
-        p.loss[L_NVALID] = (float)nvalid; p.loss[L_NFS] = fnfs; p.loss[L_NSDF] = fnsdf; p.loss[L_MEDIAN] = median;
+        double *raw = p.loss_raw;
+        raw[RAW_COLOR] = f[0]; raw[RAW_FS] = f[1]; raw[RAW_SDF] = f[2]; raw[RAW_D0] = f[3]; raw[RAW_D1] = f[4];
+        raw[RAW_NFS] = n[0]; raw[RAW_NSDF] = n[1]; raw[RAW_F0] = n[2]; raw[RAW_F1] = n[3]; raw[RAW_M0] = n[4]; raw[RAW_M1] = n[5];
+        raw[RAW_RH] = (double)Rh; raw[RAW_DEPTH] = dsum; raw[RAW_NVALID] = nvalid;
+        raw[RAW_S] = (double)p.counters[PSLAM_C_S]; raw[RAW_THRESH] = (double)thresh;
     }
+}
+
+// Stage B: raw sums of all ranks ([nrows,16] doubles; nrows = 1 on one GPU) -> loss values and
+// the coefficients backward needs.  Sums add over ranks, S is the maximum, the pad terms close as
+// S*x0 - x1.  Final arithmetic in fp32 like criterion.py.
+__global__ void k_loss_coeffs(pslam_render_t p, const double *__restrict__ rows, int nrows)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double t[16];
+    for (int k = 0; k < 16; ++k) t[k] = 0.0;
+    for (int r = 0; r < nrows; ++r) {
+        for (int k = 0; k < RAW_S; ++k) t[k] += rows[(size_t)r * 16 + k];
+        t[RAW_S] = fmax(t[RAW_S], rows[(size_t)r * 16 + RAW_S]);
+    }
+    t[RAW_THRESH] = rows[RAW_THRESH];
+    const double S = t[RAW_S];
+    const float Rh = (float)t[RAW_RH];
+    const float n = Rh * (float)S;     // elements of the reference's padded [R_h,S] tensors
+    const float fnfs = (float)(t[RAW_NFS] + S * t[RAW_F0] - t[RAW_F1]);
+    const float fnsdf = (float)(t[RAW_NSDF] + S * t[RAW_M0] - t[RAW_M1]);
+    const float fs_sum = (float)t[RAW_FS];
+    const float sdf_sum = (float)(t[RAW_SDF] + S * t[RAW_D0] - t[RAW_D1]);
+    const float nvalid = (float)t[RAW_NVALID];
+    const float fs_w = 1.0f - fnfs / (fnfs + fnsdf), sdf_w = 1.0f - fnsdf / (fnfs + fnsdf);
+    const float color = (float)t[RAW_COLOR] / (3.0f * Rh);
+    const float depth = (float)t[RAW_DEPTH] / nvalid;
+    const float fs_loss = (fs_sum / n) * fs_w, sdf_loss = (sdf_sum / n) * sdf_w;
+    p.loss[PSLAM_L_COLOR] = color; p.loss[PSLAM_L_DEPTH] = depth;
+    p.loss[PSLAM_L_FS] = fs_loss; p.loss[PSLAM_L_SDF] = sdf_loss;
+    p.loss[PSLAM_L_TOTAL] = p.w_rgb * color + p.w_depth * depth + p.w_fs * fs_loss + p.w_sdf * sdf_loss;
+    p.loss[L_THRESH] = (float)t[RAW_THRESH];
+    p.loss[L_CDEPTH] = p.w_depth / nvalid;
+    p.loss[L_CFS] = p.w_fs * fs_w * 2.0f / n;
+    p.loss[L_CSDF] = p.w_sdf * sdf_w * 2.0f * p.truncation / n;
+    p.loss[L_CCOLOR] = p.w_rgb / (3.0f * Rh);
+    p.loss[L_NVALID] = nvalid; p.loss[L_NFS] = fnfs; p.loss[L_NSDF] = fnsdf; p.loss[L_MEDIAN] = (float)t[RAW_THRESH] * 0.1f;
 }
 
 __device__ __forceinline__ float signf_(float x) { return (x > 0.0f) ? 1.0f : ((x < 0.0f) ? -1.0f : 0.0f); }
@@ -316,14 +335,22 @@ __global__ void k_zero_f(float *__restrict__ a, int n)
 int launch_composite_forward(const pslam_render_t *p, cudaStream_t st)
 {
     const int nb = ceil_div(p->R, kCompWarps);
-    float *part_f = p->scratch_f;                                // [nb,4]
-    int *part_i = p->scratch_i + 2 * (ceil_div(p->R, 128) + 8);  // after the two scan-partial arrays: [nb,2]
+    float *part_f = p->scratch_f;                                // [nb,8]
+    int *part_i = p->scratch_i + 2 * (ceil_div(p->R, 128) + 8);  // after the two scan-partial arrays: [nb,8]
     k_composite_fwd<<<nb, kCompThreads, 0, st>>>(*p, part_f, part_i);
     PSLAM_CHECK_LAUNCH("composite_fwd");
     if (p->target_depth && p->target_rgb) {
-        k_loss_finalize<<<1, 1024, 0, st>>>(*p, part_f, part_i, nb);
-        PSLAM_CHECK_LAUNCH("loss_finalize");
+        k_loss_reduce<<<1, 1024, 0, st>>>(*p, part_f, part_i, nb);
+        PSLAM_CHECK_LAUNCH("loss_reduce");
+        if (!(p->flags & PSLAM_F_DEFER_LOSS)) return launch_loss_coeffs(p, p->loss_raw, 1, st);
     }
+    return 0;
+}
+
+int launch_loss_coeffs(const pslam_render_t *p, const double *rows, int nrows, cudaStream_t st)
+{
+    k_loss_coeffs<<<1, 32, 0, st>>>(*p, rows, nrows);
+    PSLAM_CHECK_LAUNCH("loss_coeffs");
     return 0;
 }
 

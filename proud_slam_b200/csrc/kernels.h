@@ -17,5 +17,6 @@ int launch_field_backward(const pslam_render_t *p, cudaStream_t st);
 // composite.cu (SDF->weights compositing + loss)
 int launch_composite_forward(const pslam_render_t *p, cudaStream_t st);
 int launch_composite_backward(const pslam_render_t *p, cudaStream_t st);
+int launch_loss_coeffs(const pslam_render_t *p, const double *rows, int nrows, cudaStream_t st);
 
 }  // namespace pslam

@@ -80,6 +80,7 @@ class RenderPipeline:
         self.scratch_f = torch.zeros(int(self.lib.pslam_render_scratch_f_count(R)), **f32)
         self.counters = torch.zeros(_lib.C_COUNT, **i32)
         self.loss = torch.zeros(_lib.L_COUNT, **f32)
+        self.loss_raw = torch.zeros(16, dtype=torch.float64, device=d)
         self.g_rays_o = torch.zeros(R, 3, **f32)
         self.g_rays_d = torch.zeros(R, 3, **f32)
         self.dec_ws = {w: torch.empty(int(self.lib.pslam_decoder_ws_count(w)), **f32) for w in (128, 256)}
@@ -91,7 +92,7 @@ class RenderPipeline:
     def bind(self, rays_o, rays_d, map_states, dec_params, *, voxel_size, step_size, truncation,
              max_distance, max_depth=10.0, target_rgb=None, target_depth=None, noise=None, seed=0,
              weights=(0.5, 1.0, 10.0, 5000.0), tracking=False, g_emb=None, g_dec=None, grad_rays=False,
-             forward_only=False):
+             forward_only=False, defer_loss=False):
         """Fills the pslam_render_t block.  Tensors: rays_* [R,3] (or [1,R,3]) f32; map_states as the
         reference's dict (voxel_center_xyz [N,3] f32, voxel_structure [N,9] i32, voxel_vertex_idx [N,8]
         i32, voxel_vertex_emb [E,16] f32); dec_params = the 10 decoder tensors in state_dict order;
@@ -122,6 +123,8 @@ class RenderPipeline:
             flags |= F_GRAD_RAYS
         if forward_only:
             flags |= F_FORWARD_ONLY
+        if defer_loss:
+            flags |= _lib.F_DEFER_LOSS
         a.flags = flags
         a.voxel_size, a.step_size, a.truncation = float(voxel_size), float(step_size), float(truncation)
         a.max_distance, a.max_depth = float(max_distance), float(max_depth)
@@ -146,7 +149,7 @@ class RenderPipeline:
         a.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         for name in ("hit_idx", "hit_min", "hit_max", "hit_count", "hit_ray", "ray_rank", "samp_off", "samp_vox",
                      "samp_ray", "samp_z", "samp_dist", "samp_out", "samp_w", "samp_gout", "ray_out", "scratch_i",
-                     "scratch_f", "counters", "loss", "g_rays_o", "g_rays_d"):
+                     "scratch_f", "counters", "loss", "loss_raw", "g_rays_o", "g_rays_d"):
             setattr(a, name, getattr(self, name).data_ptr())
         a.g_emb = None if g_emb is None else _lib.require_cuda(g_emb, "g_emb", torch.float32).data_ptr()
         if g_dec is not None:
@@ -174,6 +177,15 @@ class RenderPipeline:
 
     def backward(self):
         self._call(self.lib.pslam_render_backward, "pslam_render_backward")
+
+    def finalize_loss(self, rows):
+        """Multi-GPU: rows = all ranks' ``loss_raw`` ([nranks,16] float64 on this device)."""
+        _lib.require_cuda(rows, "loss rows")
+        _lib.check(self.lib.pslam_loss_finalize(C.byref(self.args), ptr(rows), int(rows.shape[0]),
+                                                _lib.stream_ptr(self.device)), "pslam_loss_finalize")
+
+    def stage(self, i):
+        _lib.check(self.lib.pslam_render_stage(C.byref(self.args), int(i), _lib.stream_ptr(self.device)), f"stage {i}")
 
     def step(self):
         self._call(self.lib.pslam_render_step, "pslam_render_step")
