@@ -200,7 +200,7 @@ def run_gpu(args):
         else:
             pipe.sample()
             pipe.forward()                                            # stops at this rank's raw loss sums
-            dist.all_gather_into_tensor(rows, pipe.loss_raw)
+            dist.all_gather_into_tensor(rows.view(-1), pipe.loss_raw.view(-1))
             pipe.finalize_loss(rows)
             pipe.backward()
             dist.all_reduce(flat)

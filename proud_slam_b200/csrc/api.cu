@@ -1,5 +1,13 @@
 // libproud_b200.so: error reporting, device queries and the three-stage driver
 // of the fused render path (include/proud_slam_b200.h).
+//
+// The driver replaces the Python control flow of the reference's render_rays
+// (src/variations/render_helpers.py:351-556), Criterion.forward (src/criterion.py:16-68) and
+// loss.backward() (render_helpers.py:671): the reference synchronises with the host at least
+// seven times per call to size its padded tensors (voxel_helpers.py:582, 320, 359;
+// render_helpers.py:388-433); here every data-dependent size is a device-side counter and the
+// launches are enqueued back to back.  Errors are returned, never exit()ed
+// (sparse_voxels/include/cuda_utils.h:37-48 exits).
 #include <stdarg.h>
 #include <stddef.h>
 #include <string.h>

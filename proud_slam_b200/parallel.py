@@ -1,0 +1,78 @@
+"""Ray / keyframe data parallelism over the GPUs of one box.
+
+The reference is single-GPU.  Here every rank holds a replica of the map (octree, vertex table,
+embeddings) and of the decoder, renders its own ray batch, and two exchanges make the result equal
+to one big batch (up to fp32 re-association):
+
+1. before backward, the loss couples all rays through global means and counts
+   (``src/criterion.py:37-50, 96-112``): each rank's raw sums (16 doubles) are all-gathered and
+   closed identically on every rank (``pslam_loss_finalize``);
+2. after backward, one sum-all-reduce of a single flat fp32 buffer ``[E*16 | decoder]`` that the
+   kernels scattered their gradients straight into (no staging copy before the collective).
+
+``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests) is the plumbing.
+"""
+from typing import List, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, rank: int, world: int):
+    """Contiguous block of ``n`` items owned by ``rank`` (first ranks take the remainder)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_keyframes(frame_ids: Sequence[int], rank: int, world: int) -> List[int]:
+    """Keyframes of this rank when there are at least as many keyframes as GPUs
+    (matches the reference's per-frame ray assembly, render_helpers.py:620-646)."""
+    lo, hi = shard_bounds(len(frame_ids), rank, world)
+    return list(frame_ids[lo:hi])
+
+
+def shard_rays(tensors: Sequence[torch.Tensor], rank: int, world: int):
+    """Contiguous ray block of the concatenated batch (dim 0 = rays)."""
+    lo, hi = shard_bounds(tensors[0].shape[0], rank, world)
+    return [t[lo:hi].contiguous() for t in tensors]
+
+
+class FlatGrads:
+    """One flat fp32 buffer ``[E*16 | decoder params]`` with views for the kernels to write into."""
+
+    def __init__(self, emb: torch.Tensor, dec_params: Sequence[torch.Tensor]):
+        n = emb.numel() + sum(p.numel() for p in dec_params)
+        self.flat = torch.zeros(n, dtype=torch.float32, device=emb.device)
+        self.g_emb = self.flat[: emb.numel()].view_as(emb)
+        self.g_dec, off = [], emb.numel()
+        for p in dec_params:
+            self.g_dec.append(self.flat[off: off + p.numel()].view_as(p))
+            off += p.numel()
+
+    def zero_(self):
+        self.flat.zero_()
+
+
+class DataParallelStep:
+    """One mapping iteration across ranks.  ``pipe`` needs ``sample() / forward() / backward() /
+    finalize_loss(rows)`` and a ``loss_raw`` tensor of 16 float64 (``RenderPipeline`` bound with
+    ``defer_loss=True``)."""
+
+    def __init__(self, pipe, grads: FlatGrads, group=None):
+        self.pipe, self.grads, self.group = pipe, grads, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rows = torch.zeros(self.world, 16, dtype=torch.float64, device=pipe.loss_raw.device)
+
+    def __call__(self):
+        self.grads.zero_()
+        self.pipe.sample()
+        self.pipe.forward()
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.rows.view(-1), self.pipe.loss_raw.view(-1), group=self.group)
+        else:
+            self.rows.copy_(self.pipe.loss_raw.view(1, 16))
+        self.pipe.finalize_loss(self.rows)
+        self.pipe.backward()
+        if self.world > 1:
+            dist.all_reduce(self.grads.flat, group=self.group)

@@ -80,15 +80,22 @@ def test_step_matches_oracle(kind, frames, rays, tracking, width, device):
     from oracle import render_oracle as ro
     from proud_slam_b200 import scene as sc
     s, ms = util.build_scene(kind)
-    dec = ro.decoder_params(width=width, seed=1)
-    rays_o, rays_d, rgb, depth = sc.sample_batch(s, list(range(frames)), rays, seed=5)
-    depth = depth * (1.0 + 0.01 * torch.randn(depth.shape, generator=torch.Generator().manual_seed(4)))
-    rays_o.requires_grad_(True)
-    rays_d.requires_grad_(True)
-    inv = util.device_rcp(rays_d.detach().reshape(-1, 3), device)
-    gen = torch.Generator().manual_seed(11)
-    out, loss, parts = util.oracle_step(rays_o, rays_d, rgb, depth, ms, dec, voxel_size=s.voxel_size, tracking=tracking,
-                                        inv_dir=inv, generator=gen)
+    dec = util.test_decoder(width=width, seed=1)
+    # The losses are discontinuous at decision boundaries (util.decision_margins); pick the first
+    # seeded batch on which no decision is within fp32 rounding of flipping.
+    for seed in range(5, 12):
+        rays_o, rays_d, rgb, depth = sc.sample_batch(s, list(range(frames)), rays, seed=seed)
+        depth = depth * (1.0 + 0.01 * torch.randn(depth.shape, generator=torch.Generator().manual_seed(4)))
+        rays_o.requires_grad_(True)
+        rays_d.requires_grad_(True)
+        inv = util.device_rcp(rays_d.detach().reshape(-1, 3), device)
+        gen = torch.Generator().manual_seed(11)
+        out, loss, parts = util.oracle_step(rays_o, rays_d, rgb, depth, ms, dec, voxel_size=s.voxel_size,
+                                            tracking=tracking, inv_dir=inv, generator=gen)
+        if util.margins_ok(util.decision_margins(out, rgb, depth, tracking)):
+            break
+    else:
+        pytest.fail("no seeded batch without a near-tie decision")
     noise = out["_dbg"]["noise"]
     noise_d = noise.reshape(-1, noise.shape[-1]).to(device).contiguous()
     msd = util.to_device(ms, device)

@@ -30,6 +30,18 @@ def golden_decoder(g, device="cpu", requires_grad=True):
     return [torch.from_numpy(g[f"dec_{i}"]).to(device).requires_grad_(requires_grad) for i in range(10)]
 
 
+def test_decoder(width=128, seed=1, sdf_gain=50.0):
+    """Random decoder whose sdf head is scaled up so that |sdf| is ~1e-2 like a trained field, not
+    ~1e-4: with the default init thousands of samples sit within fp32 rounding of sdf = 0 and the
+    reference's first-sign-change decision is a coin toss there."""
+    from oracle import render_oracle as ro
+    dec = ro.decoder_params(width=width, seed=seed)
+    with torch.no_grad():
+        dec[4][0].mul_(sdf_gain)
+        dec[5][0] = dec[5][0] * sdf_gain
+    return dec
+
+
 def build_scene(kind="tiny", num_embeddings=None, seed=0, emb_scale=None):
     """(scene, map_states on CPU) through the ORACLE octree."""
     s = sc.make_scene(kind, seed=seed)
@@ -85,3 +97,113 @@ def device_rcp(x, device):
     out = torch.empty_like(xin)
     _lib.check(_lib.lib().pslam_debug_rcp(_lib.ptr(xin), _lib.ptr(out), xin.numel(), _lib.stream_ptr(device)), "rcp")
     return out.cpu().numpy()
+
+
+def decision_margins(out, rgb, depth, tracking=False, truncation=0.1):
+    """The reference's losses are discontinuous where a sign or mask decision flips (first sdf sign
+    change, sign(pred - gt) of the L1 terms, the tracking median gate).  Returns how far the oracle's
+    values are from each decision boundary, so that tests only compare cases where an fp32 rounding
+    difference cannot flip a decision."""
+    mask = out["_dbg"]["sample_mask"]
+    sdf = out["sdf"].detach()
+    ray_mask = out["ray_mask"].view(-1)
+    gt_d = depth.reshape(-1)[ray_mask]
+    gt_c = rgb.reshape(-1, 3)[ray_mask]
+    # only samples up to (and including) the first sign change decide `ind`
+    signs = (sdf[:, 1:] * sdf[:, :-1] < 0).float()
+    has = signs.sum(-1) > 0
+    ind = torch.where(has, signs.argmax(1), torch.full_like(signs.argmax(1), sdf.shape[1] - 1))
+    k = torch.arange(sdf.shape[1])[None, :]
+    relevant = mask & (k <= ind[:, None] + 1)
+    m = {
+        "sdf": float(sdf[relevant].abs().min()),
+        "depth": float((out["depth"].detach() - gt_d).abs().min()),
+        "color": float((out["color"].detach() - gt_c).abs().min()),
+    }
+    if tracking:
+        z, w, pd = out["z_vals"], out["weights"].detach(), out["depth"].detach()
+        var = torch.sum(w * (pd.unsqueeze(-1) - z) ** 2, -1)
+        tmp = (gt_d - pd).abs() / torch.sqrt(var + 1e-10)
+        thr = 10 * tmp.median()
+        m["gate"] = float(((tmp - thr).abs() / thr).min())
+    return m
+
+
+def margins_ok(m):
+    # a few times the fp32 rounding noise of each quantity (sdf ~1e-3, depth ~1, colour ~0.5)
+    return m["sdf"] > 2e-7 and m["depth"] > 2e-6 and m["color"] > 1e-6 and m.get("gate", 1.0) > 1e-4
+
+
+# ---------------------------------------------------------------- multi-rank loss closure (checker)
+RAW = dict(COLOR=0, FS=1, SDF=2, D0=3, D1=4, NFS=5, F0=6, F1=7, NSDF=8, M0=9, M1=10, RH=11, DEPTH=12, NVALID=13, S=14, THRESH=15)
+
+
+def raw_loss_sums(out, rgb, depth, truncation=0.1, max_depth=10.0):
+    """This shard's raw loss sums in the slot layout of csrc/composite.cu (RAW_*), from oracle outputs."""
+    mask = out["_dbg"]["sample_mask"]
+    ray_mask = out["ray_mask"].view(-1)
+    gt = depth.reshape(-1)[ray_mask].double()
+    gc = rgb.reshape(-1, 3)[ray_mask].double()
+    z, s = out["z_vals"].double(), out["sdf"].detach().double()
+    cnt = mask.sum(-1).double()
+    d = gt[:, None]
+    front = (z < d - truncation) & mask
+    back = (z > d + truncation)
+    dm = ((d > 0) & (d < max_depth))
+    sm = (~(z < d - truncation)) & (~back) & dm & mask
+    pad_front = (10.0 < gt - truncation)
+    pad_sm = (~pad_front) & (~(10.0 > gt + truncation)) & (gt > 0) & (gt < max_depth)
+    pad_d2 = (10.0 + truncation - gt) ** 2
+    valid = (gt > 0.01) & (gt < max_depth)
+    r = torch.zeros(16, dtype=torch.float64)
+    r[RAW["COLOR"]] = (gc - out["color"].detach().double()).abs().sum()
+    r[RAW["FS"]] = (((s - 1.0) ** 2) * front).sum()
+    r[RAW["SDF"]] = (((z + s * truncation - d) ** 2) * sm).sum()
+    r[RAW["D0"]] = (pad_d2 * pad_sm).sum()
+    r[RAW["D1"]] = (pad_d2 * pad_sm * cnt).sum()
+    r[RAW["NFS"]] = front.sum()
+    r[RAW["F0"]] = pad_front.sum()
+    r[RAW["F1"]] = (pad_front * cnt).sum()
+    r[RAW["NSDF"]] = sm.sum()
+    r[RAW["M0"]] = pad_sm.sum()
+    r[RAW["M1"]] = (pad_sm * cnt).sum()
+    r[RAW["RH"]] = float(ray_mask.sum())
+    r[RAW["DEPTH"]] = ((gt - out["depth"].detach().double()).abs() * valid).sum()
+    r[RAW["NVALID"]] = valid.sum()
+    r[RAW["S"]] = float(z.shape[1])
+    r[RAW["THRESH"]] = float("inf")
+    return r
+
+
+def close_loss(rows, weights, truncation=0.1):
+    """Restatement of k_loss_coeffs: all ranks' raw sums -> (loss dict, coefficient dict)."""
+    t = rows[:, :RAW["S"]].sum(0)
+    S = rows[:, RAW["S"]].max()
+    w_rgb, w_depth, w_fs, w_sdf = weights
+    Rh = t[RAW["RH"]]
+    n = Rh * S
+    nfs = t[RAW["NFS"]] + S * t[RAW["F0"]] - t[RAW["F1"]]
+    nsdf = t[RAW["NSDF"]] + S * t[RAW["M0"]] - t[RAW["M1"]]
+    sdf_sum = t[RAW["SDF"]] + S * t[RAW["D0"]] - t[RAW["D1"]]
+    fs_w, sdf_w = 1 - nfs / (nfs + nsdf), 1 - nsdf / (nfs + nsdf)
+    parts = dict(color_loss=t[RAW["COLOR"]] / (3 * Rh), depth_loss=t[RAW["DEPTH"]] / t[RAW["NVALID"]],
+                 fs_loss=t[RAW["FS"]] / n * fs_w, sdf_loss=sdf_sum / n * sdf_w)
+    parts["loss"] = (w_rgb * parts["color_loss"] + w_depth * parts["depth_loss"] + w_fs * parts["fs_loss"]
+                     + w_sdf * parts["sdf_loss"])
+    coef = dict(color=w_rgb / (3 * Rh), depth=w_depth / t[RAW["NVALID"]], fs=w_fs * fs_w / n, sdf=w_sdf * sdf_w / n)
+    return {k: float(v) for k, v in parts.items()}, {k: float(v) for k, v in coef.items()}
+
+
+def concat_outputs(outs):
+    """Pads the shards' oracle outputs to the common S and concatenates them (what one big padded
+    batch of the reference would hold: z pad 10, sdf pad 1, weight pad 0)."""
+    S = max(o["z_vals"].shape[1] for o in outs)
+    padc = lambda t, v: torch.cat([t, t.new_full((t.shape[0], S - t.shape[1]), v)], 1)
+    return {
+        "z_vals": torch.cat([padc(o["z_vals"], 10.0) for o in outs]),
+        "sdf": torch.cat([padc(o["sdf"], 1.0) for o in outs]),
+        "weights": torch.cat([padc(o["weights"], 0.0) for o in outs]),
+        "color": torch.cat([o["color"] for o in outs]),
+        "depth": torch.cat([o["depth"] for o in outs]),
+        "ray_mask": torch.cat([o["ray_mask"].view(-1) for o in outs]).view(1, -1),
+    }
