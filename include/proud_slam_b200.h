@@ -39,6 +39,10 @@ const char *pslam_last_error(void);
 /* Device properties the host side sizes grids with: out[0]=SM count,
  * out[1]=compute capability*10, out[2]=max opt-in smem per block. */
 int pslam_device_info(int *out3);
+/* Process-wide configuration.  PSLAM_OPT_DECODER: 0 = decoder on the tcgen05 tensor cores where
+ * available (width 128; 3xTF32 operand splitting, fp32-equivalent), 1 = always the fp32 SIMT build. */
+#define PSLAM_OPT_DECODER 1
+int pslam_set_option(int key, int value);
 
 /* ------------------------------------------------------------------------
  * `grid` module, third_party/sparse_voxels/src/binding.cpp:12-20
@@ -103,6 +107,9 @@ int pslam_uniform_ray_sampling(int b, int num_rays, int max_hits, int max_steps,
  * slab test uses (intersect_gpu.cu:91-101), so a CPU oracle can be compared
  * bit for bit. */
 int pslam_debug_rcp(const float *in, float *out, int n, pslam_stream_t stream);
+/* Test helper: D[128,N] = A[128,K] * B[N,K]^T on one CTA through the same tcgen05 / tensor-memory
+ * primitives the decoder uses (split3 != 0: 3xTF32).  N in 16..144 step 16, K in 8..144 step 8. */
+int pslam_debug_umma_gemm(const float *A, const float *B, float *D, int N, int K, int split3, pslam_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * Torch-level stages of render_rays (src/variations/render_helpers.py)

@@ -40,6 +40,9 @@ int num_sms()
     return cached[dev];
 }
 
+static int g_decoder_mode = 0;
+int decoder_mode() { return g_decoder_mode; }
+
 static int check_render(const pslam_render_t *p)
 {
     PSLAM_CHECK_ARG(p, PSLAM_E_ARG, "null pslam_render_t");
@@ -83,6 +86,13 @@ static int check_render_field(const pslam_render_t *p, bool backward)
 using namespace pslam;
 
 extern "C" int pslam_abi_version(void) { return PSLAM_ABI_VERSION; }
+
+extern "C" int pslam_set_option(int key, int value)
+{
+    if (key == PSLAM_OPT_DECODER && (value == 0 || value == 1)) { g_decoder_mode = value; return 0; }
+    set_error("unknown option %d=%d", key, value);
+    return PSLAM_E_ARG;
+}
 extern "C" const char *pslam_last_error(void) { return g_error; }
 
 extern "C" int pslam_device_info(int *out3)

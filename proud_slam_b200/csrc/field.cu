@@ -19,6 +19,7 @@
 // is aggregated over runs of consecutive samples that share a voxel before it is sent to
 // L2 as red.global.add.v4.f32.
 #include "common.cuh"
+#include "field.cuh"
 #include "kernels.h"
 
 namespace pslam {
@@ -52,34 +53,7 @@ struct FieldCfg {
     static constexpr size_t SMEM = sizeof(float) * FLOATS;
     // packed transposed weights (floats)
     static constexpr int wW1t = 0, wW2t = 16 * W, wW3t = 16 * W + W * W, wW4t = 16 * W + W * W + 128 * W;
-    static constexpr int WS = W * W + 288 * W;
-};
-
-struct FieldParams {
-    int nsamp;               // static sample count, or
-    const int *nsamp_dev;    // device-side count (pipeline)
-    // gather source (feat == nullptr)
-    const float *rays_o, *rays_d;   // [R,3]
-    const int *hit_ray;             // rank -> ray id
-    const int *samp_ray, *samp_vox; // [P]
-    const float *samp_z;            // [P]
-    const float *centres;           // [N,3]
-    const int *vertex_idx;          // [N,8]
-    const float *emb;               // [E,16]
-    float voxel_size;
-    // direct feature source (standalone decoder)
-    const float *feat;              // [P,16]
-    // decoder
-    pslam_decoder_t dec;
-    const float *ws;                // packed transposed weights
-    float *out;                     // [P,4]
-    // backward
-    const float *g_out;             // [P,4]
-    float *g_feat;                  // [P,16] (standalone) or nullptr
-    pslam_decoder_grad_t g_dec;
-    float *g_emb;                   // [E,16] +=
-    float *g_rays_o, *g_rays_d;     // [R,3] += (pipeline zeroes them first)
-    int grad_dec, grad_emb, grad_rays;
+    static constexpr int WS = W * W + 288 * W;             // floats of the SIMT pack; the tcgen05 stream follows it
 };
 
 // ------------------------------------------------------------------------------------------
@@ -745,11 +719,14 @@ static int pack_decoder(const pslam_decoder_t &d, float *ws, cudaStream_t st)
     if (d.width == 128) k_pack_decoder<128><<<ceil_div(FieldCfg<128>::WS, 256), 256, 0, st>>>(d, ws);
     else k_pack_decoder<256><<<ceil_div(FieldCfg<256>::WS, 256), 256, 0, st>>>(d, ws);
     PSLAM_CHECK_LAUNCH("pack_decoder");
+    if (d.width == 128 && decoder_mode() == 0) return tc_pack_decoder(d, ws + FieldCfg<128>::WS, st);
     return 0;
 }
+static const float *tc_region(const pslam_decoder_t &d, const float *ws) { return d.width == 128 ? ws + FieldCfg<128>::WS : nullptr; }
 
 static int launch_field(const FieldParams &fp, bool bwd, int max_samples, cudaStream_t st)
 {
+    if (!bwd && fp.dec.width == 128 && decoder_mode() == 0) return tc_launch_field_forward(fp, max_samples, st);
     if (fp.dec.width == 128) return bwd ? launch_field_t<128, true>(fp, max_samples, st) : launch_field_t<128, false>(fp, max_samples, st);
     return bwd ? launch_field_t<256, true>(fp, max_samples, st) : launch_field_t<256, false>(fp, max_samples, st);
 }
@@ -761,7 +738,7 @@ static FieldParams params_from_render(const pslam_render_t *p)
     fp.rays_o = p->rays_o; fp.rays_d = p->rays_d; fp.hit_ray = p->hit_ray;
     fp.samp_ray = p->samp_ray; fp.samp_vox = p->samp_vox; fp.samp_z = p->samp_z;
     fp.centres = p->centres; fp.vertex_idx = p->vertex_idx; fp.emb = p->emb; fp.voxel_size = p->voxel_size;
-    fp.feat = nullptr; fp.dec = p->dec; fp.ws = p->dec_ws; fp.out = p->samp_out;
+    fp.feat = nullptr; fp.dec = p->dec; fp.ws = p->dec_ws; fp.ws_tc = tc_region(p->dec, p->dec_ws); fp.out = p->samp_out;
     fp.g_out = p->samp_gout; fp.g_feat = nullptr; fp.g_dec = p->g_dec; fp.g_emb = p->g_emb;
     fp.g_rays_o = p->g_rays_o; fp.g_rays_d = p->g_rays_d;
     fp.grad_dec = (p->flags & PSLAM_F_GRAD_DEC) ? 1 : 0;
@@ -799,7 +776,7 @@ static int check_decoder(const pslam_decoder_t *dec)
 
 extern "C" int64_t pslam_decoder_ws_count(int width)
 {
-    return width == 128 ? FieldCfg<128>::WS : width == 256 ? FieldCfg<256>::WS : -1;
+    return width == 128 ? FieldCfg<128>::WS + kTcPackFloats : width == 256 ? FieldCfg<256>::WS : -1;
 }
 
 extern "C" int pslam_trilinear_fwd(int np, const float *xyz, const int *vox_idx, const float *centres, const int *vertex_idx,
@@ -835,7 +812,7 @@ extern "C" int pslam_decoder_fwd(int np, const pslam_decoder_t *dec, const float
     PSLAM_CHECK_ARG(((uintptr_t)ws | (uintptr_t)out) % 16 == 0, PSLAM_E_ALIGN, "ws/out must be 16-byte aligned");
     if (int rc = pack_decoder(*dec, ws, (cudaStream_t)stream)) return rc;
     FieldParams fp{};
-    fp.nsamp = np; fp.feat = feat; fp.dec = *dec; fp.ws = ws; fp.out = out;
+    fp.nsamp = np; fp.feat = feat; fp.dec = *dec; fp.ws = ws; fp.ws_tc = tc_region(*dec, ws); fp.out = out;
     return launch_field(fp, false, np, (cudaStream_t)stream);
 }
 
@@ -851,7 +828,7 @@ extern "C" int pslam_decoder_bwd(int np, const pslam_decoder_t *dec, const float
                         PSLAM_E_ARG, "decoder_bwd: null gradient pointer");
     if (int rc = pack_decoder(*dec, ws, (cudaStream_t)stream)) return rc;
     FieldParams fp{};
-    fp.nsamp = np; fp.feat = feat; fp.dec = *dec; fp.ws = ws; fp.g_out = g_out; fp.g_feat = g_feat;
+    fp.nsamp = np; fp.feat = feat; fp.dec = *dec; fp.ws = ws; fp.ws_tc = tc_region(*dec, ws); fp.g_out = g_out; fp.g_feat = g_feat;
     if (grad) { fp.g_dec = *grad; fp.grad_dec = 1; }
     return launch_field(fp, true, np, (cudaStream_t)stream);
 }

@@ -1,0 +1,44 @@
+// Argument block shared by the decoder/field kernels (SIMT build in field.cu, tcgen05 build in
+// field_tc.cu).
+#pragma once
+#include "common.cuh"
+
+namespace pslam {
+
+struct FieldParams {
+    int nsamp;               // static sample count, or
+    const int *nsamp_dev;    // device-side count (pipeline)
+    // gather source (feat == nullptr)
+    const float *rays_o, *rays_d;   // [R,3]
+    const int *hit_ray;             // rank -> ray id
+    const int *samp_ray, *samp_vox; // [P]
+    const float *samp_z;            // [P]
+    const float *centres;           // [N,3]
+    const int *vertex_idx;          // [N,8]
+    const float *emb;               // [E,16]
+    float voxel_size;
+    // direct feature source (standalone decoder)
+    const float *feat;              // [P,16]
+    // decoder
+    pslam_decoder_t dec;
+    const float *ws;                // packed transposed weights (SIMT build)
+    const float *ws_tc;             // weight stream in UMMA operand order (tcgen05 build)
+    float *out;                     // [P,4]
+    // backward
+    const float *g_out;             // [P,4]
+    float *g_feat;                  // [P,16] (standalone) or nullptr
+    pslam_decoder_grad_t g_dec;
+    float *g_emb;                   // [E,16] +=
+    float *g_rays_o, *g_rays_d;     // [R,3] += (pipeline zeroes them first)
+    int grad_dec, grad_emb, grad_rays;
+};
+
+
+// field_tc.cu: tcgen05 build of the width-128 decoder (3xTF32, fp32-equivalent accuracy)
+constexpr int kTcPackFloats = 114688;   // forward weight stream in UMMA operand order (hi, lo)
+// decoder build selection: 0 = tcgen05 where available (width 128), 1 = always the fp32 SIMT build
+int decoder_mode();
+int tc_pack_decoder(const pslam_decoder_t &d, float *ws_tc, cudaStream_t st);
+int tc_launch_field_forward(const FieldParams &fp, int max_samples, cudaStream_t st);
+
+}  // namespace pslam

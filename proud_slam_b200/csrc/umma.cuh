@@ -1,0 +1,143 @@
+// Thin inline-PTX layer over the sm_100a tensor-core machinery used by the decoder kernels:
+// tcgen05.mma (kind::tf32, A from tensor memory, B from shared memory), tensor-memory
+// allocation / load / store, mbarriers and 1-D bulk (TMA) copies.  Nothing here is generic:
+// it encodes exactly the operand layouts field_tc.cu uses.
+//
+//   * B operand (weights): K-major, no swizzle.  A tile of ROWS x 16 tf32 values is stored as
+//     four 16-byte k-chunks, each holding all rows contiguously (row stride 16 B):
+//         byte(row, k) = (k / 4) * ROWS * 16 + row * 16 + (k % 4) * 4
+//     i.e. 8 x 16 B core matrices, stride-byte-offset 128 B between 8-row groups and
+//     leading-byte-offset ROWS * 16 B between k-chunks.  One MMA consumes K = 8 (two chunks).
+//   * A operand (activations) and D (accumulators): tensor memory, lane = sample row,
+//     one 32-bit column per element.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pslam {
+namespace umma {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier -----------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {}
+}
+
+// ---- 1-D bulk copy global -> shared, completion on an mbarrier (TMA engine, no tensor map) ---
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---- tensor memory ------------------------------------------------------------------------
+// whole-warp calls
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// 32 lanes x 16 consecutive 32-bit columns: thread i of the warp gets lane (base lane + i)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+
+// ---- tcgen05.mma --------------------------------------------------------------------------
+// instruction descriptor, kind::tf32, fp32 accumulate, both operands K-major (cute InstrDescriptor):
+//   [4,6) c_format = 1 (F32)  [7,10) a_format = 2 (TF32)  [10,13) b_format = 2  [17,23) N>>3  [24,29) M>>4
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N)
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// shared-memory matrix descriptor for the B layout described at the top of this file
+__device__ __forceinline__ uint64_t bdesc_kmajor(uint32_t smem_addr, uint32_t rows)
+{
+    const uint64_t start = (smem_addr & 0x3FFFFu) >> 4;
+    const uint64_t lbo = (uint64_t)(rows * 16u) >> 4;   // between the two k-chunks of one MMA
+    const uint64_t sbo = 128u >> 4;                     // between 8-row groups
+    return start | (lbo << 16) | (sbo << 32) | (1ull << 46);   // bit 46: descriptor version 1 (sm_100)
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T, issued by ONE thread
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+// all MMAs issued so far by this thread arrive on `bar` when they complete
+__device__ __forceinline__ void mma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- 3xTF32 operand split ------------------------------------------------------------------
+// x = hi + lo with hi = rn_tf32(x) (low 13 mantissa bits zero) and lo = rn_tf32(x - hi);
+// a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi with ~2^-22 relative error, fp32-accumulated.
+__device__ __forceinline__ uint32_t tf32_rn(float x)
+{
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void tf32_split(float x, uint32_t &hi, uint32_t &lo)
+{
+    hi = tf32_rn(x);
+    lo = tf32_rn(x - __uint_as_float(hi));
+}
+
+}  // namespace umma
+}  // namespace pslam

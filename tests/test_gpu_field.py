@@ -87,3 +87,47 @@ def test_trilinear_forward_backward(n, device):
     torch.cuda.synchronize()
     assert rel_err(g_emb, ms["voxel_vertex_emb"].grad) < TOL
     assert rel_err(g_xyz, xyz.grad) < TOL
+
+
+@pytest.mark.parametrize("N,K", [(16, 8), (128, 16), (128, 128), (144, 128), (128, 144), (16, 128)])
+@pytest.mark.parametrize("split3", [0, 1])
+def test_umma_gemm_primitives(N, K, split3, device):
+    """tcgen05.mma (A from tensor memory, B through a shared-memory descriptor), TMEM ld/st and the
+    operand layouts of csrc/umma.cuh, against an fp64 matmul.  1xTF32 ~1e-3, 3xTF32 ~fp32."""
+    g = torch.Generator().manual_seed(N * 1000 + K)
+    A = torch.randn(128, K, generator=g)
+    B = torch.randn(N, K, generator=g)
+    ref = (A.double() @ B.double().t())
+    Ad, Bd = A.to(device), B.to(device)
+    D = torch.zeros(128, N, device=device)
+    _lib.check(_lib.lib().pslam_debug_umma_gemm(_lib.ptr(Ad), _lib.ptr(Bd), _lib.ptr(D), N, K, split3, _lib.stream_ptr(device)), "umma")
+    torch.cuda.synchronize()
+    err = rel_err(D, ref)
+    assert err < (2e-6 if split3 else 3e-3), err
+    if not split3:
+        assert err > 1e-6    # really went through TF32 tensor cores
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_decoder_forward_both_builds(mode, device):
+    """tcgen05 (3xTF32) and SIMT fp32 builds of the width-128 decoder agree with the oracle."""
+    import ctypes as C
+    from proud_slam_b200.pipeline import _decoder_struct
+    lib = _lib.lib()
+    try:
+        _lib.check(lib.pslam_set_option(1, mode), "set_option")
+        dec = ro.decoder_params(width=128, seed=4)
+        n = 5000
+        feat = torch.randn(n, 16, generator=torch.Generator().manual_seed(1)) * 0.05
+        rgb, sdf = ro.decoder_forward([p.detach() for p in dec], feat)
+        decd = [p.detach().to(device) for p in dec]
+        ws = torch.empty(int(lib.pslam_decoder_ws_count(128)), device=device)
+        out = torch.empty(n, 4, device=device)
+        ds = _decoder_struct(decd)
+        featd = feat.to(device)
+        _lib.check(lib.pslam_decoder_fwd(n, C.byref(ds), _lib.ptr(featd), _lib.ptr(ws), _lib.ptr(out), _lib.stream_ptr(device)), "fwd")
+        torch.cuda.synchronize()
+        assert rel_err(out[:, :3], rgb) < 1e-5
+        assert rel_err(out[:, 3], sdf) < 1e-5
+    finally:
+        lib.pslam_set_option(1, 0)
