@@ -70,68 +70,99 @@ def test_step_matches_reference_golden(name, device):
     assert rel_err(pipe.g_rays_d[:R], g["g_rays_d"].reshape(-1, 3)) < TOL
 
 
+@pytest.mark.parametrize("decoder_build", ["tcgen05", "simt"])
 @pytest.mark.parametrize("kind,frames,rays,tracking,width", [
     ("tiny", 2, 300, False, 128),
     ("replica_small", 2, 1024, False, 128),       # BASELINE.json configs[0]: 2048 rays on the 0.2 m octree
     ("replica_small", 1, 1024, True, 128),        # configs[2]: one tracking iteration
     ("replica_small", 2, 256, False, 256),
 ])
-def test_step_matches_oracle(kind, frames, rays, tracking, width, device):
-    from oracle import render_oracle as ro
-    from proud_slam_b200 import scene as sc
+def test_step_matches_oracle(kind, frames, rays, tracking, width, decoder_build, device):
+    """Whole iteration against the oracle, stage by stage on identical inputs.
+
+    The reference's compositing and losses contain hard decisions (first sdf sign change along the
+    ray, z < z_min + tau, sign(pred - gt), the tracking median gate).  An fp32 rounding difference in
+    one sdf value near zero flips such a decision and legitimately changes that ray's result, so an
+    end-to-end comparison is only meaningful where no decision is near a tie (the golden-fixture
+    test above).  Here every stage is instead compared on bit-identical inputs:
+      1. hit lists, sample ids/depths: bit-exact;
+      2. per-sample decoder outputs (continuous in its inputs): 1e-4;
+      3. compositing + losses + dL/d(sample outputs) evaluated by the oracle ON THE GPU'S OWN
+         per-sample outputs: identical decisions, 1e-4;
+      4. field backward (decoder dgrad/wgrad, embedding scatter, ray gradients) of the oracle fed
+         with the GPU's dL/d(sample outputs): 1e-4.
+    """
+    from proud_slam_b200 import _lib, scene as sc
+    if width == 256 and decoder_build == "tcgen05":
+        pytest.skip("width 256 always runs the SIMT build")
     s, ms = util.build_scene(kind)
     dec = util.test_decoder(width=width, seed=1)
-    # The losses are discontinuous at decision boundaries (util.decision_margins); pick the first
-    # seeded batch on which no decision is within fp32 rounding of flipping.
-    for seed in range(5, 12):
-        rays_o, rays_d, rgb, depth = sc.sample_batch(s, list(range(frames)), rays, seed=seed)
-        depth = depth * (1.0 + 0.01 * torch.randn(depth.shape, generator=torch.Generator().manual_seed(4)))
-        rays_o.requires_grad_(True)
-        rays_d.requires_grad_(True)
-        inv = util.device_rcp(rays_d.detach().reshape(-1, 3), device)
-        gen = torch.Generator().manual_seed(11)
-        out, loss, parts = util.oracle_step(rays_o, rays_d, rgb, depth, ms, dec, voxel_size=s.voxel_size,
-                                            tracking=tracking, inv_dir=inv, generator=gen)
-        if util.margins_ok(util.decision_margins(out, rgb, depth, tracking)):
-            break
-    else:
-        pytest.fail("no seeded batch without a near-tie decision")
+    rays_o, rays_d, rgb, depth = sc.sample_batch(s, list(range(frames)), rays, seed=5)
+    depth = depth * (1.0 + 0.01 * torch.randn(depth.shape, generator=torch.Generator().manual_seed(4)))
+    rays_o.requires_grad_(True)
+    rays_d.requires_grad_(True)
+    inv = util.device_rcp(rays_d.detach().reshape(-1, 3), device)
+    from oracle import render_oracle as ro
+    out = ro.render_rays(rays_o, rays_d, ms, dec, 0.1 * s.voxel_size, s.voxel_size, util.CRIT["truncation"], 10, 10.0,
+                         generator=torch.Generator().manual_seed(11), inv_dir=inv)
     noise = out["_dbg"]["noise"]
     noise_d = noise.reshape(-1, noise.shape[-1]).to(device).contiguous()
     msd = util.to_device(ms, device)
     msd["voxel_vertex_emb"] = msd["voxel_vertex_emb"].detach()
     decd = [p.detach().to(device) for p in dec]
     cw = (util.CRIT["rgb_weight"], util.CRIT["depth_weight"], util.CRIT["fs_weight"], util.CRIT["sdf_weight"])
-    pipe, g_emb, g_dec = _run_pipeline(
-        device, rays_o.detach().to(device), rays_d.detach().to(device), rgb.to(device), depth.to(device), msd, decd,
-        voxel_size=s.voxel_size, step_size=0.1 * s.voxel_size, truncation=util.CRIT["truncation"], max_distance=10.0,
-        max_depth=util.CRIT["max_depth"], weights=cw, noise=noise_d, tracking=tracking)
+    lib = _lib.lib()
+    try:
+        _lib.check(lib.pslam_set_option(1, 0 if decoder_build == "tcgen05" else 1), "set_option")
+        pipe, g_emb, g_dec = _run_pipeline(
+            device, rays_o.detach().to(device), rays_d.detach().to(device), rgb.to(device), depth.to(device), msd, decd,
+            voxel_size=s.voxel_size, step_size=0.1 * s.voxel_size, truncation=util.CRIT["truncation"], max_distance=10.0,
+            max_depth=util.CRIT["max_depth"], weights=cw, noise=noise_d, tracking=tracking)
+    finally:
+        lib.pslam_set_option(1, 0)
+    # ---- 1. bit-exact hit lists and samples
     inter, hits = pipe.intersections()
     hit_rows = hits.view(-1).cpu()
     ref_inter = out["_dbg"]["intersections"]
-    # bit-exact hit lists (ids AND depths: the oracle was fed the device's own reciprocals)
     assert np.array_equal(hit_rows.numpy(), out["ray_mask"].view(-1).numpy())
     for k in ("intersected_voxel_idx", "min_depth", "max_depth"):
         assert torch.equal(inter[k][0].cpu()[hit_rows], ref_inter[k]), k
-    # bit-exact sample indices; depths to 1 ulp-ish (FMA contraction is pinned, so expect equality)
     smp = pipe.samples()
     ref_s = out["_dbg"]["samples"]
     assert torch.equal(smp["sampled_point_voxel_idx"].cpu(), ref_s["sampled_point_voxel_idx"])
     assert torch.equal(smp["sampled_point_depth"].cpu(), ref_s["sampled_point_depth"])
     assert torch.equal(smp["sampled_point_distance"].cpu(), ref_s["sampled_point_distance"])
+    # ---- 2. per-sample decoder outputs
+    P = pipe.counts()["n_samples"]
+    assert P == int(out["_dbg"]["sample_mask"].sum())
+    so = pipe.samp_out[:P].cpu()
+    assert rel_err(so[:, :3], out["_dbg"]["rgb_p"].detach()) < TOL
+    assert rel_err(so[:, 3], out["_dbg"]["sdf_p"].detach()) < TOL
+    # ---- 3. compositing + losses on the GPU's own sample outputs
+    sdf_p = so[:, 3].clone().requires_grad_(True)
+    rgb_p = so[:, :3].clone().requires_grad_(True)
+    res, loss, parts = util.oracle_composite(out, sdf_p, rgb_p, rgb, depth, tracking)
+    loss.backward()
     o = pipe.outputs()
-    for k in ("sdf", "color", "depth", "weights"):
-        assert rel_err(o[k], out[k].detach()) < TOL, k
+    for k in ("sdf", "color", "depth", "weights", "raw"):
+        assert rel_err(o[k], res[k].detach()) < TOL, k
     l = pipe.losses()
     assert abs(l["loss"] - float(loss)) <= TOL * abs(float(loss))
     for k in ("color_loss", "depth_loss", "fs_loss", "sdf_loss"):
         assert abs(l[k] - float(parts[k])) <= TOL * max(abs(float(parts[k])), 1e-12), k
-    assert rel_err(g_emb, ms["voxel_vertex_emb"].grad) < TOL
-    for i in range(10):
-        assert rel_err(g_dec[i], dec[i].grad) < TOL, f"decoder grad {i}"
+    g_so = pipe.samp_gout[:P].cpu()
+    assert rel_err(g_so[:, :3], rgb_p.grad) < TOL
+    assert rel_err(g_so[:, 3], sdf_p.grad) < TOL
+    # ---- 4. field backward fed with the GPU's upstream gradient
+    rgb_o, sdf_o = util.oracle_field(out, rays_o, rays_d, ms, dec, s.voxel_size)
+    params = [ms["voxel_vertex_emb"], rays_o, rays_d] + list(dec)
+    grads = torch.autograd.grad((rgb_o * g_so[:, :3]).sum() + (sdf_o * g_so[:, 3]).sum(), params)
+    assert rel_err(g_emb, grads[0]) < TOL
     R = rays_o.shape[1]
-    assert rel_err(pipe.g_rays_o[:R], rays_o.grad.reshape(-1, 3)) < TOL
-    assert rel_err(pipe.g_rays_d[:R], rays_d.grad.reshape(-1, 3)) < TOL
+    assert rel_err(pipe.g_rays_o[:R], grads[1].reshape(-1, 3)) < TOL
+    assert rel_err(pipe.g_rays_d[:R], grads[2].reshape(-1, 3)) < TOL
+    for i in range(10):
+        assert rel_err(g_dec[i], grads[3 + i]) < TOL, f"decoder grad {i}"
 
 
 def test_hash_noise_is_in_range_and_deterministic(device):

@@ -207,3 +207,40 @@ def concat_outputs(outs):
         "depth": torch.cat([o["depth"] for o in outs]),
         "ray_mask": torch.cat([o["ray_mask"].view(-1) for o in outs]).view(1, -1),
     }
+
+
+# ---------------------------------------------------------------- staged parity (decision-proof)
+def oracle_composite(out, sdf_p, rgb_p, rgb, depth, tracking=False):
+    """Compositing + Criterion of the oracle evaluated on GIVEN per-sample decoder outputs
+    (sdf_p [P], rgb_p [P,3], leaf tensors).  Used to check kernel 5 on bit-identical inputs: the
+    first-sign-change / mask / sign() decisions of the reference are discontinuous, so they are
+    only comparable when both sides see the same sdf bits."""
+    smask = out["_dbg"]["sample_mask"]
+    z = out["z_vals"]
+    sdf = torch.ones_like(z).masked_scatter(smask, sdf_p)
+    colour = z.new_zeros(*z.shape, 3).masked_scatter(smask.unsqueeze(-1).expand(*z.shape, 3), rgb_p)
+    weights, z_min = ro.sdf2weights(sdf, z, smask.to(z.dtype), CRIT["truncation"])
+    res = {"weights": weights, "color": torch.sum(weights[..., None] * colour, dim=-2),
+           "depth": torch.sum(weights * z, dim=-1), "z_vals": z, "sdf": sdf, "ray_mask": out["ray_mask"], "raw": z_min}
+    kw = {k: CRIT[k] for k in ("rgb_weight", "depth_weight", "sdf_weight", "fs_weight", "truncation", "max_depth")}
+    if tracking:
+        r2 = dict(res)
+        r2["ray_mask"] = res["ray_mask"].view(-1)
+        loss, parts = ro.criterion(r2, (rgb[0], depth[0]), weight_depth_loss=True, **kw)
+    else:
+        loss, parts = ro.criterion(res, (rgb, depth), **kw)
+    return res, loss, parts
+
+
+def oracle_field(out, rays_o, rays_d, ms, dec, voxel_size):
+    """Trilinear lookup + decoder of the oracle on the oracle's own samples: (rgb_p [P,3], sdf_p [P])
+    connected to rays_o / rays_d / embeddings / decoder parameters for autograd."""
+    smask = out["_dbg"]["sample_mask"]
+    rm = out["ray_mask"]
+    ro_ = rays_o[rm].reshape(-1, 3)
+    rd_ = rays_d[rm].reshape(-1, 3)
+    z = out["z_vals"]
+    xyz = ro_.unsqueeze(1) + rd_.unsqueeze(1) * z.unsqueeze(2)
+    sidx = out["_dbg"]["samples"]["sampled_point_voxel_idx"].long()
+    f = ro.get_features_vox(xyz[smask], sidx[smask], ms, voxel_size)
+    return ro.decoder_forward(dec, f)
