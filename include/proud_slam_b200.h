@@ -157,9 +157,13 @@ int pslam_decoder_fwd(int p, const pslam_decoder_t *dec, const float *feat,
                       float *ws, float *out, pslam_stream_t stream);
 /* Backward: g_out [p,4] -> g_feat [p,16] (may be NULL) and parameter
  * gradients (grad may be NULL).  Activations are recomputed, not stored. */
+/* wgrad_ws: pslam_wgrad_ws_bytes(p) bytes of scratch for the tensor-core weight-gradient kernel
+ * (width 128), or NULL to run the SIMT build when parameter gradients are requested. */
+int64_t pslam_wgrad_ws_bytes(int max_samples);
 int pslam_decoder_bwd(int p, const pslam_decoder_t *dec, const float *feat,
                       float *ws, const float *g_out, float *g_feat,
-                      const pslam_decoder_grad_t *grad, pslam_stream_t stream);
+                      const pslam_decoder_grad_t *grad, void *wgrad_ws, int64_t wgrad_ws_bytes,
+                      pslam_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * Fused render + loss + backward (one mapping / tracking iteration):
@@ -212,6 +216,8 @@ typedef struct {
     const float *emb;                      /* [E,16] voxel_vertex_emb */
     pslam_decoder_t dec;
     float *dec_ws;                         /* [pslam_decoder_ws_count(dec.width)] repacked weights */
+    void *wgrad_ws;                        /* pslam_wgrad_ws_bytes(sample_cap) bytes, or NULL (then SIMT wgrad) */
+    int64_t wgrad_ws_bytes;
     const float *noise;                    /* [>=R_h, noise_stride] uniform(0.001,0.999) or NULL */
     int noise_stride;
     uint64_t seed;                         /* counter-based noise when noise==NULL */

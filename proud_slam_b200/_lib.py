@@ -33,7 +33,8 @@ class RenderT(C.Structure):
                                     "w_rgb", "w_depth", "w_fs", "w_sdf")]
         + [(n, C.c_void_p) for n in ("rays_o", "rays_d", "target_rgb", "target_depth", "centres", "structure",
                                      "vertex_idx", "emb")]
-        + [("dec", DecoderT), ("dec_ws", C.c_void_p), ("noise", C.c_void_p), ("noise_stride", C.c_int),
+        + [("dec", DecoderT), ("dec_ws", C.c_void_p), ("wgrad_ws", C.c_void_p), ("wgrad_ws_bytes", C.c_int64),
+           ("noise", C.c_void_p), ("noise_stride", C.c_int),
            ("seed", C.c_uint64)]
         + [(n, C.c_void_p) for n in ("hit_idx", "hit_min", "hit_max", "hit_count", "hit_ray", "ray_rank",
                                      "samp_off", "samp_vox", "samp_ray", "samp_z", "samp_dist", "samp_out",
@@ -66,7 +67,8 @@ _PROTOTYPES = {
     "pslam_trilinear_fwd": (C.c_int, [_I, _P, _P, _P, _P, _P, _F, _P, _S]),
     "pslam_trilinear_bwd": (C.c_int, [_I, _P, _P, _P, _P, _P, _F, _P, _P, _P, _S]),
     "pslam_decoder_fwd": (C.c_int, [_I, C.POINTER(DecoderT), _P, _P, _P, _S]),
-    "pslam_decoder_bwd": (C.c_int, [_I, C.POINTER(DecoderT), _P, _P, _P, _P, C.POINTER(DecoderGradT), _S]),
+    "pslam_decoder_bwd": (C.c_int, [_I, C.POINTER(DecoderT), _P, _P, _P, _P, C.POINTER(DecoderGradT), _P, C.c_int64, _S]),
+    "pslam_wgrad_ws_bytes": (C.c_int64, [_I]),
     "pslam_render_sizeof": (C.c_int, []),
     "pslam_render_offsetof_loss": (C.c_int, []),
     "pslam_render_scratch_i_count": (C.c_int64, [_I]),

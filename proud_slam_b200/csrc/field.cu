@@ -726,7 +726,12 @@ static const float *tc_region(const pslam_decoder_t &d, const float *ws) { retur
 
 static int launch_field(const FieldParams &fp, bool bwd, int max_samples, cudaStream_t st)
 {
-    if (!bwd && fp.dec.width == 128 && decoder_mode() == 0) return tc_launch_field_forward(fp, max_samples, st);
+    if (fp.dec.width == 128 && decoder_mode() == 0) {
+        if (!bwd) return tc_launch_field_forward(fp, max_samples, st);
+        // tensor-core backward needs the wgrad scratch when decoder gradients are wanted
+        if (!fp.grad_dec || (fp.wg_scratch && fp.wg_scratch_bytes >= tc_wgrad_scratch_bytes(max_samples)))
+            return tc_launch_field_backward(fp, max_samples, st);
+    }
     if (fp.dec.width == 128) return bwd ? launch_field_t<128, true>(fp, max_samples, st) : launch_field_t<128, false>(fp, max_samples, st);
     return bwd ? launch_field_t<256, true>(fp, max_samples, st) : launch_field_t<256, false>(fp, max_samples, st);
 }
@@ -741,6 +746,7 @@ static FieldParams params_from_render(const pslam_render_t *p)
     fp.feat = nullptr; fp.dec = p->dec; fp.ws = p->dec_ws; fp.ws_tc = tc_region(p->dec, p->dec_ws); fp.out = p->samp_out;
     fp.g_out = p->samp_gout; fp.g_feat = nullptr; fp.g_dec = p->g_dec; fp.g_emb = p->g_emb;
     fp.g_rays_o = p->g_rays_o; fp.g_rays_d = p->g_rays_d;
+    fp.wg_scratch = static_cast<unsigned char *>(p->wgrad_ws); fp.wg_scratch_bytes = (size_t)p->wgrad_ws_bytes;
     fp.grad_dec = (p->flags & PSLAM_F_GRAD_DEC) ? 1 : 0;
     fp.grad_emb = (p->flags & PSLAM_F_GRAD_EMB) ? 1 : 0;
     fp.grad_rays = (p->flags & PSLAM_F_GRAD_RAYS) ? 1 : 0;
@@ -816,8 +822,10 @@ extern "C" int pslam_decoder_fwd(int np, const pslam_decoder_t *dec, const float
     return launch_field(fp, false, np, (cudaStream_t)stream);
 }
 
+extern "C" int64_t pslam_wgrad_ws_bytes(int max_samples) { return (int64_t)tc_wgrad_scratch_bytes(max_samples); }
+
 extern "C" int pslam_decoder_bwd(int np, const pslam_decoder_t *dec, const float *feat, float *ws, const float *g_out, float *g_feat,
-                                 const pslam_decoder_grad_t *grad, pslam_stream_t stream)
+                                 const pslam_decoder_grad_t *grad, void *wgrad_ws, int64_t wgrad_ws_bytes, pslam_stream_t stream)
 {
     if (int rc = check_decoder(dec)) return rc;
     if (np == 0) return 0;
@@ -830,5 +838,7 @@ extern "C" int pslam_decoder_bwd(int np, const pslam_decoder_t *dec, const float
     FieldParams fp{};
     fp.nsamp = np; fp.feat = feat; fp.dec = *dec; fp.ws = ws; fp.ws_tc = tc_region(*dec, ws); fp.g_out = g_out; fp.g_feat = g_feat;
     if (grad) { fp.g_dec = *grad; fp.grad_dec = 1; }
+    PSLAM_CHECK_ARG((uintptr_t)wgrad_ws % 16 == 0, PSLAM_E_ALIGN, "wgrad_ws must be 16-byte aligned");
+    fp.wg_scratch = static_cast<unsigned char *>(wgrad_ws); fp.wg_scratch_bytes = wgrad_ws ? (size_t)wgrad_ws_bytes : 0;
     return launch_field(fp, true, np, (cudaStream_t)stream);
 }

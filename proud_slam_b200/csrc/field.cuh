@@ -27,6 +27,8 @@ struct FieldParams {
     // backward
     const float *g_out;             // [P,4]
     float *g_feat;                  // [P,16] (standalone) or nullptr
+    unsigned char *wg_scratch;      // tcgen05 wgrad scratch (tc_wgrad_scratch_bytes) or nullptr
+    size_t wg_scratch_bytes;
     pslam_decoder_grad_t g_dec;
     float *g_emb;                   // [E,16] +=
     float *g_rays_o, *g_rays_d;     // [R,3] += (pipeline zeroes them first)
@@ -35,10 +37,12 @@ struct FieldParams {
 
 
 // field_tc.cu: tcgen05 build of the width-128 decoder (3xTF32, fp32-equivalent accuracy)
-constexpr int kTcPackFloats = 114688;   // forward weight stream in UMMA operand order (hi, lo)
+constexpr int kTcPackFloats = 229376;   // forward + dgrad weight streams in UMMA operand order (hi, lo)
 // decoder build selection: 0 = tcgen05 where available (width 128), 1 = always the fp32 SIMT build
 int decoder_mode();
 int tc_pack_decoder(const pslam_decoder_t &d, float *ws_tc, cudaStream_t st);
 int tc_launch_field_forward(const FieldParams &fp, int max_samples, cudaStream_t st);
+int tc_launch_field_backward(const FieldParams &fp, int max_samples, cudaStream_t st);
+size_t tc_wgrad_scratch_bytes(int max_samples);
 
 }  // namespace pslam

@@ -1,23 +1,27 @@
 // Kernel 4 on the 5th-generation tensor cores: the width-128 SDF/colour decoder
 // (src/variations/nrgbd.py:116-135) fused with the trilinear corner-embedding lookup
-// (src/variations/render_helpers.py:105-156, 47-59), forward pass.
+// (src/variations/render_helpers.py:105-156, 47-59), forward and backward.
 //
 // Design (sm_100a only):
 //   * tile = 128 samples = the 128 lanes of tensor memory; one persistent CTA per SM.
-//   * every layer is D[128 x N] = A[128 x K] * W^T with A (activations) read from TENSOR MEMORY
-//     (tcgen05.mma, A-from-TMEM form) and W streamed from L2 into shared memory by 1-D bulk TMA
-//     copies in the exact byte order the MMA wants (weights are re-packed once per iteration by
-//     k_tc_pack), so no activation ever touches shared or global memory:
+//   * every layer is D[128 x N] = A[128 x K] * W^T with A (activations, or their gradients in the
+//     backward chain) read from TENSOR MEMORY (tcgen05.mma, A-from-TMEM form) and W streamed from
+//     L2 into shared memory by 1-D bulk TMA copies in the exact byte order the MMA wants (weights
+//     are re-packed once per iteration by k_tc_pack), so no activation touches shared memory:
 //         accumulators --tcgen05.ld--> registers (bias, ReLU, hi/lo split) --tcgen05.st--> next A.
 //   * fp32-equivalent accuracy on TF32 tensor cores by operand splitting (3xTF32):
 //         a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi,   hi = rn_tf32(x), lo = rn_tf32(x - hi)
-//     accumulated in fp32 in tensor memory (the reference runs cuBLAS SGEMM with TF32 off;
-//     the 1e-4 parity bound of the tests holds with ~100x margin).
+//     accumulated in fp32 in tensor memory (the reference runs cuBLAS SGEMM with TF32 off).
 //   * warp roles: warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane), warps 2-5 =
-//     128 worker threads, one per sample row: gather + interpolate the 8 corner embeddings,
-//     run the layer epilogues, write (r,g,b,sdf).
-//   TMEM columns: A_hi [0,144)  A_lo [144,288)  D [288,432).  Layer inputs: L1 reads the 16
-//   features kept at A columns [128,144); L4 reads [t(128); f(16)] = columns [0,144) in place.
+//     128 worker threads, one per sample row: gather + interpolate the 8 corner embeddings, run the
+//     layer epilogues, write (r,g,b,sdf) / scatter the embedding and ray gradients.
+//   * backward = forward recompute (ReLU masks kept as bits in registers) + the dgrad chain
+//     g5 -> g_hc -> (g_t, g_f) -> g_h2 -> g_h1 -> g_f, same machinery with transposed weight packs.
+//     Weight gradients are a different GEMM shape (reduction over SAMPLES): the workers spill each
+//     tile's activations and pre-activation gradients to an L2-resident scratch in MMA operand
+//     order and k_wgrad_tc contracts them with accumulators resident in tensor memory across all
+//     of a CTA's tiles (one flush of red.global.add.v4 per CTA instead of 54k atomics per tile).
+//   TMEM columns (k_field_tc): A_hi [0,144)  A_lo [144,288)  D [288,432).
 #include "field.cuh"
 #include "kernels.h"
 #include "umma.cuh"
@@ -32,21 +36,26 @@ constexpr int kStages = 8;
 constexpr int kStageBytes = 18432;   // 144 rows x 16 k x 4 B x (hi, lo)
 constexpr int kTmemCols = 512;
 constexpr int cAHI = 0, cALO = 144, cD = 288;
-constexpr int kLayers = 5;
-// forward layers: output columns N, reduction K, A column offset
-__device__ __constant__ int cN[kLayers] = {128, 128, 144, 128, 16};
-__device__ __constant__ int cK[kLayers] = {16, 128, 128, 144, 128};
-__device__ __constant__ int cAoff[kLayers] = {128, 0, 0, 0, 0};
-constexpr int hN[kLayers] = {128, 128, 144, 128, 16};
-constexpr int hK[kLayers] = {16, 128, 128, 144, 128};
+constexpr int kLayersFwd = 5, kLayersAll = 10;
+// layers: output columns N, reduction K, A column offset.  0-4 forward (L1..L5), 5-9 dgrad (D5..D1)
+__device__ __constant__ int cN[kLayersAll] = {128, 128, 144, 128, 16, 128, 144, 128, 128, 16};
+__device__ __constant__ int cK[kLayersAll] = {16, 128, 128, 144, 128, 16, 128, 144, 128, 128};
+__device__ __constant__ int cAoff[kLayersAll] = {128, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+constexpr int hN[kLayersAll] = {128, 128, 144, 128, 16, 128, 144, 128, 128, 16};
+constexpr int hK[kLayersAll] = {16, 128, 128, 144, 128, 16, 128, 144, 128, 128};
 // shared memory map
 constexpr int oBars = kStages * kStageBytes;             // full[8], empty[8], a_ready, mma_done
 constexpr int oTmemPtr = oBars + 8 * (2 * kStages + 2);
 constexpr int oBias = oTmemPtr + 16;                     // b1[128] b2[128] b3f[128] b4[128] b3_0 b5[3]
 constexpr int kSmemBytes = oBias + 4 * (4 * 128 + 4);
+
+// wgrad scratch: per tile, per 32-sample slice, 264 groups of (32 lanes x 4 floats); see k_wgrad_tc
+constexpr int gF = 0, gH1 = 4, gH2 = 36, gT = 68, gHC = 100, gG1 = 132, gG2 = 164, gG3 = 196, gG4 = 228, gG5 = 260, kGroups = 264;
+constexpr size_t kSliceBytes = (size_t)kGroups * 512;
+constexpr size_t kTileBytes = 4 * kSliceBytes;
 }  // namespace tc
 
-// source element of forward layer l at (output row n, reduction index k)
+// source element of layer l at (output row n, reduction index k)
 __device__ __forceinline__ float tc_weight(const pslam_decoder_t &d, int l, int n, int k)
 {
     switch (l) {
@@ -54,18 +63,24 @@ __device__ __forceinline__ float tc_weight(const pslam_decoder_t &d, int l, int 
         case 1: return d.W2[n * 128 + k];
         case 2: return n < 128 ? d.W3[(1 + n) * 128 + k] : (n == 128 ? d.W3[k] : 0.0f);   // features first, sdf row at 128
         case 3: return d.W4[n * 144 + k];                                                  // k over [t(128); f(16)]
-        default: return n < 3 ? d.W5[n * 128 + k] : 0.0f;
+        case 4: return n < 3 ? d.W5[n * 128 + k] : 0.0f;
+        // dgrad: B[n][k] = W[k][n] (reduction over the layer's outputs)
+        case 5: return k < 3 ? d.W5[k * 128 + n] : 0.0f;                                   // g_hc[n] = sum_c g5[c] W5[c][n]
+        case 6: return d.W4[k * 144 + n];                                                  // [g_t; g_f][n] = sum_k g_hc[k] W4[k][n]
+        case 7: return k < 128 ? d.W3[(1 + k) * 128 + n] : (k == 128 ? d.W3[n] : 0.0f);    // g_h2[n] = sum_j g_o3[j] W3[j][n]
+        case 8: return d.W2[k * 128 + n];
+        default: return d.W1[k * 16 + n];                                                  // g_f[n] = sum_k g_h1[k] W1[k][n]
     }
 }
 
-// Re-packs the decoder into the forward weight stream: layers in order, each as K/16 chunks of
+// Re-packs the decoder into the weight stream: layers in order, each as K/16 chunks of
 // [hi block | lo block], each block = 4 k-chunks x N rows x 16 B (see umma.cuh).
 __global__ void k_tc_pack(pslam_decoder_t d, float *__restrict__ out)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int base = 0;   // float offset of the layer in `out`
 #pragma unroll
-    for (int l = 0; l < tc::kLayers; ++l) {
+    for (int l = 0; l < tc::kLayersAll; ++l) {
         const int N = tc::cN[l], K = tc::cK[l];
         if (i < N * K) {
             const int n = i / K, k = i % K;
@@ -85,9 +100,49 @@ __global__ void k_tc_pack(pslam_decoder_t d, float *__restrict__ out)
 
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-__global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc_fwd(FieldParams p, const float *__restrict__ wstream)
+// One 128-column epilogue: accumulators -> registers -> (bias / activation / mask) -> next A operand
+// (hi/lo split, tensor memory) and optionally the wgrad scratch.
+//   MODE 0: y = relu(D + bias), records y > 0 in mask[]        (forward hidden layers)
+//   MODE 1: y = D + bias                                       (forward, no activation)
+//   MODE 2: y = mask ? D : 0                                   (dgrad through a ReLU)
+//   MODE 3: y = D                                              (dgrad, no activation)
+template <int MODE>
+__device__ __forceinline__ void epilogue128(uint32_t trow, const float *bias, uint32_t (&mask)[4], unsigned char *scratch)
 {
     using namespace tc;
+    if (MODE == 0) { mask[0] = mask[1] = mask[2] = mask[3] = 0u; }
+#pragma unroll
+    for (int c0 = 0; c0 < 128; c0 += 16) {   // fully unrolled: mask[] must stay in registers
+        uint32_t v[16], hi[16], lo[16];
+        tmem_ld16(trow + cD + c0, v);
+        tmem_wait_ld();
+        uint32_t bits = 0u;
+        const uint32_t mword = mask[c0 >> 5] >> (c0 & 31);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            float y = __uint_as_float(v[e]);
+            if (MODE == 0) { y = fmaxf(y + bias[c0 + e], 0.0f); bits |= (y > 0.0f ? 1u : 0u) << e; }
+            if (MODE == 1) y = y + bias[c0 + e];
+            if (MODE == 2) y = ((mword >> e) & 1u) ? y : 0.0f;
+            v[e] = __float_as_uint(y);
+            tf32_split(y, hi[e], lo[e]);
+        }
+        if (MODE == 0) mask[c0 >> 5] |= bits << (c0 & 31);
+        tmem_st16(trow + cAHI + c0, hi);
+        tmem_st16(trow + cALO + c0, lo);
+        if (scratch) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4 *>(scratch + (size_t)(c0 / 4 + j) * 512) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+    }
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc(FieldParams p, const float *__restrict__ wstream)
+{
+    using namespace tc;
+    constexpr int NL = BWD ? kLayersAll : kLayersFwd;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + oBars);
     uint64_t *empty = full + kStages;
@@ -128,7 +183,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc_fwd(FieldParams p,
             int stage = 0, phase = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const unsigned char *src = reinterpret_cast<const unsigned char *>(wstream);
-                for (int l = 0; l < kLayers; ++l) {
+                for (int l = 0; l < NL; ++l) {
                     const uint32_t bytes = (uint32_t)cN[l] * 128u;
                     for (int c = 0; c < cK[l] / 16; ++c) {
                         mbar_wait(empty + stage, phase ^ 1);
@@ -146,7 +201,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc_fwd(FieldParams p,
             int stage = 0, phase = 0;
             uint32_t uses = 0;   // a_ready phase counter
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                for (int l = 0; l < kLayers; ++l) {
+                for (int l = 0; l < NL; ++l) {
                     const int N = cN[l];
                     const uint32_t idesc = idesc_tf32(128, N);
                     mbar_wait(a_ready, uses & 1);
@@ -179,8 +234,23 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc_fwd(FieldParams p,
         const int m = q * 32 + lane;                  // row of the tile
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
         uint32_t done_uses = 0;
+        uint32_t nomask[4] = {0u, 0u, 0u, 0u};
+        auto layer_done = [&]() {
+            mbar_wait(mma_done, done_uses & 1);
+            ++done_uses;
+            fence_after_sync();
+        };
+        auto a_is_ready = [&]() {
+            tmem_wait_st();
+            fence_before_sync();
+            mbar_arrive(a_ready);
+        };
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int s = tile * 128 + m;
+            unsigned char *scr = nullptr;   // this thread's 16-byte column in the tile's wgrad scratch
+            if (BWD && p.wg_scratch) scr = p.wg_scratch + ((size_t)tile * 4 + q) * kSliceBytes + (size_t)lane * 16;
+            int vox = -1, ray = -1;
+            float z = 0.0f, px = 0.f, py = 0.f, pz = 0.f;
             // ---- features -> A[:, 128:144) ----
             {
                 float f[16];
@@ -194,15 +264,15 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc_fwd(FieldParams p,
                             f[e] = v.x; f[e + 1] = v.y; f[e + 2] = v.z; f[e + 3] = v.w;
                         }
                     } else {
-                        const int vox = __ldg(p.samp_vox + s);
-                        const float z = __ldg(p.samp_z + s);
-                        const int ray = __ldg(p.hit_ray + __ldg(p.samp_ray + s));
+                        vox = __ldg(p.samp_vox + s);
+                        z = __ldg(p.samp_z + s);
+                        ray = __ldg(p.hit_ray + __ldg(p.samp_ray + s));
                         const float x = __fadd_rn(__ldg(p.rays_o + ray * 3 + 0), __fmul_rn(__ldg(p.rays_d + ray * 3 + 0), z));
                         const float y = __fadd_rn(__ldg(p.rays_o + ray * 3 + 1), __fmul_rn(__ldg(p.rays_d + ray * 3 + 1), z));
                         const float zz = __fadd_rn(__ldg(p.rays_o + ray * 3 + 2), __fmul_rn(__ldg(p.rays_d + ray * 3 + 2), z));
-                        const float px = __fadd_rn(__fdiv_rn(__fsub_rn(x, __ldg(p.centres + (size_t)vox * 3 + 0)), p.voxel_size), 0.5f);
-                        const float py = __fadd_rn(__fdiv_rn(__fsub_rn(y, __ldg(p.centres + (size_t)vox * 3 + 1)), p.voxel_size), 0.5f);
-                        const float pz = __fadd_rn(__fdiv_rn(__fsub_rn(zz, __ldg(p.centres + (size_t)vox * 3 + 2)), p.voxel_size), 0.5f);
+                        px = __fadd_rn(__fdiv_rn(__fsub_rn(x, __ldg(p.centres + (size_t)vox * 3 + 0)), p.voxel_size), 0.5f);
+                        py = __fadd_rn(__fdiv_rn(__fsub_rn(y, __ldg(p.centres + (size_t)vox * 3 + 1)), p.voxel_size), 0.5f);
+                        pz = __fadd_rn(__fdiv_rn(__fsub_rn(zz, __ldg(p.centres + (size_t)vox * 3 + 2)), p.voxel_size), 0.5f);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int row = __ldg(p.vertex_idx + (size_t)vox * 8 + i);
@@ -223,48 +293,139 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc_fwd(FieldParams p,
                 for (int e = 0; e < 16; ++e) tf32_split(f[e], hi[e], lo[e]);
                 tmem_st16(trow + cAHI + 128, hi);
                 tmem_st16(trow + cALO + 128, lo);
-                tmem_wait_st();
-                fence_before_sync();
-                mbar_arrive(a_ready);
-            }
-            float sdf = 0.0f;
-            for (int l = 0; l < kLayers; ++l) {
-                mbar_wait(mma_done, done_uses & 1);
-                ++done_uses;
-                fence_after_sync();
-                if (l < 4) {
-                    const float *bias = sBias + l * 128;
-                    for (int c0 = 0; c0 < 128; c0 += 16) {
-                        uint32_t v[16], hi[16], lo[16];
-                        tmem_ld16(trow + cD + c0, v);
-                        tmem_wait_ld();
+                if (scr) {
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            float y = __uint_as_float(v[e]) + bias[c0 + e];
-                            if (l != 2) y = fmaxf(y, 0.0f);      // L3 (features t) has no activation
-                            tf32_split(y, hi[e], lo[e]);
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<float4 *>(scr + (size_t)(gF + j) * 512) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                }
+                a_is_ready();
+            }
+            uint32_t m1[4], m2[4], mc[4];
+            // ---- forward ----
+            layer_done();
+            epilogue128<0>(trow, sBias, m1, scr ? scr + (size_t)gH1 * 512 : nullptr);           // h1
+            a_is_ready();
+            layer_done();
+            epilogue128<0>(trow, sBias + 128, m2, scr ? scr + (size_t)gH2 * 512 : nullptr);     // h2
+            a_is_ready();
+            layer_done();
+            epilogue128<1>(trow, sBias + 256, nomask, scr ? scr + (size_t)gT * 512 : nullptr);  // t (no activation)
+            float sdf;
+            {
+                uint32_t v[16];
+                tmem_ld16(trow + cD + 128, v);   // sdf = row 0 of W3, packed as output column 128
+                tmem_wait_ld();
+                sdf = __uint_as_float(v[0]) + sBias[512];
+            }
+            a_is_ready();
+            layer_done();
+            epilogue128<0>(trow, sBias + 384, mc, scr ? scr + (size_t)gHC * 512 : nullptr);     // hc
+            a_is_ready();
+            layer_done();
+            float r, g, b;
+            {
+                uint32_t v[16];
+                tmem_ld16(trow + cD, v);
+                tmem_wait_ld();
+                r = sigmoid_f(__uint_as_float(v[0]) + sBias[513]);
+                g = sigmoid_f(__uint_as_float(v[1]) + sBias[514]);
+                b = sigmoid_f(__uint_as_float(v[2]) + sBias[515]);
+            }
+            if (!BWD) {
+                if (s < nsamp) *reinterpret_cast<float4 *>(p.out + (size_t)s * 4) = make_float4(r, g, b, sdf);
+                continue;   // D has been read; the next tile's first MMA is ordered behind it through a_ready
+            }
+            // ---- backward ----
+            float4 go = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (s < nsamp) go = __ldg(reinterpret_cast<const float4 *>(p.g_out + (size_t)s * 4));
+            {
+                // dL/d(pre-sigmoid rgb): grad * (1 - y) * y ; A[:, 0:16) = [g5 r,g,b, 0...]
+                const float g5[4] = {go.x * (1.0f - r) * r, go.y * (1.0f - g) * g, go.z * (1.0f - b) * b, go.w};
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) { hi[e] = 0u; lo[e] = 0u; }
+#pragma unroll
+                for (int e = 0; e < 3; ++e) tf32_split(g5[e], hi[e], lo[e]);
+                tmem_st16(trow + cAHI, hi);
+                tmem_st16(trow + cALO, lo);
+                if (scr) {
+                    *reinterpret_cast<float4 *>(scr + (size_t)gG5 * 512) = make_float4(g5[0], g5[1], g5[2], g5[3]);
+#pragma unroll
+                    for (int j = 1; j < 4; ++j) *reinterpret_cast<float4 *>(scr + (size_t)(gG5 + j) * 512) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                a_is_ready();
+            }
+            layer_done();
+            epilogue128<2>(trow, nullptr, mc, scr ? scr + (size_t)gG4 * 512 : nullptr);         // g_hc
+            a_is_ready();
+            layer_done();
+            epilogue128<3>(trow, nullptr, nomask, scr ? scr + (size_t)gG3 * 512 : nullptr);     // g_t
+            float gf[16];
+            {
+                uint32_t v[16], hi[16], lo[16];
+                tmem_ld16(trow + cD + 128, v);   // g_f, part through W4's last 16 input columns
+                tmem_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 16; ++e) { gf[e] = __uint_as_float(v[e]); hi[e] = 0u; lo[e] = 0u; }
+                tf32_split(go.w, hi[0], lo[0]);  // A[:, 128] = g_sdf pairs with W3 row 0 (packed at k = 128)
+                tmem_st16(trow + cAHI + 128, hi);
+                tmem_st16(trow + cALO + 128, lo);
+            }
+            a_is_ready();
+            layer_done();
+            epilogue128<2>(trow, nullptr, m2, scr ? scr + (size_t)gG2 * 512 : nullptr);         // g_h2
+            a_is_ready();
+            layer_done();
+            epilogue128<2>(trow, nullptr, m1, scr ? scr + (size_t)gG1 * 512 : nullptr);         // g_h1
+            a_is_ready();
+            layer_done();
+            {
+                uint32_t v[16];
+                tmem_ld16(trow + cD, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 16; ++e) gf[e] += __uint_as_float(v[e]);
+            }
+            if (s >= nsamp) continue;
+            if (p.g_feat) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<float4 *>(p.g_feat + (size_t)s * 16 + 4 * j) = make_float4(gf[4 * j], gf[4 * j + 1], gf[4 * j + 2], gf[4 * j + 3]);
+            }
+            if (!p.feat && (p.grad_emb || p.grad_rays)) {
+                // trilinear backward of this sample
+                float gp[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = __ldg(p.vertex_idx + (size_t)vox * 8 + i);
+                    const float wx = (i & 4) ? px : 1.0f - px, wy = (i & 2) ? py : 1.0f - py, wz = (i & 1) ? pz : 1.0f - pz;
+                    const float w = (wx * wy) * wz;
+                    if (p.grad_emb) {
+                        float *dst = p.g_emb + (size_t)row * 16;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) red_add_v4(dst + 4 * e, w * gf[4 * e], w * gf[4 * e + 1], w * gf[4 * e + 2], w * gf[4 * e + 3]);
+                    }
+                    if (p.grad_rays) {
+                        const float4 *er = reinterpret_cast<const float4 *>(p.emb + (size_t)row * 16);
+                        float d = 0.0f;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float4 v = __ldg(er + e);
+                            d = fmaf(gf[4 * e], v.x, d); d = fmaf(gf[4 * e + 1], v.y, d);
+                            d = fmaf(gf[4 * e + 2], v.z, d); d = fmaf(gf[4 * e + 3], v.w, d);
                         }
-                        tmem_st16(trow + cAHI + c0, hi);
-                        tmem_st16(trow + cALO + c0, lo);
+                        gp[0] += d * ((i & 4) ? 1.0f : -1.0f) * (wy * wz);
+                        gp[1] += d * ((i & 2) ? 1.0f : -1.0f) * (wx * wz);
+                        gp[2] += d * ((i & 1) ? 1.0f : -1.0f) * (wx * wy);
                     }
-                    if (l == 2) {   // sdf = row 0 of W3, packed as output column 128
-                        uint32_t v[16];
-                        tmem_ld16(trow + cD + 128, v);
-                        tmem_wait_ld();
-                        sdf = __uint_as_float(v[0]) + sBias[512];
+                }
+                if (p.grad_rays) {
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        const float gx = gp[a] / p.voxel_size;
+                        atomicAdd(p.g_rays_o + ray * 3 + a, gx);
+                        atomicAdd(p.g_rays_d + ray * 3 + a, z * gx);
                     }
-                    tmem_wait_st();
-                    fence_before_sync();
-                    mbar_arrive(a_ready);
-                } else {
-                    uint32_t v[16];
-                    tmem_ld16(trow + cD, v);
-                    tmem_wait_ld();
-                    const float r = sigmoid_f(__uint_as_float(v[0]) + sBias[513]);
-                    const float g = sigmoid_f(__uint_as_float(v[1]) + sBias[514]);
-                    const float b = sigmoid_f(__uint_as_float(v[2]) + sBias[515]);
-                    if (s < nsamp) *reinterpret_cast<float4 *>(p.out + (size_t)s * 4) = make_float4(r, g, b, sdf);
-                    // D has been read: order it before the next tile's first MMA through a_ready
                 }
             }
         }
@@ -275,28 +436,236 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc_fwd(FieldParams p,
 }
 
 // ------------------------------------------------------------------------------------------
-// stand-alone GEMM through the same primitives (unit test of descriptors / TMEM addressing):
-// D[128,N] = A[128,K] * B[N,K]^T, K % 8 == 0, N % 16 == 0, both <= 144.
+// Weight gradients: dW[n][k] = sum over samples of G[p][n] * A[p][k], per layer, as MMAs whose
+// reduction dimension is the SAMPLE index.  Operands come from the scratch k_field_tc<true> wrote:
+// per tile and per 32-sample slice, "groups" of 4 features x 32 samples (16 B per sample), which is
+// exactly the MN-major no-swizzle UMMA operand layout (4 contiguous MN elements, 8 consecutive K
+// = samples at 16 B stride, SBO = 512 B between feature groups, LBO = 128 B between 8-sample
+// blocks).  Threads load the fp32 groups, split them hi/lo into shared memory (3xTF32), one thread
+// issues the MMAs, accumulators stay in tensor memory for ALL tiles of the CTA:
+//   cols [0,128) dW2   [128,256) dW3 feature rows   [256,400) dW4   [400,416) dW1
+//        [416,432) HC^T*G5 (dW5 rows = columns 0..2)   [432,448) H2^T*G5 (dW3 row 0 = column 3)
+// Bias gradients are column sums of the G groups, accumulated by the loader threads.
+// ------------------------------------------------------------------------------------------
+namespace wg {
+constexpr int kThreads = 256;
+constexpr int kBufBytes = 2 * 68 * 512;         // hi + lo of up to 32 (A') + 36 (B') groups
+constexpr int oBars = 2 * kBufBytes;            // two buffers, then 2 mbarriers + tmem ptr
+constexpr int oBiasAcc = oBars + 64;            // float[4][128] column sums of G1..G4 + [16] of G5
+constexpr int kSmemBytes = oBiasAcc + 4 * (4 * 128 + 16);
+struct Step { int a_group, a_cnt, b_group, b_cnt, b2_group, b2_cnt, dcol; };
+// A' (M' = 128 output rows n) , B' (N' columns), accumulator column
+__device__ __constant__ Step cSteps[6] = {
+    {tc::gG2, 32, tc::gH1, 32, 0, 0, 0},          // dW2[n][k]   = G2^T H1
+    {tc::gG3, 32, tc::gH2, 32, 0, 0, 128},        // dW3[1+j][k] = G3^T H2
+    {tc::gG4, 32, tc::gT, 32, tc::gF, 4, 256},    // dW4[n][j]   = G4^T [T; F]
+    {tc::gG1, 32, tc::gF, 4, 0, 0, 400},          // dW1[n][k]   = G1^T F
+    {tc::gHC, 32, tc::gG5, 4, 0, 0, 416},         // D[k][c]     = HC^T G5  (c<3: dW5[c][k])
+    {tc::gH2, 32, tc::gG5, 4, 0, 0, 432},         // D[k][c]     = H2^T G5  (c=3: dW3[0][k])
+};
+}  // namespace wg
+
+// instruction descriptor with both operands MN-major (bits 15, 16)
+__host__ __device__ constexpr uint32_t idesc_tf32_mn(int M, int N) { return idesc_tf32(M, N) | (1u << 15) | (1u << 16); }
+// shared-memory descriptor, MN-major no swizzle: LBO = stride between 8-K blocks, SBO = between MN groups of 4
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t smem_addr, uint32_t lbo, uint32_t sbo)
+{
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(wg::kThreads, 1) k_wgrad_tc(FieldParams p)
+{
+    using namespace wg;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + oBars);      // buffer-free barriers
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(smem + oBars + 32);
+    float *sBiasAcc = reinterpret_cast<float *>(smem + oBiasAcc);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int nsamp = p.nsamp_dev ? *p.nsamp_dev : p.nsamp;
+    const int ntiles = (nsamp + 127) / 128;
+    if (tid == 0) { mbar_init(bars, 1); mbar_init(bars + 1, 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(tmem_ptr, 512);
+    for (int i = tid; i < 4 * 128 + 16; i += kThreads) sBiasAcc[i] = 0.0f;
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = *tmem_ptr;
+    if ((int)blockIdx.x >= ntiles) {   // nothing to do (and nothing to flush)
+        __syncthreads();
+        if (warp == 0) tmem_dealloc(tmem, 512);
+        return;
+    }
+    uint32_t use0 = 0u, use1 = 0u;    // how many commits each buffer has seen (thread-uniform)
+    int buf = 0;
+    uint32_t started = 0u;            // bit st: accumulator of step st has been written
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int sl = 0; sl < 4; ++sl) {
+            const unsigned char *slice = p.wg_scratch + ((size_t)tile * 4 + sl) * tc::kSliceBytes;
+            for (int st = 0; st < 6; ++st, buf ^= 1) {
+                const Step S = cSteps[st];
+                unsigned char *sbuf = smem + buf * kBufBytes;    // [A' hi][B' hi][A' lo][B' lo], groups of 512 B
+                const int ngroups = S.a_cnt + S.b_cnt + S.b2_cnt;
+                // wait until the MMAs that last read this buffer are done
+                const uint32_t used = buf ? use1 : use0;
+                if (used > 0) mbar_wait(bars + buf, (used - 1) & 1);
+                // load + split: one 16-byte unit (4 features of one sample) per iteration
+                for (int u = tid; u < ngroups * 32; u += kThreads) {
+                    const int gi = u >> 5, ln = u & 31;
+                    int src_group;
+                    if (gi < S.a_cnt) src_group = S.a_group + gi;
+                    else if (gi < S.a_cnt + S.b_cnt) src_group = S.b_group + (gi - S.a_cnt);
+                    else src_group = S.b2_group + (gi - S.a_cnt - S.b_cnt);
+                    const float4 v = *reinterpret_cast<const float4 *>(slice + (size_t)src_group * 512 + ln * 16);
+                    uint4 hi, lo;
+                    tf32_split(v.x, hi.x, lo.x); tf32_split(v.y, hi.y, lo.y);
+                    tf32_split(v.z, hi.z, lo.z); tf32_split(v.w, hi.w, lo.w);
+                    *reinterpret_cast<uint4 *>(sbuf + (size_t)gi * 512 + ln * 16) = hi;
+                    *reinterpret_cast<uint4 *>(sbuf + 68 * 512 + (size_t)gi * 512 + ln * 16) = lo;
+                    // bias gradients: column sums of the G operands (steps 0..3 carry G2, G3, G4, G1 as A')
+                    if (st < 4 && gi < 32) {
+                        float4 sum = v;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            sum.x += __shfl_xor_sync(0xffffffffu, sum.x, o); sum.y += __shfl_xor_sync(0xffffffffu, sum.y, o);
+                            sum.z += __shfl_xor_sync(0xffffffffu, sum.z, o); sum.w += __shfl_xor_sync(0xffffffffu, sum.w, o);
+                        }
+                        if (ln == 0) {   // one warp owns a group in a given step: no race inside the step
+                            float *acc = sBiasAcc + st * 128 + gi * 4;
+                            acc[0] += sum.x; acc[1] += sum.y; acc[2] += sum.z; acc[3] += sum.w;
+                        }
+                    } else if (st == 4 && gi == S.a_cnt) {   // G5 = (g5 r,g,b, g_sdf)
+                        float4 sum = v;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            sum.x += __shfl_xor_sync(0xffffffffu, sum.x, o); sum.y += __shfl_xor_sync(0xffffffffu, sum.y, o);
+                            sum.z += __shfl_xor_sync(0xffffffffu, sum.z, o); sum.w += __shfl_xor_sync(0xffffffffu, sum.w, o);
+                        }
+                        if (ln == 0) {
+                            float *acc = sBiasAcc + 512;
+                            acc[0] += sum.x; acc[1] += sum.y; acc[2] += sum.z; acc[3] += sum.w;
+                        }
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic smem writes -> async proxy (MMA)
+                __syncthreads();
+                if (tid == 0) {
+                    fence_after_sync();
+                    const int nb = S.b_cnt + S.b2_cnt;                 // B' groups -> N' = 4 * nb
+                    const uint32_t idesc = idesc_tf32_mn(128, nb * 4);
+                    const uint32_t a_hi = smem_u32(sbuf), b_hi = a_hi + S.a_cnt * 512;
+                    const uint32_t a_lo = a_hi + 68 * 512, b_lo = b_hi + 68 * 512;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {                    // 4 x 8 samples
+                        const uint32_t off = ks * 128;
+                        const uint64_t dah = desc_mnmajor(a_hi + off, 128, 512), dal = desc_mnmajor(a_lo + off, 128, 512);
+                        const uint64_t dbh = desc_mnmajor(b_hi + off, 128, 512), dbl = desc_mnmajor(b_lo + off, 128, 512);
+                        mma_tf32_ss(tmem + S.dcol, dal, dbh, idesc, (!((started >> st) & 1u) && ks == 0) ? 0u : 1u);
+                        mma_tf32_ss(tmem + S.dcol, dah, dbl, idesc, 1u);
+                        mma_tf32_ss(tmem + S.dcol, dah, dbh, idesc, 1u);
+                    }
+                    mma_commit(bars + buf);
+                }
+                started |= 1u << st;
+                if (buf) ++use1; else ++use0;
+            }
+        }
+    }
+    // drain: wait for the last commits, then accumulators -> global gradients
+    if (use0 > 0) mbar_wait(bars, (use0 - 1) & 1);
+    if (use1 > 0) mbar_wait(bars + 1, (use1 - 1) & 1);
+    fence_after_sync();
+    __syncthreads();
+    if (warp < 4) {
+        const int n = warp * 32 + (tid & 31);                    // accumulator row = TMEM lane
+        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        auto flush = [&](int col0, int ncols, float *dst_row) {   // dst_row: &dW[n][0], ncols % 16 == 0
+            for (int c0 = 0; c0 < ncols; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(trow + col0 + c0, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    red_add_v4(dst_row + c0 + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                               __uint_as_float(v[4 * j + 3]));
+            }
+        };
+        flush(0, 128, p.g_dec.W2 + (size_t)n * 128);
+        flush(128, 128, p.g_dec.W3 + (size_t)(1 + n) * 128);
+        flush(256, 144, p.g_dec.W4 + (size_t)n * 144);
+        flush(400, 16, p.g_dec.W1 + (size_t)n * 16);
+        {
+            uint32_t v[16], w[16];
+            tmem_ld16(trow + 416, v);
+            tmem_ld16(trow + 432, w);
+            tmem_wait_ld();
+            atomicAdd(p.g_dec.W5 + n, __uint_as_float(v[0]));
+            atomicAdd(p.g_dec.W5 + 128 + n, __uint_as_float(v[1]));
+            atomicAdd(p.g_dec.W5 + 256 + n, __uint_as_float(v[2]));
+            atomicAdd(p.g_dec.W3 + n, __uint_as_float(w[3]));
+        }
+        // bias gradients (sBiasAcc rows: step 0 = G2, 1 = G3, 2 = G4, 3 = G1)
+        atomicAdd(p.g_dec.b2 + n, sBiasAcc[n]);
+        atomicAdd(p.g_dec.b3 + 1 + n, sBiasAcc[128 + n]);
+        atomicAdd(p.g_dec.b4 + n, sBiasAcc[256 + n]);
+        atomicAdd(p.g_dec.b1 + n, sBiasAcc[384 + n]);
+        if (n < 3) atomicAdd(p.g_dec.b5 + n, sBiasAcc[512 + n]);
+        if (n == 3) atomicAdd(p.g_dec.b3, sBiasAcc[515]);
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------
+// stand-alone GEMMs through the same primitives (unit tests of descriptors / TMEM addressing).
+// mode 0/1: D[128,N] = A[128,K] * B[N,K]^T with A in tensor memory, B K-major in shared memory
+//           (1xTF32 / 3xTF32).  K % 8 == 0, N % 16 == 0, both <= 144.
+// mode 2:   D[128,N] = At[K,128]^T * Bt[K,N]: both operands from shared memory, MN-major (the
+//           wgrad form; At/Bt rows are the reduction index), 3xTF32.  K % 32 == 0.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, 1) k_debug_umma_gemm(const float *__restrict__ A, const float *__restrict__ B, float *__restrict__ D,
-                                                            int N, int K, int split3)
+                                                            int N, int K, int mode)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_ptr;
-    float *sB = reinterpret_cast<float *>(smem);           // per 8-k step: [hi: 2 chunks x N rows x 4][lo: same]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, m = threadIdx.x;
+    float *sB = reinterpret_cast<float *>(smem);
+    const int warp = threadIdx.x >> 5, m = threadIdx.x;
     if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
     if (warp == 0) tmem_alloc(&tmem_ptr, 512);
-    // B -> smem in the operand layout, one block of (hi, lo) per MMA k-step
-    for (int i = threadIdx.x; i < N * K; i += 128) {
-        const int n = i / K, k = i % K;
-        const int st = k >> 3, kc = (k >> 2) & 1, e = k & 3;
-        uint32_t hi, lo;
-        tf32_split(B[i], hi, lo);
-        float *blk = sB + st * (2 * N * 8);
-        blk[kc * N * 4 + n * 4 + e] = __uint_as_float(hi);
-        blk[N * 8 + kc * N * 4 + n * 4 + e] = __uint_as_float(lo);
+    if (mode < 2) {
+        // B -> smem in the K-major operand layout, one block of (hi, lo) per MMA k-step
+        for (int i = threadIdx.x; i < N * K; i += 128) {
+            const int n = i / K, k = i % K;
+            const int st = k >> 3, kc = (k >> 2) & 1, e = k & 3;
+            uint32_t hi, lo;
+            tf32_split(B[i], hi, lo);
+            float *blk = sB + st * (2 * N * 8);
+            blk[kc * N * 4 + n * 4 + e] = __uint_as_float(hi);
+            blk[N * 8 + kc * N * 4 + n * 4 + e] = __uint_as_float(lo);
+        }
+    } else {
+        // MN-major groups: per 32-row slice of K: [A groups (32)][B groups (N/4)] hi, then the same lo
+        const int ng = 32 + N / 4;
+        for (int i = threadIdx.x; i < K * (128 + N); i += 128) {
+            const int k = i / (128 + N), c = i % (128 + N);
+            const float x = (c < 128) ? A[(size_t)k * 128 + c] : B[(size_t)k * N + (c - 128)];
+            const int gi = c >> 2, e = c & 3, sl = k >> 5, ln = k & 31;
+            uint32_t hi, lo;
+            tf32_split(x, hi, lo);
+            float *base = sB + (size_t)sl * (2 * ng * 128);
+            base[gi * 128 + ln * 4 + e] = __uint_as_float(hi);
+            base[ng * 128 + gi * 128 + ln * 4 + e] = __uint_as_float(lo);
+        }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the MMA (async proxy)
     fence_before_sync();
@@ -304,34 +673,51 @@ __global__ void __launch_bounds__(128, 1) k_debug_umma_gemm(const float *__restr
     fence_after_sync();
     const uint32_t tmem = tmem_ptr;
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-    // A row m -> TMEM columns [0,K) hi, [144,144+K) lo
-    for (int k0 = 0; k0 < K; k0 += 16) {
-        uint32_t hi[16], lo[16];
+    if (mode < 2) {
+        // A row m -> TMEM columns [0,K) hi, [144,144+K) lo
+        for (int k0 = 0; k0 < K; k0 += 16) {
+            uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-            const float a = (k0 + e < K) ? A[(size_t)m * K + k0 + e] : 0.0f;
-            tf32_split(a, hi[e], lo[e]);
+            for (int e = 0; e < 16; ++e) {
+                const float a = (k0 + e < K) ? A[(size_t)m * K + k0 + e] : 0.0f;
+                tf32_split(a, hi[e], lo[e]);
+            }
+            tmem_st16(trow + k0, hi);
+            tmem_st16(trow + 144 + k0, lo);
         }
-        tmem_st16(trow + k0, hi);
-        tmem_st16(trow + 144 + k0, lo);
+        tmem_wait_st();
     }
-    tmem_wait_st();
     fence_before_sync();
     __syncthreads();
     if (threadIdx.x == 0) {
         fence_after_sync();
-        const uint32_t idesc = idesc_tf32(128, N);
         const uint32_t sb = smem_u32(sB);
-        for (int st = 0; st < K / 8; ++st) {
-            const uint64_t b_hi = bdesc_kmajor(sb + st * (2 * N * 8 * 4), N);
-            const uint64_t b_lo = bdesc_kmajor(sb + st * (2 * N * 8 * 4) + N * 8 * 4, N);
-            if (split3) {
-                mma_tf32_ts(tmem + 288, tmem + 144 + st * 8, b_hi, idesc, st ? 1u : 0u);
-                mma_tf32_ts(tmem + 288, tmem + st * 8, b_lo, idesc, 1u);
-                mma_tf32_ts(tmem + 288, tmem + st * 8, b_hi, idesc, 1u);
-            } else {
-                mma_tf32_ts(tmem + 288, tmem + st * 8, b_hi, idesc, st ? 1u : 0u);
+        if (mode < 2) {
+            const uint32_t idesc = idesc_tf32(128, N);
+            for (int st = 0; st < K / 8; ++st) {
+                const uint64_t b_hi = bdesc_kmajor(sb + st * (2 * N * 8 * 4), N);
+                const uint64_t b_lo = bdesc_kmajor(sb + st * (2 * N * 8 * 4) + N * 8 * 4, N);
+                if (mode == 1) {
+                    mma_tf32_ts(tmem + 288, tmem + 144 + st * 8, b_hi, idesc, st ? 1u : 0u);
+                    mma_tf32_ts(tmem + 288, tmem + st * 8, b_lo, idesc, 1u);
+                    mma_tf32_ts(tmem + 288, tmem + st * 8, b_hi, idesc, 1u);
+                } else {
+                    mma_tf32_ts(tmem + 288, tmem + st * 8, b_hi, idesc, st ? 1u : 0u);
+                }
             }
+        } else {
+            const int ng = 32 + N / 4;
+            const uint32_t idesc = idesc_tf32_mn(128, N);
+            for (int sl = 0; sl < K / 32; ++sl)
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint32_t a_hi = sb + sl * (2 * ng * 512) + ks * 128, b_hi = a_hi + 32 * 512;
+                    const uint32_t a_lo = a_hi + ng * 512, b_lo = b_hi + ng * 512;
+                    const uint64_t dah = desc_mnmajor(a_hi, 128, 512), dal = desc_mnmajor(a_lo, 128, 512);
+                    const uint64_t dbh = desc_mnmajor(b_hi, 128, 512), dbl = desc_mnmajor(b_lo, 128, 512);
+                    mma_tf32_ss(tmem + 288, dal, dbh, idesc, (sl | ks) ? 1u : 0u);
+                    mma_tf32_ss(tmem + 288, dah, dbl, idesc, 1u);
+                    mma_tf32_ss(tmem + 288, dah, dbh, idesc, 1u);
+                }
         }
         mma_commit(&bar);
     }
@@ -353,24 +739,50 @@ __global__ void __launch_bounds__(128, 1) k_debug_umma_gemm(const float *__restr
 int tc_pack_decoder(const pslam_decoder_t &d, float *ws_tc, cudaStream_t st)
 {
     int total = 0;
-    for (int l = 0; l < tc::kLayers; ++l) total += tc::hN[l] * tc::hK[l];
+    for (int l = 0; l < tc::kLayersAll; ++l) total += tc::hN[l] * tc::hK[l];
     k_tc_pack<<<ceil_div(total, 256), 256, 0, st>>>(d, ws_tc);
     PSLAM_CHECK_LAUNCH("tc_pack");
     return 0;
 }
 
-int tc_launch_field_forward(const FieldParams &fp, int max_samples, cudaStream_t st)
+size_t tc_wgrad_scratch_bytes(int max_samples) { return (size_t)ceil_div(max_samples > 0 ? max_samples : 1, 128) * tc::kTileBytes; }
+
+template <bool BWD>
+static int launch_tc(const FieldParams &fp, int max_samples, cudaStream_t st)
 {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_field_tc_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(k_field_tc<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
         if (e != cudaSuccess) { set_error("field_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         configured = true;
     }
     const int tiles = ceil_div(max_samples, 128);
     const int grid = tiles < num_sms() ? (tiles > 0 ? tiles : 1) : num_sms();
-    k_field_tc_fwd<<<grid, tc::kThreads, tc::kSmemBytes, st>>>(fp, fp.ws_tc);
-    PSLAM_CHECK_LAUNCH("field_tc_forward");
+    k_field_tc<BWD><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(fp, fp.ws_tc);
+    PSLAM_CHECK_LAUNCH(BWD ? "field_tc_backward" : "field_tc_forward");
+    return 0;
+}
+
+int tc_launch_field_forward(const FieldParams &fp, int max_samples, cudaStream_t st) { return launch_tc<false>(fp, max_samples, st); }
+
+// backward: dgrad chain (+ trilinear backward); when decoder gradients are wanted the scratch must be
+// provided and the wgrad kernel follows on the same stream
+int tc_launch_field_backward(const FieldParams &fp_in, int max_samples, cudaStream_t st)
+{
+    FieldParams fp = fp_in;
+    if (!fp.grad_dec) fp.wg_scratch = nullptr;
+    if (int rc = launch_tc<true>(fp, max_samples, st)) return rc;
+    if (!fp.grad_dec) return 0;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::kSmemBytes);
+        if (e != cudaSuccess) { set_error("wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+        configured = true;
+    }
+    const int tiles = ceil_div(max_samples, 128);
+    const int grid = tiles < num_sms() ? (tiles > 0 ? tiles : 1) : num_sms();
+    k_wgrad_tc<<<grid, wg::kThreads, wg::kSmemBytes, st>>>(fp);
+    PSLAM_CHECK_LAUNCH("wgrad_tc");
     return 0;
 }
 
@@ -378,14 +790,15 @@ int tc_launch_field_forward(const FieldParams &fp, int max_samples, cudaStream_t
 
 using namespace pslam;
 
-extern "C" int pslam_debug_umma_gemm(const float *A, const float *B, float *D, int N, int K, int split3, pslam_stream_t stream)
+extern "C" int pslam_debug_umma_gemm(const float *A, const float *B, float *D, int N, int K, int mode, pslam_stream_t stream)
 {
     PSLAM_CHECK_ARG(A && B && D, PSLAM_E_ARG, "null pointer");
     PSLAM_CHECK_ARG(N >= 16 && N <= 144 && N % 16 == 0 && K >= 8 && K <= 144 && K % 8 == 0, PSLAM_E_RANGE, "N in 16..144 step 16, K in 8..144 step 8");
-    const int smem = 2 * N * K * 4;
+    PSLAM_CHECK_ARG(mode >= 0 && mode <= 2 && (mode < 2 || K % 32 == 0), PSLAM_E_RANGE, "mode 0..2; mode 2 needs K % 32 == 0");
+    const int smem = mode < 2 ? 2 * N * K * 4 : (K / 32) * 2 * (32 + N / 4) * 512;
     cudaError_t e = cudaFuncSetAttribute(k_debug_umma_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { set_error("debug_umma: %s", cudaGetErrorString(e)); return (int)e; }
-    k_debug_umma_gemm<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, N, K, split3);
+    k_debug_umma_gemm<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, N, K, mode);
     PSLAM_CHECK_LAUNCH("debug_umma_gemm");
     return 0;
 }

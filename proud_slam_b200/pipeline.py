@@ -84,6 +84,7 @@ class RenderPipeline:
         self.g_rays_o = torch.zeros(R, 3, **f32)
         self.g_rays_d = torch.zeros(R, 3, **f32)
         self.dec_ws = {w: torch.empty(int(self.lib.pslam_decoder_ws_count(w)), **f32) for w in (128, 256)}
+        self.wgrad_ws = None   # allocated on first use (decoder gradients through the tensor-core path)
         self.args = RenderT()
         self._keep = None      # tensors referenced by self.args
         self.R = 0
@@ -141,6 +142,13 @@ class RenderPipeline:
                                                      emb.data_ptr())
         a.dec = _decoder_struct(dec_params)
         a.dec_ws = self.dec_ws[width].data_ptr()
+        if g_dec is not None and width == 128:
+            if self.wgrad_ws is None:
+                self.wgrad_ws = torch.empty(int(self.lib.pslam_wgrad_ws_bytes(self.sample_cap)), dtype=torch.uint8,
+                                            device=self.device)
+            a.wgrad_ws, a.wgrad_ws_bytes = self.wgrad_ws.data_ptr(), self.wgrad_ws.numel()
+        else:
+            a.wgrad_ws, a.wgrad_ws_bytes = None, 0
         if noise is not None:
             _lib.require_cuda(noise, "uniform_noise", torch.float32)
             a.noise, a.noise_stride = noise.data_ptr(), int(noise.shape[-1])

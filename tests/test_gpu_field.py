@@ -17,8 +17,9 @@ def _dec_struct(params):
     return _decoder_struct(params)
 
 
+@pytest.mark.parametrize("use_ws", [True, False])   # True: tcgen05 wgrad (width 128); False: SIMT wgrad
 @pytest.mark.parametrize("width,n", [(128, 1), (128, 64), (128, 1000), (256, 333), (128, 20000)])
-def test_decoder_forward_backward(width, n, device):
+def test_decoder_forward_backward(width, n, use_ws, device):
     from proud_slam_b200.pipeline import DecoderGradT, _decoder_struct
     import ctypes as C
     lib = _lib.lib()
@@ -42,8 +43,9 @@ def test_decoder_forward_backward(width, n, device):
     gs = _decoder_struct(gd, DecoderGradT)
     g_feat = torch.empty(n, 16, device=device)
     g_outd = g_out.to(device)
+    wws = torch.empty(int(lib.pslam_wgrad_ws_bytes(n)), dtype=torch.uint8, device=device) if use_ws else None
     _lib.check(lib.pslam_decoder_bwd(n, C.byref(ds), _lib.ptr(featd), _lib.ptr(ws), _lib.ptr(g_outd), _lib.ptr(g_feat),
-                                     C.byref(gs), _lib.stream_ptr(device)), "bwd")
+                                     C.byref(gs), _lib.ptr(wws), 0 if wws is None else wws.numel(), _lib.stream_ptr(device)), "bwd")
     torch.cuda.synchronize()
     assert rel_err(g_feat, feat.grad) < TOL
     for i in range(10):
@@ -91,7 +93,7 @@ def test_trilinear_forward_backward(n, device):
 
 @pytest.mark.parametrize("N,K", [(16, 8), (128, 16), (128, 128), (144, 128), (128, 144), (16, 128)])
 @pytest.mark.parametrize("split3", [0, 1])
-def test_umma_gemm_primitives(N, K, split3, device):
+def test_umma_gemm_primitives(N, K, split3, device):  # modes 0/1 of the debug kernel
     """tcgen05.mma (A from tensor memory, B through a shared-memory descriptor), TMEM ld/st and the
     operand layouts of csrc/umma.cuh, against an fp64 matmul.  1xTF32 ~1e-3, 3xTF32 ~fp32."""
     g = torch.Generator().manual_seed(N * 1000 + K)
@@ -131,3 +133,17 @@ def test_decoder_forward_both_builds(mode, device):
         assert rel_err(out[:, 3], sdf) < 1e-5
     finally:
         lib.pslam_set_option(1, 0)
+
+
+@pytest.mark.parametrize("N,K", [(16, 32), (128, 32), (144, 64), (128, 128)])
+def test_umma_gemm_mn_major_from_smem(N, K, device):
+    """The wgrad form: both operands in shared memory, MN-major (reduction index = rows), 3xTF32."""
+    g = torch.Generator().manual_seed(N + K)
+    At = torch.randn(K, 128, generator=g)
+    Bt = torch.randn(K, N, generator=g)
+    ref = At.double().t() @ Bt.double()
+    Ad, Bd = At.to(device), Bt.to(device)
+    D = torch.zeros(128, N, device=device)
+    _lib.check(_lib.lib().pslam_debug_umma_gemm(_lib.ptr(Ad), _lib.ptr(Bd), _lib.ptr(D), N, K, 2, _lib.stream_ptr(device)), "umma mn")
+    torch.cuda.synchronize()
+    assert rel_err(D, ref) < 2e-6
