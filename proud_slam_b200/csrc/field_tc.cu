@@ -438,18 +438,18 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc(FieldParams p, con
 // ------------------------------------------------------------------------------------------
 // Weight gradients: dW[n][k] = sum over samples of G[p][n] * A[p][k], per layer, as MMAs whose
 // reduction dimension is the SAMPLE index.  Operands come from the scratch k_field_tc<true> wrote:
-// per tile and per 32-sample slice, "groups" of 4 features x 32 samples (16 B per sample), which is
-// exactly the MN-major no-swizzle UMMA operand layout (4 contiguous MN elements, 8 consecutive K
-// = samples at 16 B stride, SBO = 512 B between feature groups, LBO = 128 B between 8-sample
-// blocks).  Threads load the fp32 groups, split them hi/lo into shared memory (3xTF32), one thread
-// issues the MMAs, accumulators stay in tensor memory for ALL tiles of the CTA:
+// per tile and per 32-sample slice, "groups" of 4 features x 32 samples (16 B per sample, written
+// coalesced by the sample-per-thread workers).  The loader threads transpose 4x4 blocks in
+// registers into the K-major operand layout of umma.cuh (16-byte chunks = 4 consecutive samples
+// of one feature), split hi/lo (3xTF32) into shared memory, one thread issues the MMAs (both
+// operands from shared memory), and the accumulators stay in tensor memory for ALL tiles of the CTA:
 //   cols [0,128) dW2   [128,256) dW3 feature rows   [256,400) dW4   [400,416) dW1
 //        [416,432) HC^T*G5 (dW5 rows = columns 0..2)   [432,448) H2^T*G5 (dW3 row 0 = column 3)
 // Bias gradients are column sums of the G groups, accumulated by the loader threads.
 // ------------------------------------------------------------------------------------------
 namespace wg {
 constexpr int kThreads = 256;
-constexpr int kBufBytes = 2 * 68 * 512;         // hi + lo of up to 32 (A') + 36 (B') groups
+constexpr int kBufBytes = 2 * 272 * 128;        // hi + lo of A' (128 rows) + B' (<= 144 rows), 32 samples each
 constexpr int oBars = 2 * kBufBytes;            // two buffers, then 2 mbarriers + tmem ptr
 constexpr int oBiasAcc = oBars + 64;            // float[4][128] column sums of G1..G4 + [16] of G5
 constexpr int kSmemBytes = oBiasAcc + 4 * (4 * 128 + 16);
@@ -512,45 +512,54 @@ __global__ void __launch_bounds__(wg::kThreads, 1) k_wgrad_tc(FieldParams p)
             const unsigned char *slice = p.wg_scratch + ((size_t)tile * 4 + sl) * tc::kSliceBytes;
             for (int st = 0; st < 6; ++st, buf ^= 1) {
                 const Step S = cSteps[st];
-                unsigned char *sbuf = smem + buf * kBufBytes;    // [A' hi][B' hi][A' lo][B' lo], groups of 512 B
+                unsigned char *sbuf = smem + buf * kBufBytes;    // [A' hi][B' hi][A' lo][B' lo]
                 const int ngroups = S.a_cnt + S.b_cnt + S.b2_cnt;
                 // wait until the MMAs that last read this buffer are done
                 const uint32_t used = buf ? use1 : use0;
                 if (used > 0) mbar_wait(bars + buf, (used - 1) & 1);
-                // load + split: one 16-byte unit (4 features of one sample) per iteration
-                for (int u = tid; u < ngroups * 32; u += kThreads) {
-                    const int gi = u >> 5, ln = u & 31;
-                    int src_group;
-                    if (gi < S.a_cnt) src_group = S.a_group + gi;
-                    else if (gi < S.a_cnt + S.b_cnt) src_group = S.b_group + (gi - S.a_cnt);
-                    else src_group = S.b2_group + (gi - S.a_cnt - S.b_cnt);
-                    const float4 v = *reinterpret_cast<const float4 *>(slice + (size_t)src_group * 512 + ln * 16);
-                    uint4 hi, lo;
-                    tf32_split(v.x, hi.x, lo.x); tf32_split(v.y, hi.y, lo.y);
-                    tf32_split(v.z, hi.z, lo.z); tf32_split(v.w, hi.w, lo.w);
-                    *reinterpret_cast<uint4 *>(sbuf + (size_t)gi * 512 + ln * 16) = hi;
-                    *reinterpret_cast<uint4 *>(sbuf + 68 * 512 + (size_t)gi * 512 + ln * 16) = lo;
-                    // bias gradients: column sums of the G operands (steps 0..3 carry G2, G3, G4, G1 as A')
-                    if (st < 4 && gi < 32) {
-                        float4 sum = v;
+                // load + transpose + split.  Scratch unit = 4 features of ONE sample; the K-major operand wants
+                // 16-byte chunks of 4 consecutive SAMPLES of one feature, so each thread turns a 4x4 block
+                // (4 consecutive samples x one feature group) around in registers.
+                const int rowsB = 4 * (S.b_cnt + S.b2_cnt);          // B' rows (N'); A' always has 128
+                unsigned char *sA_hi = sbuf, *sB_hi = sbuf + 128 * 128;       // [8 k-chunks][rows][16 B]
+                unsigned char *sA_lo = sbuf + 272 * 128, *sB_lo = sA_lo + 128 * 128;
+                for (int u = tid; u < ngroups * 8; u += kThreads) {
+                    const int gi = u >> 3, quad = u & 7;             // feature group, 4-sample block of the slice
+                    int src_group, row0;
+                    unsigned char *dhi, *dlo;
+                    int rows;
+                    if (gi < S.a_cnt) { src_group = S.a_group + gi; row0 = gi * 4; dhi = sA_hi; dlo = sA_lo; rows = 128; }
+                    else {
+                        const int gb = gi - S.a_cnt;
+                        src_group = gb < S.b_cnt ? S.b_group + gb : S.b2_group + (gb - S.b_cnt);
+                        row0 = gb * 4; dhi = sB_hi; dlo = sB_lo; rows = rowsB;
+                    }
+                    const float4 *src = reinterpret_cast<const float4 *>(slice + (size_t)src_group * 512 + quad * 64);
+                    const float4 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3];   // samples 4*quad .. +3
+                    const float t[4][4] = {{v0.x, v1.x, v2.x, v3.x}, {v0.y, v1.y, v2.y, v3.y}, {v0.z, v1.z, v2.z, v3.z}, {v0.w, v1.w, v2.w, v3.w}};
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-                            sum.x += __shfl_xor_sync(0xffffffffu, sum.x, o); sum.y += __shfl_xor_sync(0xffffffffu, sum.y, o);
-                            sum.z += __shfl_xor_sync(0xffffffffu, sum.z, o); sum.w += __shfl_xor_sync(0xffffffffu, sum.w, o);
-                        }
-                        if (ln == 0) {   // one warp owns a group in a given step: no race inside the step
-                            float *acc = sBiasAcc + st * 128 + gi * 4;
-                            acc[0] += sum.x; acc[1] += sum.y; acc[2] += sum.z; acc[3] += sum.w;
-                        }
-                    } else if (st == 4 && gi == S.a_cnt) {   // G5 = (g5 r,g,b, g_sdf)
-                        float4 sum = v;
+                    for (int f = 0; f < 4; ++f) {
+                        uint4 hi, lo;
+                        tf32_split(t[f][0], hi.x, lo.x); tf32_split(t[f][1], hi.y, lo.y);
+                        tf32_split(t[f][2], hi.z, lo.z); tf32_split(t[f][3], hi.w, lo.w);
+                        const size_t off = (size_t)quad * rows * 16 + (size_t)(row0 + f) * 16;
+                        *reinterpret_cast<uint4 *>(dhi + off) = hi;
+                        *reinterpret_cast<uint4 *>(dlo + off) = lo;
+                    }
+                    // bias gradients: column sums of the G operands (steps 0..3 carry G2, G3, G4, G1 as A';
+                    // step 4 carries G5 = (g5 r,g,b, g_sdf) as the first B' group)
+                    const bool is_g = (st < 4 && gi < S.a_cnt) || (st == 4 && gi == S.a_cnt);
+                    if (is_g) {   // 8 consecutive lanes share a group; shuffles name only those lanes
+                        const unsigned gm = 0xFFu << ((tid & 31) & ~7);
+                        float4 sum = make_float4(t[0][0] + t[0][1] + t[0][2] + t[0][3], t[1][0] + t[1][1] + t[1][2] + t[1][3],
+                                                 t[2][0] + t[2][1] + t[2][2] + t[2][3], t[3][0] + t[3][1] + t[3][2] + t[3][3]);
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-                            sum.x += __shfl_xor_sync(0xffffffffu, sum.x, o); sum.y += __shfl_xor_sync(0xffffffffu, sum.y, o);
-                            sum.z += __shfl_xor_sync(0xffffffffu, sum.z, o); sum.w += __shfl_xor_sync(0xffffffffu, sum.w, o);
+                        for (int o = 4; o > 0; o >>= 1) {
+                            sum.x += __shfl_xor_sync(gm, sum.x, o); sum.y += __shfl_xor_sync(gm, sum.y, o);
+                            sum.z += __shfl_xor_sync(gm, sum.z, o); sum.w += __shfl_xor_sync(gm, sum.w, o);
                         }
-                        if (ln == 0) {
-                            float *acc = sBiasAcc + 512;
+                        if (quad == 0) {   // the same thread owns this (step, group) in every slice: no race
+                            float *acc = (st < 4) ? sBiasAcc + st * 128 + gi * 4 : sBiasAcc + 512;
                             acc[0] += sum.x; acc[1] += sum.y; acc[2] += sum.z; acc[3] += sum.w;
                         }
                     }
@@ -559,15 +568,12 @@ __global__ void __launch_bounds__(wg::kThreads, 1) k_wgrad_tc(FieldParams p)
                 __syncthreads();
                 if (tid == 0) {
                     fence_after_sync();
-                    const int nb = S.b_cnt + S.b2_cnt;                 // B' groups -> N' = 4 * nb
-                    const uint32_t idesc = idesc_tf32_mn(128, nb * 4);
-                    const uint32_t a_hi = smem_u32(sbuf), b_hi = a_hi + S.a_cnt * 512;
-                    const uint32_t a_lo = a_hi + 68 * 512, b_lo = b_hi + 68 * 512;
+                    const uint32_t idesc = idesc_tf32(128, rowsB);
+                    const uint32_t a_hi = smem_u32(sA_hi), b_hi = smem_u32(sB_hi), a_lo = smem_u32(sA_lo), b_lo = smem_u32(sB_lo);
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {                    // 4 x 8 samples
-                        const uint32_t off = ks * 128;
-                        const uint64_t dah = desc_mnmajor(a_hi + off, 128, 512), dal = desc_mnmajor(a_lo + off, 128, 512);
-                        const uint64_t dbh = desc_mnmajor(b_hi + off, 128, 512), dbl = desc_mnmajor(b_lo + off, 128, 512);
+                    for (int ks = 0; ks < 4; ++ks) {                    // 4 x 8 samples = 4 x 2 k-chunks
+                        const uint64_t dah = bdesc_kmajor(a_hi + ks * 2 * 128 * 16, 128), dal = bdesc_kmajor(a_lo + ks * 2 * 128 * 16, 128);
+                        const uint64_t dbh = bdesc_kmajor(b_hi + ks * 2 * rowsB * 16, rowsB), dbl = bdesc_kmajor(b_lo + ks * 2 * rowsB * 16, rowsB);
                         mma_tf32_ss(tmem + S.dcol, dal, dbh, idesc, (!((started >> st) & 1u) && ks == 0) ? 0u : 1u);
                         mma_tf32_ss(tmem + S.dcol, dah, dbl, idesc, 1u);
                         mma_tf32_ss(tmem + S.dcol, dah, dbh, idesc, 1u);
@@ -642,7 +648,21 @@ __global__ void __launch_bounds__(128, 1) k_debug_umma_gemm(const float *__restr
     const int warp = threadIdx.x >> 5, m = threadIdx.x;
     if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
     if (warp == 0) tmem_alloc(&tmem_ptr, 512);
-    if (mode < 2) {
+    if (mode == 4) {
+        // A and B -> smem, K-major, per k-step: [A hi (2 kc x 128 rows x 4)][B hi (2 kc x N x 4)][A lo][B lo]
+        const int blk = 2 * (128 + N) * 8;
+        for (int i = threadIdx.x; i < (128 + N) * K; i += 128) {
+            const int r = i / K, k = i % K;
+            const int st = k >> 3, kc = (k >> 2) & 1, e = k & 3;
+            uint32_t hi, lo;
+            const bool isA = r < 128;
+            tf32_split(isA ? A[(size_t)r * K + k] : B[(size_t)(r - 128) * K + k], hi, lo);
+            const int rows = isA ? 128 : N, rr = isA ? r : r - 128;
+            float *base = sB + st * blk + (isA ? 0 : 128 * 8);
+            base[kc * rows * 4 + rr * 4 + e] = __uint_as_float(hi);
+            base[(128 + N) * 8 + kc * rows * 4 + rr * 4 + e] = __uint_as_float(lo);
+        }
+    } else if (mode < 2) {
         // B -> smem in the K-major operand layout, one block of (hi, lo) per MMA k-step
         for (int i = threadIdx.x; i < N * K; i += 128) {
             const int n = i / K, k = i % K;
@@ -686,13 +706,32 @@ __global__ void __launch_bounds__(128, 1) k_debug_umma_gemm(const float *__restr
             tmem_st16(trow + 144 + k0, lo);
         }
         tmem_wait_st();
+    } else {
+        // sentinel in D: tells "MMA wrote zeros" from "MMA did not write"
+        for (int c0 = 0; c0 < N; c0 += 16) {
+            uint32_t sv[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) sv[e] = __float_as_uint(123.0f);
+            tmem_st16(trow + 288 + c0, sv);
+        }
+        tmem_wait_st();
     }
     fence_before_sync();
     __syncthreads();
     if (threadIdx.x == 0) {
         fence_after_sync();
         const uint32_t sb = smem_u32(sB);
-        if (mode < 2) {
+        if (mode == 4) {
+            const uint32_t idesc = idesc_tf32(128, N);
+            const uint32_t blkb = 2 * (128 + N) * 8 * 4;
+            for (int st = 0; st < K / 8; ++st) {
+                const uint32_t a_hi = sb + st * blkb, b_hi = a_hi + 128 * 8 * 4;
+                const uint32_t a_lo = a_hi + (128 + N) * 8 * 4, b_lo = b_hi + (128 + N) * 8 * 4;
+                mma_tf32_ss(tmem + 288, bdesc_kmajor(a_lo, 128), bdesc_kmajor(b_hi, N), idesc, st ? 1u : 0u);
+                mma_tf32_ss(tmem + 288, bdesc_kmajor(a_hi, 128), bdesc_kmajor(b_lo, N), idesc, 1u);
+                mma_tf32_ss(tmem + 288, bdesc_kmajor(a_hi, 128), bdesc_kmajor(b_hi, N), idesc, 1u);
+            }
+        } else if (mode < 2) {
             const uint32_t idesc = idesc_tf32(128, N);
             for (int st = 0; st < K / 8; ++st) {
                 const uint64_t b_hi = bdesc_kmajor(sb + st * (2 * N * 8 * 4), N);
@@ -712,8 +751,9 @@ __global__ void __launch_bounds__(128, 1) k_debug_umma_gemm(const float *__restr
                 for (int ks = 0; ks < 4; ++ks) {
                     const uint32_t a_hi = sb + sl * (2 * ng * 512) + ks * 128, b_hi = a_hi + 32 * 512;
                     const uint32_t a_lo = a_hi + ng * 512, b_lo = b_hi + ng * 512;
-                    const uint64_t dah = desc_mnmajor(a_hi, 128, 512), dal = desc_mnmajor(a_lo, 128, 512);
-                    const uint64_t dbh = desc_mnmajor(b_hi, 128, 512), dbl = desc_mnmajor(b_lo, 128, 512);
+                    const uint32_t lbo = (mode == 3) ? 512 : 128, sbo = (mode == 3) ? 128 : 512;
+                    const uint64_t dah = desc_mnmajor(a_hi, lbo, sbo), dal = desc_mnmajor(a_lo, lbo, sbo);
+                    const uint64_t dbh = desc_mnmajor(b_hi, lbo, sbo), dbl = desc_mnmajor(b_lo, lbo, sbo);
                     mma_tf32_ss(tmem + 288, dal, dbh, idesc, (sl | ks) ? 1u : 0u);
                     mma_tf32_ss(tmem + 288, dah, dbl, idesc, 1u);
                     mma_tf32_ss(tmem + 288, dah, dbh, idesc, 1u);
@@ -794,8 +834,9 @@ extern "C" int pslam_debug_umma_gemm(const float *A, const float *B, float *D, i
 {
     PSLAM_CHECK_ARG(A && B && D, PSLAM_E_ARG, "null pointer");
     PSLAM_CHECK_ARG(N >= 16 && N <= 144 && N % 16 == 0 && K >= 8 && K <= 144 && K % 8 == 0, PSLAM_E_RANGE, "N in 16..144 step 16, K in 8..144 step 8");
-    PSLAM_CHECK_ARG(mode >= 0 && mode <= 2 && (mode < 2 || K % 32 == 0), PSLAM_E_RANGE, "mode 0..2; mode 2 needs K % 32 == 0");
-    const int smem = mode < 2 ? 2 * N * K * 4 : (K / 32) * 2 * (32 + N / 4) * 512;
+    PSLAM_CHECK_ARG(mode >= 0 && mode <= 4 && (mode < 2 || mode == 4 || K % 32 == 0), PSLAM_E_RANGE, "mode 0..4; modes 2,3 need K % 32 == 0");
+    const int smem = mode == 4 ? 2 * (128 + N) * K * 4 : (mode < 2 ? 2 * N * K * 4 : (K / 32) * 2 * (32 + N / 4) * 512);
+    PSLAM_CHECK_ARG(smem <= 200 * 1024, PSLAM_E_RANGE, "operands do not fit in shared memory");
     cudaError_t e = cudaFuncSetAttribute(k_debug_umma_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { set_error("debug_umma: %s", cudaGetErrorString(e)); return (int)e; }
     k_debug_umma_gemm<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, N, K, mode);

@@ -28,6 +28,17 @@ def test_decoder_forward_backward(width, n, use_ws, device):
     feat = (torch.randn(n, 16, generator=g) * 0.05).requires_grad_(True)
     rgb, sdf = ro.decoder_forward(dec, feat)
     g_out = torch.randn(n, 4, generator=g)
+    # ReLU'(0) is a hard decision: a pre-activation within fp32 rounding of 0 flips one unit's mask
+    # between two correct implementations and changes that sample's gradient by O(1).  Samples
+    # with such a unit get zero upstream gradient on both sides (they then contribute nothing).
+    with torch.no_grad():
+        W1, b1, W2, b2, W3, b3, W4, b4, W5, b5 = dec
+        a1 = feat @ W1.t() + b1
+        a2 = torch.relu(a1) @ W2.t() + b2
+        t = (torch.relu(a2) @ W3.t() + b3)[:, 1:]
+        a4 = torch.cat([t, feat], 1) @ W4.t() + b4
+        near = (a1.abs().min(1).values < 2e-6) | (a2.abs().min(1).values < 2e-6) | (a4.abs().min(1).values < 2e-6)
+        g_out[near] = 0.0
     (torch.cat([rgb, sdf[:, None]], 1) * g_out).sum().backward()
 
     decd = [p.detach().to(device) for p in dec]
@@ -135,15 +146,15 @@ def test_decoder_forward_both_builds(mode, device):
         lib.pslam_set_option(1, 0)
 
 
-@pytest.mark.parametrize("N,K", [(16, 32), (128, 32), (144, 64), (128, 128)])
-def test_umma_gemm_mn_major_from_smem(N, K, device):
-    """The wgrad form: both operands in shared memory, MN-major (reduction index = rows), 3xTF32."""
+@pytest.mark.parametrize("N,K", [(16, 8), (16, 32), (128, 32), (144, 64)])
+def test_umma_gemm_both_operands_from_smem(N, K, device):
+    """The wgrad form: A and B both through shared-memory descriptors (K-major), 3xTF32."""
     g = torch.Generator().manual_seed(N + K)
-    At = torch.randn(K, 128, generator=g)
-    Bt = torch.randn(K, N, generator=g)
-    ref = At.double().t() @ Bt.double()
-    Ad, Bd = At.to(device), Bt.to(device)
+    A = torch.randn(128, K, generator=g)
+    B = torch.randn(N, K, generator=g)
+    ref = A.double() @ B.double().t()
+    Ad, Bd = A.to(device), B.to(device)
     D = torch.zeros(128, N, device=device)
-    _lib.check(_lib.lib().pslam_debug_umma_gemm(_lib.ptr(Ad), _lib.ptr(Bd), _lib.ptr(D), N, K, 2, _lib.stream_ptr(device)), "umma mn")
+    _lib.check(_lib.lib().pslam_debug_umma_gemm(_lib.ptr(Ad), _lib.ptr(Bd), _lib.ptr(D), N, K, 4, _lib.stream_ptr(device)), "umma ss")
     torch.cuda.synchronize()
     assert rel_err(D, ref) < 2e-6
