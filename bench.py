@@ -173,13 +173,9 @@ def run_gpu(args):
     R = batch_cpu[0].shape[0]
     E = ms["voxel_vertex_emb"].shape[0]
     # one flat gradient buffer [E*16 | decoder]: the kernels scatter straight into what NCCL reduces
-    n_dec = sum(p.numel() for p in dec)
-    flat = torch.zeros(E * 16 + n_dec, device=device)
-    g_emb = flat[: E * 16].view(E, 16)
-    g_dec, off = [], E * 16
-    for p in dec:
-        g_dec.append(flat[off: off + p.numel()].view_as(p))
-        off += p.numel()
+    from proud_slam_b200.parallel import FlatGrads
+    fg = FlatGrads(ms["voxel_vertex_emb"], dec)
+    flat, g_emb, g_dec = fg.flat, fg.g_emb, fg.g_dec
     host = [t.pin_memory() for t in batch_cpu]                        # e2e: inputs start in pinned host memory
     dev_in = [torch.empty_like(t, device=device) for t in batch_cpu]
     for d, h in zip(dev_in, host):

@@ -266,6 +266,12 @@ int pslam_render_forward(const pslam_render_t *p, pslam_stream_t stream);
 int pslam_loss_finalize(const pslam_render_t *p, const double *rows, int nrows, pslam_stream_t stream);
 /* Stage 3: backward of stage 2 into g_emb / g_dec / g_rays_*. */
 int pslam_render_backward(const pslam_render_t *p, pslam_stream_t stream);
+/* Stage 3 for a caller-side loss: backward of stage 2 from arbitrary upstream gradients w.r.t.
+ * the render_rays outputs -- g_color [R_h,3], g_depth [R_h] (by hit-ray rank), g_sdf and g_weight
+ * per sample in CSR order; any of them may be NULL.  This is what the autograd wrapper of the
+ * drop-in render_rays (render_helpers.py:351-556) calls. */
+int pslam_render_backward_ext(const pslam_render_t *p, const float *g_color, const float *g_depth,
+                              const float *g_sdf, const float *g_weight, pslam_stream_t stream);
 /* All three stages back to back. */
 int pslam_render_step(const pslam_render_t *p, pslam_stream_t stream);
 /* Profiling hook: one stage of the step (0 intersect, 1 sampling, 2 field fwd, 3 composite fwd + loss,

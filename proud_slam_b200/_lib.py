@@ -77,6 +77,7 @@ _PROTOTYPES = {
     "pslam_render_forward": (C.c_int, [C.POINTER(RenderT), _S]),
     "pslam_render_backward": (C.c_int, [C.POINTER(RenderT), _S]),
     "pslam_loss_finalize": (C.c_int, [C.POINTER(RenderT), _P, _I, _S]),
+    "pslam_render_backward_ext": (C.c_int, [C.POINTER(RenderT), _P, _P, _P, _P, _S]),
     "pslam_render_step": (C.c_int, [C.POINTER(RenderT), _S]),
     "pslam_render_stage": (C.c_int, [C.POINTER(RenderT), _I, _S]),
     "pslam_octree_new": (C.c_void_p, [_I]),

@@ -65,7 +65,7 @@ static int check_render_field(const pslam_render_t *p, bool backward)
                     PSLAM_E_ARG, "null decoder parameter");
     PSLAM_CHECK_ARG(p->dec_ws && p->samp_out && p->ray_out && p->loss && p->loss_raw, PSLAM_E_ARG, "null forward buffer");
     PSLAM_CHECK_ARG((p->target_rgb == nullptr) == (p->target_depth == nullptr), PSLAM_E_ARG, "target_rgb and target_depth go together");
-    if (backward) PSLAM_CHECK_ARG(p->target_rgb && p->target_depth, PSLAM_E_ARG, "backward needs the Criterion targets");
+    if (backward) PSLAM_CHECK_ARG(p->target_rgb && p->target_depth, PSLAM_E_ARG, "backward needs the Criterion targets (use pslam_render_backward_ext otherwise)");
     PSLAM_CHECK_ARG(((uintptr_t)p->dec.W1 | (uintptr_t)p->dec.W2 | (uintptr_t)p->dec.W3 | (uintptr_t)p->dec.W4 | (uintptr_t)p->dec_ws |
                      (uintptr_t)p->samp_out | (uintptr_t)p->emb) % 16 == 0,
                     PSLAM_E_ALIGN, "decoder weights, dec_ws, samp_out and emb must be 16-byte aligned");
@@ -77,6 +77,9 @@ static int check_render_field(const pslam_render_t *p, bool backward)
             PSLAM_CHECK_ARG(p->g_dec.W1 && p->g_dec.b1 && p->g_dec.W2 && p->g_dec.b2 && p->g_dec.W3 && p->g_dec.b3 && p->g_dec.W4 &&
                                 p->g_dec.b4 && p->g_dec.W5 && p->g_dec.b5,
                             PSLAM_E_ARG, "null decoder gradient pointer");
+        if (p->flags & PSLAM_F_GRAD_DEC)
+            PSLAM_CHECK_ARG(((uintptr_t)p->g_dec.W1 | (uintptr_t)p->g_dec.W2 | (uintptr_t)p->g_dec.W3 | (uintptr_t)p->g_dec.W4) % 16 == 0,
+                            PSLAM_E_ALIGN, "decoder weight gradients must be 16-byte aligned");
     }
     return 0;
 }
@@ -147,6 +150,16 @@ extern "C" int pslam_render_backward(const pslam_render_t *p, pslam_stream_t str
     if (int rc = check_render_field(p, true)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (int rc = launch_composite_backward(p, st)) return rc;
+    return launch_field_backward(p, st);
+}
+
+extern "C" int pslam_render_backward_ext(const pslam_render_t *p, const float *g_color, const float *g_depth, const float *g_sdf,
+                                         const float *g_weight, pslam_stream_t stream)
+{
+    if (int rc = check_render(p)) return rc;
+    PSLAM_CHECK_ARG(p->dec_ws && p->samp_out && p->ray_out && p->samp_gout, PSLAM_E_ARG, "null forward buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = launch_composite_backward_ext(p, g_color, g_depth, g_sdf, g_weight, st)) return rc;
     return launch_field_backward(p, st);
 }
 

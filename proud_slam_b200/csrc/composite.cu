@@ -326,6 +326,47 @@ k_composite_bwd(pslam_render_t p)
     }
 }
 
+// Backward of compositing for ARBITRARY upstream gradients (the autograd route of the drop-in
+// render_rays: a caller-side Criterion produced dL/d(color, depth, sdf, weights)).  g_color [R_h,3],
+// g_depth [R_h] by rank; g_sdf / g_weight per sample in CSR order (either may be NULL).
+__global__ void __launch_bounds__(kCompThreads)
+k_composite_bwd_ext(pslam_render_t p, const float *__restrict__ g_color, const float *__restrict__ g_depth,
+                    const float *__restrict__ g_sdf, const float *__restrict__ g_weight)
+{
+    const int Rh = p.counters[PSLAM_C_RH];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.x * kCompWarps + warp;
+    if (q >= Rh) return;
+    const int beg = p.samp_off[q], cnt = min(p.samp_off[q + 1], p.sample_cap) - beg;
+    if (cnt <= 0) return;
+    const float tau = p.truncation;
+    const float *ro = p.ray_out + (size_t)q * 8;
+    const float U = ro[5], z_cut = __fadd_rn(ro[4], tau);
+    const float g_r = g_color ? g_color[q * 3] : 0.f, g_g = g_color ? g_color[q * 3 + 1] : 0.f, g_b = g_color ? g_color[q * 3 + 2] : 0.f;
+    const float g_d = g_depth ? g_depth[q] : 0.f;
+    float dot = 0.0f;
+    for (int k = lane; k < cnt; k += 32) {
+        const float4 o = __ldg(reinterpret_cast<const float4 *>(p.samp_out + (size_t)(beg + k) * 4));
+        const float z = __ldg(p.samp_z + beg + k);
+        const float x = o.w / tau;
+        const float w = (z < z_cut) ? (sigmoidf_(x) * sigmoidf_(-x)) / U : 0.0f;
+        dot = fmaf(w, g_r * o.x + g_g * o.y + g_b * o.z + g_d * z + (g_weight ? g_weight[beg + k] : 0.f), dot);
+    }
+    dot = warp_sum(dot);
+    for (int k = lane; k < cnt; k += 32) {
+        const float4 o = __ldg(reinterpret_cast<const float4 *>(p.samp_out + (size_t)(beg + k) * 4));
+        const float z = __ldg(p.samp_z + beg + k);
+        const float x = o.w / tau;
+        const float sp = sigmoidf_(x), sn = sigmoidf_(-x);
+        const bool in = z < z_cut;
+        const float w = in ? (sp * sn) / U : 0.0f;
+        const float g_w = g_r * o.x + g_g * o.y + g_b * o.z + g_d * z + (g_weight ? g_weight[beg + k] : 0.f);
+        float g_s = in ? ((g_w - dot) / U) * (sp * sn * (sn - sp) / tau) : 0.0f;
+        if (g_sdf) g_s += g_sdf[beg + k];
+        *reinterpret_cast<float4 *>(p.samp_gout + (size_t)(beg + k) * 4) = make_float4(w * g_r, w * g_g, w * g_b, g_s);
+    }
+}
+
 __global__ void k_zero_f(float *__restrict__ a, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -351,6 +392,19 @@ int launch_loss_coeffs(const pslam_render_t *p, const double *rows, int nrows, c
 {
     k_loss_coeffs<<<1, 32, 0, st>>>(*p, rows, nrows);
     PSLAM_CHECK_LAUNCH("loss_coeffs");
+    return 0;
+}
+
+int launch_composite_backward_ext(const pslam_render_t *p, const float *g_color, const float *g_depth, const float *g_sdf,
+                                  const float *g_weight, cudaStream_t st)
+{
+    if (p->flags & PSLAM_F_GRAD_RAYS) {
+        k_zero_f<<<ceil_div(p->R * 3, 256), 256, 0, st>>>(p->g_rays_o, p->R * 3);
+        k_zero_f<<<ceil_div(p->R * 3, 256), 256, 0, st>>>(p->g_rays_d, p->R * 3);
+        PSLAM_CHECK_LAUNCH("zero_ray_grads");
+    }
+    k_composite_bwd_ext<<<ceil_div(p->R, kCompWarps), kCompThreads, 0, st>>>(*p, g_color, g_depth, g_sdf, g_weight);
+    PSLAM_CHECK_LAUNCH("composite_bwd_ext");
     return 0;
 }
 

@@ -834,6 +834,9 @@ extern "C" int pslam_decoder_bwd(int np, const pslam_decoder_t *dec, const float
     if (grad)
         PSLAM_CHECK_ARG(grad->W1 && grad->b1 && grad->W2 && grad->b2 && grad->W3 && grad->b3 && grad->W4 && grad->b4 && grad->W5 && grad->b5,
                         PSLAM_E_ARG, "decoder_bwd: null gradient pointer");
+    if (grad)
+        PSLAM_CHECK_ARG(((uintptr_t)grad->W1 | (uintptr_t)grad->W2 | (uintptr_t)grad->W3 | (uintptr_t)grad->W4) % 16 == 0, PSLAM_E_ALIGN,
+                        "decoder weight gradients must be 16-byte aligned");
     if (int rc = pack_decoder(*dec, ws, (cudaStream_t)stream)) return rc;
     FieldParams fp{};
     fp.nsamp = np; fp.feat = feat; fp.dec = *dec; fp.ws = ws; fp.ws_tc = tc_region(*dec, ws); fp.g_out = g_out; fp.g_feat = g_feat;

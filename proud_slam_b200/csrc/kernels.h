@@ -17,6 +17,8 @@ int launch_field_backward(const pslam_render_t *p, cudaStream_t st);
 // composite.cu (SDF->weights compositing + loss)
 int launch_composite_forward(const pslam_render_t *p, cudaStream_t st);
 int launch_composite_backward(const pslam_render_t *p, cudaStream_t st);
+int launch_composite_backward_ext(const pslam_render_t *p, const float *g_color, const float *g_depth, const float *g_sdf,
+                                  const float *g_weight, cudaStream_t st);
 int launch_loss_coeffs(const pslam_render_t *p, const double *rows, int nrows, cudaStream_t st);
 
 }  // namespace pslam

@@ -42,13 +42,14 @@ class FlatGrads:
     """One flat fp32 buffer ``[E*16 | decoder params]`` with views for the kernels to write into."""
 
     def __init__(self, emb: torch.Tensor, dec_params: Sequence[torch.Tensor]):
-        n = emb.numel() + sum(p.numel() for p in dec_params)
+        pad4 = lambda k: (k + 3) // 4 * 4      # every segment starts 16-byte aligned (vector reductions)
+        n = pad4(emb.numel()) + sum(pad4(p.numel()) for p in dec_params)
         self.flat = torch.zeros(n, dtype=torch.float32, device=emb.device)
         self.g_emb = self.flat[: emb.numel()].view_as(emb)
-        self.g_dec, off = [], emb.numel()
+        self.g_dec, off = [], pad4(emb.numel())
         for p in dec_params:
             self.g_dec.append(self.flat[off: off + p.numel()].view_as(p))
-            off += p.numel()
+            off += pad4(p.numel())
 
     def zero_(self):
         self.flat.zero_()

@@ -186,6 +186,11 @@ class RenderPipeline:
     def backward(self):
         self._call(self.lib.pslam_render_backward, "pslam_render_backward")
 
+    def backward_ext(self, g_color=None, g_depth=None, g_sdf=None, g_weight=None):
+        """Backward from upstream gradients w.r.t. the rendered outputs (rank / CSR order)."""
+        _lib.check(self.lib.pslam_render_backward_ext(C.byref(self.args), ptr(g_color), ptr(g_depth), ptr(g_sdf), ptr(g_weight),
+                                                      _lib.stream_ptr(self.device)), "pslam_render_backward_ext")
+
     def finalize_loss(self, rows):
         """Multi-GPU: rows = all ranks' ``loss_raw`` ([nranks,16] float64 on this device)."""
         _lib.require_cuda(rows, "loss rows")

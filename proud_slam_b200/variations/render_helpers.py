@@ -1,0 +1,339 @@
+"""Drop-in for the render-path part of ``src/variations/render_helpers.py``.
+
+* ``get_features_vox`` (``:105-156``), differentiable w.r.t. the sample positions and the embedding
+  table through the CUDA trilinear kernels;
+* ``render_rays`` (``:351-556``): same arguments, same returned dict, differentiable w.r.t.
+  ``rays_o``, ``rays_d``, ``map_states['voxel_vertex_emb']`` and the decoder parameters.  Forward =
+  fused intersection + sampling + lookup + decoder + compositing; backward = one fused kernel
+  chain fed with the caller's gradients (any Criterion works on the returned tensors);
+* ``bundle_adjust_frames`` (``:559-676``) and ``track_frame`` (``:679-761``): the reference's loops with
+  the whole iteration (render + Criterion + backward) as ONE device-side call and no host sync.
+
+The reference's per-call debug dumps (``np.savetxt``, ``:403-405``) and the dead ``resnet`` argument
+are accepted and ignored.
+"""
+import itertools
+import weakref
+from copy import deepcopy
+
+import torch
+
+from .. import _lib
+from ..pipeline import RenderPipeline
+
+_seed_counter = itertools.count(1)
+
+
+def _next_seed():
+    """Sampling-noise seed: follows torch.manual_seed, advances per call, needs no device sync."""
+    return (torch.initial_seed() * 0x9E3779B97F4A7C15 + next(_seed_counter)) & 0xFFFFFFFFFFFFFFFF
+
+
+# ------------------------------------------------------------------------------------------
+# pipelines are pooled by (device, capacity); one is pinned while an autograd graph refers to it
+# ------------------------------------------------------------------------------------------
+_pool = {}
+
+
+def _acquire(num_rays, device):
+    cap = 1 << max(10, (int(num_rays) - 1).bit_length())
+    key = (str(device), cap)
+    free = _pool.setdefault(key, [])
+    return (free.pop() if free else RenderPipeline(cap, device)), key
+
+
+def _release(pipe, key):
+    _pool.setdefault(key, []).append(pipe)
+
+
+class _Lease:
+    """Returns the pipeline to the pool when the autograd node (or the caller) lets go of it."""
+
+    def __init__(self, pipe, key):
+        self.pipe, self.key = pipe, key
+        self._fin = weakref.finalize(self, _release, pipe, key)
+
+
+def decoder_params_of(sdf_network):
+    """The 10 decoder tensors in C-ABI order from our Decoder or the reference's (nrgbd.py:106-113)."""
+    if hasattr(sdf_network, "param_list"):
+        return sdf_network.param_list()
+    if isinstance(sdf_network, (list, tuple)):
+        return list(sdf_network)
+    m = sdf_network
+    return [m.pts_linears[0].weight, m.pts_linears[0].bias, m.pts_linears[1].weight, m.pts_linears[1].bias,
+            m.sdf_out.weight, m.sdf_out.bias, m.color_out[0].weight, m.color_out[0].bias,
+            m.color_out[2].weight, m.color_out[2].bias]
+
+
+def _device_states(map_states, device):
+    """map_states tensors on the device with the dtypes the kernels take (the reference calls
+    ``.cuda()`` on them at every use, render_helpers.py:108-110)."""
+    return {
+        "voxel_center_xyz": map_states["voxel_center_xyz"].to(device, torch.float32).contiguous(),
+        "voxel_structure": map_states["voxel_structure"].to(device, torch.int32).contiguous(),
+        "voxel_vertex_idx": map_states["voxel_vertex_idx"].to(device, torch.int32).contiguous(),
+        "voxel_vertex_emb": map_states["voxel_vertex_emb"].to(device, torch.float32),
+    }
+
+
+# ------------------------------------------------------------------------------------------
+# get_features_vox
+# ------------------------------------------------------------------------------------------
+class _TrilinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xyz, emb, vox_idx, centres, vertex_idx, voxel_size):
+        lib = _lib.lib()
+        xyz_c, emb_c = xyz.contiguous().float(), emb.contiguous()
+        n = xyz_c.shape[0]
+        feat = torch.empty(n, 16, device=xyz.device, dtype=torch.float32)
+        _lib.check(lib.pslam_trilinear_fwd(n, _lib.ptr(xyz_c), _lib.ptr(vox_idx), _lib.ptr(centres), _lib.ptr(vertex_idx),
+                                           _lib.ptr(emb_c), float(voxel_size), _lib.ptr(feat), _lib.stream_ptr(xyz.device)),
+                   "trilinear forward")
+        ctx.save_for_backward(xyz_c, emb_c, vox_idx, centres, vertex_idx)
+        ctx.voxel_size = float(voxel_size)
+        return feat
+
+    @staticmethod
+    def backward(ctx, g_feat):
+        lib = _lib.lib()
+        xyz, emb, vox_idx, centres, vertex_idx = ctx.saved_tensors
+        n = xyz.shape[0]
+        g_xyz = torch.empty_like(xyz) if ctx.needs_input_grad[0] else None
+        g_emb = torch.zeros_like(emb) if ctx.needs_input_grad[1] else None
+        _lib.check(lib.pslam_trilinear_bwd(n, _lib.ptr(xyz), _lib.ptr(vox_idx), _lib.ptr(centres), _lib.ptr(vertex_idx), _lib.ptr(emb),
+                                           ctx.voxel_size, _lib.ptr(g_feat.contiguous()), _lib.ptr(g_emb), _lib.ptr(g_xyz),
+                                           _lib.stream_ptr(xyz.device)), "trilinear backward")
+        return g_xyz, g_emb, None, None, None, None
+
+
+def get_features_vox(samples, map_states, voxel_size):
+    """render_helpers.py:105-156: samples {'sampled_point_xyz' [p,3], 'sampled_point_voxel_idx' [p],
+    'sampled_point_distance' [p]} -> {'dists', 'emb' [p,16]}."""
+    xyz = samples["sampled_point_xyz"]
+    ms = _device_states(map_states, xyz.device)
+    idx = samples["sampled_point_voxel_idx"].to(torch.int32).contiguous()
+    feats = _TrilinearFn.apply(xyz, ms["voxel_vertex_emb"], idx, ms["voxel_center_xyz"], ms["voxel_vertex_idx"], voxel_size)
+    return {"dists": samples["sampled_point_distance"], "emb": feats}
+
+
+# ------------------------------------------------------------------------------------------
+# render_rays
+# ------------------------------------------------------------------------------------------
+class _RenderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rays_o, rays_d, emb, cfg, *dec_params):
+        device = rays_o.device
+        R = rays_o.reshape(-1, 3).shape[0]
+        pipe, key = _acquire(R, device)
+        lease = _Lease(pipe, key)
+        ms = dict(cfg["map_states"])
+        ms["voxel_vertex_emb"] = emb.detach().contiguous()
+        dec = [p.detach().contiguous() for p in dec_params]
+        pipe.bind(rays_o.detach().float().contiguous(), rays_d.detach().float().contiguous(), ms, dec,
+                  voxel_size=cfg["voxel_size"], step_size=cfg["step_size"], truncation=cfg["truncation"],
+                  max_distance=cfg["max_distance"], noise=cfg["noise"], seed=cfg["seed"], forward_only=True)
+        pipe.sample()
+        pipe.forward()
+        c = pipe.counts()                         # host sync, as the reference has at render_helpers.py:388
+        ctx.lease, ctx.R, ctx.counts = lease, R, c
+        ctx.dec, ctx.ms, ctx.cfg = dec, ms, cfg
+        if c["R_h"] == 0 or c["n_samples"] == 0:
+            ctx.empty = True
+            z = torch.zeros(0, 0, device=device)
+            return z, torch.zeros(0, 3, device=device), torch.zeros(0, device=device), z, z, (pipe.hit_count[:R] > 0).view(1, -1), torch.zeros(0, 1, device=device)
+        ctx.empty = False
+        o = pipe.outputs()
+        ctx.sample_mask = o["sample_mask"]
+        for k in ("z_vals", "ray_mask", "raw"):
+            ctx.mark_non_differentiable(o[k])
+        return o["weights"], o["color"], o["depth"], o["sdf"], o["z_vals"], o["ray_mask"], o["raw"]
+
+    @staticmethod
+    def backward(ctx, g_weights, g_color, g_depth, g_sdf, *_):
+        n_dec = len(ctx.dec)
+        if ctx.empty:
+            return (None,) * (4 + n_dec)
+        pipe = ctx.lease.pipe
+        need_o, need_d, need_e = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        need_p = any(ctx.needs_input_grad[4:])
+        emb = ctx.ms["voxel_vertex_emb"]
+        g_emb = torch.zeros_like(emb) if need_e else None
+        g_dec = [torch.zeros_like(p) for p in ctx.dec] if need_p else None
+        a = pipe.args
+        # same intermediates, now with gradient targets
+        flags = a.flags & ~(_lib.F_GRAD_EMB | _lib.F_GRAD_DEC | _lib.F_GRAD_RAYS | _lib.F_FORWARD_ONLY)
+        if need_e:
+            flags |= _lib.F_GRAD_EMB
+            a.g_emb = g_emb.data_ptr()
+        if need_p:
+            from ..pipeline import DecoderGradT, _decoder_struct
+            flags |= _lib.F_GRAD_DEC
+            a.g_dec = _decoder_struct(g_dec, DecoderGradT)
+            if int(ctx.dec[0].shape[0]) == 128:
+                if pipe.wgrad_ws is None:
+                    pipe.wgrad_ws = torch.empty(int(pipe.lib.pslam_wgrad_ws_bytes(pipe.sample_cap)), dtype=torch.uint8, device=pipe.device)
+                a.wgrad_ws, a.wgrad_ws_bytes = pipe.wgrad_ws.data_ptr(), pipe.wgrad_ws.numel()
+        if need_o or need_d:
+            flags |= _lib.F_GRAD_RAYS
+        a.flags = flags
+        m = ctx.sample_mask
+        g_sdf_csr = g_sdf[m].contiguous() if g_sdf is not None else None
+        g_w_csr = g_weights[m].contiguous() if g_weights is not None else None
+        pipe.backward_ext(None if g_color is None else g_color.contiguous(), None if g_depth is None else g_depth.contiguous(),
+                          g_sdf_csr, g_w_csr)
+        R = ctx.R
+        g_o = pipe.g_rays_o[:R].clone().view(1, R, 3) if need_o else None
+        g_d = pipe.g_rays_d[:R].clone().view(1, R, 3) if need_d else None
+        return (g_o, g_d, g_emb, None, *(g_dec if need_p else [None] * n_dec))
+
+
+def render_rays(rays_o, rays_d, map_states, sdf_network, resnet, step_size, voxel_size, truncation, max_voxel_hit,
+                max_distance, chunk_size=10000, profiler=None, return_raw=False, noise=None, seed=None):
+    """render_helpers.py:351-556.  rays_o / rays_d [1,R,3]; returns the reference's dict
+    {weights [R_h,S], color [R_h,3], depth [R_h], z_vals [R_h,S], sdf [R_h,S] (pad 1), ray_mask [1,R],
+    raw ([R_h,1] z_min, or None)} -- or ``(None, 0)`` when no sample exists (:433).  Raises
+    AssertionError when no ray hits the map (:388).  ``noise`` ([>=R_h, M] uniform numbers) replays a
+    recorded draw (used by the parity tests); by default the device-side counter noise is used."""
+    if profiler is not None:
+        profiler.tick("render_rays_fused")
+    device = rays_o.device
+    ms = _device_states(map_states, device)
+    emb = map_states["voxel_vertex_emb"]
+    if not emb.is_cuda:
+        emb = emb.to(device)
+    dec = decoder_params_of(sdf_network)
+    cfg = dict(map_states=ms, voxel_size=float(voxel_size), step_size=float(step_size), truncation=float(truncation),
+               max_distance=float(max_distance), noise=noise, seed=_next_seed() if seed is None else int(seed))
+    weights, color, depth, sdf, z_vals, ray_mask, raw = _RenderFn.apply(rays_o, rays_d, emb, cfg, *dec)
+    if profiler is not None:
+        profiler.tok("render_rays_fused")
+    assert ray_mask.sum() > 0, "no ray hits the map"   # render_helpers.py:388
+    if z_vals.numel() == 0:
+        return None, 0                                   # render_helpers.py:433
+    return {"weights": weights, "color": color, "depth": depth, "z_vals": z_vals, "sdf": sdf, "ray_mask": ray_mask,
+            "raw": raw if return_raw else None}
+
+
+# ------------------------------------------------------------------------------------------
+# fused iteration used by the SLAM loops
+# ------------------------------------------------------------------------------------------
+def _criterion_cfg(loss_criteria):
+    return dict(weights=(loss_criteria.rgb_weight, loss_criteria.depth_weight, loss_criteria.fs_weight, loss_criteria.sdf_weight),
+                truncation=loss_criteria.truncation, max_depth=loss_criteria.max_dpeth)
+
+
+class FusedIteration:
+    """One optimisation iteration = ``pslam_render_step`` (render + Criterion + backward).  Gradients land
+    in ``g_emb`` / ``g_dec`` / ``pipe.g_rays_o`` / ``pipe.g_rays_d``; the loss block stays on the device."""
+
+    def __init__(self, max_rays, device, width):
+        self.pipe = RenderPipeline(max_rays, device)
+        self.g_emb = None
+        self.g_dec = None
+        self.width = width
+
+    def run(self, rays_o, rays_d, rgb, depth, ms, dec, crit, *, voxel_size, step_size, max_distance, tracking, grad_emb,
+            grad_dec, grad_rays, seed):
+        if grad_emb and (self.g_emb is None or self.g_emb.shape != ms["voxel_vertex_emb"].shape):
+            self.g_emb = torch.zeros_like(ms["voxel_vertex_emb"])
+        if grad_dec and self.g_dec is None:
+            self.g_dec = [torch.zeros_like(p) for p in dec]
+        if grad_emb:
+            self.g_emb.zero_()
+        if grad_dec:
+            for g in self.g_dec:
+                g.zero_()
+        self.pipe.bind(rays_o, rays_d, ms, dec, voxel_size=voxel_size, step_size=step_size, truncation=crit["truncation"],
+                       max_distance=max_distance, max_depth=crit["max_depth"], target_rgb=rgb, target_depth=depth, seed=seed,
+                       weights=crit["weights"], tracking=tracking, g_emb=self.g_emb if grad_emb else None,
+                       g_dec=self.g_dec if grad_dec else None, grad_rays=grad_rays)
+        self.pipe.step()
+        return self.pipe.loss
+
+
+def bundle_adjust_frames(keyframe_graph, map_states, sdf_network, resnet, loss_criteria, voxel_size, step_size, N_rays=512,
+                         num_iterations=10, truncation=0.1, max_voxel_hit=10, max_distance=10, learning_rate=[1e-2, 5e-3],
+                         embed_optim=None, model_optim=None, resnet_optim=None, update_pose=True):
+    """render_helpers.py:559-676.  Same loop; per iteration the rays of all keyframes are assembled as
+    in the reference (pose autograd kept in torch, se3pose.py), then ONE fused call produces the loss
+    and every gradient; ``.grad`` fields are filled and the caller's optimizers stepped."""
+    optimizers = [embed_optim] + ([model_optim] if model_optim is not None else [])
+    for keyframe in keyframe_graph:
+        if keyframe.stamp != 0 and update_pose:
+            optimizers += [keyframe.optim]
+    emb = map_states["voxel_vertex_emb"]
+    device = emb.device if emb.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    ms = _device_states(map_states, device)
+    dec_params = decoder_params_of(sdf_network)
+    crit = _criterion_cfg(loss_criteria)
+    crit["truncation"] = truncation
+    it = FusedIteration(N_rays * max(len(keyframe_graph), 1), device, int(dec_params[0].shape[0]))
+    for _ in range(num_iterations):
+        rays_o, rays_d, rgb_samples, depth_samples = [], [], [], []
+        for frame in keyframe_graph:
+            pose = frame.get_pose().to(device)
+            frame.sample_rays(N_rays)
+            sample_mask = frame.sample_mask.to(device)
+            sampled_rays_d = frame.rays_d.to(device)[sample_mask]
+            sampled_rays_d = sampled_rays_d @ pose[:3, :3].transpose(-1, -2)
+            rays_d += [sampled_rays_d]
+            rays_o += [pose[:3, 3].reshape(1, -1).expand_as(sampled_rays_d)]
+            rgb_samples += [frame.rgb.to(device)[sample_mask]]
+            depth_samples += [frame.depth.to(device)[sample_mask]]
+        rays_d = torch.cat(rays_d, dim=0)
+        rays_o = torch.cat(rays_o, dim=0)
+        rgb_samples = torch.cat(rgb_samples, dim=0).float().contiguous()
+        depth_samples = torch.cat(depth_samples, dim=0).float().contiguous()
+        need_pose = rays_d.requires_grad or rays_o.requires_grad
+        ms["voxel_vertex_emb"] = emb.detach() if emb.is_cuda else emb.detach().to(device)
+        dec = [p.detach() for p in dec_params]
+        it.run(rays_o.detach().float().contiguous(), rays_d.detach().float().contiguous(), rgb_samples, depth_samples, ms, dec, crit,
+               voxel_size=voxel_size, step_size=step_size, max_distance=max_distance, tracking=False, grad_emb=True,
+               grad_dec=model_optim is not None, grad_rays=need_pose, seed=_next_seed())
+        for optim in optimizers:
+            optim.zero_grad()
+        emb.grad = it.g_emb if emb.is_cuda else it.g_emb.to(emb.device)
+        if model_optim is not None:
+            for p, g in zip(dec_params, it.g_dec):
+                p.grad = g.clone()
+        if need_pose:
+            R = rays_o.shape[0]
+            torch.autograd.backward([rays_o, rays_d], [it.pipe.g_rays_o[:R], it.pipe.g_rays_d[:R]])
+        for optim in optimizers:
+            optim.step()
+
+
+def track_frame(frame_pose, curr_frame, map_states, sdf_network, resnet, loss_criteria, voxel_size, N_rays=512, step_size=0.05,
+                num_iterations=10, truncation=0.1, learning_rate=1e-3, max_voxel_hit=10, max_distance=10, profiler=None,
+                depth_variance=False):
+    """render_helpers.py:679-761: optimise the 6-vector pose of ``curr_frame`` against the fixed map.
+    Returns (pose, optim, hit_mask) like the reference."""
+    device = torch.device("cuda", torch.cuda.current_device())
+    init_pose = deepcopy(frame_pose).to(device)
+    init_pose.requires_grad_(True)
+    optim = torch.optim.Adam(init_pose.parameters(), lr=learning_rate)
+    ms = _device_states(map_states, device)
+    ms["voxel_vertex_emb"] = ms["voxel_vertex_emb"].detach().contiguous()
+    dec = [p.detach().to(device).contiguous() for p in decoder_params_of(sdf_network)]
+    crit = _criterion_cfg(loss_criteria)
+    crit["truncation"] = truncation
+    it = FusedIteration(N_rays, device, int(dec[0].shape[0]))
+    hit_mask = None
+    for _ in range(num_iterations):
+        curr_frame.sample_rays(N_rays)
+        sample_mask = curr_frame.sample_mask.to(device)
+        ray_dirs = curr_frame.rays_d.to(device)[sample_mask]
+        rgb = curr_frame.rgb.to(device)[sample_mask].float().contiguous()
+        depth = curr_frame.depth.to(device)[sample_mask].float().contiguous()
+        ray_dirs_iter = ray_dirs @ init_pose.rotation().transpose(-1, -2)
+        ray_start_iter = init_pose.translation().reshape(1, -1).expand_as(ray_dirs_iter)
+        it.run(ray_start_iter.detach().float().contiguous(), ray_dirs_iter.detach().float().contiguous(), rgb, depth, ms, dec, crit,
+               voxel_size=voxel_size, step_size=step_size, max_distance=max_distance, tracking=depth_variance, grad_emb=False,
+               grad_dec=False, grad_rays=True, seed=_next_seed())
+        optim.zero_grad()
+        R = ray_dirs_iter.shape[0]
+        torch.autograd.backward([ray_start_iter, ray_dirs_iter], [it.pipe.g_rays_o[:R], it.pipe.g_rays_d[:R]])
+        optim.step()
+        hit_mask = it.pipe.hit_count[:R] > 0
+    return init_pose, optim, hit_mask

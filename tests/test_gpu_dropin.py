@@ -1,0 +1,193 @@
+"""The reference-facing Python surface (same names, arguments, tensors in and out as
+src/variations/{voxel_helpers,render_helpers,nrgbd}.py and src/criterion.py) on the GPU."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import render_oracle as ro
+from tests import util
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _setup(device, kind="tiny", rays=200, frames=(0, 1), width=128):
+    from proud_slam_b200 import scene as sc
+    s, ms = util.build_scene(kind)
+    dec = util.test_decoder(width=width, seed=1)
+    rays_o, rays_d, rgb, depth = sc.sample_batch(s, list(frames), rays, seed=5)
+    msd = {k: v.detach().to(device) for k, v in ms.items()}
+    return s, ms, msd, dec, rays_o, rays_d, rgb, depth
+
+
+def test_ray_intersect_vox_and_ray_sample_match_oracle(device):
+    from proud_slam_b200.variations import voxel_helpers as vh
+    s, ms, msd, dec, rays_o, rays_d, rgb, depth = _setup(device, "replica_small", 500)
+    inv = util.device_rcp(rays_d.reshape(-1, 3), device)
+    ref, ref_hits = ro.ray_intersect_vox(rays_o, rays_d, ms["voxel_center_xyz"].detach(), ms["voxel_structure"], s.voxel_size, 10, 10.0, inv_dir=inv)
+    out, hits = vh.ray_intersect_vox(rays_o.to(device), rays_d.to(device), msd["voxel_center_xyz"], msd["voxel_structure"], s.voxel_size, 10, 10.0)
+    assert torch.equal(hits.cpu(), ref_hits)
+    for k in ref:
+        assert torch.equal(out[k].cpu(), ref[k]), k
+    # sampling on the hit rays, replaying the oracle's noise
+    mask = ref_hits.view(-1)
+    inter_ref = {k: v[0][mask] for k, v in ref.items()}
+    smp_ref, noise = ro.ray_sample(inter_ref, 0.1 * s.voxel_size, generator=torch.Generator().manual_seed(3))
+    inter = {k: v[0][mask.to(device)] for k, v in out.items()}
+    smp = vh.ray_sample(inter, 0.1 * s.voxel_size, noise=noise.to(device))
+    for k in ("sampled_point_voxel_idx", "sampled_point_depth", "sampled_point_distance"):
+        assert torch.equal(smp[k].cpu(), smp_ref[k]), k
+    assert "probs" in inter and "steps" in inter   # the reference adds them to the dict too
+
+
+def test_get_features_vox_autograd(device):
+    from proud_slam_b200.variations import render_helpers as rh
+    s, ms = util.build_scene("tiny", emb_scale=0.5)
+    leaf = torch.nonzero((ms["voxel_vertex_idx"] >= 0).all(-1)).view(-1)
+    g = torch.Generator().manual_seed(0)
+    vox = leaf[torch.randint(0, leaf.numel(), (3000,), generator=g)]
+    xyz = (ms["voxel_center_xyz"].detach()[vox] + (torch.rand(3000, 3, generator=g) - 0.5) * s.voxel_size).requires_grad_(True)
+    f = ro.get_features_vox(xyz, vox, ms, s.voxel_size)
+    gf = torch.randn(3000, 16, generator=g)
+    (f * gf).sum().backward()
+    msd = {k: v.detach().to(device) for k, v in ms.items()}
+    msd["voxel_vertex_emb"].requires_grad_(True)
+    xd = xyz.detach().to(device).requires_grad_(True)
+    out = rh.get_features_vox({"sampled_point_xyz": xd, "sampled_point_voxel_idx": vox.to(device),
+                               "sampled_point_distance": torch.zeros(3000, device=device)}, msd, s.voxel_size)
+    assert set(out) == {"dists", "emb"}
+    (out["emb"] * gf.to(device)).sum().backward()
+    assert rel_err(out["emb"], f.detach()) < TOL
+    assert rel_err(xd.grad, xyz.grad) < TOL
+    assert rel_err(msd["voxel_vertex_emb"].grad, ms["voxel_vertex_emb"].grad) < TOL
+
+
+@pytest.mark.parametrize("width", [128, 256])
+def test_decoder_module_is_state_dict_compatible(width, device):
+    from proud_slam_b200.variations.nrgbd import Decoder
+    dec = Decoder(depth=2, width=width, in_dim=16, skips=[], embedder="none").to(device)
+    assert set(dec.state_dict()) == {f"pts_linears.{i}.{p}" for i in (0, 1) for p in ("weight", "bias")} | {
+        "sdf_out.weight", "sdf_out.bias", "color_out.0.weight", "color_out.0.bias", "color_out.2.weight", "color_out.2.bias"}
+    x = (torch.randn(700, 16, generator=torch.Generator().manual_seed(1)) * 0.05)
+    params = [p.detach().cpu().clone().requires_grad_(True) for p in dec.param_list()]
+    xc = x.clone().requires_grad_(True)
+    rgb, sdf = ro.decoder_forward(params, xc)
+    (rgb.sum() * 0.3 + (sdf * sdf).sum()).backward()
+    xd = x.to(device).requires_grad_(True)
+    out = dec({"emb": xd})
+    assert set(out) == {"color", "sdf"} and out["color"].shape == (700, 3)
+    (out["color"].sum() * 0.3 + (out["sdf"] * out["sdf"]).sum()).backward()
+    assert rel_err(out["color"], rgb.detach()) < TOL and rel_err(out["sdf"], sdf.detach()) < TOL
+    assert rel_err(xd.grad, xc.grad) < TOL
+    for p, q in zip(dec.param_list(), params):
+        assert rel_err(p.grad, q.grad) < TOL
+    vals = dec.get_values(xd)
+    assert vals.shape == (700, 4) and torch.equal(vals[:, 3], dec.get_sdf({"emb": xd}))
+    with pytest.raises(NotImplementedError):
+        Decoder()   # the reference's defaults (depth 8, nerf embedder) are not on the SLAM path
+
+
+def test_render_rays_with_criterion_equals_fused_step(device):
+    """Modular route (render_rays -> Criterion -> autograd) and fused route (pslam_render_step) agree."""
+    from proud_slam_b200.criterion import Criterion
+    from proud_slam_b200.pipeline import RenderPipeline
+    from proud_slam_b200.variations import render_helpers as rh
+    s, ms, msd, dec, rays_o, rays_d, rgb, depth = _setup(device, "replica_small", 400)
+    decd = [p.detach().to(device).requires_grad_(True) for p in dec]
+    msd["voxel_vertex_emb"].requires_grad_(True)
+    ro_d, rd_d = rays_o.to(device).requires_grad_(True), rays_d.to(device).requires_grad_(True)
+    args = types.SimpleNamespace(criteria=dict(rgb_weight=0.5, depth_weight=1.0, sdf_weight=5000.0, fs_weight=10.0, sdf_truncation=0.1),
+                                 data_specs=dict(max_depth=10.0))
+    crit = Criterion(args)
+    out = rh.render_rays(ro_d, rd_d, msd, decd, None, 0.1 * s.voxel_size, s.voxel_size, 0.1, 10, 10.0, seed=77, return_raw=True)
+    assert set(out) == {"weights", "color", "depth", "z_vals", "sdf", "ray_mask", "raw"}
+    loss, parts = crit(out, (rgb.to(device), depth.to(device)))
+    loss.backward()
+    # fused
+    R = rays_o.shape[1]
+    pipe = RenderPipeline(R, device)
+    g_emb = torch.zeros_like(msd["voxel_vertex_emb"])
+    g_dec = [torch.zeros_like(p) for p in decd]
+    pipe.bind(rays_o.to(device), rays_d.to(device), {k: v.detach() for k, v in msd.items()}, [p.detach() for p in decd],
+              voxel_size=s.voxel_size, step_size=0.1 * s.voxel_size, truncation=0.1, max_distance=10.0,
+              target_rgb=rgb.to(device), target_depth=depth.to(device), seed=77, weights=crit.weights(), g_emb=g_emb, g_dec=g_dec,
+              grad_rays=True)
+    pipe.step()
+    l = pipe.losses()
+    assert abs(l["loss"] - float(loss)) < 1e-5 * abs(float(loss))
+    for k in ("color_loss", "depth_loss", "fs_loss", "sdf_loss"):
+        assert abs(l[k] - parts[k]) <= 1e-5 * max(abs(parts[k]), 1e-12)
+    assert rel_err(msd["voxel_vertex_emb"].grad, g_emb) < 1e-5
+    for a, b in zip(decd, g_dec):
+        assert rel_err(a.grad, b) < 1e-5
+    assert rel_err(ro_d.grad.view(-1, 3), pipe.g_rays_o[:R]) < 1e-5
+    assert rel_err(rd_d.grad.view(-1, 3), pipe.g_rays_d[:R]) < 1e-5
+
+
+def test_render_rays_edge_cases(device):
+    from proud_slam_b200.variations import render_helpers as rh
+    s, ms, msd, dec, rays_o, rays_d, rgb, depth = _setup(device)
+    decd = [p.detach().to(device) for p in dec]
+    away = rays_o.clone() + 500.0   # rays that never meet the map: the reference asserts (render_helpers.py:388)
+    with pytest.raises(AssertionError):
+        rh.render_rays(away.to(device), rays_d.to(device), msd, decd, None, 0.02, s.voxel_size, 0.1, 10, 10.0)
+    out = rh.render_rays(rays_o.to(device), rays_d.to(device), msd, decd, None, 0.02, s.voxel_size, 0.1, 10, 10.0)
+    assert out["raw"] is None and out["ray_mask"].shape == (1, rays_o.shape[1])
+    Rh = int(out["ray_mask"].sum())
+    assert out["color"].shape == (Rh, 3) and out["depth"].shape == (Rh,) and out["weights"].shape == out["z_vals"].shape == out["sdf"].shape
+    assert torch.all(out["sdf"][out["z_vals"] == 10.0] == 1.0)            # pads: z = 10, sdf = 1
+    assert torch.allclose(out["weights"].sum(-1), torch.ones(Rh, device=device), atol=1e-4)
+
+
+def test_tracking_and_mapping_loops_run_and_improve(device):
+    """bundle_adjust_frames lowers the loss on a fixed batch; track_frame pulls a perturbed pose back."""
+    from proud_slam_b200 import scene as sc, svo
+    from proud_slam_b200.criterion import Criterion
+    from proud_slam_b200.variations import render_helpers as rh
+    from proud_slam_b200.variations.nrgbd import Decoder
+    torch.manual_seed(0)
+    s = sc.make_scene("tiny")
+    tree = svo.Octree()
+    tree.init(s.grid_dim, 16, s.voxel_size, 8)
+    tree.insert(torch.from_numpy(s.voxels))
+    ms = svo.build_map_states(tree, s.voxel_size, num_embeddings=2048, device=device, seed=0)
+    ms["voxel_vertex_emb"].requires_grad_(True)
+    dec = Decoder(depth=2, width=128, in_dim=16, skips=[], embedder="none").to(device)
+    args = types.SimpleNamespace(criteria=dict(rgb_weight=0.5, depth_weight=1.0, sdf_weight=5000.0, fs_weight=10.0, sdf_truncation=0.1),
+                                 data_specs=dict(max_depth=10.0))
+    crit = Criterion(args)
+    frames = [util.TestFrame(s, s.frames[i], stamp=i, device=device, seed=i) for i in range(2)]
+    embed_optim = torch.optim.Adam([ms["voxel_vertex_emb"]], lr=5e-3)
+    model_optim = torch.optim.Adam(dec.parameters(), lr=5e-3)
+
+    def eval_loss():
+        g = torch.Generator().manual_seed(123)
+        f = frames[0]
+        idx = torch.randperm(f.rays_d.shape[0], generator=g)[:512].to(device)
+        pose = f.get_pose().detach()
+        rd = (f.rays_d[idx] @ pose[:3, :3].t()).unsqueeze(0)
+        ro_ = pose[:3, 3].view(1, 1, 3).expand_as(rd).contiguous()
+        with torch.no_grad():
+            out = rh.render_rays(ro_, rd, ms, dec, None, 0.1 * s.voxel_size, s.voxel_size, 0.1, 10, 10.0, seed=5)
+            loss, _ = crit(out, (f.rgb[idx].unsqueeze(0), f.depth[idx].unsqueeze(0)))
+        return float(loss)
+
+    before = eval_loss()
+    rh.bundle_adjust_frames(frames, ms, dec, None, crit, s.voxel_size, 0.1 * s.voxel_size, N_rays=512, num_iterations=30,
+                            truncation=0.1, max_voxel_hit=10, max_distance=10.0, embed_optim=embed_optim, model_optim=model_optim,
+                            update_pose=True)
+    after = eval_loss()
+    assert after < 0.7 * before, (before, after)
+    # tracking: start 3 cm off, expect to end closer to the true pose
+    true_t = frames[1].pose.translation().detach().clone()
+    start = util.TestFrame(s, s.frames[1], stamp=1, device=device, perturb=(0.03, -0.02, 0.02), seed=9)
+    e0 = float((start.pose.translation().detach() - true_t).norm())
+    pose, optim, hit_mask = rh.track_frame(start.pose, start, {k: v.detach() for k, v in ms.items()}, dec, None, crit, s.voxel_size,
+                                           N_rays=1024, step_size=0.1 * s.voxel_size, num_iterations=40, truncation=0.1,
+                                           learning_rate=0.01, max_voxel_hit=10, max_distance=10.0, depth_variance=True)
+    e1 = float((pose.translation().detach() - true_t).norm())
+    assert hit_mask.shape == (1024,) and hit_mask.dtype == torch.bool
+    assert e1 < e0, (e0, e1)

@@ -244,3 +244,32 @@ def oracle_field(out, rays_o, rays_d, ms, dec, voxel_size):
     sidx = out["_dbg"]["samples"]["sampled_point_voxel_idx"].long()
     f = ro.get_features_vox(xyz[smask], sidx[smask], ms, voxel_size)
     return ro.decoder_forward(dec, f)
+
+
+# ---------------------------------------------------------------- a frame like the reference's RGBDFrame
+class TestFrame:
+    """Duck-type of reference ``src/frame.py:10-85`` for the loop tests: rays_d per pixel, rgb, depth,
+    an OptimizablePose, ``sample_rays`` (uniform without replacement), ``get_pose``."""
+
+    def __init__(self, scene, frame, stamp, device, perturb=None, seed=0):
+        from proud_slam_b200.se3pose import OptimizablePose
+        self.stamp = stamp
+        self.rays_d = scene.rays_cam.reshape(-1, 3).to(device)
+        self.rgb = frame.rgb.reshape(-1, 3).to(device)
+        self.depth = frame.depth.reshape(-1).to(device)
+        pose = frame.pose.clone()
+        if perturb is not None:
+            pose[:3, 3] += torch.as_tensor(perturb, dtype=torch.float32)
+        self.pose = OptimizablePose.from_matrix(pose).to(device)
+        self.optim = torch.optim.Adam(self.pose.parameters(), lr=1e-3)
+        self.gen = torch.Generator().manual_seed(seed)
+        self.sample_mask = None
+
+    def get_pose(self):
+        return self.pose.matrix()
+
+    def sample_rays(self, n):
+        idx = torch.randperm(self.rays_d.shape[0], generator=self.gen)[:n]
+        m = torch.zeros(self.rays_d.shape[0], dtype=torch.bool)
+        m[idx] = True
+        self.sample_mask = m.to(self.rays_d.device)
