@@ -38,8 +38,12 @@ def test_ray_intersect_vox_and_ray_sample_match_oracle(device):
     smp_ref, noise = ro.ray_sample(inter_ref, 0.1 * s.voxel_size, generator=torch.Generator().manual_seed(3))
     inter = {k: v[0][mask.to(device)] for k, v in out.items()}
     smp = vh.ray_sample(inter, 0.1 * s.voxel_size, noise=noise.to(device))
-    for k in ("sampled_point_voxel_idx", "sampled_point_depth", "sampled_point_distance"):
-        assert torch.equal(smp[k].cpu(), smp_ref[k]), k
+    # ids bit-exact; depths only to rounding here because probs/steps come from torch.sum, whose
+    # reduction order differs between CPU and CUDA (SURVEY A-Q10) -- the kernel itself is compared
+    # bit for bit on identical inputs in test_gpu_grid.py
+    assert torch.equal(smp["sampled_point_voxel_idx"].cpu(), smp_ref["sampled_point_voxel_idx"])
+    for k in ("sampled_point_depth", "sampled_point_distance"):
+        assert torch.allclose(smp[k].cpu(), smp_ref[k], rtol=1e-5, atol=1e-6), k
     assert "probs" in inter and "steps" in inter   # the reference adds them to the dict too
 
 
