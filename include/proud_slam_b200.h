@@ -109,6 +109,8 @@ int pslam_uniform_ray_sampling(int b, int num_rays, int max_hits, int max_steps,
 int pslam_debug_rcp(const float *in, float *out, int n, pslam_stream_t stream);
 /* Test helper: D[128,N] = A[128,K] * B[N,K]^T on one CTA through the same tcgen05 / tensor-memory
  * primitives the decoder uses (split3 != 0: 3xTF32).  N in 16..144 step 16, K in 8..144 step 8. */
+/* Test helper: timeline trace of CTA 0 of the tcgen05 decoder kernels into dev_buf[4*10*8] (clock64), NULL = off. */
+int pslam_debug_tc_trace(long long *dev_buf);
 int pslam_debug_umma_gemm(const float *A, const float *B, float *D, int N, int K, int split3, pslam_stream_t stream);
 
 /* ------------------------------------------------------------------------

@@ -61,6 +61,7 @@ _PROTOTYPES = {
     "pslam_inverse_cdf_sampling": (C.c_int, [_I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _S]),
     "pslam_uniform_ray_sampling": (C.c_int, [_I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _S]),
     "pslam_debug_rcp": (C.c_int, [_P, _P, _I, _S]),
+    "pslam_debug_tc_trace": (C.c_int, [_P]),
     "pslam_debug_umma_gemm": (C.c_int, [_P, _P, _P, _I, _I, _I, _S]),
     "pslam_set_option": (C.c_int, [_I, _I]),
     "pslam_decoder_ws_count": (C.c_int64, [_I]),

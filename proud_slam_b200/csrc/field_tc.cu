@@ -31,7 +31,8 @@ namespace pslam {
 using namespace umma;
 
 namespace tc {
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;     // warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 workers
+constexpr int kWorkers = 256;
 constexpr int kStages = 8;
 constexpr int kStageBytes = 18432;   // 144 rows x 16 k x 4 B x (hi, lo)
 constexpr int kTmemCols = 512;
@@ -100,43 +101,52 @@ __global__ void k_tc_pack(pslam_decoder_t d, float *__restrict__ out)
 
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-// One 128-column epilogue: accumulators -> registers -> (bias / activation / mask) -> next A operand
-// (hi/lo split, tensor memory) and optionally the wgrad scratch.
+// One epilogue over this thread's 64 accumulator columns [col0, col0+64): accumulators -> registers ->
+// (bias / activation / mask) -> next A operand (hi/lo split, tensor memory) and optionally the wgrad
+// scratch.  Two worker warps share each TMEM lane quarter and split the columns in halves.
 //   MODE 0: y = relu(D + bias), records y > 0 in mask[]        (forward hidden layers)
 //   MODE 1: y = D + bias                                       (forward, no activation)
 //   MODE 2: y = mask ? D : 0                                   (dgrad through a ReLU)
 //   MODE 3: y = D                                              (dgrad, no activation)
 template <int MODE>
-__device__ __forceinline__ void epilogue128(uint32_t trow, const float *bias, uint32_t (&mask)[4], unsigned char *scratch)
+__device__ __forceinline__ void epilogue64(uint32_t trow, int col0, const float *bias, uint32_t (&mask)[2], unsigned char *scratch)
 {
     using namespace tc;
-    if (MODE == 0) { mask[0] = mask[1] = mask[2] = mask[3] = 0u; }
 #pragma unroll
-    for (int c0 = 0; c0 < 128; c0 += 16) {   // fully unrolled: mask[] must stay in registers
-        uint32_t v[16], hi[16], lo[16];
-        tmem_ld16(trow + cD + c0, v);
+    for (int b = 0; b < 2; ++b) {   // fully unrolled: mask[] must stay in registers
+        const int c0 = col0 + 32 * b;
+        uint32_t v[32];
+        tmem_ld32(trow + cD + c0, v);
         tmem_wait_ld();
         uint32_t bits = 0u;
-        const uint32_t mword = mask[c0 >> 5] >> (c0 & 31);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
+        for (int e = 0; e < 32; ++e) {
             float y = __uint_as_float(v[e]);
             if (MODE == 0) { y = fmaxf(y + bias[c0 + e], 0.0f); bits |= (y > 0.0f ? 1u : 0u) << e; }
             if (MODE == 1) y = y + bias[c0 + e];
-            if (MODE == 2) y = ((mword >> e) & 1u) ? y : 0.0f;
+            if (MODE == 2) y = ((mask[b] >> e) & 1u) ? y : 0.0f;
             v[e] = __float_as_uint(y);
-            tf32_split(y, hi[e], lo[e]);
         }
-        if (MODE == 0) mask[c0 >> 5] |= bits << (c0 & 31);
-        tmem_st16(trow + cAHI + c0, hi);
-        tmem_st16(trow + cALO + c0, lo);
+        if (MODE == 0) mask[b] = bits;
         if (scratch) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < 8; ++j)
                 *reinterpret_cast<uint4 *>(scratch + (size_t)(c0 / 4 + j) * 512) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
+        uint32_t lo[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) { uint32_t h; tf32_split(__uint_as_float(v[e]), h, lo[e]); v[e] = h; }
+        tmem_st32(trow + cAHI + c0, v);
+        tmem_st32(trow + cALO + c0, lo);
     }
 }
+
+// optional timeline trace of CTA 0 (pslam_debug_tc_trace): [tile<4][layer<10][8] clock64 stamps
+__device__ long long *g_tc_trace = nullptr;
+#define TC_TRACE(tile_i, layer, slot)                                                                   \
+    do {                                                                                                \
+        if (g_tc_trace && blockIdx.x == 0 && (tile_i) < 4) g_tc_trace[((tile_i) * 10 + (layer)) * 8 + (slot)] = clock64(); \
+    } while (0)
 
 template <bool BWD>
 __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc(FieldParams p, const float *__restrict__ wstream)
@@ -157,7 +167,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc(FieldParams p, con
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
-        mbar_init(a_ready, 128);
+        mbar_init(a_ready, kWorkers);
         mbar_init(mma_done, 1);
         fence_barrier_init();
     }
@@ -178,40 +188,46 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc(FieldParams p, con
     const uint32_t tmem = *tmem_ptr;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            int stage = 0, phase = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const unsigned char *src = reinterpret_cast<const unsigned char *>(wstream);
-                for (int l = 0; l < NL; ++l) {
-                    const uint32_t bytes = (uint32_t)cN[l] * 128u;
-                    for (int c = 0; c < cK[l] / 16; ++c) {
-                        mbar_wait(empty + stage, phase ^ 1);
+        // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
+        int stage = 0, phase = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const unsigned char *src = reinterpret_cast<const unsigned char *>(wstream);
+            for (int l = 0; l < NL; ++l) {
+                const uint32_t bytes = (uint32_t)cN[l] * 128u;
+                for (int c = 0; c < cK[l] / 16; ++c) {
+                    mbar_wait(empty + stage, phase ^ 1);
+                    if (elect_one()) {
                         mbar_arrive_expect_tx(full + stage, bytes);
                         bulk_g2s(smem + stage * kStageBytes, src, bytes, full + stage);
-                        src += bytes;
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
+                    __syncwarp();
+                    src += bytes;
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            int stage = 0, phase = 0;
-            uint32_t uses = 0;   // a_ready phase counter
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                for (int l = 0; l < NL; ++l) {
-                    const int N = cN[l];
-                    const uint32_t idesc = idesc_tf32(128, N);
-                    mbar_wait(a_ready, uses & 1);
-                    ++uses;
+        // ===================== MMA issuer (whole warp loops so that operands stay warp-uniform;
+        // one elected lane issues tcgen05.mma / tcgen05.commit) =====================
+        int stage = 0, phase = 0;
+        uint32_t uses = 0;   // a_ready phase counter
+        int tile_i = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_i) {
+            for (int l = 0; l < NL; ++l) {
+                const int N = cN[l];
+                const uint32_t idesc = idesc_tf32(128, N);
+                if (lane == 0) TC_TRACE(tile_i, l, 0);          // MMA warp starts waiting for A
+                mbar_wait(a_ready, uses & 1);
+                ++uses;
+                fence_after_sync();
+                if (lane == 0) TC_TRACE(tile_i, l, 1);          // A ready seen
+                const uint32_t a_hi = tmem + cAHI + cAoff[l], a_lo = tmem + cALO + cAoff[l], d = tmem + cD;
+                const int nchunks = cK[l] / 16;
+                for (int c = 0; c < nchunks; ++c) {
+                    mbar_wait(full + stage, phase);
                     fence_after_sync();
-                    const uint32_t a_hi = tmem + cAHI + cAoff[l], a_lo = tmem + cALO + cAoff[l], d = tmem + cD;
-                    for (int c = 0; c < cK[l] / 16; ++c) {
-                        mbar_wait(full + stage, phase);
-                        fence_after_sync();
-                        const uint32_t sb = smem_u32(smem + stage * kStageBytes);
+                    const uint32_t sb = smem_u32(smem + stage * kStageBytes);
+                    if (elect_one()) {
 #pragma unroll
                         for (int s = 0; s < 2; ++s) {
                             const uint32_t k = c * 16 + s * 8;
@@ -221,38 +237,48 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc(FieldParams p, con
                             mma_tf32_ts(d, a_hi + k, b_lo, idesc, 1u);
                             mma_tf32_ts(d, a_hi + k, b_hi, idesc, 1u);
                         }
-                        mma_commit(empty + stage);   // stage is free once these MMAs have read it
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        mma_commit(empty + stage);                     // stage is free once these MMAs have read it
+                        if (c == nchunks - 1) mma_commit(mma_done);
                     }
-                    mma_commit(mma_done);
+                    __syncwarp();
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
+                if (lane == 0) TC_TRACE(tile_i, l, 2);          // all MMAs of the layer issued + committed
             }
         }
     } else {
-        // ===================== workers: one thread per sample row =====================
+        // ===================== workers: two threads per sample row (64 accumulator columns each) =====================
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;             // which 64 columns
+        const int col0 = half * 64;
+        const bool lead = half == 0;                  // the row's thread that also gathers / scatters
         const int m = q * 32 + lane;                  // row of the tile
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
         uint32_t done_uses = 0;
-        uint32_t nomask[4] = {0u, 0u, 0u, 0u};
+        uint32_t nomask[2] = {0u, 0u};
+        int tile_i = 0, lcount = -1;                  // trace bookkeeping (warp 2 lane 0 stamps)
         auto layer_done = [&]() {
             mbar_wait(mma_done, done_uses & 1);
             ++done_uses;
             fence_after_sync();
+            if (threadIdx.x == 64) TC_TRACE(tile_i, lcount, 3);     // worker sees the accumulators
         };
         auto a_is_ready = [&]() {
             tmem_wait_st();
             fence_before_sync();
+            if (threadIdx.x == 64) TC_TRACE(tile_i, lcount + 1, 5);  // worker has produced the A of layer lcount+1
             mbar_arrive(a_ready);
+            ++lcount;
         };
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_i, lcount = -1) {
             const int s = tile * 128 + m;
             unsigned char *scr = nullptr;   // this thread's 16-byte column in the tile's wgrad scratch
             if (BWD && p.wg_scratch) scr = p.wg_scratch + ((size_t)tile * 4 + q) * kSliceBytes + (size_t)lane * 16;
             int vox = -1, ray = -1;
             float z = 0.0f, px = 0.f, py = 0.f, pz = 0.f;
-            // ---- features -> A[:, 128:144) ----
-            {
+            if (threadIdx.x == 64) TC_TRACE(tile_i, 0, 6);            // gather starts
+            // ---- features -> A[:, 128:144) (the lead thread of each row) ----
+            if (lead) {
                 float f[16];
 #pragma unroll
                 for (int e = 0; e < 16; ++e) f[e] = 0.0f;
@@ -298,20 +324,20 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc(FieldParams p, con
                     for (int j = 0; j < 4; ++j)
                         *reinterpret_cast<float4 *>(scr + (size_t)(gF + j) * 512) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
                 }
-                a_is_ready();
             }
-            uint32_t m1[4], m2[4], mc[4];
+            a_is_ready();
+            uint32_t m1[2], m2[2], mc[2];
             // ---- forward ----
             layer_done();
-            epilogue128<0>(trow, sBias, m1, scr ? scr + (size_t)gH1 * 512 : nullptr);           // h1
+            epilogue64<0>(trow, col0, sBias, m1, scr ? scr + (size_t)gH1 * 512 : nullptr);           // h1
             a_is_ready();
             layer_done();
-            epilogue128<0>(trow, sBias + 128, m2, scr ? scr + (size_t)gH2 * 512 : nullptr);     // h2
+            epilogue64<0>(trow, col0, sBias + 128, m2, scr ? scr + (size_t)gH2 * 512 : nullptr);     // h2
             a_is_ready();
             layer_done();
-            epilogue128<1>(trow, sBias + 256, nomask, scr ? scr + (size_t)gT * 512 : nullptr);  // t (no activation)
-            float sdf;
-            {
+            epilogue64<1>(trow, col0, sBias + 256, nomask, scr ? scr + (size_t)gT * 512 : nullptr);  // t (no activation)
+            float sdf = 0.0f;
+            if (lead) {
                 uint32_t v[16];
                 tmem_ld16(trow + cD + 128, v);   // sdf = row 0 of W3, packed as output column 128
                 tmem_wait_ld();
@@ -319,11 +345,11 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc(FieldParams p, con
             }
             a_is_ready();
             layer_done();
-            epilogue128<0>(trow, sBias + 384, mc, scr ? scr + (size_t)gHC * 512 : nullptr);     // hc
+            epilogue64<0>(trow, col0, sBias + 384, mc, scr ? scr + (size_t)gHC * 512 : nullptr);     // hc
             a_is_ready();
             layer_done();
-            float r, g, b;
-            {
+            float r = 0.f, g = 0.f, b = 0.f;
+            if (lead) {
                 uint32_t v[16];
                 tmem_ld16(trow + cD, v);
                 tmem_wait_ld();
@@ -332,13 +358,13 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc(FieldParams p, con
                 b = sigmoid_f(__uint_as_float(v[2]) + sBias[515]);
             }
             if (!BWD) {
-                if (s < nsamp) *reinterpret_cast<float4 *>(p.out + (size_t)s * 4) = make_float4(r, g, b, sdf);
+                if (lead && s < nsamp) *reinterpret_cast<float4 *>(p.out + (size_t)s * 4) = make_float4(r, g, b, sdf);
                 continue;   // D has been read; the next tile's first MMA is ordered behind it through a_ready
             }
             // ---- backward ----
             float4 go = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (s < nsamp) go = __ldg(reinterpret_cast<const float4 *>(p.g_out + (size_t)s * 4));
-            {
+            if (lead) {
+                if (s < nsamp) go = __ldg(reinterpret_cast<const float4 *>(p.g_out + (size_t)s * 4));
                 // dL/d(pre-sigmoid rgb): grad * (1 - y) * y ; A[:, 0:16) = [g5 r,g,b, 0...]
                 const float g5[4] = {go.x * (1.0f - r) * r, go.y * (1.0f - g) * g, go.z * (1.0f - b) * b, go.w};
                 uint32_t hi[16], lo[16];
@@ -353,15 +379,17 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc(FieldParams p, con
 #pragma unroll
                     for (int j = 1; j < 4; ++j) *reinterpret_cast<float4 *>(scr + (size_t)(gG5 + j) * 512) = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                a_is_ready();
             }
-            layer_done();
-            epilogue128<2>(trow, nullptr, mc, scr ? scr + (size_t)gG4 * 512 : nullptr);         // g_hc
             a_is_ready();
             layer_done();
-            epilogue128<3>(trow, nullptr, nomask, scr ? scr + (size_t)gG3 * 512 : nullptr);     // g_t
+            epilogue64<2>(trow, col0, nullptr, mc, scr ? scr + (size_t)gG4 * 512 : nullptr);         // g_hc
+            a_is_ready();
+            layer_done();
+            epilogue64<3>(trow, col0, nullptr, nomask, scr ? scr + (size_t)gG3 * 512 : nullptr);     // g_t
             float gf[16];
-            {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) gf[e] = 0.0f;
+            if (lead) {
                 uint32_t v[16], hi[16], lo[16];
                 tmem_ld16(trow + cD + 128, v);   // g_f, part through W4's last 16 input columns
                 tmem_wait_ld();
@@ -373,12 +401,13 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc(FieldParams p, con
             }
             a_is_ready();
             layer_done();
-            epilogue128<2>(trow, nullptr, m2, scr ? scr + (size_t)gG2 * 512 : nullptr);         // g_h2
+            epilogue64<2>(trow, col0, nullptr, m2, scr ? scr + (size_t)gG2 * 512 : nullptr);         // g_h2
             a_is_ready();
             layer_done();
-            epilogue128<2>(trow, nullptr, m1, scr ? scr + (size_t)gG1 * 512 : nullptr);         // g_h1
+            epilogue64<2>(trow, col0, nullptr, m1, scr ? scr + (size_t)gG1 * 512 : nullptr);         // g_h1
             a_is_ready();
             layer_done();
+            if (!lead) continue;
             {
                 uint32_t v[16];
                 tmem_ld16(trow + cD, v);
@@ -448,10 +477,20 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc(FieldParams p, con
 // Bias gradients are column sums of the G groups, accumulated by the loader threads.
 // ------------------------------------------------------------------------------------------
 namespace wg {
-constexpr int kThreads = 256;
-constexpr int kBufBytes = 2 * 272 * 128;        // hi + lo of A' (128 rows) + B' (<= 144 rows), 32 samples each
-constexpr int oBars = 2 * kBufBytes;            // two buffers, then 2 mbarriers + tmem ptr
-constexpr int oBiasAcc = oBars + 64;            // float[4][128] column sums of G1..G4 + [16] of G5
+constexpr int kXformWarps = 12;
+constexpr int kXform = kXformWarps * 32;
+constexpr int kThreads = kXform + 64;           // transform warps, then the TMA producer warp, then the MMA issuer warp
+constexpr int kStepSamples = 32;                // samples contracted per step (one scratch slice; 4 MMA k-steps)
+constexpr int kQuads = kStepSamples / 4;        // 16-byte k-chunks per step
+constexpr int kPieces = 32 / kStepSamples;      // steps per 32-sample scratch slice
+constexpr int kStepsPerTile = (128 / kStepSamples) * 6;
+constexpr int kRawPitch = kStepSamples * 16;    // raw group pitch (unpadded: whole operands arrive as single bulk copies)
+constexpr int kRawBytes = 68 * kRawPitch;       // one step's raw fp32 groups: A' (32) + B' (<= 36)
+constexpr int kOpBytes = 2 * 272 * kStepSamples * 4;   // hi + lo of A' (128 rows) + B' (<= 144 rows)
+constexpr int kRawStages = kStepSamples == 32 ? 2 : 6, kOpStages = 2;
+constexpr int oOps = kRawStages * kRawBytes;
+constexpr int oBars = oOps + kOpStages * kOpBytes;   // raw_full[6] raw_free[6] op_full[2] op_free[2] all_done, tmem ptr
+constexpr int oBiasAcc = oBars + 256;           // float[4][128] column sums of G1..G4 + [16] of G5
 constexpr int kSmemBytes = oBiasAcc + 4 * (4 * 128 + 16);
 struct Step { int a_group, a_cnt, b_group, b_cnt, b2_group, b2_cnt, dcol; };
 // A' (M' = 128 output rows n) , B' (N' columns), accumulator column
@@ -465,13 +504,6 @@ __device__ __constant__ Step cSteps[6] = {
 };
 }  // namespace wg
 
-// instruction descriptor with both operands MN-major (bits 15, 16)
-__host__ __device__ constexpr uint32_t idesc_tf32_mn(int M, int N) { return idesc_tf32(M, N) | (1u << 15) | (1u << 16); }
-// shared-memory descriptor, MN-major no swizzle: LBO = stride between 8-K blocks, SBO = between MN groups of 4
-__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t smem_addr, uint32_t lbo, uint32_t sbo)
-{
-    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
-}
 __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile(
@@ -482,143 +514,184 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, ui
         : "memory");
 }
 
+// Three-role pipeline per CTA (persistent over its tiles, 24 steps per tile = 4 slices x 6 GEMMs):
+//   TMA producer   : bulk-copies the step's raw fp32 groups from the scratch into a small ring
+//   transform warps: raw -> registers (transpose, hi/lo split) -> operand buffers (2 stages)
+//   MMA issuer     : 12 MMAs per step (4 k-steps x 3xTF32), commit frees the operand buffer
+#define WG_TRACE(g, slot)                                                                           \
+    do {                                                                                            \
+        if (g_tc_trace && blockIdx.x == 0 && (g) < 40) g_tc_trace[(g) * 8 + (slot)] = clock64();     \
+    } while (0)
+
 __global__ void __launch_bounds__(wg::kThreads, 1) k_wgrad_tc(FieldParams p)
 {
     using namespace wg;
     extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + oBars);      // buffer-free barriers
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(smem + oBars + 32);
+    uint64_t *raw_full = reinterpret_cast<uint64_t *>(smem + oBars);
+    uint64_t *raw_free = raw_full + kRawStages, *op_full = raw_free + kRawStages, *op_free = op_full + 2, *all_done = op_free + 2;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(smem + oBars + 192);
     float *sBiasAcc = reinterpret_cast<float *>(smem + oBiasAcc);
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nsamp = p.nsamp_dev ? *p.nsamp_dev : p.nsamp;
     const int ntiles = (nsamp + 127) / 128;
-    if (tid == 0) { mbar_init(bars, 1); mbar_init(bars + 1, 1); fence_barrier_init(); }
-    if (warp == 0) tmem_alloc(tmem_ptr, 512);
+    if (tid == 0) {
+        for (int i = 0; i < kRawStages; ++i) { mbar_init(raw_full + i, 1); mbar_init(raw_free + i, kXform); }
+        for (int i = 0; i < 2; ++i) { mbar_init(op_full + i, kXform); mbar_init(op_free + i, 1); }
+        mbar_init(all_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == kXformWarps + 1) tmem_alloc(tmem_ptr, 512);
     for (int i = tid; i < 4 * 128 + 16; i += kThreads) sBiasAcc[i] = 0.0f;
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem = *tmem_ptr;
-    if ((int)blockIdx.x >= ntiles) {   // nothing to do (and nothing to flush)
-        __syncthreads();
-        if (warp == 0) tmem_dealloc(tmem, 512);
-        return;
-    }
-    uint32_t use0 = 0u, use1 = 0u;    // how many commits each buffer has seen (thread-uniform)
-    int buf = 0;
-    uint32_t started = 0u;            // bit st: accumulator of step st has been written
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int sl = 0; sl < 4; ++sl) {
-            const unsigned char *slice = p.wg_scratch + ((size_t)tile * 4 + sl) * tc::kSliceBytes;
-            for (int st = 0; st < 6; ++st, buf ^= 1) {
-                const Step S = cSteps[st];
-                unsigned char *sbuf = smem + buf * kBufBytes;    // [A' hi][B' hi][A' lo][B' lo]
-                const int ngroups = S.a_cnt + S.b_cnt + S.b2_cnt;
-                // wait until the MMAs that last read this buffer are done
-                const uint32_t used = buf ? use1 : use0;
-                if (used > 0) mbar_wait(bars + buf, (used - 1) & 1);
-                // load + transpose + split.  Scratch unit = 4 features of ONE sample; the K-major operand wants
-                // 16-byte chunks of 4 consecutive SAMPLES of one feature, so each thread turns a 4x4 block
-                // (4 consecutive samples x one feature group) around in registers.
-                const int rowsB = 4 * (S.b_cnt + S.b2_cnt);          // B' rows (N'); A' always has 128
-                unsigned char *sA_hi = sbuf, *sB_hi = sbuf + 128 * 128;       // [8 k-chunks][rows][16 B]
-                unsigned char *sA_lo = sbuf + 272 * 128, *sB_lo = sA_lo + 128 * 128;
-                for (int u = tid; u < ngroups * 8; u += kThreads) {
-                    const int gi = u >> 3, quad = u & 7;             // feature group, 4-sample block of the slice
-                    int src_group, row0;
-                    unsigned char *dhi, *dlo;
-                    int rows;
-                    if (gi < S.a_cnt) { src_group = S.a_group + gi; row0 = gi * 4; dhi = sA_hi; dlo = sA_lo; rows = 128; }
-                    else {
-                        const int gb = gi - S.a_cnt;
-                        src_group = gb < S.b_cnt ? S.b_group + gb : S.b2_group + (gb - S.b_cnt);
-                        row0 = gb * 4; dhi = sB_hi; dlo = sB_lo; rows = rowsB;
-                    }
-                    const float4 *src = reinterpret_cast<const float4 *>(slice + (size_t)src_group * 512 + quad * 64);
-                    const float4 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3];   // samples 4*quad .. +3
-                    const float t[4][4] = {{v0.x, v1.x, v2.x, v3.x}, {v0.y, v1.y, v2.y, v3.y}, {v0.z, v1.z, v2.z, v3.z}, {v0.w, v1.w, v2.w, v3.w}};
-#pragma unroll
-                    for (int f = 0; f < 4; ++f) {
-                        uint4 hi, lo;
-                        tf32_split(t[f][0], hi.x, lo.x); tf32_split(t[f][1], hi.y, lo.y);
-                        tf32_split(t[f][2], hi.z, lo.z); tf32_split(t[f][3], hi.w, lo.w);
-                        const size_t off = (size_t)quad * rows * 16 + (size_t)(row0 + f) * 16;
-                        *reinterpret_cast<uint4 *>(dhi + off) = hi;
-                        *reinterpret_cast<uint4 *>(dlo + off) = lo;
-                    }
-                    // bias gradients: column sums of the G operands (steps 0..3 carry G2, G3, G4, G1 as A';
-                    // step 4 carries G5 = (g5 r,g,b, g_sdf) as the first B' group)
-                    const bool is_g = (st < 4 && gi < S.a_cnt) || (st == 4 && gi == S.a_cnt);
-                    if (is_g) {   // 8 consecutive lanes share a group; shuffles name only those lanes
-                        const unsigned gm = 0xFFu << ((tid & 31) & ~7);
-                        float4 sum = make_float4(t[0][0] + t[0][1] + t[0][2] + t[0][3], t[1][0] + t[1][1] + t[1][2] + t[1][3],
-                                                 t[2][0] + t[2][1] + t[2][2] + t[2][3], t[3][0] + t[3][1] + t[3][2] + t[3][3]);
-#pragma unroll
-                        for (int o = 4; o > 0; o >>= 1) {
-                            sum.x += __shfl_xor_sync(gm, sum.x, o); sum.y += __shfl_xor_sync(gm, sum.y, o);
-                            sum.z += __shfl_xor_sync(gm, sum.z, o); sum.w += __shfl_xor_sync(gm, sum.w, o);
-                        }
-                        if (quad == 0) {   // the same thread owns this (step, group) in every slice: no race
-                            float *acc = (st < 4) ? sBiasAcc + st * 128 + gi * 4 : sBiasAcc + 512;
-                            acc[0] += sum.x; acc[1] += sum.y; acc[2] += sum.z; acc[3] += sum.w;
-                        }
-                    }
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic smem writes -> async proxy (MMA)
-                __syncthreads();
-                if (tid == 0) {
-                    fence_after_sync();
-                    const uint32_t idesc = idesc_tf32(128, rowsB);
-                    const uint32_t a_hi = smem_u32(sA_hi), b_hi = smem_u32(sB_hi), a_lo = smem_u32(sA_lo), b_lo = smem_u32(sB_lo);
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {                    // 4 x 8 samples = 4 x 2 k-chunks
-                        const uint64_t dah = bdesc_kmajor(a_hi + ks * 2 * 128 * 16, 128), dal = bdesc_kmajor(a_lo + ks * 2 * 128 * 16, 128);
-                        const uint64_t dbh = bdesc_kmajor(b_hi + ks * 2 * rowsB * 16, rowsB), dbl = bdesc_kmajor(b_lo + ks * 2 * rowsB * 16, rowsB);
-                        mma_tf32_ss(tmem + S.dcol, dal, dbh, idesc, (!((started >> st) & 1u) && ks == 0) ? 0u : 1u);
-                        mma_tf32_ss(tmem + S.dcol, dah, dbl, idesc, 1u);
-                        mma_tf32_ss(tmem + S.dcol, dah, dbh, idesc, 1u);
-                    }
-                    mma_commit(bars + buf);
-                }
-                started |= 1u << st;
-                if (buf) ++use1; else ++use0;
+    const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int nsteps = my_tiles * kStepsPerTile;
+
+    if (warp == kXformWarps) {
+        // ===================== TMA producer =====================
+        for (int g = 0; g < nsteps; ++g) {
+            const int tl = g / kStepsPerTile, hs = (g / 6) % (4 * kPieces), st = g % 6, rs = g % kRawStages, use = g / kRawStages;
+            const Step S = cSteps[st];
+            // piece hs of the tile: lanes [kStepSamples (hs % kPieces), +kStepSamples) of slice hs / kPieces
+            const unsigned char *slice = p.wg_scratch + ((size_t)(blockIdx.x + (size_t)tl * gridDim.x) * 4 + hs / kPieces) * tc::kSliceBytes +
+                                         (hs % kPieces) * (kStepSamples * 16);
+            if (use >= 1) mbar_wait(raw_free + rs, (use - 1) & 1);
+            if (lane == 0) WG_TRACE(g, 0);
+            if (elect_one()) {
+                unsigned char *dst = smem + rs * kRawBytes;
+                mbar_arrive_expect_tx(raw_full + rs, (uint32_t)(S.a_cnt + S.b_cnt + S.b2_cnt) * 512u);
+                bulk_g2s(dst, slice + (size_t)S.a_group * 512, S.a_cnt * 512u, raw_full + rs);
+                bulk_g2s(dst + S.a_cnt * 512, slice + (size_t)S.b_group * 512, S.b_cnt * 512u, raw_full + rs);
+                if (S.b2_cnt) bulk_g2s(dst + (S.a_cnt + S.b_cnt) * 512, slice + (size_t)S.b2_group * 512, S.b2_cnt * 512u, raw_full + rs);
             }
+            __syncwarp();
         }
-    }
-    // drain: wait for the last commits, then accumulators -> global gradients
-    if (use0 > 0) mbar_wait(bars, (use0 - 1) & 1);
-    if (use1 > 0) mbar_wait(bars + 1, (use1 - 1) & 1);
-    fence_after_sync();
-    __syncthreads();
-    if (warp < 4) {
-        const int n = warp * 32 + (tid & 31);                    // accumulator row = TMEM lane
-        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-        auto flush = [&](int col0, int ncols, float *dst_row) {   // dst_row: &dW[n][0], ncols % 16 == 0
-            for (int c0 = 0; c0 < ncols; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(trow + col0 + c0, v);
+    } else if (warp == kXformWarps + 1) {
+        // ===================== MMA issuer =====================
+        uint32_t started = 0u;            // bit st: accumulator of GEMM st has been written
+        for (int g = 0; g < nsteps; ++g) {
+            const int st = g % 6, ob = g & 1;
+            const Step S = cSteps[st];
+            const int rowsB = 4 * (S.b_cnt + S.b2_cnt);
+            mbar_wait(op_full + ob, (g >> 1) & 1);
+            fence_after_sync();
+            if (lane == 0) WG_TRACE(g, 4);
+            const uint32_t base = smem_u32(smem + oOps + ob * kOpBytes);
+            const uint32_t a_hi = base, b_hi = base + 128 * kQuads * 16, a_lo = base + 272 * kQuads * 16, b_lo = a_lo + 128 * kQuads * 16;
+            const uint32_t idesc = idesc_tf32(128, rowsB);
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < kQuads / 2; ++ks) {           // 8 samples = 2 k-chunks per MMA
+                    const uint64_t dah = bdesc_kmajor(a_hi + ks * 2 * 128 * 16, 128), dal = bdesc_kmajor(a_lo + ks * 2 * 128 * 16, 128);
+                    const uint64_t dbh = bdesc_kmajor(b_hi + ks * 2 * rowsB * 16, rowsB), dbl = bdesc_kmajor(b_lo + ks * 2 * rowsB * 16, rowsB);
+                    mma_tf32_ss(tmem + S.dcol, dal, dbh, idesc, (!((started >> st) & 1u) && ks == 0) ? 0u : 1u);
+                    mma_tf32_ss(tmem + S.dcol, dah, dbl, idesc, 1u);
+                    mma_tf32_ss(tmem + S.dcol, dah, dbh, idesc, 1u);
+                }
+                mma_commit(op_free + ob);
+                if (g == nsteps - 1) mma_commit(all_done);
+            }
+            __syncwarp();
+            if (lane == 0) WG_TRACE(g, 5);
+            started |= 1u << st;
+        }
+    } else {
+        // ===================== transform warps =====================
+        for (int g = 0; g < nsteps; ++g) {
+            const int st = g % 6, rs = g % kRawStages, ob = g & 1;
+            const Step S = cSteps[st];
+            const int rowsB = 4 * (S.b_cnt + S.b2_cnt);          // B' rows (N'); A' always has 128
+            mbar_wait(raw_full + rs, (g / kRawStages) & 1);
+            if (tid == 0) WG_TRACE(g, 1);
+            if (g >= 2) mbar_wait(op_free + ob, ((g >> 1) - 1) & 1);
+            if (tid == 0) WG_TRACE(g, 2);
+            const unsigned char *raw = smem + rs * kRawBytes;
+            unsigned char *sbuf = smem + oOps + ob * kOpBytes;
+            unsigned char *sA_hi = sbuf, *sB_hi = sbuf + 128 * kQuads * 16;        // [k-chunk][rows][16 B]
+            unsigned char *sA_lo = sbuf + 272 * kQuads * 16, *sB_lo = sA_lo + 128 * kQuads * 16;
+            // Scratch unit = 4 features of ONE sample; the K-major operand wants 16-byte chunks of 4 consecutive
+            // SAMPLES of one feature.  A warp takes one feature group per iteration: lane = (4-sample block q,
+            // feature c of the group).  The four scalar reads of a lane are issued in a q-dependent rotation so
+            // that the 32 lanes always hit 32 distinct banks of the unpadded [sample][4 features] group.
+            const int ngroups = S.a_cnt + S.b_cnt + S.b2_cnt;
+            const int q = lane >> 2, c = lane & 3, rot = (q >> 1) & 3;
+#pragma unroll 2
+            for (int gi = warp; gi < ngroups; gi += kXformWarps) {
+                const bool isA = gi < S.a_cnt;
+                const int rl = (isA ? gi : gi - S.a_cnt) * 4 + c, rows = isA ? 128 : rowsB;
+                const float *src = reinterpret_cast<const float *>(raw + (size_t)gi * 512 + q * 64) + c;
+                float r[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) r[j] = src[((j + rot) & 3) * 4];      // r[j] = sample 4q + (j + rot) % 4
+                // undo the rotation branch-free (two conditional rotations): t[k] = sample 4q + k = r[(k - rot) & 3]
+                const bool rot1 = (rot & 1) != 0, rot2 = (rot & 2) != 0;
+                const float a0 = rot1 ? r[3] : r[0], a1 = rot1 ? r[0] : r[1], a2 = rot1 ? r[1] : r[2], a3 = rot1 ? r[2] : r[3];
+                const float t[4] = {rot2 ? a2 : a0, rot2 ? a3 : a1, rot2 ? a0 : a2, rot2 ? a1 : a3};
+                uint4 hi, lo;
+                tf32_split(t[0], hi.x, lo.x); tf32_split(t[1], hi.y, lo.y);
+                tf32_split(t[2], hi.z, lo.z); tf32_split(t[3], hi.w, lo.w);
+                const size_t off = (size_t)q * rows * 16 + (size_t)rl * 16;
+                *reinterpret_cast<uint4 *>((isA ? sA_hi : sB_hi) + off) = hi;
+                *reinterpret_cast<uint4 *>((isA ? sA_lo : sB_lo) + off) = lo;
+                // bias gradients: column sums of the G operands (steps 0..3 carry G2, G3, G4, G1 as A';
+                // step 4 carries G5 = (g5 r,g,b, g_sdf) as the first B' group)
+                const bool is_g = (st < 4 && isA) || (st == 4 && gi == S.a_cnt);     // warp-uniform
+                if (is_g) {
+                    float sum = (t[0] + t[1]) + (t[2] + t[3]);
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+                    if (q == 0) {   // the same thread owns this (step, row) in every slice: no race, fixed order
+                        float *acc = (st < 4) ? sBiasAcc + st * 128 + rl : sBiasAcc + 512 + c;
+                        *acc += sum;
+                    }
+                }
+            }
+            mbar_arrive(raw_free + rs);                                   // raw stage consumed
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic smem writes -> async proxy (MMA)
+            mbar_arrive(op_full + ob);
+            if (tid == 0) WG_TRACE(g, 3);
+        }
+        // drain: accumulators -> global gradients (warps 0-3 own the four TMEM lane quarters)
+        if (nsteps > 0 && warp < 4) {
+            mbar_wait(all_done, 0);
+            fence_after_sync();
+            const int n = warp * 32 + lane;                          // accumulator row = TMEM lane
+            const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+            auto flush = [&](int col0, int ncols, float *dst_row) {   // dst_row: &dW[n][0], ncols % 16 == 0
+                for (int c0 = 0; c0 < ncols; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(trow + col0 + c0, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        red_add_v4(dst_row + c0 + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                   __uint_as_float(v[4 * j + 3]));
+                }
+            };
+            flush(0, 128, p.g_dec.W2 + (size_t)n * 128);
+            flush(128, 128, p.g_dec.W3 + (size_t)(1 + n) * 128);
+            flush(256, 144, p.g_dec.W4 + (size_t)n * 144);
+            flush(400, 16, p.g_dec.W1 + (size_t)n * 16);
+            {
+                uint32_t v[16], w[16];
+                tmem_ld16(trow + 416, v);
+                tmem_ld16(trow + 432, w);
                 tmem_wait_ld();
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    red_add_v4(dst_row + c0 + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                               __uint_as_float(v[4 * j + 3]));
+                atomicAdd(p.g_dec.W5 + n, __uint_as_float(v[0]));
+                atomicAdd(p.g_dec.W5 + 128 + n, __uint_as_float(v[1]));
+                atomicAdd(p.g_dec.W5 + 256 + n, __uint_as_float(v[2]));
+                atomicAdd(p.g_dec.W3 + n, __uint_as_float(w[3]));
             }
-        };
-        flush(0, 128, p.g_dec.W2 + (size_t)n * 128);
-        flush(128, 128, p.g_dec.W3 + (size_t)(1 + n) * 128);
-        flush(256, 144, p.g_dec.W4 + (size_t)n * 144);
-        flush(400, 16, p.g_dec.W1 + (size_t)n * 16);
-        {
-            uint32_t v[16], w[16];
-            tmem_ld16(trow + 416, v);
-            tmem_ld16(trow + 432, w);
-            tmem_wait_ld();
-            atomicAdd(p.g_dec.W5 + n, __uint_as_float(v[0]));
-            atomicAdd(p.g_dec.W5 + 128 + n, __uint_as_float(v[1]));
-            atomicAdd(p.g_dec.W5 + 256 + n, __uint_as_float(v[2]));
-            atomicAdd(p.g_dec.W3 + n, __uint_as_float(w[3]));
         }
-        // bias gradients (sBiasAcc rows: step 0 = G2, 1 = G3, 2 = G4, 3 = G1)
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (nsteps > 0 && tid < 128) {
+        // bias gradients (sBiasAcc rows: step 0 = G2, 1 = G3, 2 = G4, 3 = G1); complete after the barrier above
+        const int n = tid;
         atomicAdd(p.g_dec.b2 + n, sBiasAcc[n]);
         atomicAdd(p.g_dec.b3 + 1 + n, sBiasAcc[128 + n]);
         atomicAdd(p.g_dec.b4 + n, sBiasAcc[256 + n]);
@@ -626,17 +699,14 @@ __global__ void __launch_bounds__(wg::kThreads, 1) k_wgrad_tc(FieldParams p)
         if (n < 3) atomicAdd(p.g_dec.b5 + n, sBiasAcc[512 + n]);
         if (n == 3) atomicAdd(p.g_dec.b3, sBiasAcc[515]);
     }
-    fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 512);
+    if (warp == kXformWarps + 1) tmem_dealloc(tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------------
 // stand-alone GEMMs through the same primitives (unit tests of descriptors / TMEM addressing).
 // mode 0/1: D[128,N] = A[128,K] * B[N,K]^T with A in tensor memory, B K-major in shared memory
 //           (1xTF32 / 3xTF32).  K % 8 == 0, N % 16 == 0, both <= 144.
-// mode 2:   D[128,N] = At[K,128]^T * Bt[K,N]: both operands from shared memory, MN-major (the
-//           wgrad form; At/Bt rows are the reduction index), 3xTF32.  K % 32 == 0.
+// mode 4:   same product with BOTH operands K-major in shared memory (the wgrad form), 3xTF32.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, 1) k_debug_umma_gemm(const float *__restrict__ A, const float *__restrict__ B, float *__restrict__ D,
                                                             int N, int K, int mode)
@@ -672,19 +742,6 @@ __global__ void __launch_bounds__(128, 1) k_debug_umma_gemm(const float *__restr
             float *blk = sB + st * (2 * N * 8);
             blk[kc * N * 4 + n * 4 + e] = __uint_as_float(hi);
             blk[N * 8 + kc * N * 4 + n * 4 + e] = __uint_as_float(lo);
-        }
-    } else {
-        // MN-major groups: per 32-row slice of K: [A groups (32)][B groups (N/4)] hi, then the same lo
-        const int ng = 32 + N / 4;
-        for (int i = threadIdx.x; i < K * (128 + N); i += 128) {
-            const int k = i / (128 + N), c = i % (128 + N);
-            const float x = (c < 128) ? A[(size_t)k * 128 + c] : B[(size_t)k * N + (c - 128)];
-            const int gi = c >> 2, e = c & 3, sl = k >> 5, ln = k & 31;
-            uint32_t hi, lo;
-            tf32_split(x, hi, lo);
-            float *base = sB + (size_t)sl * (2 * ng * 128);
-            base[gi * 128 + ln * 4 + e] = __uint_as_float(hi);
-            base[ng * 128 + gi * 128 + ln * 4 + e] = __uint_as_float(lo);
         }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the MMA (async proxy)
@@ -744,20 +801,6 @@ __global__ void __launch_bounds__(128, 1) k_debug_umma_gemm(const float *__restr
                     mma_tf32_ts(tmem + 288, tmem + st * 8, b_hi, idesc, st ? 1u : 0u);
                 }
             }
-        } else {
-            const int ng = 32 + N / 4;
-            const uint32_t idesc = idesc_tf32_mn(128, N);
-            for (int sl = 0; sl < K / 32; ++sl)
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint32_t a_hi = sb + sl * (2 * ng * 512) + ks * 128, b_hi = a_hi + 32 * 512;
-                    const uint32_t a_lo = a_hi + ng * 512, b_lo = b_hi + ng * 512;
-                    const uint32_t lbo = (mode == 3) ? 512 : 128, sbo = (mode == 3) ? 128 : 512;
-                    const uint64_t dah = desc_mnmajor(a_hi, lbo, sbo), dal = desc_mnmajor(a_lo, lbo, sbo);
-                    const uint64_t dbh = desc_mnmajor(b_hi, lbo, sbo), dbl = desc_mnmajor(b_lo, lbo, sbo);
-                    mma_tf32_ss(tmem + 288, dal, dbh, idesc, (sl | ks) ? 1u : 0u);
-                    mma_tf32_ss(tmem + 288, dah, dbl, idesc, 1u);
-                    mma_tf32_ss(tmem + 288, dah, dbh, idesc, 1u);
-                }
         }
         mma_commit(&bar);
     }
@@ -830,12 +873,19 @@ int tc_launch_field_backward(const FieldParams &fp_in, int max_samples, cudaStre
 
 using namespace pslam;
 
+extern "C" int pslam_debug_tc_trace(long long *dev_buf)
+{
+    cudaError_t e = cudaMemcpyToSymbol(g_tc_trace, &dev_buf, sizeof(dev_buf));
+    if (e != cudaSuccess) { set_error("tc_trace: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+
 extern "C" int pslam_debug_umma_gemm(const float *A, const float *B, float *D, int N, int K, int mode, pslam_stream_t stream)
 {
     PSLAM_CHECK_ARG(A && B && D, PSLAM_E_ARG, "null pointer");
     PSLAM_CHECK_ARG(N >= 16 && N <= 144 && N % 16 == 0 && K >= 8 && K <= 144 && K % 8 == 0, PSLAM_E_RANGE, "N in 16..144 step 16, K in 8..144 step 8");
-    PSLAM_CHECK_ARG(mode >= 0 && mode <= 4 && (mode < 2 || mode == 4 || K % 32 == 0), PSLAM_E_RANGE, "mode 0..4; modes 2,3 need K % 32 == 0");
-    const int smem = mode == 4 ? 2 * (128 + N) * K * 4 : (mode < 2 ? 2 * N * K * 4 : (K / 32) * 2 * (32 + N / 4) * 512);
+    PSLAM_CHECK_ARG(mode == 0 || mode == 1 || mode == 4, PSLAM_E_RANGE, "mode must be 0, 1 or 4");
+    const int smem = mode == 4 ? 2 * (128 + N) * K * 4 : 2 * N * K * 4;
     PSLAM_CHECK_ARG(smem <= 200 * 1024, PSLAM_E_RANGE, "operands do not fit in shared memory");
     cudaError_t e = cudaFuncSetAttribute(k_debug_umma_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { set_error("debug_umma: %s", cudaGetErrorString(e)); return (int)e; }
