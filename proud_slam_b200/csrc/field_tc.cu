@@ -31,10 +31,12 @@ namespace pslam {
 using namespace umma;
 
 namespace tc {
-constexpr int kThreads = 320;     // warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 workers
+constexpr int kThreads = 352;     // warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 workers, warp 10 scratch store
 constexpr int kWorkers = 256;
-constexpr int kStages = 8;
+constexpr int kStages = 8;        // weight ring depth of the forward kernel
+constexpr int kStagesBwd = 4;     // ... of the backward kernel (the rest of shared memory stages the wgrad scratch)
 constexpr int kStageBytes = 18432;   // 144 rows x 16 k x 4 B x (hi, lo)
+constexpr int kStagingBytes = 65536; // one layer of one tile in scratch order: [4 slices][32 groups][32 samples][16 B]
 constexpr int kTmemCols = 512;
 constexpr int cAHI = 0, cALO = 144, cD = 288;
 constexpr int kLayersFwd = 5, kLayersAll = 10;
@@ -44,11 +46,16 @@ __device__ __constant__ int cK[kLayersAll] = {16, 128, 128, 144, 128, 16, 128, 1
 __device__ __constant__ int cAoff[kLayersAll] = {128, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 constexpr int hN[kLayersAll] = {128, 128, 144, 128, 16, 128, 144, 128, 128, 16};
 constexpr int hK[kLayersAll] = {16, 128, 128, 144, 128, 16, 128, 144, 128, 128};
-// shared memory map
-constexpr int oBars = kStages * kStageBytes;             // full[8], empty[8], a_ready, mma_done
-constexpr int oTmemPtr = oBars + 8 * (2 * kStages + 2);
-constexpr int oBias = oTmemPtr + 16;                     // b1[128] b2[128] b3f[128] b4[128] b3_0 b5[3]
-constexpr int kSmemBytes = oBias + 4 * (4 * 128 + 4);
+// shared memory map: [weight ring][scratch staging x2 (backward only)][barriers][tmem ptr][biases]
+template <bool BWD>
+struct Smem {
+    static constexpr int nStages = BWD ? kStagesBwd : kStages;
+    static constexpr int oStaging = nStages * kStageBytes;
+    static constexpr int oBars = oStaging + (BWD ? 2 * kStagingBytes : 0);   // full[8], empty[8], a_ready, mma_done, st_full[2], st_free[2]
+    static constexpr int oTmemPtr = oBars + 8 * (2 * kStages + 2 + 4);
+    static constexpr int oBias = oTmemPtr + 16;                     // b1[128] b2[128] b3f[128] b4[128] b3_0 b5[3]
+    static constexpr int bytes = oBias + 4 * (4 * 128 + 4);
+};
 
 // wgrad scratch: per tile, per 32-sample slice, 264 groups of (32 lanes x 4 floats); see k_wgrad_tc
 constexpr int gF = 0, gH1 = 4, gH2 = 36, gT = 68, gHC = 100, gG1 = 132, gG2 = 164, gG3 = 196, gG4 = 228, gG5 = 260, kGroups = 264;
@@ -141,7 +148,7 @@ __device__ __forceinline__ void epilogue64(uint32_t trow, int col0, const float 
     }
 }
 
-// optional timeline trace of CTA 0 (pslam_debug_tc_trace): [tile<4][layer<10][8] clock64 stamps
+// optional timeline trace of CTA 0 (pslam_debug_tc_trace): [tile<4][layer<10][8] clock64 stamps (+ 40 x 8 for k_wgrad_tc)
 __device__ long long *g_tc_trace = nullptr;
 #define TC_TRACE(tile_i, layer, slot)                                                                   \
     do {                                                                                                \
@@ -153,13 +160,16 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc(FieldParams p, con
 {
     using namespace tc;
     constexpr int NL = BWD ? kLayersAll : kLayersFwd;
+    using SM = Smem<BWD>;
+    constexpr int NS = SM::nStages;
     extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + oBars);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + SM::oBars);
     uint64_t *empty = full + kStages;
     uint64_t *a_ready = empty + kStages;
     uint64_t *mma_done = a_ready + 1;
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(smem + oTmemPtr);
-    float *sBias = reinterpret_cast<float *>(smem + oBias);
+    uint64_t *st_full = mma_done + 1, *st_free = st_full + 2;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(smem + SM::oTmemPtr);
+    float *sBias = reinterpret_cast<float *>(smem + SM::oBias);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nsamp = p.nsamp_dev ? *p.nsamp_dev : p.nsamp;
@@ -169,9 +179,11 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc(FieldParams p, con
         for (int i = 0; i < kStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
         mbar_init(a_ready, kWorkers);
         mbar_init(mma_done, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(st_full + i, kWorkers); mbar_init(st_free + i, 1); }
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(tmem_ptr, kTmemCols);
+    const bool spill = BWD && p.wg_scratch != nullptr;   // activations / gradients go to the wgrad scratch
     for (int i = threadIdx.x; i < 4 * 128 + 4; i += kThreads) {
         float v;
         if (i < 128) v = p.dec.b1[i];
@@ -202,7 +214,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc(FieldParams p, con
                     }
                     __syncwarp();
                     src += bytes;
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    if (++stage == NS) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -241,10 +253,34 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc(FieldParams p, con
                         if (c == nchunks - 1) mma_commit(mma_done);
                     }
                     __syncwarp();
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    if (++stage == NS) { stage = 0; phase ^= 1; }
                 }
                 if (lane == 0) TC_TRACE(tile_i, l, 2);          // all MMAs of the layer issued + committed
             }
+        }
+    } else if (warp == 10) {
+        // ===================== scratch store warp: staged layer (shared memory) -> wgrad scratch by bulk TMA =====================
+        if (spill) {
+            const int g0s[8] = {gH1, gH2, gT, gHC, gG4, gG3, gG2, gG1};   // order in which the workers produce the layers
+            uint32_t sc = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i, ++sc) {
+                    const int b = sc & 1;
+                    mbar_wait(st_full + b, (sc >> 1) & 1);
+                    if (elect_one()) {
+                        const unsigned char *src = smem + SM::oStaging + b * kStagingBytes;
+                        for (int q4 = 0; q4 < 4; ++q4)
+                            bulk_s2g(p.wg_scratch + ((size_t)tile * 4 + q4) * kSliceBytes + (size_t)g0s[i] * 512, src + q4 * 16384, 16384u);
+                        bulk_commit();
+                        bulk_wait_read0();                    // the staging buffer may be rewritten
+                        mbar_arrive(st_free + b);
+                    }
+                    __syncwarp();
+                }
+            }
+            if (elect_one()) bulk_wait_all0();
+            __syncwarp();
         }
     } else {
         // ===================== workers: two threads per sample row (64 accumulator columns each) =====================
@@ -257,6 +293,21 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc(FieldParams p, con
         uint32_t done_uses = 0;
         uint32_t nomask[2] = {0u, 0u};
         int tile_i = 0, lcount = -1;                  // trace bookkeeping (warp 2 lane 0 stamps)
+        uint32_t sc = 0;                              // staged layers so far (two staging buffers alternate)
+        // staging: this thread's 16-byte column of the current buffer ([slice q][group][lane][16 B]); waits until the
+        // bulk store that last read the buffer is done
+        auto stage_begin = [&]() -> unsigned char * {
+            if (!spill) return nullptr;
+            const int b = sc & 1;
+            if (sc >= 2) mbar_wait(st_free + b, ((sc >> 1) - 1) & 1);
+            return smem + SM::oStaging + b * kStagingBytes + q * 16384 + lane * 16;
+        };
+        auto stage_end = [&]() {
+            if (!spill) return;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic smem writes -> bulk-copy engine
+            mbar_arrive(st_full + (sc & 1));
+            ++sc;
+        };
         auto layer_done = [&]() {
             mbar_wait(mma_done, done_uses & 1);
             ++done_uses;
@@ -272,8 +323,8 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc(FieldParams p, con
         };
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_i, lcount = -1) {
             const int s = tile * 128 + m;
-            unsigned char *scr = nullptr;   // this thread's 16-byte column in the tile's wgrad scratch
-            if (BWD && p.wg_scratch) scr = p.wg_scratch + ((size_t)tile * 4 + q) * kSliceBytes + (size_t)lane * 16;
+            unsigned char *scr = nullptr;   // this thread's 16-byte column in the tile's wgrad scratch (small groups go direct)
+            if (spill) scr = p.wg_scratch + ((size_t)tile * 4 + q) * kSliceBytes + (size_t)lane * 16;
             int vox = -1, ray = -1;
             float z = 0.0f, px = 0.f, py = 0.f, pz = 0.f;
             if (threadIdx.x == 64) TC_TRACE(tile_i, 0, 6);            // gather starts
@@ -329,13 +380,16 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc(FieldParams p, con
             uint32_t m1[2], m2[2], mc[2];
             // ---- forward ----
             layer_done();
-            epilogue64<0>(trow, col0, sBias, m1, scr ? scr + (size_t)gH1 * 512 : nullptr);           // h1
+            epilogue64<0>(trow, col0, sBias, m1, stage_begin());                                     // h1
+            stage_end();
             a_is_ready();
             layer_done();
-            epilogue64<0>(trow, col0, sBias + 128, m2, scr ? scr + (size_t)gH2 * 512 : nullptr);     // h2
+            epilogue64<0>(trow, col0, sBias + 128, m2, stage_begin());                               // h2
+            stage_end();
             a_is_ready();
             layer_done();
-            epilogue64<1>(trow, col0, sBias + 256, nomask, scr ? scr + (size_t)gT * 512 : nullptr);  // t (no activation)
+            epilogue64<1>(trow, col0, sBias + 256, nomask, stage_begin());                           // t (no activation)
+            stage_end();
             float sdf = 0.0f;
             if (lead) {
                 uint32_t v[16];
@@ -345,7 +399,8 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc(FieldParams p, con
             }
             a_is_ready();
             layer_done();
-            epilogue64<0>(trow, col0, sBias + 384, mc, scr ? scr + (size_t)gHC * 512 : nullptr);     // hc
+            epilogue64<0>(trow, col0, sBias + 384, mc, stage_begin());                               // hc
+            stage_end();
             a_is_ready();
             layer_done();
             float r = 0.f, g = 0.f, b = 0.f;
@@ -382,10 +437,12 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc(FieldParams p, con
             }
             a_is_ready();
             layer_done();
-            epilogue64<2>(trow, col0, nullptr, mc, scr ? scr + (size_t)gG4 * 512 : nullptr);         // g_hc
+            epilogue64<2>(trow, col0, nullptr, mc, stage_begin());                                   // g_hc
+            stage_end();
             a_is_ready();
             layer_done();
-            epilogue64<3>(trow, col0, nullptr, nomask, scr ? scr + (size_t)gG3 * 512 : nullptr);     // g_t
+            epilogue64<3>(trow, col0, nullptr, nomask, stage_begin());                               // g_t
+            stage_end();
             float gf[16];
 #pragma unroll
             for (int e = 0; e < 16; ++e) gf[e] = 0.0f;
@@ -401,10 +458,12 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc(FieldParams p, con
             }
             a_is_ready();
             layer_done();
-            epilogue64<2>(trow, col0, nullptr, m2, scr ? scr + (size_t)gG2 * 512 : nullptr);         // g_h2
+            epilogue64<2>(trow, col0, nullptr, m2, stage_begin());                                   // g_h2
+            stage_end();
             a_is_ready();
             layer_done();
-            epilogue64<2>(trow, col0, nullptr, m1, scr ? scr + (size_t)gG1 * 512 : nullptr);         // g_h1
+            epilogue64<2>(trow, col0, nullptr, m1, stage_begin());                                   // g_h1
+            stage_end();
             a_is_ready();
             layer_done();
             if (!lead) continue;
@@ -520,7 +579,7 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, ui
 //   MMA issuer     : 12 MMAs per step (4 k-steps x 3xTF32), commit frees the operand buffer
 #define WG_TRACE(g, slot)                                                                           \
     do {                                                                                            \
-        if (g_tc_trace && blockIdx.x == 0 && (g) < 40) g_tc_trace[(g) * 8 + (slot)] = clock64();     \
+        if (g_tc_trace && blockIdx.x == 0 && (g) < 40) g_tc_trace[320 + (g) * 8 + (slot)] = clock64();     \
     } while (0)
 
 __global__ void __launch_bounds__(wg::kThreads, 1) k_wgrad_tc(FieldParams p)
@@ -835,13 +894,13 @@ static int launch_tc(const FieldParams &fp, int max_samples, cudaStream_t st)
 {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_field_tc<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(k_field_tc<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Smem<BWD>::bytes);
         if (e != cudaSuccess) { set_error("field_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         configured = true;
     }
     const int tiles = ceil_div(max_samples, 128);
     const int grid = tiles < num_sms() ? (tiles > 0 ? tiles : 1) : num_sms();
-    k_field_tc<BWD><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(fp, fp.ws_tc);
+    k_field_tc<BWD><<<grid, tc::kThreads, tc::Smem<BWD>::bytes, st>>>(fp, fp.ws_tc);
     PSLAM_CHECK_LAUNCH(BWD ? "field_tc_backward" : "field_tc_forward");
     return 0;
 }

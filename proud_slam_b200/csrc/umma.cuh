@@ -58,6 +58,15 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32
                  : "memory");
 }
 
+// 1-D bulk copy shared -> global (bulk async-group completion)
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // sources may be reused
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }         // writes are complete
+
 // ---- tensor memory ------------------------------------------------------------------------
 // whole-warp calls
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols)

@@ -11,7 +11,7 @@ feat = torch.randn(n, 16, device=dev) * 0.05
 ws = torch.empty(int(lib.pslam_decoder_ws_count(128)), device=dev)
 out = torch.zeros(n, 4, device=dev)
 ds = _decoder_struct(dec)
-buf = torch.zeros(4 * 10 * 8, dtype=torch.int64, device=dev)
+buf = torch.zeros(640, dtype=torch.int64, device=dev)
 for rep in range(2):
     lib.pslam_decoder_fwd(n, C.byref(ds), _lib.ptr(feat), _lib.ptr(ws), _lib.ptr(out), _lib.stream_ptr(dev))
 torch.cuda.synchronize()
@@ -19,7 +19,7 @@ lib.pslam_debug_tc_trace(_lib.ptr(buf))
 lib.pslam_decoder_fwd(n, C.byref(ds), _lib.ptr(feat), _lib.ptr(ws), _lib.ptr(out), _lib.stream_ptr(dev))
 torch.cuda.synchronize()
 lib.pslam_debug_tc_trace(None)
-t = buf.cpu().view(4, 10, 8)
+t = buf.cpu()[:320].view(4, 10, 8)
 t0 = int(t[0, 0, 6])
 names = ["mma_wait_A", "mma_A_seen", "mma_committed", "wrk_D_seen", "-", "wrk_A_produced", "gather_start"]
 for tile in range(3):

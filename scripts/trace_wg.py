@@ -11,11 +11,11 @@ feat = torch.randn(n, 16, device=dev) * 0.05; g_out = torch.randn(n, 4, device=d
 ws = torch.empty(int(lib.pslam_decoder_ws_count(128)), device=dev); g_feat = torch.zeros(n, 16, device=dev)
 ds = _decoder_struct(dec); gd = [torch.zeros_like(p) for p in dec]; gs = _decoder_struct(gd, DecoderGradT)
 wws = torch.empty(int(lib.pslam_wgrad_ws_bytes(n)), dtype=torch.uint8, device=dev)
-buf = torch.zeros(4 * 10 * 8, dtype=torch.int64, device=dev)
+buf = torch.zeros(640, dtype=torch.int64, device=dev)
 run = lambda: lib.pslam_decoder_bwd(n, C.byref(ds), _lib.ptr(feat), _lib.ptr(ws), _lib.ptr(g_out), _lib.ptr(g_feat), C.byref(gs), _lib.ptr(wws), wws.numel(), _lib.stream_ptr(dev))
 run(); run(); torch.cuda.synchronize()
 lib.pslam_debug_tc_trace(_lib.ptr(buf)); run(); torch.cuda.synchronize(); lib.pslam_debug_tc_trace(None)
-t = buf.cpu().view(40, 8)
+t = buf.cpu()[320:].view(40, 8)
 # k_field_tc<1> wrote into the same buffer first (tile/layer stamps), then k_wgrad_tc overwrote g<40 slots 0..5
 t0 = int(t[12, 0])
 for g in range(12, 30):

@@ -1,0 +1,87 @@
+"""Multi-rank step on the device.  With one GPU the ranks are emulated as two pipelines whose raw loss
+rows are exchanged by hand (no kernels wait on each other); the closed loss and the summed gradients
+must equal ONE padded batch evaluated by the oracle on the GPU's own per-sample outputs."""
+import pytest
+import torch
+
+from oracle import render_oracle as ro
+from tests import util
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def test_two_shards_close_to_one_padded_batch(device):
+    from proud_slam_b200 import parallel, scene as sc
+    from proud_slam_b200.pipeline import RenderPipeline
+    s, ms = util.build_scene("replica_small")
+    dec = util.test_decoder(seed=1)
+    rays_o, rays_d, rgb, depth = sc.sample_batch(s, [0, 1], 300, seed=5)
+    batch = [rays_o[0], rays_d[0], rgb[0], depth[0]]
+    batch = [t[:599] for t in batch]                    # uneven shards: 300 + 299
+    msd = {k: v.detach().to(device) for k, v in ms.items()}
+    decd = [p.detach().to(device) for p in dec]
+    cw = (util.CRIT["rgb_weight"], util.CRIT["depth_weight"], util.CRIT["fs_weight"], util.CRIT["sdf_weight"])
+    fg = parallel.FlatGrads(msd["voxel_vertex_emb"], decd)     # both "ranks" accumulate into it = the all-reduce
+    pipes, outs, shards = [], [], []
+    rows = torch.zeros(2, 16, dtype=torch.float64, device=device)
+    for r in range(2):
+        sh = parallel.shard_rays(batch, r, 2)
+        shards.append(sh)
+        inv = util.device_rcp(sh[1], device)
+        out = ro.render_rays(sh[0][None], sh[1][None], ms, dec, 0.1 * s.voxel_size, s.voxel_size, 0.1, 10, 10.0,
+                             generator=torch.Generator().manual_seed(100 + r), inv_dir=inv)
+        outs.append(out)
+        noise = out["_dbg"]["noise"]
+        pipe = RenderPipeline(sh[0].shape[0], device, samples_per_ray=96)
+        pipe.bind(sh[0].to(device), sh[1].to(device), msd, decd, voxel_size=s.voxel_size, step_size=0.1 * s.voxel_size,
+                  truncation=0.1, max_distance=10.0, target_rgb=sh[2].to(device), target_depth=sh[3].to(device),
+                  noise=noise.reshape(-1, noise.shape[-1]).to(device).contiguous(), weights=cw, g_emb=fg.g_emb, g_dec=fg.g_dec,
+                  grad_rays=True, defer_loss=True)
+        pipe.sample()
+        pipe.forward()
+        rows[r].copy_(pipe.loss_raw)
+        pipes.append(pipe)
+    for pipe in pipes:
+        pipe.finalize_loss(rows)
+        pipe.backward()
+    torch.cuda.synchronize()
+    assert pipes[0].losses() == pipes[1].losses()            # every rank closes the loss identically
+    # one padded batch, oracle compositing on the GPU's own per-sample outputs (decision-proof, see test_gpu_pipeline)
+    sdf_ps, rgb_ps, ress = [], [], []
+    for pipe, out in zip(pipes, outs):
+        P = pipe.counts()["n_samples"]
+        so = pipe.samp_out[:P].cpu()
+        sdf_p, rgb_p = so[:, 3].clone().requires_grad_(True), so[:, :3].clone().requires_grad_(True)
+        smask, z = out["_dbg"]["sample_mask"], out["z_vals"]
+        sdf = torch.ones_like(z).masked_scatter(smask, sdf_p)
+        colour = z.new_zeros(*z.shape, 3).masked_scatter(smask.unsqueeze(-1).expand(*z.shape, 3), rgb_p)
+        w, _ = ro.sdf2weights(sdf, z, smask.to(z.dtype), 0.1)
+        ress.append({"weights": w, "color": torch.sum(w[..., None] * colour, -2), "depth": torch.sum(w * z, -1), "z_vals": z,
+                     "sdf": sdf, "ray_mask": out["ray_mask"]})
+        sdf_ps.append(sdf_p)
+        rgb_ps.append(rgb_p)
+    big = util.concat_outputs(ress)
+    kw = {k: util.CRIT[k] for k in ("rgb_weight", "depth_weight", "sdf_weight", "fs_weight", "truncation", "max_depth")}
+    loss, parts = ro.criterion(big, (batch[2][None], batch[3][None]), **kw)
+    loss.backward()
+    l = pipes[0].losses()
+    assert abs(l["loss"] - float(loss)) <= TOL * abs(float(loss))
+    for k in ("color_loss", "depth_loss", "fs_loss", "sdf_loss"):
+        assert abs(l[k] - float(parts[k])) <= TOL * max(abs(float(parts[k])), 1e-12), k
+    for pipe, sdf_p, rgb_p in zip(pipes, sdf_ps, rgb_ps):
+        P = pipe.counts()["n_samples"]
+        g = pipe.samp_gout[:P].cpu()
+        assert rel_err(g[:, 3], sdf_p.grad) < TOL and rel_err(g[:, :3], rgb_p.grad) < TOL
+    # summed parameter gradients = oracle field backward fed with each shard's upstream gradient
+    tot = None
+    for pipe, out, sh in zip(pipes, outs, shards):
+        P = pipe.counts()["n_samples"]
+        g = pipe.samp_gout[:P].cpu()
+        rgb_o, sdf_o = util.oracle_field(out, sh[0][None], sh[1][None], ms, dec, s.voxel_size)
+        grads = torch.autograd.grad((rgb_o * g[:, :3]).sum() + (sdf_o * g[:, 3]).sum(), [ms["voxel_vertex_emb"]] + list(dec))
+        tot = grads if tot is None else [a + b for a, b in zip(tot, grads)]
+    assert rel_err(fg.g_emb, tot[0]) < TOL
+    for i in range(10):
+        assert rel_err(fg.g_dec[i], tot[1 + i]) < TOL, f"decoder grad {i}"
