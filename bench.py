@@ -253,12 +253,14 @@ def run_gpu(args):
     if rank == 0:
         pipe.args.flags = pipe.args.flags & ~_lib.F_DEFER_LOSS
         stage_ms = []
-        for stage_id in range(6):
+        for stage_id in range(8):
             reps = []
             for it in range(max(3, min(args.steps, 10))):
                 flat.zero_()
-                for k in range(stage_id):        # bring the pipeline to this stage
+                for k in range(min(stage_id, 5)):        # bring the pipeline to this stage
                     pipe.stage(k)
+                if stage_id == 7:
+                    pipe.stage(6)                        # the wgrad kernel consumes what the dgrad kernel spilled
                 flush.zero_()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
@@ -267,7 +269,8 @@ def run_gpu(args):
                 torch.cuda.synchronize()
                 reps.append(a.elapsed_time(b))
             stage_ms.append(sum(reps[1:]) / max(len(reps) - 1, 1))
-        prof = dict(zip(["intersect", "sample", "field_fwd", "composite_fwd", "composite_bwd", "field_bwd"], stage_ms))
+        prof = dict(zip(["intersect", "sample", "field_fwd", "composite_fwd", "composite_bwd", "field_bwd", "field_bwd_dgrad_kernel",
+                         "field_bwd_wgrad_kernel"], stage_ms))
 
     if world > 1:
         t = torch.tensor([ms_step, ms_e2e], device=device, dtype=torch.float64)
@@ -282,8 +285,10 @@ def run_gpu(args):
     if rank == 0:
         peaks = measured_peaks()
         P = counts["n_samples"]
-        flops_bwd = 4.0 * macs_per_sample(WIDTH) * P              # dgrad + wgrad; recompute not counted
-        t_k = prof["field_bwd"] * 1e-3
+        # dominant kernel: k_field_tc<bwd> (forward recompute + dgrad chain + trilinear backward + scratch spill);
+        # algorithmic FLOPs = the dgrad GEMMs once (2 MACs P), neither the recompute nor the x3 of the TF32 split
+        flops_bwd = 2.0 * macs_per_sample(WIDTH) * P
+        t_k = prof["field_bwd_dgrad_kernel"] * 1e-3
         achieved = flops_bwd / t_k / 1e12
         value = world * R / (ms_step * 1e-3)
         line = {
@@ -298,12 +303,13 @@ def run_gpu(args):
                        "loss": loss_val},
             "e2e": {"value": world * R / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(sum(t.numel() * 4 for t in host)), "d2h_bytes_per_step": 64},
-            "gpu_launches": args.steps * 15,
+            "gpu_launches": args.steps * 19,
             "clocks": clocks,
-            "roofline": {"kernel": "k_field<128,bwd> (decoder dgrad+wgrad, fused trilinear backward)", "bound": "tensor",
+            "roofline": {"kernel": "k_field_tc<bwd> (tcgen05 3xTF32: decoder recompute + dgrad, fused trilinear backward, wgrad spill)", "bound": "tensor",
                          "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
-                         "traffic": None, "peak_source": peaks["source"] + ", bf16 burst; kernel math is fp32 SIMT in this round",
-                         "algorithmic_flops_per_launch": flops_bwd, "kernel_ms": prof["field_bwd"]},
+                         "traffic": None, "peak_source": peaks["source"] + ", dense bf16 burst (the kernel issues kind::tf32 MMAs, x3 for the fp32-equivalent "
+                                                        "split and x2 for the recompute: 6 hardware TF32 FLOPs per algorithmic FLOP)",
+                         "algorithmic_flops_per_launch": flops_bwd, "kernel_ms": prof["field_bwd_dgrad_kernel"]},
             "stage_ms": prof,
         }
         line["cpu_baseline"] = cpu_baseline(s, ms_cpu)

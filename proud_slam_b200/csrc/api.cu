@@ -49,6 +49,7 @@ static int check_render(const pslam_render_t *p)
     PSLAM_CHECK_ARG(p->R > 0 && p->N > 0 && p->E > 0 && p->n_max > 0 && p->sample_cap > 0, PSLAM_E_ARG,
                     "sizes must be positive (R=%d N=%d E=%d n_max=%d sample_cap=%d)", p->R, p->N, p->E, p->n_max, p->sample_cap);
     PSLAM_CHECK_ARG(p->R <= (1 << 26), PSLAM_E_RANGE, "R=%d too large", p->R);
+    PSLAM_CHECK_ARG(p->N <= (1 << 26), PSLAM_E_RANGE, "N=%d octree rows exceed the traversal's 26-bit row ids", p->N);
     PSLAM_CHECK_ARG(p->voxel_size > 0.0f && p->step_size > 0.0f && p->truncation > 0.0f, PSLAM_E_ARG, "voxel_size, step_size and truncation must be > 0");
     PSLAM_CHECK_ARG(p->rays_o && p->rays_d && p->centres && p->structure && p->vertex_idx && p->emb, PSLAM_E_ARG, "null input pointer");
     PSLAM_CHECK_ARG(p->hit_idx && p->hit_min && p->hit_max && p->hit_count && p->hit_ray && p->ray_rank && p->samp_off && p->samp_vox &&
@@ -114,7 +115,7 @@ extern "C" int pslam_device_info(int *out3)
 
 extern "C" int64_t pslam_render_scratch_i_count(int R)
 {
-    return 2 * ((int64_t)ceil_div(R, 128) + 8) + 8 * (int64_t)ceil_div(R, 8) + 64;
+    return ((int64_t)ceil_div(R, 64) + 8) + ((int64_t)ceil_div(R, 128) + 8) + 8 * (int64_t)ceil_div(R, 8) + 64;
 }
 extern "C" int64_t pslam_render_scratch_f_count(int R) { return 8 * (int64_t)ceil_div(R, 8) + 64; }
 
@@ -177,7 +178,8 @@ extern "C" int pslam_render_offsetof_loss(void) { return (int)offsetof(pslam_ren
 
 /* Profiling hook: launches ONE stage of the step so that a benchmark can bracket a single kernel
  * with events.  0 intersect(+compaction) 1 sampling 2 field fwd 3 composite fwd(+loss) 4 composite bwd
- * 5 field bwd.  The preceding stages must have run on the same argument block. */
+ * 5 field bwd (6 / 7: only its dgrad / wgrad kernel in the tcgen05 build).  The preceding stages must have run
+ * on the same argument block. */
 extern "C" int pslam_render_stage(const pslam_render_t *p, int stage, pslam_stream_t stream)
 {
     if (int rc = check_render(p)) return rc;
@@ -193,6 +195,8 @@ extern "C" int pslam_render_stage(const pslam_render_t *p, int stage, pslam_stre
         case 3: if (int rc = check_render_field(p, false)) return rc; return launch_composite_forward(p, st);
         case 4: if (int rc = check_render_field(p, true)) return rc; return launch_composite_backward(p, st);
         case 5: if (int rc = check_render_field(p, true)) return rc; return launch_field_backward(p, st);
+        case 6: if (int rc = check_render_field(p, true)) return rc; return launch_field_backward(p, st, 1);
+        case 7: if (int rc = check_render_field(p, true)) return rc; return launch_field_backward(p, st, 2);
     }
     set_error("unknown stage %d", stage);
     return PSLAM_E_ARG;

@@ -724,13 +724,13 @@ static int pack_decoder(const pslam_decoder_t &d, float *ws, cudaStream_t st)
 }
 static const float *tc_region(const pslam_decoder_t &d, const float *ws) { return d.width == 128 ? ws + FieldCfg<128>::WS : nullptr; }
 
-static int launch_field(const FieldParams &fp, bool bwd, int max_samples, cudaStream_t st)
+static int launch_field(const FieldParams &fp, bool bwd, int max_samples, cudaStream_t st, int part = 0)
 {
     if (fp.dec.width == 128 && decoder_mode() == 0) {
         if (!bwd) return tc_launch_field_forward(fp, max_samples, st);
         // tensor-core backward needs the wgrad scratch when decoder gradients are wanted
         if (!fp.grad_dec || (fp.wg_scratch && fp.wg_scratch_bytes >= tc_wgrad_scratch_bytes(max_samples)))
-            return tc_launch_field_backward(fp, max_samples, st);
+            return tc_launch_field_backward(fp, max_samples, st, part);
     }
     if (fp.dec.width == 128) return bwd ? launch_field_t<128, true>(fp, max_samples, st) : launch_field_t<128, false>(fp, max_samples, st);
     return bwd ? launch_field_t<256, true>(fp, max_samples, st) : launch_field_t<256, false>(fp, max_samples, st);
@@ -759,10 +759,10 @@ int launch_field_forward(const pslam_render_t *p, cudaStream_t st)
     return launch_field(params_from_render(p), false, p->sample_cap, st);
 }
 
-int launch_field_backward(const pslam_render_t *p, cudaStream_t st)
+int launch_field_backward(const pslam_render_t *p, cudaStream_t st, int part)
 {
     // dec_ws was packed by the forward of the same step
-    return launch_field(params_from_render(p), true, p->sample_cap, st);
+    return launch_field(params_from_render(p), true, p->sample_cap, st, part);
 }
 
 }  // namespace pslam

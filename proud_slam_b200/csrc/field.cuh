@@ -42,7 +42,8 @@ constexpr int kTcPackFloats = 229376;   // forward + dgrad weight streams in UMM
 int decoder_mode();
 int tc_pack_decoder(const pslam_decoder_t &d, float *ws_tc, cudaStream_t st);
 int tc_launch_field_forward(const FieldParams &fp, int max_samples, cudaStream_t st);
-int tc_launch_field_backward(const FieldParams &fp, int max_samples, cudaStream_t st);
+// part: 0 = dgrad kernel + wgrad kernel, 1 = dgrad kernel only, 2 = wgrad kernel only (profiling)
+int tc_launch_field_backward(const FieldParams &fp, int max_samples, cudaStream_t st, int part = 0);
 size_t tc_wgrad_scratch_bytes(int max_samples);
 
 }  // namespace pslam

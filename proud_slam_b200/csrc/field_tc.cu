@@ -909,12 +909,13 @@ int tc_launch_field_forward(const FieldParams &fp, int max_samples, cudaStream_t
 
 // backward: dgrad chain (+ trilinear backward); when decoder gradients are wanted the scratch must be
 // provided and the wgrad kernel follows on the same stream
-int tc_launch_field_backward(const FieldParams &fp_in, int max_samples, cudaStream_t st)
+int tc_launch_field_backward(const FieldParams &fp_in, int max_samples, cudaStream_t st, int part)
 {
     FieldParams fp = fp_in;
     if (!fp.grad_dec) fp.wg_scratch = nullptr;
-    if (int rc = launch_tc<true>(fp, max_samples, st)) return rc;
-    if (!fp.grad_dec) return 0;
+    if (part != 2)
+        if (int rc = launch_tc<true>(fp, max_samples, st)) return rc;
+    if (!fp.grad_dec || part == 1) return 0;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::kSmemBytes);

@@ -166,6 +166,127 @@ k_intersect_fused(int R, float half_voxel, int n_max, float max_distance, const 
     if (threadIdx.x == 0) block_hits[blockIdx.x] = nhit;
 }
 
+// ---- fused layout, 8 lanes per ray -----------------------------------------------------------
+// The per-thread DFS above is a chain of ~70-200 dependent loads per ray (and a warp waits for its
+// slowest ray).  Here a ray owns 8 lanes: when an internal node is expanded, lane c loads child c, its
+// centre, and runs the slab test, so the dependent chain is one step per HIT INTERNAL node instead of
+// one per tested node, and leaves cost no extra round trip (their interval is computed when the
+// parent is expanded and waits on the stack).  Hit children are pushed in ascending child order, so
+// the pop order -- and with it the emission order and the n_max cut -- is the reference's
+// (children 0..7 pushed, 7 popped first, intersect_gpu.cu:259-265; misses contribute nothing there
+// either).  The child's box half-size is half_voxel * side with side = parent side / 2, the same
+// integer the reference reads from children[c*9+8].  Hits are collected and sorted in shared memory.
+constexpr int kWideRays = 64;                    // rays per block
+constexpr int kWideThreads = kWideRays * 8;
+constexpr int kWideStack = 64;                   // 7 pending siblings per level + 8: enough for 9 levels (grid 512)
+constexpr int kWideHits = 50;                    // == n_max of the reference (voxel_helpers.py:561)
+constexpr size_t kWideSmem = sizeof(int) * 3 * (kWideStack + kWideHits) * kWideRays;
+
+__global__ void __launch_bounds__(kWideThreads)
+k_intersect_wide(int R, float half_voxel, int n_max, float max_distance, const float *__restrict__ ray_start,
+                 const float *__restrict__ ray_dir, const float *__restrict__ points, const int *__restrict__ children,
+                 int *__restrict__ hit_idx, float *__restrict__ hit_min, float *__restrict__ hit_max, int *__restrict__ hit_count,
+                 int *__restrict__ block_hits, int *__restrict__ counters)
+{
+    extern __shared__ int s_wide[];
+    int *s_id = s_wide;                                                    // [kWideStack][kWideRays]: id | log2(side) << 26
+    float *s_lo = reinterpret_cast<float *>(s_wide + kWideStack * kWideRays);
+    float *s_hi = s_lo + kWideStack * kWideRays;
+    int *h_id = s_wide + 3 * kWideStack * kWideRays;                       // [kWideHits][kWideRays]
+    float *h_lo = reinterpret_cast<float *>(h_id + kWideHits * kWideRays);
+    float *h_hi = h_lo + kWideHits * kWideRays;
+
+    const int lane = threadIdx.x & 31, sub = threadIdx.x & 7, rl = threadIdx.x >> 3;
+    const int r = blockIdx.x * kWideRays + rl;
+    const bool valid = r < R;
+    Ray ray{};
+    if (valid) ray = load_ray(ray_start, ray_dir, r);
+    if (n_max > kWideHits) n_max = kWideHits;
+    int top = -1, cnt = 0, cur = -1, cur_side = 0;
+    bool overflow = false;
+    if (valid) {   // the root (row 0, intersect_gpu.cu:232)
+        const int side = __ldg(children + 8);
+        float lo, hi;
+        if (slab(ray, __ldg(points), __ldg(points + 1), __ldg(points + 2), __fmul_rn(half_voxel, (float)side), lo, hi)) {
+            if (side == 1) { h_id[rl] = 0; h_lo[rl] = lo; h_hi[rl] = hi; cnt = 1; }
+            else { cur = 0; cur_side = side; }
+        }
+    }
+    while (__any_sync(0xffffffffu, cur >= 0)) {
+        bool hit = false;
+        int cid = -1;
+        float lo = 0.f, hi = 0.f;
+        const int cside = cur_side >> 1;
+        if (cur >= 0) {
+            cid = __ldg(children + (int64_t)cur * 9 + sub);
+            if (cid > -1)
+                hit = slab(ray, __ldg(points + (int64_t)cid * 3), __ldg(points + (int64_t)cid * 3 + 1), __ldg(points + (int64_t)cid * 3 + 2),
+                           __fmul_rn(half_voxel, (float)cside), lo, hi);
+        }
+        const unsigned mine = (__ballot_sync(0xffffffffu, hit) >> (lane & ~7)) & 0xFFu;
+        if (hit) {
+            const int pos = top + 1 + __popc(mine & ((1u << sub) - 1u));
+            if (pos < kWideStack) {
+                s_id[pos * kWideRays + rl] = cid | ((31 - __clz(cside)) << 26);
+                s_lo[pos * kWideRays + rl] = lo; s_hi[pos * kWideRays + rl] = hi;
+            } else overflow = true;
+        }
+        top = min(top + __popc(mine), kWideStack - 1);
+        __syncwarp();
+        // pop: leaves are emitted straight away, the first internal node becomes the next expansion
+        cur = -1;
+        while (top >= 0 && cnt < n_max) {
+            const int e = s_id[top * kWideRays + rl];
+            const int side = 1 << (e >> 26), id = e & 0x3FFFFFF;
+            if (side == 1) {
+                if (sub == 0) { h_id[cnt * kWideRays + rl] = id; h_lo[cnt * kWideRays + rl] = s_lo[top * kWideRays + rl]; h_hi[cnt * kWideRays + rl] = s_hi[top * kWideRays + rl]; }
+                ++cnt; --top;
+            } else { cur = id; cur_side = side; --top; break; }
+        }
+        if (cnt >= n_max) { cur = -1; top = -1; }   // intersect_gpu.cu:233: the walk stops at n_max hits
+        __syncwarp();
+    }
+    int count = 0;
+    if (valid && sub == 0) {
+        // stable insertion sort by entry depth: ties keep DFS order (SURVEY A-Q3)
+        for (int i = 1; i < cnt; ++i) {
+            const float kmin = h_lo[i * kWideRays + rl], kmax = h_hi[i * kWideRays + rl];
+            const int kidx = h_id[i * kWideRays + rl];
+            int j = i - 1;
+            while (j >= 0 && h_lo[j * kWideRays + rl] > kmin) {
+                h_lo[(j + 1) * kWideRays + rl] = h_lo[j * kWideRays + rl]; h_hi[(j + 1) * kWideRays + rl] = h_hi[j * kWideRays + rl];
+                h_id[(j + 1) * kWideRays + rl] = h_id[j * kWideRays + rl];
+                --j;
+            }
+            h_lo[(j + 1) * kWideRays + rl] = kmin; h_hi[(j + 1) * kWideRays + rl] = kmax; h_id[(j + 1) * kWideRays + rl] = kidx;
+        }
+    }
+    __syncwarp();   // outside any divergent region: a warp may hold valid and out-of-range rays
+    if (valid) {
+        // drop hits that start beyond max_distance (voxel_helpers.py:578)
+        while (count < cnt && !(h_lo[count * kWideRays + rl] > max_distance)) ++count;
+        for (int i = sub; i < count; i += 8) {
+            const int64_t at = (int64_t)i * R + r;
+            hit_idx[at] = h_id[i * kWideRays + rl]; hit_min[at] = h_lo[i * kWideRays + rl]; hit_max[at] = h_hi[i * kWideRays + rl];
+        }
+        if (sub == 0) hit_count[r] = count;
+    }
+    const int nhit = __syncthreads_count(sub == 0 && count > 0);
+    const int wmax = warp_max_i(count);
+    if (lane == 0 && wmax > 0) atomicMax(counters + PSLAM_C_P, wmax);
+    if (overflow) atomicOr(counters + PSLAM_C_OVERFLOW, 2);
+    if (threadIdx.x == 0) block_hits[blockIdx.x] = nhit;
+}
+
+// Pulls the flattened octree into L2 before the latency-bound traversal: the DFS is a chain of ~70
+// dependent loads per ray, so every miss to HBM is paid in full.  One 128-byte line per thread.
+__global__ void k_prefetch_l2(const char *__restrict__ a, size_t na, const char *__restrict__ b, size_t nb)
+{
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 128;
+    if (i < na) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + i));
+    if (i < nb) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + i));
+}
+
 // Exclusive scan of `nb` block partials by one block; total -> *total_out.
 __global__ void __launch_bounds__(1024) k_scan_partials(int *__restrict__ partials, int nb, int *__restrict__ total_out)
 {
@@ -209,7 +330,7 @@ __global__ void __launch_bounds__(kIntersectThreads)
 k_compact_rays(int R, const int *__restrict__ hit_count, const int *__restrict__ block_base, int *__restrict__ hit_ray,
                int *__restrict__ ray_rank)
 {
-    __shared__ int s_warp[kIntersectThreads / 32];
+    __shared__ int s_warp[kIntersectThreads / 32];   // launched with kWideRays threads per block (<= kIntersectThreads)
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     const bool hit = (r < R) && hit_count[r] > 0;
     const unsigned ballot = __ballot_sync(0xffffffffu, hit);
@@ -415,15 +536,26 @@ int scan_partials(int *partials, int nb, int *total_out, cudaStream_t st)
 
 int launch_intersect_fused(const pslam_render_t *p, cudaStream_t st)
 {
-    const int nb = ceil_div(p->R, kIntersectThreads);
+    const int nb = ceil_div(p->R, kWideRays);
     int *block_hits = p->scratch_i;  // [nb]
-    const size_t smem = sizeof(int) * kSmemStack * kIntersectThreads;
-    k_intersect_fused<<<nb, kIntersectThreads, smem, st>>>(p->R, (float)(p->voxel_size * 0.5), p->n_max, p->max_distance,
-                                                          p->rays_o, p->rays_d, p->centres, p->structure, p->hit_idx,
-                                                          p->hit_min, p->hit_max, p->hit_count, block_hits, p->counters);
-    PSLAM_CHECK_LAUNCH("intersect_fused");
+    {
+        const size_t na = (size_t)p->N * 12, nbytes = (size_t)p->N * 36;
+        k_prefetch_l2<<<(int)ceil_div64((int64_t)(nbytes / 128 + 1), 256), 256, 0, st>>>(reinterpret_cast<const char *>(p->centres), na,
+                                                                                  reinterpret_cast<const char *>(p->structure), nbytes);
+        PSLAM_CHECK_LAUNCH("prefetch_l2");
+    }
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_intersect_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWideSmem);
+        if (e != cudaSuccess) { set_error("intersect: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+        configured = true;
+    }
+    k_intersect_wide<<<nb, kWideThreads, kWideSmem, st>>>(p->R, (float)(p->voxel_size * 0.5), p->n_max, p->max_distance, p->rays_o,
+                                                         p->rays_d, p->centres, p->structure, p->hit_idx, p->hit_min, p->hit_max,
+                                                         p->hit_count, block_hits, p->counters);
+    PSLAM_CHECK_LAUNCH("intersect_wide");
     if (int rc = scan_partials(block_hits, nb, p->counters + PSLAM_C_RH, st)) return rc;
-    k_compact_rays<<<nb, kIntersectThreads, 0, st>>>(p->R, p->hit_count, block_hits, p->hit_ray, p->ray_rank);
+    k_compact_rays<<<nb, kWideRays, 0, st>>>(p->R, p->hit_count, block_hits, p->hit_ray, p->ray_rank);
     PSLAM_CHECK_LAUNCH("compact_rays");
     return 0;
 }

@@ -13,7 +13,7 @@ int launch_intersect_fused(const pslam_render_t *p, cudaStream_t st);
 int launch_sample_fused(const pslam_render_t *p, cudaStream_t st);
 // field.cu (trilinear lookup + decoder MLP)
 int launch_field_forward(const pslam_render_t *p, cudaStream_t st);
-int launch_field_backward(const pslam_render_t *p, cudaStream_t st);
+int launch_field_backward(const pslam_render_t *p, cudaStream_t st, int part = 0);  // part 1/2: dgrad / wgrad kernel only (tcgen05 build)
 // composite.cu (SDF->weights compositing + loss)
 int launch_composite_forward(const pslam_render_t *p, cudaStream_t st);
 int launch_composite_backward(const pslam_render_t *p, cudaStream_t st);

@@ -114,6 +114,7 @@ k_inverse_cdf_ref(int b, int num_rays, int P, int max_steps, float fixed_step_si
 struct FusedHits {
     const int *hit_idx; const float *hit_min, *hit_max; const int *hit_count, *hit_ray;
     int R, Rh, P, chunk_base_rank;  // rank of (g, 800c + 0)
+    int own_j, own_r, own_cnt;      // this thread's ray: every (j, bin) access of the sampling loop is to it
     float total;                    // sum of this ray's segment lengths
     float max_distance;             // value the reference reads in padded slots (voxel_helpers.py:579-580)
     __device__ __forceinline__ int ray_of(int j) const
@@ -126,18 +127,16 @@ struct FusedHits {
     {
         return (b < __ldg(hit_count + r)) ? __ldg(hit_idx + (int64_t)b * R + r) : -1;
     }
-    __device__ __forceinline__ int idx(int j, int b) const { return idx_r(ray_of(j), b); }
-    __device__ __forceinline__ int flat_idx(int f) const { return idx_r(ray_of(f / P), f % P); }
-    __device__ __forceinline__ float tmin(int j, int b) const
+    // own ray: one load instead of three dependent ones (rank -> ray -> count -> slot)
+    __device__ __forceinline__ int idx(int, int b) const { return (b < own_cnt) ? __ldg(hit_idx + (int64_t)b * R + own_r) : -1; }
+    // the tail loop's flat index may land on another ray of the chunk (SURVEY A-Q7)
+    __device__ __forceinline__ int flat_idx(int f) const
     {
-        const int r = ray_of(j);
-        return (b < __ldg(hit_count + r)) ? __ldg(hit_min + (int64_t)b * R + r) : max_distance;
+        const int j = f / P;
+        return j == own_j ? idx(j, f % P) : idx_r(ray_of(j), f % P);
     }
-    __device__ __forceinline__ float tmax(int j, int b) const
-    {
-        const int r = ray_of(j);
-        return (b < __ldg(hit_count + r)) ? __ldg(hit_max + (int64_t)b * R + r) : max_distance;
-    }
+    __device__ __forceinline__ float tmin(int, int b) const { return (b < own_cnt) ? __ldg(hit_min + (int64_t)b * R + own_r) : max_distance; }
+    __device__ __forceinline__ float tmax(int, int b) const { return (b < own_cnt) ? __ldg(hit_max + (int64_t)b * R + own_r) : max_distance; }
     __device__ __forceinline__ float prob(int j, int b) const
     {
         return __fdiv_rn(__fsub_rn(tmax(j, b), tmin(j, b)), total);  // voxel_helpers.py:639-643
@@ -201,6 +200,7 @@ k_sample_fused(pslam_render_t p, int *__restrict__ block_counts)
         hv.hit_count = p.hit_count; hv.hit_ray = p.hit_ray;
         hv.R = p.R; hv.Rh = Rh; hv.P = P; hv.chunk_base_rank = g * n + c * kChunkRays;
         hv.total = total; hv.max_distance = p.max_distance;
+        hv.own_j = j; hv.own_r = r; hv.own_cnt = cnt;
         const float prob0 = hv.prob(j, 0);
         int room = 0, off = 0;
         if (WRITE) {
@@ -272,7 +272,7 @@ k_sample_offsets(pslam_render_t p, const int *__restrict__ block_base)
 int launch_sample_fused(const pslam_render_t *p, cudaStream_t st)
 {
     const int nb = ceil_div(p->R, kSampleThreads);
-    int *block_counts = p->scratch_i + ceil_div(p->R, 128) + 8;  // after intersect's block_hits
+    int *block_counts = p->scratch_i + ceil_div(p->R, 64) + 8;   // after intersect's block_hits (64 rays per block)
     k_sample_fused<false><<<nb, kSampleThreads, 0, st>>>(*p, block_counts);
     PSLAM_CHECK_LAUNCH("sample_count");
     if (int rc = scan_partials(block_counts, nb, p->counters + PSLAM_C_TILE2, st)) return rc;
