@@ -312,10 +312,82 @@ def run_gpu(args):
                          "algorithmic_flops_per_launch": flops_bwd, "kernel_ms": prof["field_bwd_dgrad_kernel"]},
             "stage_ms": prof,
         }
+        if world == 1:
+            line["tracking"] = tracking_bench(s, ms, dec, device)
         line["cpu_baseline"] = cpu_baseline(s, ms_cpu)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+class _Frame:
+    """Minimal stand-in for the reference's RGBDFrame (src/frame.py:10-85) with everything on the device."""
+
+    def __init__(self, scene, frame, device, seed=0):
+        self.rays_d = scene.rays_cam.reshape(-1, 3).to(device)
+        self.rgb = frame.rgb.reshape(-1, 3).to(device)
+        self.depth = frame.depth.reshape(-1).to(device)
+        self.gen = torch.Generator(device=device).manual_seed(seed)
+        self.sample_mask = None
+
+    def sample_rays(self, n):
+        self.sample_mask = torch.randint(0, self.rays_d.shape[0], (n,), device=self.rays_d.device, generator=self.gen)
+
+
+def tracking_bench(scene, ms, dec, device, frames=5, iters=30, n_rays=1024):
+    """BASELINE.json configs[2]: SE(3) pose optimisation, 1024 rays x 30 iterations per frame
+    (configs/replica/replica.yaml:25-34) through the drop-in track_frame: per iteration one fused
+    render + median-gated Criterion + backward to the rays, torch autograd into the 6 pose numbers, Adam."""
+    import types
+    from proud_slam_b200.criterion import Criterion
+    from proud_slam_b200.se3pose import OptimizablePose
+    from proud_slam_b200.variations import render_helpers as rh
+    crit = Criterion(types.SimpleNamespace(criteria=dict(rgb_weight=0.5, depth_weight=1.0, sdf_weight=5000.0, fs_weight=10.0,
+                                                          sdf_truncation=0.1), data_specs=dict(max_depth=10.0)))
+    times = []
+    for i in range(frames + 2):
+        f = scene.frames[i % len(scene.frames)]
+        frame = _Frame(scene, f, device, seed=i)
+        pose = f.pose.clone()
+        pose[:3, 3] += torch.tensor([0.02, -0.01, 0.015])
+        init = OptimizablePose.from_matrix(pose)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rh.track_frame(init, frame, ms, dec, None, crit, scene.voxel_size, N_rays=n_rays, step_size=0.1 * scene.voxel_size,
+                       num_iterations=iters, truncation=0.1, learning_rate=0.01, max_voxel_hit=10, max_distance=10.0,
+                       depth_variance=True)
+        b.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            times.append(a.elapsed_time(b))
+    ms_plain = sum(times) / len(times)
+    # the same loop with one CUDA graph per iteration (GraphTracker): no per-iteration host work
+    tracker = rh.GraphTracker(scene.rays_cam.reshape(-1, 3).shape[0], ms, dec, crit, scene.voxel_size, N_rays=n_rays,
+                              step_size=0.1 * scene.voxel_size, truncation=0.1, learning_rate=0.01, max_distance=10.0,
+                              depth_variance=True, device=device)
+    times, errs = [], []
+    for i in range(frames + 2):
+        f = scene.frames[i % len(scene.frames)]
+        frame = _Frame(scene, f, device, seed=i)
+        pose = f.pose.clone()
+        pose[:3, 3] += torch.tensor([0.02, -0.01, 0.015])
+        init = OptimizablePose.from_matrix(pose)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out_pose, _, _ = tracker.track(init, frame, iters)
+        b.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            times.append(a.elapsed_time(b))
+            errs.append(float((out_pose.translation().detach().cpu() - f.pose[:3, 3]).norm()))   # (untrained map: timing only)
+    ms_frame = sum(times) / len(times)
+    return {"ms_per_frame": ms_frame, "fps": 1000.0 / ms_frame, "rays": n_rays, "iters_per_frame": iters, "frames_timed": len(times),
+            "ms_per_frame_python_loop": ms_plain,
+            "note": "GraphTracker: frame upload to static buffers + 30 replays of one CUDA graph (pixel sampling, ray assembly, fused "
+                    "render + median-gated loss + backward, pose autograd, Adam); ms_per_frame_python_loop = the drop-in track_frame "
+                    "with the reference's per-iteration host loop; random-init map, so only the timing is meaningful"}
 
 
 def cpu_baseline(s, ms_cpu):

@@ -223,6 +223,7 @@ typedef struct {
     const float *noise;                    /* [>=R_h, noise_stride] uniform(0.001,0.999) or NULL */
     int noise_stride;
     uint64_t seed;                         /* counter-based noise when noise==NULL */
+    const uint64_t *seed_dev;              /* optional device-side addend to `seed` (lets a CUDA graph replay draw fresh noise) */
     /* intermediates (caller-allocated; readable by tests / the drop-in API) */
     int *hit_idx;                          /* [n_max,R] slot-major, sorted by entry depth */
     float *hit_min, *hit_max;              /* [n_max,R] */

@@ -35,7 +35,7 @@ class RenderT(C.Structure):
                                      "vertex_idx", "emb")]
         + [("dec", DecoderT), ("dec_ws", C.c_void_p), ("wgrad_ws", C.c_void_p), ("wgrad_ws_bytes", C.c_int64),
            ("noise", C.c_void_p), ("noise_stride", C.c_int),
-           ("seed", C.c_uint64)]
+           ("seed", C.c_uint64), ("seed_dev", C.c_void_p)]
         + [(n, C.c_void_p) for n in ("hit_idx", "hit_min", "hit_max", "hit_count", "hit_ray", "ray_rank",
                                      "samp_off", "samp_vox", "samp_ray", "samp_z", "samp_dist", "samp_out",
                                      "samp_w", "samp_gout", "ray_out", "scratch_i", "scratch_f", "counters")]

@@ -215,7 +215,7 @@ k_sample_fused(pslam_render_t p, int *__restrict__ block_counts)
             s = WRITE ? sample_ray(hv, nz, csr, j, nc, P, prob0, steps, -1.0f)
                       : sample_ray(hv, nz, cs, j, nc, P, prob0, steps, -1.0f);
         } else {
-            HashNoise nz{p.seed ^ ((uint64_t)(uint32_t)q * 0xD1B54A32D192ED03ull)};
+            HashNoise nz{(p.seed + (p.seed_dev ? *p.seed_dev : 0ull)) ^ ((uint64_t)(uint32_t)q * 0xD1B54A32D192ED03ull)};
             s = WRITE ? sample_ray(hv, nz, csr, j, nc, P, prob0, steps, -1.0f)
                       : sample_ray(hv, nz, cs, j, nc, P, prob0, steps, -1.0f);
         }

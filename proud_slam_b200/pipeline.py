@@ -93,7 +93,7 @@ class RenderPipeline:
     def bind(self, rays_o, rays_d, map_states, dec_params, *, voxel_size, step_size, truncation,
              max_distance, max_depth=10.0, target_rgb=None, target_depth=None, noise=None, seed=0,
              weights=(0.5, 1.0, 10.0, 5000.0), tracking=False, g_emb=None, g_dec=None, grad_rays=False,
-             forward_only=False, defer_loss=False):
+             forward_only=False, defer_loss=False, seed_dev=None):
         """Fills the pslam_render_t block.  Tensors: rays_* [R,3] (or [1,R,3]) f32; map_states as the
         reference's dict (voxel_center_xyz [N,3] f32, voxel_structure [N,9] i32, voxel_vertex_idx [N,8]
         i32, voxel_vertex_emb [E,16] f32); dec_params = the 10 decoder tensors in state_dict order;
@@ -155,6 +155,7 @@ class RenderPipeline:
         else:
             a.noise, a.noise_stride = None, 0
         a.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        a.seed_dev = None if seed_dev is None else seed_dev.data_ptr()   # int64 device scalar added to the seed
         for name in ("hit_idx", "hit_min", "hit_max", "hit_count", "hit_ray", "ray_rank", "samp_off", "samp_vox",
                      "samp_ray", "samp_z", "samp_dist", "samp_out", "samp_w", "samp_gout", "ray_out", "scratch_i",
                      "scratch_f", "counters", "loss", "loss_raw", "g_rays_o", "g_rays_d"):
@@ -169,7 +170,7 @@ class RenderPipeline:
         else:
             a.g_dec = DecoderGradT()
         self._keep = (rays_o, rays_d, target_rgb, target_depth, centres, structure, vidx, emb, list(dec_params), noise,
-                      g_emb, g_dec)
+                      g_emb, g_dec, seed_dev)
         self.R = R
         return self
 

@@ -195,3 +195,13 @@ def test_tracking_and_mapping_loops_run_and_improve(device):
     e1 = float((pose.translation().detach() - true_t).norm())
     assert hit_mask.shape == (1024,) and hit_mask.dtype == torch.bool
     assert e1 < e0, (e0, e1)
+    # the same optimisation as one CUDA graph per iteration
+    start2 = util.TestFrame(s, s.frames[1], stamp=1, device=device, perturb=(0.03, -0.02, 0.02), seed=9)
+    tracker = rh.GraphTracker(start2.rays_d.shape[0], {k: v.detach() for k, v in ms.items()}, dec, crit, s.voxel_size, N_rays=1024,
+                              step_size=0.1 * s.voxel_size, truncation=0.1, learning_rate=0.01, max_distance=10.0, depth_variance=True,
+                              device=device)
+    pose2, _, hm2 = tracker.track(start2.pose, start2, 40)
+    e2 = float((pose2.translation().detach() - true_t).norm())
+    assert e2 < e0, (e0, e2)
+    pose3, _, _ = tracker.track(start2.pose, start2, 40)      # the captured graph is reused for the next frame
+    assert float((pose3.translation().detach() - true_t).norm()) < e0
