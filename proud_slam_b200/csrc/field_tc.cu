@@ -37,6 +37,8 @@ constexpr int kStages = 8;        // weight ring depth of the forward kernel
 constexpr int kStagesBwd = 4;     // ... of the backward kernel (the rest of shared memory stages the wgrad scratch)
 constexpr int kStageBytes = 18432;   // 144 rows x 16 k x 4 B x (hi, lo)
 constexpr int kStagingBytes = 65536; // one layer of one tile in scratch order: [4 slices][32 groups][32 samples][16 B]
+constexpr int kCluster = 2;          // CTAs that share one multicast weight stream (each loads its share of every chunk)
+constexpr uint16_t kClusterMask = (1u << kCluster) - 1u;
 constexpr int kTmemCols = 512;
 constexpr int cAHI = 0, cALO = 144, cD = 288;
 constexpr int kLayersFwd = 5, kLayersAll = 10;
@@ -156,7 +158,8 @@ __device__ long long *g_tc_trace = nullptr;
     } while (0)
 
 template <bool BWD>
-__global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc(FieldParams p, const float *__restrict__ wstream)
+__global__ void __cluster_dims__(tc::kCluster, 1, 1) __launch_bounds__(tc::kThreads, 1)
+k_field_tc(FieldParams p, const float *__restrict__ wstream)
 {
     using namespace tc;
     constexpr int NL = BWD ? kLayersAll : kLayersFwd;
@@ -174,9 +177,13 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc(FieldParams p, con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nsamp = p.nsamp_dev ? *p.nsamp_dev : p.nsamp;
     const int ntiles = (nsamp + 127) / 128;
+    // The CTAs of a cluster consume one shared weight stream in lockstep, so they all run the same number of
+    // tile iterations; iterations whose tile index is past the end are dummies (no valid rows, nothing stored).
+    const int iters = (ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    const uint32_t crank = cluster_ctarank();
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+        for (int i = 0; i < kStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, kCluster); }
         mbar_init(a_ready, kWorkers);
         mbar_init(mma_done, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(st_full + i, kWorkers); mbar_init(st_free + i, 1); }
@@ -197,20 +204,23 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc(FieldParams p, con
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
+    cluster_sync();   // every CTA's barriers are initialised before any peer multicasts into them
     const uint32_t tmem = *tmem_ptr;
 
     if (warp == 0) {
         // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
+        // each CTA fetches its share of every chunk and multicasts it to the whole cluster: the L2 -> SM weight
+        // traffic per SM drops by the cluster size (it was the busiest stream on the SM's L2 port)
         int stage = 0, phase = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int it = 0; it < iters; ++it) {
             const unsigned char *src = reinterpret_cast<const unsigned char *>(wstream);
             for (int l = 0; l < NL; ++l) {
-                const uint32_t bytes = (uint32_t)cN[l] * 128u;
+                const uint32_t bytes = (uint32_t)cN[l] * 128u, part = bytes / kCluster;
                 for (int c = 0; c < cK[l] / 16; ++c) {
-                    mbar_wait(empty + stage, phase ^ 1);
+                    mbar_wait(empty + stage, phase ^ 1);     // all kCluster CTAs are done reading this stage
                     if (elect_one()) {
                         mbar_arrive_expect_tx(full + stage, bytes);
-                        bulk_g2s(smem + stage * kStageBytes, src, bytes, full + stage);
+                        bulk_g2s_mcast(smem + stage * kStageBytes + crank * part, src + crank * part, part, full + stage, kClusterMask);
                     }
                     __syncwarp();
                     src += bytes;
@@ -224,7 +234,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc(FieldParams p, con
         int stage = 0, phase = 0;
         uint32_t uses = 0;   // a_ready phase counter
         int tile_i = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_i) {
+        for (int it = 0; it < iters; ++it, ++tile_i) {
             for (int l = 0; l < NL; ++l) {
                 const int N = cN[l];
                 const uint32_t idesc = idesc_tf32(128, N);
@@ -249,7 +259,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc(FieldParams p, con
                             mma_tf32_ts(d, a_hi + k, b_lo, idesc, 1u);
                             mma_tf32_ts(d, a_hi + k, b_hi, idesc, 1u);
                         }
-                        mma_commit(empty + stage);                     // stage is free once these MMAs have read it
+                        mma_commit_mcast(empty + stage, kClusterMask);  // this CTA is done with the stage: tell every producer
                         if (c == nchunks - 1) mma_commit(mma_done);
                     }
                     __syncwarp();
@@ -263,7 +273,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc(FieldParams p, con
         if (spill) {
             const int g0s[8] = {gH1, gH2, gT, gHC, gG4, gG3, gG2, gG1};   // order in which the workers produce the layers
             uint32_t sc = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {   // dummy iterations store nothing
 #pragma unroll
                 for (int i = 0; i < 8; ++i, ++sc) {
                     const int b = sc & 1;
@@ -296,14 +306,15 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc(FieldParams p, con
         uint32_t sc = 0;                              // staged layers so far (two staging buffers alternate)
         // staging: this thread's 16-byte column of the current buffer ([slice q][group][lane][16 B]); waits until the
         // bulk store that last read the buffer is done
+        bool real_tile = true;
         auto stage_begin = [&]() -> unsigned char * {
-            if (!spill) return nullptr;
+            if (!spill || !real_tile) return nullptr;
             const int b = sc & 1;
             if (sc >= 2) mbar_wait(st_free + b, ((sc >> 1) - 1) & 1);
             return smem + SM::oStaging + b * kStagingBytes + q * 16384 + lane * 16;
         };
         auto stage_end = [&]() {
-            if (!spill) return;
+            if (!spill || !real_tile) return;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic smem writes -> bulk-copy engine
             mbar_arrive(st_full + (sc & 1));
             ++sc;
@@ -321,10 +332,12 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc(FieldParams p, con
             mbar_arrive(a_ready);
             ++lcount;
         };
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_i, lcount = -1) {
-            const int s = tile * 128 + m;
+        for (int it = 0; it < iters; ++it, ++tile_i, lcount = -1) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            real_tile = tile < ntiles;
+            const int s = real_tile ? tile * 128 + m : nsamp;      // rows of a dummy iteration are all out of range
             unsigned char *scr = nullptr;   // this thread's 16-byte column in the tile's wgrad scratch (small groups go direct)
-            if (spill) scr = p.wg_scratch + ((size_t)tile * 4 + q) * kSliceBytes + (size_t)lane * 16;
+            if (spill && real_tile) scr = p.wg_scratch + ((size_t)tile * 4 + q) * kSliceBytes + (size_t)lane * 16;
             int vox = -1, ray = -1;
             float z = 0.0f, px = 0.f, py = 0.f, pz = 0.f;
             if (threadIdx.x == 64) TC_TRACE(tile_i, 0, 6);            // gather starts
@@ -520,6 +533,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) k_field_tc(FieldParams p, con
     }
     fence_before_sync();
     __syncthreads();
+    cluster_sync();   // no CTA leaves while a peer may still multicast into its shared memory or signal its barriers
     if (warp == 0) tmem_dealloc(tmem, tc::kTmemCols);
 }
 
@@ -898,8 +912,25 @@ static int launch_tc(const FieldParams &fp, int max_samples, cudaStream_t st)
         if (e != cudaSuccess) { set_error("field_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         configured = true;
     }
+    // persistent grid = as many whole clusters as can be resident at once (GPC boundaries may strand a few SMs)
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(num_sms() / tc::kCluster * tc::kCluster);
+        cfg.blockDim = dim3(tc::kThreads);
+        cfg.dynamicSmemBytes = tc::Smem<BWD>::bytes;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = tc::kCluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        int n = 0;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&n, k_field_tc<BWD>, &cfg);
+        if (e != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = num_sms() / tc::kCluster; }
+        max_clusters = n < num_sms() / tc::kCluster ? n : num_sms() / tc::kCluster;
+    }
     const int tiles = ceil_div(max_samples, 128);
-    const int grid = tiles < num_sms() ? (tiles > 0 ? tiles : 1) : num_sms();
+    int grid = ceil_div(tiles > 0 ? tiles : 1, tc::kCluster) * tc::kCluster;
+    if (grid > max_clusters * tc::kCluster) grid = max_clusters * tc::kCluster;
     k_field_tc<BWD><<<grid, tc::kThreads, tc::Smem<BWD>::bytes, st>>>(fp, fp.ws_tc);
     PSLAM_CHECK_LAUNCH(BWD ? "field_tc_backward" : "field_tc_forward");
     return 0;
