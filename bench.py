@@ -307,7 +307,8 @@ def run_gpu(args):
             "clocks": clocks,
             "roofline": {"kernel": "k_field_tc<bwd> (tcgen05 3xTF32: decoder recompute + dgrad, fused trilinear backward, wgrad spill)", "bound": "tensor",
                          "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
-                         "traffic": None, "peak_source": peaks["source"] + ", dense bf16 burst (the kernel issues kind::tf32 MMAs, x3 for the fp32-equivalent "
+                         "traffic": 985.8e6 if (P > 190000 and P < 194000) else None,   # dram read+write per launch, ncu --set full (profiles/r01_tc_summary.md)
+                         "peak_source": peaks["source"] + ", dense bf16 burst (the kernel issues kind::tf32 MMAs, x3 for the fp32-equivalent "
                                                         "split and x2 for the recompute: 6 hardware TF32 FLOPs per algorithmic FLOP)",
                          "algorithmic_flops_per_launch": flops_bwd, "kernel_ms": prof["field_bwd_dgrad_kernel"]},
             "stage_ms": prof,

@@ -184,3 +184,26 @@ def test_hash_noise_is_in_range_and_deterministic(device):
         zs.append(pipe.samples()["sampled_point_depth"].cpu())
     assert torch.equal(zs[0], zs[1])
     assert zs[0].shape != zs[2].shape or not torch.equal(zs[0], zs[2])
+
+
+@pytest.mark.parametrize("R", [1, 5, 63, 65, 299])
+def test_ragged_batch_sizes_hit_lists(R, device):
+    """Batch sizes that leave warps / blocks of the 8-lanes-per-ray traversal partly empty."""
+    from oracle import render_oracle as ro
+    from proud_slam_b200 import scene as sc
+    from proud_slam_b200.pipeline import RenderPipeline
+    s, ms = util.build_scene("tiny")
+    dec = [p.detach().to(device) for p in ro.decoder_params(seed=1)]
+    rays_o, rays_d, rgb, depth = sc.sample_batch(s, [0], R, seed=R)
+    inv = util.device_rcp(rays_d.reshape(-1, 3), device)
+    ref, ref_hits = ro.ray_intersect_vox(rays_o, rays_d, ms["voxel_center_xyz"].detach(), ms["voxel_structure"], s.voxel_size, 10, 10.0, inv_dir=inv)
+    msd = {k: v.detach().to(device) for k, v in ms.items()}
+    pipe = RenderPipeline(R, device)
+    pipe.bind(rays_o.to(device), rays_d.to(device), msd, dec, voxel_size=s.voxel_size, step_size=0.1 * s.voxel_size, truncation=0.1,
+              max_distance=10.0, seed=1, forward_only=True)
+    pipe.step()
+    inter, hits = pipe.intersections()
+    assert torch.equal(hits.cpu(), ref_hits)
+    for k in ref:
+        assert torch.equal(inter[k].cpu(), ref[k]), k
+    assert pipe.counts()["R_h"] == int(ref_hits.sum())
