@@ -36,6 +36,10 @@ CRIT_W = (0.5, 1.0, 10.0, 5000.0)      # rgb, depth, fs, sdf (configs/replica/re
 WIDTH = 128
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel at the bench workload (ncu --set full, profiles/*_summary.md)
+NCU_TRAFFIC = {0: 985.8e6, 2: None}
+
+
 def macs_per_sample(w):
     return 16 * w + w * w + w * 129 + 144 * w + w * 3      # nrgbd.py:106-113
 
@@ -285,6 +289,11 @@ def run_gpu(args):
     if rank == 0:
         peaks = measured_peaks()
         P = counts["n_samples"]
+        build = int(os.environ.get("PSLAM_DECODER", "2"))   # include/proud_slam_b200.h: PSLAM_OPT_DECODER
+        kname, ktext, dtype = {
+            0: ("k_field_tc<bwd>", "tcgen05 3xTF32", "f32 (3xTF32 split, f32 accumulate)"),
+            1: ("k_field<128,bwd>", "fp32 SIMT", "f32"),
+            2: ("k_field_bf<bwd>", "tcgen05 3xBF16", "bf16x3 (hi/lo bf16 split, f32 accumulate)")}[build]
         # dominant kernel: k_field_tc<bwd> (forward recompute + dgrad chain + trilinear backward + scratch spill);
         # algorithmic FLOPs = the dgrad GEMMs once (2 MACs P), neither the recompute nor the x3 of the TF32 split
         flops_bwd = 2.0 * macs_per_sample(WIDTH) * P
@@ -293,7 +302,7 @@ def run_gpu(args):
         value = world * R / (ms_step * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype,
             "data": "synthetic",
             "config": {"workload": f"{SCENE}: {KEYFRAMES} keyframes x {RAYS_PER_FRAME} rays = {R} rays/iter per GPU, {n_oct} octants "
                                    f"({n_vox} voxels) at 0.2 m, {E}x16 embeddings, decoder width {WIDTH}, mapping fwd+bwd",
@@ -305,11 +314,11 @@ def run_gpu(args):
                     "h2d_bytes_per_step": int(sum(t.numel() * 4 for t in host)), "d2h_bytes_per_step": 64},
             "gpu_launches": args.steps * 19,
             "clocks": clocks,
-            "roofline": {"kernel": "k_field_tc<bwd> (tcgen05 3xTF32: decoder recompute + dgrad, fused trilinear backward, wgrad spill)", "bound": "tensor",
+            "roofline": {"kernel": f"{kname} ({ktext}: decoder recompute + dgrad, fused trilinear backward, wgrad spill)", "bound": "tensor",
                          "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
-                         "traffic": 985.8e6 if (P > 190000 and P < 194000) else None,   # dram read+write per launch, ncu --set full (profiles/r01_tc_summary.md)
-                         "peak_source": peaks["source"] + ", dense bf16 burst (the kernel issues kind::tf32 MMAs, x3 for the fp32-equivalent "
-                                                        "split and x2 for the recompute: 6 hardware TF32 FLOPs per algorithmic FLOP)",
+                         "traffic": NCU_TRAFFIC.get(build) if (P > 190000 and P < 194000) else None,   # dram read+write per launch, ncu --set full (profiles/)
+                         "peak_source": peaks["source"] + ", dense bf16 burst (the kernel issues 3 split MMAs per product and recomputes the "
+                                                        "forward: 6 hardware FLOPs per algorithmic FLOP, so frac <= 1/6 by construction)",
                          "algorithmic_flops_per_launch": flops_bwd, "kernel_ms": prof["field_bwd_dgrad_kernel"]},
             "stage_ms": prof,
         }

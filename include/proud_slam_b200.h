@@ -39,8 +39,10 @@ const char *pslam_last_error(void);
 /* Device properties the host side sizes grids with: out[0]=SM count,
  * out[1]=compute capability*10, out[2]=max opt-in smem per block. */
 int pslam_device_info(int *out3);
-/* Process-wide configuration.  PSLAM_OPT_DECODER: 0 = decoder on the tcgen05 tensor cores where
- * available (width 128; 3xTF32 operand splitting, fp32-equivalent), 1 = always the fp32 SIMT build. */
+/* Process-wide configuration.  PSLAM_OPT_DECODER selects the build of the width-128 decoder:
+ * 0 = tcgen05 tensor cores with 3xTF32 operand splitting (fp32-equivalent), 1 = fp32 SIMT build,
+ * 2 = tcgen05 tensor cores with 3xBF16 operand splitting (16-17 significant bits per operand,
+ * <= ~1e-5 relative; inside the 1e-4 parity bound).  Width 256 always runs the SIMT build. */
 #define PSLAM_OPT_DECODER 1
 int pslam_set_option(int key, int value);
 
@@ -112,6 +114,11 @@ int pslam_debug_rcp(const float *in, float *out, int n, pslam_stream_t stream);
 /* Test helper: timeline trace of CTA 0 of the tcgen05 decoder kernels into dev_buf[4*10*8] (clock64), NULL = off. */
 int pslam_debug_tc_trace(long long *dev_buf);
 int pslam_debug_umma_gemm(const float *A, const float *B, float *D, int N, int K, int split3, pslam_stream_t stream);
+/* Same for the 3xBF16 build (kind::f16).  mode 0: D = A[128,K] * B[N,K]^T with A packed in tensor memory and B
+ * K-major in shared memory; mode 1: D = At[K,128]^T * Bt[K,N], both operands MN-major in shared memory (the
+ * weight-gradient form; K <= 64).  N in 16..144 step 16, K a multiple of 16. */
+int pslam_debug_umma_gemm_bf(const float *A, const float *B, float *D, int N, int K, int mode, pslam_stream_t stream);
+int pslam_debug_bf_trace(long long *dev_buf);
 
 /* ------------------------------------------------------------------------
  * Torch-level stages of render_rays (src/variations/render_helpers.py)

@@ -63,6 +63,8 @@ _PROTOTYPES = {
     "pslam_debug_rcp": (C.c_int, [_P, _P, _I, _S]),
     "pslam_debug_tc_trace": (C.c_int, [_P]),
     "pslam_debug_umma_gemm": (C.c_int, [_P, _P, _P, _I, _I, _I, _S]),
+    "pslam_debug_umma_gemm_bf": (C.c_int, [_P, _P, _P, _I, _I, _I, _S]),
+    "pslam_debug_bf_trace": (C.c_int, [_P]),
     "pslam_set_option": (C.c_int, [_I, _I]),
     "pslam_decoder_ws_count": (C.c_int64, [_I]),
     "pslam_trilinear_fwd": (C.c_int, [_I, _P, _P, _P, _P, _P, _F, _P, _S]),
@@ -118,6 +120,9 @@ def lib():
                            f"({handle.pslam_render_sizeof()} vs {C.sizeof(RenderT)})")
     if handle.pslam_render_offsetof_loss() != RenderT.loss.offset:
         raise RuntimeError("pslam_render_t field offsets differ between the library and its Python mirror")
+    mode = os.environ.get("PSLAM_DECODER")   # decoder build override (include/proud_slam_b200.h: PSLAM_OPT_DECODER)
+    if mode is not None and handle.pslam_set_option(1, int(mode)) != 0:
+        raise RuntimeError(f"PSLAM_DECODER={mode}: " + handle.pslam_last_error().decode(errors="replace"))
     _lib = handle
     return _lib
 

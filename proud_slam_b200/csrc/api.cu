@@ -40,7 +40,7 @@ int num_sms()
     return cached[dev];
 }
 
-static int g_decoder_mode = 0;
+static int g_decoder_mode = 2;   // tcgen05 3xBF16 (field_bf.cu)
 int decoder_mode() { return g_decoder_mode; }
 
 static int check_render(const pslam_render_t *p)
@@ -93,7 +93,7 @@ extern "C" int pslam_abi_version(void) { return PSLAM_ABI_VERSION; }
 
 extern "C" int pslam_set_option(int key, int value)
 {
-    if (key == PSLAM_OPT_DECODER && (value == 0 || value == 1)) { g_decoder_mode = value; return 0; }
+    if (key == PSLAM_OPT_DECODER && (value == 0 || value == 1 || value == 2)) { g_decoder_mode = value; return 0; }
     set_error("unknown option %d=%d", key, value);
     return PSLAM_E_ARG;
 }

@@ -720,6 +720,7 @@ static int pack_decoder(const pslam_decoder_t &d, float *ws, cudaStream_t st)
     else k_pack_decoder<256><<<ceil_div(FieldCfg<256>::WS, 256), 256, 0, st>>>(d, ws);
     PSLAM_CHECK_LAUNCH("pack_decoder");
     if (d.width == 128 && decoder_mode() == 0) return tc_pack_decoder(d, ws + FieldCfg<128>::WS, st);
+    if (d.width == 128 && decoder_mode() == 2) return bf_pack_decoder(d, ws + FieldCfg<128>::WS, st);
     return 0;
 }
 static const float *tc_region(const pslam_decoder_t &d, const float *ws) { return d.width == 128 ? ws + FieldCfg<128>::WS : nullptr; }
@@ -731,6 +732,11 @@ static int launch_field(const FieldParams &fp, bool bwd, int max_samples, cudaSt
         // tensor-core backward needs the wgrad scratch when decoder gradients are wanted
         if (!fp.grad_dec || (fp.wg_scratch && fp.wg_scratch_bytes >= tc_wgrad_scratch_bytes(max_samples)))
             return tc_launch_field_backward(fp, max_samples, st, part);
+    }
+    if (fp.dec.width == 128 && decoder_mode() == 2) {
+        if (!bwd) return bf_launch_field_forward(fp, max_samples, st);
+        if (!fp.grad_dec || (fp.wg_scratch && fp.wg_scratch_bytes >= bf_wgrad_scratch_bytes(max_samples)))
+            return bf_launch_field_backward(fp, max_samples, st, part);
     }
     if (fp.dec.width == 128) return bwd ? launch_field_t<128, true>(fp, max_samples, st) : launch_field_t<128, false>(fp, max_samples, st);
     return bwd ? launch_field_t<256, true>(fp, max_samples, st) : launch_field_t<256, false>(fp, max_samples, st);

@@ -1,0 +1,892 @@
+// Kernel 4 on the 5th-generation tensor cores, "3xBF16" build: the width-128 SDF/colour decoder
+// (src/variations/nrgbd.py:116-135) fused with the trilinear corner-embedding lookup
+// (src/variations/render_helpers.py:105-156, 47-59), forward and backward.
+//
+// Same tile / role structure as field_tc.cu (tile = 128 samples = the 128 lanes of tensor memory, A operand
+// from tensor memory, weights streamed by multicast bulk TMA, persistent 2-CTA clusters), but every value is
+// split into TWO bf16 halves instead of two tf32 halves:
+//         x = hi + lo,  hi = rn_bf16(x), lo = rn_bf16(x - hi)        (16-17 significant bits)
+//         a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi                   (kind::f16 MMAs, fp32 accumulate in TMEM)
+// which is <= ~1e-5 relative per product (the reference's tolerance is 1e-4; field_tc.cu stays the
+// fp32-equivalent build).  What that buys:
+//   * one MMA covers K = 16 instead of 8: half the tcgen05.mma instructions, half the weight-stream bytes,
+//     half the tensor-memory columns and tcgen05.st traffic for the A operand (two values per 32-bit column);
+//   * hi and lo of one value are 4 bytes together, so the wgrad scratch can hold the operands ALREADY SPLIT
+//     and in MMA order at the same 4 B/element as raw fp32.  The scratch is written in the MN-major
+//     (sample-major) core-matrix layout, so k_wgrad_bf is nothing but bulk-TMA loads feeding tcgen05.mma
+//     with both operands MN-major from shared memory: no transform warps, no transposition, no re-split.
+//   TMEM columns (k_field_bf): A_hi [0,72)  A_lo [72,144)  D [144,288).
+#include "decoder_layers.cuh"
+#include "field.cuh"
+#include "kernels.h"
+#include "umma.cuh"
+
+namespace pslam {
+
+using namespace umma;
+
+namespace bf {
+constexpr int kThreads = 352;     // warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 workers, warp 10 scratch store
+constexpr int kWorkers = 256;
+constexpr int kStages = 8;        // weight ring depth of the forward kernel
+constexpr int kStagesBwd = 4;     // ... of the backward kernel (the rest of shared memory stages the wgrad scratch)
+constexpr int kChunkK = 32;       // reduction elements per weight chunk (two MMA k-steps; the tail chunk of K = 144 / 16 has one)
+constexpr int kStageBytes = 18432;   // 144 rows x 32 k x 2 B x (hi, lo)
+constexpr int kStagingBytes = 65536; // one 128-feature operand of one tile in scratch order
+constexpr int kCluster = 2;
+constexpr uint16_t kClusterMask = (1u << kCluster) - 1u;
+constexpr int kTmemCols = 512;
+constexpr int cAHI = 0, cALO = 72, cD = 144;
+using declayers::kLayersAll;
+using declayers::kLayersFwd;
+__device__ __constant__ int cN[kLayersAll] = {128, 128, 144, 128, 16, 128, 144, 128, 128, 16};
+__device__ __constant__ int cK[kLayersAll] = {16, 128, 128, 144, 128, 16, 128, 144, 128, 128};
+__device__ __constant__ int cAcol[kLayersAll] = {64, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // packed A column of the layer's k = 0
+template <bool BWD>
+struct Smem {
+    static constexpr int nStages = BWD ? kStagesBwd : kStages;
+    static constexpr int oStaging = nStages * kStageBytes;
+    static constexpr int oBars = oStaging + (BWD ? 2 * kStagingBytes : 0);   // full[8], empty[8], a_ready, mma_done, st_full[2], st_free[2]
+    static constexpr int oTmemPtr = oBars + 8 * (2 * kStages + 2 + 4);
+    static constexpr int oBias = oTmemPtr + 16;                     // b1[128] b2[128] b3f[128] b4[128] b3_0 b5[3]
+    static constexpr int bytes = oBias + 4 * (4 * 128 + 4);
+};
+
+// wgrad scratch, per 128-sample tile: eight 128-feature operands and two 16-feature operands, each already split
+// (hi / lo bf16 planes) and in the MN-major no-swizzle core-matrix layout of tcgen05.mma (umma.cuh: sdesc):
+//     [half h = sample / 64][plane hi, lo][kb = (sample / 8) % 8][fb = feature / 8][sample % 8][8 features x 2 B]
+// so that (operand, half) = one contiguous bulk copy whose 16-sample k-steps are 2 kb blocks apart.
+constexpr size_t kOpBytes = 65536, kSmallBytes = 8192;
+constexpr int oH1 = 0, oH2 = 1, oT = 2, oHC = 3, oG1 = 4, oG2 = 5, oG3 = 6, oG4 = 7;   // x kOpBytes
+constexpr size_t oF = 8 * kOpBytes, oG5 = oF + kSmallBytes, kTileBytes = oG5 + kSmallBytes;   // 540 672 B = 4.2 kB / sample
+}  // namespace bf
+
+// Re-packs the decoder into the bf16 weight stream: layers in order, each as ceil(K/32) chunks of
+// [hi block | lo block], each block = kk/8 k-chunks x N rows x 16 B (8 bf16 along K) -- K-major, no swizzle.
+__global__ void k_bf_pack(pslam_decoder_t d, uint16_t *__restrict__ out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int base = 0;   // uint16 offset of the layer in `out`
+#pragma unroll
+    for (int l = 0; l < bf::kLayersAll; ++l) {
+        const int N = bf::cN[l], K = bf::cK[l];
+        if (i < N * K) {
+            const int n = i / K, k = i % K;
+            const int c = k / bf::kChunkK, kr = k % bf::kChunkK;
+            const int kk = (K - c * bf::kChunkK) < bf::kChunkK ? (K - c * bf::kChunkK) : bf::kChunkK;
+            uint32_t hi, lo;
+            bf16_split2(tc_weight(d, l, n, k), 0.0f, hi, lo);
+            uint16_t *chunk = out + base + c * (N * bf::kChunkK * 2);
+            const int off = (kr >> 3) * (N * 8) + n * 8 + (kr & 7);
+            chunk[off] = (uint16_t)(hi & 0xffffu);
+            chunk[N * kk + off] = (uint16_t)(lo & 0xffffu);
+            return;
+        }
+        i -= N * K;
+        base += 2 * N * K;
+    }
+}
+
+// One epilogue over this thread's 64 accumulator columns [col0, col0+64): accumulators -> registers ->
+// (bias / activation / mask) -> hi/lo bf16 pairs -> next A operand (tensor memory, two values per column)
+// and optionally the staging buffer of the wgrad scratch (the same packed words, 16 B = one core-matrix row).
+//   MODE 0: y = relu(D + bias), records y > 0 in mask[]        (forward hidden layers)
+//   MODE 1: y = D + bias                                       (forward, no activation)
+//   MODE 2: y = mask ? D : 0                                   (dgrad through a ReLU)
+//   MODE 3: y = D                                              (dgrad, no activation)
+template <int MODE>
+__device__ __forceinline__ void bf_epilogue64(uint32_t trow, int col0, const float *bias, uint32_t (&mask)[2], unsigned char *stg)
+{
+    using namespace bf;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {   // fully unrolled: mask[] must stay in registers
+        const int c0 = col0 + 32 * b;
+        uint32_t v[32];
+        tmem_ld32(trow + cD + c0, v);
+        tmem_wait_ld();
+        uint32_t bits = 0u;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+            float y = __uint_as_float(v[e]);
+            if (MODE == 0) { y = fmaxf(y + bias[c0 + e], 0.0f); bits |= (y > 0.0f ? 1u : 0u) << e; }
+            if (MODE == 1) y = y + bias[c0 + e];
+            if (MODE == 2) y = ((mask[b] >> e) & 1u) ? y : 0.0f;
+            v[e] = __float_as_uint(y);
+        }
+        if (MODE == 0) mask[b] = bits;
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) bf16_split2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]), hi[e], lo[e]);
+        if (stg) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                unsigned char *dst = stg + (size_t)(c0 / 8 + j) * 128;
+                *reinterpret_cast<uint4 *>(dst) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                *reinterpret_cast<uint4 *>(dst + 16384) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+            }
+        }
+        tmem_st16(trow + cAHI + c0 / 2, hi);
+        tmem_st16(trow + cALO + c0 / 2, lo);
+    }
+}
+
+// optional timeline trace of CTA 0 (pslam_debug_bf_trace): [tile<4][layer<10][8] clock64 stamps (+ 40 x 8 for k_wgrad_bf)
+__device__ long long *g_bf_trace = nullptr;
+#define BF_TRACE(tile_i, layer, slot)                                                                   \
+    do {                                                                                                \
+        if (g_bf_trace && blockIdx.x == 0 && (tile_i) < 4) g_bf_trace[((tile_i) * 10 + (layer)) * 8 + (slot)] = clock64(); \
+    } while (0)
+
+template <bool BWD>
+__global__ void __cluster_dims__(bf::kCluster, 1, 1) __launch_bounds__(bf::kThreads, 1)
+k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
+{
+    using namespace bf;
+    constexpr int NL = BWD ? kLayersAll : kLayersFwd;
+    using SM = Smem<BWD>;
+    constexpr int NS = SM::nStages;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + SM::oBars);
+    uint64_t *empty = full + kStages;
+    uint64_t *a_ready = empty + kStages;
+    uint64_t *mma_done = a_ready + 1;
+    uint64_t *st_full = mma_done + 1, *st_free = st_full + 2;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(smem + SM::oTmemPtr);
+    float *sBias = reinterpret_cast<float *>(smem + SM::oBias);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nsamp = p.nsamp_dev ? *p.nsamp_dev : p.nsamp;
+    const int ntiles = (nsamp + 127) / 128;
+    // The CTAs of a cluster consume one shared weight stream in lockstep, so they all run the same number of
+    // tile iterations; iterations whose tile index is past the end are dummies (no valid rows, nothing stored).
+    const int iters = (ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    const uint32_t crank = cluster_ctarank();
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, kCluster); }
+        mbar_init(a_ready, kWorkers);
+        mbar_init(mma_done, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(st_full + i, kWorkers); mbar_init(st_free + i, 1); }
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_ptr, kTmemCols);
+    const bool spill = BWD && p.wg_scratch != nullptr;   // activations / gradients go to the wgrad scratch
+    for (int i = threadIdx.x; i < 4 * 128 + 4; i += kThreads) {
+        float v;
+        if (i < 128) v = p.dec.b1[i];
+        else if (i < 256) v = p.dec.b2[i - 128];
+        else if (i < 384) v = p.dec.b3[1 + i - 256];
+        else if (i < 512) v = p.dec.b4[i - 384];
+        else if (i == 512) v = p.dec.b3[0];
+        else v = p.dec.b5[i - 513];
+        sBias[i] = v;
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    cluster_sync();   // every CTA's barriers are initialised before any peer multicasts into them
+    const uint32_t tmem = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
+        // each CTA fetches its share of every chunk and multicasts it to the whole cluster
+        int stage = 0, phase = 0;
+        for (int it = 0; it < iters; ++it) {
+            const unsigned char *src = wstream;
+            for (int l = 0; l < NL; ++l) {
+                const int N = cN[l], K = cK[l];
+                for (int k0 = 0; k0 < K; k0 += kChunkK) {
+                    const int kk = (K - k0) < kChunkK ? (K - k0) : kChunkK;
+                    const uint32_t bytes = (uint32_t)(N * kk * 4), part = bytes / kCluster;
+                    mbar_wait(empty + stage, phase ^ 1);     // all kCluster CTAs are done reading this stage
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(full + stage, bytes);
+                        bulk_g2s_mcast(smem + stage * kStageBytes + crank * part, src + crank * part, part, full + stage, kClusterMask);
+                    }
+                    __syncwarp();
+                    src += bytes;
+                    if (++stage == NS) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (whole warp loops; one elected lane issues) =====================
+        int stage = 0, phase = 0;
+        uint32_t uses = 0;   // a_ready phase counter
+        int tile_i = 0;
+        for (int it = 0; it < iters; ++it, ++tile_i) {
+            for (int l = 0; l < NL; ++l) {
+                const int N = cN[l], K = cK[l];
+                const uint32_t idesc = idesc_bf16(128, N);
+                if (lane == 0) BF_TRACE(tile_i, l, 0);          // MMA warp starts waiting for A
+                mbar_wait(a_ready, uses & 1);
+                ++uses;
+                fence_after_sync();
+                if (lane == 0) BF_TRACE(tile_i, l, 1);          // A ready seen
+                const uint32_t a_hi = tmem + cAHI + cAcol[l], a_lo = tmem + cALO + cAcol[l], d = tmem + cD;
+                for (int k0 = 0; k0 < K; k0 += kChunkK) {
+                    const int kk = (K - k0) < kChunkK ? (K - k0) : kChunkK;
+                    mbar_wait(full + stage, phase);
+                    fence_after_sync();
+                    const uint32_t sb = smem_u32(smem + stage * kStageBytes);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int s = 0; s < 2; ++s) {
+                            if (s * 16 < kk) {
+                                const uint32_t acol = (uint32_t)(k0 + s * 16) >> 1;
+                                const uint64_t b_hi = sdesc(sb + s * (2 * N * 16), N * 16, 128);
+                                const uint64_t b_lo = sdesc(sb + N * kk * 2 + s * (2 * N * 16), N * 16, 128);
+                                mma_bf16_ts(d, a_lo + acol, b_hi, idesc, (k0 | s) ? 1u : 0u);
+                                mma_bf16_ts(d, a_hi + acol, b_lo, idesc, 1u);
+                                mma_bf16_ts(d, a_hi + acol, b_hi, idesc, 1u);
+                            }
+                        }
+                        mma_commit_mcast(empty + stage, kClusterMask);  // this CTA is done with the stage: tell every producer
+                        if (k0 + kChunkK >= K) mma_commit(mma_done);
+                    }
+                    __syncwarp();
+                    if (++stage == NS) { stage = 0; phase ^= 1; }
+                }
+                if (lane == 0) BF_TRACE(tile_i, l, 2);          // all MMAs of the layer issued + committed
+            }
+        }
+    } else if (warp == 10) {
+        // ===================== scratch store warp: staged operand (shared memory) -> wgrad scratch by bulk TMA =====================
+        if (spill) {
+            const int ops[8] = {oH1, oH2, oT, oHC, oG4, oG3, oG2, oG1};   // order in which the workers produce the operands
+            uint32_t sc = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {   // dummy iterations store nothing
+#pragma unroll
+                for (int i = 0; i < 8; ++i, ++sc) {
+                    const int b = sc & 1;
+                    mbar_wait(st_full + b, (sc >> 1) & 1);
+                    if (elect_one()) {
+                        bulk_s2g(p.wg_scratch + (size_t)tile * kTileBytes + (size_t)ops[i] * kOpBytes, smem + SM::oStaging + b * kStagingBytes,
+                                 (uint32_t)kStagingBytes);
+                        bulk_commit();
+                        bulk_wait_read0();                    // the staging buffer may be rewritten
+                        mbar_arrive(st_free + b);
+                    }
+                    __syncwarp();
+                }
+            }
+            if (elect_one()) bulk_wait_all0();
+            __syncwarp();
+        }
+    } else {
+        // ===================== workers: two threads per sample row (64 accumulator columns each) =====================
+        const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;             // which 64 columns
+        const int col0 = half * 64;
+        const bool lead = half == 0;                  // the row's thread that also gathers / scatters
+        const int m = q * 32 + lane;                  // row of the tile
+        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+        // this row's 16 bytes inside an operand: [half][plane][kb][fb][m % 8] (big operands: 16 fb, small: 2 fb)
+        const int rowoff_big = (m >> 6) * 32768 + ((m >> 3) & 7) * 2048 + (m & 7) * 16;
+        const int rowoff_small = (m >> 6) * 4096 + ((m >> 3) & 7) * 256 + (m & 7) * 16;
+        uint32_t done_uses = 0;
+        uint32_t nomask[2] = {0u, 0u};
+        int tile_i = 0, lcount = -1;                  // trace bookkeeping
+        uint32_t sc = 0;                              // staged operands so far (two staging buffers alternate)
+        bool real_tile = true;
+        auto stage_begin = [&]() -> unsigned char * {
+            if (!spill || !real_tile) return nullptr;
+            const int b = sc & 1;
+            if (sc >= 2) mbar_wait(st_free + b, ((sc >> 1) - 1) & 1);
+            return smem + SM::oStaging + b * kStagingBytes + rowoff_big;
+        };
+        auto stage_end = [&]() {
+            if (!spill || !real_tile) return;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic smem writes -> bulk-copy engine
+            mbar_arrive(st_full + (sc & 1));
+            ++sc;
+        };
+        auto layer_done = [&]() {
+            mbar_wait(mma_done, done_uses & 1);
+            ++done_uses;
+            fence_after_sync();
+            if (threadIdx.x == 64) BF_TRACE(tile_i, lcount, 3);     // worker sees the accumulators
+        };
+        auto a_is_ready = [&]() {
+            tmem_wait_st();
+            fence_before_sync();
+            if (threadIdx.x == 64) BF_TRACE(tile_i, lcount + 1, 5);  // worker has produced the A of layer lcount+1
+            mbar_arrive(a_ready);
+            ++lcount;
+        };
+        for (int it = 0; it < iters; ++it, ++tile_i, lcount = -1) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            real_tile = tile < ntiles;
+            const int s = real_tile ? tile * 128 + m : nsamp;      // rows of a dummy iteration are all out of range
+            unsigned char *scr = nullptr;   // this tile's wgrad scratch (the two small operands go direct)
+            if (spill && real_tile) scr = p.wg_scratch + (size_t)tile * kTileBytes;
+            int vox = -1, ray = -1;
+            float z = 0.0f, px = 0.f, py = 0.f, pz = 0.f;
+            if (threadIdx.x == 64) BF_TRACE(tile_i, 0, 6);            // gather starts
+            // ---- features -> A[:, 128:144) (the lead thread of each row) ----
+            if (lead) {
+                float f[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) f[e] = 0.0f;
+                if (s < nsamp) {
+                    if (p.feat) {
+#pragma unroll
+                        for (int e = 0; e < 16; e += 4) {
+                            const float4 v = __ldg(reinterpret_cast<const float4 *>(p.feat + (size_t)s * 16 + e));
+                            f[e] = v.x; f[e + 1] = v.y; f[e + 2] = v.z; f[e + 3] = v.w;
+                        }
+                    } else {
+                        vox = __ldg(p.samp_vox + s);
+                        z = __ldg(p.samp_z + s);
+                        ray = __ldg(p.hit_ray + __ldg(p.samp_ray + s));
+                        const float x = __fadd_rn(__ldg(p.rays_o + ray * 3 + 0), __fmul_rn(__ldg(p.rays_d + ray * 3 + 0), z));
+                        const float y = __fadd_rn(__ldg(p.rays_o + ray * 3 + 1), __fmul_rn(__ldg(p.rays_d + ray * 3 + 1), z));
+                        const float zz = __fadd_rn(__ldg(p.rays_o + ray * 3 + 2), __fmul_rn(__ldg(p.rays_d + ray * 3 + 2), z));
+                        px = __fadd_rn(__fdiv_rn(__fsub_rn(x, __ldg(p.centres + (size_t)vox * 3 + 0)), p.voxel_size), 0.5f);
+                        py = __fadd_rn(__fdiv_rn(__fsub_rn(y, __ldg(p.centres + (size_t)vox * 3 + 1)), p.voxel_size), 0.5f);
+                        pz = __fadd_rn(__fdiv_rn(__fsub_rn(zz, __ldg(p.centres + (size_t)vox * 3 + 2)), p.voxel_size), 0.5f);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int row = __ldg(p.vertex_idx + (size_t)vox * 8 + i);
+                            const float wx = (i & 4) ? px : 1.0f - px, wy = (i & 2) ? py : 1.0f - py, wz = (i & 1) ? pz : 1.0f - pz;
+                            const float w = (wx * wy) * wz;
+                            const float4 *er = reinterpret_cast<const float4 *>(p.emb + (size_t)row * 16);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float4 v = __ldg(er + e);
+                                f[4 * e] = fmaf(w, v.x, f[4 * e]); f[4 * e + 1] = fmaf(w, v.y, f[4 * e + 1]);
+                                f[4 * e + 2] = fmaf(w, v.z, f[4 * e + 2]); f[4 * e + 3] = fmaf(w, v.w, f[4 * e + 3]);
+                            }
+                        }
+                    }
+                }
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) bf16_split2(f[2 * e], f[2 * e + 1], hi[e], lo[e]);
+                tmem_st8(trow + cAHI + 64, hi);
+                tmem_st8(trow + cALO + 64, lo);
+                if (scr) {
+                    unsigned char *dst = scr + oF + rowoff_small;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        *reinterpret_cast<uint4 *>(dst + j * 128) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                        *reinterpret_cast<uint4 *>(dst + 2048 + j * 128) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                    }
+                }
+            }
+            a_is_ready();
+            uint32_t m1[2], m2[2], mc[2];
+            // ---- forward ----
+            layer_done();
+            bf_epilogue64<0>(trow, col0, sBias, m1, stage_begin());                                     // h1
+            stage_end();
+            a_is_ready();
+            layer_done();
+            bf_epilogue64<0>(trow, col0, sBias + 128, m2, stage_begin());                               // h2
+            stage_end();
+            a_is_ready();
+            layer_done();
+            bf_epilogue64<1>(trow, col0, sBias + 256, nomask, stage_begin());                           // t (no activation)
+            stage_end();
+            float sdf = 0.0f;
+            if (lead) {
+                uint32_t v[8];
+                tmem_ld8(trow + cD + 128, v);   // sdf = row 0 of W3, packed as output column 128
+                tmem_wait_ld();
+                sdf = __uint_as_float(v[0]) + sBias[512];
+            }
+            a_is_ready();
+            layer_done();
+            bf_epilogue64<0>(trow, col0, sBias + 384, mc, stage_begin());                               // hc
+            stage_end();
+            a_is_ready();
+            layer_done();
+            float r = 0.f, g = 0.f, b = 0.f;
+            if (lead) {
+                uint32_t v[8];
+                tmem_ld8(trow + cD, v);
+                tmem_wait_ld();
+                r = sigmoid_f(__uint_as_float(v[0]) + sBias[513]);
+                g = sigmoid_f(__uint_as_float(v[1]) + sBias[514]);
+                b = sigmoid_f(__uint_as_float(v[2]) + sBias[515]);
+            }
+            if (!BWD) {
+                if (lead && s < nsamp) *reinterpret_cast<float4 *>(p.out + (size_t)s * 4) = make_float4(r, g, b, sdf);
+                continue;   // D has been read; the next tile's first MMA is ordered behind it through a_ready
+            }
+            // ---- backward ----
+            float4 go = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lead) {
+                if (s < nsamp) go = __ldg(reinterpret_cast<const float4 *>(p.g_out + (size_t)s * 4));
+                // dL/d(pre-sigmoid rgb): grad * (1 - y) * y ; A[:, 0:16) = [g5 r,g,b, 0...]
+                const float g5[4] = {go.x * (1.0f - r) * r, go.y * (1.0f - g) * g, go.z * (1.0f - b) * b, go.w};
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { hi[e] = 0u; lo[e] = 0u; }
+                bf16_split2(g5[0], g5[1], hi[0], lo[0]);
+                bf16_split2(g5[2], 0.0f, hi[1], lo[1]);
+                tmem_st8(trow + cAHI, hi);
+                tmem_st8(trow + cALO, lo);
+                if (scr) {
+                    // wgrad operand G5 = (g5 r, g, b, g_sdf, 0 ...)
+                    uint32_t h1w, l1w;
+                    bf16_split2(g5[2], g5[3], h1w, l1w);
+                    unsigned char *dst = scr + oG5 + rowoff_small;
+                    *reinterpret_cast<uint4 *>(dst) = make_uint4(hi[0], h1w, 0u, 0u);
+                    *reinterpret_cast<uint4 *>(dst + 128) = make_uint4(0u, 0u, 0u, 0u);
+                    *reinterpret_cast<uint4 *>(dst + 2048) = make_uint4(lo[0], l1w, 0u, 0u);
+                    *reinterpret_cast<uint4 *>(dst + 2048 + 128) = make_uint4(0u, 0u, 0u, 0u);
+                    // bias gradients of the two heads: column sums of G5 (k_wgrad_bf takes the others on the tensor cores)
+                    const float s0 = warp_sum(g5[0]), s1 = warp_sum(g5[1]), s2 = warp_sum(g5[2]), s3 = warp_sum(g5[3]);
+                    if (lane == 0) {
+                        atomicAdd(p.g_dec.b5 + 0, s0); atomicAdd(p.g_dec.b5 + 1, s1); atomicAdd(p.g_dec.b5 + 2, s2);
+                        atomicAdd(p.g_dec.b3, s3);
+                    }
+                }
+            }
+            a_is_ready();
+            layer_done();
+            bf_epilogue64<2>(trow, col0, nullptr, mc, stage_begin());                                   // g_hc
+            stage_end();
+            a_is_ready();
+            layer_done();
+            bf_epilogue64<3>(trow, col0, nullptr, nomask, stage_begin());                               // g_t
+            stage_end();
+            float gf[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) gf[e] = 0.0f;
+            if (lead) {
+                uint32_t v[16], hi[8], lo[8];
+                tmem_ld16(trow + cD + 128, v);   // g_f, part through W4's last 16 input columns
+                tmem_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 16; ++e) gf[e] = __uint_as_float(v[e]);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { hi[e] = 0u; lo[e] = 0u; }
+                bf16_split2(go.w, 0.0f, hi[0], lo[0]);  // A[:, 128] = g_sdf pairs with W3 row 0 (packed at k = 128)
+                tmem_st8(trow + cAHI + 64, hi);
+                tmem_st8(trow + cALO + 64, lo);
+            }
+            a_is_ready();
+            layer_done();
+            bf_epilogue64<2>(trow, col0, nullptr, m2, stage_begin());                                   // g_h2
+            stage_end();
+            a_is_ready();
+            layer_done();
+            bf_epilogue64<2>(trow, col0, nullptr, m1, stage_begin());                                   // g_h1
+            stage_end();
+            a_is_ready();
+            layer_done();
+            if (!lead) continue;
+            {
+                uint32_t v[16];
+                tmem_ld16(trow + cD, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 16; ++e) gf[e] += __uint_as_float(v[e]);
+            }
+            if (s >= nsamp) continue;
+            if (p.g_feat) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<float4 *>(p.g_feat + (size_t)s * 16 + 4 * j) = make_float4(gf[4 * j], gf[4 * j + 1], gf[4 * j + 2], gf[4 * j + 3]);
+            }
+            if (!p.feat && (p.grad_emb || p.grad_rays)) {
+                // trilinear backward of this sample
+                float gp[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = __ldg(p.vertex_idx + (size_t)vox * 8 + i);
+                    const float wx = (i & 4) ? px : 1.0f - px, wy = (i & 2) ? py : 1.0f - py, wz = (i & 1) ? pz : 1.0f - pz;
+                    const float w = (wx * wy) * wz;
+                    if (p.grad_emb) {
+                        float *dst = p.g_emb + (size_t)row * 16;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) red_add_v4(dst + 4 * e, w * gf[4 * e], w * gf[4 * e + 1], w * gf[4 * e + 2], w * gf[4 * e + 3]);
+                    }
+                    if (p.grad_rays) {
+                        const float4 *er = reinterpret_cast<const float4 *>(p.emb + (size_t)row * 16);
+                        float d = 0.0f;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float4 v = __ldg(er + e);
+                            d = fmaf(gf[4 * e], v.x, d); d = fmaf(gf[4 * e + 1], v.y, d);
+                            d = fmaf(gf[4 * e + 2], v.z, d); d = fmaf(gf[4 * e + 3], v.w, d);
+                        }
+                        gp[0] += d * ((i & 4) ? 1.0f : -1.0f) * (wy * wz);
+                        gp[1] += d * ((i & 2) ? 1.0f : -1.0f) * (wx * wz);
+                        gp[2] += d * ((i & 1) ? 1.0f : -1.0f) * (wx * wy);
+                    }
+                }
+                if (p.grad_rays) {
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        const float gx = gp[a] / p.voxel_size;
+                        atomicAdd(p.g_rays_o + ray * 3 + a, gx);
+                        atomicAdd(p.g_rays_d + ray * 3 + a, z * gx);
+                    }
+                }
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    cluster_sync();   // no CTA leaves while a peer may still multicast into its shared memory or signal its barriers
+    if (warp == 0) tmem_dealloc(tmem, bf::kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------
+// Weight gradients: dW[n][k] = sum over samples of G[p][n] * A[p][k] -- MMAs whose reduction dimension is
+// the SAMPLE index.  The scratch holds every operand already split and in the MN-major core-matrix layout,
+// so a stage is 2 (+2 small) bulk-TMA copies and the MMAs read them in place (A and B both MN-major from
+// shared memory).  Accumulators stay in tensor memory for ALL tiles of the CTA (512 of 512 columns):
+//   [0,128) dW2 = G2^T H1    [128,256) dW3 rows 1.. = G3^T H2    [256,384) dW4[:, :128] = G4^T T
+//   [384,400) dW4[:, 128:] = G4^T F    [400,416) dW1 = G1^T F    [416,432) HC^T G5 (cols 0..2 = dW5 rows)
+//   [432,448) H2^T G5 (col 3 = dW3 row 0)    [448,512) column sums of G2, G3, G4, G1 (x ones: bias gradients)
+// Steps per (tile, 64-sample half): 0: (G2, H1)   1: (G3, H2) + G5   2: (G4, T) + F   3: (G1, HC) + F + G5
+// ------------------------------------------------------------------------------------------
+namespace wgb {
+constexpr int kThreads = 192;                   // warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 drain
+constexpr int kStages = 3;
+constexpr int kHalfBytes = 32768;               // (128-feature operand, 64-sample half): [plane 2][kb 8][fb 16][128 B]
+constexpr int kSmallHalf = 4096;                // (16-feature operand, half):           [plane 2][kb 8][fb 2][128 B]
+constexpr int oB = kHalfBytes, oFs = 2 * kHalfBytes, oG5s = oFs + kSmallHalf;
+constexpr int kStageBytes = oG5s + kSmallHalf;  // 73 728
+constexpr int oOnes = kStages * kStageBytes;    // 16 samples x 16 features of bf16 1.0: [kb 2][fb 2][128 B]
+constexpr int oBars = oOnes + 512;              // full[3] free[3] all_done, tmem ptr
+constexpr int kSmemBytes = oBars + 128;
+struct Step { int a_op, b_op, use_f, use_g5; };
+__device__ __constant__ Step cSteps[4] = {
+    {bf::oG2, bf::oH1, 0, 0}, {bf::oG3, bf::oH2, 0, 1}, {bf::oG4, bf::oT, 1, 0}, {bf::oG1, bf::oHC, 1, 1}};
+}  // namespace wgb
+
+#define WGB_TRACE(g, slot)                                                                          \
+    do {                                                                                            \
+        if (g_bf_trace && blockIdx.x == 0 && (g) < 40) g_bf_trace[320 + (g) * 8 + (slot)] = clock64();     \
+    } while (0)
+
+__global__ void __launch_bounds__(wgb::kThreads, 1) k_wgrad_bf(FieldParams p)
+{
+    using namespace wgb;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + oBars);
+    uint64_t *freeb = full + kStages, *all_done = freeb + kStages;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(smem + oBars + 64);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nsamp = p.nsamp_dev ? *p.nsamp_dev : p.nsamp;
+    const int ntiles = (nsamp + 127) / 128;
+    if (tid == 0) {
+        for (int i = 0; i < kStages; ++i) { mbar_init(full + i, 1); mbar_init(freeb + i, 1); }
+        mbar_init(all_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, 512);
+    for (int i = tid; i < 128; i += kThreads) reinterpret_cast<uint32_t *>(smem + oOnes)[i] = 0x3F803F80u;   // bf16 1.0 pairs
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = *tmem_ptr;
+    const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int nsteps = my_tiles * 8;   // 2 halves x 4 steps
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        for (int g = 0; g < nsteps; ++g) {
+            const int tl = g >> 3, h = (g >> 2) & 1, st = g & 3, rs = g % kStages, use = g / kStages;
+            const Step S = cSteps[st];
+            const unsigned char *tile = p.wg_scratch + (size_t)(blockIdx.x + (size_t)tl * gridDim.x) * bf::kTileBytes;
+            if (use >= 1) mbar_wait(freeb + rs, (use - 1) & 1);
+            if (lane == 0) WGB_TRACE(g, 0);
+            if (elect_one()) {
+                unsigned char *dst = smem + rs * kStageBytes;
+                mbar_arrive_expect_tx(full + rs, (uint32_t)(2 * kHalfBytes + (S.use_f + S.use_g5) * kSmallHalf));
+                bulk_g2s(dst, tile + (size_t)S.a_op * bf::kOpBytes + (size_t)h * kHalfBytes, kHalfBytes, full + rs);
+                bulk_g2s(dst + oB, tile + (size_t)S.b_op * bf::kOpBytes + (size_t)h * kHalfBytes, kHalfBytes, full + rs);
+                if (S.use_f) bulk_g2s(dst + oFs, tile + bf::oF + (size_t)h * kSmallHalf, kSmallHalf, full + rs);
+                if (S.use_g5) bulk_g2s(dst + oG5s, tile + bf::oG5 + (size_t)h * kSmallHalf, kSmallHalf, full + rs);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t id128 = idesc_bf16(128, 128, 1, 1), id16 = idesc_bf16(128, 16, 1, 1);
+        const uint64_t ones = sdesc(smem_u32(smem + oOnes), 256, 128);
+        for (int g = 0; g < nsteps; ++g) {
+            const int st = g & 3, rs = g % kStages;
+            mbar_wait(full + rs, (g / kStages) & 1);
+            fence_after_sync();
+            if (lane == 0) WGB_TRACE(g, 4);
+            const uint32_t base = smem_u32(smem + rs * kStageBytes);
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {            // 16 samples = 2 kb blocks per MMA
+                    const uint32_t fresh = (g < 8 && (g >> 2) == 0 && ks == 0) ? 0u : 1u;   // first touch of this step's accumulators
+                    const uint64_t a_hi = sdesc(base + ks * 4096, 2048, 128), a_lo = sdesc(base + 16384 + ks * 4096, 2048, 128);
+                    const uint64_t b_hi = sdesc(base + oB + ks * 4096, 2048, 128), b_lo = sdesc(base + oB + 16384 + ks * 4096, 2048, 128);
+                    const uint64_t f_hi = sdesc(base + oFs + ks * 512, 256, 128), f_lo = sdesc(base + oFs + 2048 + ks * 512, 256, 128);
+                    const uint64_t g_hi = sdesc(base + oG5s + ks * 512, 256, 128), g_lo = sdesc(base + oG5s + 2048 + ks * 512, 256, 128);
+                    auto prod3 = [&](uint32_t dcol, uint64_t xh, uint64_t xl, uint64_t yh, uint64_t yl, uint32_t idesc) {
+                        mma_bf16_ss(tmem + dcol, xl, yh, idesc, fresh);
+                        mma_bf16_ss(tmem + dcol, xh, yl, idesc, 1u);
+                        mma_bf16_ss(tmem + dcol, xh, yh, idesc, 1u);
+                    };
+                    auto colsum = [&](uint32_t dcol, uint64_t xh, uint64_t xl) {
+                        mma_bf16_ss(tmem + dcol, xh, ones, id16, fresh);
+                        mma_bf16_ss(tmem + dcol, xl, ones, id16, 1u);
+                    };
+                    if (st == 0) {
+                        prod3(0, a_hi, a_lo, b_hi, b_lo, id128);            // dW2 = G2^T H1
+                        colsum(448, a_hi, a_lo);                            // db2
+                    } else if (st == 1) {
+                        prod3(128, a_hi, a_lo, b_hi, b_lo, id128);          // dW3[1..] = G3^T H2
+                        prod3(432, b_hi, b_lo, g_hi, g_lo, id16);           // H2^T G5 (col 3 -> dW3[0])
+                        colsum(464, a_hi, a_lo);                            // db3[1..]
+                    } else if (st == 2) {
+                        prod3(256, a_hi, a_lo, b_hi, b_lo, id128);          // dW4[:, :128] = G4^T T
+                        prod3(384, a_hi, a_lo, f_hi, f_lo, id16);           // dW4[:, 128:] = G4^T F
+                        colsum(480, a_hi, a_lo);                            // db4
+                    } else {
+                        prod3(400, a_hi, a_lo, f_hi, f_lo, id16);           // dW1 = G1^T F
+                        prod3(416, b_hi, b_lo, g_hi, g_lo, id16);           // HC^T G5 (cols 0..2 -> dW5)
+                        colsum(496, a_hi, a_lo);                            // db1
+                    }
+                }
+                mma_commit(freeb + rs);
+                if (g == nsteps - 1) mma_commit(all_done);
+            }
+            __syncwarp();
+            if (lane == 0) WGB_TRACE(g, 5);
+        }
+    } else if (nsteps > 0) {
+        // ===================== drain: accumulators -> global gradients (warp & 3 = TMEM lane quarter) =====================
+        mbar_wait(all_done, 0);
+        fence_after_sync();
+        const int qd = warp & 3;
+        const int n = qd * 32 + lane;                            // accumulator row = TMEM lane
+        const uint32_t trow = tmem + ((uint32_t)(qd * 32) << 16);
+        auto flush = [&](int col0, int ncols, float *dst_row) {   // dst_row: &dW[n][0], ncols % 16 == 0
+            for (int c0 = 0; c0 < ncols; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(trow + col0 + c0, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    red_add_v4(dst_row + c0 + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                               __uint_as_float(v[4 * j + 3]));
+            }
+        };
+        flush(0, 128, p.g_dec.W2 + (size_t)n * 128);
+        flush(128, 128, p.g_dec.W3 + (size_t)(1 + n) * 128);
+        flush(256, 128, p.g_dec.W4 + (size_t)n * 144);
+        flush(384, 16, p.g_dec.W4 + (size_t)n * 144 + 128);
+        flush(400, 16, p.g_dec.W1 + (size_t)n * 16);
+        {
+            uint32_t v[8], w[8], bs[8];
+            tmem_ld8(trow + 416, v);
+            tmem_ld8(trow + 432, w);
+            tmem_wait_ld();
+            atomicAdd(p.g_dec.W5 + n, __uint_as_float(v[0]));
+            atomicAdd(p.g_dec.W5 + 128 + n, __uint_as_float(v[1]));
+            atomicAdd(p.g_dec.W5 + 256 + n, __uint_as_float(v[2]));
+            atomicAdd(p.g_dec.W3 + n, __uint_as_float(w[3]));
+            tmem_ld8(trow + 448, bs); tmem_wait_ld(); atomicAdd(p.g_dec.b2 + n, __uint_as_float(bs[0]));
+            tmem_ld8(trow + 464, bs); tmem_wait_ld(); atomicAdd(p.g_dec.b3 + 1 + n, __uint_as_float(bs[0]));
+            tmem_ld8(trow + 480, bs); tmem_wait_ld(); atomicAdd(p.g_dec.b4 + n, __uint_as_float(bs[0]));
+            tmem_ld8(trow + 496, bs); tmem_wait_ld(); atomicAdd(p.g_dec.b1 + n, __uint_as_float(bs[0]));
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------
+// stand-alone GEMMs through the same primitives (unit tests of descriptors / TMEM packing), 3xBF16.
+// mode 0: D[128,N] = A[128,K] * B[N,K]^T, A packed in tensor memory, B K-major in shared memory (the chain form)
+// mode 1: D[128,N] = At[K,128]^T * Bt[K,N], both operands MN-major in shared memory (the wgrad form)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) k_debug_umma_bf(const float *__restrict__ A, const float *__restrict__ B, float *__restrict__ D,
+                                                          int N, int K, int mode)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_ptr;
+    uint16_t *s16 = reinterpret_cast<uint16_t *>(smem);
+    const int warp = threadIdx.x >> 5, m = threadIdx.x;
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(&tmem_ptr, 512);
+    const int nkb = K / 8;
+    const int planeA = nkb * 16 * 64, planeB = nkb * (N / 8) * 64;   // uint16 elements of one MN-major plane
+    if (mode == 0) {
+        // B -> per 16-k step: [hi: 2 k-chunks x N rows x 8][lo: same]
+        for (int i = threadIdx.x; i < N * K; i += 128) {
+            const int n = i / K, k = i % K, st = k >> 4, kc = (k >> 3) & 1, e = k & 7;
+            uint32_t hi, lo;
+            bf16_split2(B[i], 0.0f, hi, lo);
+            uint16_t *blk = s16 + st * (2 * N * 16);
+            blk[kc * N * 8 + n * 8 + e] = (uint16_t)hi;
+            blk[N * 16 + kc * N * 8 + n * 8 + e] = (uint16_t)lo;
+        }
+    } else {
+        // At [K][128] -> A planes [kb][fb 16][8 samples][8 features]; Bt [K][N] -> B planes [kb][fb N/8][8][8]
+        for (int i = threadIdx.x; i < K * (128 + N); i += 128) {
+            const bool isA = i < K * 128;
+            const int j = isA ? i : i - K * 128, F = isA ? 128 : N;
+            const int k = j / F, f = j % F;
+            uint32_t hi, lo;
+            bf16_split2(isA ? A[j] : B[j], 0.0f, hi, lo);
+            uint16_t *pl = s16 + (isA ? 0 : 2 * planeA);
+            const int off = (k >> 3) * (F / 8) * 64 + (f >> 3) * 64 + (k & 7) * 8 + (f & 7);
+            pl[off] = (uint16_t)hi;
+            pl[(isA ? planeA : planeB) + off] = (uint16_t)lo;
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = tmem_ptr;
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    if (mode == 0) {
+        for (int k0 = 0; k0 < K; k0 += 16) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) bf16_split2(A[(size_t)m * K + k0 + 2 * e], A[(size_t)m * K + k0 + 2 * e + 1], hi[e], lo[e]);
+            tmem_st8(trow + k0 / 2, hi);
+            tmem_st8(trow + 72 + k0 / 2, lo);
+        }
+        tmem_wait_st();
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        fence_after_sync();
+        const uint32_t sb = smem_u32(smem);
+        if (mode == 0) {
+            const uint32_t id_lh = idesc_bf16(128, N), id_hl = id_lh, id_hh = id_lh;
+            for (int st = 0; st < K / 16; ++st) {
+                const uint64_t b_hi = sdesc(sb + st * (2 * N * 16 * 2), N * 16, 128);
+                const uint64_t b_lo = sdesc(sb + st * (2 * N * 16 * 2) + N * 16 * 2, N * 16, 128);
+                mma_bf16_ts(tmem + 144, tmem + 72 + st * 8, b_hi, id_lh, st ? 1u : 0u);
+                mma_bf16_ts(tmem + 144, tmem + st * 8, b_lo, id_hl, 1u);
+                mma_bf16_ts(tmem + 144, tmem + st * 8, b_hi, id_hh, 1u);
+            }
+        } else {
+            const uint32_t id_lh = idesc_bf16(128, N, 1, 1), id_hl = id_lh, id_hh = id_lh;
+            const uint32_t lboA = 16 * 128, lboB = (N / 8) * 128;
+            const uint32_t a_hi = sb, a_lo = sb + planeA * 2, b_hi = sb + planeA * 4, b_lo = b_hi + planeB * 2;
+            for (int st = 0; st < K / 16; ++st) {
+                mma_bf16_ss(tmem + 144, sdesc(a_lo + st * 2 * lboA, lboA, 128), sdesc(b_hi + st * 2 * lboB, lboB, 128), id_lh, st ? 1u : 0u);
+                mma_bf16_ss(tmem + 144, sdesc(a_hi + st * 2 * lboA, lboA, 128), sdesc(b_lo + st * 2 * lboB, lboB, 128), id_hl, 1u);
+                mma_bf16_ss(tmem + 144, sdesc(a_hi + st * 2 * lboA, lboA, 128), sdesc(b_hi + st * 2 * lboB, lboB, 128), id_hh, 1u);
+            }
+        }
+        mma_commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    fence_after_sync();
+    for (int c0 = 0; c0 < N; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(trow + 144 + c0, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) D[(size_t)m * N + c0 + e] = __uint_as_float(v[e]);
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------
+int bf_pack_decoder(const pslam_decoder_t &d, float *ws_tc, cudaStream_t st)
+{
+    int total = 0;
+    for (int l = 0; l < declayers::kLayersAll; ++l) total += declayers::hN[l] * declayers::hK[l];
+    k_bf_pack<<<ceil_div(total, 256), 256, 0, st>>>(d, reinterpret_cast<uint16_t *>(ws_tc));
+    PSLAM_CHECK_LAUNCH("bf_pack");
+    return 0;
+}
+
+size_t bf_wgrad_scratch_bytes(int max_samples) { return (size_t)ceil_div(max_samples > 0 ? max_samples : 1, 128) * bf::kTileBytes; }
+
+template <bool BWD>
+static int launch_bf(const FieldParams &fp, int max_samples, cudaStream_t st)
+{
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_field_bf<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, bf::Smem<BWD>::bytes);
+        if (e != cudaSuccess) { set_error("field_bf: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+        configured = true;
+    }
+    // persistent grid = as many whole clusters as can be resident at once (GPC boundaries may strand a few SMs)
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(num_sms() / bf::kCluster * bf::kCluster);
+        cfg.blockDim = dim3(bf::kThreads);
+        cfg.dynamicSmemBytes = bf::Smem<BWD>::bytes;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = bf::kCluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        int n = 0;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&n, k_field_bf<BWD>, &cfg);
+        if (e != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = num_sms() / bf::kCluster; }
+        max_clusters = n < num_sms() / bf::kCluster ? n : num_sms() / bf::kCluster;
+    }
+    const int tiles = ceil_div(max_samples, 128);
+    int grid = ceil_div(tiles > 0 ? tiles : 1, bf::kCluster) * bf::kCluster;
+    if (grid > max_clusters * bf::kCluster) grid = max_clusters * bf::kCluster;
+    k_field_bf<BWD><<<grid, bf::kThreads, bf::Smem<BWD>::bytes, st>>>(fp, reinterpret_cast<const unsigned char *>(fp.ws_tc));
+    PSLAM_CHECK_LAUNCH(BWD ? "field_bf_backward" : "field_bf_forward");
+    return 0;
+}
+
+int bf_launch_field_forward(const FieldParams &fp, int max_samples, cudaStream_t st) { return launch_bf<false>(fp, max_samples, st); }
+
+// backward: dgrad chain (+ trilinear backward); when decoder gradients are wanted the scratch must be
+// provided and the wgrad kernel follows on the same stream
+int bf_launch_field_backward(const FieldParams &fp_in, int max_samples, cudaStream_t st, int part)
+{
+    FieldParams fp = fp_in;
+    if (!fp.grad_dec) fp.wg_scratch = nullptr;
+    if (part != 2)
+        if (int rc = launch_bf<true>(fp, max_samples, st)) return rc;
+    if (!fp.grad_dec || part == 1) return 0;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_wgrad_bf, cudaFuncAttributeMaxDynamicSharedMemorySize, wgb::kSmemBytes);
+        if (e != cudaSuccess) { set_error("wgrad_bf: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+        configured = true;
+    }
+    const int tiles = ceil_div(max_samples, 128);
+    const int grid = tiles < num_sms() ? (tiles > 0 ? tiles : 1) : num_sms();
+    k_wgrad_bf<<<grid, wgb::kThreads, wgb::kSmemBytes, st>>>(fp);
+    PSLAM_CHECK_LAUNCH("wgrad_bf");
+    return 0;
+}
+
+}  // namespace pslam
+
+using namespace pslam;
+
+extern "C" int pslam_debug_bf_trace(long long *dev_buf)
+{
+    cudaError_t e = cudaMemcpyToSymbol(g_bf_trace, &dev_buf, sizeof(dev_buf));
+    if (e != cudaSuccess) { set_error("bf_trace: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+
+extern "C" int pslam_debug_umma_gemm_bf(const float *A, const float *B, float *D, int N, int K, int mode, pslam_stream_t stream)
+{
+    PSLAM_CHECK_ARG(A && B && D, PSLAM_E_ARG, "null pointer");
+    PSLAM_CHECK_ARG(N >= 16 && N <= 144 && N % 16 == 0 && K >= 16 && K <= 144 && K % 16 == 0, PSLAM_E_RANGE, "N in 16..144 step 16, K in 16..144 step 16");
+    PSLAM_CHECK_ARG(mode == 0 || mode == 1, PSLAM_E_RANGE, "mode must be 0 or 1");
+    const int smem = mode == 1 ? (128 + N) * K * 4 : N * K * 4;
+    cudaError_t e = cudaFuncSetAttribute(k_debug_umma_bf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_error("debug_umma_bf: %s", cudaGetErrorString(e)); return (int)e; }
+    k_debug_umma_bf<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, N, K, mode);
+    PSLAM_CHECK_LAUNCH("debug_umma_gemm_bf");
+    return 0;
+}

@@ -25,6 +25,7 @@
 #include "field.cuh"
 #include "kernels.h"
 #include "umma.cuh"
+#include "decoder_layers.cuh"
 
 namespace pslam {
 
@@ -65,24 +66,6 @@ constexpr size_t kSliceBytes = (size_t)kGroups * 512;
 constexpr size_t kTileBytes = 4 * kSliceBytes;
 }  // namespace tc
 
-// source element of layer l at (output row n, reduction index k)
-__device__ __forceinline__ float tc_weight(const pslam_decoder_t &d, int l, int n, int k)
-{
-    switch (l) {
-        case 0: return d.W1[n * 16 + k];
-        case 1: return d.W2[n * 128 + k];
-        case 2: return n < 128 ? d.W3[(1 + n) * 128 + k] : (n == 128 ? d.W3[k] : 0.0f);   // features first, sdf row at 128
-        case 3: return d.W4[n * 144 + k];                                                  // k over [t(128); f(16)]
-        case 4: return n < 3 ? d.W5[n * 128 + k] : 0.0f;
-        // dgrad: B[n][k] = W[k][n] (reduction over the layer's outputs)
-        case 5: return k < 3 ? d.W5[k * 128 + n] : 0.0f;                                   // g_hc[n] = sum_c g5[c] W5[c][n]
-        case 6: return d.W4[k * 144 + n];                                                  // [g_t; g_f][n] = sum_k g_hc[k] W4[k][n]
-        case 7: return k < 128 ? d.W3[(1 + k) * 128 + n] : (k == 128 ? d.W3[n] : 0.0f);    // g_h2[n] = sum_j g_o3[j] W3[j][n]
-        case 8: return d.W2[k * 128 + n];
-        default: return d.W1[k * 16 + n];                                                  // g_f[n] = sum_k g_h1[k] W1[k][n]
-    }
-}
-
 // Re-packs the decoder into the weight stream: layers in order, each as K/16 chunks of
 // [hi block | lo block], each block = 4 k-chunks x N rows x 16 B (see umma.cuh).
 __global__ void k_tc_pack(pslam_decoder_t d, float *__restrict__ out)
@@ -107,8 +90,6 @@ __global__ void k_tc_pack(pslam_decoder_t d, float *__restrict__ out)
         base += 2 * N * K;
     }
 }
-
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // One epilogue over this thread's 64 accumulator columns [col0, col0+64): accumulators -> registers ->
 // (bias / activation / mask) -> next A operand (hi/lo split, tensor memory) and optionally the wgrad
