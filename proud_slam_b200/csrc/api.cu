@@ -115,7 +115,7 @@ extern "C" int pslam_device_info(int *out3)
 
 extern "C" int64_t pslam_render_scratch_i_count(int R)
 {
-    return ((int64_t)ceil_div(R, 64) + 8) + ((int64_t)ceil_div(R, 128) + 8) + 8 * (int64_t)ceil_div(R, 8) + 64;
+    return (int64_t)scratch_i_composite_off(R) + 8 * (int64_t)ceil_div(R, 8) + 64;
 }
 extern "C" int64_t pslam_render_scratch_f_count(int R) { return 8 * (int64_t)ceil_div(R, 8) + 64; }
 

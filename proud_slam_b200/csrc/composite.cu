@@ -377,7 +377,7 @@ int launch_composite_forward(const pslam_render_t *p, cudaStream_t st)
 {
     const int nb = ceil_div(p->R, kCompWarps);
     float *part_f = p->scratch_f;                                // [nb,8]
-    int *part_i = p->scratch_i + (ceil_div(p->R, 64) + 8) + (ceil_div(p->R, 128) + 8);  // after the two scan-partial arrays: [nb,8]
+    int *part_i = p->scratch_i + scratch_i_composite_off(p->R);  // after the two scan-partial arrays: [nb,8]
     k_composite_fwd<<<nb, kCompThreads, 0, st>>>(*p, part_f, part_i);
     PSLAM_CHECK_LAUNCH("composite_fwd");
     if (p->target_depth && p->target_rgb) {

@@ -6,6 +6,10 @@
 
 namespace pslam {
 
+// scratch_i layout: [intersect block hits: R/64 + 8][sample block counts: R/64 + 8][composite partials: 8 x R/8 + 64]
+static inline int scratch_i_sample_off(int R) { return (R + 63) / 64 + 8; }
+static inline int scratch_i_composite_off(int R) { return 2 * ((R + 63) / 64 + 8); }
+
 // intersect.cu
 int scan_partials(int *partials, int nb, int *total_out, cudaStream_t st);
 int launch_intersect_fused(const pslam_render_t *p, cudaStream_t st);

@@ -22,7 +22,7 @@
 
 namespace pslam {
 
-constexpr int kSampleThreads = 128;
+constexpr int kSampleThreads = 64;    // fused path: one ray per thread, 2 warps per block so that 8192 rays cover 128 SMs
 constexpr int kGroups = 200;      // voxel_helpers.py:300
 constexpr int kChunkRays = 800;   // voxel_helpers.py:331 (4*G)
 
@@ -89,7 +89,7 @@ struct PaddedSink {
     }
 };
 
-__global__ void __launch_bounds__(kSampleThreads)
+__global__ void __launch_bounds__(128)
 k_inverse_cdf_ref(int b, int num_rays, int P, int max_steps, float fixed_step_size, const int *__restrict__ pts_idx,
                   const float *__restrict__ min_depth, const float *__restrict__ max_depth,
                   const float *__restrict__ noise, const float *__restrict__ probs, const float *__restrict__ steps,
@@ -115,6 +115,9 @@ struct FusedHits {
     const int *hit_idx; const float *hit_min, *hit_max; const int *hit_count, *hit_ray;
     int R, Rh, P, chunk_base_rank;  // rank of (g, 800c + 0)
     int own_j, own_r, own_cnt;      // this thread's ray: every (j, bin) access of the sampling loop is to it
+    // ... and its hit list is staged in shared memory ([slot][thread], conflict-free): the loop's bin changes happen at
+    // different steps in different lanes, so from global memory every one of them was a serialised L2 round trip
+    const int *s_idx; const float *s_min, *s_max;
     float total;                    // sum of this ray's segment lengths
     float max_distance;             // value the reference reads in padded slots (voxel_helpers.py:579-580)
     __device__ __forceinline__ int ray_of(int j) const
@@ -128,15 +131,15 @@ struct FusedHits {
         return (b < __ldg(hit_count + r)) ? __ldg(hit_idx + (int64_t)b * R + r) : -1;
     }
     // own ray: one load instead of three dependent ones (rank -> ray -> count -> slot)
-    __device__ __forceinline__ int idx(int, int b) const { return (b < own_cnt) ? __ldg(hit_idx + (int64_t)b * R + own_r) : -1; }
+    __device__ __forceinline__ int idx(int, int b) const { return (b < own_cnt) ? s_idx[b * kSampleThreads] : -1; }
     // the tail loop's flat index may land on another ray of the chunk (SURVEY A-Q7)
     __device__ __forceinline__ int flat_idx(int f) const
     {
         const int j = f / P;
         return j == own_j ? idx(j, f % P) : idx_r(ray_of(j), f % P);
     }
-    __device__ __forceinline__ float tmin(int, int b) const { return (b < own_cnt) ? __ldg(hit_min + (int64_t)b * R + own_r) : max_distance; }
-    __device__ __forceinline__ float tmax(int, int b) const { return (b < own_cnt) ? __ldg(hit_max + (int64_t)b * R + own_r) : max_distance; }
+    __device__ __forceinline__ float tmin(int, int b) const { return (b < own_cnt) ? s_min[b * kSampleThreads] : max_distance; }
+    __device__ __forceinline__ float tmax(int, int b) const { return (b < own_cnt) ? s_max[b * kSampleThreads] : max_distance; }
     __device__ __forceinline__ float prob(int j, int b) const
     {
         return __fdiv_rn(__fsub_rn(tmax(j, b), tmin(j, b)), total);  // voxel_helpers.py:639-643
@@ -179,6 +182,10 @@ template <bool WRITE>
 __global__ void __launch_bounds__(kSampleThreads)
 k_sample_fused(pslam_render_t p, int *__restrict__ block_counts)
 {
+    extern __shared__ __align__(16) unsigned char s_hits[];   // [3][n_max][kSampleThreads]: idx, min, max of this block's rays
+    int *s_idx = reinterpret_cast<int *>(s_hits) + threadIdx.x;
+    float *s_min = reinterpret_cast<float *>(s_hits) + (size_t)p.n_max * kSampleThreads + threadIdx.x;
+    float *s_max = s_min + (size_t)p.n_max * kSampleThreads;
     const int Rh = p.counters[PSLAM_C_RH];
     const int P = p.counters[PSLAM_C_P];
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -189,11 +196,15 @@ k_sample_fused(pslam_render_t p, int *__restrict__ block_counts)
         const int c = jf / kChunkRays, j = jf % kChunkRays;
         const int nc = min(kChunkRays, n - c * kChunkRays);
         const int r = __ldg(p.hit_ray + q);
-        const int cnt = __ldg(p.hit_count + r);
+        const int cnt = min(__ldg(p.hit_count + r), p.n_max);
+        for (int b = 0; b < cnt; ++b) {      // independent loads, coalesced over the rays of a warp where ranks are consecutive
+            s_idx[b * kSampleThreads] = __ldg(p.hit_idx + (int64_t)b * p.R + r);
+            s_min[b * kSampleThreads] = __ldg(p.hit_min + (int64_t)b * p.R + r);
+            s_max[b * kSampleThreads] = __ldg(p.hit_max + (int64_t)b * p.R + r);
+        }
         // a5: dists, their sum (left-to-right fp32), probs and steps (voxel_helpers.py:639-644)
         float total = 0.0f;
-        for (int b = 0; b < cnt; ++b)
-            total = __fadd_rn(total, __fsub_rn(__ldg(p.hit_max + (int64_t)b * p.R + r), __ldg(p.hit_min + (int64_t)b * p.R + r)));
+        for (int b = 0; b < cnt; ++b) total = __fadd_rn(total, __fsub_rn(s_max[b * kSampleThreads], s_min[b * kSampleThreads]));
         const float steps = __fdiv_rn(total, p.step_size);
         FusedHits hv;
         hv.hit_idx = p.hit_idx; hv.hit_min = p.hit_min; hv.hit_max = p.hit_max;
@@ -201,6 +212,7 @@ k_sample_fused(pslam_render_t p, int *__restrict__ block_counts)
         hv.R = p.R; hv.Rh = Rh; hv.P = P; hv.chunk_base_rank = g * n + c * kChunkRays;
         hv.total = total; hv.max_distance = p.max_distance;
         hv.own_j = j; hv.own_r = r; hv.own_cnt = cnt;
+        hv.s_idx = s_idx; hv.s_min = s_min; hv.s_max = s_max;
         const float prob0 = hv.prob(j, 0);
         int room = 0, off = 0;
         if (WRITE) {
@@ -272,13 +284,15 @@ k_sample_offsets(pslam_render_t p, const int *__restrict__ block_base)
 int launch_sample_fused(const pslam_render_t *p, cudaStream_t st)
 {
     const int nb = ceil_div(p->R, kSampleThreads);
-    int *block_counts = p->scratch_i + ceil_div(p->R, 64) + 8;   // after intersect's block_hits (64 rays per block)
-    k_sample_fused<false><<<nb, kSampleThreads, 0, st>>>(*p, block_counts);
+    int *block_counts = p->scratch_i + scratch_i_sample_off(p->R);   // after intersect's block_hits
+    const size_t smem = (size_t)p->n_max * kSampleThreads * 12;
+    PSLAM_CHECK_ARG(smem <= 48 * 1024, PSLAM_E_RANGE, "n_max=%d: the per-block hit staging exceeds 48 KB of shared memory", p->n_max);
+    k_sample_fused<false><<<nb, kSampleThreads, smem, st>>>(*p, block_counts);
     PSLAM_CHECK_LAUNCH("sample_count");
     if (int rc = scan_partials(block_counts, nb, p->counters + PSLAM_C_TILE2, st)) return rc;
     k_sample_offsets<<<nb, kSampleThreads, 0, st>>>(*p, block_counts);
     PSLAM_CHECK_LAUNCH("sample_offsets");
-    k_sample_fused<true><<<nb, kSampleThreads, 0, st>>>(*p, nullptr);
+    k_sample_fused<true><<<nb, kSampleThreads, smem, st>>>(*p, nullptr);
     PSLAM_CHECK_LAUNCH("sample_write");
     return 0;
 }
@@ -340,8 +354,8 @@ extern "C" int pslam_inverse_cdf_sampling(int b, int num_rays, int max_hits, int
                     "sizes must be positive (b=%d num_rays=%d max_hits=%d max_steps=%d)", b, num_rays, max_hits, max_steps);
     PSLAM_CHECK_ARG(pts_idx && min_depth && max_depth && uniform_noise && probs && steps, PSLAM_E_ARG, "null input pointer");
     PSLAM_CHECK_ARG(sampled_idx && sampled_depth && sampled_dists, PSLAM_E_ARG, "null output pointer");
-    const int blocks = (int)ceil_div64((int64_t)b * num_rays, kSampleThreads);
-    k_inverse_cdf_ref<<<blocks, kSampleThreads, 0, (cudaStream_t)stream>>>(
+    const int blocks = (int)ceil_div64((int64_t)b * num_rays, 128);
+    k_inverse_cdf_ref<<<blocks, 128, 0, (cudaStream_t)stream>>>(
         b, num_rays, max_hits, max_steps, fixed_step_size, pts_idx, min_depth, max_depth, uniform_noise, probs, steps,
         sampled_idx, sampled_depth, sampled_dists);
     PSLAM_CHECK_LAUNCH("inverse_cdf_sampling");
