@@ -828,7 +828,11 @@ extern "C" int pslam_decoder_fwd(int np, const pslam_decoder_t *dec, const float
     return launch_field(fp, false, np, (cudaStream_t)stream);
 }
 
-extern "C" int64_t pslam_wgrad_ws_bytes(int max_samples) { return (int64_t)tc_wgrad_scratch_bytes(max_samples); }
+extern "C" int64_t pslam_wgrad_ws_bytes(int max_samples)
+{
+    const size_t a = tc_wgrad_scratch_bytes(max_samples), b = bf_wgrad_scratch_bytes(max_samples);   // either build may be selected later
+    return (int64_t)(a > b ? a : b);
+}
 
 extern "C" int pslam_decoder_bwd(int np, const pslam_decoder_t *dec, const float *feat, float *ws, const float *g_out, float *g_feat,
                                  const pslam_decoder_grad_t *grad, void *wgrad_ws, int64_t wgrad_ws_bytes, pslam_stream_t stream)

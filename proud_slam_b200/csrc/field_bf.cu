@@ -26,7 +26,11 @@ namespace pslam {
 using namespace umma;
 
 namespace bf {
-constexpr int kThreads = 352;     // warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 workers, warp 10 scratch store
+// warpgroup 0: warp 0 TMA producer, warp 1 MMA issuer, warp 2 scratch store, warp 3 idle; warpgroups 1-2: workers.
+// The split is by warpgroup so that setmaxnreg can move registers from the three single-lane roles to the
+// workers (56 vs 224 per thread): at the launch-time 168 the backward workers spilled inside the epilogues.
+constexpr int kThreads = 384;
+constexpr int kRegsIssue = 56, kRegsWorker = 224;
 constexpr int kWorkers = 256;
 constexpr int kStages = 8;        // weight ring depth of the forward kernel
 constexpr int kStagesBwd = 4;     // ... of the backward kernel (the rest of shared memory stages the wgrad scratch)
@@ -52,13 +56,18 @@ struct Smem {
     static constexpr int bytes = oBias + 4 * (4 * 128 + 4);
 };
 
-// wgrad scratch, per 128-sample tile: eight 128-feature operands and two 16-feature operands, each already split
+// wgrad scratch, per 128-sample tile: six 128-feature operands and two 16-feature operands, each already split
 // (hi / lo bf16 planes) and in the MN-major no-swizzle core-matrix layout of tcgen05.mma (umma.cuh: sdesc):
 //     [half h = sample / 64][plane hi, lo][kb = (sample / 8) % 8][fb = feature / 8][sample % 8][8 features x 2 B]
 // so that (operand, half) = one contiguous bulk copy whose 16-sample k-steps are 2 kb blocks apart.
+// T = W3 h2 + b3 and G3 = g_t = W4t^T G4 are linear images of spilled operands, so neither is spilled: with
+// M = G4^T H2 (accumulated by k_wgrad_bf) the two gradients that would need them are tiny post-products,
+//     dW3[1+j][k] = sum_n W4[n][j] M[n][k],     dW4[n][j] = sum_k M[n][k] W3[1+j][k] + db4[n] b3[1+j]   (k_wgrad_finish)
+// which takes a quarter off the scratch traffic that bounds both backward kernels.
 constexpr size_t kOpBytes = 65536, kSmallBytes = 8192;
-constexpr int oH1 = 0, oH2 = 1, oT = 2, oHC = 3, oG1 = 4, oG2 = 5, oG3 = 6, oG4 = 7;   // x kOpBytes
-constexpr size_t oF = 8 * kOpBytes, oG5 = oF + kSmallBytes, kTileBytes = oG5 + kSmallBytes;   // 540 672 B = 4.2 kB / sample
+constexpr int oH1 = 0, oH2 = 1, oHC = 2, oG1 = 3, oG2 = 4, oG4 = 5, kBigOps = 6;   // x kOpBytes
+constexpr size_t oF = kBigOps * kOpBytes, oG5 = oF + kSmallBytes, kTileBytes = oG5 + kSmallBytes;   // 409 600 B = 3.2 kB / sample
+constexpr size_t kFinishFloats = 128 * 128 + 128;   // after the tiles: M = G4^T H2 and the column sums of G4 (zeroed per launch)
 }  // namespace bf
 
 // Re-packs the decoder into the bf16 weight stream: layers in order, each as ceil(K/32) chunks of
@@ -187,6 +196,8 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
     cluster_sync();   // every CTA's barriers are initialised before any peer multicasts into them
     const uint32_t tmem = *tmem_ptr;
 
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsIssue));
     if (warp == 0) {
         // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
         // each CTA fetches its share of every chunk and multicasts it to the whole cluster
@@ -250,14 +261,14 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
                 if (lane == 0) BF_TRACE(tile_i, l, 2);          // all MMAs of the layer issued + committed
             }
         }
-    } else if (warp == 10) {
+    } else if (warp == 2) {
         // ===================== scratch store warp: staged operand (shared memory) -> wgrad scratch by bulk TMA =====================
         if (spill) {
-            const int ops[8] = {oH1, oH2, oT, oHC, oG4, oG3, oG2, oG1};   // order in which the workers produce the operands
+            const int ops[kBigOps] = {oH1, oH2, oHC, oG4, oG2, oG1};   // order in which the workers produce the operands
             uint32_t sc = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {   // dummy iterations store nothing
 #pragma unroll
-                for (int i = 0; i < 8; ++i, ++sc) {
+                for (int i = 0; i < kBigOps; ++i, ++sc) {
                     const int b = sc & 1;
                     mbar_wait(st_full + b, (sc >> 1) & 1);
                     if (elect_one()) {
@@ -273,10 +284,12 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
             if (elect_one()) bulk_wait_all0();
             __syncwarp();
         }
+    }
     } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsWorker));
         // ===================== workers: two threads per sample row (64 accumulator columns each) =====================
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;             // which 64 columns
+        const int half = (warp - 4) >> 2;             // which 64 columns
         const int col0 = half * 64;
         const bool lead = half == 0;                  // the row's thread that also gathers / scatters
         const int m = q * 32 + lane;                  // row of the tile
@@ -305,12 +318,12 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
             mbar_wait(mma_done, done_uses & 1);
             ++done_uses;
             fence_after_sync();
-            if (threadIdx.x == 64) BF_TRACE(tile_i, lcount, 3);     // worker sees the accumulators
+            if (threadIdx.x == 128) BF_TRACE(tile_i, lcount, 3);     // worker sees the accumulators
         };
         auto a_is_ready = [&]() {
             tmem_wait_st();
             fence_before_sync();
-            if (threadIdx.x == 64) BF_TRACE(tile_i, lcount + 1, 5);  // worker has produced the A of layer lcount+1
+            if (threadIdx.x == 128) BF_TRACE(tile_i, lcount + 1, 5);  // worker has produced the A of layer lcount+1
             mbar_arrive(a_ready);
             ++lcount;
         };
@@ -322,7 +335,7 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
             if (spill && real_tile) scr = p.wg_scratch + (size_t)tile * kTileBytes;
             int vox = -1, ray = -1;
             float z = 0.0f, px = 0.f, py = 0.f, pz = 0.f;
-            if (threadIdx.x == 64) BF_TRACE(tile_i, 0, 6);            // gather starts
+            if (threadIdx.x == 128) BF_TRACE(tile_i, 0, 6);            // gather starts
             // ---- features -> A[:, 128:144) (the lead thread of each row) ----
             if (lead) {
                 float f[16];
@@ -386,8 +399,7 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
             stage_end();
             a_is_ready();
             layer_done();
-            bf_epilogue64<1>(trow, col0, sBias + 256, nomask, stage_begin());                           // t (no activation)
-            stage_end();
+            bf_epilogue64<1>(trow, col0, sBias + 256, nomask, nullptr);                                 // t (no activation; not spilled)
             float sdf = 0.0f;
             if (lead) {
                 uint32_t v[8];
@@ -450,8 +462,7 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
             stage_end();
             a_is_ready();
             layer_done();
-            bf_epilogue64<3>(trow, col0, nullptr, nomask, stage_begin());                               // g_t
-            stage_end();
+            bf_epilogue64<3>(trow, col0, nullptr, nomask, nullptr);                                     // g_t (not spilled)
             float gf[16];
 #pragma unroll
             for (int e = 0; e < 16; ++e) gf[e] = 0.0f;
@@ -539,15 +550,16 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
 // Weight gradients: dW[n][k] = sum over samples of G[p][n] * A[p][k] -- MMAs whose reduction dimension is
 // the SAMPLE index.  The scratch holds every operand already split and in the MN-major core-matrix layout,
 // so a stage is 2 (+2 small) bulk-TMA copies and the MMAs read them in place (A and B both MN-major from
-// shared memory).  Accumulators stay in tensor memory for ALL tiles of the CTA (512 of 512 columns):
-//   [0,128) dW2 = G2^T H1    [128,256) dW3 rows 1.. = G3^T H2    [256,384) dW4[:, :128] = G4^T T
-//   [384,400) dW4[:, 128:] = G4^T F    [400,416) dW1 = G1^T F    [416,432) HC^T G5 (cols 0..2 = dW5 rows)
-//   [432,448) H2^T G5 (col 3 = dW3 row 0)    [448,512) column sums of G2, G3, G4, G1 (x ones: bias gradients)
-// Steps per (tile, 64-sample half): 0: (G2, H1)   1: (G3, H2) + G5   2: (G4, T) + F   3: (G1, HC) + F + G5
+// shared memory).  Accumulators stay in tensor memory for ALL tiles of the CTA:
+//   [0,128) dW2 = G2^T H1      [128,256) M = G4^T H2 (-> dW3, dW4[:, :128] in k_wgrad_finish)
+//   [256,272) dW4[:, 128:] = G4^T F    [272,288) dW1 = G1^T F    [288,304) HC^T G5 (cols 0..2 = dW5 rows)
+//   [304,320) H2^T G5 (col 3 = dW3 row 0)    [320,368) column sums of G2, G4, G1 (x ones: bias gradients)
+// Steps per (tile, 64-sample half): 0: (G2, H1)   1: (G4, H2) + F + G5   2: (G1, HC) + F + G5
 // ------------------------------------------------------------------------------------------
 namespace wgb {
 constexpr int kThreads = 192;                   // warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 drain
 constexpr int kStages = 3;
+constexpr int kStepsPerHalf = 3;
 constexpr int kHalfBytes = 32768;               // (128-feature operand, 64-sample half): [plane 2][kb 8][fb 16][128 B]
 constexpr int kSmallHalf = 4096;                // (16-feature operand, half):           [plane 2][kb 8][fb 2][128 B]
 constexpr int oB = kHalfBytes, oFs = 2 * kHalfBytes, oG5s = oFs + kSmallHalf;
@@ -555,9 +567,9 @@ constexpr int kStageBytes = oG5s + kSmallHalf;  // 73 728
 constexpr int oOnes = kStages * kStageBytes;    // 16 samples x 16 features of bf16 1.0: [kb 2][fb 2][128 B]
 constexpr int oBars = oOnes + 512;              // full[3] free[3] all_done, tmem ptr
 constexpr int kSmemBytes = oBars + 128;
-struct Step { int a_op, b_op, use_f, use_g5; };
-__device__ __constant__ Step cSteps[4] = {
-    {bf::oG2, bf::oH1, 0, 0}, {bf::oG3, bf::oH2, 0, 1}, {bf::oG4, bf::oT, 1, 0}, {bf::oG1, bf::oHC, 1, 1}};
+constexpr int cW2 = 0, cM = 128, cW4f = 256, cW1 = 272, cHCG5 = 288, cH2G5 = 304, cS2 = 320, cS4 = 336, cS1 = 352;
+struct Step { int a_op, b_op, use_small; };
+__device__ __constant__ Step cSteps[kStepsPerHalf] = {{bf::oG2, bf::oH1, 0}, {bf::oG4, bf::oH2, 1}, {bf::oG1, bf::oHC, 1}};
 }  // namespace wgb
 
 #define WGB_TRACE(g, slot)                                                                          \
@@ -565,7 +577,7 @@ __device__ __constant__ Step cSteps[4] = {
         if (g_bf_trace && blockIdx.x == 0 && (g) < 40) g_bf_trace[320 + (g) * 8 + (slot)] = clock64();     \
     } while (0)
 
-__global__ void __launch_bounds__(wgb::kThreads, 1) k_wgrad_bf(FieldParams p)
+__global__ void __launch_bounds__(wgb::kThreads, 1) k_wgrad_bf(FieldParams p, float *__restrict__ finish)
 {
     using namespace wgb;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -588,32 +600,37 @@ __global__ void __launch_bounds__(wgb::kThreads, 1) k_wgrad_bf(FieldParams p)
     fence_after_sync();
     const uint32_t tmem = *tmem_ptr;
     const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    const int nsteps = my_tiles * 8;   // 2 halves x 4 steps
+    const int nsteps = my_tiles * 2 * kStepsPerHalf;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
+        int tl = 0, h = 0, st = 0;
         for (int g = 0; g < nsteps; ++g) {
-            const int tl = g >> 3, h = (g >> 2) & 1, st = g & 3, rs = g % kStages, use = g / kStages;
+            const int rs = g % kStages, use = g / kStages;
             const Step S = cSteps[st];
             const unsigned char *tile = p.wg_scratch + (size_t)(blockIdx.x + (size_t)tl * gridDim.x) * bf::kTileBytes;
             if (use >= 1) mbar_wait(freeb + rs, (use - 1) & 1);
             if (lane == 0) WGB_TRACE(g, 0);
             if (elect_one()) {
                 unsigned char *dst = smem + rs * kStageBytes;
-                mbar_arrive_expect_tx(full + rs, (uint32_t)(2 * kHalfBytes + (S.use_f + S.use_g5) * kSmallHalf));
+                mbar_arrive_expect_tx(full + rs, (uint32_t)(2 * kHalfBytes + S.use_small * 2 * kSmallHalf));
                 bulk_g2s(dst, tile + (size_t)S.a_op * bf::kOpBytes + (size_t)h * kHalfBytes, kHalfBytes, full + rs);
                 bulk_g2s(dst + oB, tile + (size_t)S.b_op * bf::kOpBytes + (size_t)h * kHalfBytes, kHalfBytes, full + rs);
-                if (S.use_f) bulk_g2s(dst + oFs, tile + bf::oF + (size_t)h * kSmallHalf, kSmallHalf, full + rs);
-                if (S.use_g5) bulk_g2s(dst + oG5s, tile + bf::oG5 + (size_t)h * kSmallHalf, kSmallHalf, full + rs);
+                if (S.use_small) {
+                    bulk_g2s(dst + oFs, tile + bf::oF + (size_t)h * kSmallHalf, kSmallHalf, full + rs);
+                    bulk_g2s(dst + oG5s, tile + bf::oG5 + (size_t)h * kSmallHalf, kSmallHalf, full + rs);
+                }
             }
             __syncwarp();
+            if (++st == kStepsPerHalf) { st = 0; if (++h == 2) { h = 0; ++tl; } }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         const uint32_t id128 = idesc_bf16(128, 128, 1, 1), id16 = idesc_bf16(128, 16, 1, 1);
         const uint64_t ones = sdesc(smem_u32(smem + oOnes), 256, 128);
+        int st = 0;
         for (int g = 0; g < nsteps; ++g) {
-            const int st = g & 3, rs = g % kStages;
+            const int rs = g % kStages;
             mbar_wait(full + rs, (g / kStages) & 1);
             fence_after_sync();
             if (lane == 0) WGB_TRACE(g, 4);
@@ -621,7 +638,7 @@ __global__ void __launch_bounds__(wgb::kThreads, 1) k_wgrad_bf(FieldParams p)
             if (elect_one()) {
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {            // 16 samples = 2 kb blocks per MMA
-                    const uint32_t fresh = (g < 8 && (g >> 2) == 0 && ks == 0) ? 0u : 1u;   // first touch of this step's accumulators
+                    const uint32_t fresh = (g < kStepsPerHalf && ks == 0) ? 0u : 1u;   // first touch of this step's accumulators
                     const uint64_t a_hi = sdesc(base + ks * 4096, 2048, 128), a_lo = sdesc(base + 16384 + ks * 4096, 2048, 128);
                     const uint64_t b_hi = sdesc(base + oB + ks * 4096, 2048, 128), b_lo = sdesc(base + oB + 16384 + ks * 4096, 2048, 128);
                     const uint64_t f_hi = sdesc(base + oFs + ks * 512, 256, 128), f_lo = sdesc(base + oFs + 2048 + ks * 512, 256, 128);
@@ -636,20 +653,17 @@ __global__ void __launch_bounds__(wgb::kThreads, 1) k_wgrad_bf(FieldParams p)
                         mma_bf16_ss(tmem + dcol, xl, ones, id16, 1u);
                     };
                     if (st == 0) {
-                        prod3(0, a_hi, a_lo, b_hi, b_lo, id128);            // dW2 = G2^T H1
-                        colsum(448, a_hi, a_lo);                            // db2
+                        prod3(cW2, a_hi, a_lo, b_hi, b_lo, id128);          // dW2 = G2^T H1
+                        colsum(cS2, a_hi, a_lo);                            // db2
                     } else if (st == 1) {
-                        prod3(128, a_hi, a_lo, b_hi, b_lo, id128);          // dW3[1..] = G3^T H2
-                        prod3(432, b_hi, b_lo, g_hi, g_lo, id16);           // H2^T G5 (col 3 -> dW3[0])
-                        colsum(464, a_hi, a_lo);                            // db3[1..]
-                    } else if (st == 2) {
-                        prod3(256, a_hi, a_lo, b_hi, b_lo, id128);          // dW4[:, :128] = G4^T T
-                        prod3(384, a_hi, a_lo, f_hi, f_lo, id16);           // dW4[:, 128:] = G4^T F
-                        colsum(480, a_hi, a_lo);                            // db4
+                        prod3(cM, a_hi, a_lo, b_hi, b_lo, id128);           // M = G4^T H2
+                        prod3(cW4f, a_hi, a_lo, f_hi, f_lo, id16);          // dW4[:, 128:] = G4^T F
+                        prod3(cH2G5, b_hi, b_lo, g_hi, g_lo, id16);         // H2^T G5 (col 3 -> dW3[0])
+                        colsum(cS4, a_hi, a_lo);                            // db4
                     } else {
-                        prod3(400, a_hi, a_lo, f_hi, f_lo, id16);           // dW1 = G1^T F
-                        prod3(416, b_hi, b_lo, g_hi, g_lo, id16);           // HC^T G5 (cols 0..2 -> dW5)
-                        colsum(496, a_hi, a_lo);                            // db1
+                        prod3(cW1, a_hi, a_lo, f_hi, f_lo, id16);           // dW1 = G1^T F
+                        prod3(cHCG5, b_hi, b_lo, g_hi, g_lo, id16);         // HC^T G5 (cols 0..2 -> dW5)
+                        colsum(cS1, a_hi, a_lo);                            // db1
                     }
                 }
                 mma_commit(freeb + rs);
@@ -657,6 +671,7 @@ __global__ void __launch_bounds__(wgb::kThreads, 1) k_wgrad_bf(FieldParams p)
             }
             __syncwarp();
             if (lane == 0) WGB_TRACE(g, 5);
+            if (++st == kStepsPerHalf) st = 0;
         }
     } else if (nsteps > 0) {
         // ===================== drain: accumulators -> global gradients (warp & 3 = TMEM lane quarter) =====================
@@ -676,29 +691,54 @@ __global__ void __launch_bounds__(wgb::kThreads, 1) k_wgrad_bf(FieldParams p)
                                __uint_as_float(v[4 * j + 3]));
             }
         };
-        flush(0, 128, p.g_dec.W2 + (size_t)n * 128);
-        flush(128, 128, p.g_dec.W3 + (size_t)(1 + n) * 128);
-        flush(256, 128, p.g_dec.W4 + (size_t)n * 144);
-        flush(384, 16, p.g_dec.W4 + (size_t)n * 144 + 128);
-        flush(400, 16, p.g_dec.W1 + (size_t)n * 16);
+        flush(cW2, 128, p.g_dec.W2 + (size_t)n * 128);
+        flush(cM, 128, finish + (size_t)n * 128);
+        flush(cW4f, 16, p.g_dec.W4 + (size_t)n * 144 + 128);
+        flush(cW1, 16, p.g_dec.W1 + (size_t)n * 16);
         {
             uint32_t v[8], w[8], bs[8];
-            tmem_ld8(trow + 416, v);
-            tmem_ld8(trow + 432, w);
+            tmem_ld8(trow + cHCG5, v);
+            tmem_ld8(trow + cH2G5, w);
             tmem_wait_ld();
             atomicAdd(p.g_dec.W5 + n, __uint_as_float(v[0]));
             atomicAdd(p.g_dec.W5 + 128 + n, __uint_as_float(v[1]));
             atomicAdd(p.g_dec.W5 + 256 + n, __uint_as_float(v[2]));
             atomicAdd(p.g_dec.W3 + n, __uint_as_float(w[3]));
-            tmem_ld8(trow + 448, bs); tmem_wait_ld(); atomicAdd(p.g_dec.b2 + n, __uint_as_float(bs[0]));
-            tmem_ld8(trow + 464, bs); tmem_wait_ld(); atomicAdd(p.g_dec.b3 + 1 + n, __uint_as_float(bs[0]));
-            tmem_ld8(trow + 480, bs); tmem_wait_ld(); atomicAdd(p.g_dec.b4 + n, __uint_as_float(bs[0]));
-            tmem_ld8(trow + 496, bs); tmem_wait_ld(); atomicAdd(p.g_dec.b1 + n, __uint_as_float(bs[0]));
+            tmem_ld8(trow + cS2, bs); tmem_wait_ld(); atomicAdd(p.g_dec.b2 + n, __uint_as_float(bs[0]));
+            tmem_ld8(trow + cS4, bs); tmem_wait_ld(); atomicAdd(finish + 128 * 128 + n, __uint_as_float(bs[0]));
+            tmem_ld8(trow + cS1, bs); tmem_wait_ld(); atomicAdd(p.g_dec.b1 + n, __uint_as_float(bs[0]));
         }
     }
     fence_before_sync();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// The gradients that go through M = G4^T H2 [128,128] and s4 = column sums of G4 (see the scratch layout):
+//   block j:  dW3[1+j][k] += sum_n W4[n][j] M[n][k]          db3[1+j] += sum_n W4[n][j] s4[n]
+//   block n:  dW4[n][j]   += sum_k M[n][k] W3[1+j][k] + s4[n] b3[1+j]          db4[n] += s4[n]
+__global__ void __launch_bounds__(128) k_wgrad_finish(FieldParams p, const float *__restrict__ finish)
+{
+    __shared__ float sRow[128], sCol[128];
+    const int b = blockIdx.x, t = threadIdx.x;
+    const float *M = finish, *s4 = finish + 128 * 128;
+    sRow[t] = M[(size_t)b * 128 + t];                 // M[n = b][k = t]
+    sCol[t] = p.dec.W4[(size_t)t * 144 + b];          // W4[n = t][j = b]
+    __syncthreads();
+    float acc3 = 0.0f, acc4 = 0.0f;
+    for (int n = 0; n < 128; ++n) acc3 = fmaf(sCol[n], M[(size_t)n * 128 + t], acc3);
+    for (int k = 0; k < 128; ++k) acc4 = fmaf(sRow[k], p.dec.W3[(size_t)(1 + t) * 128 + k], acc4);
+    atomicAdd(p.g_dec.W3 + (size_t)(1 + b) * 128 + t, acc3);
+    atomicAdd(p.g_dec.W4 + (size_t)b * 144 + t, acc4 + s4[b] * p.dec.b3[1 + t]);
+    float v = sCol[t] * s4[t];                         // db3[1 + b] = sum_n W4[n][b] s4[n]
+    v = warp_sum(v);
+    __syncthreads();
+    if ((t & 31) == 0) sRow[t >> 5] = v;
+    __syncthreads();
+    if (t == 0) {
+        atomicAdd(p.g_dec.b3 + 1 + b, (sRow[0] + sRow[1]) + (sRow[2] + sRow[3]));
+        atomicAdd(p.g_dec.b4 + b, s4[b]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -808,7 +848,10 @@ int bf_pack_decoder(const pslam_decoder_t &d, float *ws_tc, cudaStream_t st)
     return 0;
 }
 
-size_t bf_wgrad_scratch_bytes(int max_samples) { return (size_t)ceil_div(max_samples > 0 ? max_samples : 1, 128) * bf::kTileBytes; }
+size_t bf_wgrad_scratch_bytes(int max_samples)
+{
+    return (size_t)ceil_div(max_samples > 0 ? max_samples : 1, 128) * bf::kTileBytes + bf::kFinishFloats * sizeof(float);
+}
 
 template <bool BWD>
 static int launch_bf(const FieldParams &fp, int max_samples, cudaStream_t st)
@@ -860,10 +903,15 @@ int bf_launch_field_backward(const FieldParams &fp_in, int max_samples, cudaStre
         if (e != cudaSuccess) { set_error("wgrad_bf: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         configured = true;
     }
-    const int tiles = ceil_div(max_samples, 128);
-    const int grid = tiles < num_sms() ? (tiles > 0 ? tiles : 1) : num_sms();
-    k_wgrad_bf<<<grid, wgb::kThreads, wgb::kSmemBytes, st>>>(fp);
+    const int tiles = ceil_div(max_samples > 0 ? max_samples : 1, 128);
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    float *finish = reinterpret_cast<float *>(fp.wg_scratch + (size_t)tiles * bf::kTileBytes);
+    cudaError_t e = cudaMemsetAsync(finish, 0, bf::kFinishFloats * sizeof(float), st);
+    if (e != cudaSuccess) { set_error("wgrad_bf: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
+    k_wgrad_bf<<<grid, wgb::kThreads, wgb::kSmemBytes, st>>>(fp, finish);
     PSLAM_CHECK_LAUNCH("wgrad_bf");
+    k_wgrad_finish<<<128, 128, 0, st>>>(fp, finish);
+    PSLAM_CHECK_LAUNCH("wgrad_finish");
     return 0;
 }
 
