@@ -44,6 +44,10 @@ int pslam_device_info(int *out3);
  * 2 = tcgen05 tensor cores with 3xBF16 operand splitting (16-17 significant bits per operand,
  * <= ~1e-5 relative; inside the 1e-4 parity bound).  Width 256 always runs the SIMT build. */
 #define PSLAM_OPT_DECODER 1
+/* PSLAM_OPT_SAVE_ACT (3xBF16 build): 1 (default) = a forward that will be followed by a decoder-gradient
+ * backward (PSLAM_F_GRAD_DEC with a wgrad workspace) spills its activations and ReLU masks, and that backward
+ * runs the gradient chain only; 0 = the backward always recomputes the forward. */
+#define PSLAM_OPT_SAVE_ACT 2
 int pslam_set_option(int key, int value);
 
 /* ------------------------------------------------------------------------

@@ -756,6 +756,7 @@ static FieldParams params_from_render(const pslam_render_t *p)
     fp.grad_dec = (p->flags & PSLAM_F_GRAD_DEC) ? 1 : 0;
     fp.grad_emb = (p->flags & PSLAM_F_GRAD_EMB) ? 1 : 0;
     fp.grad_rays = (p->flags & PSLAM_F_GRAD_RAYS) ? 1 : 0;
+    fp.paired = 1;
     return fp;
 }
 

@@ -28,6 +28,10 @@ struct FieldParams {
     const float *g_out;             // [P,4]
     float *g_feat;                  // [P,16] (standalone) or nullptr
     unsigned char *wg_scratch;      // tcgen05 wgrad scratch (tc_wgrad_scratch_bytes) or nullptr
+    uint32_t *act_masks;            // ReLU masks saved by the forward (3xBF16 build, inside wg_scratch; set by its launcher)
+    uint32_t *gscale;               // bit pattern of max |g_out| of this backward launch (3xF16 build; set by its launcher)
+    int paired;                     // forward and backward come from one pslam_render_t (fused pipeline): the forward may save
+                                    // its activations for the backward; stand-alone calls (pslam_decoder_*) always recompute
     size_t wg_scratch_bytes;
     pslam_decoder_grad_t g_dec;
     float *g_emb;                   // [E,16] +=
@@ -51,5 +55,6 @@ int bf_pack_decoder(const pslam_decoder_t &d, float *ws_tc, cudaStream_t st);
 int bf_launch_field_forward(const FieldParams &fp, int max_samples, cudaStream_t st);
 int bf_launch_field_backward(const FieldParams &fp, int max_samples, cudaStream_t st, int part = 0);
 size_t bf_wgrad_scratch_bytes(int max_samples);
+void bf_set_save_activations(int on);   // PSLAM_OPT_SAVE_ACT
 
 }  // namespace pslam

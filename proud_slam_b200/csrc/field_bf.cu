@@ -41,13 +41,26 @@ constexpr int kCluster = 2;
 constexpr uint16_t kClusterMask = (1u << kCluster) - 1u;
 constexpr int kTmemCols = 512;
 constexpr int cAHI = 0, cALO = 72, cD = 144;
+// Power-of-two operand scales that keep the f16 halves in their precise window (umma.cuh: h16_split2).  Weights and
+// forward activations are stored x16 (|value| < 4094 representable; absolute resolution 2^-29): an accumulator then
+// holds 256 x the product and the epilogue folds 1/16 into its bias FMA, which leaves the next layer's operand
+// scaled x16 again.  Gradients carry a per-launch scale Sg = 2^k taken from max |g_out| (k_grad_scale) so that
+// the chain stays near 2^8; gradient accumulators hold 16 x Sg x the product.
+constexpr float kScale = 16.0f, kInvScale = 1.0f / 16.0f;
 using declayers::kLayersAll;
 using declayers::kLayersFwd;
 __device__ __constant__ int cN[kLayersAll] = {128, 128, 144, 128, 16, 128, 144, 128, 128, 16};
 __device__ __constant__ int cK[kLayersAll] = {16, 128, 128, 144, 128, 16, 128, 144, 128, 128};
 __device__ __constant__ int cAcol[kLayersAll] = {64, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // packed A column of the layer's k = 0
-template <bool BWD>
+// Kernel kinds.  The mapping iteration runs kFwdSave + kBwdSaved: the forward spills its activations (H1, H2, HC, F)
+// and ReLU masks, so the backward is the dgrad chain alone.  kBwdRecompute (stand-alone backward: forward recompute +
+// dgrad, spills everything itself) serves calls whose forward did not save (pslam_decoder_bwd, tracking).
+constexpr int kFwd = 0, kBwdRecompute = 1, kFwdSave = 2, kBwdSaved = 3;
+constexpr int kMaskBytes = 3 * 2 * 2 * 128 * 4;   // per tile: [layer h1, h2, hc][column half][32-column batch][row] ReLU bits
+constexpr int kFwdStreamBytes = 4 * (128 * 16 + 128 * 128 + 144 * 128 + 128 * 144 + 16 * 128);   // weight stream of layers 0-4
+template <int KIND>
 struct Smem {
+    static constexpr bool BWD = KIND != kFwd;   // has the two staging buffers of the wgrad scratch
     static constexpr int nStages = BWD ? kStagesBwd : kStages;
     static constexpr int oStaging = nStages * kStageBytes;
     static constexpr int oBars = oStaging + (BWD ? 2 * kStagingBytes : 0);   // full[8], empty[8], a_ready, mma_done, st_full[2], st_free[2]
@@ -84,7 +97,7 @@ __global__ void k_bf_pack(pslam_decoder_t d, uint16_t *__restrict__ out)
             const int c = k / bf::kChunkK, kr = k % bf::kChunkK;
             const int kk = (K - c * bf::kChunkK) < bf::kChunkK ? (K - c * bf::kChunkK) : bf::kChunkK;
             uint32_t hi, lo;
-            bf16_split2(tc_weight(d, l, n, k), 0.0f, hi, lo);
+            h16_split2(bf::kScale * tc_weight(d, l, n, k), 0.0f, hi, lo);
             uint16_t *chunk = out + base + c * (N * bf::kChunkK * 2);
             const int off = (kr >> 3) * (N * 8) + n * 8 + (kr & 7);
             chunk[off] = (uint16_t)(hi & 0xffffu);
@@ -96,13 +109,37 @@ __global__ void k_bf_pack(pslam_decoder_t d, uint16_t *__restrict__ out)
     }
 }
 
+// Gradient scale of one backward launch: gscale[0] holds the bit pattern of max |g_out| (k_grad_scale); Sg = 2^(8 - e)
+// brings that maximum to [256, 512).  Powers of two: scaling and unscaling are exact.
+__device__ __forceinline__ float grad_scale(const uint32_t *gscale)
+{
+    const uint32_t bits = gscale ? *gscale : 0u;
+    const int e = (int)((bits >> 23) & 0xffu);          // biased exponent of the maximum
+    if (e == 0 || e == 255) return 1.0f;                // all zero / not finite: leave alone
+    int k = 127 + 8 - (e - 127);                        // biased exponent of Sg
+    k = k < 1 ? 1 : (k > 254 ? 254 : k);
+    return __uint_as_float((uint32_t)k << 23);
+}
+__global__ void k_grad_scale(const float4 *__restrict__ g_out, int n, const int *__restrict__ n_dev, uint32_t *__restrict__ gscale)
+{
+    if (n_dev) n = *n_dev;
+    float m = 0.0f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 v = __ldg(g_out + i);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(gscale, __float_as_uint(m));   // non-negative floats order like their bits
+}
+
 // One epilogue over this thread's 64 accumulator columns [col0, col0+64): accumulators -> registers ->
 // (bias / activation / mask) -> hi/lo bf16 pairs -> next A operand (tensor memory, two values per column)
 // and optionally the staging buffer of the wgrad scratch (the same packed words, 16 B = one core-matrix row).
-//   MODE 0: y = relu(D + bias), records y > 0 in mask[]        (forward hidden layers)
-//   MODE 1: y = D + bias                                       (forward, no activation)
-//   MODE 2: y = mask ? D : 0                                   (dgrad through a ReLU)
-//   MODE 3: y = D                                              (dgrad, no activation)
+//   MODE 0: y = relu(D/16 + bias), records y > 0 in mask[]     (forward hidden layers; bias pre-scaled x16, y = 16 x activation)
+//   MODE 1: y = D/16 + bias                                    (forward, no activation)
+//   MODE 2: y = mask ? D/16 : 0                                (dgrad through a ReLU; y = Sg x gradient)
+//   MODE 3: y = D/16                                           (dgrad, no activation)
 template <int MODE>
 __device__ __forceinline__ void bf_epilogue64(uint32_t trow, int col0, const float *bias, uint32_t (&mask)[2], unsigned char *stg)
 {
@@ -117,15 +154,16 @@ __device__ __forceinline__ void bf_epilogue64(uint32_t trow, int col0, const flo
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
             float y = __uint_as_float(v[e]);
-            if (MODE == 0) { y = fmaxf(y + bias[c0 + e], 0.0f); bits |= (y > 0.0f ? 1u : 0u) << e; }
-            if (MODE == 1) y = y + bias[c0 + e];
-            if (MODE == 2) y = ((mask[b] >> e) & 1u) ? y : 0.0f;
+            if (MODE == 0) { y = fmaxf(fmaf(y, kInvScale, bias[c0 + e]), 0.0f); bits |= (y > 0.0f ? 1u : 0u) << e; }
+            if (MODE == 1) y = fmaf(y, kInvScale, bias[c0 + e]);
+            if (MODE == 2) y = ((mask[b] >> e) & 1u) ? y * kInvScale : 0.0f;
+            if (MODE == 3) y = y * kInvScale;
             v[e] = __float_as_uint(y);
         }
         if (MODE == 0) mask[b] = bits;
         uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) bf16_split2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]), hi[e], lo[e]);
+        for (int e = 0; e < 16; ++e) h16_split2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]), hi[e], lo[e]);
         if (stg) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -146,13 +184,14 @@ __device__ long long *g_bf_trace = nullptr;
         if (g_bf_trace && blockIdx.x == 0 && (tile_i) < 4) g_bf_trace[((tile_i) * 10 + (layer)) * 8 + (slot)] = clock64(); \
     } while (0)
 
-template <bool BWD>
+template <int KIND>
 __global__ void __cluster_dims__(bf::kCluster, 1, 1) __launch_bounds__(bf::kThreads, 1)
 k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
 {
     using namespace bf;
-    constexpr int NL = BWD ? kLayersAll : kLayersFwd;
-    using SM = Smem<BWD>;
+    constexpr bool kHasFwd = KIND != kBwdSaved, kHasBwd = KIND == kBwdRecompute || KIND == kBwdSaved;
+    constexpr int L0 = kHasFwd ? 0 : kLayersFwd, L1 = kHasBwd ? kLayersAll : kLayersFwd;   // layers [L0, L1) of the chain
+    using SM = Smem<KIND>;
     constexpr int NS = SM::nStages;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + SM::oBars);
@@ -179,7 +218,8 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(tmem_ptr, kTmemCols);
-    const bool spill = BWD && p.wg_scratch != nullptr;   // activations / gradients go to the wgrad scratch
+    // activations / gradients go to the wgrad scratch (the stand-alone backward also runs without decoder gradients)
+    const bool spill = KIND == kFwdSave || KIND == kBwdSaved || (KIND == kBwdRecompute && p.wg_scratch != nullptr);
     for (int i = threadIdx.x; i < 4 * 128 + 4; i += kThreads) {
         float v;
         if (i < 128) v = p.dec.b1[i];
@@ -188,7 +228,7 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
         else if (i < 512) v = p.dec.b4[i - 384];
         else if (i == 512) v = p.dec.b3[0];
         else v = p.dec.b5[i - 513];
-        sBias[i] = v;
+        sBias[i] = i < 512 ? kScale * v : v;
     }
     fence_before_sync();
     __syncthreads();
@@ -203,8 +243,8 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
         // each CTA fetches its share of every chunk and multicasts it to the whole cluster
         int stage = 0, phase = 0;
         for (int it = 0; it < iters; ++it) {
-            const unsigned char *src = wstream;
-            for (int l = 0; l < NL; ++l) {
+            const unsigned char *src = wstream + (kHasFwd ? 0 : kFwdStreamBytes);
+            for (int l = L0; l < L1; ++l) {
                 const int N = cN[l], K = cK[l];
                 for (int k0 = 0; k0 < K; k0 += kChunkK) {
                     const int kk = (K - k0) < kChunkK ? (K - k0) : kChunkK;
@@ -226,9 +266,9 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
         uint32_t uses = 0;   // a_ready phase counter
         int tile_i = 0;
         for (int it = 0; it < iters; ++it, ++tile_i) {
-            for (int l = 0; l < NL; ++l) {
+            for (int l = L0; l < L1; ++l) {
                 const int N = cN[l], K = cK[l];
-                const uint32_t idesc = idesc_bf16(128, N);
+                const uint32_t idesc = idesc_h16(128, N);
                 if (lane == 0) BF_TRACE(tile_i, l, 0);          // MMA warp starts waiting for A
                 mbar_wait(a_ready, uses & 1);
                 ++uses;
@@ -247,9 +287,9 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
                                 const uint32_t acol = (uint32_t)(k0 + s * 16) >> 1;
                                 const uint64_t b_hi = sdesc(sb + s * (2 * N * 16), N * 16, 128);
                                 const uint64_t b_lo = sdesc(sb + N * kk * 2 + s * (2 * N * 16), N * 16, 128);
-                                mma_bf16_ts(d, a_lo + acol, b_hi, idesc, (k0 | s) ? 1u : 0u);
-                                mma_bf16_ts(d, a_hi + acol, b_lo, idesc, 1u);
-                                mma_bf16_ts(d, a_hi + acol, b_hi, idesc, 1u);
+                                mma_h16_ts(d, a_lo + acol, b_hi, idesc, (k0 | s) ? 1u : 0u);
+                                mma_h16_ts(d, a_hi + acol, b_lo, idesc, 1u);
+                                mma_h16_ts(d, a_hi + acol, b_hi, idesc, 1u);
                             }
                         }
                         mma_commit_mcast(empty + stage, kClusterMask);  // this CTA is done with the stage: tell every producer
@@ -265,10 +305,11 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
         // ===================== scratch store warp: staged operand (shared memory) -> wgrad scratch by bulk TMA =====================
         if (spill) {
             const int ops[kBigOps] = {oH1, oH2, oHC, oG4, oG2, oG1};   // order in which the workers produce the operands
+            constexpr int i0 = kHasFwd ? 0 : 3, i1 = kHasBwd ? kBigOps : 3;
             uint32_t sc = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {   // dummy iterations store nothing
 #pragma unroll
-                for (int i = 0; i < kBigOps; ++i, ++sc) {
+                for (int i = i0; i < i1; ++i, ++sc) {
                     const int b = sc & 1;
                     mbar_wait(st_full + b, (sc >> 1) & 1);
                     if (elect_one()) {
@@ -299,7 +340,8 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
         const int rowoff_small = (m >> 6) * 4096 + ((m >> 3) & 7) * 256 + (m & 7) * 16;
         uint32_t done_uses = 0;
         uint32_t nomask[2] = {0u, 0u};
-        int tile_i = 0, lcount = -1;                  // trace bookkeeping
+        const float Sg = kHasBwd ? grad_scale(p.gscale) : 1.0f, invSg = 1.0f / Sg;
+        int tile_i = 0, lcount = L0 - 1;              // trace bookkeeping
         uint32_t sc = 0;                              // staged operands so far (two staging buffers alternate)
         bool real_tile = true;
         auto stage_begin = [&]() -> unsigned char * {
@@ -327,7 +369,7 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
             mbar_arrive(a_ready);
             ++lcount;
         };
-        for (int it = 0; it < iters; ++it, ++tile_i, lcount = -1) {
+        for (int it = 0; it < iters; ++it, ++tile_i, lcount = L0 - 1) {
             const int tile = blockIdx.x + it * gridDim.x;
             real_tile = tile < ntiles;
             const int s = real_tile ? tile * 128 + m : nsamp;      // rows of a dummy iteration are all out of range
@@ -336,17 +378,21 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
             int vox = -1, ray = -1;
             float z = 0.0f, px = 0.f, py = 0.f, pz = 0.f;
             if (threadIdx.x == 128) BF_TRACE(tile_i, 0, 6);            // gather starts
-            // ---- features -> A[:, 128:144) (the lead thread of each row) ----
+            uint32_t m1[2], m2[2], mc[2];
+            float sdf = 0.0f, r = 0.f, g = 0.f, b = 0.f;
+            // ---- features -> A[:, 128:144) (the lead thread of each row); kBwdSaved only needs the sample's position ----
             if (lead) {
                 float f[16];
 #pragma unroll
                 for (int e = 0; e < 16; ++e) f[e] = 0.0f;
                 if (s < nsamp) {
                     if (p.feat) {
+                        if (kHasFwd) {
 #pragma unroll
-                        for (int e = 0; e < 16; e += 4) {
-                            const float4 v = __ldg(reinterpret_cast<const float4 *>(p.feat + (size_t)s * 16 + e));
-                            f[e] = v.x; f[e + 1] = v.y; f[e + 2] = v.z; f[e + 3] = v.w;
+                            for (int e = 0; e < 16; e += 4) {
+                                const float4 v = __ldg(reinterpret_cast<const float4 *>(p.feat + (size_t)s * 16 + e));
+                                f[e] = v.x; f[e + 1] = v.y; f[e + 2] = v.z; f[e + 3] = v.w;
+                            }
                         }
                     } else {
                         vox = __ldg(p.samp_vox + s);
@@ -358,27 +404,31 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
                         px = __fadd_rn(__fdiv_rn(__fsub_rn(x, __ldg(p.centres + (size_t)vox * 3 + 0)), p.voxel_size), 0.5f);
                         py = __fadd_rn(__fdiv_rn(__fsub_rn(y, __ldg(p.centres + (size_t)vox * 3 + 1)), p.voxel_size), 0.5f);
                         pz = __fadd_rn(__fdiv_rn(__fsub_rn(zz, __ldg(p.centres + (size_t)vox * 3 + 2)), p.voxel_size), 0.5f);
+                        if (kHasFwd) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int row = __ldg(p.vertex_idx + (size_t)vox * 8 + i);
-                            const float wx = (i & 4) ? px : 1.0f - px, wy = (i & 2) ? py : 1.0f - py, wz = (i & 1) ? pz : 1.0f - pz;
-                            const float w = (wx * wy) * wz;
-                            const float4 *er = reinterpret_cast<const float4 *>(p.emb + (size_t)row * 16);
+                            for (int i = 0; i < 8; ++i) {
+                                const int row = __ldg(p.vertex_idx + (size_t)vox * 8 + i);
+                                const float wx = (i & 4) ? px : 1.0f - px, wy = (i & 2) ? py : 1.0f - py, wz = (i & 1) ? pz : 1.0f - pz;
+                                const float w = (wx * wy) * wz;
+                                const float4 *er = reinterpret_cast<const float4 *>(p.emb + (size_t)row * 16);
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float4 v = __ldg(er + e);
-                                f[4 * e] = fmaf(w, v.x, f[4 * e]); f[4 * e + 1] = fmaf(w, v.y, f[4 * e + 1]);
-                                f[4 * e + 2] = fmaf(w, v.z, f[4 * e + 2]); f[4 * e + 3] = fmaf(w, v.w, f[4 * e + 3]);
+                                for (int e = 0; e < 4; ++e) {
+                                    const float4 v = __ldg(er + e);
+                                    f[4 * e] = fmaf(w, v.x, f[4 * e]); f[4 * e + 1] = fmaf(w, v.y, f[4 * e + 1]);
+                                    f[4 * e + 2] = fmaf(w, v.z, f[4 * e + 2]); f[4 * e + 3] = fmaf(w, v.w, f[4 * e + 3]);
+                                }
                             }
                         }
                     }
                 }
                 uint32_t hi[8], lo[8];
+                if (kHasFwd) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) bf16_split2(f[2 * e], f[2 * e + 1], hi[e], lo[e]);
-                tmem_st8(trow + cAHI + 64, hi);
-                tmem_st8(trow + cALO + 64, lo);
-                if (scr) {
+                    for (int e = 0; e < 8; ++e) h16_split2(kScale * f[2 * e], kScale * f[2 * e + 1], hi[e], lo[e]);
+                    tmem_st8(trow + cAHI + 64, hi);
+                    tmem_st8(trow + cALO + 64, lo);
+                }
+                if (kHasFwd && scr) {
                     unsigned char *dst = scr + oF + rowoff_small;
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
@@ -387,8 +437,8 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
                     }
                 }
             }
+            if constexpr (kHasFwd) {
             a_is_ready();
-            uint32_t m1[2], m2[2], mc[2];
             // ---- forward ----
             layer_done();
             bf_epilogue64<0>(trow, col0, sBias, m1, stage_begin());                                     // h1
@@ -400,12 +450,11 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
             a_is_ready();
             layer_done();
             bf_epilogue64<1>(trow, col0, sBias + 256, nomask, nullptr);                                 // t (no activation; not spilled)
-            float sdf = 0.0f;
             if (lead) {
                 uint32_t v[8];
                 tmem_ld8(trow + cD + 128, v);   // sdf = row 0 of W3, packed as output column 128
                 tmem_wait_ld();
-                sdf = __uint_as_float(v[0]) + sBias[512];
+                sdf = fmaf(__uint_as_float(v[0]), kInvScale * kInvScale, sBias[512]);
             }
             a_is_ready();
             layer_done();
@@ -413,36 +462,50 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
             stage_end();
             a_is_ready();
             layer_done();
-            float r = 0.f, g = 0.f, b = 0.f;
             if (lead) {
                 uint32_t v[8];
                 tmem_ld8(trow + cD, v);
                 tmem_wait_ld();
-                r = sigmoid_f(__uint_as_float(v[0]) + sBias[513]);
-                g = sigmoid_f(__uint_as_float(v[1]) + sBias[514]);
-                b = sigmoid_f(__uint_as_float(v[2]) + sBias[515]);
+                r = sigmoid_f(fmaf(__uint_as_float(v[0]), kInvScale * kInvScale, sBias[513]));
+                g = sigmoid_f(fmaf(__uint_as_float(v[1]), kInvScale * kInvScale, sBias[514]));
+                b = sigmoid_f(fmaf(__uint_as_float(v[2]), kInvScale * kInvScale, sBias[515]));
             }
-            if (!BWD) {
+            }   // kHasFwd
+            if constexpr (!kHasBwd) {
                 if (lead && s < nsamp) *reinterpret_cast<float4 *>(p.out + (size_t)s * 4) = make_float4(r, g, b, sdf);
+                if (KIND == kFwdSave && real_tile) {
+                    // ReLU masks of this thread's 64 columns for the dgrad kernel that follows
+                    uint32_t *mk = p.act_masks + (size_t)tile * (kMaskBytes / 4) + half * 256 + m;
+                    mk[0] = m1[0]; mk[128] = m1[1]; mk[512] = m2[0]; mk[512 + 128] = m2[1]; mk[1024] = mc[0]; mk[1024 + 128] = mc[1];
+                }
                 continue;   // D has been read; the next tile's first MMA is ordered behind it through a_ready
+            }
+            if constexpr (KIND == kBwdSaved) {
+                const uint32_t *mk = p.act_masks + (size_t)(real_tile ? tile : 0) * (kMaskBytes / 4) + half * 256 + m;
+                m1[0] = mk[0]; m1[1] = mk[128]; m2[0] = mk[512]; m2[1] = mk[512 + 128]; mc[0] = mk[1024]; mc[1] = mk[1024 + 128];
+                if (lead && s < nsamp) {
+                    const float4 o = __ldg(reinterpret_cast<const float4 *>(p.out + (size_t)s * 4));
+                    r = o.x; g = o.y; b = o.z;
+                }
             }
             // ---- backward ----
             float4 go = make_float4(0.f, 0.f, 0.f, 0.f);
             if (lead) {
                 if (s < nsamp) go = __ldg(reinterpret_cast<const float4 *>(p.g_out + (size_t)s * 4));
+                go.x *= Sg; go.y *= Sg; go.z *= Sg; go.w *= Sg;     // the whole chain is linear in g_out: it carries Sg to the end
                 // dL/d(pre-sigmoid rgb): grad * (1 - y) * y ; A[:, 0:16) = [g5 r,g,b, 0...]
                 const float g5[4] = {go.x * (1.0f - r) * r, go.y * (1.0f - g) * g, go.z * (1.0f - b) * b, go.w};
                 uint32_t hi[8], lo[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) { hi[e] = 0u; lo[e] = 0u; }
-                bf16_split2(g5[0], g5[1], hi[0], lo[0]);
-                bf16_split2(g5[2], 0.0f, hi[1], lo[1]);
+                h16_split2(g5[0], g5[1], hi[0], lo[0]);
+                h16_split2(g5[2], 0.0f, hi[1], lo[1]);
                 tmem_st8(trow + cAHI, hi);
                 tmem_st8(trow + cALO, lo);
                 if (scr) {
                     // wgrad operand G5 = (g5 r, g, b, g_sdf, 0 ...)
                     uint32_t h1w, l1w;
-                    bf16_split2(g5[2], g5[3], h1w, l1w);
+                    h16_split2(g5[2], g5[3], h1w, l1w);
                     unsigned char *dst = scr + oG5 + rowoff_small;
                     *reinterpret_cast<uint4 *>(dst) = make_uint4(hi[0], h1w, 0u, 0u);
                     *reinterpret_cast<uint4 *>(dst + 128) = make_uint4(0u, 0u, 0u, 0u);
@@ -451,8 +514,8 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
                     // bias gradients of the two heads: column sums of G5 (k_wgrad_bf takes the others on the tensor cores)
                     const float s0 = warp_sum(g5[0]), s1 = warp_sum(g5[1]), s2 = warp_sum(g5[2]), s3 = warp_sum(g5[3]);
                     if (lane == 0) {
-                        atomicAdd(p.g_dec.b5 + 0, s0); atomicAdd(p.g_dec.b5 + 1, s1); atomicAdd(p.g_dec.b5 + 2, s2);
-                        atomicAdd(p.g_dec.b3, s3);
+                        atomicAdd(p.g_dec.b5 + 0, s0 * invSg); atomicAdd(p.g_dec.b5 + 1, s1 * invSg); atomicAdd(p.g_dec.b5 + 2, s2 * invSg);
+                        atomicAdd(p.g_dec.b3, s3 * invSg);
                     }
                 }
             }
@@ -471,10 +534,10 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
                 tmem_ld16(trow + cD + 128, v);   // g_f, part through W4's last 16 input columns
                 tmem_wait_ld();
 #pragma unroll
-                for (int e = 0; e < 16; ++e) gf[e] = __uint_as_float(v[e]);
+                for (int e = 0; e < 16; ++e) gf[e] = __uint_as_float(v[e]);      // 16 x Sg x g_f (first part)
 #pragma unroll
                 for (int e = 0; e < 8; ++e) { hi[e] = 0u; lo[e] = 0u; }
-                bf16_split2(go.w, 0.0f, hi[0], lo[0]);  // A[:, 128] = g_sdf pairs with W3 row 0 (packed at k = 128)
+                h16_split2(go.w, 0.0f, hi[0], lo[0]);  // A[:, 128] = g_sdf pairs with W3 row 0 (packed at k = 128)
                 tmem_st8(trow + cAHI + 64, hi);
                 tmem_st8(trow + cALO + 64, lo);
             }
@@ -494,7 +557,7 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
                 tmem_ld16(trow + cD, v);
                 tmem_wait_ld();
 #pragma unroll
-                for (int e = 0; e < 16; ++e) gf[e] += __uint_as_float(v[e]);
+                for (int e = 0; e < 16; ++e) gf[e] = (gf[e] + __uint_as_float(v[e])) * (kInvScale * invSg);   // unscaled g_f
             }
             if (s >= nsamp) continue;
             if (p.g_feat) {
@@ -593,7 +656,7 @@ __global__ void __launch_bounds__(wgb::kThreads, 1) k_wgrad_bf(FieldParams p, fl
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr, 512);
-    for (int i = tid; i < 128; i += kThreads) reinterpret_cast<uint32_t *>(smem + oOnes)[i] = 0x3F803F80u;   // bf16 1.0 pairs
+    for (int i = tid; i < 128; i += kThreads) reinterpret_cast<uint32_t *>(smem + oOnes)[i] = 0x3C003C00u;   // f16 1.0 pairs
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     fence_before_sync();
     __syncthreads();
@@ -626,7 +689,7 @@ __global__ void __launch_bounds__(wgb::kThreads, 1) k_wgrad_bf(FieldParams p, fl
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        const uint32_t id128 = idesc_bf16(128, 128, 1, 1), id16 = idesc_bf16(128, 16, 1, 1);
+        const uint32_t id128 = idesc_h16(128, 128, 1, 1), id16 = idesc_h16(128, 16, 1, 1);
         const uint64_t ones = sdesc(smem_u32(smem + oOnes), 256, 128);
         int st = 0;
         for (int g = 0; g < nsteps; ++g) {
@@ -644,13 +707,13 @@ __global__ void __launch_bounds__(wgb::kThreads, 1) k_wgrad_bf(FieldParams p, fl
                     const uint64_t f_hi = sdesc(base + oFs + ks * 512, 256, 128), f_lo = sdesc(base + oFs + 2048 + ks * 512, 256, 128);
                     const uint64_t g_hi = sdesc(base + oG5s + ks * 512, 256, 128), g_lo = sdesc(base + oG5s + 2048 + ks * 512, 256, 128);
                     auto prod3 = [&](uint32_t dcol, uint64_t xh, uint64_t xl, uint64_t yh, uint64_t yl, uint32_t idesc) {
-                        mma_bf16_ss(tmem + dcol, xl, yh, idesc, fresh);
-                        mma_bf16_ss(tmem + dcol, xh, yl, idesc, 1u);
-                        mma_bf16_ss(tmem + dcol, xh, yh, idesc, 1u);
+                        mma_h16_ss(tmem + dcol, xl, yh, idesc, fresh);
+                        mma_h16_ss(tmem + dcol, xh, yl, idesc, 1u);
+                        mma_h16_ss(tmem + dcol, xh, yh, idesc, 1u);
                     };
                     auto colsum = [&](uint32_t dcol, uint64_t xh, uint64_t xl) {
-                        mma_bf16_ss(tmem + dcol, xh, ones, id16, fresh);
-                        mma_bf16_ss(tmem + dcol, xl, ones, id16, 1u);
+                        mma_h16_ss(tmem + dcol, xh, ones, id16, fresh);
+                        mma_h16_ss(tmem + dcol, xl, ones, id16, 1u);
                     };
                     if (st == 0) {
                         prod3(cW2, a_hi, a_lo, b_hi, b_lo, id128);          // dW2 = G2^T H1
@@ -680,6 +743,8 @@ __global__ void __launch_bounds__(wgb::kThreads, 1) k_wgrad_bf(FieldParams p, fl
         const int qd = warp & 3;
         const int n = qd * 32 + lane;                            // accumulator row = TMEM lane
         const uint32_t trow = tmem + ((uint32_t)(qd * 32) << 16);
+        // accumulators hold 16 x Sg x (sum of products), the column sums Sg x (sum): both factors are powers of two
+        const float invSg = 1.0f / grad_scale(p.gscale), cW = bf::kInvScale * invSg;
         auto flush = [&](int col0, int ncols, float *dst_row) {   // dst_row: &dW[n][0], ncols % 16 == 0
             for (int c0 = 0; c0 < ncols; c0 += 16) {
                 uint32_t v[16];
@@ -687,8 +752,8 @@ __global__ void __launch_bounds__(wgb::kThreads, 1) k_wgrad_bf(FieldParams p, fl
                 tmem_wait_ld();
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    red_add_v4(dst_row + c0 + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                               __uint_as_float(v[4 * j + 3]));
+                    red_add_v4(dst_row + c0 + 4 * j, cW * __uint_as_float(v[4 * j]), cW * __uint_as_float(v[4 * j + 1]),
+                               cW * __uint_as_float(v[4 * j + 2]), cW * __uint_as_float(v[4 * j + 3]));
             }
         };
         flush(cW2, 128, p.g_dec.W2 + (size_t)n * 128);
@@ -700,13 +765,13 @@ __global__ void __launch_bounds__(wgb::kThreads, 1) k_wgrad_bf(FieldParams p, fl
             tmem_ld8(trow + cHCG5, v);
             tmem_ld8(trow + cH2G5, w);
             tmem_wait_ld();
-            atomicAdd(p.g_dec.W5 + n, __uint_as_float(v[0]));
-            atomicAdd(p.g_dec.W5 + 128 + n, __uint_as_float(v[1]));
-            atomicAdd(p.g_dec.W5 + 256 + n, __uint_as_float(v[2]));
-            atomicAdd(p.g_dec.W3 + n, __uint_as_float(w[3]));
-            tmem_ld8(trow + cS2, bs); tmem_wait_ld(); atomicAdd(p.g_dec.b2 + n, __uint_as_float(bs[0]));
-            tmem_ld8(trow + cS4, bs); tmem_wait_ld(); atomicAdd(finish + 128 * 128 + n, __uint_as_float(bs[0]));
-            tmem_ld8(trow + cS1, bs); tmem_wait_ld(); atomicAdd(p.g_dec.b1 + n, __uint_as_float(bs[0]));
+            atomicAdd(p.g_dec.W5 + n, cW * __uint_as_float(v[0]));
+            atomicAdd(p.g_dec.W5 + 128 + n, cW * __uint_as_float(v[1]));
+            atomicAdd(p.g_dec.W5 + 256 + n, cW * __uint_as_float(v[2]));
+            atomicAdd(p.g_dec.W3 + n, cW * __uint_as_float(w[3]));
+            tmem_ld8(trow + cS2, bs); tmem_wait_ld(); atomicAdd(p.g_dec.b2 + n, invSg * __uint_as_float(bs[0]));
+            tmem_ld8(trow + cS4, bs); tmem_wait_ld(); atomicAdd(finish + 128 * 128 + n, invSg * __uint_as_float(bs[0]));
+            tmem_ld8(trow + cS1, bs); tmem_wait_ld(); atomicAdd(p.g_dec.b1 + n, invSg * __uint_as_float(bs[0]));
         }
     }
     fence_before_sync();
@@ -763,7 +828,7 @@ __global__ void __launch_bounds__(128, 1) k_debug_umma_bf(const float *__restric
         for (int i = threadIdx.x; i < N * K; i += 128) {
             const int n = i / K, k = i % K, st = k >> 4, kc = (k >> 3) & 1, e = k & 7;
             uint32_t hi, lo;
-            bf16_split2(B[i], 0.0f, hi, lo);
+            h16_split2(B[i], 0.0f, hi, lo);
             uint16_t *blk = s16 + st * (2 * N * 16);
             blk[kc * N * 8 + n * 8 + e] = (uint16_t)hi;
             blk[N * 16 + kc * N * 8 + n * 8 + e] = (uint16_t)lo;
@@ -775,7 +840,7 @@ __global__ void __launch_bounds__(128, 1) k_debug_umma_bf(const float *__restric
             const int j = isA ? i : i - K * 128, F = isA ? 128 : N;
             const int k = j / F, f = j % F;
             uint32_t hi, lo;
-            bf16_split2(isA ? A[j] : B[j], 0.0f, hi, lo);
+            h16_split2(isA ? A[j] : B[j], 0.0f, hi, lo);
             uint16_t *pl = s16 + (isA ? 0 : 2 * planeA);
             const int off = (k >> 3) * (F / 8) * 64 + (f >> 3) * 64 + (k & 7) * 8 + (f & 7);
             pl[off] = (uint16_t)hi;
@@ -792,7 +857,7 @@ __global__ void __launch_bounds__(128, 1) k_debug_umma_bf(const float *__restric
         for (int k0 = 0; k0 < K; k0 += 16) {
             uint32_t hi[8], lo[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) bf16_split2(A[(size_t)m * K + k0 + 2 * e], A[(size_t)m * K + k0 + 2 * e + 1], hi[e], lo[e]);
+            for (int e = 0; e < 8; ++e) h16_split2(A[(size_t)m * K + k0 + 2 * e], A[(size_t)m * K + k0 + 2 * e + 1], hi[e], lo[e]);
             tmem_st8(trow + k0 / 2, hi);
             tmem_st8(trow + 72 + k0 / 2, lo);
         }
@@ -804,22 +869,22 @@ __global__ void __launch_bounds__(128, 1) k_debug_umma_bf(const float *__restric
         fence_after_sync();
         const uint32_t sb = smem_u32(smem);
         if (mode == 0) {
-            const uint32_t id_lh = idesc_bf16(128, N), id_hl = id_lh, id_hh = id_lh;
+            const uint32_t id_lh = idesc_h16(128, N), id_hl = id_lh, id_hh = id_lh;
             for (int st = 0; st < K / 16; ++st) {
                 const uint64_t b_hi = sdesc(sb + st * (2 * N * 16 * 2), N * 16, 128);
                 const uint64_t b_lo = sdesc(sb + st * (2 * N * 16 * 2) + N * 16 * 2, N * 16, 128);
-                mma_bf16_ts(tmem + 144, tmem + 72 + st * 8, b_hi, id_lh, st ? 1u : 0u);
-                mma_bf16_ts(tmem + 144, tmem + st * 8, b_lo, id_hl, 1u);
-                mma_bf16_ts(tmem + 144, tmem + st * 8, b_hi, id_hh, 1u);
+                mma_h16_ts(tmem + 144, tmem + 72 + st * 8, b_hi, id_lh, st ? 1u : 0u);
+                mma_h16_ts(tmem + 144, tmem + st * 8, b_lo, id_hl, 1u);
+                mma_h16_ts(tmem + 144, tmem + st * 8, b_hi, id_hh, 1u);
             }
         } else {
-            const uint32_t id_lh = idesc_bf16(128, N, 1, 1), id_hl = id_lh, id_hh = id_lh;
+            const uint32_t id_lh = idesc_h16(128, N, 1, 1), id_hl = id_lh, id_hh = id_lh;
             const uint32_t lboA = 16 * 128, lboB = (N / 8) * 128;
             const uint32_t a_hi = sb, a_lo = sb + planeA * 2, b_hi = sb + planeA * 4, b_lo = b_hi + planeB * 2;
             for (int st = 0; st < K / 16; ++st) {
-                mma_bf16_ss(tmem + 144, sdesc(a_lo + st * 2 * lboA, lboA, 128), sdesc(b_hi + st * 2 * lboB, lboB, 128), id_lh, st ? 1u : 0u);
-                mma_bf16_ss(tmem + 144, sdesc(a_hi + st * 2 * lboA, lboA, 128), sdesc(b_lo + st * 2 * lboB, lboB, 128), id_hl, 1u);
-                mma_bf16_ss(tmem + 144, sdesc(a_hi + st * 2 * lboA, lboA, 128), sdesc(b_hi + st * 2 * lboB, lboB, 128), id_hh, 1u);
+                mma_h16_ss(tmem + 144, sdesc(a_lo + st * 2 * lboA, lboA, 128), sdesc(b_hi + st * 2 * lboB, lboB, 128), id_lh, st ? 1u : 0u);
+                mma_h16_ss(tmem + 144, sdesc(a_hi + st * 2 * lboA, lboA, 128), sdesc(b_lo + st * 2 * lboB, lboB, 128), id_hl, 1u);
+                mma_h16_ss(tmem + 144, sdesc(a_hi + st * 2 * lboA, lboA, 128), sdesc(b_hi + st * 2 * lboB, lboB, 128), id_hh, 1u);
             }
         }
         mma_commit(&bar);
@@ -848,17 +913,29 @@ int bf_pack_decoder(const pslam_decoder_t &d, float *ws_tc, cudaStream_t st)
     return 0;
 }
 
+// scratch = [tiles x kTileBytes operands][kFinishFloats][tiles x kMaskBytes ReLU masks]
 size_t bf_wgrad_scratch_bytes(int max_samples)
 {
-    return (size_t)ceil_div(max_samples > 0 ? max_samples : 1, 128) * bf::kTileBytes + bf::kFinishFloats * sizeof(float);
+    return (size_t)ceil_div(max_samples > 0 ? max_samples : 1, 128) * (bf::kTileBytes + bf::kMaskBytes) + bf::kFinishFloats * sizeof(float);
+}
+static unsigned char *scratch_finish(const FieldParams &fp, int max_samples)
+{
+    return fp.wg_scratch + (size_t)ceil_div(max_samples > 0 ? max_samples : 1, 128) * bf::kTileBytes;
 }
 
-template <bool BWD>
+// Which scratch holds the activations + masks of the most recent saving forward of a fused pipeline (stream-ordered
+// with the backward that consumes them), together with the sample outputs it wrote.  Only `paired` launches (both
+// from one pslam_render_t) save / consume; any other launch that writes the same scratch clears the record.
+static const void *g_saved_scratch = nullptr, *g_saved_out = nullptr;
+static int g_save_activations = 1;
+void bf_set_save_activations(int on) { g_save_activations = on ? 1 : 0; g_saved_scratch = nullptr; }
+
+template <int KIND>
 static int launch_bf(const FieldParams &fp, int max_samples, cudaStream_t st)
 {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_field_bf<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, bf::Smem<BWD>::bytes);
+        cudaError_t e = cudaFuncSetAttribute(k_field_bf<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, bf::Smem<KIND>::bytes);
         if (e != cudaSuccess) { set_error("field_bf: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         configured = true;
     }
@@ -868,25 +945,38 @@ static int launch_bf(const FieldParams &fp, int max_samples, cudaStream_t st)
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(num_sms() / bf::kCluster * bf::kCluster);
         cfg.blockDim = dim3(bf::kThreads);
-        cfg.dynamicSmemBytes = bf::Smem<BWD>::bytes;
+        cfg.dynamicSmemBytes = bf::Smem<KIND>::bytes;
         cudaLaunchAttribute attr;
         attr.id = cudaLaunchAttributeClusterDimension;
         attr.val.clusterDim.x = bf::kCluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
         cfg.attrs = &attr; cfg.numAttrs = 1;
         int n = 0;
-        cudaError_t e = cudaOccupancyMaxActiveClusters(&n, k_field_bf<BWD>, &cfg);
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&n, k_field_bf<KIND>, &cfg);
         if (e != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = num_sms() / bf::kCluster; }
         max_clusters = n < num_sms() / bf::kCluster ? n : num_sms() / bf::kCluster;
     }
     const int tiles = ceil_div(max_samples, 128);
     int grid = ceil_div(tiles > 0 ? tiles : 1, bf::kCluster) * bf::kCluster;
     if (grid > max_clusters * bf::kCluster) grid = max_clusters * bf::kCluster;
-    k_field_bf<BWD><<<grid, bf::kThreads, bf::Smem<BWD>::bytes, st>>>(fp, reinterpret_cast<const unsigned char *>(fp.ws_tc));
-    PSLAM_CHECK_LAUNCH(BWD ? "field_bf_backward" : "field_bf_forward");
+    k_field_bf<KIND><<<grid, bf::kThreads, bf::Smem<KIND>::bytes, st>>>(fp, reinterpret_cast<const unsigned char *>(fp.ws_tc));
+    static const char *names[4] = {"field_bf_forward", "field_bf_backward", "field_bf_forward_save", "field_bf_backward_saved"};
+    PSLAM_CHECK_LAUNCH(names[KIND]);
     return 0;
 }
 
-int bf_launch_field_forward(const FieldParams &fp, int max_samples, cudaStream_t st) { return launch_bf<false>(fp, max_samples, st); }
+// forward; with decoder gradients to follow (fp.grad_dec) and a scratch, it also spills its activations and ReLU masks
+int bf_launch_field_forward(const FieldParams &fp_in, int max_samples, cudaStream_t st)
+{
+    FieldParams fp = fp_in;
+    const bool save = g_save_activations && fp.paired && fp.grad_dec && fp.wg_scratch && fp.wg_scratch_bytes >= bf_wgrad_scratch_bytes(max_samples);
+    if (fp.wg_scratch && fp.wg_scratch == g_saved_scratch) g_saved_scratch = nullptr;
+    if (!save) return launch_bf<bf::kFwd>(fp, max_samples, st);
+    fp.act_masks = reinterpret_cast<uint32_t *>(scratch_finish(fp, max_samples) + bf::kFinishFloats * sizeof(float));
+    if (int rc = launch_bf<bf::kFwdSave>(fp, max_samples, st)) return rc;
+    g_saved_scratch = fp.wg_scratch;
+    g_saved_out = fp.out;
+    return 0;
+}
 
 // backward: dgrad chain (+ trilinear backward); when decoder gradients are wanted the scratch must be
 // provided and the wgrad kernel follows on the same stream
@@ -894,8 +984,22 @@ int bf_launch_field_backward(const FieldParams &fp_in, int max_samples, cudaStre
 {
     FieldParams fp = fp_in;
     if (!fp.grad_dec) fp.wg_scratch = nullptr;
-    if (part != 2)
-        if (int rc = launch_bf<true>(fp, max_samples, st)) return rc;
+    // per-launch gradient scale: 4 bytes at the end of the weight-stream region (the f16 stream fills only its first half)
+    fp.gscale = reinterpret_cast<uint32_t *>(const_cast<float *>(fp.ws_tc)) + kTcPackFloats - 4;
+    if (part != 2) {
+        cudaError_t e = cudaMemsetAsync(fp.gscale, 0, sizeof(uint32_t), st);
+        if (e != cudaSuccess) { set_error("field_bf: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
+        k_grad_scale<<<num_sms(), 256, 0, st>>>(reinterpret_cast<const float4 *>(fp.g_out), fp.nsamp, fp.nsamp_dev, fp.gscale);
+        PSLAM_CHECK_LAUNCH("grad_scale");
+        const bool saved = g_save_activations && fp.paired && fp.wg_scratch && fp.wg_scratch == g_saved_scratch && fp.out == g_saved_out;
+        if (!saved && fp.wg_scratch && fp.wg_scratch == g_saved_scratch) g_saved_scratch = nullptr;   // about to be overwritten
+        fp.act_masks = fp.wg_scratch ? reinterpret_cast<uint32_t *>(scratch_finish(fp, max_samples) + bf::kFinishFloats * sizeof(float)) : nullptr;
+        if (saved) {
+            if (int rc = launch_bf<bf::kBwdSaved>(fp, max_samples, st)) return rc;
+        } else {
+            if (int rc = launch_bf<bf::kBwdRecompute>(fp, max_samples, st)) return rc;
+        }
+    }
     if (!fp.grad_dec || part == 1) return 0;
     static bool configured = false;
     if (!configured) {
@@ -905,7 +1009,7 @@ int bf_launch_field_backward(const FieldParams &fp_in, int max_samples, cudaStre
     }
     const int tiles = ceil_div(max_samples > 0 ? max_samples : 1, 128);
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    float *finish = reinterpret_cast<float *>(fp.wg_scratch + (size_t)tiles * bf::kTileBytes);
+    float *finish = reinterpret_cast<float *>(scratch_finish(fp, max_samples));
     cudaError_t e = cudaMemsetAsync(finish, 0, bf::kFinishFloats * sizeof(float), st);
     if (e != cudaSuccess) { set_error("wgrad_bf: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
     k_wgrad_bf<<<grid, wgb::kThreads, wgb::kSmemBytes, st>>>(fp, finish);

@@ -214,8 +214,8 @@ __device__ __forceinline__ void tf32_split(float x, uint32_t &hi, uint32_t &lo)
 }
 
 
-// ---- kind::f16 (bf16 operands, fp32 accumulate): the "3xBF16" build (field_bf.cu) -------------
-// 8 consecutive columns of 32 lanes (16 packed bf16 values per lane)
+// ---- kind::f16 (two 16-bit halves per value, fp32 accumulate): the "3xF16" build (field_bf.cu) -------------
+// 8 consecutive columns of 32 lanes (16 packed 16-bit values per lane)
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8])
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -229,20 +229,22 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
                  "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
 }
-// instruction descriptor, kind::f16 with bf16 sources: a/b format = 1 (BF16), bit 15 / 16 = A / B is MN-major
-__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn = 0, int b_mn = 0)
+// instruction descriptor, kind::f16: a/b source format 0 = f16, 1 = bf16 (they must be EQUAL: measured on B200, an MMA
+// with a_format != b_format raises an illegal-instruction error); bit 15 / 16 = A / B is MN-major
+constexpr int kFmtF16 = 0, kFmtBF16 = 1;
+__host__ __device__ constexpr uint32_t idesc_h16(int M, int N, int a_mn = 0, int b_mn = 0, int fmt = kFmtF16)
 {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
-           ((uint32_t)(M >> 4) << 24);
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // generic no-swizzle shared-memory descriptor.  Core matrix = 8 x 16 B, 128 contiguous bytes.
-//   K-major : rows = M/N index, 16 B = 8 bf16 along K.   lbo = next 16 B along K,  sbo = next 8 rows along M/N
-//   MN-major: rows = K index,  16 B = 8 bf16 along M/N.  lbo = next 8 rows along K, sbo = next 16 B along M/N
+//   K-major : rows = M/N index, 16 B = 8 halves along K.   lbo = next 16 B along K,  sbo = next 8 rows along M/N
+//   MN-major: rows = K index,  16 B = 8 halves along M/N.  lbo = next 8 rows along K, sbo = next 16 B along M/N
 __device__ __forceinline__ uint64_t sdesc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo)
 {
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
 }
-__device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+__device__ __forceinline__ void mma_h16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -251,7 +253,7 @@ __device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
         ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
         : "memory");
 }
-__device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+__device__ __forceinline__ void mma_h16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -260,15 +262,19 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, ui
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
         : "memory");
 }
-// x = hi + lo (+ <= 2^-17 |x|) with hi = rn_bf16(x), lo = rn_bf16(x - hi), two values per 32-bit word
-// (element 0 in the low half).  a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi: relative error <= ~1e-5 per product.
-// (An f16 hi half with a bf16 lo half would give ~2^-21, but one kind::f16 MMA cannot mix source formats between
-// A and B: measured on B200, a_format != b_format raises an illegal-instruction error.)
-__device__ __forceinline__ void bf16_split2(float x0, float x1, uint32_t &hi, uint32_t &lo)
+// x = hi + lo with hi = rn_f16(x) and lo = rn_f16(x - hi), two values per 32-bit word (element 0 in the low half):
+// 22 significant bits while lo is a normal f16 (|x| >= 2^-3), an absolute error <= 2^-25 below that, saturating at
+// 65504.  The callers keep their operands in that window with power-of-two scales (field_bf.cu), so
+// a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi is fp32-equivalent (~2^-21 relative) at half the MMA count of 3xTF32.
+// (bf16 halves need no scaling but give 16 bits, ~1e-5 per product: measured 2e-4 on the rendered sdf -- outside the
+// 1e-4 parity bound -- and ReLU decisions flip 30x more often.)
+__device__ __forceinline__ void h16_split2(float x0, float x1, uint32_t &hi, uint32_t &lo)
 {
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
-    const float r0 = x0 - __uint_as_float(hi << 16), r1 = x1 - __uint_as_float(hi & 0xffff0000u);
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+    float h0, h1;
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(h0), "=f"(h1) : "r"(hi));
+    const float r0 = x0 - h0, r1 = x1 - h1;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
 }
 
 }  // namespace umma

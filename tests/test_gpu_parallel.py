@@ -43,9 +43,16 @@ def test_two_shards_close_to_one_padded_batch(device):
         pipe.forward()
         rows[r].copy_(pipe.loss_raw)
         pipes.append(pipe)
-    for pipe in pipes:
+    g_full = []
+    for pipe, out, sh in zip(pipes, outs, shards):
         pipe.finalize_loss(rows)
-        pipe.backward()
+        # = pipe.backward(), with the upstream gradient zeroed where a ReLU decision is within rounding of a tie (tests/util.py)
+        pipe.stage(4)
+        P = int(out["_dbg"]["sample_mask"].sum())
+        near = util.relu_near_samples(out, sh[0][None], sh[1][None], ms, dec, s.voxel_size, util.RELU_MARGIN["f16"])
+        g_full.append(pipe.samp_gout[:P].clone())
+        pipe.samp_gout[:P][near.to(device)] = 0.0
+        pipe.stage(5)
     torch.cuda.synchronize()
     assert pipes[0].losses() == pipes[1].losses()            # every rank closes the loss identically
     # one padded batch, oracle compositing on the GPU's own per-sample outputs (decision-proof, see test_gpu_pipeline)
@@ -70,9 +77,8 @@ def test_two_shards_close_to_one_padded_batch(device):
     assert abs(l["loss"] - float(loss)) <= TOL * abs(float(loss))
     for k in ("color_loss", "depth_loss", "fs_loss", "sdf_loss"):
         assert abs(l[k] - float(parts[k])) <= TOL * max(abs(float(parts[k])), 1e-12), k
-    for pipe, sdf_p, rgb_p in zip(pipes, sdf_ps, rgb_ps):
-        P = pipe.counts()["n_samples"]
-        g = pipe.samp_gout[:P].cpu()
+    for g, sdf_p, rgb_p in zip(g_full, sdf_ps, rgb_ps):
+        g = g.cpu()
         assert rel_err(g[:, 3], sdf_p.grad) < TOL and rel_err(g[:, :3], rgb_p.grad) < TOL
     # summed parameter gradients = oracle field backward fed with each shard's upstream gradient
     tot = None

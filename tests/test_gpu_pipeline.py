@@ -16,7 +16,7 @@ TOL = 1e-4
 
 
 def _run_pipeline(device, rays_o, rays_d, rgb, depth, ms, dec, *, voxel_size, step_size, truncation, max_distance,
-                  max_depth, weights, noise, tracking, grads=True):
+                  max_depth, weights, noise, tracking, grads=True, zero_upstream=None):
     from proud_slam_b200.pipeline import RenderPipeline
     R = rays_o.reshape(-1, 3).shape[0]
     pipe = RenderPipeline(R, device, samples_per_ray=96)
@@ -25,13 +25,28 @@ def _run_pipeline(device, rays_o, rays_d, rgb, depth, ms, dec, *, voxel_size, st
     pipe.bind(rays_o, rays_d, ms, dec, voxel_size=voxel_size, step_size=step_size, truncation=truncation,
               max_distance=max_distance, max_depth=max_depth, target_rgb=rgb, target_depth=depth, noise=noise,
               weights=weights, tracking=tracking, g_emb=g_emb, g_dec=g_dec, grad_rays=grads)
-    pipe.step()
+    if zero_upstream is None:
+        pipe.step()
+    else:
+        # same launches as step(), with the upstream gradient of the flagged samples zeroed before the field backward
+        pipe.sample()
+        pipe.forward()
+        pipe.stage(4)                                   # compositing backward -> samp_gout
+        pipe.g_full = pipe.samp_gout[:zero_upstream.numel()].clone()
+        pipe.samp_gout[:zero_upstream.numel()][zero_upstream.to(device)] = 0.0
+        pipe.stage(5)                                   # field backward
     torch.cuda.synchronize()
     return pipe, g_emb, g_dec
 
 
+@pytest.mark.parametrize("build", ["f16", "f16-recompute", "tf32"])
 @pytest.mark.parametrize("name", ["mapping_tiny", "tracking_tiny", "mapping_tiny_w256"])
-def test_step_matches_reference_golden(name, device):
+def test_step_matches_reference_golden(name, build, device):
+    with util.decoder_build(build.split("-")[0], save_activations=not build.endswith("recompute")):
+        _golden_step(name, device)
+
+
+def _golden_step(name, device):
     g = util.load_golden(name)
     ms = util.golden_map_states(g, device, requires_grad=False)
     dec = util.golden_decoder(g, device, requires_grad=False)
@@ -70,7 +85,7 @@ def test_step_matches_reference_golden(name, device):
     assert rel_err(pipe.g_rays_d[:R], g["g_rays_d"].reshape(-1, 3)) < TOL
 
 
-@pytest.mark.parametrize("decoder_build", ["tcgen05", "simt"])
+@pytest.mark.parametrize("decoder_build", ["f16", "f16-recompute", "tf32", "simt"])
 @pytest.mark.parametrize("kind,frames,rays,tracking,width", [
     ("tiny", 2, 300, False, 128),
     ("replica_small", 2, 1024, False, 128),       # BASELINE.json configs[0]: 2048 rays on the 0.2 m octree
@@ -93,7 +108,7 @@ def test_step_matches_oracle(kind, frames, rays, tracking, width, decoder_build,
          with the GPU's dL/d(sample outputs): 1e-4.
     """
     from proud_slam_b200 import _lib, scene as sc
-    if width == 256 and decoder_build == "tcgen05":
+    if width == 256 and decoder_build != "simt":
         pytest.skip("width 256 always runs the SIMT build")
     s, ms = util.build_scene(kind)
     dec = util.test_decoder(width=width, seed=1)
@@ -111,15 +126,13 @@ def test_step_matches_oracle(kind, frames, rays, tracking, width, decoder_build,
     msd["voxel_vertex_emb"] = msd["voxel_vertex_emb"].detach()
     decd = [p.detach().to(device) for p in dec]
     cw = (util.CRIT["rgb_weight"], util.CRIT["depth_weight"], util.CRIT["fs_weight"], util.CRIT["sdf_weight"])
-    lib = _lib.lib()
-    try:
-        _lib.check(lib.pslam_set_option(1, 0 if decoder_build == "tcgen05" else 1), "set_option")
+    near = util.relu_near_samples(out, rays_o.detach(), rays_d.detach(), ms, dec, s.voxel_size, util.RELU_MARGIN[decoder_build.split("-")[0]])
+    assert float(near.float().mean()) < 0.5
+    with util.decoder_build(decoder_build.split("-")[0], save_activations=not decoder_build.endswith("recompute")):
         pipe, g_emb, g_dec = _run_pipeline(
             device, rays_o.detach().to(device), rays_d.detach().to(device), rgb.to(device), depth.to(device), msd, decd,
             voxel_size=s.voxel_size, step_size=0.1 * s.voxel_size, truncation=util.CRIT["truncation"], max_distance=10.0,
-            max_depth=util.CRIT["max_depth"], weights=cw, noise=noise_d, tracking=tracking)
-    finally:
-        lib.pslam_set_option(1, 0)
+            max_depth=util.CRIT["max_depth"], weights=cw, noise=noise_d, tracking=tracking, zero_upstream=near)
     # ---- 1. bit-exact hit lists and samples
     inter, hits = pipe.intersections()
     hit_rows = hits.view(-1).cpu()
@@ -150,10 +163,11 @@ def test_step_matches_oracle(kind, frames, rays, tracking, width, decoder_build,
     assert abs(l["loss"] - float(loss)) <= TOL * abs(float(loss))
     for k in ("color_loss", "depth_loss", "fs_loss", "sdf_loss"):
         assert abs(l[k] - float(parts[k])) <= TOL * max(abs(float(parts[k])), 1e-12), k
-    g_so = pipe.samp_gout[:P].cpu()
+    g_so = pipe.g_full.cpu()
     assert rel_err(g_so[:, :3], rgb_p.grad) < TOL
     assert rel_err(g_so[:, 3], sdf_p.grad) < TOL
-    # ---- 4. field backward fed with the GPU's upstream gradient
+    # ---- 4. field backward fed with the GPU's upstream gradient (zero where a ReLU decision is within rounding of a tie)
+    g_so = pipe.samp_gout[:P].cpu()
     rgb_o, sdf_o = util.oracle_field(out, rays_o, rays_d, ms, dec, s.voxel_size)
     params = [ms["voxel_vertex_emb"], rays_o, rays_d] + list(dec)
     grads = torch.autograd.grad((rgb_o * g_so[:, :3]).sum() + (sdf_o * g_so[:, 3]).sum(), params)
@@ -163,6 +177,33 @@ def test_step_matches_oracle(kind, frames, rays, tracking, width, decoder_build,
     assert rel_err(pipe.g_rays_d[:R], grads[2].reshape(-1, 3)) < TOL
     for i in range(10):
         assert rel_err(g_dec[i], grads[3 + i]) < TOL, f"decoder grad {i}"
+
+
+def test_saved_activations_equal_recompute(device):
+    """3xF16 build: the backward that starts from the activations / ReLU masks spilled by the forward (kFwdSave +
+    kBwdSaved) gives the same gradients as the stand-alone backward that recomputes the forward (same arithmetic,
+    same decisions; only the order of the floating-point atomics differs)."""
+    from proud_slam_b200 import scene as sc
+    s, ms = util.build_scene("replica_small")
+    dec = util.test_decoder(width=128, seed=3)
+    rays_o, rays_d, rgb, depth = sc.sample_batch(s, [0, 1], 1024, seed=9)
+    msd = util.to_device(ms, device)
+    msd["voxel_vertex_emb"] = msd["voxel_vertex_emb"].detach()
+    decd = [p.detach().to(device) for p in dec]
+    noise = torch.rand(2048, 96, generator=torch.Generator().manual_seed(2)).clamp(0.001, 0.999).to(device)
+    cw = (util.CRIT["rgb_weight"], util.CRIT["depth_weight"], util.CRIT["fs_weight"], util.CRIT["sdf_weight"])
+    res = []
+    for save in (True, False):
+        with util.decoder_build("f16", save_activations=save):
+            pipe, g_emb, g_dec = _run_pipeline(
+                device, rays_o.to(device), rays_d.to(device), rgb.to(device), depth.to(device), msd, decd, voxel_size=s.voxel_size,
+                step_size=0.1 * s.voxel_size, truncation=util.CRIT["truncation"], max_distance=10.0, max_depth=util.CRIT["max_depth"],
+                weights=cw, noise=noise, tracking=False)
+        assert pipe.counts()["n_samples"] > 20000          # many tiles per CTA pair
+        res.append([g_emb.clone(), pipe.g_rays_o.clone(), pipe.g_rays_d.clone(), pipe.samp_out.clone()] + [g.clone() for g in g_dec])
+    assert torch.equal(res[0][3], res[1][3])               # forward outputs: bit-identical
+    for a, b in zip(res[0], res[1]):
+        assert rel_err(a, b) < 1e-5
 
 
 def test_hash_noise_is_in_range_and_deterministic(device):

@@ -1,4 +1,5 @@
 """Shared helpers for the test-suite (fixtures, scene construction, error metrics)."""
+import contextlib
 import os
 
 import numpy as np
@@ -246,6 +247,29 @@ def oracle_field(out, rays_o, rays_d, ms, dec, voxel_size):
     return ro.decoder_forward(dec, f)
 
 
+# ReLU'(0) is a hard decision: a pre-activation within a build's own rounding error of 0 flips one unit's mask between
+# two correct implementations and changes that sample's gradient by O(1) (the reference's fp32 has the same kink at its
+# own rounding level).  Backward comparisons therefore give such samples zero upstream gradient on both sides.
+RELU_MARGIN = {"tf32": 2e-6, "simt": 2e-6, "f16": 4e-6}
+
+
+def relu_near_samples(out, rays_o, rays_d, ms, dec, voxel_size, eps):
+    """bool [P]: samples (oracle / CSR order) with a decoder pre-activation closer to 0 than eps."""
+    with torch.no_grad():
+        smask = out["_dbg"]["sample_mask"]
+        rm = out["ray_mask"]
+        z = out["z_vals"]
+        xyz = rays_o[rm].reshape(-1, 3).unsqueeze(1) + rays_d[rm].reshape(-1, 3).unsqueeze(1) * z.unsqueeze(2)
+        sidx = out["_dbg"]["samples"]["sampled_point_voxel_idx"].long()
+        f = ro.get_features_vox(xyz[smask], sidx[smask], ms, voxel_size)
+        W1, b1, W2, b2, W3, b3, W4, b4, W5, b5 = [p.detach() for p in dec]
+        a1 = f @ W1.t() + b1
+        a2 = torch.relu(a1) @ W2.t() + b2
+        t = (torch.relu(a2) @ W3.t() + b3)[:, 1:]
+        a4 = torch.cat([t, f], 1) @ W4.t() + b4
+        return (a1.abs().min(1).values < eps) | (a2.abs().min(1).values < eps) | (a4.abs().min(1).values < eps)
+
+
 # ---------------------------------------------------------------- a frame like the reference's RGBDFrame
 class TestFrame:
     """Duck-type of reference ``src/frame.py:10-85`` for the loop tests: rays_d per pixel, rgb, depth,
@@ -273,3 +297,23 @@ class TestFrame:
         m = torch.zeros(self.rays_d.shape[0], dtype=torch.bool)
         m[idx] = True
         self.sample_mask = m.to(self.rays_d.device)
+
+
+# PSLAM_OPT_DECODER values (include/proud_slam_b200.h); the library default is the 3xF16 tensor-core build
+DECODER_BUILDS = {"tf32": 0, "simt": 1, "f16": 2}
+DEFAULT_DECODER_BUILD = int(os.environ.get("PSLAM_DECODER", "2"))
+
+
+@contextlib.contextmanager
+def decoder_build(build, save_activations=True):
+    """Selects the decoder build (name or option value) for a block and restores the defaults afterwards."""
+    from proud_slam_b200 import _lib
+    lib = _lib.lib()
+    mode = DECODER_BUILDS[build] if isinstance(build, str) else int(build)
+    _lib.check(lib.pslam_set_option(1, mode), "set_option")
+    _lib.check(lib.pslam_set_option(2, 1 if save_activations else 0), "set_option")
+    try:
+        yield mode
+    finally:
+        lib.pslam_set_option(1, DEFAULT_DECODER_BUILD)
+        lib.pslam_set_option(2, 1)
