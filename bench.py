@@ -293,7 +293,7 @@ def run_gpu(args):
         kname, ktext, dtype = {
             0: ("k_field_tc<bwd>", "tcgen05 3xTF32", "f32 (3xTF32 split, f32 accumulate)"),
             1: ("k_field<128,bwd>", "fp32 SIMT", "f32"),
-            2: ("k_field_bf<bwd>", "tcgen05 3xBF16", "bf16x3 (hi/lo bf16 split, f32 accumulate)")}[build]
+            2: ("k_field_bf<kBwdSaved>", "tcgen05 3xF16", "f16x3 (f16 hi/lo split with power-of-two scales, f32 accumulate)")}[build]
         # dominant kernel: k_field_tc<bwd> (forward recompute + dgrad chain + trilinear backward + scratch spill);
         # algorithmic FLOPs = the dgrad GEMMs once (2 MACs P), neither the recompute nor the x3 of the TF32 split
         flops_bwd = 2.0 * macs_per_sample(WIDTH) * P
@@ -314,7 +314,7 @@ def run_gpu(args):
                     "h2d_bytes_per_step": int(sum(t.numel() * 4 for t in host)), "d2h_bytes_per_step": 64},
             "gpu_launches": args.steps * 19,
             "clocks": clocks,
-            "roofline": {"kernel": f"{kname} ({ktext}: decoder recompute + dgrad, fused trilinear backward, wgrad spill)", "bound": "tensor",
+            "roofline": {"kernel": f"{kname} ({ktext}: " + ("dgrad chain from the forward's saved ReLU masks" if build == 2 else "decoder recompute + dgrad") + ", fused trilinear backward, wgrad spill)", "bound": "tensor",
                          "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
                          "traffic": NCU_TRAFFIC.get(build) if (P > 190000 and P < 194000) else None,   # dram read+write per launch, ncu --set full (profiles/)
                          "peak_source": peaks["source"] + ", dense bf16 burst (the kernel issues 3 split MMAs per product and recomputes the "

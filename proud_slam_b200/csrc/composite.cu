@@ -50,14 +50,14 @@ __device__ __forceinline__ int first_sign_change(const float *__restrict__ out, 
 __global__ void __launch_bounds__(kCompThreads)
 k_composite_fwd(pslam_render_t p, float *__restrict__ part_f, int *__restrict__ part_i)
 {
-    __shared__ float s_f[kCompWarps][5];
-    __shared__ int s_i[kCompWarps][6];
+    __shared__ float s_f[kCompWarps][6];
+    __shared__ int s_i[kCompWarps][7];
     const int Rh = p.counters[PSLAM_C_RH];
     const int S = p.counters[PSLAM_C_S];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = blockIdx.x * kCompWarps + warp;
-    float sum_color = 0.f, sum_fs = 0.f, sum_sdf = 0.f;
-    int n_fs = 0, n_sdf = 0;
+    float sum_color = 0.f, sum_fs = 0.f, sum_sdf = 0.f, sum_dep = 0.f;   // sum_dep / n_valid: depth loss without the tracking gate
+    int n_fs = 0, n_sdf = 0, n_valid = 0;
     // pad terms, linear in S so that they can be closed after a cross-rank max of S:
     //   pads of a ray = (S - cnt) copies of (z=10, sdf=1)  ->  S*x0 - x1 with x1 = x0*cnt
     float pad_d0 = 0.f, pad_d1 = 0.f;           // sum over rays of [sdf-mask pad] d^2 (and * cnt)
@@ -129,6 +129,7 @@ k_composite_fwd(pslam_render_t p, float *__restrict__ part_f, int *__restrict__ 
                 sum_color = fabsf(__ldg(tc) - r) + fabsf(__ldg(tc + 1) - g) + fabsf(__ldg(tc + 2) - b);
                 ro[6] = fabsf(gt - dep) / sqrtf(var + 1e-10f);
                 ro[7] = (gt > 0.01f && gt < p.max_depth) ? 1.0f : 0.0f;
+                if (ro[7] != 0.0f) { sum_dep = fabsf(gt - dep); n_valid = 1; }
             } else {
                 ro[6] = 0.0f; ro[7] = 0.0f;
             }
@@ -138,32 +139,45 @@ k_composite_fwd(pslam_render_t p, float *__restrict__ part_f, int *__restrict__ 
     }
     if (lane == 0) {
         s_f[warp][0] = sum_color; s_f[warp][1] = sum_fs; s_f[warp][2] = sum_sdf; s_f[warp][3] = pad_d0; s_f[warp][4] = pad_d1;
+        s_f[warp][5] = sum_dep;
         s_i[warp][0] = n_fs; s_i[warp][1] = n_sdf; s_i[warp][2] = pad_f0; s_i[warp][3] = pad_f1;
-        s_i[warp][4] = pad_m0; s_i[warp][5] = pad_m1;
+        s_i[warp][4] = pad_m0; s_i[warp][5] = pad_m1; s_i[warp][6] = n_valid;
     }
     __syncthreads();
-    if (threadIdx.x < 5) {
+    if (threadIdx.x < 6) {
         float t = 0.0f;
         for (int w = 0; w < kCompWarps; ++w) t += s_f[w][threadIdx.x];
         part_f[(size_t)blockIdx.x * 8 + threadIdx.x] = t;
-    } else if (threadIdx.x >= 8 && threadIdx.x < 14) {
+    } else if (threadIdx.x >= 8 && threadIdx.x < 15) {
         int t = 0;
         for (int w = 0; w < kCompWarps; ++w) t += s_i[w][threadIdx.x - 8];
         part_i[(size_t)blockIdx.x * 8 + threadIdx.x - 8] = t;
     }
 }
 
-// block-wide sum (1024 threads) in double, deterministic order
-__device__ __forceinline__ double block_sum_d(double v, double *s_buf)
+// block-wide sums (1024 threads) of N values in double, deterministic order; the totals are valid in thread 0 only
+template <int N>
+__device__ __forceinline__ void block_sums_d(double (&v)[N], double *s_buf /* [32][N] */, double *s_tot /* [N] */)
 {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    for (int k = 0; k < N; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    }
     __syncthreads();
-    if ((threadIdx.x & 31) == 0) s_buf[threadIdx.x >> 5] = v;
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) s_buf[(threadIdx.x >> 5) * N + k] = v[k];
+    }
     __syncthreads();
-    double t = 0.0;
-    for (int w = 0; w < 32; ++w) t += s_buf[w];
-    return t;
+    if (threadIdx.x < N) {
+        double t = 0.0;
+        for (int w = 0; w < 32; ++w) t += s_buf[w * N + threadIdx.x];
+        s_tot[threadIdx.x] = t;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = s_tot[k];
 }
 
 // Stage A of the loss: this rank's raw sums -> raw[16] (double).  Slots: see RAW_* below.
@@ -173,22 +187,22 @@ enum { RAW_COLOR = 0, RAW_FS, RAW_SDF, RAW_D0, RAW_D1, RAW_NFS, RAW_F0, RAW_F1, 
 __global__ void __launch_bounds__(1024)
 k_loss_reduce(pslam_render_t p, const float *__restrict__ part_f, const int *__restrict__ part_i, int nblocks)
 {
-    __shared__ double s_d[32];
+    __shared__ double s_d[32 * 13], s_tot[13];
     __shared__ unsigned s_hist[256];
     __shared__ unsigned s_prefix, s_rank;
     const int Rh = p.counters[PSLAM_C_RH];
     const int tid = threadIdx.x;
-    double f[5] = {0, 0, 0, 0, 0}, n[6] = {0, 0, 0, 0, 0, 0};
+    double acc[13];   // f[0..5] (colour, fs, sdf, pad d0, pad d1, ungated depth), n[0..6] (.., ungated valid count)
+#pragma unroll
+    for (int k = 0; k < 13; ++k) acc[k] = 0.0;
     for (int b = tid; b < nblocks; b += 1024) {
 #pragma unroll
-        for (int k = 0; k < 5; ++k) f[k] += (double)part_f[(size_t)b * 8 + k];
+        for (int k = 0; k < 6; ++k) acc[k] += (double)part_f[(size_t)b * 8 + k];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) n[k] += (double)part_i[(size_t)b * 8 + k];
+        for (int k = 0; k < 7; ++k) acc[6 + k] += (double)part_i[(size_t)b * 8 + k];
     }
-#pragma unroll
-    for (int k = 0; k < 5; ++k) f[k] = block_sum_d(f[k], s_d);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) n[k] = block_sum_d(n[k], s_d);
+    block_sums_d<13>(acc, s_d, s_tot);
+    const double *f = acc, *n = acc + 6;
 
     // tracking: lower median of tmp = |dd|/sqrt(var) over the hit rays (torch.median), by
     // 4 x 8-bit radix select on the float bit patterns (all values are >= 0)
@@ -220,15 +234,17 @@ k_loss_reduce(pslam_render_t p, const float *__restrict__ part_f, const int *__r
         }
         thresh = 10.0f * __uint_as_float(s_prefix);
     }
-    // depth loss over valid (and gated) rays, criterion.py:41-50
-    double dsum = 0.0, nvalid = 0.0;
-    for (int q = tid; q < Rh; q += 1024) {
-        const float *ro = p.ray_out + (size_t)q * 8;
-        const bool ok = ro[7] != 0.0f && (!(p.flags & PSLAM_F_TRACKING) || ro[6] < thresh);
-        if (ok) { dsum += (double)fabsf(__ldg(p.target_depth + p.hit_ray[q]) - ro[3]); nvalid += 1.0; }
+    // depth loss over valid (and gated) rays, criterion.py:41-50; without the tracking gate k_composite_fwd already summed it
+    double dn[2] = {f[5], n[6]};
+    if (p.flags & PSLAM_F_TRACKING) {
+        dn[0] = 0.0; dn[1] = 0.0;
+        for (int q = tid; q < Rh; q += 1024) {
+            const float *ro = p.ray_out + (size_t)q * 8;
+            if (ro[7] != 0.0f && ro[6] < thresh) { dn[0] += (double)fabsf(__ldg(p.target_depth + p.hit_ray[q]) - ro[3]); dn[1] += 1.0; }
+        }
+        block_sums_d<2>(dn, s_d, s_tot);
     }
-    dsum = block_sum_d(dsum, s_d);
-    nvalid = block_sum_d(nvalid, s_d);
+    const double dsum = dn[0], nvalid = dn[1];
     if (tid == 0) {
         double *raw = p.loss_raw;
         raw[RAW_COLOR] = f[0]; raw[RAW_FS] = f[1]; raw[RAW_SDF] = f[2]; raw[RAW_D0] = f[3]; raw[RAW_D1] = f[4];

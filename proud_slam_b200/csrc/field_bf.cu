@@ -780,29 +780,42 @@ __global__ void __launch_bounds__(wgb::kThreads, 1) k_wgrad_bf(FieldParams p, fl
 }
 
 // The gradients that go through M = G4^T H2 [128,128] and s4 = column sums of G4 (see the scratch layout):
-//   block j:  dW3[1+j][k] += sum_n W4[n][j] M[n][k]          db3[1+j] += sum_n W4[n][j] s4[n]
-//   block n:  dW4[n][j]   += sum_k M[n][k] W3[1+j][k] + s4[n] b3[1+j]          db4[n] += s4[n]
+//   blocks 0..127   (j):  dW3[1+j][k] += sum_n W4[n][j] M[n][k]          db3[1+j] += sum_n W4[n][j] s4[n]
+//   blocks 128..255 (n):  dW4[n][j]   += sum_k M[n][k] W3[1+j][k] + s4[n] b3[1+j]          db4[n] += s4[n]
 __global__ void __launch_bounds__(128) k_wgrad_finish(FieldParams p, const float *__restrict__ finish)
 {
-    __shared__ float sRow[128], sCol[128];
-    const int b = blockIdx.x, t = threadIdx.x;
+    __shared__ float sVec[128], sRed[4];
+    const int b = blockIdx.x & 127, t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const float *M = finish, *s4 = finish + 128 * 128;
-    sRow[t] = M[(size_t)b * 128 + t];                 // M[n = b][k = t]
-    sCol[t] = p.dec.W4[(size_t)t * 144 + b];          // W4[n = t][j = b]
-    __syncthreads();
-    float acc3 = 0.0f, acc4 = 0.0f;
-    for (int n = 0; n < 128; ++n) acc3 = fmaf(sCol[n], M[(size_t)n * 128 + t], acc3);
-    for (int k = 0; k < 128; ++k) acc4 = fmaf(sRow[k], p.dec.W3[(size_t)(1 + t) * 128 + k], acc4);
-    atomicAdd(p.g_dec.W3 + (size_t)(1 + b) * 128 + t, acc3);
-    atomicAdd(p.g_dec.W4 + (size_t)b * 144 + t, acc4 + s4[b] * p.dec.b3[1 + t]);
-    float v = sCol[t] * s4[t];                         // db3[1 + b] = sum_n W4[n][b] s4[n]
-    v = warp_sum(v);
-    __syncthreads();
-    if ((t & 31) == 0) sRow[t >> 5] = v;
-    __syncthreads();
-    if (t == 0) {
-        atomicAdd(p.g_dec.b3 + 1 + b, (sRow[0] + sRow[1]) + (sRow[2] + sRow[3]));
-        atomicAdd(p.g_dec.b4 + b, s4[b]);
+    if (blockIdx.x < 128) {
+        sVec[t] = p.dec.W4[(size_t)t * 144 + b];          // W4[n = t][j = b]
+        __syncthreads();
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;     // thread t = column k of M: coalesced rows, 4 independent chains
+        for (int n = 0; n < 128; n += 4) {
+            a0 = fmaf(sVec[n], M[(size_t)n * 128 + t], a0);
+            a1 = fmaf(sVec[n + 1], M[(size_t)(n + 1) * 128 + t], a1);
+            a2 = fmaf(sVec[n + 2], M[(size_t)(n + 2) * 128 + t], a2);
+            a3 = fmaf(sVec[n + 3], M[(size_t)(n + 3) * 128 + t], a3);
+        }
+        atomicAdd(p.g_dec.W3 + (size_t)(1 + b) * 128 + t, (a0 + a1) + (a2 + a3));
+        const float v = warp_sum(sVec[t] * s4[t]);        // db3[1 + b] = sum_n W4[n][b] s4[n]
+        if (lane == 0) sRed[warp] = v;
+        __syncthreads();
+        if (t == 0) atomicAdd(p.g_dec.b3 + 1 + b, (sRed[0] + sRed[1]) + (sRed[2] + sRed[3]));
+    } else {
+        sVec[t] = M[(size_t)b * 128 + t];                 // M[n = b][k = t]
+        __syncthreads();
+        const float sb = s4[b];
+        // warp w takes outputs j = w, w+4, ...: the lanes read one W3 row coalesced and reduce by shuffles
+        for (int j = warp; j < 128; j += 4) {
+            const float *row = p.dec.W3 + (size_t)(1 + j) * 128;
+            float a = sVec[lane] * row[lane] + sVec[lane + 32] * row[lane + 32];
+            a = fmaf(sVec[lane + 64], row[lane + 64], a);
+            a = fmaf(sVec[lane + 96], row[lane + 96], a);
+            a = warp_sum(a);
+            if (lane == 0) atomicAdd(p.g_dec.W4 + (size_t)b * 144 + j, a + sb * p.dec.b3[1 + j]);
+        }
+        if (t == 0) atomicAdd(p.g_dec.b4 + b, sb);
     }
 }
 
@@ -1014,7 +1027,7 @@ int bf_launch_field_backward(const FieldParams &fp_in, int max_samples, cudaStre
     if (e != cudaSuccess) { set_error("wgrad_bf: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
     k_wgrad_bf<<<grid, wgb::kThreads, wgb::kSmemBytes, st>>>(fp, finish);
     PSLAM_CHECK_LAUNCH("wgrad_bf");
-    k_wgrad_finish<<<128, 128, 0, st>>>(fp, finish);
+    k_wgrad_finish<<<256, 128, 0, st>>>(fp, finish);
     PSLAM_CHECK_LAUNCH("wgrad_finish");
     return 0;
 }
