@@ -28,9 +28,9 @@ using namespace umma;
 namespace bf {
 // warpgroup 0: warp 0 TMA producer, warp 1 MMA issuer, warp 2 scratch store, warp 3 idle; warpgroups 1-2: workers.
 // The split is by warpgroup so that setmaxnreg can move registers from the three single-lane roles to the
-// workers (56 vs 224 per thread): at the launch-time 168 the backward workers spilled inside the epilogues.
+// workers (64 vs 216 per thread): at the launch-time 168 the backward workers spilled inside the epilogues.
 constexpr int kThreads = 384;
-constexpr int kRegsIssue = 56, kRegsWorker = 224;
+constexpr int kRegsIssue = 64, kRegsWorker = 216;   // 128 x (168 - 64) registers released >= 256 x (216 - 168) acquired, else setmaxnreg.inc never returns
 constexpr int kWorkers = 256;
 constexpr int kStages = 8;        // weight ring depth of the forward kernel
 constexpr int kStagesBwd = 4;     // ... of the backward kernel (the rest of shared memory stages the wgrad scratch)
@@ -184,6 +184,82 @@ __device__ long long *g_bf_trace = nullptr;
         if (g_bf_trace && blockIdx.x == 0 && (tile_i) < 4) g_bf_trace[((tile_i) * 10 + (layer)) * 8 + (slot)] = clock64(); \
     } while (0)
 
+// The MMA-issuing thread's state and one layer of the chain: D[128 x N] = A[128 x K] * W^T as K/16 k-steps of three
+// MMAs (a_lo*b_hi, a_hi*b_lo, a_hi*b_hi), the weights arriving in chunks of <= 32 k through the ring.
+template <int NS>
+struct MmaIssuer {
+    unsigned char *smem;
+    uint64_t *full, *empty, *a_ready, *mma_done;
+    uint32_t tmem;
+    int stage, phase;
+    uint32_t uses;   // a_ready phase counter
+    template <int N, int K, int ACOL>
+    __device__ __forceinline__ void layer()
+    {
+        using namespace bf;
+        constexpr uint32_t idesc = idesc_h16(128, N);
+        mbar_wait(a_ready, uses & 1);
+        ++uses;
+        fence_after_sync();
+        uint32_t t = tmem;
+        asm volatile("" : "+r"(t));   // opaque: keeps the compiler from hoisting every layer's operand addresses out of the tile loop (64 registers here)
+        const uint32_t a_hi = t + cAHI + ACOL, a_lo = t + cALO + ACOL, d = t + cD;
+#pragma unroll
+        for (int k0 = 0; k0 < K; k0 += kChunkK) {
+            constexpr int kLast = (K - 1) / kChunkK * kChunkK;
+            const int kk = (K - k0) < kChunkK ? (K - k0) : kChunkK;      // constant after unrolling
+            mbar_wait(full + stage, phase);
+            fence_after_sync();
+            // descriptor of the chunk's first 16-byte k-chunk; the others are constant 16-byte-unit offsets from it
+            const uint64_t b0 = sdesc(smem_u32(smem + stage * kStageBytes), N * 16, 128);
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                if (s * 16 < kk) {
+                    const uint32_t acol = (uint32_t)(k0 + s * 16) >> 1;
+                    const uint64_t b_hi = b0 + (uint64_t)((s * (2 * N * 16)) >> 4);
+                    const uint64_t b_lo = b0 + (uint64_t)((N * kk * 2 + s * (2 * N * 16)) >> 4);
+                    mma_h16_ts(d, a_lo + acol, b_hi, idesc, (k0 | s) ? 1u : 0u);
+                    mma_h16_ts(d, a_hi + acol, b_lo, idesc, 1u);
+                    mma_h16_ts(d, a_hi + acol, b_hi, idesc, 1u);
+                }
+            }
+            mma_commit_mcast(empty + stage, kClusterMask);  // this CTA is done with the stage: tell every producer
+            if (k0 == kLast) mma_commit(mma_done);
+            if (++stage == NS) { stage = 0; phase ^= 1; }
+        }
+    }
+    // same with run-time N / K: the 10-layer stand-alone backward would not fit the issuer's 64 registers when unrolled
+    __device__ __forceinline__ void layer_rt(int N, int K, int acol0)
+    {
+        using namespace bf;
+        const uint32_t idesc = idesc_h16(128, N);
+        mbar_wait(a_ready, uses & 1);
+        ++uses;
+        fence_after_sync();
+        const uint32_t a_hi = tmem + cAHI + acol0, a_lo = tmem + cALO + acol0, d = tmem + cD;
+        for (int k0 = 0; k0 < K; k0 += kChunkK) {
+            const int kk = (K - k0) < kChunkK ? (K - k0) : kChunkK;
+            mbar_wait(full + stage, phase);
+            fence_after_sync();
+            const uint64_t b0 = sdesc(smem_u32(smem + stage * kStageBytes), N * 16, 128);
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                if (s * 16 < kk) {
+                    const uint32_t acol = (uint32_t)(k0 + s * 16) >> 1;
+                    const uint64_t b_hi = b0 + (uint64_t)((s * (2 * N * 16)) >> 4);
+                    const uint64_t b_lo = b0 + (uint64_t)((N * kk * 2 + s * (2 * N * 16)) >> 4);
+                    mma_h16_ts(d, a_lo + acol, b_hi, idesc, (k0 | s) ? 1u : 0u);
+                    mma_h16_ts(d, a_hi + acol, b_lo, idesc, 1u);
+                    mma_h16_ts(d, a_hi + acol, b_hi, idesc, 1u);
+                }
+            }
+            mma_commit_mcast(empty + stage, kClusterMask);
+            if (k0 + kChunkK >= K) mma_commit(mma_done);
+            if (++stage == NS) { stage = 0; phase ^= 1; }
+        }
+    }
+};
+
 template <int KIND>
 __global__ void __cluster_dims__(bf::kCluster, 1, 1) __launch_bounds__(bf::kThreads, 1)
 k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
@@ -261,46 +337,34 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (whole warp loops; one elected lane issues) =====================
-        int stage = 0, phase = 0;
-        uint32_t uses = 0;   // a_ready phase counter
-        int tile_i = 0;
-        for (int it = 0; it < iters; ++it, ++tile_i) {
-            for (int l = L0; l < L1; ++l) {
-                const int N = cN[l], K = cK[l];
-                const uint32_t idesc = idesc_h16(128, N);
-                if (lane == 0) BF_TRACE(tile_i, l, 0);          // MMA warp starts waiting for A
-                mbar_wait(a_ready, uses & 1);
-                ++uses;
-                fence_after_sync();
-                if (lane == 0) BF_TRACE(tile_i, l, 1);          // A ready seen
-                const uint32_t a_hi = tmem + cAHI + cAcol[l], a_lo = tmem + cALO + cAcol[l], d = tmem + cD;
-                for (int k0 = 0; k0 < K; k0 += kChunkK) {
-                    const int kk = (K - k0) < kChunkK ? (K - k0) : kChunkK;
-                    mbar_wait(full + stage, phase);
-                    fence_after_sync();
-                    const uint32_t sb = smem_u32(smem + stage * kStageBytes);
-                    if (elect_one()) {
-#pragma unroll
-                        for (int s = 0; s < 2; ++s) {
-                            if (s * 16 < kk) {
-                                const uint32_t acol = (uint32_t)(k0 + s * 16) >> 1;
-                                const uint64_t b_hi = sdesc(sb + s * (2 * N * 16), N * 16, 128);
-                                const uint64_t b_lo = sdesc(sb + N * kk * 2 + s * (2 * N * 16), N * 16, 128);
-                                mma_h16_ts(d, a_lo + acol, b_hi, idesc, (k0 | s) ? 1u : 0u);
-                                mma_h16_ts(d, a_hi + acol, b_lo, idesc, 1u);
-                                mma_h16_ts(d, a_hi + acol, b_hi, idesc, 1u);
-                            }
-                        }
-                        mma_commit_mcast(empty + stage, kClusterMask);  // this CTA is done with the stage: tell every producer
-                        if (k0 + kChunkK >= K) mma_commit(mma_done);
-                    }
-                    __syncwarp();
-                    if (++stage == NS) { stage = 0; phase ^= 1; }
+        // ===================== MMA issuer: ONE thread, every layer's chunk loop unrolled with its N / K as constants.
+        // The issue side is the critical path of a layer (6 MMAs of 64 clk per chunk against what it takes to wait for
+        // the chunk, build 4 descriptors and commit), so nothing here is warp-wide (no elect / re-convergence per chunk)
+        // and all descriptor arithmetic beyond "stage base + constant" folds at compile time. =====================
+        if (lane == 0) {
+            MmaIssuer<NS> mi{smem, full, empty, a_ready, mma_done, tmem, 0, 0, 0u};
+            for (int it = 0; it < iters; ++it) {
+                if constexpr (KIND == kBwdRecompute) {
+                    for (int l = 0; l < kLayersAll; ++l) { BF_TRACE(it, l, 0); mi.layer_rt(cN[l], cK[l], cAcol[l]); BF_TRACE(it, l, 2); }
+                    continue;
                 }
-                if (lane == 0) BF_TRACE(tile_i, l, 2);          // all MMAs of the layer issued + committed
+                if constexpr (kHasFwd) {
+                    BF_TRACE(it, 0, 0); mi.template layer<128, 16, 64>(); BF_TRACE(it, 0, 2);
+                    BF_TRACE(it, 1, 0); mi.template layer<128, 128, 0>(); BF_TRACE(it, 1, 2);
+                    BF_TRACE(it, 2, 0); mi.template layer<144, 128, 0>(); BF_TRACE(it, 2, 2);
+                    BF_TRACE(it, 3, 0); mi.template layer<128, 144, 0>(); BF_TRACE(it, 3, 2);
+                    BF_TRACE(it, 4, 0); mi.template layer<16, 128, 0>(); BF_TRACE(it, 4, 2);
+                }
+                if constexpr (kHasBwd) {
+                    BF_TRACE(it, 5, 0); mi.template layer<128, 16, 0>(); BF_TRACE(it, 5, 2);
+                    BF_TRACE(it, 6, 0); mi.template layer<144, 128, 0>(); BF_TRACE(it, 6, 2);
+                    BF_TRACE(it, 7, 0); mi.template layer<128, 144, 0>(); BF_TRACE(it, 7, 2);
+                    BF_TRACE(it, 8, 0); mi.template layer<128, 128, 0>(); BF_TRACE(it, 8, 2);
+                    BF_TRACE(it, 9, 0); mi.template layer<16, 128, 0>(); BF_TRACE(it, 9, 2);
+                }
             }
         }
+        __syncwarp();   // the warp must be converged again for the aligned cluster barrier at the end
     } else if (warp == 2) {
         // ===================== scratch store warp: staged operand (shared memory) -> wgrad scratch by bulk TMA =====================
         if (spill) {

@@ -38,7 +38,7 @@ def trace(fn, layers):
     t = buf.cpu()[:320].view(4, 10, 8); t0 = int(t[1, 0, 6])
     for l in range(layers):
         print("  layer", l, "mma_wait_start", int(t[1, l, 0]) - t0, "A_seen", int(t[1, l, 1]) - t0, "committed", int(t[1, l, 2]) - t0,
-              "D_seen", int(t[1, l, 3]) - t0, "A_next_produced", int(t[1, l + 1, 5]) - t0 if l < layers - 1 else "-")
+              "weight_wait", int(t[1, l, 4]), "D_seen", int(t[1, l, 3]) - t0, "A_next_produced", int(t[1, l + 1, 5]) - t0 if l < layers - 1 else "-")
     print("  next tile gather", int(t[2, 0, 6]) - t0)
 print("samples", n, "= tiles/CTA", tiles_per_cta)
 print("fwd ms", timed(fwd)); trace(fwd, 5)
