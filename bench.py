@@ -37,7 +37,7 @@ WIDTH = 128
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel at the bench workload (ncu --set full, profiles/*_summary.md)
-NCU_TRAFFIC = {0: 985.8e6, 2: 905.1e6}
+NCU_TRAFFIC = {0: 985.8e6, 2: 273.7e6}
 
 
 def macs_per_sample(w):
@@ -171,7 +171,8 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
-    s, ms_cpu, batch_cpu, n_oct, n_vox = build_workload(rank)
+    SCENE, RAYS_PER_FRAME = args.workload, args.rays // KEYFRAMES     # defaults = BASELINE.json configs[1]
+    s, ms_cpu, batch_cpu, n_oct, n_vox = build_workload(rank, rays_per_frame=RAYS_PER_FRAME, scene_kind=SCENE)
     ms = {k: v.to(device).contiguous() for k, v in ms_cpu.items()}
     dec = decoder_params(WIDTH, device)
     R = batch_cpu[0].shape[0]
@@ -184,7 +185,7 @@ def run_gpu(args):
     dev_in = [torch.empty_like(t, device=device) for t in batch_cpu]
     for d, h in zip(dev_in, host):
         d.copy_(h)
-    pipe = RenderPipeline(R, device, samples_per_ray=64)
+    pipe = RenderPipeline(R, device, samples_per_ray=64 if SCENE != "scannet_large" else 128)
     pipe.bind(dev_in[0], dev_in[1], ms, dec, voxel_size=s.voxel_size, step_size=0.1 * s.voxel_size, truncation=0.1,
               max_distance=10.0, max_depth=10.0, target_rgb=dev_in[2], target_depth=dev_in[3], noise=None, seed=1,
               weights=CRIT_W, g_emb=g_emb, g_dec=g_dec, grad_rays=True, defer_loss=(world > 1))
@@ -305,7 +306,7 @@ def run_gpu(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype,
             "data": "synthetic",
             "config": {"workload": f"{SCENE}: {KEYFRAMES} keyframes x {RAYS_PER_FRAME} rays = {R} rays/iter per GPU, {n_oct} octants "
-                                   f"({n_vox} voxels) at 0.2 m, {E}x16 embeddings, decoder width {WIDTH}, mapping fwd+bwd",
+                                   f"({n_vox} voxels) at {s.voxel_size:g} m, {E}x16 embeddings, decoder width {WIDTH} ({ktext}), mapping fwd+bwd",
                        "rays_per_gpu": R, "hit_rays": counts["R_h"], "samples_per_iter_per_gpu": P, "max_samples_per_ray": counts["S"],
                        "total_samples_all_gpus": total_samples, "l2": "flushed (192 MiB write) between timed iterations",
                        "parallelism": f"dp{world} (rays sharded, map replicated, grads all-reduced)" if world > 1 else "single GPU",
@@ -317,14 +318,16 @@ def run_gpu(args):
             "roofline": {"kernel": f"{kname} ({ktext}: " + ("dgrad chain from the forward's saved ReLU masks" if build == 2 else "decoder recompute + dgrad") + ", fused trilinear backward, wgrad spill)", "bound": "tensor",
                          "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
                          "traffic": NCU_TRAFFIC.get(build) if (P > 190000 and P < 194000) else None,   # dram read+write per launch, ncu --set full (profiles/)
-                         "peak_source": peaks["source"] + ", dense bf16 burst (the kernel issues 3 split MMAs per product and recomputes the "
-                                                        "forward: 6 hardware FLOPs per algorithmic FLOP, so frac <= 1/6 by construction)",
+                         "peak_source": peaks["source"] + ", dense bf16 burst; the kernel issues 3 split MMAs per product"
+                                        + (" (3 hardware FLOPs per algorithmic FLOP, so frac <= 1/3 by construction)" if build == 2 else
+                                           " and recomputes the forward (6 hardware FLOPs per algorithmic FLOP, so frac <= 1/6 by construction)"),
                          "algorithmic_flops_per_launch": flops_bwd, "kernel_ms": prof["field_bwd_dgrad_kernel"]},
             "stage_ms": prof,
         }
-        if world == 1:
+        if world == 1 and not args.no_extras:
             line["tracking"] = tracking_bench(s, ms, dec, device)
-        line["cpu_baseline"] = cpu_baseline(s, ms_cpu)
+        if not args.no_extras:
+            line["cpu_baseline"] = cpu_baseline(s, ms_cpu)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -432,6 +435,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    # sweeps (BASELINE.json configs[3], configs[4]); the defaults are the contract workload, configs[1]
+    ap.add_argument("--workload", default=SCENE, choices=["replica_20k", "replica_small", "scannet_large"])
+    ap.add_argument("--rays", type=int, default=KEYFRAMES * RAYS_PER_FRAME, help="rays per GPU and iteration (multiple of 8)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the tracking and CPU-baseline legs (sweeps)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
