@@ -15,11 +15,12 @@
 //     and in MMA order at the same 4 B/element as raw fp32.  The scratch is written in the MN-major
 //     (sample-major) core-matrix layout, so k_wgrad_bf is nothing but bulk-TMA loads feeding tcgen05.mma
 //     with both operands MN-major from shared memory: no transform warps, no transposition, no re-split.
-//   TMEM columns (k_field_bf): A_hi [0,72)  A_lo [72,144)  D [144,288).
+//   TMEM columns (k_field_bf): A_hi [0,72)  A_lo [72,144)  D0 [144,288)  D1 [288,432).
 #include "decoder_layers.cuh"
 #include "field.cuh"
 #include "kernels.h"
 #include "umma.cuh"
+#include <type_traits>
 
 namespace pslam {
 
@@ -40,13 +41,18 @@ constexpr int kStagingBytes = 65536; // one 128-feature operand of one tile in s
 constexpr int kCluster = 2;
 constexpr uint16_t kClusterMask = (1u << kCluster) - 1u;
 constexpr int kTmemCols = 512;
-constexpr int cAHI = 0, cALO = 72, cD = 144;
+constexpr int cAHI = 0, cALO = 72, cD = 144, kDCols = 144;   // two accumulator buffers D0 [144,288), D1 [288,432) alternate per layer
 // Power-of-two operand scales that keep the f16 halves in their precise window (umma.cuh: h16_split2).  Weights and
 // forward activations are stored x16 (|value| < 4094 representable; absolute resolution 2^-29): an accumulator then
 // holds 256 x the product and the epilogue folds 1/16 into its bias FMA, which leaves the next layer's operand
 // scaled x16 again.  Gradients carry a per-launch scale Sg = 2^k taken from max |g_out| (k_grad_scale) so that
 // the chain stays near 2^8; gradient accumulators hold 16 x Sg x the product.
 constexpr float kScale = 16.0f, kInvScale = 1.0f / 16.0f;
+// Order in which a layer's 32-wide k-chunks are streamed and issued.  An epilogue writes the next A operand in two
+// batches (k in [0,32) u [64,96), then [32,64) u [96,128): each row's two worker threads own 64 columns) and the
+// MMAs of the next layer start after the FIRST batch, so the chunks of the first batch come first: 0, 2, 1, 3, (4).
+__host__ __device__ constexpr int chunk_pos(int K, int c) { return K < 64 ? c : (c == 1 ? 2 : (c == 2 ? 1 : c)); }   // chunk c -> position
+__host__ __device__ constexpr int chunk_at(int K, int pos) { return chunk_pos(K, pos); }                              // (an involution)
 using declayers::kLayersAll;
 using declayers::kLayersFwd;
 __device__ __constant__ int cN[kLayersAll] = {128, 128, 144, 128, 16, 128, 144, 128, 128, 16};
@@ -64,7 +70,7 @@ struct Smem {
     static constexpr int nStages = BWD ? kStagesBwd : kStages;
     static constexpr int oStaging = nStages * kStageBytes;
     static constexpr int oBars = oStaging + (BWD ? 2 * kStagingBytes : 0);   // full[8], empty[8], a_ready, mma_done, st_full[2], st_free[2]
-    static constexpr int oTmemPtr = oBars + 8 * (2 * kStages + 2 + 4);
+    static constexpr int oTmemPtr = oBars + 8 * (2 * kStages + 3 + 4);   // ... a_ready[2], mma_done, st_full[2], st_free[2]
     static constexpr int oBias = oTmemPtr + 16;                     // b1[128] b2[128] b3f[128] b4[128] b3_0 b5[3]
     static constexpr int bytes = oBias + 4 * (4 * 128 + 4);
 };
@@ -98,7 +104,7 @@ __global__ void k_bf_pack(pslam_decoder_t d, uint16_t *__restrict__ out)
             const int kk = (K - c * bf::kChunkK) < bf::kChunkK ? (K - c * bf::kChunkK) : bf::kChunkK;
             uint32_t hi, lo;
             h16_split2(bf::kScale * tc_weight(d, l, n, k), 0.0f, hi, lo);
-            uint16_t *chunk = out + base + c * (N * bf::kChunkK * 2);
+            uint16_t *chunk = out + base + bf::chunk_pos(K, c) * (N * bf::kChunkK * 2);
             const int off = (kr >> 3) * (N * 8) + n * 8 + (kr & 7);
             chunk[off] = (uint16_t)(hi & 0xffffu);
             chunk[N * kk + off] = (uint16_t)(lo & 0xffffu);
@@ -141,40 +147,36 @@ __global__ void k_grad_scale(const float4 *__restrict__ g_out, int n, const int 
 //   MODE 2: y = mask ? D/16 : 0                                (dgrad through a ReLU; y = Sg x gradient)
 //   MODE 3: y = D/16                                           (dgrad, no activation)
 template <int MODE>
-__device__ __forceinline__ void bf_epilogue64(uint32_t trow, int col0, const float *bias, uint32_t (&mask)[2], unsigned char *stg)
+__device__ __forceinline__ void bf_epilogue32(uint32_t trow, uint32_t dcol, int c0, const float *bias, uint32_t &mask, unsigned char *stg)
 {
     using namespace bf;
+    uint32_t v[32];
+    tmem_ld32(trow + dcol + c0, v);
+    tmem_wait_ld();
+    uint32_t bits = 0u;
 #pragma unroll
-    for (int b = 0; b < 2; ++b) {   // fully unrolled: mask[] must stay in registers
-        const int c0 = col0 + 32 * b;
-        uint32_t v[32];
-        tmem_ld32(trow + cD + c0, v);
-        tmem_wait_ld();
-        uint32_t bits = 0u;
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-            float y = __uint_as_float(v[e]);
-            if (MODE == 0) { y = fmaxf(fmaf(y, kInvScale, bias[c0 + e]), 0.0f); bits |= (y > 0.0f ? 1u : 0u) << e; }
-            if (MODE == 1) y = fmaf(y, kInvScale, bias[c0 + e]);
-            if (MODE == 2) y = ((mask[b] >> e) & 1u) ? y * kInvScale : 0.0f;
-            if (MODE == 3) y = y * kInvScale;
-            v[e] = __float_as_uint(y);
-        }
-        if (MODE == 0) mask[b] = bits;
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) h16_split2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]), hi[e], lo[e]);
-        if (stg) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                unsigned char *dst = stg + (size_t)(c0 / 8 + j) * 128;
-                *reinterpret_cast<uint4 *>(dst) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                *reinterpret_cast<uint4 *>(dst + 16384) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-            }
-        }
-        tmem_st16(trow + cAHI + c0 / 2, hi);
-        tmem_st16(trow + cALO + c0 / 2, lo);
+    for (int e = 0; e < 32; ++e) {
+        float y = __uint_as_float(v[e]);
+        if (MODE == 0) { y = fmaxf(fmaf(y, kInvScale, bias[c0 + e]), 0.0f); bits |= (y > 0.0f ? 1u : 0u) << e; }
+        if (MODE == 1) y = fmaf(y, kInvScale, bias[c0 + e]);
+        if (MODE == 2) y = ((mask >> e) & 1u) ? y * kInvScale : 0.0f;
+        if (MODE == 3) y = y * kInvScale;
+        v[e] = __float_as_uint(y);
     }
+    if (MODE == 0) mask = bits;
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) h16_split2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]), hi[e], lo[e]);
+    if (stg) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            unsigned char *dst = stg + (size_t)(c0 / 8 + j) * 128;
+            *reinterpret_cast<uint4 *>(dst) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+            *reinterpret_cast<uint4 *>(dst + 16384) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+        }
+    }
+    tmem_st16(trow + cAHI + c0 / 2, hi);
+    tmem_st16(trow + cALO + c0 / 2, lo);
 }
 
 // optional timeline trace of CTA 0 (pslam_debug_bf_trace): [tile<4][layer<10][8] clock64 stamps (+ 40 x 8 for k_wgrad_bf)
@@ -185,79 +187,62 @@ __device__ long long *g_bf_trace = nullptr;
     } while (0)
 
 // The MMA-issuing thread's state and one layer of the chain: D[128 x N] = A[128 x K] * W^T as K/16 k-steps of three
-// MMAs (a_lo*b_hi, a_hi*b_lo, a_hi*b_hi), the weights arriving in chunks of <= 32 k through the ring.
+// MMAs (a_lo*b_hi, a_hi*b_lo, a_hi*b_hi), the weights arriving in chunks of <= 32 k through the ring in chunk_at()
+// order.  The workers publish the A operand in two halves (a_ready[0], a_ready[1]): the first two chunks are issued
+// while the second half of the previous epilogue is still running; D alternates between two accumulator buffers so
+// that this is safe.
 template <int NS>
 struct MmaIssuer {
     unsigned char *smem;
     uint64_t *full, *empty, *a_ready, *mma_done;
     uint32_t tmem;
     int stage, phase;
-    uint32_t uses;   // a_ready phase counter
-    template <int N, int K, int ACOL>
-    __device__ __forceinline__ void layer()
+    uint32_t uses;   // layers issued so far: a_ready phase and accumulator buffer
+    __device__ __forceinline__ void chunk(int N, int k0, int kk, uint32_t a_hi, uint32_t a_lo, uint32_t d, uint32_t idesc, bool first, bool last)
     {
         using namespace bf;
-        constexpr uint32_t idesc = idesc_h16(128, N);
-        mbar_wait(a_ready, uses & 1);
-        ++uses;
+        mbar_wait(full + stage, phase);
         fence_after_sync();
-        uint32_t t = tmem;
-        asm volatile("" : "+r"(t));   // opaque: keeps the compiler from hoisting every layer's operand addresses out of the tile loop (64 registers here)
-        const uint32_t a_hi = t + cAHI + ACOL, a_lo = t + cALO + ACOL, d = t + cD;
+        // descriptor of the chunk's first 16-byte k-chunk; the others are constant 16-byte-unit offsets from it
+        const uint64_t b0 = sdesc(smem_u32(smem + stage * kStageBytes), N * 16, 128);
 #pragma unroll
-        for (int k0 = 0; k0 < K; k0 += kChunkK) {
-            constexpr int kLast = (K - 1) / kChunkK * kChunkK;
-            const int kk = (K - k0) < kChunkK ? (K - k0) : kChunkK;      // constant after unrolling
-            mbar_wait(full + stage, phase);
-            fence_after_sync();
-            // descriptor of the chunk's first 16-byte k-chunk; the others are constant 16-byte-unit offsets from it
-            const uint64_t b0 = sdesc(smem_u32(smem + stage * kStageBytes), N * 16, 128);
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                if (s * 16 < kk) {
-                    const uint32_t acol = (uint32_t)(k0 + s * 16) >> 1;
-                    const uint64_t b_hi = b0 + (uint64_t)((s * (2 * N * 16)) >> 4);
-                    const uint64_t b_lo = b0 + (uint64_t)((N * kk * 2 + s * (2 * N * 16)) >> 4);
-                    mma_h16_ts(d, a_lo + acol, b_hi, idesc, (k0 | s) ? 1u : 0u);
-                    mma_h16_ts(d, a_hi + acol, b_lo, idesc, 1u);
-                    mma_h16_ts(d, a_hi + acol, b_hi, idesc, 1u);
-                }
+        for (int s = 0; s < 2; ++s) {
+            if (s * 16 < kk) {
+                const uint32_t acol = (uint32_t)(k0 + s * 16) >> 1;
+                const uint64_t b_hi = b0 + (uint64_t)((s * (2 * N * 16)) >> 4);
+                const uint64_t b_lo = b0 + (uint64_t)((N * kk * 2 + s * (2 * N * 16)) >> 4);
+                mma_h16_ts(d, a_lo + acol, b_hi, idesc, (first && s == 0) ? 0u : 1u);
+                mma_h16_ts(d, a_hi + acol, b_lo, idesc, 1u);
+                mma_h16_ts(d, a_hi + acol, b_hi, idesc, 1u);
             }
-            mma_commit_mcast(empty + stage, kClusterMask);  // this CTA is done with the stage: tell every producer
-            if (k0 == kLast) mma_commit(mma_done);
-            if (++stage == NS) { stage = 0; phase ^= 1; }
         }
+        mma_commit_mcast(empty + stage, kClusterMask);  // this CTA is done with the stage: tell every producer
+        if (last) mma_commit(mma_done);
+        if (++stage == NS) { stage = 0; phase ^= 1; }
     }
-    // same with run-time N / K: the 10-layer stand-alone backward would not fit the issuer's 64 registers when unrolled
     __device__ __forceinline__ void layer_rt(int N, int K, int acol0)
     {
         using namespace bf;
         const uint32_t idesc = idesc_h16(128, N);
+        uint32_t t = tmem;
+        asm volatile("" : "+r"(t));   // opaque: keeps the compiler from hoisting every layer's operand addresses out of the tile loop (64 registers here)
+        const uint32_t a_hi = t + cAHI + acol0, a_lo = t + cALO + acol0, d = t + cD + (uses & 1) * kDCols;
+        const int nch = (K + kChunkK - 1) / kChunkK;
         mbar_wait(a_ready, uses & 1);
-        ++uses;
         fence_after_sync();
-        const uint32_t a_hi = tmem + cAHI + acol0, a_lo = tmem + cALO + acol0, d = tmem + cD;
-        for (int k0 = 0; k0 < K; k0 += kChunkK) {
-            const int kk = (K - k0) < kChunkK ? (K - k0) : kChunkK;
-            mbar_wait(full + stage, phase);
-            fence_after_sync();
-            const uint64_t b0 = sdesc(smem_u32(smem + stage * kStageBytes), N * 16, 128);
+        if (K < 64) { mbar_wait(a_ready + 1, uses & 1); fence_after_sync(); }
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                if (s * 16 < kk) {
-                    const uint32_t acol = (uint32_t)(k0 + s * 16) >> 1;
-                    const uint64_t b_hi = b0 + (uint64_t)((s * (2 * N * 16)) >> 4);
-                    const uint64_t b_lo = b0 + (uint64_t)((N * kk * 2 + s * (2 * N * 16)) >> 4);
-                    mma_h16_ts(d, a_lo + acol, b_hi, idesc, (k0 | s) ? 1u : 0u);
-                    mma_h16_ts(d, a_hi + acol, b_lo, idesc, 1u);
-                    mma_h16_ts(d, a_hi + acol, b_hi, idesc, 1u);
-                }
+        for (int pos = 0; pos < 5; ++pos) {
+            if (pos < nch) {
+                if (pos == 2) { mbar_wait(a_ready + 1, uses & 1); fence_after_sync(); }   // second half of A (and k >= 128)
+                const int k0 = chunk_at(K, pos) * kChunkK;
+                chunk(N, k0, (K - k0) < kChunkK ? (K - k0) : kChunkK, a_hi, a_lo, d, idesc, pos == 0, pos == nch - 1);
             }
-            mma_commit_mcast(empty + stage, kClusterMask);
-            if (k0 + kChunkK >= K) mma_commit(mma_done);
-            if (++stage == NS) { stage = 0; phase ^= 1; }
         }
+        ++uses;
     }
+    template <int N, int K, int ACOL>
+    __device__ __forceinline__ void layer() { layer_rt(N, K, ACOL); }   // everything folds: N, K are constants here
 };
 
 template <int KIND>
@@ -272,8 +257,8 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + SM::oBars);
     uint64_t *empty = full + kStages;
-    uint64_t *a_ready = empty + kStages;
-    uint64_t *mma_done = a_ready + 1;
+    uint64_t *a_ready = empty + kStages;   // [2]: first / second half of the next A operand is in tensor memory
+    uint64_t *mma_done = a_ready + 2;
     uint64_t *st_full = mma_done + 1, *st_free = st_full + 2;
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(smem + SM::oTmemPtr);
     float *sBias = reinterpret_cast<float *>(smem + SM::oBias);
@@ -289,6 +274,7 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, kCluster); }
         mbar_init(a_ready, kWorkers);
+        mbar_init(a_ready + 1, kWorkers);
         mbar_init(mma_done, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(st_full + i, kWorkers); mbar_init(st_free + i, 1); }
         fence_barrier_init();
@@ -404,6 +390,8 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
         const int rowoff_small = (m >> 6) * 4096 + ((m >> 3) & 7) * 256 + (m & 7) * 16;
         uint32_t done_uses = 0;
         uint32_t nomask[2] = {0u, 0u};
+        uint32_t nlayers = 0;                         // layers consumed so far: which accumulator buffer the next layer_done() refers to
+        uint32_t dcol = cD;                           // accumulator buffer of the layer just completed
         const float Sg = kHasBwd ? grad_scale(p.gscale) : 1.0f, invSg = 1.0f / Sg;
         int tile_i = 0, lcount = L0 - 1;              // trace bookkeeping
         uint32_t sc = 0;                              // staged operands so far (two staging buffers alternate)
@@ -423,16 +411,36 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
         auto layer_done = [&]() {
             mbar_wait(mma_done, done_uses & 1);
             ++done_uses;
+            dcol = cD + (nlayers & 1) * kDCols;
+            ++nlayers;
             fence_after_sync();
             if (threadIdx.x == 128) BF_TRACE(tile_i, lcount, 3);     // worker sees the accumulators
         };
-        auto a_is_ready = [&]() {
+        auto a_half_ready = [&]() {                   // first half of the next A operand (k in [0,32) u [64,96)) is written
+            tmem_wait_st();
+            fence_before_sync();
+            mbar_arrive(a_ready);
+        };
+        auto a_is_ready = [&]() {                     // ... and the rest, including anything the lead thread adds (k >= 128)
             tmem_wait_st();
             fence_before_sync();
             if (threadIdx.x == 128) BF_TRACE(tile_i, lcount + 1, 5);  // worker has produced the A of layer lcount+1
-            mbar_arrive(a_ready);
+            mbar_arrive(a_ready + 1);
             ++lcount;
         };
+        // epilogue of one layer in two 32-column batches with the half-way signal between them
+        auto epilogue = [&](auto mode, const float *bias, uint32_t (&mask)[2], bool staged) {
+            constexpr int MODE = decltype(mode)::value;
+            unsigned char *stg = staged ? stage_begin() : nullptr;
+            if (threadIdx.x == 128) BF_TRACE(tile_i, lcount, 7);       // staging buffer is free
+            bf_epilogue32<MODE>(trow, dcol, col0, bias, mask[0], stg);
+            a_half_ready();
+            bf_epilogue32<MODE>(trow, dcol, col0 + 32, bias, mask[1], stg);
+            if (staged) stage_end();
+            if (threadIdx.x == 128) BF_TRACE(tile_i, lcount, 4);       // epilogue done (operand staged)
+        };
+        using M0 = std::integral_constant<int, 0>; using M1 = std::integral_constant<int, 1>;
+        using M2 = std::integral_constant<int, 2>; using M3 = std::integral_constant<int, 3>;
         for (int it = 0; it < iters; ++it, ++tile_i, lcount = L0 - 1) {
             const int tile = blockIdx.x + it * gridDim.x;
             real_tile = tile < ntiles;
@@ -502,33 +510,31 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
                 }
             }
             if constexpr (kHasFwd) {
+            a_half_ready();   // layer 1 (K = 16) reads only the features the lead thread just wrote: both halves at once
             a_is_ready();
             // ---- forward ----
             layer_done();
-            bf_epilogue64<0>(trow, col0, sBias, m1, stage_begin());                                     // h1
-            stage_end();
+            epilogue(M0{}, sBias, m1, true);                                                            // h1
             a_is_ready();
             layer_done();
-            bf_epilogue64<0>(trow, col0, sBias + 128, m2, stage_begin());                               // h2
-            stage_end();
+            epilogue(M0{}, sBias + 128, m2, true);                                                      // h2
             a_is_ready();
             layer_done();
-            bf_epilogue64<1>(trow, col0, sBias + 256, nomask, nullptr);                                 // t (no activation; not spilled)
+            epilogue(M1{}, sBias + 256, nomask, false);                                                 // t (no activation; not spilled)
             if (lead) {
                 uint32_t v[8];
-                tmem_ld8(trow + cD + 128, v);   // sdf = row 0 of W3, packed as output column 128
+                tmem_ld8(trow + dcol + 128, v);   // sdf = row 0 of W3, packed as output column 128
                 tmem_wait_ld();
                 sdf = fmaf(__uint_as_float(v[0]), kInvScale * kInvScale, sBias[512]);
             }
             a_is_ready();
             layer_done();
-            bf_epilogue64<0>(trow, col0, sBias + 384, mc, stage_begin());                               // hc
-            stage_end();
+            epilogue(M0{}, sBias + 384, mc, true);                                                      // hc
             a_is_ready();
             layer_done();
             if (lead) {
                 uint32_t v[8];
-                tmem_ld8(trow + cD, v);
+                tmem_ld8(trow + dcol, v);
                 tmem_wait_ld();
                 r = sigmoid_f(fmaf(__uint_as_float(v[0]), kInvScale * kInvScale, sBias[513]));
                 g = sigmoid_f(fmaf(__uint_as_float(v[1]), kInvScale * kInvScale, sBias[514]));
@@ -583,19 +589,19 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
                     }
                 }
             }
+            a_half_ready();   // D5 (K = 16) reads only g5
             a_is_ready();
             layer_done();
-            bf_epilogue64<2>(trow, col0, nullptr, mc, stage_begin());                                   // g_hc
-            stage_end();
+            epilogue(M2{}, nullptr, mc, true);                                                          // g_hc
             a_is_ready();
             layer_done();
-            bf_epilogue64<3>(trow, col0, nullptr, nomask, nullptr);                                     // g_t (not spilled)
+            epilogue(M3{}, nullptr, nomask, false);                                                     // g_t (not spilled)
             float gf[16];
 #pragma unroll
             for (int e = 0; e < 16; ++e) gf[e] = 0.0f;
             if (lead) {
                 uint32_t v[16], hi[8], lo[8];
-                tmem_ld16(trow + cD + 128, v);   // g_f, part through W4's last 16 input columns
+                tmem_ld16(trow + dcol + 128, v);   // g_f, part through W4's last 16 input columns
                 tmem_wait_ld();
 #pragma unroll
                 for (int e = 0; e < 16; ++e) gf[e] = __uint_as_float(v[e]);      // 16 x Sg x g_f (first part)
@@ -607,18 +613,16 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
             }
             a_is_ready();
             layer_done();
-            bf_epilogue64<2>(trow, col0, nullptr, m2, stage_begin());                                   // g_h2
-            stage_end();
+            epilogue(M2{}, nullptr, m2, true);                                                          // g_h2
             a_is_ready();
             layer_done();
-            bf_epilogue64<2>(trow, col0, nullptr, m1, stage_begin());                                   // g_h1
-            stage_end();
+            epilogue(M2{}, nullptr, m1, true);                                                          // g_h1
             a_is_ready();
             layer_done();
             if (!lead) continue;
             {
                 uint32_t v[16];
-                tmem_ld16(trow + cD, v);
+                tmem_ld16(trow + dcol, v);
                 tmem_wait_ld();
 #pragma unroll
                 for (int e = 0; e < 16; ++e) gf[e] = (gf[e] + __uint_as_float(v[e])) * (kInvScale * invSg);   // unscaled g_f
@@ -671,6 +675,84 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
     __syncthreads();
     cluster_sync();   // no CTA leaves while a peer may still multicast into its shared memory or signal its barriers
     if (warp == 0) tmem_dealloc(tmem, bf::kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel 3 split off the tensor-core kernels for the fused pipeline.  The trilinear lookup is three dependent
+// gathers per sample (sample -> voxel -> 8 corner rows -> 8 x 64 B) and its backward 32 vector reductions per
+// sample; inside k_field_bf they ran on the 128 lead threads with nothing to overlap them, between two tiles'
+// MMAs (traces: 6k of a 21k-clock forward tile, 19k of a 33k-clock backward tile).  As kernels of their own they
+// have the whole GPU's memory-level parallelism (4 threads per sample, one 16-byte quarter of the feature row each)
+// and the tensor-core kernels read / write plain [P,16] rows (64 B per sample, L2-resident at the mapping sizes).
+// Arithmetic and corner order are those of the fused path, so the features are bit-identical.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sample_position(const FieldParams &p, int s, int &vox, int &ray, float &z, float &px, float &py, float &pz)
+{
+    vox = __ldg(p.samp_vox + s);
+    z = __ldg(p.samp_z + s);
+    ray = __ldg(p.hit_ray + __ldg(p.samp_ray + s));
+    const float x = __fadd_rn(__ldg(p.rays_o + ray * 3 + 0), __fmul_rn(__ldg(p.rays_d + ray * 3 + 0), z));
+    const float y = __fadd_rn(__ldg(p.rays_o + ray * 3 + 1), __fmul_rn(__ldg(p.rays_d + ray * 3 + 1), z));
+    const float zz = __fadd_rn(__ldg(p.rays_o + ray * 3 + 2), __fmul_rn(__ldg(p.rays_d + ray * 3 + 2), z));
+    px = __fadd_rn(__fdiv_rn(__fsub_rn(x, __ldg(p.centres + (size_t)vox * 3 + 0)), p.voxel_size), 0.5f);
+    py = __fadd_rn(__fdiv_rn(__fsub_rn(y, __ldg(p.centres + (size_t)vox * 3 + 1)), p.voxel_size), 0.5f);
+    pz = __fadd_rn(__fdiv_rn(__fsub_rn(zz, __ldg(p.centres + (size_t)vox * 3 + 2)), p.voxel_size), 0.5f);
+}
+
+__global__ void __launch_bounds__(256) k_tri_gather(FieldParams p, float *__restrict__ feat)
+{
+    const int nsamp = p.nsamp_dev ? *p.nsamp_dev : p.nsamp;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = t >> 2, c = t & 3;
+    if (s >= nsamp) return;
+    int vox, ray;
+    float z, px, py, pz;
+    sample_position(p, s, vox, ray, z, px, py, pz);
+    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = __ldg(p.vertex_idx + (size_t)vox * 8 + i);
+        const float wx = (i & 4) ? px : 1.0f - px, wy = (i & 2) ? py : 1.0f - py, wz = (i & 1) ? pz : 1.0f - pz;
+        const float w = (wx * wy) * wz;
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(p.emb + (size_t)row * 16 + c * 4));
+        f.x = fmaf(w, v.x, f.x); f.y = fmaf(w, v.y, f.y); f.z = fmaf(w, v.z, f.z); f.w = fmaf(w, v.w, f.w);
+    }
+    *reinterpret_cast<float4 *>(feat + (size_t)s * 16 + c * 4) = f;
+}
+
+__global__ void __launch_bounds__(256) k_tri_scatter(FieldParams p, const float *__restrict__ g_feat)
+{
+    const int nsamp = p.nsamp_dev ? *p.nsamp_dev : p.nsamp;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = min(t >> 2, nsamp - 1), c = t & 3;
+    const bool live = (t >> 2) < nsamp;
+    if (nsamp <= 0 || __all_sync(0xffffffffu, !live)) return;     // whole warps leave; partial warps keep their shuffles converged
+    int vox, ray;
+    float z, px, py, pz;
+    sample_position(p, s, vox, ray, z, px, py, pz);
+    const float4 g = __ldg(reinterpret_cast<const float4 *>(g_feat + (size_t)s * 16 + c * 4));
+    float gp[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = __ldg(p.vertex_idx + (size_t)vox * 8 + i);
+        const float wx = (i & 4) ? px : 1.0f - px, wy = (i & 2) ? py : 1.0f - py, wz = (i & 1) ? pz : 1.0f - pz;
+        const float w = (wx * wy) * wz;
+        if (p.grad_emb && live) red_add_v4(p.g_emb + (size_t)row * 16 + c * 4, w * g.x, w * g.y, w * g.z, w * g.w);
+        if (p.grad_rays) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(p.emb + (size_t)row * 16 + c * 4));
+            float d = fmaf(g.w, v.w, fmaf(g.z, v.z, fmaf(g.y, v.y, g.x * v.x)));
+            d += __shfl_xor_sync(0xffffffffu, d, 1, 4);
+            d += __shfl_xor_sync(0xffffffffu, d, 2, 4);
+            gp[0] += d * ((i & 4) ? 1.0f : -1.0f) * (wy * wz);
+            gp[1] += d * ((i & 2) ? 1.0f : -1.0f) * (wx * wz);
+            gp[2] += d * ((i & 1) ? 1.0f : -1.0f) * (wx * wy);
+        }
+    }
+    if (p.grad_rays && live && c < 3) {
+        const float gx = gp[c] / p.voxel_size;
+        atomicAdd(p.g_rays_o + ray * 3 + c, gx);
+        atomicAdd(p.g_rays_d + ray * 3 + c, z * gx);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -990,10 +1072,31 @@ int bf_pack_decoder(const pslam_decoder_t &d, float *ws_tc, cudaStream_t st)
     return 0;
 }
 
-// scratch = [tiles x kTileBytes operands][kFinishFloats][tiles x kMaskBytes ReLU masks]
+// scratch = [tiles x kTileBytes operands][kFinishFloats][tiles x kMaskBytes ReLU masks][tiles x 8 kB features][tiles x 8 kB feature gradients]
+constexpr size_t kFeatTileBytes = 128 * 16 * sizeof(float);
 size_t bf_wgrad_scratch_bytes(int max_samples)
 {
-    return (size_t)ceil_div(max_samples > 0 ? max_samples : 1, 128) * (bf::kTileBytes + bf::kMaskBytes) + bf::kFinishFloats * sizeof(float);
+    return (size_t)ceil_div(max_samples > 0 ? max_samples : 1, 128) * (bf::kTileBytes + bf::kMaskBytes + 2 * kFeatTileBytes) +
+           bf::kFinishFloats * sizeof(float);
+}
+static float *scratch_feat(const FieldParams &fp, int max_samples, int which)   // 0: features, 1: their gradients
+{
+    const size_t tiles = (size_t)ceil_div(max_samples > 0 ? max_samples : 1, 128);
+    return reinterpret_cast<float *>(fp.wg_scratch + tiles * (bf::kTileBytes + bf::kMaskBytes) + bf::kFinishFloats * sizeof(float) +
+                                     (size_t)which * tiles * kFeatTileBytes);
+}
+// the fused pipeline with a workspace runs the trilinear stages as kernels of their own (k_tri_gather / k_tri_scatter)
+static bool split_trilinear(const FieldParams &fp, int max_samples)
+{
+    return fp.paired && !fp.feat && fp.wg_scratch && fp.wg_scratch_bytes >= bf_wgrad_scratch_bytes(max_samples);
+}
+static int launch_tri_gather(FieldParams &fp, int max_samples, cudaStream_t st)
+{
+    float *feat = scratch_feat(fp, max_samples, 0);
+    k_tri_gather<<<(int)ceil_div64((int64_t)(max_samples > 0 ? max_samples : 1) * 4, 256), 256, 0, st>>>(fp, feat);
+    PSLAM_CHECK_LAUNCH("tri_gather");
+    fp.feat = feat;
+    return 0;
 }
 static unsigned char *scratch_finish(const FieldParams &fp, int max_samples)
 {
@@ -1047,6 +1150,8 @@ int bf_launch_field_forward(const FieldParams &fp_in, int max_samples, cudaStrea
     FieldParams fp = fp_in;
     const bool save = g_save_activations && fp.paired && fp.grad_dec && fp.wg_scratch && fp.wg_scratch_bytes >= bf_wgrad_scratch_bytes(max_samples);
     if (fp.wg_scratch && fp.wg_scratch == g_saved_scratch) g_saved_scratch = nullptr;
+    if (split_trilinear(fp, max_samples))
+        if (int rc = launch_tri_gather(fp, max_samples, st)) return rc;
     if (!save) return launch_bf<bf::kFwd>(fp, max_samples, st);
     fp.act_masks = reinterpret_cast<uint32_t *>(scratch_finish(fp, max_samples) + bf::kFinishFloats * sizeof(float));
     if (int rc = launch_bf<bf::kFwdSave>(fp, max_samples, st)) return rc;
@@ -1071,10 +1176,21 @@ int bf_launch_field_backward(const FieldParams &fp_in, int max_samples, cudaStre
         const bool saved = g_save_activations && fp.paired && fp.wg_scratch && fp.wg_scratch == g_saved_scratch && fp.out == g_saved_out;
         if (!saved && fp.wg_scratch && fp.wg_scratch == g_saved_scratch) g_saved_scratch = nullptr;   // about to be overwritten
         fp.act_masks = fp.wg_scratch ? reinterpret_cast<uint32_t *>(scratch_finish(fp, max_samples) + bf::kFinishFloats * sizeof(float)) : nullptr;
+        const bool split = split_trilinear(fp, max_samples);
+        FieldParams fps = fp;                           // the scatter kernel wants the sample tables, not the feature rows
+        if (split) {
+            if (saved) fp.feat = scratch_feat(fp, max_samples, 0);          // (not read: marks the trilinear stages as external)
+            else if (int rc = launch_tri_gather(fp, max_samples, st)) return rc;   // the recompute needs the features again
+            fp.g_feat = scratch_feat(fp, max_samples, 1);
+        }
         if (saved) {
             if (int rc = launch_bf<bf::kBwdSaved>(fp, max_samples, st)) return rc;
         } else {
             if (int rc = launch_bf<bf::kBwdRecompute>(fp, max_samples, st)) return rc;
+        }
+        if (split && (fp.grad_emb || fp.grad_rays)) {
+            k_tri_scatter<<<(int)ceil_div64((int64_t)(max_samples > 0 ? max_samples : 1) * 4, 256), 256, 0, st>>>(fps, fp.g_feat);
+            PSLAM_CHECK_LAUNCH("tri_scatter");
         }
     }
     if (!fp.grad_dec || part == 1) return 0;
