@@ -48,11 +48,14 @@ constexpr int cAHI = 0, cALO = 72, cD = 144, kDCols = 144;   // two accumulator 
 // scaled x16 again.  Gradients carry a per-launch scale Sg = 2^k taken from max |g_out| (k_grad_scale) so that
 // the chain stays near 2^8; gradient accumulators hold 16 x Sg x the product.
 constexpr float kScale = 16.0f, kInvScale = 1.0f / 16.0f;
-// Order in which a layer's 32-wide k-chunks are streamed and issued.  An epilogue writes the next A operand in two
-// batches (k in [0,32) u [64,96), then [32,64) u [96,128): each row's two worker threads own 64 columns) and the
-// MMAs of the next layer start after the FIRST batch, so the chunks of the first batch come first: 0, 2, 1, 3, (4).
-__host__ __device__ constexpr int chunk_pos(int K, int c) { return K < 64 ? c : (c == 1 ? 2 : (c == 2 ? 1 : c)); }   // chunk c -> position
-__host__ __device__ constexpr int chunk_at(int K, int pos) { return chunk_pos(K, pos); }                              // (an involution)
+// Weight chunks follow the order in which the A operand becomes available.  An epilogue writes the next A in four
+// batches of 16 columns per thread; each row has two worker threads (columns [0,64) and [64,128)), so batch j
+// completes the k-steps j and j + 4 (k in [16j, 16j+16) and [64+16j, 64+16j+16)).  Chunk j of a layer therefore holds
+// exactly those two k-steps and its MMAs are issued as soon as a_ready[j] fires, while the epilogue is still
+// producing the later batches; chunk 4 (K = 144) holds k-step 8, K = 16 layers have the single chunk 0.
+__host__ __device__ constexpr int kstep_chunk(int K, int ks) { return (K < 64 || ks >= 8) ? (K < 64 ? 0 : 4) : (ks & 3); }
+__host__ __device__ constexpr int kstep_slot(int K, int ks) { return (K < 64 || ks >= 8) ? 0 : (ks >> 2); }
+__host__ __device__ constexpr int chunk_kk(int K, int c) { return (K < 64 || c == 4) ? 16 : 32; }
 using declayers::kLayersAll;
 using declayers::kLayersFwd;
 __device__ __constant__ int cN[kLayersAll] = {128, 128, 144, 128, 16, 128, 144, 128, 128, 16};
@@ -70,7 +73,7 @@ struct Smem {
     static constexpr int nStages = BWD ? kStagesBwd : kStages;
     static constexpr int oStaging = nStages * kStageBytes;
     static constexpr int oBars = oStaging + (BWD ? 2 * kStagingBytes : 0);   // full[8], empty[8], a_ready, mma_done, st_full[2], st_free[2]
-    static constexpr int oTmemPtr = oBars + 8 * (2 * kStages + 3 + 4);   // ... a_ready[2], mma_done, st_full[2], st_free[2]
+    static constexpr int oTmemPtr = oBars + 8 * (2 * kStages + 5 + 4);   // ... a_ready[4], mma_done, st_full[2], st_free[2]
     static constexpr int oBias = oTmemPtr + 16;                     // b1[128] b2[128] b3f[128] b4[128] b3_0 b5[3]
     static constexpr int bytes = oBias + 4 * (4 * 128 + 4);
 };
@@ -100,11 +103,11 @@ __global__ void k_bf_pack(pslam_decoder_t d, uint16_t *__restrict__ out)
         const int N = bf::cN[l], K = bf::cK[l];
         if (i < N * K) {
             const int n = i / K, k = i % K;
-            const int c = k / bf::kChunkK, kr = k % bf::kChunkK;
-            const int kk = (K - c * bf::kChunkK) < bf::kChunkK ? (K - c * bf::kChunkK) : bf::kChunkK;
+            const int ks = k >> 4, c = bf::kstep_chunk(K, ks), kk = bf::chunk_kk(K, c);
+            const int kr = bf::kstep_slot(K, ks) * 16 + (k & 15);     // position of k inside its chunk
             uint32_t hi, lo;
             h16_split2(bf::kScale * tc_weight(d, l, n, k), 0.0f, hi, lo);
-            uint16_t *chunk = out + base + bf::chunk_pos(K, c) * (N * bf::kChunkK * 2);
+            uint16_t *chunk = out + base + c * (N * bf::kChunkK * 2);
             const int off = (kr >> 3) * (N * 8) + n * 8 + (kr & 7);
             chunk[off] = (uint16_t)(hi & 0xffffu);
             chunk[N * kk + off] = (uint16_t)(lo & 0xffffu);
@@ -147,36 +150,37 @@ __global__ void k_grad_scale(const float4 *__restrict__ g_out, int n, const int 
 //   MODE 2: y = mask ? D/16 : 0                                (dgrad through a ReLU; y = Sg x gradient)
 //   MODE 3: y = D/16                                           (dgrad, no activation)
 template <int MODE>
-__device__ __forceinline__ void bf_epilogue32(uint32_t trow, uint32_t dcol, int c0, const float *bias, uint32_t &mask, unsigned char *stg)
+__device__ __forceinline__ void bf_epilogue16(uint32_t trow, uint32_t dcol, int c0, const float *bias, uint32_t &mask, int shift,
+                                              unsigned char *stg)
 {
     using namespace bf;
-    uint32_t v[32];
-    tmem_ld32(trow + dcol + c0, v);
+    uint32_t v[16];
+    tmem_ld16(trow + dcol + c0, v);
     tmem_wait_ld();
     uint32_t bits = 0u;
 #pragma unroll
-    for (int e = 0; e < 32; ++e) {
+    for (int e = 0; e < 16; ++e) {
         float y = __uint_as_float(v[e]);
         if (MODE == 0) { y = fmaxf(fmaf(y, kInvScale, bias[c0 + e]), 0.0f); bits |= (y > 0.0f ? 1u : 0u) << e; }
         if (MODE == 1) y = fmaf(y, kInvScale, bias[c0 + e]);
-        if (MODE == 2) y = ((mask >> e) & 1u) ? y * kInvScale : 0.0f;
+        if (MODE == 2) y = ((mask >> (shift + e)) & 1u) ? y * kInvScale : 0.0f;
         if (MODE == 3) y = y * kInvScale;
         v[e] = __float_as_uint(y);
     }
-    if (MODE == 0) mask = bits;
-    uint32_t hi[16], lo[16];
+    if (MODE == 0) mask = shift ? (mask | (bits << 16)) : bits;     // (shift is 0 or 16; the low half is written first)
+    uint32_t hi[8], lo[8];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) h16_split2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]), hi[e], lo[e]);
+    for (int e = 0; e < 8; ++e) h16_split2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]), hi[e], lo[e]);
     if (stg) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 2; ++j) {
             unsigned char *dst = stg + (size_t)(c0 / 8 + j) * 128;
             *reinterpret_cast<uint4 *>(dst) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
             *reinterpret_cast<uint4 *>(dst + 16384) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
         }
     }
-    tmem_st16(trow + cAHI + c0 / 2, hi);
-    tmem_st16(trow + cALO + c0 / 2, lo);
+    tmem_st8(trow + cAHI + c0 / 2, hi);
+    tmem_st8(trow + cALO + c0 / 2, lo);
 }
 
 // optional timeline trace of CTA 0 (pslam_debug_bf_trace): [tile<4][layer<10][8] clock64 stamps (+ 40 x 8 for k_wgrad_bf)
@@ -187,10 +191,10 @@ __device__ long long *g_bf_trace = nullptr;
     } while (0)
 
 // The MMA-issuing thread's state and one layer of the chain: D[128 x N] = A[128 x K] * W^T as K/16 k-steps of three
-// MMAs (a_lo*b_hi, a_hi*b_lo, a_hi*b_hi), the weights arriving in chunks of <= 32 k through the ring in chunk_at()
-// order.  The workers publish the A operand in two halves (a_ready[0], a_ready[1]): the first two chunks are issued
-// while the second half of the previous epilogue is still running; D alternates between two accumulator buffers so
-// that this is safe.
+// MMAs (a_lo*b_hi, a_hi*b_lo, a_hi*b_hi), the weights arriving through the ring in chunks of two k-steps (j, j + 4).
+// The workers publish the A operand in four quarters (a_ready[0..3]) and chunk j is issued as soon as quarter j is
+// there, i.e. while the rest of the previous epilogue is still running; D alternates between two accumulator buffers
+// so that this is safe.
 template <int NS>
 struct MmaIssuer {
     unsigned char *smem;
@@ -198,7 +202,8 @@ struct MmaIssuer {
     uint32_t tmem;
     int stage, phase;
     uint32_t uses;   // layers issued so far: a_ready phase and accumulator buffer
-    __device__ __forceinline__ void chunk(int N, int k0, int kk, uint32_t a_hi, uint32_t a_lo, uint32_t d, uint32_t idesc, bool first, bool last)
+    // one chunk: k-steps at k = kA and (kk == 32) k = kB
+    __device__ __forceinline__ void chunk(int N, int kA, int kB, int kk, uint32_t a_hi, uint32_t a_lo, uint32_t d, uint32_t idesc, bool first, bool last)
     {
         using namespace bf;
         mbar_wait(full + stage, phase);
@@ -208,7 +213,7 @@ struct MmaIssuer {
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
             if (s * 16 < kk) {
-                const uint32_t acol = (uint32_t)(k0 + s * 16) >> 1;
+                const uint32_t acol = (uint32_t)(s ? kB : kA) >> 1;
                 const uint64_t b_hi = b0 + (uint64_t)((s * (2 * N * 16)) >> 4);
                 const uint64_t b_lo = b0 + (uint64_t)((N * kk * 2 + s * (2 * N * 16)) >> 4);
                 mma_h16_ts(d, a_lo + acol, b_hi, idesc, (first && s == 0) ? 0u : 1u);
@@ -227,17 +232,21 @@ struct MmaIssuer {
         uint32_t t = tmem;
         asm volatile("" : "+r"(t));   // opaque: keeps the compiler from hoisting every layer's operand addresses out of the tile loop (64 registers here)
         const uint32_t a_hi = t + cAHI + acol0, a_lo = t + cALO + acol0, d = t + cD + (uses & 1) * kDCols;
-        const int nch = (K + kChunkK - 1) / kChunkK;
-        mbar_wait(a_ready, uses & 1);
-        fence_after_sync();
-        if (K < 64) { mbar_wait(a_ready + 1, uses & 1); fence_after_sync(); }
+        const uint32_t par = uses & 1;
+        if (K < 64) {
+            // a single k-step written by the lead threads alone; every worker still arrives on all four barriers
 #pragma unroll
-        for (int pos = 0; pos < 5; ++pos) {
-            if (pos < nch) {
-                if (pos == 2) { mbar_wait(a_ready + 1, uses & 1); fence_after_sync(); }   // second half of A (and k >= 128)
-                const int k0 = chunk_at(K, pos) * kChunkK;
-                chunk(N, k0, (K - k0) < kChunkK ? (K - k0) : kChunkK, a_hi, a_lo, d, idesc, pos == 0, pos == nch - 1);
+            for (int j = 0; j < 4; ++j) mbar_wait(a_ready + j, par);
+            fence_after_sync();
+            chunk(N, 0, 0, 16, a_hi, a_lo, d, idesc, true, true);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                mbar_wait(a_ready + j, par);
+                fence_after_sync();
+                chunk(N, 16 * j, 16 * (j + 4), 32, a_hi, a_lo, d, idesc, j == 0, j == 3 && K == 128);
             }
+            if (K > 128) chunk(N, 128, 128, 16, a_hi, a_lo, d, idesc, false, true);   // k >= 128: there since before a_ready[3]
         }
         ++uses;
     }
@@ -257,8 +266,8 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + SM::oBars);
     uint64_t *empty = full + kStages;
-    uint64_t *a_ready = empty + kStages;   // [2]: first / second half of the next A operand is in tensor memory
-    uint64_t *mma_done = a_ready + 2;
+    uint64_t *a_ready = empty + kStages;   // [4]: quarter j of the next A operand (k-steps j and j + 4) is in tensor memory
+    uint64_t *mma_done = a_ready + 4;
     uint64_t *st_full = mma_done + 1, *st_free = st_full + 2;
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(smem + SM::oTmemPtr);
     float *sBias = reinterpret_cast<float *>(smem + SM::oBias);
@@ -273,8 +282,7 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, kCluster); }
-        mbar_init(a_ready, kWorkers);
-        mbar_init(a_ready + 1, kWorkers);
+        for (int i = 0; i < 4; ++i) mbar_init(a_ready + i, kWorkers);
         mbar_init(mma_done, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(st_full + i, kWorkers); mbar_init(st_free + i, 1); }
         fence_barrier_init();
@@ -416,26 +424,32 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
             fence_after_sync();
             if (threadIdx.x == 128) BF_TRACE(tile_i, lcount, 3);     // worker sees the accumulators
         };
-        auto a_half_ready = [&]() {                   // first half of the next A operand (k in [0,32) u [64,96)) is written
+        auto a_quarter_ready = [&](int j) {           // quarter j of the next A operand (k-steps j and j + 4) is written
             tmem_wait_st();
             fence_before_sync();
-            mbar_arrive(a_ready);
+            mbar_arrive(a_ready + j);
         };
-        auto a_is_ready = [&]() {                     // ... and the rest, including anything the lead thread adds (k >= 128)
+        auto a_is_ready = [&]() {                     // ... the last quarter, and anything the lead thread adds (k >= 128)
             tmem_wait_st();
             fence_before_sync();
             if (threadIdx.x == 128) BF_TRACE(tile_i, lcount + 1, 5);  // worker has produced the A of layer lcount+1
-            mbar_arrive(a_ready + 1);
+            mbar_arrive(a_ready + 3);
             ++lcount;
         };
-        // epilogue of one layer in two 32-column batches with the half-way signal between them
+        auto a_small_ready = [&]() {                  // a K = 16 layer reads only what the lead thread wrote: all quarters at once
+            a_quarter_ready(0); mbar_arrive(a_ready + 1); mbar_arrive(a_ready + 2);
+            a_is_ready();
+        };
+        // epilogue of one layer in four 16-column batches, each followed by its quarter's signal (the last one by the caller)
         auto epilogue = [&](auto mode, const float *bias, uint32_t (&mask)[2], bool staged) {
             constexpr int MODE = decltype(mode)::value;
             unsigned char *stg = staged ? stage_begin() : nullptr;
             if (threadIdx.x == 128) BF_TRACE(tile_i, lcount, 7);       // staging buffer is free
-            bf_epilogue32<MODE>(trow, dcol, col0, bias, mask[0], stg);
-            a_half_ready();
-            bf_epilogue32<MODE>(trow, dcol, col0 + 32, bias, mask[1], stg);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                bf_epilogue16<MODE>(trow, dcol, col0 + 16 * j, bias, mask[j >> 1], (j & 1) * 16, stg);
+                if (j < 3) a_quarter_ready(j);
+            }
             if (staged) stage_end();
             if (threadIdx.x == 128) BF_TRACE(tile_i, lcount, 4);       // epilogue done (operand staged)
         };
@@ -510,8 +524,7 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
                 }
             }
             if constexpr (kHasFwd) {
-            a_half_ready();   // layer 1 (K = 16) reads only the features the lead thread just wrote: both halves at once
-            a_is_ready();
+            a_small_ready();  // layer 1 (K = 16) reads only the features the lead thread just wrote
             // ---- forward ----
             layer_done();
             epilogue(M0{}, sBias, m1, true);                                                            // h1
@@ -589,8 +602,7 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
                     }
                 }
             }
-            a_half_ready();   // D5 (K = 16) reads only g5
-            a_is_ready();
+            a_small_ready();  // D5 (K = 16) reads only g5
             layer_done();
             epilogue(M2{}, nullptr, mc, true);                                                          // g_hc
             a_is_ready();
