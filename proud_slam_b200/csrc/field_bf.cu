@@ -203,11 +203,22 @@ struct MmaIssuer {
     int stage, phase;
     uint32_t uses;   // layers issued so far: a_ready phase and accumulator buffer
     // one chunk: k-steps at k = kA and (kk == 32) k = kB
-    __device__ __forceinline__ void chunk(int N, int kA, int kB, int kk, uint32_t a_hi, uint32_t a_lo, uint32_t d, uint32_t idesc, bool first, bool last)
+    // The weights of the layer's first chunks are waited for up front (weights_ahead), while the issuer would otherwise
+    // idle until the epilogue publishes the first quarter of A: the per-chunk critical path is then one barrier wait,
+    // six MMAs and a commit.
+    __device__ __forceinline__ void weights_ahead(int nch)
+    {
+        int st = stage, ph = phase;
+        for (int j = 0; j < nch && j < NS; ++j) {
+            mbar_wait(full + st, ph);
+            if (++st == NS) { st = 0; ph ^= 1; }
+        }
+    }
+    __device__ __forceinline__ void chunk(int N, int kA, int kB, int kk, uint32_t a_hi, uint32_t a_lo, uint32_t d, uint32_t idesc, bool first, bool last,
+                                          bool waited)
     {
         using namespace bf;
-        mbar_wait(full + stage, phase);
-        fence_after_sync();
+        if (!waited) { mbar_wait(full + stage, phase); fence_after_sync(); }
         // descriptor of the chunk's first 16-byte k-chunk; the others are constant 16-byte-unit offsets from it
         const uint64_t b0 = sdesc(smem_u32(smem + stage * kStageBytes), N * 16, 128);
 #pragma unroll
@@ -233,20 +244,21 @@ struct MmaIssuer {
         asm volatile("" : "+r"(t));   // opaque: keeps the compiler from hoisting every layer's operand addresses out of the tile loop (64 registers here)
         const uint32_t a_hi = t + cAHI + acol0, a_lo = t + cALO + acol0, d = t + cD + (uses & 1) * kDCols;
         const uint32_t par = uses & 1;
+        weights_ahead(K < 64 ? 1 : (K > 128 ? 5 : 4));
         if (K < 64) {
             // a single k-step written by the lead threads alone; every worker still arrives on all four barriers
 #pragma unroll
             for (int j = 0; j < 4; ++j) mbar_wait(a_ready + j, par);
             fence_after_sync();
-            chunk(N, 0, 0, 16, a_hi, a_lo, d, idesc, true, true);
+            chunk(N, 0, 0, 16, a_hi, a_lo, d, idesc, true, true, true);
         } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 mbar_wait(a_ready + j, par);
                 fence_after_sync();
-                chunk(N, 16 * j, 16 * (j + 4), 32, a_hi, a_lo, d, idesc, j == 0, j == 3 && K == 128);
+                chunk(N, 16 * j, 16 * (j + 4), 32, a_hi, a_lo, d, idesc, j == 0, j == 3 && K == 128, j < NS);
             }
-            if (K > 128) chunk(N, 128, 128, 16, a_hi, a_lo, d, idesc, false, true);   // k >= 128: there since before a_ready[3]
+            if (K > 128) chunk(N, 128, 128, 16, a_hi, a_lo, d, idesc, false, true, 4 < NS);   // k >= 128: there since before a_ready[3]
         }
         ++uses;
     }
@@ -940,20 +952,34 @@ __global__ void __launch_bounds__(wgb::kThreads, 1) k_wgrad_bf(FieldParams p, fl
 // The gradients that go through M = G4^T H2 [128,128] and s4 = column sums of G4 (see the scratch layout):
 //   blocks 0..127   (j):  dW3[1+j][k] += sum_n W4[n][j] M[n][k]          db3[1+j] += sum_n W4[n][j] s4[n]
 //   blocks 128..255 (n):  dW4[n][j]   += sum_k M[n][k] W3[1+j][k] + s4[n] b3[1+j]          db4[n] += s4[n]
+// Each block first pulls the whole 128 x 128 matrix it contracts with (M, resp. W3's feature rows) into shared
+// memory with all its loads in flight at once; row pitch 129 keeps the second form's column walk conflict-free.
+constexpr int kFinishPitch = 129;
+constexpr int kFinishSmem = 128 * kFinishPitch * 4;
 __global__ void __launch_bounds__(128) k_wgrad_finish(FieldParams p, const float *__restrict__ finish)
 {
+    extern __shared__ float sMat[];   // [128][129]
     __shared__ float sVec[128], sRed[4];
     const int b = blockIdx.x & 127, t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const float *M = finish, *s4 = finish + 128 * 128;
-    if (blockIdx.x < 128) {
-        sVec[t] = p.dec.W4[(size_t)t * 144 + b];          // W4[n = t][j = b]
-        __syncthreads();
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;     // thread t = column k of M: coalesced rows, 4 independent chains
+    const bool first = blockIdx.x < 128;
+    const float *src = first ? M : p.dec.W3 + 128;      // W3 rows 1..128
+#pragma unroll 8
+    for (int i = t; i < 128 * 32; i += 128) {           // 128 rows x 32 float4
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(src) + i);
+        float *dst = sMat + (i >> 5) * kFinishPitch + (i & 31) * 4;
+        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    }
+    sVec[t] = first ? p.dec.W4[(size_t)t * 144 + b] : M[(size_t)b * 128 + t];   // W4[n = t][j = b]  /  M[n = b][k = t]
+    __syncthreads();
+    if (first) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // thread t = column k of M
+#pragma unroll 8
         for (int n = 0; n < 128; n += 4) {
-            a0 = fmaf(sVec[n], M[(size_t)n * 128 + t], a0);
-            a1 = fmaf(sVec[n + 1], M[(size_t)(n + 1) * 128 + t], a1);
-            a2 = fmaf(sVec[n + 2], M[(size_t)(n + 2) * 128 + t], a2);
-            a3 = fmaf(sVec[n + 3], M[(size_t)(n + 3) * 128 + t], a3);
+            a0 = fmaf(sVec[n], sMat[n * kFinishPitch + t], a0);
+            a1 = fmaf(sVec[n + 1], sMat[(n + 1) * kFinishPitch + t], a1);
+            a2 = fmaf(sVec[n + 2], sMat[(n + 2) * kFinishPitch + t], a2);
+            a3 = fmaf(sVec[n + 3], sMat[(n + 3) * kFinishPitch + t], a3);
         }
         atomicAdd(p.g_dec.W3 + (size_t)(1 + b) * 128 + t, (a0 + a1) + (a2 + a3));
         const float v = warp_sum(sVec[t] * s4[t]);        // db3[1 + b] = sum_n W4[n][b] s4[n]
@@ -961,18 +987,16 @@ __global__ void __launch_bounds__(128) k_wgrad_finish(FieldParams p, const float
         __syncthreads();
         if (t == 0) atomicAdd(p.g_dec.b3 + 1 + b, (sRed[0] + sRed[1]) + (sRed[2] + sRed[3]));
     } else {
-        sVec[t] = M[(size_t)b * 128 + t];                 // M[n = b][k = t]
-        __syncthreads();
         const float sb = s4[b];
-        // warp w takes outputs j = w, w+4, ...: the lanes read one W3 row coalesced and reduce by shuffles
-        for (int j = warp; j < 128; j += 4) {
-            const float *row = p.dec.W3 + (size_t)(1 + j) * 128;
-            float a = sVec[lane] * row[lane] + sVec[lane + 32] * row[lane + 32];
-            a = fmaf(sVec[lane + 64], row[lane + 64], a);
-            a = fmaf(sVec[lane + 96], row[lane + 96], a);
-            a = warp_sum(a);
-            if (lane == 0) atomicAdd(p.g_dec.W4 + (size_t)b * 144 + j, a + sb * p.dec.b3[1 + j]);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // thread t = output j: walks row t of W3's feature rows
+#pragma unroll 8
+        for (int k = 0; k < 128; k += 4) {
+            a0 = fmaf(sVec[k], sMat[t * kFinishPitch + k], a0);
+            a1 = fmaf(sVec[k + 1], sMat[t * kFinishPitch + k + 1], a1);
+            a2 = fmaf(sVec[k + 2], sMat[t * kFinishPitch + k + 2], a2);
+            a3 = fmaf(sVec[k + 3], sMat[t * kFinishPitch + k + 3], a3);
         }
+        atomicAdd(p.g_dec.W4 + (size_t)b * 144 + t, ((a0 + a1) + (a2 + a3)) + sb * p.dec.b3[1 + t]);
         if (t == 0) atomicAdd(p.g_dec.b4 + b, sb);
     }
 }
@@ -1172,11 +1196,31 @@ int bf_launch_field_forward(const FieldParams &fp_in, int max_samples, cudaStrea
     return 0;
 }
 
+// one non-blocking side stream + fork / join events per device (created on first use, never destroyed)
+struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
+static SideStream *side_stream()
+{
+    static SideStream table[64] = {};
+    static bool ready[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!ready[dev]) {
+        SideStream s{};
+        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+        table[dev] = s;
+        ready[dev] = true;
+    }
+    return &table[dev];
+}
+
 // backward: dgrad chain (+ trilinear backward); when decoder gradients are wanted the scratch must be
 // provided and the wgrad kernel follows on the same stream
 int bf_launch_field_backward(const FieldParams &fp_in, int max_samples, cudaStream_t st, int part)
 {
     FieldParams fp = fp_in;
+    cudaEvent_t joined = nullptr;
     if (!fp.grad_dec) fp.wg_scratch = nullptr;
     // per-launch gradient scale: 4 bytes at the end of the weight-stream region (the f16 stream fills only its first half)
     fp.gscale = reinterpret_cast<uint32_t *>(const_cast<float *>(fp.ws_tc)) + kTcPackFloats - 4;
@@ -1201,8 +1245,23 @@ int bf_launch_field_backward(const FieldParams &fp_in, int max_samples, cudaStre
             if (int rc = launch_bf<bf::kBwdRecompute>(fp, max_samples, st)) return rc;
         }
         if (split && (fp.grad_emb || fp.grad_rays)) {
-            k_tri_scatter<<<(int)ceil_div64((int64_t)(max_samples > 0 ? max_samples : 1) * 4, 256), 256, 0, st>>>(fps, fp.g_feat);
+            // the embedding / ray scatter and the weight-gradient kernels both depend on the kernel above only: the scatter
+            // (L2 atomics, few threads per SM) runs on a side stream underneath the HBM-bound wgrad kernel
+            cudaStream_t ss = st;
+            SideStream *side = (fp.grad_dec && part == 0) ? side_stream() : nullptr;
+            if (side) {
+                if (cudaEventRecord(side->fork, st) != cudaSuccess || cudaStreamWaitEvent(side->stream, side->fork, 0) != cudaSuccess) {
+                    set_error("field_bf: stream fork: %s", cudaGetErrorString(cudaGetLastError()));
+                    return PSLAM_E_ARG;
+                }
+                ss = side->stream;
+            }
+            k_tri_scatter<<<(int)ceil_div64((int64_t)(max_samples > 0 ? max_samples : 1) * 4, 256), 256, 0, ss>>>(fps, fp.g_feat);
             PSLAM_CHECK_LAUNCH("tri_scatter");
+            if (side) {
+                if (cudaEventRecord(side->join, side->stream) != cudaSuccess) { set_error("field_bf: stream join: %s", cudaGetErrorString(cudaGetLastError())); return PSLAM_E_ARG; }
+                joined = side->join;
+            }
         }
     }
     if (!fp.grad_dec || part == 1) return 0;
@@ -1219,8 +1278,18 @@ int bf_launch_field_backward(const FieldParams &fp_in, int max_samples, cudaStre
     if (e != cudaSuccess) { set_error("wgrad_bf: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
     k_wgrad_bf<<<grid, wgb::kThreads, wgb::kSmemBytes, st>>>(fp, finish);
     PSLAM_CHECK_LAUNCH("wgrad_bf");
-    k_wgrad_finish<<<256, 128, 0, st>>>(fp, finish);
+    static bool finish_configured = false;
+    if (!finish_configured) {
+        cudaError_t e2 = cudaFuncSetAttribute(k_wgrad_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinishSmem);
+        if (e2 != cudaSuccess) { set_error("wgrad_finish: cudaFuncSetAttribute: %s", cudaGetErrorString(e2)); return (int)e2; }
+        finish_configured = true;
+    }
+    k_wgrad_finish<<<256, 128, kFinishSmem, st>>>(fp, finish);
     PSLAM_CHECK_LAUNCH("wgrad_finish");
+    if (joined) {                                       // the scatter kernel forked onto the side stream joins here
+        cudaError_t e3 = cudaStreamWaitEvent(st, joined, 0);
+        if (e3 != cudaSuccess) { set_error("field_bf: cudaStreamWaitEvent: %s", cudaGetErrorString(e3)); return (int)e3; }
+    }
     return 0;
 }
 
