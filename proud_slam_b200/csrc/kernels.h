@@ -6,9 +6,9 @@
 
 namespace pslam {
 
-// scratch_i layout: [intersect block hits: R/64 + 8][sample block counts: R/64 + 8][composite partials: 8 x R/8 + 64]
+// scratch_i layout: [intersect block hits: R/64 + 8][sample block counts / look-back state: 2 x (R/64 + 8)][composite partials: 8 x R/8 + 64]
 static inline int scratch_i_sample_off(int R) { return (R + 63) / 64 + 8; }
-static inline int scratch_i_composite_off(int R) { return 2 * ((R + 63) / 64 + 8); }
+static inline int scratch_i_composite_off(int R) { return 3 * ((R + 63) / 64 + 8); }
 
 // intersect.cu
 int scan_partials(int *partials, int nb, int *total_out, cudaStream_t st);

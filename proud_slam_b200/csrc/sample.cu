@@ -184,6 +184,43 @@ struct CsrSink {
     }
 };
 
+// Everything one thread does for the ray of rank q: stage its hit list, rebuild the reference's group / chunk
+// indexing, run the sampling loop into `sink`.  Returns the number of emissions.
+template <class Sink>
+__device__ __forceinline__ int run_ray(const pslam_render_t &p, int q, int Rh, int P, int *s_idx, float *s_min, float *s_max, Sink &sink)
+{
+    const int n = (Rh + kGroups - 1) / kGroups;
+    const int g = q / n, jf = q % n;
+    const int c = jf / kChunkRays, j = jf % kChunkRays;
+    const int nc = min(kChunkRays, n - c * kChunkRays);
+    const int r = __ldg(p.hit_ray + q);
+    const int cnt = min(__ldg(p.hit_count + r), p.n_max);
+    for (int b = 0; b < cnt; ++b) {      // independent loads, coalesced over the rays of a warp where ranks are consecutive
+        s_idx[b * kSampleThreads] = __ldg(p.hit_idx + (int64_t)b * p.R + r);
+        s_min[b * kSampleThreads] = __ldg(p.hit_min + (int64_t)b * p.R + r);
+        s_max[b * kSampleThreads] = __ldg(p.hit_max + (int64_t)b * p.R + r);
+    }
+    // a5: dists, their sum (left-to-right fp32), probs and steps (voxel_helpers.py:639-644)
+    float total = 0.0f;
+    for (int b = 0; b < cnt; ++b) total = __fadd_rn(total, __fsub_rn(s_max[b * kSampleThreads], s_min[b * kSampleThreads]));
+    const float steps = __fdiv_rn(total, p.step_size);
+    FusedHits hv;
+    hv.hit_idx = p.hit_idx; hv.hit_min = p.hit_min; hv.hit_max = p.hit_max;
+    hv.hit_count = p.hit_count; hv.hit_ray = p.hit_ray;
+    hv.R = p.R; hv.Rh = Rh; hv.P = P; hv.chunk_base_rank = g * n + c * kChunkRays;
+    hv.total = total; hv.max_distance = p.max_distance;
+    hv.own_j = j; hv.own_r = r; hv.own_cnt = cnt;
+    hv.s_idx = s_idx; hv.s_min = s_min; hv.s_max = s_max;
+    const float prob0 = hv.prob(j, 0);
+    if (p.noise) {
+        TensorNoise nz{p.noise + (int64_t)q * p.noise_stride, p.noise_stride};
+        return sample_ray(hv, nz, sink, j, nc, P, prob0, steps, -1.0f);
+    }
+    const HashNoise nz((p.seed + (p.seed_dev ? *p.seed_dev : 0ull)) ^ ((uint64_t)(uint32_t)q * 0xD1B54A32D192ED03ull));
+    return sample_ray(hv, nz, sink, j, nc, P, prob0, steps, -1.0f);
+}
+
+// Two-pass form (count -> offsets -> write): used when the one-pass kernel's shared-memory buffers do not fit.
 template <bool WRITE>
 __global__ void __launch_bounds__(kSampleThreads)
 k_sample_fused(pslam_render_t p, int *__restrict__ block_counts)
@@ -197,47 +234,14 @@ k_sample_fused(pslam_render_t p, int *__restrict__ block_counts)
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     int nsamp = 0;
     if (q < Rh) {
-        const int n = (Rh + kGroups - 1) / kGroups;
-        const int g = q / n, jf = q % n;
-        const int c = jf / kChunkRays, j = jf % kChunkRays;
-        const int nc = min(kChunkRays, n - c * kChunkRays);
-        const int r = __ldg(p.hit_ray + q);
-        const int cnt = min(__ldg(p.hit_count + r), p.n_max);
-        for (int b = 0; b < cnt; ++b) {      // independent loads, coalesced over the rays of a warp where ranks are consecutive
-            s_idx[b * kSampleThreads] = __ldg(p.hit_idx + (int64_t)b * p.R + r);
-            s_min[b * kSampleThreads] = __ldg(p.hit_min + (int64_t)b * p.R + r);
-            s_max[b * kSampleThreads] = __ldg(p.hit_max + (int64_t)b * p.R + r);
-        }
-        // a5: dists, their sum (left-to-right fp32), probs and steps (voxel_helpers.py:639-644)
-        float total = 0.0f;
-        for (int b = 0; b < cnt; ++b) total = __fadd_rn(total, __fsub_rn(s_max[b * kSampleThreads], s_min[b * kSampleThreads]));
-        const float steps = __fdiv_rn(total, p.step_size);
-        FusedHits hv;
-        hv.hit_idx = p.hit_idx; hv.hit_min = p.hit_min; hv.hit_max = p.hit_max;
-        hv.hit_count = p.hit_count; hv.hit_ray = p.hit_ray;
-        hv.R = p.R; hv.Rh = Rh; hv.P = P; hv.chunk_base_rank = g * n + c * kChunkRays;
-        hv.total = total; hv.max_distance = p.max_distance;
-        hv.own_j = j; hv.own_r = r; hv.own_cnt = cnt;
-        hv.s_idx = s_idx; hv.s_min = s_min; hv.s_max = s_max;
-        const float prob0 = hv.prob(j, 0);
-        int room = 0, off = 0;
         if (WRITE) {
-            off = min(p.samp_off[q], p.sample_cap);
-            room = max(0, min(p.samp_off[q + 1], p.sample_cap) - off);
-        }
-        CsrSink csr{p.samp_vox + off, p.samp_z + off, p.samp_dist + off, p.samp_ray + off, q, room};
-        CountSink cs{0};
-        int s;
-        if (p.noise) {
-            TensorNoise nz{p.noise + (int64_t)q * p.noise_stride, p.noise_stride};
-            s = WRITE ? sample_ray(hv, nz, csr, j, nc, P, prob0, steps, -1.0f)
-                      : sample_ray(hv, nz, cs, j, nc, P, prob0, steps, -1.0f);
+            const int off = min(p.samp_off[q], p.sample_cap);
+            const int room = max(0, min(p.samp_off[q + 1], p.sample_cap) - off);
+            CsrSink csr{p.samp_vox + off, p.samp_z + off, p.samp_dist + off, p.samp_ray + off, q, room};
+            run_ray(p, q, Rh, P, s_idx, s_min, s_max, csr);
         } else {
-            const HashNoise nz((p.seed + (p.seed_dev ? *p.seed_dev : 0ull)) ^ ((uint64_t)(uint32_t)q * 0xD1B54A32D192ED03ull));
-            s = WRITE ? sample_ray(hv, nz, csr, j, nc, P, prob0, steps, -1.0f)
-                      : sample_ray(hv, nz, cs, j, nc, P, prob0, steps, -1.0f);
-        }
-        if (!WRITE) {
+            CountSink cs{0};
+            const int s = run_ray(p, q, Rh, P, s_idx, s_min, s_max, cs);
             // a trailing -1 id (A-Q7) is not a sample and can only be the last emission
             nsamp = (s > 0 && cs.last == -1) ? s - 1 : s;
             p.samp_off[q] = nsamp;  // counts now; turned into offsets by k_sample_offsets
@@ -255,6 +259,112 @@ k_sample_fused(pslam_render_t p, int *__restrict__ block_counts)
             int t = 0;
             for (int w = 0; w < kSampleThreads / 32; ++w) t += s_sum[w];
             block_counts[blockIdx.x] = t;
+        }
+    }
+}
+
+// One-pass form: the sampling loop runs ONCE per ray into a shared-memory buffer ([slot][thread]); the CSR offsets
+// come from a block scan plus a decoupled look-back over the per-block totals (state[b]: flag in the high word --
+// 1 = this block's total, 2 = inclusive prefix -- value in the low word; zeroed before the launch), then every thread
+// copies its samples out.  A ray with more emissions than buffer slots simply reruns its loop straight into global memory.
+constexpr int kSampleBuf = 96;
+struct BufSink {
+    int *vox; float *z, *dist; int last;
+    __device__ __forceinline__ void operator()(int s, int v, float d, float zz)
+    {
+        last = v;
+        if (s < kSampleBuf) { vox[s * kSampleThreads] = v; z[s * kSampleThreads] = zz; dist[s * kSampleThreads] = fmaxf(d, 0.0f); }
+    }
+};
+
+__global__ void __launch_bounds__(kSampleThreads)
+k_sample_onepass(pslam_render_t p, unsigned long long *__restrict__ state)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];   // hits [3][n_max][T], then samples [3][kSampleBuf][T]
+    __shared__ int s_wsum[kSampleThreads / 32];
+    __shared__ int s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int *s_idx = reinterpret_cast<int *>(s_raw) + tid;
+    float *s_min = reinterpret_cast<float *>(s_raw) + (size_t)p.n_max * kSampleThreads + tid;
+    float *s_max = s_min + (size_t)p.n_max * kSampleThreads;
+    int *b_vox = reinterpret_cast<int *>(s_raw) + (size_t)3 * p.n_max * kSampleThreads + tid;
+    float *b_z = reinterpret_cast<float *>(b_vox) + kSampleBuf * kSampleThreads;
+    float *b_dist = b_z + kSampleBuf * kSampleThreads;
+    const int Rh = p.counters[PSLAM_C_RH];
+    const int P = p.counters[PSLAM_C_P];
+    const int q = blockIdx.x * kSampleThreads + tid;
+    int nsamp = 0;
+    if (q < Rh) {
+        BufSink bs{b_vox, b_z, b_dist, 0};
+        const int s = run_ray(p, q, Rh, P, s_idx, s_min, s_max, bs);
+        nsamp = (s > 0 && bs.last == -1) ? s - 1 : s;   // a trailing -1 id (A-Q7) is not a sample and can only be the last emission
+    }
+    // block scan of the counts
+    int x = nsamp;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    const int wmax = warp_max_i(nsamp);
+    if (lane == 31) s_wsum[warp] = x;
+    if (lane == 0 && wmax > 0) atomicMax(p.counters + PSLAM_C_S, wmax);
+    __syncthreads();
+    int excl = x - nsamp, btotal = 0;
+    for (int w = 0; w < kSampleThreads / 32; ++w) { if (w < warp) excl += s_wsum[w]; btotal += s_wsum[w]; }
+    // decoupled look-back (warp 0): exclusive prefix of this block over all earlier blocks
+    if (warp == 0) {
+        const int b = blockIdx.x;
+        if (lane == 0) {
+            const unsigned long long v = ((unsigned long long)(b == 0 ? 2u : 1u) << 32) | (unsigned)btotal;
+            __threadfence();
+            atomicExch(state + b, v);
+        }
+        int base = 0;
+        for (int hi_b = b - 1; hi_b >= 0; hi_b -= 32) {
+            const int idx = hi_b - lane;                        // lane 0 looks at the nearest predecessor
+            unsigned long long v = 2ull << 32;                  // out of range: a zero prefix
+            if (idx >= 0) {
+                do { v = *reinterpret_cast<volatile unsigned long long *>(state + idx); } while ((v >> 32) == 0ull);
+            }
+            const unsigned done = __ballot_sync(0xffffffffu, (v >> 32) == 2ull);
+            const int stop = done ? __ffs(done) - 1 : 32;       // nearest lane that already has its inclusive prefix
+            int part = (lane <= stop) ? (int)(unsigned)(v & 0xffffffffull) : 0;
+            part = warp_sum_i(part);
+            base += part;
+            if (done) break;
+        }
+        if (lane == 0) {
+            s_base = base;
+            if (b > 0) {
+                __threadfence();
+                atomicExch(state + b, (2ull << 32) | (unsigned)(base + btotal));
+            }
+        }
+    }
+    __syncthreads();
+    const int off_raw = s_base + excl;
+    if (q < Rh) {
+        p.samp_off[q] = off_raw;
+        if (q == Rh - 1) {
+            const int total = off_raw + nsamp;
+            p.samp_off[Rh] = total;
+            p.counters[PSLAM_C_NSAMP] = min(total, p.sample_cap);
+            if (total > p.sample_cap) atomicOr(p.counters + PSLAM_C_OVERFLOW, 1);
+        }
+        const int off = min(off_raw, p.sample_cap);
+        const int room = max(0, min(off_raw + nsamp, p.sample_cap) - off);
+        if (nsamp <= kSampleBuf) {
+            const int m = min(nsamp, room);
+            for (int k = 0; k < m; ++k) {
+                p.samp_vox[off + k] = b_vox[k * kSampleThreads];
+                p.samp_z[off + k] = b_z[k * kSampleThreads];
+                p.samp_dist[off + k] = b_dist[k * kSampleThreads];
+                p.samp_ray[off + k] = q;
+            }
+        } else {
+            CsrSink csr{p.samp_vox + off, p.samp_z + off, p.samp_dist + off, p.samp_ray + off, q, room};
+            run_ray(p, q, Rh, P, s_idx, s_min, s_max, csr);
         }
     }
 }
@@ -290,9 +400,24 @@ k_sample_offsets(pslam_render_t p, const int *__restrict__ block_base)
 int launch_sample_fused(const pslam_render_t *p, cudaStream_t st)
 {
     const int nb = ceil_div(p->R, kSampleThreads);
-    int *block_counts = p->scratch_i + scratch_i_sample_off(p->R);   // after intersect's block_hits
+    int *block_counts = p->scratch_i + scratch_i_sample_off(p->R);   // after intersect's block_hits; 2 ints per block
     const size_t smem = (size_t)p->n_max * kSampleThreads * 12;
     PSLAM_CHECK_ARG(smem <= 48 * 1024, PSLAM_E_RANGE, "n_max=%d: the per-block hit staging exceeds 48 KB of shared memory", p->n_max);
+    const size_t smem1 = smem + (size_t)kSampleBuf * kSampleThreads * 12;
+    if (smem1 <= 112 * 1024) {
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t e = cudaFuncSetAttribute(k_sample_onepass, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+            if (e != cudaSuccess) { set_error("sample: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+            configured = true;
+        }
+        unsigned long long *state = reinterpret_cast<unsigned long long *>(block_counts + (((uintptr_t)block_counts & 7) ? 1 : 0));
+        cudaError_t e = cudaMemsetAsync(state, 0, (size_t)nb * sizeof(unsigned long long), st);
+        if (e != cudaSuccess) { set_error("sample: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
+        k_sample_onepass<<<nb, kSampleThreads, smem1, st>>>(*p, state);
+        PSLAM_CHECK_LAUNCH("sample_onepass");
+        return 0;
+    }
     k_sample_fused<false><<<nb, kSampleThreads, smem, st>>>(*p, block_counts);
     PSLAM_CHECK_LAUNCH("sample_count");
     if (int rc = scan_partials(block_counts, nb, p->counters + PSLAM_C_TILE2, st)) return rc;
