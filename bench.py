@@ -37,7 +37,7 @@ WIDTH = 128
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel at the bench workload (ncu --set full, profiles/*_summary.md)
-NCU_TRAFFIC = {0: 985.8e6, 2: 273.7e6}
+NCU_TRAFFIC = {0: 985.8e6, 2: 272.4e6}   # 3xF16: k_field_bf<kFwdSave> 12.6 + 259.8 MB (kBwdSaved: 15.7 + 261.2 MB)
 
 
 def macs_per_sample(w):
@@ -258,7 +258,7 @@ def run_gpu(args):
     if rank == 0:
         pipe.args.flags = pipe.args.flags & ~_lib.F_DEFER_LOSS
         stage_ms = []
-        for stage_id in range(8):
+        for stage_id in range(10 if int(os.environ.get("PSLAM_DECODER", "2")) == 2 else 8):
             reps = []
             for it in range(max(3, min(args.steps, 10))):
                 flat.zero_()
@@ -274,8 +274,10 @@ def run_gpu(args):
                 torch.cuda.synchronize()
                 reps.append(a.elapsed_time(b))
             stage_ms.append(sum(reps[1:]) / max(len(reps) - 1, 1))
+        # field_bwd_dgrad_kernel / _wgrad_kernel: the two halves of the backward stage (scale + chain kernel + scatter; memset +
+        # wgrad kernel + finish); decoder_fwd_kernel / decoder_bwd_kernel: k_field_bf<kFwdSave> / <kBwdSaved> alone
         prof = dict(zip(["intersect", "sample", "field_fwd", "composite_fwd", "composite_bwd", "field_bwd", "field_bwd_dgrad_kernel",
-                         "field_bwd_wgrad_kernel"], stage_ms))
+                         "field_bwd_wgrad_kernel", "decoder_fwd_kernel", "decoder_bwd_kernel"], stage_ms))
 
     if world > 1:
         t = torch.tensor([ms_step, ms_e2e], device=device, dtype=torch.float64)
@@ -298,8 +300,25 @@ def run_gpu(args):
         # dominant kernel: k_field_tc<bwd> (forward recompute + dgrad chain + trilinear backward + scratch spill);
         # algorithmic FLOPs = the dgrad GEMMs once (2 MACs P), neither the recompute nor the x3 of the TF32 split
         flops_bwd = 2.0 * macs_per_sample(WIDTH) * P
-        t_k = prof["field_bwd_dgrad_kernel"] * 1e-3
+        dom = "decoder_bwd_kernel"
+        if build == 2 and prof["decoder_fwd_kernel"] > prof["decoder_bwd_kernel"]:
+            dom, kname = "decoder_fwd_kernel", "k_field_bf<kFwdSave>"
+        if build != 2:
+            dom = "field_bwd_dgrad_kernel"
+        t_k = prof[dom] * 1e-3
         achieved = flops_bwd / t_k / 1e12
+        # the other kernels of the decoder, each against its own bound (same measured peaks)
+        others = []
+        if build == 2:
+            for name, key in (("k_field_bf<kFwdSave>", "decoder_fwd_kernel"), ("k_field_bf<kBwdSaved>", "decoder_bwd_kernel")):
+                a = flops_bwd / (prof[key] * 1e-3) / 1e12
+                others.append({"kernel": name, "bound": "tensor", "achieved": a, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                               "frac": a / peaks["bf16_tflops"], "kernel_ms": prof[key]})
+            wg_bytes = 409600.0 / 128.0 * P          # 3.2 kB of pre-split operands per sample
+            a = wg_bytes / (prof["field_bwd_wgrad_kernel"] * 1e-3) / 1e9
+            others.append({"kernel": "k_wgrad_bf (+ memset, k_wgrad_finish: the whole stage is timed)", "bound": "hbm", "achieved": a,
+                           "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": a / peaks["hbm_gbs"], "kernel_ms": prof["field_bwd_wgrad_kernel"],
+                           "traffic": 619.5e6 if (P > 190000 and P < 194000) else None})
         value = world * R / (ms_step * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -313,15 +332,19 @@ def run_gpu(args):
                        "loss": loss_val},
             "e2e": {"value": world * R / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(sum(t.numel() * 4 for t in host)), "d2h_bytes_per_step": 64},
-            "gpu_launches": args.steps * 19,
+            # our kernels per mapping iteration (3xF16 build): prefetch, intersect, scan, compact | sample | pack x2, gather, decoder fwd |
+            # composite, loss reduce, loss coeffs | composite bwd, zero x2, grad scale, decoder bwd, scatter, wgrad, wgrad finish
+            # (cudaMemsetAsync nodes, torch's gradient-buffer fill and NCCL not counted)
+            "gpu_launches": args.steps * (20 if build == 2 else 19),
             "clocks": clocks,
-            "roofline": {"kernel": f"{kname} ({ktext}: " + ("dgrad chain from the forward's saved ReLU masks" if build == 2 else "decoder recompute + dgrad") + ", fused trilinear backward, wgrad spill)", "bound": "tensor",
+            "roofline": {"kernel": f"{kname} ({ktext}: " + (("5 layers, activations + ReLU masks spilled for the backward" if dom == "decoder_fwd_kernel" else "dgrad chain from the forward's saved ReLU masks, gradient operands spilled for the wgrad kernel") if build == 2 else "decoder recompute + dgrad, fused trilinear backward, wgrad spill") + ")", "bound": "tensor",
                          "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
                          "traffic": NCU_TRAFFIC.get(build) if (P > 190000 and P < 194000) else None,   # dram read+write per launch, ncu --set full (profiles/)
                          "peak_source": peaks["source"] + ", dense bf16 burst; the kernel issues 3 split MMAs per product"
                                         + (" (3 hardware FLOPs per algorithmic FLOP, so frac <= 1/3 by construction)" if build == 2 else
                                            " and recomputes the forward (6 hardware FLOPs per algorithmic FLOP, so frac <= 1/6 by construction)"),
-                         "algorithmic_flops_per_launch": flops_bwd, "kernel_ms": prof["field_bwd_dgrad_kernel"]},
+                         "algorithmic_flops_per_launch": flops_bwd, "kernel_ms": prof[dom]},
+            "roofline_kernels": others,
             "stage_ms": prof,
         }
         if world == 1 and not args.no_extras:

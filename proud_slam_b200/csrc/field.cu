@@ -734,7 +734,7 @@ static int launch_field(const FieldParams &fp, bool bwd, int max_samples, cudaSt
             return tc_launch_field_backward(fp, max_samples, st, part);
     }
     if (fp.dec.width == 128 && decoder_mode() == 2) {
-        if (!bwd) return bf_launch_field_forward(fp, max_samples, st);
+        if (!bwd) return bf_launch_field_forward(fp, max_samples, st, part);
         if (!fp.grad_dec || (fp.wg_scratch && fp.wg_scratch_bytes >= bf_wgrad_scratch_bytes(max_samples)))
             return bf_launch_field_backward(fp, max_samples, st, part);
     }
@@ -760,10 +760,11 @@ static FieldParams params_from_render(const pslam_render_t *p)
     return fp;
 }
 
-int launch_field_forward(const pslam_render_t *p, cudaStream_t st)
+int launch_field_forward(const pslam_render_t *p, cudaStream_t st, int part)
 {
-    if (int rc = pack_decoder(p->dec, p->dec_ws, st)) return rc;
-    return launch_field(params_from_render(p), false, p->sample_cap, st);
+    if (part != 3)   // part 3 (profiling): the decoder kernel alone, after a full forward of the same arguments
+        if (int rc = pack_decoder(p->dec, p->dec_ws, st)) return rc;
+    return launch_field(params_from_render(p), false, p->sample_cap, st, part);
 }
 
 int launch_field_backward(const pslam_render_t *p, cudaStream_t st, int part)

@@ -52,7 +52,7 @@ int tc_launch_field_backward(const FieldParams &fp, int max_samples, cudaStream_
 size_t tc_wgrad_scratch_bytes(int max_samples);
 // field_bf.cu: 3xBF16 build, same entry points; its weight stream (bf16 hi/lo) fits in the first half of the tc region
 int bf_pack_decoder(const pslam_decoder_t &d, float *ws_tc, cudaStream_t st);
-int bf_launch_field_forward(const FieldParams &fp, int max_samples, cudaStream_t st);
+int bf_launch_field_forward(const FieldParams &fp, int max_samples, cudaStream_t st, int part = 0);
 int bf_launch_field_backward(const FieldParams &fp, int max_samples, cudaStream_t st, int part = 0);
 size_t bf_wgrad_scratch_bytes(int max_samples);
 void bf_set_save_activations(int on);   // PSLAM_OPT_SAVE_ACT

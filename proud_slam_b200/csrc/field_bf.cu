@@ -1181,13 +1181,15 @@ static int launch_bf(const FieldParams &fp, int max_samples, cudaStream_t st)
 }
 
 // forward; with decoder gradients to follow (fp.grad_dec) and a scratch, it also spills its activations and ReLU masks
-int bf_launch_field_forward(const FieldParams &fp_in, int max_samples, cudaStream_t st)
+int bf_launch_field_forward(const FieldParams &fp_in, int max_samples, cudaStream_t st, int part)
 {
     FieldParams fp = fp_in;
     const bool save = g_save_activations && fp.paired && fp.grad_dec && fp.wg_scratch && fp.wg_scratch_bytes >= bf_wgrad_scratch_bytes(max_samples);
     if (fp.wg_scratch && fp.wg_scratch == g_saved_scratch) g_saved_scratch = nullptr;
-    if (split_trilinear(fp, max_samples))
-        if (int rc = launch_tri_gather(fp, max_samples, st)) return rc;
+    if (split_trilinear(fp, max_samples)) {
+        if (part == 3) fp.feat = scratch_feat(fp, max_samples, 0);      // profiling: the rows of the previous full forward
+        else if (int rc = launch_tri_gather(fp, max_samples, st)) return rc;
+    }
     if (!save) return launch_bf<bf::kFwd>(fp, max_samples, st);
     fp.act_masks = reinterpret_cast<uint32_t *>(scratch_finish(fp, max_samples) + bf::kFinishFloats * sizeof(float));
     if (int rc = launch_bf<bf::kFwdSave>(fp, max_samples, st)) return rc;
@@ -1225,10 +1227,12 @@ int bf_launch_field_backward(const FieldParams &fp_in, int max_samples, cudaStre
     // per-launch gradient scale: 4 bytes at the end of the weight-stream region (the f16 stream fills only its first half)
     fp.gscale = reinterpret_cast<uint32_t *>(const_cast<float *>(fp.ws_tc)) + kTcPackFloats - 4;
     if (part != 2) {
-        cudaError_t e = cudaMemsetAsync(fp.gscale, 0, sizeof(uint32_t), st);
-        if (e != cudaSuccess) { set_error("field_bf: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
-        k_grad_scale<<<num_sms(), 256, 0, st>>>(reinterpret_cast<const float4 *>(fp.g_out), fp.nsamp, fp.nsamp_dev, fp.gscale);
-        PSLAM_CHECK_LAUNCH("grad_scale");
+        if (part != 3) {   // part 3 (profiling): the chain kernel alone; the scale of the previous full backward is still there
+            cudaError_t e = cudaMemsetAsync(fp.gscale, 0, sizeof(uint32_t), st);
+            if (e != cudaSuccess) { set_error("field_bf: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
+            k_grad_scale<<<num_sms(), 256, 0, st>>>(reinterpret_cast<const float4 *>(fp.g_out), fp.nsamp, fp.nsamp_dev, fp.gscale);
+            PSLAM_CHECK_LAUNCH("grad_scale");
+        }
         const bool saved = g_save_activations && fp.paired && fp.wg_scratch && fp.wg_scratch == g_saved_scratch && fp.out == g_saved_out;
         if (!saved && fp.wg_scratch && fp.wg_scratch == g_saved_scratch) g_saved_scratch = nullptr;   // about to be overwritten
         fp.act_masks = fp.wg_scratch ? reinterpret_cast<uint32_t *>(scratch_finish(fp, max_samples) + bf::kFinishFloats * sizeof(float)) : nullptr;
@@ -1244,7 +1248,7 @@ int bf_launch_field_backward(const FieldParams &fp_in, int max_samples, cudaStre
         } else {
             if (int rc = launch_bf<bf::kBwdRecompute>(fp, max_samples, st)) return rc;
         }
-        if (split && (fp.grad_emb || fp.grad_rays)) {
+        if (split && (fp.grad_emb || fp.grad_rays) && part != 3) {
             // the embedding / ray scatter and the weight-gradient kernels both depend on the kernel above only: the scatter
             // (L2 atomics, few threads per SM) runs on a side stream underneath the HBM-bound wgrad kernel
             cudaStream_t ss = st;
@@ -1264,7 +1268,7 @@ int bf_launch_field_backward(const FieldParams &fp_in, int max_samples, cudaStre
             }
         }
     }
-    if (!fp.grad_dec || part == 1) return 0;
+    if (!fp.grad_dec || part == 1 || part == 3) return 0;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_wgrad_bf, cudaFuncAttributeMaxDynamicSharedMemorySize, wgb::kSmemBytes);
