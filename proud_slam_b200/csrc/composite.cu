@@ -292,6 +292,15 @@ __global__ void k_loss_coeffs(pslam_render_t p, const double *__restrict__ rows,
 
 __device__ __forceinline__ float signf_(float x) { return (x > 0.0f) ? 1.0f : ((x < 0.0f) ? -1.0f : 0.0f); }
 
+// max |dL/d(sample outputs)| of this backward (bit pattern, counters[PSLAM_C_TILE]; reset by k_bwd_prologue): the 3xF16
+// decoder backward takes its power-of-two gradient scale from it instead of running a reduction of its own
+__device__ __forceinline__ void publish_gmax(const pslam_render_t &p, float gmax, int lane)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+    if (lane == 0 && gmax > 0.0f) atomicMax(reinterpret_cast<unsigned *>(p.counters + PSLAM_C_TILE), __float_as_uint(gmax));
+}
+
 __global__ void __launch_bounds__(kCompThreads)
 k_composite_bwd(pslam_render_t p)
 {
@@ -301,6 +310,7 @@ k_composite_bwd(pslam_render_t p)
     const int q = blockIdx.x * kCompWarps + warp;
     if (q >= Rh) return;
     const int beg = p.samp_off[q], cnt = min(p.samp_off[q + 1], p.sample_cap) - beg;
+    float gmax = 0.0f;
     if (cnt <= 0) return;
     const int ray = p.hit_ray[q];
     const float gt = __ldg(p.target_depth + ray);
@@ -339,7 +349,9 @@ k_composite_bwd(pslam_render_t p)
         if (front) g_s = fmaf(cfs, o.w - 1.0f, g_s);
         if (sm) g_s = fmaf(csdf, (z + o.w * tau) - gt, g_s);
         *reinterpret_cast<float4 *>(p.samp_gout + (size_t)(beg + k) * 4) = make_float4(w * g_r, w * g_g, w * g_b, g_s);
+        gmax = fmaxf(gmax, fmaxf(fmaxf(fabsf(w * g_r), fabsf(w * g_g)), fmaxf(fabsf(w * g_b), fabsf(g_s))));
     }
+    publish_gmax(p, gmax, lane);
 }
 
 // Backward of compositing for ARBITRARY upstream gradients (the autograd route of the drop-in
@@ -354,6 +366,7 @@ k_composite_bwd_ext(pslam_render_t p, const float *__restrict__ g_color, const f
     const int q = blockIdx.x * kCompWarps + warp;
     if (q >= Rh) return;
     const int beg = p.samp_off[q], cnt = min(p.samp_off[q + 1], p.sample_cap) - beg;
+    float gmax = 0.0f;
     if (cnt <= 0) return;
     const float tau = p.truncation;
     const float *ro = p.ray_out + (size_t)q * 8;
@@ -380,7 +393,17 @@ k_composite_bwd_ext(pslam_render_t p, const float *__restrict__ g_color, const f
         float g_s = in ? ((g_w - dot) / U) * (sp * sn * (sn - sp) / tau) : 0.0f;
         if (g_sdf) g_s += g_sdf[beg + k];
         *reinterpret_cast<float4 *>(p.samp_gout + (size_t)(beg + k) * 4) = make_float4(w * g_r, w * g_g, w * g_b, g_s);
+        gmax = fmaxf(gmax, fmaxf(fmaxf(fabsf(w * g_r), fabsf(w * g_g)), fmaxf(fabsf(w * g_b), fabsf(g_s))));
     }
+    publish_gmax(p, gmax, lane);
+}
+
+// before a backward: zero the ray-gradient accumulators and reset the gradient maximum
+__global__ void k_bwd_prologue(pslam_render_t p)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) p.counters[PSLAM_C_TILE] = 0;
+    if ((p.flags & PSLAM_F_GRAD_RAYS) && i < p.R * 3) { p.g_rays_o[i] = 0.0f; p.g_rays_d[i] = 0.0f; }
 }
 
 __global__ void k_zero_f(float *__restrict__ a, int n)
@@ -414,11 +437,8 @@ int launch_loss_coeffs(const pslam_render_t *p, const double *rows, int nrows, c
 int launch_composite_backward_ext(const pslam_render_t *p, const float *g_color, const float *g_depth, const float *g_sdf,
                                   const float *g_weight, cudaStream_t st)
 {
-    if (p->flags & PSLAM_F_GRAD_RAYS) {
-        k_zero_f<<<ceil_div(p->R * 3, 256), 256, 0, st>>>(p->g_rays_o, p->R * 3);
-        k_zero_f<<<ceil_div(p->R * 3, 256), 256, 0, st>>>(p->g_rays_d, p->R * 3);
-        PSLAM_CHECK_LAUNCH("zero_ray_grads");
-    }
+    k_bwd_prologue<<<(p->flags & PSLAM_F_GRAD_RAYS) ? ceil_div(p->R * 3, 256) : 1, 256, 0, st>>>(*p);
+    PSLAM_CHECK_LAUNCH("bwd_prologue");
     k_composite_bwd_ext<<<ceil_div(p->R, kCompWarps), kCompThreads, 0, st>>>(*p, g_color, g_depth, g_sdf, g_weight);
     PSLAM_CHECK_LAUNCH("composite_bwd_ext");
     return 0;
@@ -426,11 +446,8 @@ int launch_composite_backward_ext(const pslam_render_t *p, const float *g_color,
 
 int launch_composite_backward(const pslam_render_t *p, cudaStream_t st)
 {
-    if (p->flags & PSLAM_F_GRAD_RAYS) {
-        k_zero_f<<<ceil_div(p->R * 3, 256), 256, 0, st>>>(p->g_rays_o, p->R * 3);
-        k_zero_f<<<ceil_div(p->R * 3, 256), 256, 0, st>>>(p->g_rays_d, p->R * 3);
-        PSLAM_CHECK_LAUNCH("zero_ray_grads");
-    }
+    k_bwd_prologue<<<(p->flags & PSLAM_F_GRAD_RAYS) ? ceil_div(p->R * 3, 256) : 1, 256, 0, st>>>(*p);
+    PSLAM_CHECK_LAUNCH("bwd_prologue");
     k_composite_bwd<<<ceil_div(p->R, kCompWarps), kCompThreads, 0, st>>>(*p);
     PSLAM_CHECK_LAUNCH("composite_bwd");
     return 0;

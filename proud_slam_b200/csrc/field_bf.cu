@@ -1237,8 +1237,10 @@ int bf_launch_field_backward(const FieldParams &fp_in, int max_samples, cudaStre
     if (!fp.grad_dec) fp.wg_scratch = nullptr;
     // per-launch gradient scale: 4 bytes at the end of the weight-stream region (the f16 stream fills only its first half)
     fp.gscale = reinterpret_cast<uint32_t *>(const_cast<float *>(fp.ws_tc)) + kTcPackFloats - 4;
+    const bool gmax_known = fp.paired && fp.gmax_ready;
+    if (gmax_known) fp.gscale = fp.gmax_ready;          // k_composite_bwd published max |g_out| while it wrote g_out
     if (part != 2) {
-        if (part != 3) {   // part 3 (profiling): the chain kernel alone; the scale of the previous full backward is still there
+        if (!gmax_known && part != 3) {   // part 3 (profiling): the chain kernel alone; the scale of the previous full backward is still there
             cudaError_t e = cudaMemsetAsync(fp.gscale, 0, sizeof(uint32_t), st);
             if (e != cudaSuccess) { set_error("field_bf: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
             k_grad_scale<<<num_sms(), 256, 0, st>>>(reinterpret_cast<const float4 *>(fp.g_out), fp.nsamp, fp.nsamp_dev, fp.gscale);
