@@ -180,6 +180,8 @@ __device__ __forceinline__ void block_sums_d(double (&v)[N], double *s_buf /* [3
     for (int k = 0; k < N; ++k) v[k] = s_tot[k];
 }
 
+__device__ void loss_coeffs_body(const pslam_render_t &p, const double *rows, int nrows);
+
 // Stage A of the loss: this rank's raw sums -> raw[16] (double).  Slots: see RAW_* below.
 enum { RAW_COLOR = 0, RAW_FS, RAW_SDF, RAW_D0, RAW_D1, RAW_NFS, RAW_F0, RAW_F1, RAW_NSDF, RAW_M0, RAW_M1, RAW_RH,
        RAW_DEPTH, RAW_NVALID, RAW_S, RAW_THRESH };
@@ -251,6 +253,8 @@ k_loss_reduce(pslam_render_t p, const float *__restrict__ part_f, const int *__r
         raw[RAW_NFS] = n[0]; raw[RAW_NSDF] = n[1]; raw[RAW_F0] = n[2]; raw[RAW_F1] = n[3]; raw[RAW_M0] = n[4]; raw[RAW_M1] = n[5];
         raw[RAW_RH] = (double)Rh; raw[RAW_DEPTH] = dsum; raw[RAW_NVALID] = nvalid;
         raw[RAW_S] = (double)p.counters[PSLAM_C_S]; raw[RAW_THRESH] = (double)thresh;
+        // single rank: close the loss right here (stage B) instead of a launch of its own
+        if (!(p.flags & PSLAM_F_DEFER_LOSS)) loss_coeffs_body(p, raw, 1);
     }
 }
 
@@ -260,6 +264,11 @@ k_loss_reduce(pslam_render_t p, const float *__restrict__ part_f, const int *__r
 __global__ void k_loss_coeffs(pslam_render_t p, const double *__restrict__ rows, int nrows)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    loss_coeffs_body(p, rows, nrows);
+}
+
+__device__ void loss_coeffs_body(const pslam_render_t &p, const double *rows, int nrows)
+{
     double t[16];
     for (int k = 0; k < 16; ++k) t[k] = 0.0;
     for (int r = 0; r < nrows; ++r) {
@@ -422,7 +431,6 @@ int launch_composite_forward(const pslam_render_t *p, cudaStream_t st)
     if (p->target_depth && p->target_rgb) {
         k_loss_reduce<<<1, 1024, 0, st>>>(*p, part_f, part_i, nb);
         PSLAM_CHECK_LAUNCH("loss_reduce");
-        if (!(p->flags & PSLAM_F_DEFER_LOSS)) return launch_loss_coeffs(p, p->loss_raw, 1, st);
     }
     return 0;
 }
