@@ -37,7 +37,7 @@ WIDTH = 128
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel at the bench workload (ncu --set full, profiles/*_summary.md)
-NCU_TRAFFIC = {0: 985.8e6, 2: 272.4e6}   # 3xF16: k_field_bf<kFwdSave> 12.6 + 259.8 MB (kBwdSaved: 15.7 + 261.2 MB)
+NCU_TRAFFIC = {0: 985.8e6, 2: 273.1e6}   # 3xF16: k_field_bf<kFwdSave> 12.8 + 260.4 MB (kBwdSaved: 16.0 + 261.0 MB)
 
 
 def macs_per_sample(w):
