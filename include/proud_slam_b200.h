@@ -197,7 +197,7 @@ enum {
     PSLAM_C_P = 1,        /* max hits per ray after trimming (P / H) */
     PSLAM_C_NSAMP = 2,    /* total valid samples */
     PSLAM_C_S = 3,        /* max samples per ray (S) */
-    PSLAM_C_OVERFLOW = 4, /* !=0: sample_cap too small or DFS stack overflow */
+    PSLAM_C_OVERFLOW = 4, /* bit 0: sample_cap too small, bit 1: DFS stack overflow, bit 2: decoder operand outside the 3xF16 range */
     PSLAM_C_TILE = 5,     /* internal work counters */
     PSLAM_C_TILE2 = 6,
     PSLAM_C_COUNT = 16

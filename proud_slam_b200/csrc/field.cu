@@ -716,7 +716,7 @@ static int launch_field_t(const FieldParams &fp, int max_samples, cudaStream_t s
 
 // simt_needed = false: a width-128 tensor-core build whose backward is known to have its wgrad workspace (or no decoder
 // gradients), so nothing will run the SIMT kernels on these weights
-static int pack_decoder(const pslam_decoder_t &d, float *ws, cudaStream_t st, bool simt_needed = true)
+static int pack_decoder(const pslam_decoder_t &d, float *ws, cudaStream_t st, bool simt_needed = true, int *range_flag = nullptr)
 {
     if (d.width != 128 || decoder_mode() == 1) simt_needed = true;
     if (simt_needed) {
@@ -725,7 +725,7 @@ static int pack_decoder(const pslam_decoder_t &d, float *ws, cudaStream_t st, bo
         PSLAM_CHECK_LAUNCH("pack_decoder");
     }
     if (d.width == 128 && decoder_mode() == 0) return tc_pack_decoder(d, ws + FieldCfg<128>::WS, st);
-    if (d.width == 128 && decoder_mode() == 2) return bf_pack_decoder(d, ws + FieldCfg<128>::WS, st);
+    if (d.width == 128 && decoder_mode() == 2) return bf_pack_decoder(d, ws + FieldCfg<128>::WS, st, range_flag);
     return 0;
 }
 static const float *tc_region(const pslam_decoder_t &d, const float *ws) { return d.width == 128 ? ws + FieldCfg<128>::WS : nullptr; }
@@ -763,6 +763,7 @@ static FieldParams params_from_render(const pslam_render_t *p)
     fp.grad_rays = (p->flags & PSLAM_F_GRAD_RAYS) ? 1 : 0;
     fp.paired = 1;
     fp.gmax_ready = reinterpret_cast<uint32_t *>(p->counters + PSLAM_C_TILE);
+    fp.range_flag = p->counters + PSLAM_C_OVERFLOW;
     return fp;
 }
 
@@ -772,7 +773,7 @@ int launch_field_forward(const pslam_render_t *p, cudaStream_t st, int part)
     {
         // the SIMT weights are only read by a SIMT backward: decoder gradients wanted without a large enough workspace
         const bool simt = (p->flags & PSLAM_F_GRAD_DEC) && !(p->wgrad_ws && (size_t)p->wgrad_ws_bytes >= (size_t)pslam_wgrad_ws_bytes(p->sample_cap));
-        if (int rc = pack_decoder(p->dec, p->dec_ws, st, simt)) return rc;
+        if (int rc = pack_decoder(p->dec, p->dec_ws, st, simt, p->counters + PSLAM_C_OVERFLOW)) return rc;
     }
     return launch_field(params_from_render(p), false, p->sample_cap, st, part);
 }

@@ -30,6 +30,7 @@ struct FieldParams {
     unsigned char *wg_scratch;      // tcgen05 wgrad scratch (tc_wgrad_scratch_bytes) or nullptr
     uint32_t *act_masks;            // ReLU masks saved by the forward (3xBF16 build, inside wg_scratch; set by its launcher)
     uint32_t *gscale;               // bit pattern of max |g_out| of this backward launch (3xF16 build; set by its launcher)
+    int *range_flag;                // fused pipeline: counters[PSLAM_C_OVERFLOW]; bit 4 = an operand left the 3xF16 window
     uint32_t *gmax_ready;           // fused pipeline: the compositing backward already left that maximum here (counters[PSLAM_C_TILE])
     int paired;                     // forward and backward come from one pslam_render_t (fused pipeline): the forward may save
                                     // its activations for the backward; stand-alone calls (pslam_decoder_*) always recompute
@@ -52,7 +53,7 @@ int tc_launch_field_forward(const FieldParams &fp, int max_samples, cudaStream_t
 int tc_launch_field_backward(const FieldParams &fp, int max_samples, cudaStream_t st, int part = 0);
 size_t tc_wgrad_scratch_bytes(int max_samples);
 // field_bf.cu: 3xBF16 build, same entry points; its weight stream (bf16 hi/lo) fits in the first half of the tc region
-int bf_pack_decoder(const pslam_decoder_t &d, float *ws_tc, cudaStream_t st);
+int bf_pack_decoder(const pslam_decoder_t &d, float *ws_tc, cudaStream_t st, int *range_flag = nullptr);
 int bf_launch_field_forward(const FieldParams &fp, int max_samples, cudaStream_t st, int part = 0);
 int bf_launch_field_backward(const FieldParams &fp, int max_samples, cudaStream_t st, int part = 0);
 size_t bf_wgrad_scratch_bytes(int max_samples);

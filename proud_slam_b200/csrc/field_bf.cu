@@ -97,7 +97,7 @@ constexpr size_t kFinishFloats = 128 * 128 + 128;   // after the tiles: M = G4^T
 
 // Re-packs the decoder into the bf16 weight stream: layers in order, each as ceil(K/32) chunks of
 // [hi block | lo block], each block = kk/8 k-chunks x N rows x 16 B (8 bf16 along K) -- K-major, no swizzle.
-__global__ void k_bf_pack(pslam_decoder_t d, uint16_t *__restrict__ out)
+__global__ void k_bf_pack(pslam_decoder_t d, uint16_t *__restrict__ out, int *__restrict__ range_flag)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int base = 0;   // uint16 offset of the layer in `out`
@@ -109,7 +109,9 @@ __global__ void k_bf_pack(pslam_decoder_t d, uint16_t *__restrict__ out)
             const int ks = k >> 4, c = bf::kstep_chunk(K, ks), kk = bf::chunk_kk(K, c);
             const int kr = bf::kstep_slot(K, ks) * 16 + (k & 15);     // position of k inside its chunk
             uint32_t hi, lo;
-            h16_split2(bf::kScale * tc_weight(d, l, n, k), 0.0f, hi, lo);
+            const float ws = bf::kScale * tc_weight(d, l, n, k);
+            if (range_flag && fabsf(ws) >= 32752.0f) atomicOr(range_flag, 4);
+            h16_split2(ws, 0.0f, hi, lo);
             uint16_t *chunk = out + base + c * (N * bf::kChunkK * 2);
             const int off = (kr >> 3) * (N * 8) + n * 8 + (kr & 7);
             chunk[off] = (uint16_t)(hi & 0xffffu);
@@ -154,7 +156,7 @@ __global__ void k_grad_scale(const float4 *__restrict__ g_out, int n, const int 
 //   MODE 3: y = D/16                                           (dgrad, no activation)
 template <int MODE>
 __device__ __forceinline__ void bf_epilogue16(uint32_t trow, uint32_t dcol, int c0, const float *bias, uint32_t &mask, int shift,
-                                              unsigned char *stg)
+                                              unsigned char *stg, float &ymax)
 {
     using namespace bf;
     uint32_t v[16];
@@ -168,6 +170,7 @@ __device__ __forceinline__ void bf_epilogue16(uint32_t trow, uint32_t dcol, int 
         if (MODE == 1) y = fmaf(y, kInvScale, bias[c0 + e]);
         if (MODE == 2) y = ((mask >> (shift + e)) & 1u) ? y * kInvScale : 0.0f;
         if (MODE == 3) y = y * kInvScale;
+        ymax = fmaxf(ymax, fabsf(y));                // range guard of the f16 operand window (checked once per tile)
         v[e] = __float_as_uint(y);
     }
     if (MODE == 0) mask = shift ? (mask | (bits << 16)) : bits;     // (shift is 0 or 16; the low half is written first)
@@ -413,6 +416,7 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
         const int rowoff_small = (m >> 6) * 4096 + ((m >> 3) & 7) * 256 + (m & 7) * 16;
         uint32_t done_uses = 0;
         uint32_t nomask[2] = {0u, 0u};
+        float ymax = 0.0f;                            // largest |operand| this thread produced (x16 activations, xSg gradients)
         uint32_t nlayers = 0;                         // layers consumed so far: which accumulator buffer the next layer_done() refers to
         uint32_t dcol = cD;                           // accumulator buffer of the layer just completed
         const float Sg = kHasBwd ? grad_scale(p.gscale) : 1.0f, invSg = 1.0f / Sg;
@@ -469,7 +473,7 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
             if (threadIdx.x == 128) BF_TRACE(tile_i, lcount, 7);       // staging buffer is free
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                bf_epilogue16<MODE>(trow, dcol, col0 + 16 * j, bias, mask[j >> 1], (j & 1) * 16, stg);
+                bf_epilogue16<MODE>(trow, dcol, col0 + 16 * j, bias, mask[j >> 1], (j & 1) * 16, stg, ymax);
                 if (j < 3) a_quarter_ready(j);
             }
             if (staged) stage_end();
@@ -532,6 +536,8 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
                 }
                 uint32_t hi[8], lo[8];
                 if (kHasFwd) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) ymax = fmaxf(ymax, fabsf(kScale * f[e]));
 #pragma unroll
                     for (int e = 0; e < 8; ++e) h16_split2(kScale * f[2 * e], kScale * f[2 * e + 1], hi[e], lo[e]);
                     tmem_st8(trow + cAHI + 64, hi);
@@ -705,6 +711,9 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
                 }
             }
         }
+        // f16 saturates at 65504: an operand that reached the top of the window (|activation| or |weight| >= 2047, a
+        // gradient chain that grew 64x beyond max |g_out|) is reported instead of silently clipped
+        if (p.range_flag && ymax >= 32752.0f) atomicOr(p.range_flag, 4);
     }
     fence_before_sync();
     __syncthreads();
@@ -1110,11 +1119,11 @@ __global__ void __launch_bounds__(128, 1) k_debug_umma_bf(const float *__restric
 }
 
 // ------------------------------------------------------------------------------------------
-int bf_pack_decoder(const pslam_decoder_t &d, float *ws_tc, cudaStream_t st)
+int bf_pack_decoder(const pslam_decoder_t &d, float *ws_tc, cudaStream_t st, int *range_flag)
 {
     int total = 0;
     for (int l = 0; l < declayers::kLayersAll; ++l) total += declayers::hN[l] * declayers::hK[l];
-    k_bf_pack<<<ceil_div(total, 256), 256, 0, st>>>(d, reinterpret_cast<uint16_t *>(ws_tc));
+    k_bf_pack<<<ceil_div(total, 256), 256, 0, st>>>(d, reinterpret_cast<uint16_t *>(ws_tc), range_flag);
     PSLAM_CHECK_LAUNCH("bf_pack");
     return 0;
 }

@@ -209,6 +209,9 @@ class RenderPipeline:
         c = self.counters.tolist()
         if c[C_OVERFLOW] & 1:
             raise RuntimeError(f"sample capacity exceeded ({self.sample_cap}); build the pipeline with a larger samples_per_ray")
+        if c[C_OVERFLOW] & 4:
+            raise RuntimeError("a decoder weight, activation or gradient left the range of the 3xF16 tensor-core build "
+                               "(|16 x value| >= 32752); select the 3xTF32 build: pslam_set_option(PSLAM_OPT_DECODER, 0)")
         if c[C_OVERFLOW] & 2:
             raise RuntimeError("octree traversal stack overflow (the reference asserts here, intersect_gpu.cu:235)")
         return dict(R_h=c[C_RH], P=c[C_P], n_samples=c[C_NSAMP], S=c[C_S])

@@ -209,6 +209,31 @@ def test_saved_activations_equal_recompute(device):
         assert rel_err(a, b) < 1e-5
 
 
+def test_f16_operand_range_is_guarded(device):
+    """3xF16 build: operands are kept in f16's window by fixed power-of-two scales; a decoder whose activations leave it
+    (|16 x value| >= 32752) must be reported through the overflow counter, not silently clipped."""
+    from proud_slam_b200 import scene as sc
+    from proud_slam_b200.pipeline import RenderPipeline
+    s, ms = util.build_scene("tiny")
+    msd = {k: v.detach().to(device) for k, v in ms.items()}
+    rays_o, rays_d, rgb, depth = sc.sample_batch(s, [0, 1], 200, seed=5)
+    for gain, expect_error in ((1.0, False), (3.0e5, True)):
+        dec = [p.detach().clone().to(device) for p in util.test_decoder(width=128, seed=1)]
+        dec[0] *= gain                                   # first-layer weights: activations (and the weights themselves) blow up
+        pipe = RenderPipeline(400, device)
+        pipe.bind(rays_o.to(device), rays_d.to(device), msd, dec, voxel_size=s.voxel_size, step_size=0.1 * s.voxel_size,
+                  truncation=0.1, max_distance=10.0, target_rgb=rgb.to(device), target_depth=depth.to(device), seed=1,
+                  forward_only=True)
+        with util.decoder_build("f16"):
+            pipe.step()
+            torch.cuda.synchronize()
+        if expect_error:
+            with pytest.raises(RuntimeError, match="3xF16"):
+                pipe.counts()
+        else:
+            pipe.counts()
+
+
 def test_hash_noise_is_in_range_and_deterministic(device):
     """Production noise (no tensor): same seed -> identical samples; range like the reference's clamp."""
     from oracle import render_oracle as ro
