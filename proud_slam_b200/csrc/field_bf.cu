@@ -307,7 +307,7 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
     }
     if (warp == 0) tmem_alloc(tmem_ptr, kTmemCols);
     // activations / gradients go to the wgrad scratch (the stand-alone backward also runs without decoder gradients)
-    const bool spill = KIND == kFwdSave || KIND == kBwdSaved || (KIND == kBwdRecompute && p.wg_scratch != nullptr);
+    const bool spill = p.wg_scratch != nullptr && p.spill_ops != 0;   // (kFwdSave / kBwdSaved without it: ReLU masks only, e.g. tracking)
     for (int i = threadIdx.x; i < 4 * 128 + 4; i += kThreads) {
         float v;
         if (i < 128) v = p.dec.b1[i];
@@ -1204,7 +1204,11 @@ static int launch_bf(const FieldParams &fp, int max_samples, cudaStream_t st)
 int bf_launch_field_forward(const FieldParams &fp_in, int max_samples, cudaStream_t st, int part)
 {
     FieldParams fp = fp_in;
-    const bool save = g_save_activations && fp.paired && fp.grad_dec && fp.wg_scratch && fp.wg_scratch_bytes >= bf_wgrad_scratch_bytes(max_samples);
+    // the forward saves its ReLU masks for any backward that will follow on this pslam_render_t, and spills the wgrad
+    // operands when that backward wants decoder gradients
+    const bool save = g_save_activations && fp.paired && (fp.grad_dec || fp.grad_emb || fp.grad_rays) && fp.wg_scratch &&
+                      fp.wg_scratch_bytes >= bf_wgrad_scratch_bytes(max_samples);
+    fp.spill_ops = fp.grad_dec;
     if (fp.wg_scratch && fp.wg_scratch == g_saved_scratch) g_saved_scratch = nullptr;
     if (split_trilinear(fp, max_samples)) {
         if (part == 3) fp.feat = scratch_feat(fp, max_samples, 0);      // profiling: the rows of the previous full forward
@@ -1243,7 +1247,8 @@ int bf_launch_field_backward(const FieldParams &fp_in, int max_samples, cudaStre
 {
     FieldParams fp = fp_in;
     cudaEvent_t joined = nullptr;
-    if (!fp.grad_dec) fp.wg_scratch = nullptr;
+    if (!fp.grad_dec && !fp.paired) fp.wg_scratch = nullptr;
+    fp.spill_ops = fp.grad_dec;
     // per-launch gradient scale: 4 bytes at the end of the weight-stream region (the f16 stream fills only its first half)
     fp.gscale = reinterpret_cast<uint32_t *>(const_cast<float *>(fp.ws_tc)) + kTcPackFloats - 4;
     const bool gmax_known = fp.paired && fp.gmax_ready;

@@ -84,7 +84,7 @@ class RenderPipeline:
         self.g_rays_o = torch.zeros(R, 3, **f32)
         self.g_rays_d = torch.zeros(R, 3, **f32)
         self.dec_ws = {w: torch.empty(int(self.lib.pslam_decoder_ws_count(w)), **f32) for w in (128, 256)}
-        self.wgrad_ws = None   # allocated on first use (decoder gradients through the tensor-core path)
+        self.wgrad_ws = None   # allocated on first use (any backward through the tensor-core path)
         self.args = RenderT()
         self._keep = None      # tensors referenced by self.args
         self.R = 0
@@ -142,7 +142,9 @@ class RenderPipeline:
                                                      emb.data_ptr())
         a.dec = _decoder_struct(dec_params)
         a.dec_ws = self.dec_ws[width].data_ptr()
-        if g_dec is not None and width == 128:
+        # width 128: the workspace holds the wgrad operands (decoder gradients) and, for any backward, the forward's ReLU
+        # masks and the feature rows of the stand-alone trilinear kernels
+        if (g_dec is not None or g_emb is not None or grad_rays) and width == 128 and not forward_only:
             if self.wgrad_ws is None:
                 self.wgrad_ws = torch.empty(int(self.lib.pslam_wgrad_ws_bytes(self.sample_cap)), dtype=torch.uint8,
                                             device=self.device)
