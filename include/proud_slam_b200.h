@@ -293,6 +293,21 @@ int pslam_render_step(const pslam_render_t *p, pslam_stream_t stream);
 int pslam_render_stage(const pslam_render_t *p, int stage, pslam_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * SE(3) pose of the tracking loop (src/se3pose.py:24-34, 62-91: 6-vector (t, w), Rodrigues' formula with the
+ * reference's 11-term series; render_helpers.py:679-761: per iteration the sampled camera-frame ray directions
+ * are rotated by the current pose, and the pose takes one Adam step from the rendered loss).
+ * pslam_track_assemble: rays_o[i] = t, rays_d[i] = R(w) rays_d_cam[idx[i]], rgb / depth gathered with the same
+ * indices (NULL outputs are skipped).  pslam_track_pose_step: dL/dpose from dL/d(rays_o, rays_d) (the analytic
+ * derivative of the same series) followed by torch.optim.Adam's update, in place on pose6 and on the optimizer's
+ * exp_avg [6] / exp_avg_sq [6] / step [1] (float, the capturable form); grad_out [6] optional.
+ * ---------------------------------------------------------------------- */
+int pslam_track_assemble(int n, const float *pose6, const long long *idx, const float *rays_d_cam, const float *rgb_all,
+                         const float *depth_all, float *rays_o, float *rays_d, float *rgb, float *depth, pslam_stream_t stream);
+int pslam_track_pose_step(int n, float *pose6, const long long *idx, const float *rays_d_cam, const float *g_rays_o,
+                          const float *g_rays_d, float *exp_avg, float *exp_avg_sq, float *step, double lr, double beta1,
+                          double beta2, double eps, float *grad_out, pslam_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * Host-side octree: torch.classes.svo.Octree,
  * third_party/sparse_octree/src/bindings.cpp:11-35 (init / insert /
  * get_centres_and_children / has_voxel / count_nodes / count_leaf_nodes /

@@ -351,7 +351,7 @@ class GraphTracker:
     frame's own ``sample_rays``, and the frame's tensors are copied into static buffers once per frame."""
 
     def __init__(self, n_pixels, map_states, sdf_network, loss_criteria, voxel_size, N_rays=1024, step_size=0.02, truncation=0.1,
-                 learning_rate=0.01, max_distance=10.0, depth_variance=True, device=None):
+                 learning_rate=0.01, max_distance=10.0, depth_variance=True, device=None, fused_pose=True):
         from ..se3pose import OptimizablePose
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         d = self.device
@@ -372,8 +372,47 @@ class GraphTracker:
         self.base_seed = _next_seed()
         self.hit_mask = torch.zeros(self.N, dtype=torch.bool, device=d)
         self.graph = None
+        # fused_pose: ray assembly from the pose and the pose's Adam step are two kernels of the library
+        # (csrc/pose.cu) instead of ~250 torch launches (Rodrigues series + autograd + optimizer) per iteration;
+        # the Adam state they update is the one torch.optim.Adam owns, so the returned optimizer stays consistent
+        self.fused_pose = bool(fused_pose)
+        if self.fused_pose:
+            p = self.pose.data
+            st = self.optim.state[p]
+            st["step"] = torch.zeros((), dtype=torch.float32, device=d)
+            st["exp_avg"] = torch.zeros_like(p)
+            st["exp_avg_sq"] = torch.zeros_like(p)
+            self.rays_o = torch.zeros(self.N, 3, device=d)
+            self.rays_d = torch.zeros(self.N, 3, device=d)
+            self.rgb = torch.zeros(self.N, 3, device=d)
+            self.depth = torch.zeros(self.N, device=d)
+
+    def _iteration_fused(self):
+        from .. import _lib
+        lib, d = _lib.lib(), self.device
+        idx = torch.randint(0, self.HW, (self.N,), device=d)
+        pose = self.pose.data
+        _lib.check(lib.pslam_track_assemble(self.N, _lib.ptr(pose), _lib.ptr(idx), _lib.ptr(self.rays_d_all), _lib.ptr(self.rgb_all),
+                                            _lib.ptr(self.depth_all), _lib.ptr(self.rays_o), _lib.ptr(self.rays_d), _lib.ptr(self.rgb),
+                                            _lib.ptr(self.depth), _lib.stream_ptr(d)), "pslam_track_assemble")
+        self.counter.add_(1)
+        pipe = self.it.pipe
+        pipe.bind(self.rays_o, self.rays_d, self.ms, self.dec, voxel_size=self.cfg["voxel_size"], step_size=self.cfg["step_size"],
+                  truncation=self.crit["truncation"], max_distance=self.cfg["max_distance"], max_depth=self.crit["max_depth"],
+                  target_rgb=self.rgb, target_depth=self.depth, seed=self.base_seed, seed_dev=self.counter,
+                  weights=self.crit["weights"], tracking=self.cfg["tracking"], grad_rays=True)
+        pipe.step()
+        g = self.optim.param_groups[0]
+        st = self.optim.state[pose]
+        _lib.check(lib.pslam_track_pose_step(self.N, _lib.ptr(pose), _lib.ptr(idx), _lib.ptr(self.rays_d_all), _lib.ptr(pipe.g_rays_o),
+                                             _lib.ptr(pipe.g_rays_d), _lib.ptr(st["exp_avg"]), _lib.ptr(st["exp_avg_sq"]),
+                                             _lib.ptr(st["step"]), float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]),
+                                             float(g["eps"]), None, _lib.stream_ptr(d)), "pslam_track_pose_step")
+        self.hit_mask.copy_(pipe.hit_count[: self.N] > 0)
 
     def _iteration(self):
+        if self.fused_pose:
+            return self._iteration_fused()
         idx = torch.randint(0, self.HW, (self.N,), device=self.device)
         ray_dirs = self.rays_d_all[idx] @ self.pose.rotation().transpose(-1, -2)
         ray_start = self.pose.translation().reshape(1, -1).expand_as(ray_dirs)

@@ -253,6 +253,17 @@ def oracle_field(out, rays_o, rays_d, ms, dec, voxel_size):
 RELU_MARGIN = {"tf32": 2e-6, "simt": 2e-6, "f16": 4e-6}
 
 
+def decoder_near(dec, f, eps):
+    """bool [P]: rows of the feature matrix f with a decoder pre-activation closer to 0 than eps."""
+    with torch.no_grad():
+        W1, b1, W2, b2, W3, b3, W4, b4, W5, b5 = [p.detach() for p in dec]
+        a1 = f @ W1.t() + b1
+        a2 = torch.relu(a1) @ W2.t() + b2
+        t = (torch.relu(a2) @ W3.t() + b3)[:, 1:]
+        a4 = torch.cat([t, f], 1) @ W4.t() + b4
+        return (a1.abs().min(1).values < eps) | (a2.abs().min(1).values < eps) | (a4.abs().min(1).values < eps)
+
+
 def relu_near_samples(out, rays_o, rays_d, ms, dec, voxel_size, eps):
     """bool [P]: samples (oracle / CSR order) with a decoder pre-activation closer to 0 than eps."""
     with torch.no_grad():
