@@ -312,7 +312,21 @@ def track_frame(frame_pose, curr_frame, map_states, sdf_network, resnet, loss_cr
     device = torch.device("cuda", torch.cuda.current_device())
     init_pose = deepcopy(frame_pose).to(device)
     init_pose.requires_grad_(True)
-    optim = torch.optim.Adam(init_pose.parameters(), lr=learning_rate)
+    # the pose side of the iteration (rotation of the sampled rays, dL/dpose, Adam) runs as two kernels of the library
+    # (csrc/pose.cu) when the pose is the 6-vector (t, w) of se3pose.py; any other pose object keeps the torch route
+    pdata = getattr(init_pose, "data", None)
+    fused_pose = (torch.is_tensor(pdata) and tuple(pdata.shape) == (6,) and pdata.dtype == torch.float32 and pdata.is_cuda
+                  and len(list(init_pose.parameters())) == 1)
+    optim = torch.optim.Adam(init_pose.parameters(), lr=learning_rate, capturable=fused_pose)
+    if fused_pose:
+        from .. import _lib
+        lib = _lib.lib()
+        st = optim.state[init_pose.data]
+        st["step"] = torch.zeros((), dtype=torch.float32, device=device)
+        st["exp_avg"] = torch.zeros_like(init_pose.data)
+        st["exp_avg_sq"] = torch.zeros_like(init_pose.data)
+        grp = optim.param_groups[0]
+        idx_all = torch.arange(N_rays, device=device)
     ms = _device_states(map_states, device)
     ms["voxel_vertex_emb"] = ms["voxel_vertex_emb"].detach().contiguous()
     dec = [p.detach().to(device).contiguous() for p in decoder_params_of(sdf_network)]
@@ -326,22 +340,37 @@ def track_frame(frame_pose, curr_frame, map_states, sdf_network, resnet, loss_cr
         ray_dirs = curr_frame.rays_d.to(device)[sample_mask]
         rgb = curr_frame.rgb.to(device)[sample_mask].float().contiguous()
         depth = curr_frame.depth.to(device)[sample_mask].float().contiguous()
-        ray_dirs_iter = ray_dirs @ init_pose.rotation().transpose(-1, -2)
-        ray_start_iter = init_pose.translation().reshape(1, -1).expand_as(ray_dirs_iter)
+        if fused_pose:
+            ray_dirs = ray_dirs.float().contiguous()
+            R = ray_dirs.shape[0]
+            idx = idx_all[:R] if R <= idx_all.numel() else torch.arange(R, device=device)
+            ray_start_iter, ray_dirs_iter = torch.empty_like(ray_dirs), torch.empty_like(ray_dirs)
+            _lib.check(lib.pslam_track_assemble(R, _lib.ptr(init_pose.data), _lib.ptr(idx), _lib.ptr(ray_dirs), None, None,
+                                                _lib.ptr(ray_start_iter), _lib.ptr(ray_dirs_iter), None, None, _lib.stream_ptr(device)),
+                       "pslam_track_assemble")
+        else:
+            ray_dirs_iter = ray_dirs @ init_pose.rotation().transpose(-1, -2)
+            ray_start_iter = init_pose.translation().reshape(1, -1).expand_as(ray_dirs_iter)
         it.run(ray_start_iter.detach().float().contiguous(), ray_dirs_iter.detach().float().contiguous(), rgb, depth, ms, dec, crit,
                voxel_size=voxel_size, step_size=step_size, max_distance=max_distance, tracking=depth_variance, grad_emb=False,
                grad_dec=False, grad_rays=True, seed=_next_seed())
-        optim.zero_grad()
         R = ray_dirs_iter.shape[0]
-        torch.autograd.backward([ray_start_iter, ray_dirs_iter], [it.pipe.g_rays_o[:R], it.pipe.g_rays_d[:R]])
-        optim.step()
+        if fused_pose:
+            _lib.check(lib.pslam_track_pose_step(R, _lib.ptr(init_pose.data), _lib.ptr(idx), _lib.ptr(ray_dirs), _lib.ptr(it.pipe.g_rays_o),
+                                                 _lib.ptr(it.pipe.g_rays_d), _lib.ptr(st["exp_avg"]), _lib.ptr(st["exp_avg_sq"]),
+                                                 _lib.ptr(st["step"]), float(grp["lr"]), float(grp["betas"][0]), float(grp["betas"][1]),
+                                                 float(grp["eps"]), None, _lib.stream_ptr(device)), "pslam_track_pose_step")
+        else:
+            optim.zero_grad()
+            torch.autograd.backward([ray_start_iter, ray_dirs_iter], [it.pipe.g_rays_o[:R], it.pipe.g_rays_d[:R]])
+            optim.step()
         hit_mask = it.pipe.hit_count[:R] > 0
     return init_pose, optim, hit_mask
 
 
 # ------------------------------------------------------------------------------------------
 # CUDA-graph tracker: the whole tracking iteration (pixel sampling, ray assembly from the pose,
-# fused render + loss + backward, pose autograd, Adam) captured once and replayed per iteration
+# fused render + loss + backward, pose gradient + Adam) captured once and replayed per iteration
 # ------------------------------------------------------------------------------------------
 class GraphTracker:
     """Per-frame pose optimisation of ``track_frame`` (render_helpers.py:679-761) without per-iteration
