@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PSLAM_ABI_VERSION 1
+#define PSLAM_ABI_VERSION 2
 #define PSLAM_E_ARG (-1)      /* null pointer / non-positive size */
 #define PSLAM_E_RANGE (-2)    /* size outside what the kernels support */
 #define PSLAM_E_ALIGN (-3)    /* pointer not 16-byte aligned where required */
@@ -259,6 +259,11 @@ typedef struct {
     float *g_emb;                          /* [E,16] += */
     pslam_decoder_grad_t g_dec;            /* += */
     float *g_rays_o, *g_rays_d;            /* [R,3] by ray id, overwritten */
+    /* optional traversal cache: [N,8] x 16 B child records (child row id + child centre), rebuilt by every
+     * pslam_render_sample from `structure` / `centres`; halves the dependent-load chain of the octree walk.
+     * NULL or node_cache_bytes < 128*N: the walk reads the two arrays directly. */
+    void *node_cache;
+    int64_t node_cache_bytes;
 } pslam_render_t;
 
 /* sizeof(pslam_render_t) and offsetof(.., loss): lets a binding check its mirror of the struct. */

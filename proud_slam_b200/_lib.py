@@ -40,7 +40,7 @@ class RenderT(C.Structure):
                                      "samp_off", "samp_vox", "samp_ray", "samp_z", "samp_dist", "samp_out",
                                      "samp_w", "samp_gout", "ray_out", "scratch_i", "scratch_f", "counters")]
         + [("loss_raw", C.c_void_p), ("loss", C.c_void_p), ("g_emb", C.c_void_p), ("g_dec", DecoderGradT),
-           ("g_rays_o", C.c_void_p), ("g_rays_d", C.c_void_p)]
+           ("g_rays_o", C.c_void_p), ("g_rays_d", C.c_void_p), ("node_cache", C.c_void_p), ("node_cache_bytes", C.c_int64)]
     )
 
 

@@ -182,11 +182,30 @@ constexpr int kWideStack = 64;                   // 7 pending siblings per level
 constexpr int kWideHits = 50;                    // == n_max of the reference (voxel_helpers.py:561)
 constexpr size_t kWideSmem = sizeof(int) * 3 * (kWideStack + kWideHits) * kWideRays;
 
+// Child records for the walk: rec[node][c] = (row id of child c or -1, centre of that child).  Expanding a node then
+// costs ONE dependent 16-byte load per lane instead of two (child id, then its centre): the walk is a chain of ~25
+// dependent expansions per ray and nothing but that chain's latency.
+__global__ void k_build_child_records(int N, const float *__restrict__ points, const int *__restrict__ children, int4 *__restrict__ rec)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * 8) return;
+    const int node = t >> 3, c = t & 7;
+    const int cid = __ldg(children + (int64_t)node * 9 + c);
+    int4 r = make_int4(cid, 0, 0, 0);
+    if (cid > -1) {
+        r.y = __float_as_int(__ldg(points + (int64_t)cid * 3));
+        r.z = __float_as_int(__ldg(points + (int64_t)cid * 3 + 1));
+        r.w = __float_as_int(__ldg(points + (int64_t)cid * 3 + 2));
+    }
+    rec[t] = r;
+}
+
+template <bool CACHED>
 __global__ void __launch_bounds__(kWideThreads)
 k_intersect_wide(int R, float half_voxel, int n_max, float max_distance, const float *__restrict__ ray_start,
                  const float *__restrict__ ray_dir, const float *__restrict__ points, const int *__restrict__ children,
-                 int *__restrict__ hit_idx, float *__restrict__ hit_min, float *__restrict__ hit_max, int *__restrict__ hit_count,
-                 int *__restrict__ block_hits, int *__restrict__ counters)
+                 const int4 *__restrict__ rec, int *__restrict__ hit_idx, float *__restrict__ hit_min, float *__restrict__ hit_max,
+                 int *__restrict__ hit_count, int *__restrict__ block_hits, int *__restrict__ counters)
 {
     extern __shared__ int s_wide[];
     int *s_id = s_wide;                                                    // [kWideStack][kWideRays]: id | log2(side) << 26
@@ -218,10 +237,17 @@ k_intersect_wide(int R, float half_voxel, int n_max, float max_distance, const f
         float lo = 0.f, hi = 0.f;
         const int cside = cur_side >> 1;
         if (cur >= 0) {
-            cid = __ldg(children + (int64_t)cur * 9 + sub);
-            if (cid > -1)
-                hit = slab(ray, __ldg(points + (int64_t)cid * 3), __ldg(points + (int64_t)cid * 3 + 1), __ldg(points + (int64_t)cid * 3 + 2),
-                           __fmul_rn(half_voxel, (float)cside), lo, hi);
+            if (CACHED) {
+                const int4 r4 = __ldg(rec + (int64_t)cur * 8 + sub);
+                cid = r4.x;
+                if (cid > -1)
+                    hit = slab(ray, __int_as_float(r4.y), __int_as_float(r4.z), __int_as_float(r4.w), __fmul_rn(half_voxel, (float)cside), lo, hi);
+            } else {
+                cid = __ldg(children + (int64_t)cur * 9 + sub);
+                if (cid > -1)
+                    hit = slab(ray, __ldg(points + (int64_t)cid * 3), __ldg(points + (int64_t)cid * 3 + 1), __ldg(points + (int64_t)cid * 3 + 2),
+                               __fmul_rn(half_voxel, (float)cside), lo, hi);
+            }
         }
         const unsigned mine = (__ballot_sync(0xffffffffu, hit) >> (lane & ~7)) & 0xFFu;
         if (hit) {
@@ -538,7 +564,10 @@ int launch_intersect_fused(const pslam_render_t *p, cudaStream_t st)
 {
     const int nb = ceil_div(p->R, kWideRays);
     int *block_hits = p->scratch_i;  // [nb]
-    {
+    // the record table costs a pass over the octree per call: worth it while the walk (about 64 node tests per ray) is the larger job
+    const bool cached = p->node_cache && p->node_cache_bytes >= (int64_t)128 * p->N && ((uintptr_t)p->node_cache % 16 == 0) &&
+                        (int64_t)p->N * 8 <= (int64_t)p->R * 256;
+    if (!cached) {   // (building the record table reads both arrays and leaves the table in L2: no separate prefetch then)
         const size_t na = (size_t)p->N * 12, nbytes = (size_t)p->N * 36;
         k_prefetch_l2<<<(int)ceil_div64((int64_t)(nbytes / 128 + 1), 256), 256, 0, st>>>(reinterpret_cast<const char *>(p->centres), na,
                                                                                   reinterpret_cast<const char *>(p->structure), nbytes);
@@ -546,13 +575,23 @@ int launch_intersect_fused(const pslam_render_t *p, cudaStream_t st)
     }
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_intersect_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWideSmem);
+        cudaError_t e = cudaFuncSetAttribute(k_intersect_wide<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWideSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_intersect_wide<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWideSmem);
         if (e != cudaSuccess) { set_error("intersect: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         configured = true;
     }
-    k_intersect_wide<<<nb, kWideThreads, kWideSmem, st>>>(p->R, (float)(p->voxel_size * 0.5), p->n_max, p->max_distance, p->rays_o,
-                                                         p->rays_d, p->centres, p->structure, p->hit_idx, p->hit_min, p->hit_max,
-                                                         p->hit_count, block_hits, p->counters);
+    if (cached) {
+        int4 *rec = static_cast<int4 *>(p->node_cache);
+        k_build_child_records<<<(int)ceil_div64((int64_t)p->N * 8, 256), 256, 0, st>>>(p->N, p->centres, p->structure, rec);
+        PSLAM_CHECK_LAUNCH("build_child_records");
+        k_intersect_wide<true><<<nb, kWideThreads, kWideSmem, st>>>(p->R, (float)(p->voxel_size * 0.5), p->n_max, p->max_distance, p->rays_o,
+                                                                   p->rays_d, p->centres, p->structure, rec, p->hit_idx, p->hit_min,
+                                                                   p->hit_max, p->hit_count, block_hits, p->counters);
+    } else {
+        k_intersect_wide<false><<<nb, kWideThreads, kWideSmem, st>>>(p->R, (float)(p->voxel_size * 0.5), p->n_max, p->max_distance, p->rays_o,
+                                                                    p->rays_d, p->centres, p->structure, nullptr, p->hit_idx, p->hit_min,
+                                                                    p->hit_max, p->hit_count, block_hits, p->counters);
+    }
     PSLAM_CHECK_LAUNCH("intersect_wide");
     if (int rc = scan_partials(block_hits, nb, p->counters + PSLAM_C_RH, st)) return rc;
     k_compact_rays<<<nb, kWideRays, 0, st>>>(p->R, p->hit_count, block_hits, p->hit_ray, p->ray_rank);

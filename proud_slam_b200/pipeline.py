@@ -85,6 +85,7 @@ class RenderPipeline:
         self.g_rays_d = torch.zeros(R, 3, **f32)
         self.dec_ws = {w: torch.empty(int(self.lib.pslam_decoder_ws_count(w)), **f32) for w in (128, 256)}
         self.wgrad_ws = None   # allocated on first use (any backward through the tensor-core path)
+        self.node_cache = None
         self.args = RenderT()
         self._keep = None      # tensors referenced by self.args
         self.R = 0
@@ -142,6 +143,11 @@ class RenderPipeline:
                                                      emb.data_ptr())
         a.dec = _decoder_struct(dec_params)
         a.dec_ws = self.dec_ws[width].data_ptr()
+        # traversal cache of the octree walk: 128 B per octree row, rebuilt by every sample() from the bound map
+        need = 128 * int(centres.shape[0])
+        if self.node_cache is None or self.node_cache.numel() < need:
+            self.node_cache = torch.empty(need, dtype=torch.uint8, device=self.device)
+        a.node_cache, a.node_cache_bytes = self.node_cache.data_ptr(), self.node_cache.numel()
         # width 128: the workspace holds the wgrad operands (decoder gradients) and, for any backward, the forward's ReLU
         # masks and the feature rows of the stand-alone trilinear kernels
         if (g_dec is not None or g_emb is not None or grad_rays) and width == 128 and not forward_only:

@@ -53,7 +53,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 25
     for n in names:
         assert hasattr(h, n), f"{n} declared in include/proud_slam_b200.h but not exported"
-    assert h.pslam_abi_version() == 1
+    assert h.pslam_abi_version() == 2
 
 
 def test_python_mirror_matches_header_and_struct():
