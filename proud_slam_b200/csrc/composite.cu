@@ -222,15 +222,34 @@ k_loss_reduce(pslam_render_t p, const float *__restrict__ part_f, const int *__r
                 if ((bits & himask) == prefix) atomicAdd(&s_hist[(bits >> shift) & 255u], 1u);
             }
             __syncthreads();
-            if (tid == 0) {
-                unsigned rank = s_rank, acc = 0u;
-                int bin = 0;
-                for (; bin < 255; ++bin) {
-                    if (acc + s_hist[bin] > rank) break;
-                    acc += s_hist[bin];
+            if (tid < 32) {
+                // bin of the wanted rank: warp-parallel prefix over the 256 counts (8 per lane) instead of a serial walk
+                const unsigned rank = s_rank;
+                unsigned c[8], sum = 0u;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { c[k] = s_hist[tid * 8 + k]; sum += c[k]; }
+                unsigned incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (tid >= o) incl += y;
                 }
-                s_rank = rank - acc;
-                s_prefix = prefix | ((unsigned)bin << shift);
+                const unsigned excl = incl - sum;
+                const bool mine = rank >= excl && rank < incl;          // exactly one lane (the counts sum to more than rank)
+                const unsigned owner = __ballot_sync(0xffffffffu, mine);
+                if (mine) {
+                    unsigned acc = excl;
+                    int k = 0;
+                    for (; k < 7; ++k) {
+                        if (acc + c[k] > rank) break;
+                        acc += c[k];
+                    }
+                    s_rank = rank - acc;
+                    s_prefix = prefix | ((unsigned)(tid * 8 + k) << shift);
+                } else if (owner == 0u && tid == 31) {                  // (cannot happen for rank < count; mirrors the old walk's last bin)
+                    s_rank = rank - (incl - c[7]);
+                    s_prefix = prefix | (255u << shift);
+                }
             }
             __syncthreads();
         }
