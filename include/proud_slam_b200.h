@@ -304,13 +304,14 @@ int pslam_render_stage(const pslam_render_t *p, int stage, pslam_stream_t stream
  * pslam_track_assemble: rays_o[i] = t, rays_d[i] = R(w) rays_d_cam[idx[i]], rgb / depth gathered with the same
  * indices (NULL outputs are skipped).  pslam_track_pose_step: dL/dpose from dL/d(rays_o, rays_d) (the analytic
  * derivative of the same series) followed by torch.optim.Adam's update, in place on pose6 and on the optimizer's
- * exp_avg [6] / exp_avg_sq [6] / step [1] (float, the capturable form); grad_out [6] optional.
+ * exp_avg [6] / exp_avg_sq [6] / step [1] (float, the capturable form; step == NULL: the count lives on the host
+ * and step_value is its new value); grad_out [6] optional.
  * ---------------------------------------------------------------------- */
 int pslam_track_assemble(int n, const float *pose6, const long long *idx, const float *rays_d_cam, const float *rgb_all,
                          const float *depth_all, float *rays_o, float *rays_d, float *rgb, float *depth, pslam_stream_t stream);
 int pslam_track_pose_step(int n, float *pose6, const long long *idx, const float *rays_d_cam, const float *g_rays_o,
-                          const float *g_rays_d, float *exp_avg, float *exp_avg_sq, float *step, double lr, double beta1,
-                          double beta2, double eps, float *grad_out, pslam_stream_t stream);
+                          const float *g_rays_d, float *exp_avg, float *exp_avg_sq, float *step, double step_value, double lr,
+                          double beta1, double beta2, double eps, float *grad_out, pslam_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * Host-side octree: torch.classes.svo.Octree,

@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256) k_track_pose_step(int n, float *__restric
                                                          const float *__restrict__ dirs, const float *__restrict__ g_o,
                                                          const float *__restrict__ g_d, float *__restrict__ exp_avg,
                                                          float *__restrict__ exp_avg_sq, float *__restrict__ step, float lr, float beta1,
-                                                         float beta2, float omb1, float omb2, float eps, float *__restrict__ grad_out)
+                                                         float beta2, float omb1, float omb2, float eps, float step_value, float *__restrict__ grad_out)
 {
     __shared__ float s_part[8][12];
     float acc[12];
@@ -134,8 +134,9 @@ __global__ void __launch_bounds__(256) k_track_pose_step(int n, float *__restric
         grad[3 + k] = gk;
     }
     // torch.optim.Adam (no weight decay, no amsgrad), capturable form: the step count is a float tensor on the device
-    const float t = *step + 1.0f;
-    *step = t;
+    // step == NULL: the optimizer keeps its count on the host (non-capturable Adam) and passes the new value
+    const float t = step ? *step + 1.0f : step_value;
+    if (step) *step = t;
     const float bc1 = 1.0f - powf(beta1, t), bc2 = 1.0f - powf(beta2, t);
     for (int k = 0; k < 6; ++k) {
         const float g = grad[k];
@@ -162,13 +163,13 @@ extern "C" int pslam_track_assemble(int n, const float *pose6, const long long *
 }
 
 extern "C" int pslam_track_pose_step(int n, float *pose6, const long long *idx, const float *rays_d_cam, const float *g_rays_o,
-                                     const float *g_rays_d, float *exp_avg, float *exp_avg_sq, float *step, double lr, double beta1,
-                                     double beta2, double eps, float *grad_out, pslam_stream_t stream)
+                                     const float *g_rays_d, float *exp_avg, float *exp_avg_sq, float *step, double step_value, double lr,
+                                     double beta1, double beta2, double eps, float *grad_out, pslam_stream_t stream)
 {
-    PSLAM_CHECK_ARG(n > 0 && pose6 && idx && rays_d_cam && g_rays_o && g_rays_d && exp_avg && exp_avg_sq && step, PSLAM_E_ARG,
-                    "track_pose_step: bad argument");
+    PSLAM_CHECK_ARG(n > 0 && pose6 && idx && rays_d_cam && g_rays_o && g_rays_d && exp_avg && exp_avg_sq && (step || step_value >= 1.0),
+                    PSLAM_E_ARG, "track_pose_step: bad argument");
     k_track_pose_step<<<1, 256, 0, (cudaStream_t)stream>>>(n, pose6, idx, rays_d_cam, g_rays_o, g_rays_d, exp_avg, exp_avg_sq, step, (float)lr,
-                                                           (float)beta1, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps, grad_out);
+                                                           (float)beta1, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps, (float)step_value, grad_out);
     PSLAM_CHECK_LAUNCH("track_pose_step");
     return 0;
 }

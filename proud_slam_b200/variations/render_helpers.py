@@ -258,12 +258,27 @@ def bundle_adjust_frames(keyframe_graph, map_states, sdf_network, resnet, loss_c
     """render_helpers.py:559-676.  Same loop; per iteration the rays of all keyframes are assembled as
     in the reference (pose autograd kept in torch, se3pose.py), then ONE fused call produces the loss
     and every gradient; ``.grad`` fields are filled and the caller's optimizers stepped."""
-    optimizers = [embed_optim] + ([model_optim] if model_optim is not None else [])
-    for keyframe in keyframe_graph:
-        if keyframe.stamp != 0 and update_pose:
-            optimizers += [keyframe.optim]
+    from .. import _lib
+    lib = _lib.lib()
     emb = map_states["voxel_vertex_emb"]
     device = emb.device if emb.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    optimizers = [embed_optim] + ([model_optim] if model_optim is not None else [])
+    # Keyframes whose pose is the 6-vector (t, w) of se3pose.py on this device with a plain Adam of their own take the
+    # pose side of the iteration (rotation of the sampled rays, dL/dpose, Adam) as two kernels per frame (csrc/pose.cu)
+    # instead of ~250 torch launches per frame and iteration; any other frame keeps the torch route.
+    fused = {}
+    for keyframe in keyframe_graph:
+        pose_obj, opt = getattr(keyframe, "pose", None), getattr(keyframe, "optim", None)
+        pdata = getattr(pose_obj, "data", None)
+        ok = (torch.is_tensor(pdata) and tuple(pdata.shape) == (6,) and pdata.dtype == torch.float32 and pdata.is_cuda
+              and pdata.device == device and isinstance(opt, torch.optim.Adam) and len(opt.param_groups) == 1
+              and len(opt.param_groups[0]["params"]) == 1 and opt.param_groups[0]["params"][0] is pdata
+              and not opt.param_groups[0].get("amsgrad", False) and opt.param_groups[0].get("weight_decay", 0) == 0
+              and not opt.param_groups[0].get("maximize", False))
+        if ok:
+            fused[id(keyframe)] = True
+        elif keyframe.stamp != 0 and update_pose:
+            optimizers += [keyframe.optim]
     ms = _device_states(map_states, device)
     dec_params = decoder_params_of(sdf_network)
     crit = _criterion_cfg(loss_criteria)
@@ -271,21 +286,36 @@ def bundle_adjust_frames(keyframe_graph, map_states, sdf_network, resnet, loss_c
     it = FusedIteration(N_rays * max(len(keyframe_graph), 1), device, int(dec_params[0].shape[0]))
     for _ in range(num_iterations):
         rays_o, rays_d, rgb_samples, depth_samples = [], [], [], []
+        cam_dirs = []
         for frame in keyframe_graph:
-            pose = frame.get_pose().to(device)
             frame.sample_rays(N_rays)
             sample_mask = frame.sample_mask.to(device)
             sampled_rays_d = frame.rays_d.to(device)[sample_mask]
-            sampled_rays_d = sampled_rays_d @ pose[:3, :3].transpose(-1, -2)
-            rays_d += [sampled_rays_d]
-            rays_o += [pose[:3, 3].reshape(1, -1).expand_as(sampled_rays_d)]
+            if id(frame) in fused:
+                cam = sampled_rays_d.float().contiguous()
+                n = cam.shape[0]
+                idx = torch.arange(n, device=device)
+                o_k, d_k = torch.empty_like(cam), torch.empty_like(cam)
+                _lib.check(lib.pslam_track_assemble(n, _lib.ptr(frame.pose.data), _lib.ptr(idx), _lib.ptr(cam), None, None, _lib.ptr(o_k),
+                                                    _lib.ptr(d_k), None, None, _lib.stream_ptr(device)), "pslam_track_assemble")
+                cam_dirs += [(cam, idx)]
+                rays_d += [d_k]
+                rays_o += [o_k]
+            else:
+                pose = frame.get_pose().to(device)
+                cam_dirs += [None]
+                sampled_rays_d = sampled_rays_d @ pose[:3, :3].transpose(-1, -2)
+                rays_d += [sampled_rays_d]
+                rays_o += [pose[:3, 3].reshape(1, -1).expand_as(sampled_rays_d)]
             rgb_samples += [frame.rgb.to(device)[sample_mask]]
             depth_samples += [frame.depth.to(device)[sample_mask]]
+        counts = [t.shape[0] for t in rays_d]
         rays_d = torch.cat(rays_d, dim=0)
         rays_o = torch.cat(rays_o, dim=0)
         rgb_samples = torch.cat(rgb_samples, dim=0).float().contiguous()
         depth_samples = torch.cat(depth_samples, dim=0).float().contiguous()
-        need_pose = rays_d.requires_grad or rays_o.requires_grad
+        torch_pose = rays_d.requires_grad or rays_o.requires_grad
+        need_pose = torch_pose or (update_pose and any(id(f) in fused and f.stamp != 0 for f in keyframe_graph))
         ms["voxel_vertex_emb"] = emb.detach() if emb.is_cuda else emb.detach().to(device)
         dec = [p.detach() for p in dec_params]
         it.run(rays_o.detach().float().contiguous(), rays_d.detach().float().contiguous(), rgb_samples, depth_samples, ms, dec, crit,
@@ -297,11 +327,31 @@ def bundle_adjust_frames(keyframe_graph, map_states, sdf_network, resnet, loss_c
         if model_optim is not None:
             for p, g in zip(dec_params, it.g_dec):
                 p.grad = g.clone()
-        if need_pose:
+        if torch_pose:
             R = rays_o.shape[0]
             torch.autograd.backward([rays_o, rays_d], [it.pipe.g_rays_o[:R], it.pipe.g_rays_d[:R]])
         for optim in optimizers:
             optim.step()
+        off = 0
+        for frame, cd, n in zip(keyframe_graph, cam_dirs, counts):
+            if cd is not None and frame.stamp != 0 and update_pose and n > 0:
+                cam, idx = cd
+                opt, pdata = frame.optim, frame.pose.data
+                grp, st = opt.param_groups[0], opt.state[pdata]
+                if len(st) == 0:                                   # what torch.optim.Adam creates on its first step
+                    st["step"] = (torch.zeros((), dtype=torch.float32, device=device) if grp.get("capturable", False)
+                                  else torch.tensor(0.0, dtype=torch.float32))
+                    st["exp_avg"] = torch.zeros_like(pdata)
+                    st["exp_avg_sq"] = torch.zeros_like(pdata)
+                on_dev = st["step"].is_cuda
+                if not on_dev:
+                    st["step"] += 1                                # host-side count: passed by value
+                _lib.check(lib.pslam_track_pose_step(n, _lib.ptr(pdata), _lib.ptr(idx), _lib.ptr(cam), _lib.ptr(it.pipe.g_rays_o[off:off + n]),
+                                                     _lib.ptr(it.pipe.g_rays_d[off:off + n]), _lib.ptr(st["exp_avg"]), _lib.ptr(st["exp_avg_sq"]),
+                                                     _lib.ptr(st["step"]) if on_dev else None, 0.0 if on_dev else float(st["step"]),
+                                                     float(grp["lr"]), float(grp["betas"][0]), float(grp["betas"][1]), float(grp["eps"]),
+                                                     None, _lib.stream_ptr(device)), "pslam_track_pose_step")
+            off += n
 
 
 def track_frame(frame_pose, curr_frame, map_states, sdf_network, resnet, loss_criteria, voxel_size, N_rays=512, step_size=0.05,
@@ -358,7 +408,7 @@ def track_frame(frame_pose, curr_frame, map_states, sdf_network, resnet, loss_cr
         if fused_pose:
             _lib.check(lib.pslam_track_pose_step(R, _lib.ptr(init_pose.data), _lib.ptr(idx), _lib.ptr(ray_dirs), _lib.ptr(it.pipe.g_rays_o),
                                                  _lib.ptr(it.pipe.g_rays_d), _lib.ptr(st["exp_avg"]), _lib.ptr(st["exp_avg_sq"]),
-                                                 _lib.ptr(st["step"]), float(grp["lr"]), float(grp["betas"][0]), float(grp["betas"][1]),
+                                                 _lib.ptr(st["step"]), 0.0, float(grp["lr"]), float(grp["betas"][0]), float(grp["betas"][1]),
                                                  float(grp["eps"]), None, _lib.stream_ptr(device)), "pslam_track_pose_step")
         else:
             optim.zero_grad()
@@ -435,7 +485,7 @@ class GraphTracker:
         st = self.optim.state[pose]
         _lib.check(lib.pslam_track_pose_step(self.N, _lib.ptr(pose), _lib.ptr(idx), _lib.ptr(self.rays_d_all), _lib.ptr(pipe.g_rays_o),
                                              _lib.ptr(pipe.g_rays_d), _lib.ptr(st["exp_avg"]), _lib.ptr(st["exp_avg_sq"]),
-                                             _lib.ptr(st["step"]), float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]),
+                                             _lib.ptr(st["step"]), 0.0, float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]),
                                              float(g["eps"]), None, _lib.stream_ptr(d)), "pslam_track_pose_step")
         self.hit_mask.copy_(pipe.hit_count[: self.N] > 0)
 

@@ -226,6 +226,7 @@ def test_fused_pose_kernels_match_torch_autograd_and_adam(device):
     opt = torch.optim.Adam(ref.parameters(), lr=0.01, capturable=True)
     pose = init.clone().to(device)
     m, v, step = torch.zeros(6, device=device), torch.zeros(6, device=device), torch.zeros((), device=device)
+    pose_h, m_h, v_h = init.clone().to(device), torch.zeros(6, device=device), torch.zeros(6, device=device)
     rays_o, rays_d = torch.empty(N, 3, device=device), torch.empty(N, 3, device=device)
     rgb, depth = torch.empty(N, 3, device=device), torch.empty(N, device=device)
     grad = torch.empty(6, device=device)
@@ -248,9 +249,13 @@ def test_fused_pose_kernels_match_torch_autograd_and_adam(device):
             assert rel_err(rays_d, rd.detach()) < 1e-6 and rel_err(rays_o, ro_ref) < 1e-6
             assert torch.equal(rgb, rgb_all[idx]) and torch.equal(depth, depth_all[idx])
         _lib.check(lib.pslam_track_pose_step(N, _lib.ptr(pose), _lib.ptr(idx), _lib.ptr(dirs), _lib.ptr(g_o), _lib.ptr(g_d), _lib.ptr(m),
-                                             _lib.ptr(v), _lib.ptr(step), 0.01, 0.9, 0.999, 1e-8, _lib.ptr(grad), _lib.stream_ptr(device)), "pose step")
+                                             _lib.ptr(v), _lib.ptr(step), 0.0, 0.01, 0.9, 0.999, 1e-8, _lib.ptr(grad), _lib.stream_ptr(device)), "pose step")
+        # host-side step count (non-capturable Adam): step == NULL, the new count passed by value
+        _lib.check(lib.pslam_track_pose_step(N, _lib.ptr(pose_h), _lib.ptr(idx), _lib.ptr(dirs), _lib.ptr(g_o), _lib.ptr(g_d), _lib.ptr(m_h),
+                                             _lib.ptr(v_h), None, float(it + 1), 0.01, 0.9, 0.999, 1e-8, None, _lib.stream_ptr(device)), "pose step")
         torch.cuda.synchronize()
         assert rel_err(grad, ref_grad) < 1e-5, it
         assert rel_err(pose, ref.data.detach()) < 1e-5, it
+        assert torch.equal(pose_h, pose) and torch.equal(m_h, m) and torch.equal(v_h, v)
     st = opt.state[ref.data]
     assert rel_err(m, st["exp_avg"]) < 1e-5 and rel_err(v, st["exp_avg_sq"]) < 1e-5 and float(step) == float(st["step"])
