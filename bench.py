@@ -54,27 +54,75 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed regions.  The regions are tens of milliseconds long, so the
+    samples come from NVML in a thread (every 2 ms); `nvidia-smi -lms` as a subprocess is the fallback when the NVML
+    bindings are missing (it needs ~100 ms to deliver its first line)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self.thread, self.active, self.alive = index, [], None, None, None, False, False
+        self.reason_bits, self.max_mhz = 0, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        nv = self.nvml
+        while self.alive:
+            if self.active:
+                try:
+                    self.rows.append(int(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                    self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    pass
+            time.sleep(0.002)
 
     def start(self):
+        """begin (or resume) sampling: call right before a timed region"""
+        if self.nvml is not None:
+            if self.thread is None:
+                self.alive = True
+                self.thread = threading.Thread(target=self._poll, daemon=True)
+                self.thread.start()
+            self.active = True
+            return
+        if self.proc is not None:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
+
+    def pause(self):
+        """right after a timed region"""
+        self.active = False
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.active = self.alive = False
+            nv, sm, b = self.nvml, sorted(self.rows), self.reason_bits
+            names = [("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+                     ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap")]
+            alt = {"nvmlClocksEventReasonHwSlowdown": 0x8, "nvmlClocksEventReasonHwThermalSlowdown": 0x40,
+                   "nvmlClocksEventReasonSwThermalSlowdown": 0x20, "nvmlClocksEventReasonSwPowerCap": 0x4}
+            reasons = sorted(n for n, attr in names if b & int(getattr(nv, attr, alt[attr])))
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm),
+                    "source": "NVML, 2 ms period, during the timed regions only"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -84,7 +132,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi -lms 20"}
 
 
 def build_workload(rank, rays_per_frame=RAYS_PER_FRAME, keyframes=KEYFRAMES, scene_kind=SCENE):
@@ -237,7 +285,7 @@ def run_gpu(args):
     barrier()
     ms_step = timed(lambda i: step(i + 1), args.steps)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    sampler.pause()
 
     # end to end through the public call with HOST buffers: H2D of the step's inputs, D2H of the loss
     def e2e_step(i):
@@ -249,8 +297,11 @@ def run_gpu(args):
     for i in range(2):
         e2e_step(i)
     barrier()
+    if rank == 0:
+        sampler.start()
     ms_e2e = timed(e2e_step, args.steps)
     barrier()
+    clocks = sampler.stop() if rank == 0 else None
     loss_val = float(loss_host[0])
 
     # dominant kernel alone (field backward = decoder dgrad+wgrad + embedding scatter), events around it

@@ -307,6 +307,11 @@ int pslam_render_stage(const pslam_render_t *p, int stage, pslam_stream_t stream
  * exp_avg [6] / exp_avg_sq [6] / step [1] (float, the capturable form; step == NULL: the count lives on the host
  * and step_value is its new value); grad_out [6] optional.
  * ---------------------------------------------------------------------- */
+/* n distinct pixel indices out of hw, uniform (frame.sample_rays / src/utils/sample_util.py:4-20: Gumbel top-k over uniform
+ * weights = uniform sampling without replacement), from a keyed permutation of [0, hw) evaluated at 0..n-1; seed_dev is an
+ * optional device-side addend to `seed` (a CUDA-graph replay then draws a fresh set). */
+int pslam_sample_pixels(int n, long long hw, unsigned long long seed, const unsigned long long *seed_dev, long long *idx,
+                        pslam_stream_t stream);
 int pslam_track_assemble(int n, const float *pose6, const long long *idx, const float *rays_d_cam, const float *rgb_all,
                          const float *depth_all, float *rays_o, float *rays_d, float *rgb, float *depth, pslam_stream_t stream);
 int pslam_track_pose_step(int n, float *pose6, const long long *idx, const float *rays_d_cam, const float *g_rays_o,

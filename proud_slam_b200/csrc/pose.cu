@@ -148,9 +148,57 @@ __global__ void __launch_bounds__(256) k_track_pose_step(int n, float *__restric
     }
 }
 
+// Pixel selection of a tracking / mapping iteration: n DISTINCT pixels out of hw, uniformly (the reference draws them with
+// a Gumbel top-k over uniform weights, src/utils/sample_util.py:4-20, i.e. uniformly without replacement; its cost there
+// is a sort-like pass over all H*W pixels per frame and iteration).  Here thread i evaluates a keyed pseudo-random
+// PERMUTATION of [0, hw) at i: a 4-round Feistel network on the next even number of bits, cycle-walked back into range.
+// Distinct inputs give distinct outputs by construction, so no rejection, no sort and no scratch memory.
+__device__ __forceinline__ uint32_t feistel_round(uint32_t x, uint32_t k)
+{
+    x = (x ^ k) * 0x9E3779B1u;
+    x ^= x >> 15; x *= 0x85EBCA77u;
+    x ^= x >> 13;
+    return x;
+}
+__global__ void k_sample_pixels(int n, long long hw, unsigned long long seed, const unsigned long long *__restrict__ seed_dev,
+                                long long *__restrict__ idx)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long key = seed + (seed_dev ? *seed_dev : 0ull);
+    key ^= key >> 30; key *= 0xBF58476D1CE4E5B9ull;
+    key ^= key >> 27; key *= 0x94D049BB133111EBull;
+    key ^= key >> 31;
+    int bits = 2;
+    while (bits < 62 && (1ll << bits) < hw) bits += 2;       // even width >= log2(hw)
+    const int hb = bits >> 1;
+    const uint32_t hmask = (hb >= 32) ? 0xffffffffu : ((1u << hb) - 1u);
+    unsigned long long x = (unsigned long long)i;
+    do {
+        uint32_t L = (uint32_t)(x >> hb) & hmask, Rr = (uint32_t)x & hmask;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const uint32_t t = L ^ (feistel_round(Rr, (uint32_t)(key >> (16 * r)) + 0x632BE5ABu * (uint32_t)r) & hmask);
+            L = Rr; Rr = t;
+        }
+        x = ((unsigned long long)L << hb) | Rr;
+    } while ((long long)x >= hw);
+    idx[i] = (long long)x;
+}
+
 }  // namespace pslam
 
 using namespace pslam;
+
+extern "C" int pslam_sample_pixels(int n, long long hw, unsigned long long seed, const unsigned long long *seed_dev, long long *idx,
+                                   pslam_stream_t stream)
+{
+    PSLAM_CHECK_ARG(n > 0 && hw > 0 && idx, PSLAM_E_ARG, "sample_pixels: bad argument");
+    PSLAM_CHECK_ARG((long long)n <= hw, PSLAM_E_RANGE, "sample_pixels: cannot draw %d distinct pixels out of %lld", n, hw);
+    k_sample_pixels<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(n, hw, seed, seed_dev, idx);
+    PSLAM_CHECK_LAUNCH("sample_pixels");
+    return 0;
+}
 
 extern "C" int pslam_track_assemble(int n, const float *pose6, const long long *idx, const float *rays_d_cam, const float *rgb_all,
                                     const float *depth_all, float *rays_o, float *rays_d, float *rgb, float *depth, pslam_stream_t stream)

@@ -426,7 +426,7 @@ class GraphTracker:
     """Per-frame pose optimisation of ``track_frame`` (render_helpers.py:679-761) without per-iteration
     host work.  The reference's 30 x 1024-ray loop costs ~2 ms of Python/launch overhead per iteration
     around ~0.3 ms of GPU work; here one iteration is a CUDA graph.  Differences from the plain
-    ``track_frame`` above: pixels are drawn on the device with replacement (``torch.randint``) instead of the
+    ``track_frame`` above: pixels are drawn on the device (``pslam_sample_pixels``: distinct, uniform) instead of by the
     frame's own ``sample_rays``, and the frame's tensors are copied into static buffers once per frame."""
 
     def __init__(self, n_pixels, map_states, sdf_network, loss_criteria, voxel_size, N_rays=1024, step_size=0.02, truncation=0.1,
@@ -465,16 +465,19 @@ class GraphTracker:
             self.rays_d = torch.zeros(self.N, 3, device=d)
             self.rgb = torch.zeros(self.N, 3, device=d)
             self.depth = torch.zeros(self.N, device=d)
+            self.idx = torch.zeros(self.N, dtype=torch.int64, device=d)
 
     def _iteration_fused(self):
         from .. import _lib
         lib, d = _lib.lib(), self.device
-        idx = torch.randint(0, self.HW, (self.N,), device=d)
+        self.counter.add_(1)
+        idx = self.idx          # distinct pixels, uniform, like the frame's own sample_rays (no replacement)
+        _lib.check(lib.pslam_sample_pixels(self.N, self.HW, self.base_seed ^ 0x5851F42D4C957F2D, _lib.ptr(self.counter), _lib.ptr(idx),
+                                           _lib.stream_ptr(d)), "pslam_sample_pixels")
         pose = self.pose.data
         _lib.check(lib.pslam_track_assemble(self.N, _lib.ptr(pose), _lib.ptr(idx), _lib.ptr(self.rays_d_all), _lib.ptr(self.rgb_all),
                                             _lib.ptr(self.depth_all), _lib.ptr(self.rays_o), _lib.ptr(self.rays_d), _lib.ptr(self.rgb),
                                             _lib.ptr(self.depth), _lib.stream_ptr(d)), "pslam_track_assemble")
-        self.counter.add_(1)
         pipe = self.it.pipe
         pipe.bind(self.rays_o, self.rays_d, self.ms, self.dec, voxel_size=self.cfg["voxel_size"], step_size=self.cfg["step_size"],
                   truncation=self.crit["truncation"], max_distance=self.cfg["max_distance"], max_depth=self.crit["max_depth"],

@@ -34,12 +34,14 @@ def timed(fn):
         a.record(); fn(); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
     return sorted(ts)[len(ts) // 2]
 def trace(fn, layers):
+    """slots: 0 = MMA thread starts waiting for the layer's A, 2 = its MMAs are issued and committed, 3 = workers see the
+    accumulators, 7 = staging decided, 4 = epilogue done, 5 = last quarter of the next A published, 6 = tile starts"""
     lib.pslam_debug_bf_trace(_lib.ptr(buf)); fn(); torch.cuda.synchronize(); lib.pslam_debug_bf_trace(None)
     t = buf.cpu()[:320].view(4, 10, 8); t0 = int(t[1, 0, 6])
     for l in range(layers):
-        print("  layer", l, "mma_wait_start", int(t[1, l, 0]) - t0, "A_seen", int(t[1, l, 1]) - t0, "committed", int(t[1, l, 2]) - t0,
-              "weight_wait", int(t[1, l, 4]), "D_seen", int(t[1, l, 3]) - t0, "A_next_produced", int(t[1, l + 1, 5]) - t0 if l < layers - 1 else "-")
-    print("  next tile gather", int(t[2, 0, 6]) - t0)
+        print("  layer", l, "mma_wait", int(t[1, l, 0]) - t0, "issued", int(t[1, l, 2]) - t0, "D_seen", int(t[1, l, 3]) - t0,
+              "epi_done", int(t[1, l, 4]) - t0, "A_next_produced", int(t[1, l + 1, 5]) - t0 if l < layers - 1 else "-")
+    print("  next tile starts", int(t[2, 0, 6]) - t0)
 print("samples", n, "= tiles/CTA", tiles_per_cta)
 print("fwd ms", timed(fwd)); trace(fwd, 5)
 for with_grad in (False, True):

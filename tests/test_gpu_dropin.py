@@ -259,3 +259,27 @@ def test_fused_pose_kernels_match_torch_autograd_and_adam(device):
         assert torch.equal(pose_h, pose) and torch.equal(m_h, m) and torch.equal(v_h, v)
     st = opt.state[ref.data]
     assert rel_err(m, st["exp_avg"]) < 1e-5 and rel_err(v, st["exp_avg_sq"]) < 1e-5 and float(step) == float(st["step"])
+
+
+@pytest.mark.parametrize("hw,n", [(1200 * 680, 1024), (4800, 4800), (5, 3), (1 << 20, 4096)])
+def test_sample_pixels_distinct_uniform(hw, n, device):
+    """pslam_sample_pixels: n distinct indices in [0, hw) (sampling without replacement like frame.sample_rays), a fresh
+    set per value of the device-side counter, spread over the whole range."""
+    from proud_slam_b200 import _lib
+    lib = _lib.lib()
+    idx = torch.empty(n, dtype=torch.int64, device=device)
+    counter = torch.zeros(1, dtype=torch.int64, device=device)
+    sets = []
+    for it in range(3):
+        counter.fill_(it)
+        _lib.check(lib.pslam_sample_pixels(n, hw, 12345, _lib.ptr(counter), _lib.ptr(idx), _lib.stream_ptr(device)), "sample_pixels")
+        torch.cuda.synchronize()
+        v = idx.cpu()
+        assert int(v.min()) >= 0 and int(v.max()) < hw
+        assert v.unique().numel() == n                         # no replacement
+        sets.append(v)
+    if n < hw:
+        assert not torch.equal(sets[0], sets[1]) and not torch.equal(sets[1], sets[2])
+    if n >= 1024 and n < hw:
+        assert abs(float(sets[0].double().mean()) / hw - 0.5) < 0.05      # uniform over the range
+    assert lib.pslam_sample_pixels(10, 5, 0, None, _lib.ptr(idx), _lib.stream_ptr(device)) != 0   # more pixels than there are
