@@ -78,7 +78,9 @@ struct Smem {
     static constexpr int oBars = oStaging + (BWD ? 2 * kStagingBytes : 0);   // full[8], empty[8], a_ready, mma_done, st_full[2], st_free[2]
     static constexpr int oTmemPtr = oBars + 8 * (2 * kStages + 5 + 4);   // ... a_ready[4], mma_done, st_full[2], st_free[2]
     static constexpr int oBias = oTmemPtr + 16;                     // b1[128] b2[128] b3f[128] b4[128] b3_0 b5[3]
-    static constexpr int bytes = oBias + 4 * (4 * 128 + 4);
+    static constexpr int oW5 = oBias + 4 * (4 * 128 + 4);           // W5 [3][128] fp32: the colour head runs on the CUDA cores
+    static constexpr int oHead = oW5 + 4 * 3 * 128;                 // [128 rows][4]: partial dot products of the rows' second threads
+    static constexpr int bytes = oHead + 4 * 128 * 4;
 };
 
 // wgrad scratch, per 128-sample tile: six 128-feature operands and two 16-feature operands, each already split
@@ -154,9 +156,12 @@ __global__ void k_grad_scale(const float4 *__restrict__ g_out, int n, const int 
 //   MODE 1: y = D/16 + bias                                    (forward, no activation)
 //   MODE 2: y = mask ? D/16 : 0                                (dgrad through a ReLU; y = Sg x gradient)
 //   MODE 3: y = D/16                                           (dgrad, no activation)
-template <int MODE>
+// HEAD: this is the hc layer -- its colour head (3 x 128, sigmoid outside) is taken right here on the CUDA cores from the fp32
+// values (head[c] += W5[c][col] * y), so the N = 16 tensor-core layer that cost a full issue-bound layer slot for 3 useful
+// columns is gone and the next A operand is not written at all.
+template <int MODE, bool HEAD = false>
 __device__ __forceinline__ void bf_epilogue16(uint32_t trow, uint32_t dcol, int c0, const float *bias, uint32_t &mask, int shift,
-                                              unsigned char *stg, float &ymax)
+                                              unsigned char *stg, float &ymax, const float *w5 = nullptr, float *head = nullptr)
 {
     using namespace bf;
     uint32_t v[16];
@@ -171,6 +176,11 @@ __device__ __forceinline__ void bf_epilogue16(uint32_t trow, uint32_t dcol, int 
         if (MODE == 2) y = ((mask >> (shift + e)) & 1u) ? y * kInvScale : 0.0f;
         if (MODE == 3) y = y * kInvScale;
         ymax = fmaxf(ymax, fabsf(y));                // range guard of the f16 operand window (checked once per tile)
+        if (HEAD) {
+            head[0] = fmaf(w5[c0 + e], y, head[0]);
+            head[1] = fmaf(w5[128 + c0 + e], y, head[1]);
+            head[2] = fmaf(w5[256 + c0 + e], y, head[2]);
+        }
         v[e] = __float_as_uint(y);
     }
     if (MODE == 0) mask = shift ? (mask | (bits << 16)) : bits;     // (shift is 0 or 16; the low half is written first)
@@ -185,8 +195,10 @@ __device__ __forceinline__ void bf_epilogue16(uint32_t trow, uint32_t dcol, int 
             *reinterpret_cast<uint4 *>(dst + 16384) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
         }
     }
-    tmem_st8(trow + cAHI + c0 / 2, hi);
-    tmem_st8(trow + cALO + c0 / 2, lo);
+    if (!HEAD) {
+        tmem_st8(trow + cAHI + c0 / 2, hi);
+        tmem_st8(trow + cALO + c0 / 2, lo);
+    }
 }
 
 // optional timeline trace of CTA 0 (pslam_debug_bf_trace): [tile<4][layer<10][8] clock64 stamps (+ 40 x 8 for k_wgrad_bf)
@@ -289,6 +301,7 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
     uint64_t *st_full = mma_done + 1, *st_free = st_full + 2;
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(smem + SM::oTmemPtr);
     float *sBias = reinterpret_cast<float *>(smem + SM::oBias);
+    float *sW5 = reinterpret_cast<float *>(smem + SM::oW5), *sHead = reinterpret_cast<float *>(smem + SM::oHead);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nsamp = p.nsamp_dev ? *p.nsamp_dev : p.nsamp;
@@ -318,6 +331,7 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
         else v = p.dec.b5[i - 513];
         sBias[i] = i < 512 ? kScale * v : v;
     }
+    for (int i = threadIdx.x; i < 3 * 128; i += kThreads) sW5[i] = p.dec.W5[i];
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
@@ -334,6 +348,7 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
             const unsigned char *src = wstream + (kHasFwd ? 0 : kFwdStreamBytes);
             for (int l = L0; l < L1; ++l) {
                 const int N = cN[l], K = cK[l];
+                if (l == 4) { src += N * K * 4; continue; }   // layer 5 of the decoder (colour head) does not run on the tensor cores
                 for (int k0 = 0; k0 < K; k0 += kChunkK) {
                     const int kk = (K - k0) < kChunkK ? (K - k0) : kChunkK;
                     const uint32_t bytes = (uint32_t)(N * kk * 4), part = bytes / kCluster;
@@ -357,7 +372,10 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
             MmaIssuer<NS> mi{smem, full, empty, a_ready, mma_done, tmem, 0, 0, 0u};
             for (int it = 0; it < iters; ++it) {
                 if constexpr (KIND == kBwdRecompute) {
-                    for (int l = 0; l < kLayersAll; ++l) { BF_TRACE(it, l, 0); mi.layer_rt(cN[l], cK[l], cAcol[l]); BF_TRACE(it, l, 2); }
+                    for (int l = 0; l < kLayersAll; ++l) {
+                        if (l == 4) continue;   // the colour head is taken in the hc epilogue
+                        BF_TRACE(it, l, 0); mi.layer_rt(cN[l], cK[l], cAcol[l]); BF_TRACE(it, l, 2);
+                    }
                     continue;
                 }
                 if constexpr (kHasFwd) {
@@ -365,7 +383,6 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
                     BF_TRACE(it, 1, 0); mi.template layer<128, 128, 0>(); BF_TRACE(it, 1, 2);
                     BF_TRACE(it, 2, 0); mi.template layer<144, 128, 0>(); BF_TRACE(it, 2, 2);
                     BF_TRACE(it, 3, 0); mi.template layer<128, 144, 0>(); BF_TRACE(it, 3, 2);
-                    BF_TRACE(it, 4, 0); mi.template layer<16, 128, 0>(); BF_TRACE(it, 4, 2);
                 }
                 if constexpr (kHasBwd) {
                     BF_TRACE(it, 5, 0); mi.template layer<128, 16, 0>(); BF_TRACE(it, 5, 2);
@@ -571,16 +588,22 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
             }
             a_is_ready();
             layer_done();
-            epilogue(M0{}, sBias + 384, mc, true);                                                      // hc
-            a_is_ready();
-            layer_done();
-            if (lead) {
-                uint32_t v[8];
-                tmem_ld8(trow + dcol, v);
-                tmem_wait_ld();
-                r = sigmoid_f(fmaf(__uint_as_float(v[0]), kInvScale * kInvScale, sBias[513]));
-                g = sigmoid_f(fmaf(__uint_as_float(v[1]), kInvScale * kInvScale, sBias[514]));
-                b = sigmoid_f(fmaf(__uint_as_float(v[2]), kInvScale * kInvScale, sBias[515]));
+            {
+                // hc + colour head: no tensor-core layer follows in the forward direction, so nothing is handed to the MMA thread
+                float head[3] = {0.f, 0.f, 0.f};
+                unsigned char *stg = stage_begin();
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    bf_epilogue16<0, true>(trow, dcol, col0 + 16 * j, sBias + 384, mc[j >> 1], (j & 1) * 16, stg, ymax, sW5, head);
+                stage_end();
+                if (!lead) { sHead[m * 4] = head[0]; sHead[m * 4 + 1] = head[1]; sHead[m * 4 + 2] = head[2]; }
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");    // the two warps of this lane quarter
+                if (lead) {   // y was 16 x hc
+                    r = sigmoid_f(fmaf(head[0] + sHead[m * 4], kInvScale, sBias[513]));
+                    g = sigmoid_f(fmaf(head[1] + sHead[m * 4 + 1], kInvScale, sBias[514]));
+                    b = sigmoid_f(fmaf(head[2] + sHead[m * 4 + 2], kInvScale, sBias[515]));
+                }
+                if (threadIdx.x == 128) BF_TRACE(tile_i, lcount, 4);
             }
             }   // kHasFwd
             if constexpr (!kHasBwd) {
