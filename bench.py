@@ -70,6 +70,8 @@ class ClockSampler:
             phys = int(vis.split(",")[index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else index
             self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)          # first calls are slow: not inside a timed region
+            pynvml.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
             self.nvml = pynvml
         except Exception:
             self.nvml = None
@@ -84,6 +86,19 @@ class ClockSampler:
                 except Exception:
                     pass
             time.sleep(0.002)
+
+    def sample_now(self, k=3):
+        """k samples from the calling thread: called after a timed region's launches are queued and before the
+        synchronize, i.e. while the GPU is executing them (the polling thread may not get scheduled in ~10 ms)"""
+        if self.nvml is None:
+            return
+        for _ in range(k):
+            try:
+                self.rows.append(int(self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM)))
+                self.reason_bits |= int(self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            except Exception:
+                pass
+            time.sleep(0.001)
 
     def start(self):
         """begin (or resume) sampling: call right before a timed region"""
@@ -122,7 +137,7 @@ class ClockSampler:
                    "nvmlClocksEventReasonSwThermalSlowdown": 0x20, "nvmlClocksEventReasonSwPowerCap": 0x4}
             reasons = sorted(n for n, attr in names if b & int(getattr(nv, attr, alt[attr])))
             return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm),
-                    "source": "NVML, 2 ms period, during the timed regions only"}
+                    "source": "NVML: a 2 ms polling thread plus 3 samples taken between the last launch and the synchronize of each timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -254,6 +269,8 @@ def run_gpu(args):
             pipe.backward()
             dist.all_reduce(flat)
 
+    clock_sampler = None
+
     def timed(fn, n):
         """n steps, each bracketed by events on the launching stream, L2 flushed in between."""
         total = 0.0
@@ -265,6 +282,8 @@ def run_gpu(args):
             fn(i)
             b.record()
             evs.append((a, b))
+        if rank == 0 and clock_sampler is not None:
+            clock_sampler.sample_now()       # the queued steps are executing now
         torch.cuda.synchronize()
         for a, b in evs:
             total += a.elapsed_time(b)
@@ -281,6 +300,7 @@ def run_gpu(args):
     counts = pipe.counts()
     sampler = ClockSampler(local)
     if rank == 0:
+        clock_sampler = sampler
         sampler.start()
     barrier()
     ms_step = timed(lambda i: step(i + 1), args.steps)
