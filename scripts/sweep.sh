@@ -2,7 +2,7 @@
 # Ray-batch sweep (BASELINE.json configs[4]) and the large scene (configs[3]) on one GPU; one JSON line per run.
 out=${1:-gpurun_out/sweep.jsonl}
 : > $out
-for r in 4096 8192 16384 32768 65536 131072 262144; do
+for r in 4096 8192 16384 32768 65536 131072 262144 524288; do
   timeout 120 python bench.py --rays $r --steps 5 --warmup 3 --no-extras 2>/dev/null | tail -1 >> $out
 done
 timeout 120 python bench.py --workload scannet_large --rays 8192 --steps 5 --warmup 3 --no-extras 2>/dev/null | tail -1 >> $out
