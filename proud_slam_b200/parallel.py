@@ -77,3 +77,48 @@ class DataParallelStep:
         self.pipe.backward()
         if self.world > 1:
             dist.all_reduce(self.grads.flat, group=self.group)
+
+
+class ChunkedStep:
+    """One mapping iteration over a ray batch larger than one launch's workspace (the wgrad scratch is 3.2 kB per
+    sample: about 2^19 rays per 180 GB GPU).  The batch is cut into chunks that go through the same two-exchange
+    protocol as the ranks of ``DataParallelStep``, as *virtual ranks* of one device:
+
+    pass 1  every chunk is rendered with the loss deferred and leaves its 16 raw sums;
+            the sums of all chunks (and, with ``torch.distributed``, of all ranks) close the loss once;
+    pass 2  every chunk is rendered again (same seed, hence the same samples) and runs its backward; the
+            gradients of the embeddings and of the decoder accumulate in the flat buffer (the kernels add).
+
+    ``bind_chunk(k)`` binds chunk ``k``'s rays and targets to ``pipe`` (``defer_loss=True``, a seed that depends only on
+    ``k`` and the iteration); ``after_backward(k)``, if given, runs after chunk ``k``'s backward while its per-ray
+    gradients (``pipe.g_rays_o / g_rays_d``) are still in place.  Costs one extra forward per chunk."""
+
+    def __init__(self, pipe, grads: FlatGrads, n_chunks: int, bind_chunk, group=None, after_backward=None):
+        self.pipe, self.grads, self.n, self.bind_chunk, self.group = pipe, grads, int(n_chunks), bind_chunk, group
+        self.after_backward = after_backward
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        dev = pipe.loss_raw.device
+        self.local = torch.zeros(self.n, 16, dtype=torch.float64, device=dev)
+        self.rows = torch.zeros(self.world * self.n, 16, dtype=torch.float64, device=dev)
+
+    def __call__(self):
+        self.grads.zero_()
+        for k in range(self.n):
+            self.bind_chunk(k)
+            self.pipe.sample()
+            self.pipe.forward()
+            self.local[k].copy_(self.pipe.loss_raw.view(16))
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.rows.view(-1), self.local.view(-1), group=self.group)
+        else:
+            self.rows.copy_(self.local)
+        for k in range(self.n):
+            self.bind_chunk(k)
+            self.pipe.sample()
+            self.pipe.forward()
+            self.pipe.finalize_loss(self.rows)
+            self.pipe.backward()
+            if self.after_backward is not None:
+                self.after_backward(k)
+        if self.world > 1:
+            dist.all_reduce(self.grads.flat, group=self.group)

@@ -115,6 +115,54 @@ def test_two_rank_step_equals_one_padded_batch():
         assert err < 1e-4, f"rank {rank}: all-reduced gradient differs ({err})"
 
 
+class AccumulatingFakePipe(FakePipe):
+    """... whose backward ADDS into the gradient buffers like the CUDA kernels do, and whose ray shard can be re-bound."""
+
+    def bind(self, shard, seed):
+        self.rays_o, self.rays_d, self.rgb, self.depth = shard
+        self.seed = seed
+
+    def backward(self):
+        keep = parallel_clone(self.grads)
+        super().backward()
+        self.grads.g_emb.add_(keep[0])
+        for dst, src in zip(self.grads.g_dec, keep[1:]):
+            dst.add_(src)
+
+
+def parallel_clone(grads):
+    return [grads.g_emb.clone()] + [g.clone() for g in grads.g_dec]
+
+
+def test_chunked_step_equals_one_padded_batch():
+    """parallel.ChunkedStep on one device (no process group): two chunks as virtual ranks == one padded batch."""
+    from oracle import render_oracle as ro
+    from proud_slam_b200 import parallel, scene as sc
+    torch.set_num_threads(2)
+    s, ms = util.build_scene("tiny")
+    dec = ro.decoder_params(seed=1)
+    rays_o, rays_d, rgb, depth = sc.sample_batch(s, [0, 1], 150, seed=5)
+    batch = [t[:299] for t in (rays_o[0], rays_d[0], rgb[0], depth[0])]
+    shards = [parallel.shard_rays(batch, k, 2) for k in range(2)]
+    pipe = AccumulatingFakePipe(shards[0], ms, dec, s.voxel_size, seed=100)
+    grads = parallel.FlatGrads(ms["voxel_vertex_emb"], dec)
+    pipe.grads = grads
+    seen = []
+    step = parallel.ChunkedStep(pipe, grads, 2, lambda k: pipe.bind(shards[k], 100 + k), after_backward=seen.append)
+    step()
+    assert seen == [0, 1]
+    outs = [ro.render_rays(sh[0][None], sh[1][None], ms, dec, 0.1 * s.voxel_size, s.voxel_size, 0.1, 10, 10.0,
+                           generator=torch.Generator().manual_seed(100 + k)) for k, sh in enumerate(shards)]
+    big = util.concat_outputs(outs)
+    kw = {k: util.CRIT[k] for k in ("rgb_weight", "depth_weight", "sdf_weight", "fs_weight", "truncation", "max_depth")}
+    loss, parts = ro.criterion(big, (batch[2][None], batch[3][None]), **kw)
+    ref = torch.autograd.grad(loss, [ms["voxel_vertex_emb"]] + list(dec))
+    assert abs(pipe.parts["loss"] - float(loss)) < 1e-5 * abs(float(loss))
+    assert util.rel_err(grads.g_emb, ref[0]) < 1e-4
+    for a, b in zip(grads.g_dec, ref[1:]):
+        assert util.rel_err(a, b) < 1e-4
+
+
 def test_shard_bounds_cover_everything():
     from proud_slam_b200.parallel import shard_bounds, shard_keyframes
     for n in (1, 7, 8, 8192, 8191):

@@ -91,3 +91,51 @@ def test_two_shards_close_to_one_padded_batch(device):
     assert rel_err(fg.g_emb, tot[0]) < TOL
     for i in range(10):
         assert rel_err(fg.g_dec[i], tot[1 + i]) < TOL, f"decoder grad {i}"
+
+
+def test_chunked_step_matches_separate_pipelines(device):
+    """parallel.ChunkedStep (a batch larger than one launch's workspace, chunks as virtual ranks of one pipeline, each
+    rendered twice) against the same chunks on separate pipelines that keep their state between the two passes."""
+    from proud_slam_b200 import parallel, scene as sc
+    from proud_slam_b200.pipeline import RenderPipeline
+    s, ms = util.build_scene("tiny")
+    dec = util.test_decoder(width=128, seed=1)
+    rays_o, rays_d, rgb, depth = sc.sample_batch(s, [0, 1], 300, seed=5)
+    batch = [t[:599].to(device) for t in (rays_o[0], rays_d[0], rgb[0], depth[0])]
+    msd = {k: v.detach().to(device) for k, v in ms.items()}
+    decd = [p.detach().to(device) for p in dec]
+    cw = (util.CRIT["rgb_weight"], util.CRIT["depth_weight"], util.CRIT["fs_weight"], util.CRIT["sdf_weight"])
+    chunks = [parallel.shard_rays(batch, k, 2) for k in range(2)]
+
+    def bind(pipe, fg, k):
+        sh = chunks[k]
+        pipe.bind(sh[0], sh[1], msd, decd, voxel_size=s.voxel_size, step_size=0.1 * s.voxel_size, truncation=0.1, max_distance=10.0,
+                  target_rgb=sh[2], target_depth=sh[3], seed=50 + k, weights=cw, g_emb=fg.g_emb, g_dec=fg.g_dec, grad_rays=True,
+                  defer_loss=True)
+
+    # reference: one pipeline per chunk, state kept between the loss exchange and the backward
+    fg_ref = parallel.FlatGrads(msd["voxel_vertex_emb"], decd)
+    rows = torch.zeros(2, 16, dtype=torch.float64, device=device)
+    pipes = []
+    for k in range(2):
+        pipe = RenderPipeline(300, device, samples_per_ray=96)
+        bind(pipe, fg_ref, k)
+        pipe.sample()
+        pipe.forward()
+        rows[k].copy_(pipe.loss_raw)
+        pipes.append(pipe)
+    for pipe in pipes:
+        pipe.finalize_loss(rows)
+        pipe.backward()
+    # chunked: ONE pipeline, every chunk rendered twice
+    fg = parallel.FlatGrads(msd["voxel_vertex_emb"], decd)
+    one = RenderPipeline(300, device, samples_per_ray=96)
+    ray_grads = {}
+    step = parallel.ChunkedStep(one, fg, 2, lambda k: bind(one, fg, k),
+                                after_backward=lambda k: ray_grads.__setitem__(k, one.g_rays_d[: chunks[k][0].shape[0]].clone()))
+    step()
+    torch.cuda.synchronize()
+    assert one.losses() == pipes[1].losses()
+    assert rel_err(fg.flat, fg_ref.flat) < 1e-5
+    for k in range(2):
+        assert rel_err(ray_grads[k], pipes[k].g_rays_d[: chunks[k][0].shape[0]]) < 1e-5
