@@ -498,6 +498,32 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
         };
         using M0 = std::integral_constant<int, 0>; using M1 = std::integral_constant<int, 1>;
         using M2 = std::integral_constant<int, 2>; using M3 = std::integral_constant<int, 3>;
+        // Software prefetch of the NEXT tile's per-row inputs (feature rows for the forward; ReLU masks, rgb and upstream gradient
+        // for the saved backward): issued a few layers before the tile ends, so their L2 / HBM latency hides behind the MMAs
+        // instead of sitting between two tiles.
+        float4 pf[4];
+        uint32_t pm[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+        float4 po = make_float4(0.f, 0.f, 0.f, 0.f), pgo = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) pf[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto prefetch_tile = [&](int tn) {
+            const int sn = tn * 128 + m;
+            const bool in = tn < ntiles && sn < nsamp;
+            if (kHasFwd && p.feat && lead) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    pf[e] = in ? __ldg(reinterpret_cast<const float4 *>(p.feat + (size_t)sn * 16) + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (KIND == kBwdSaved) {
+                const uint32_t *mk = p.act_masks + (size_t)(tn < ntiles ? tn : 0) * (kMaskBytes / 4) + half * 256 + m;
+                pm[0] = mk[0]; pm[1] = mk[128]; pm[2] = mk[512]; pm[3] = mk[512 + 128]; pm[4] = mk[1024]; pm[5] = mk[1024 + 128];
+                if (lead) {
+                    po = in ? __ldg(reinterpret_cast<const float4 *>(p.out + (size_t)sn * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    pgo = in ? __ldg(reinterpret_cast<const float4 *>(p.g_out + (size_t)sn * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        };
+        prefetch_tile((int)blockIdx.x);
         for (int it = 0; it < iters; ++it, ++tile_i, lcount = L0 - 1) {
             const int tile = blockIdx.x + it * gridDim.x;
             tile_cur = tile;
@@ -519,10 +545,7 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
                     if (p.feat) {
                         if (kHasFwd) {
 #pragma unroll
-                            for (int e = 0; e < 16; e += 4) {
-                                const float4 v = __ldg(reinterpret_cast<const float4 *>(p.feat + (size_t)s * 16 + e));
-                                f[e] = v.x; f[e + 1] = v.y; f[e + 2] = v.z; f[e + 3] = v.w;
-                            }
+                            for (int e = 0; e < 4; ++e) { f[4 * e] = pf[e].x; f[4 * e + 1] = pf[e].y; f[4 * e + 2] = pf[e].z; f[4 * e + 3] = pf[e].w; }
                         }
                     } else {
                         vox = __ldg(p.samp_vox + s);
@@ -577,6 +600,7 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
             a_is_ready();
             layer_done();
             epilogue(M0{}, sBias + 128, m2, true);                                                      // h2
+            prefetch_tile(tile + (int)gridDim.x);
             a_is_ready();
             layer_done();
             epilogue(M1{}, sBias + 256, nomask, false);                                                 // t (no activation; not spilled)
@@ -616,17 +640,13 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
                 continue;   // D has been read; the next tile's first MMA is ordered behind it through a_ready
             }
             if constexpr (KIND == kBwdSaved) {
-                const uint32_t *mk = p.act_masks + (size_t)(real_tile ? tile : 0) * (kMaskBytes / 4) + half * 256 + m;
-                m1[0] = mk[0]; m1[1] = mk[128]; m2[0] = mk[512]; m2[1] = mk[512 + 128]; mc[0] = mk[1024]; mc[1] = mk[1024 + 128];
-                if (lead && s < nsamp) {
-                    const float4 o = __ldg(reinterpret_cast<const float4 *>(p.out + (size_t)s * 4));
-                    r = o.x; g = o.y; b = o.z;
-                }
+                m1[0] = pm[0]; m1[1] = pm[1]; m2[0] = pm[2]; m2[1] = pm[3]; mc[0] = pm[4]; mc[1] = pm[5];
+                if (lead && s < nsamp) { r = po.x; g = po.y; b = po.z; }
             }
             // ---- backward ----
             float4 go = make_float4(0.f, 0.f, 0.f, 0.f);
             if (lead) {
-                if (s < nsamp) go = __ldg(reinterpret_cast<const float4 *>(p.g_out + (size_t)s * 4));
+                if (s < nsamp) go = (KIND == kBwdSaved) ? pgo : __ldg(reinterpret_cast<const float4 *>(p.g_out + (size_t)s * 4));
                 go.x *= Sg; go.y *= Sg; go.z *= Sg; go.w *= Sg;     // the whole chain is linear in g_out: it carries Sg to the end
                 // dL/d(pre-sigmoid rgb): grad * (1 - y) * y ; A[:, 0:16) = [g5 r,g,b, 0...]
                 const float g5[4] = {go.x * (1.0f - r) * r, go.y * (1.0f - g) * g, go.z * (1.0f - b) * b, go.w};
@@ -678,6 +698,7 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
             a_is_ready();
             layer_done();
             epilogue(M2{}, nullptr, m2, true);                                                          // g_h2
+            if (KIND == kBwdSaved) prefetch_tile(tile + (int)gridDim.x);
             a_is_ready();
             layer_done();
             epilogue(M2{}, nullptr, m1, true);                                                          // g_h1
