@@ -79,8 +79,8 @@ struct Smem {
     static constexpr int oTmemPtr = oBars + 8 * (2 * kStages + 5 + 4);   // ... a_ready[4], mma_done, st_full[2], st_free[2]
     static constexpr int oBias = oTmemPtr + 16;                     // b1[128] b2[128] b3f[128] b4[128] b3_0 b5[3]
     static constexpr int oW5 = oBias + 4 * (4 * 128 + 4);           // W5 [3][128] fp32: the colour head runs on the CUDA cores
-    static constexpr int oHead = oW5 + 4 * 3 * 128;                 // [128 rows][4]: partial dot products of the rows' second threads
-    static constexpr int bytes = oHead + 4 * 128 * 4;
+    static constexpr int oHead = oW5 + 4 * 3 * 128;                 // [128 rows][2 threads][4]: each thread's partial dot products of the colour head
+    static constexpr int bytes = oHead + 4 * 128 * 8;
 };
 
 // wgrad scratch, per 128-sample tile: six 128-feature operands and two 16-feature operands, each already split
@@ -348,7 +348,7 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
             const unsigned char *src = wstream + (kHasFwd ? 0 : kFwdStreamBytes);
             for (int l = L0; l < L1; ++l) {
                 const int N = cN[l], K = cK[l];
-                if (l == 4) { src += N * K * 4; continue; }   // layer 5 of the decoder (colour head) does not run on the tensor cores
+                if (l == 4 || l == 5) { src += N * K * 4; continue; }   // the colour head and its dgrad do not run on the tensor cores
                 for (int k0 = 0; k0 < K; k0 += kChunkK) {
                     const int kk = (K - k0) < kChunkK ? (K - k0) : kChunkK;
                     const uint32_t bytes = (uint32_t)(N * kk * 4), part = bytes / kCluster;
@@ -373,7 +373,7 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
             for (int it = 0; it < iters; ++it) {
                 if constexpr (KIND == kBwdRecompute) {
                     for (int l = 0; l < kLayersAll; ++l) {
-                        if (l == 4) continue;   // the colour head is taken in the hc epilogue
+                        if (l == 4 || l == 5) continue;   // the colour head and its dgrad (W5, 3 x 128) run on the CUDA cores
                         BF_TRACE(it, l, 0); mi.layer_rt(cN[l], cK[l], cAcol[l]); BF_TRACE(it, l, 2);
                     }
                     continue;
@@ -385,7 +385,6 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
                     BF_TRACE(it, 3, 0); mi.template layer<128, 144, 0>(); BF_TRACE(it, 3, 2);
                 }
                 if constexpr (kHasBwd) {
-                    BF_TRACE(it, 5, 0); mi.template layer<128, 16, 0>(); BF_TRACE(it, 5, 2);
                     BF_TRACE(it, 6, 0); mi.template layer<144, 128, 0>(); BF_TRACE(it, 6, 2);
                     BF_TRACE(it, 7, 0); mi.template layer<128, 144, 0>(); BF_TRACE(it, 7, 2);
                     BF_TRACE(it, 8, 0); mi.template layer<128, 128, 0>(); BF_TRACE(it, 8, 2);
@@ -517,10 +516,8 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
             if (KIND == kBwdSaved) {
                 const uint32_t *mk = p.act_masks + (size_t)(tn < ntiles ? tn : 0) * (kMaskBytes / 4) + half * 256 + m;
                 pm[0] = mk[0]; pm[1] = mk[128]; pm[2] = mk[512]; pm[3] = mk[512 + 128]; pm[4] = mk[1024]; pm[5] = mk[1024 + 128];
-                if (lead) {
-                    po = in ? __ldg(reinterpret_cast<const float4 *>(p.out + (size_t)sn * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    pgo = in ? __ldg(reinterpret_cast<const float4 *>(p.g_out + (size_t)sn * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+                po = in ? __ldg(reinterpret_cast<const float4 *>(p.out + (size_t)sn * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                pgo = in ? __ldg(reinterpret_cast<const float4 *>(p.g_out + (size_t)sn * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
         prefetch_tile((int)blockIdx.x);
@@ -620,12 +617,13 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
                 for (int j = 0; j < 4; ++j)
                     bf_epilogue16<0, true>(trow, dcol, col0 + 16 * j, sBias + 384, mc[j >> 1], (j & 1) * 16, stg, ymax, sW5, head);
                 stage_end();
-                if (!lead) { sHead[m * 4] = head[0]; sHead[m * 4 + 1] = head[1]; sHead[m * 4 + 2] = head[2]; }
+                sHead[m * 8 + half * 4] = head[0]; sHead[m * 8 + half * 4 + 1] = head[1]; sHead[m * 8 + half * 4 + 2] = head[2];
                 asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");    // the two warps of this lane quarter
-                if (lead) {   // y was 16 x hc
-                    r = sigmoid_f(fmaf(head[0] + sHead[m * 4], kInvScale, sBias[513]));
-                    g = sigmoid_f(fmaf(head[1] + sHead[m * 4 + 1], kInvScale, sBias[514]));
-                    b = sigmoid_f(fmaf(head[2] + sHead[m * 4 + 2], kInvScale, sBias[515]));
+                {   // both threads of the row (the backward takes g_hc on the CUDA cores too); fixed order of the two partial sums; y was 16 x hc
+                    const float *h0 = sHead + m * 8, *h1 = h0 + 4;
+                    r = sigmoid_f(fmaf(h0[0] + h1[0], kInvScale, sBias[513]));
+                    g = sigmoid_f(fmaf(h0[1] + h1[1], kInvScale, sBias[514]));
+                    b = sigmoid_f(fmaf(h0[2] + h1[2], kInvScale, sBias[515]));
                 }
                 if (threadIdx.x == 128) BF_TRACE(tile_i, lcount, 4);
             }
@@ -641,22 +639,17 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
             }
             if constexpr (KIND == kBwdSaved) {
                 m1[0] = pm[0]; m1[1] = pm[1]; m2[0] = pm[2]; m2[1] = pm[3]; mc[0] = pm[4]; mc[1] = pm[5];
-                if (lead && s < nsamp) { r = po.x; g = po.y; b = po.z; }
+                if (s < nsamp) { r = po.x; g = po.y; b = po.z; }
             }
             // ---- backward ----
             float4 go = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (s < nsamp) go = (KIND == kBwdSaved) ? pgo : __ldg(reinterpret_cast<const float4 *>(p.g_out + (size_t)s * 4));
+            go.x *= Sg; go.y *= Sg; go.z *= Sg; go.w *= Sg;     // the whole chain is linear in g_out: it carries Sg to the end
+            // dL/d(pre-sigmoid rgb): grad * (1 - y) * y   (both threads of the row: each needs it for its half of g_hc)
+            const float g5[4] = {go.x * (1.0f - r) * r, go.y * (1.0f - g) * g, go.z * (1.0f - b) * b, go.w};
             if (lead) {
-                if (s < nsamp) go = (KIND == kBwdSaved) ? pgo : __ldg(reinterpret_cast<const float4 *>(p.g_out + (size_t)s * 4));
-                go.x *= Sg; go.y *= Sg; go.z *= Sg; go.w *= Sg;     // the whole chain is linear in g_out: it carries Sg to the end
-                // dL/d(pre-sigmoid rgb): grad * (1 - y) * y ; A[:, 0:16) = [g5 r,g,b, 0...]
-                const float g5[4] = {go.x * (1.0f - r) * r, go.y * (1.0f - g) * g, go.z * (1.0f - b) * b, go.w};
                 uint32_t hi[8], lo[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) { hi[e] = 0u; lo[e] = 0u; }
                 h16_split2(g5[0], g5[1], hi[0], lo[0]);
-                h16_split2(g5[2], 0.0f, hi[1], lo[1]);
-                tmem_st8(trow + cAHI, hi);
-                tmem_st8(trow + cALO, lo);
                 if (scr) {
                     // wgrad operand G5 = (g5 r, g, b, g_sdf, 0 ...)
                     uint32_t h1w, l1w;
@@ -674,9 +667,37 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
                     }
                 }
             }
-            a_small_ready();  // D5 (K = 16) reads only g5
-            layer_done();
-            epilogue(M2{}, nullptr, mc, true);                                                          // g_hc
+            {
+                // g_hc = mask_hc . (W5^T g5): three FMAs per output, taken here instead of a K = 16 tensor-core layer and its round trip
+                unsigned char *stg = stage_begin();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int c0 = col0 + 16 * j;
+                    const uint32_t bits = mc[j >> 1] >> ((j & 1) * 16);
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        float y0 = fmaf(g5[2], sW5[256 + c0 + 2 * e], fmaf(g5[1], sW5[128 + c0 + 2 * e], g5[0] * sW5[c0 + 2 * e]));
+                        float y1 = fmaf(g5[2], sW5[256 + c0 + 2 * e + 1], fmaf(g5[1], sW5[128 + c0 + 2 * e + 1], g5[0] * sW5[c0 + 2 * e + 1]));
+                        y0 = ((bits >> (2 * e)) & 1u) ? y0 : 0.0f;
+                        y1 = ((bits >> (2 * e + 1)) & 1u) ? y1 : 0.0f;
+                        ymax = fmaxf(ymax, fmaxf(fabsf(y0), fabsf(y1)));
+                        h16_split2(y0, y1, hi[e], lo[e]);
+                    }
+                    if (stg) {
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            unsigned char *dst = stg + (size_t)(c0 / 8 + k) * 128;
+                            *reinterpret_cast<uint4 *>(dst) = make_uint4(hi[4 * k], hi[4 * k + 1], hi[4 * k + 2], hi[4 * k + 3]);
+                            *reinterpret_cast<uint4 *>(dst + 16384) = make_uint4(lo[4 * k], lo[4 * k + 1], lo[4 * k + 2], lo[4 * k + 3]);
+                        }
+                    }
+                    tmem_st8(trow + cAHI + c0 / 2, hi);
+                    tmem_st8(trow + cALO + c0 / 2, lo);
+                    if (j < 3) a_quarter_ready(j);
+                }
+                stage_end();
+            }
             a_is_ready();
             layer_done();
             epilogue(M3{}, nullptr, nomask, false);                                                     // g_t (not spilled)
