@@ -37,7 +37,7 @@ WIDTH = 128
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel at the bench workload (ncu --set full, profiles/*_summary.md)
-NCU_TRAFFIC = {0: 985.8e6, 2: 273.1e6}   # 3xF16: k_field_bf<kFwdSave> 12.8 + 260.4 MB (kBwdSaved: 16.0 + 261.0 MB)
+NCU_TRAFFIC = {0: 985.8e6, 2: 280.5e6}   # 3xF16: k_field_bf<kBwdSaved> 15.9 + 264.7 MB (kFwdSave: 12.8 + 261.3 MB), profiles/r01_final_kernels_full.csv
 
 
 def macs_per_sample(w):
