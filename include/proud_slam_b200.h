@@ -48,6 +48,9 @@ int pslam_device_info(int *out3);
  * backward (PSLAM_F_GRAD_DEC with a wgrad workspace) spills its activations and ReLU masks, and that backward
  * runs the gradient chain only; 0 = the backward always recomputes the forward. */
 #define PSLAM_OPT_SAVE_ACT 2
+/* PSLAM_OPT_PDL: 1 (default) = the kernels of the fused step are launched with programmatic stream serialization
+ * (each starts with griddepcontrol.wait, so only launch latency overlaps, never data); 0 = plain stream order. */
+#define PSLAM_OPT_PDL 3
 int pslam_set_option(int key, int value);
 
 /* ------------------------------------------------------------------------

@@ -126,6 +126,9 @@ def lib():
     mode = os.environ.get("PSLAM_DECODER")   # decoder build override (include/proud_slam_b200.h: PSLAM_OPT_DECODER)
     if mode is not None and handle.pslam_set_option(1, int(mode)) != 0:
         raise RuntimeError(f"PSLAM_DECODER={mode}: " + handle.pslam_last_error().decode(errors="replace"))
+    pdl = os.environ.get("PSLAM_PDL")        # programmatic dependent launch on / off (PSLAM_OPT_PDL)
+    if pdl is not None and handle.pslam_set_option(3, int(pdl)) != 0:
+        raise RuntimeError(f"PSLAM_PDL={pdl}: " + handle.pslam_last_error().decode(errors="replace"))
     _lib = handle
     return _lib
 

@@ -43,6 +43,8 @@ int num_sms()
 
 static int g_decoder_mode = 2;   // tcgen05 3xBF16 (field_bf.cu)
 int decoder_mode() { return g_decoder_mode; }
+static int g_pdl = 1;             // programmatic dependent launch between the kernels of the fused step
+int pdl_enabled() { return g_pdl; }
 
 static int check_render(const pslam_render_t *p)
 {
@@ -96,6 +98,7 @@ extern "C" int pslam_set_option(int key, int value)
 {
     if (key == PSLAM_OPT_DECODER && (value == 0 || value == 1 || value == 2)) { g_decoder_mode = value; return 0; }
     if (key == PSLAM_OPT_SAVE_ACT && (value == 0 || value == 1)) { bf_set_save_activations(value); return 0; }
+    if (key == PSLAM_OPT_PDL && (value == 0 || value == 1)) { g_pdl = value; return 0; }
     set_error("unknown option %d=%d", key, value);
     return PSLAM_E_ARG;
 }

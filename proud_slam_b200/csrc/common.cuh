@@ -59,4 +59,30 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
 
 int num_sms();
 
+// Programmatic dependent launch (PSLAM_OPT_PDL).  Every kernel of the fused step starts with pdl_wait() (all earlier grids
+// complete, their memory visible; a no-op for a plain launch) followed by pdl_trigger() (the next grid may be scheduled as
+// soon as every CTA of this one has started), so consecutive launches overlap their launch latency and prologue but never
+// their data.  Because the wait comes first, "my predecessor has started" implies "its predecessors have completed".
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_wait(); pdl_trigger(); }
+
+int pdl_enabled();
+
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(static_cast<Args &&>(args))...);
+}
+
 }  // namespace pslam

@@ -50,6 +50,7 @@ __device__ __forceinline__ int first_sign_change(const float *__restrict__ out, 
 __global__ void __launch_bounds__(kCompThreads)
 k_composite_fwd(pslam_render_t p, float *__restrict__ part_f, int *__restrict__ part_i)
 {
+    pdl_enter();
     __shared__ float s_f[kCompWarps][6];
     __shared__ int s_i[kCompWarps][7];
     const int Rh = p.counters[PSLAM_C_RH];
@@ -189,6 +190,7 @@ enum { RAW_COLOR = 0, RAW_FS, RAW_SDF, RAW_D0, RAW_D1, RAW_NFS, RAW_F0, RAW_F1, 
 __global__ void __launch_bounds__(1024)
 k_loss_reduce(pslam_render_t p, const float *__restrict__ part_f, const int *__restrict__ part_i, int nblocks)
 {
+    pdl_enter();
     __shared__ double s_d[32 * 13], s_tot[13];
     __shared__ unsigned s_hist[256];
     __shared__ unsigned s_prefix, s_rank;
@@ -332,6 +334,7 @@ __device__ __forceinline__ void publish_gmax(const pslam_render_t &p, float gmax
 __global__ void __launch_bounds__(kCompThreads)
 k_composite_bwd(pslam_render_t p)
 {
+    pdl_enter();
     const int Rh = p.counters[PSLAM_C_RH];
     const int S = p.counters[PSLAM_C_S];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -429,6 +432,7 @@ k_composite_bwd_ext(pslam_render_t p, const float *__restrict__ g_color, const f
 // before a backward: zero the ray-gradient accumulators and reset the gradient maximum
 __global__ void k_bwd_prologue(pslam_render_t p)
 {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) p.counters[PSLAM_C_TILE] = 0;
     if ((p.flags & PSLAM_F_GRAD_RAYS) && i < p.R * 3) { p.g_rays_o[i] = 0.0f; p.g_rays_d[i] = 0.0f; }
@@ -445,10 +449,10 @@ int launch_composite_forward(const pslam_render_t *p, cudaStream_t st)
     const int nb = ceil_div(p->R, kCompWarps);
     float *part_f = p->scratch_f;                                // [nb,8]
     int *part_i = p->scratch_i + scratch_i_composite_off(p->R);  // after the two scan-partial arrays: [nb,8]
-    k_composite_fwd<<<nb, kCompThreads, 0, st>>>(*p, part_f, part_i);
+    launch_chain(k_composite_fwd, dim3(nb), dim3(kCompThreads), 0, st, *p, part_f, part_i);
     PSLAM_CHECK_LAUNCH("composite_fwd");
     if (p->target_depth && p->target_rgb) {
-        k_loss_reduce<<<1, 1024, 0, st>>>(*p, part_f, part_i, nb);
+        launch_chain(k_loss_reduce, dim3(1), dim3(1024), 0, st, *p, part_f, part_i, nb);
         PSLAM_CHECK_LAUNCH("loss_reduce");
     }
     return 0;
@@ -464,7 +468,7 @@ int launch_loss_coeffs(const pslam_render_t *p, const double *rows, int nrows, c
 int launch_composite_backward_ext(const pslam_render_t *p, const float *g_color, const float *g_depth, const float *g_sdf,
                                   const float *g_weight, cudaStream_t st)
 {
-    k_bwd_prologue<<<(p->flags & PSLAM_F_GRAD_RAYS) ? ceil_div(p->R * 3, 256) : 1, 256, 0, st>>>(*p);
+    launch_chain(k_bwd_prologue, dim3((p->flags & PSLAM_F_GRAD_RAYS) ? ceil_div(p->R * 3, 256) : 1), dim3(256), 0, st, *p);
     PSLAM_CHECK_LAUNCH("bwd_prologue");
     k_composite_bwd_ext<<<ceil_div(p->R, kCompWarps), kCompThreads, 0, st>>>(*p, g_color, g_depth, g_sdf, g_weight);
     PSLAM_CHECK_LAUNCH("composite_bwd_ext");
@@ -473,9 +477,9 @@ int launch_composite_backward_ext(const pslam_render_t *p, const float *g_color,
 
 int launch_composite_backward(const pslam_render_t *p, cudaStream_t st)
 {
-    k_bwd_prologue<<<(p->flags & PSLAM_F_GRAD_RAYS) ? ceil_div(p->R * 3, 256) : 1, 256, 0, st>>>(*p);
+    launch_chain(k_bwd_prologue, dim3((p->flags & PSLAM_F_GRAD_RAYS) ? ceil_div(p->R * 3, 256) : 1), dim3(256), 0, st, *p);
     PSLAM_CHECK_LAUNCH("bwd_prologue");
-    k_composite_bwd<<<ceil_div(p->R, kCompWarps), kCompThreads, 0, st>>>(*p);
+    launch_chain(k_composite_bwd, dim3(ceil_div(p->R, kCompWarps)), dim3(kCompThreads), 0, st, *p);
     PSLAM_CHECK_LAUNCH("composite_bwd");
     return 0;
 }

@@ -31,6 +31,7 @@ struct FieldParams {
     uint32_t *act_masks;            // ReLU masks saved by the forward (3xBF16 build, inside wg_scratch; set by its launcher)
     uint32_t *gscale;               // bit pattern of max |g_out| of this backward launch (3xF16 build; set by its launcher)
     int spill_ops;                  // 3xF16 build: write the wgrad operands to wg_scratch (decoder gradients wanted)
+    float *finish_zero;             // 3xF16 backward: the wgrad kernel's reduction block (kFinishFloats), cleared by the chain kernel that precedes it
     int *range_flag;                // fused pipeline: counters[PSLAM_C_OVERFLOW]; bit 4 = an operand left the 3xF16 window
     uint32_t *gmax_ready;           // fused pipeline: the compositing backward already left that maximum here (counters[PSLAM_C_TILE])
     int paired;                     // forward and backward come from one pslam_render_t (fused pipeline): the forward may save

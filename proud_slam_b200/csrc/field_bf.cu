@@ -101,6 +101,7 @@ constexpr size_t kFinishFloats = 128 * 128 + 128;   // after the tiles: M = G4^T
 // [hi block | lo block], each block = kk/8 k-chunks x N rows x 16 B (8 bf16 along K) -- K-major, no swizzle.
 __global__ void k_bf_pack(pslam_decoder_t d, uint16_t *__restrict__ out, int *__restrict__ range_flag)
 {
+    pdl_enter();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int base = 0;   // uint16 offset of the layer in `out`
 #pragma unroll
@@ -288,6 +289,7 @@ template <int KIND>
 __global__ void __cluster_dims__(bf::kCluster, 1, 1) __launch_bounds__(bf::kThreads, 1)
 k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
 {
+    pdl_enter();
     using namespace bf;
     constexpr bool kHasFwd = KIND != kBwdSaved, kHasBwd = KIND == kBwdRecompute || KIND == kBwdSaved;
     constexpr int L0 = kHasFwd ? 0 : kLayersFwd, L1 = kHasBwd ? kLayersAll : kLayersFwd;   // layers [L0, L1) of the chain
@@ -436,6 +438,10 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
         uint32_t nlayers = 0;                         // layers consumed so far: which accumulator buffer the next layer_done() refers to
         uint32_t dcol = cD;                           // accumulator buffer of the layer just completed
         const float Sg = kHasBwd ? grad_scale(p.gscale) : 1.0f, invSg = 1.0f / Sg;
+        if (kHasBwd && p.finish_zero) {                // clear the wgrad kernel's reduction block (one float4 per thread)
+            for (int i = (int)blockIdx.x * (kThreads - 128) + (int)threadIdx.x - 128; i < (int)(kFinishFloats / 4); i += (int)gridDim.x * (kThreads - 128))
+                reinterpret_cast<float4 *>(p.finish_zero)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         int tile_i = 0, lcount = L0 - 1;              // trace bookkeeping
         uint32_t sc = 0;                              // staged operands so far (two staging buffers alternate)
         bool real_tile = true;
@@ -810,6 +816,7 @@ __device__ __forceinline__ void sample_position(const FieldParams &p, int s, int
 
 __global__ void __launch_bounds__(256) k_tri_gather(FieldParams p, float *__restrict__ feat)
 {
+    pdl_enter();
     const int nsamp = p.nsamp_dev ? *p.nsamp_dev : p.nsamp;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int s = t >> 2, c = t & 3;
@@ -831,6 +838,7 @@ __global__ void __launch_bounds__(256) k_tri_gather(FieldParams p, float *__rest
 
 __global__ void __launch_bounds__(256) k_tri_scatter(FieldParams p, const float *__restrict__ g_feat)
 {
+    pdl_enter();
     const int nsamp = p.nsamp_dev ? *p.nsamp_dev : p.nsamp;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int s = min(t >> 2, nsamp - 1), c = t & 3;
@@ -897,6 +905,7 @@ __device__ __constant__ Step cSteps[kStepsPerHalf] = {{bf::oG2, bf::oH1, 0}, {bf
 
 __global__ void __launch_bounds__(wgb::kThreads, 1) k_wgrad_bf(FieldParams p, float *__restrict__ finish)
 {
+    pdl_enter();
     using namespace wgb;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + oBars);
@@ -1043,6 +1052,7 @@ constexpr int kFinishPitch = 129;
 constexpr int kFinishSmem = 128 * kFinishPitch * 4;
 __global__ void __launch_bounds__(128) k_wgrad_finish(FieldParams p, const float *__restrict__ finish)
 {
+    pdl_enter();
     extern __shared__ float sMat[];   // [128][129]
     __shared__ float sVec[128], sRed[4];
     const int b = blockIdx.x & 127, t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -1188,7 +1198,7 @@ int bf_pack_decoder(const pslam_decoder_t &d, float *ws_tc, cudaStream_t st, int
 {
     int total = 0;
     for (int l = 0; l < declayers::kLayersAll; ++l) total += declayers::hN[l] * declayers::hK[l];
-    k_bf_pack<<<ceil_div(total, 256), 256, 0, st>>>(d, reinterpret_cast<uint16_t *>(ws_tc), range_flag);
+    launch_chain(k_bf_pack, dim3(ceil_div(total, 256)), dim3(256), 0, st, d, reinterpret_cast<uint16_t *>(ws_tc), range_flag);
     PSLAM_CHECK_LAUNCH("bf_pack");
     return 0;
 }
@@ -1214,7 +1224,7 @@ static bool split_trilinear(const FieldParams &fp, int max_samples)
 static int launch_tri_gather(FieldParams &fp, int max_samples, cudaStream_t st)
 {
     float *feat = scratch_feat(fp, max_samples, 0);
-    k_tri_gather<<<(int)ceil_div64((int64_t)(max_samples > 0 ? max_samples : 1) * 4, 256), 256, 0, st>>>(fp, feat);
+    launch_chain(k_tri_gather, dim3((int)ceil_div64((int64_t)(max_samples > 0 ? max_samples : 1) * 4, 256)), dim3(256), 0, st, fp, feat);
     PSLAM_CHECK_LAUNCH("tri_gather");
     fp.feat = feat;
     return 0;
@@ -1259,7 +1269,7 @@ static int launch_bf(const FieldParams &fp, int max_samples, cudaStream_t st)
     const int tiles = ceil_div(max_samples, 128);
     int grid = ceil_div(tiles > 0 ? tiles : 1, bf::kCluster) * bf::kCluster;
     if (grid > max_clusters * bf::kCluster) grid = max_clusters * bf::kCluster;
-    k_field_bf<KIND><<<grid, bf::kThreads, bf::Smem<KIND>::bytes, st>>>(fp, reinterpret_cast<const unsigned char *>(fp.ws_tc));
+    launch_chain(k_field_bf<KIND>, dim3(grid), dim3(bf::kThreads), bf::Smem<KIND>::bytes, st, fp, reinterpret_cast<const unsigned char *>(fp.ws_tc));
     static const char *names[4] = {"field_bf_forward", "field_bf_backward", "field_bf_forward_save", "field_bf_backward_saved"};
     PSLAM_CHECK_LAUNCH(names[KIND]);
     return 0;
@@ -1328,6 +1338,7 @@ int bf_launch_field_backward(const FieldParams &fp_in, int max_samples, cudaStre
         const bool saved = g_save_activations && fp.paired && fp.wg_scratch && fp.wg_scratch == g_saved_scratch && fp.out == g_saved_out;
         if (!saved && fp.wg_scratch && fp.wg_scratch == g_saved_scratch) g_saved_scratch = nullptr;   // about to be overwritten
         fp.act_masks = fp.wg_scratch ? reinterpret_cast<uint32_t *>(scratch_finish(fp, max_samples) + bf::kFinishFloats * sizeof(float)) : nullptr;
+        if (fp.grad_dec && fp.wg_scratch) fp.finish_zero = reinterpret_cast<float *>(scratch_finish(fp, max_samples));
         const bool split = split_trilinear(fp, max_samples);
         FieldParams fps = fp;                           // the scatter kernel wants the sample tables, not the feature rows
         if (split) {
@@ -1370,9 +1381,11 @@ int bf_launch_field_backward(const FieldParams &fp_in, int max_samples, cudaStre
     const int tiles = ceil_div(max_samples > 0 ? max_samples : 1, 128);
     const int grid = tiles < num_sms() ? tiles : num_sms();
     float *finish = reinterpret_cast<float *>(scratch_finish(fp, max_samples));
-    cudaError_t e = cudaMemsetAsync(finish, 0, bf::kFinishFloats * sizeof(float), st);
-    if (e != cudaSuccess) { set_error("wgrad_bf: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
-    k_wgrad_bf<<<grid, wgb::kThreads, wgb::kSmemBytes, st>>>(fp, finish);
+    if (!fp.finish_zero) {                              // the chain kernel did not clear the reduction block (part 2 on its own grid)
+        cudaError_t e = cudaMemsetAsync(finish, 0, bf::kFinishFloats * sizeof(float), st);
+        if (e != cudaSuccess) { set_error("wgrad_bf: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
+    }
+    launch_chain(k_wgrad_bf, dim3(grid), dim3(wgb::kThreads), wgb::kSmemBytes, st, fp, finish);
     PSLAM_CHECK_LAUNCH("wgrad_bf");
     static bool finish_configured = false;
     if (!finish_configured) {
@@ -1380,7 +1393,7 @@ int bf_launch_field_backward(const FieldParams &fp_in, int max_samples, cudaStre
         if (e2 != cudaSuccess) { set_error("wgrad_finish: cudaFuncSetAttribute: %s", cudaGetErrorString(e2)); return (int)e2; }
         finish_configured = true;
     }
-    k_wgrad_finish<<<256, 128, kFinishSmem, st>>>(fp, finish);
+    launch_chain(k_wgrad_finish, dim3(256), dim3(128), kFinishSmem, st, fp, finish);
     PSLAM_CHECK_LAUNCH("wgrad_finish");
     if (joined) {                                       // the scatter kernel forked onto the side stream joins here
         cudaError_t e3 = cudaStreamWaitEvent(st, joined, 0);

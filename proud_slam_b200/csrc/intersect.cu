@@ -187,6 +187,7 @@ constexpr size_t kWideSmem = sizeof(int) * 3 * (kWideStack + kWideHits) * kWideR
 // dependent expansions per ray and nothing but that chain's latency.
 __global__ void k_build_child_records(int N, const float *__restrict__ points, const int *__restrict__ children, int4 *__restrict__ rec)
 {
+    pdl_enter();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= N * 8) return;
     const int node = t >> 3, c = t & 7;
@@ -207,6 +208,7 @@ k_intersect_wide(int R, float half_voxel, int n_max, float max_distance, const f
                  const int4 *__restrict__ rec, int *__restrict__ hit_idx, float *__restrict__ hit_min, float *__restrict__ hit_max,
                  int *__restrict__ hit_count, int *__restrict__ block_hits, int *__restrict__ counters)
 {
+    pdl_enter();
     extern __shared__ int s_wide[];
     int *s_id = s_wide;                                                    // [kWideStack][kWideRays]: id | log2(side) << 26
     float *s_lo = reinterpret_cast<float *>(s_wide + kWideStack * kWideRays);
@@ -316,6 +318,7 @@ __global__ void k_prefetch_l2(const char *__restrict__ a, size_t na, const char 
 // Exclusive scan of `nb` block partials by one block; total -> *total_out.
 __global__ void __launch_bounds__(1024) k_scan_partials(int *__restrict__ partials, int nb, int *__restrict__ total_out)
 {
+    pdl_enter();
     __shared__ int s_warp[32];
     __shared__ int s_carry;
     if (threadIdx.x == 0) s_carry = 0;
@@ -354,8 +357,10 @@ __global__ void __launch_bounds__(1024) k_scan_partials(int *__restrict__ partia
 // rank of every hit ray (order-preserving compaction, render_helpers.py:390-398).
 __global__ void __launch_bounds__(kIntersectThreads)
 k_compact_rays(int R, const int *__restrict__ hit_count, const int *__restrict__ block_base, int *__restrict__ hit_ray,
-               int *__restrict__ ray_rank)
+               int *__restrict__ ray_rank, int *__restrict__ zero, int zero_n)
 {
+    pdl_enter();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < zero_n; i += gridDim.x * blockDim.x) zero[i] = 0;   // the sampling kernel's look-back state
     __shared__ int s_warp[kIntersectThreads / 32];   // launched with kWideRays threads per block (<= kIntersectThreads)
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     const bool hit = (r < R) && hit_count[r] > 0;
@@ -555,7 +560,7 @@ extern "C" int pslam_debug_rcp(const float *in, float *out, int n, pslam_stream_
 namespace pslam {
 int scan_partials(int *partials, int nb, int *total_out, cudaStream_t st)
 {
-    k_scan_partials<<<1, 1024, 0, st>>>(partials, nb, total_out);
+    launch_chain(k_scan_partials, dim3(1), dim3(1024), 0, st, partials, nb, total_out);
     PSLAM_CHECK_LAUNCH("scan_partials");
     return 0;
 }
@@ -582,19 +587,20 @@ int launch_intersect_fused(const pslam_render_t *p, cudaStream_t st)
     }
     if (cached) {
         int4 *rec = static_cast<int4 *>(p->node_cache);
-        k_build_child_records<<<(int)ceil_div64((int64_t)p->N * 8, 256), 256, 0, st>>>(p->N, p->centres, p->structure, rec);
+        launch_chain(k_build_child_records, dim3((int)ceil_div64((int64_t)p->N * 8, 256)), dim3(256), 0, st, p->N, p->centres, p->structure, rec);
         PSLAM_CHECK_LAUNCH("build_child_records");
-        k_intersect_wide<true><<<nb, kWideThreads, kWideSmem, st>>>(p->R, (float)(p->voxel_size * 0.5), p->n_max, p->max_distance, p->rays_o,
+        launch_chain(k_intersect_wide<true>, dim3(nb), dim3(kWideThreads), kWideSmem, st, p->R, (float)(p->voxel_size * 0.5), p->n_max, p->max_distance, p->rays_o,
                                                                    p->rays_d, p->centres, p->structure, rec, p->hit_idx, p->hit_min,
                                                                    p->hit_max, p->hit_count, block_hits, p->counters);
     } else {
-        k_intersect_wide<false><<<nb, kWideThreads, kWideSmem, st>>>(p->R, (float)(p->voxel_size * 0.5), p->n_max, p->max_distance, p->rays_o,
+        launch_chain(k_intersect_wide<false>, dim3(nb), dim3(kWideThreads), kWideSmem, st, p->R, (float)(p->voxel_size * 0.5), p->n_max, p->max_distance, p->rays_o,
                                                                     p->rays_d, p->centres, p->structure, nullptr, p->hit_idx, p->hit_min,
                                                                     p->hit_max, p->hit_count, block_hits, p->counters);
     }
     PSLAM_CHECK_LAUNCH("intersect_wide");
     if (int rc = scan_partials(block_hits, nb, p->counters + PSLAM_C_RH, st)) return rc;
-    k_compact_rays<<<nb, kWideRays, 0, st>>>(p->R, p->hit_count, block_hits, p->hit_ray, p->ray_rank);
+    launch_chain(k_compact_rays, dim3(nb), dim3(kWideRays), 0, st, p->R, p->hit_count, block_hits, p->hit_ray, p->ray_rank,
+                 p->scratch_i + scratch_i_sample_off(p->R), 2 * scratch_i_sample_off(p->R));
     PSLAM_CHECK_LAUNCH("compact_rays");
     return 0;
 }

@@ -57,6 +57,7 @@ __global__ void k_track_assemble(int n, const float *__restrict__ pose, const lo
                                  const float *__restrict__ rgb_all, const float *__restrict__ depth_all, float *__restrict__ rays_o,
                                  float *__restrict__ rays_d, float *__restrict__ rgb, float *__restrict__ depth)
 {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float w[3] = {pose[3], pose[4], pose[5]};
@@ -80,6 +81,7 @@ __global__ void __launch_bounds__(256) k_track_pose_step(int n, float *__restric
                                                          float *__restrict__ exp_avg_sq, float *__restrict__ step, float lr, float beta1,
                                                          float beta2, float omb1, float omb2, float eps, float step_value, float *__restrict__ grad_out)
 {
+    pdl_enter();
     __shared__ float s_part[8][12];
     float acc[12];
 #pragma unroll
@@ -163,6 +165,7 @@ __device__ __forceinline__ uint32_t feistel_round(uint32_t x, uint32_t k)
 __global__ void k_sample_pixels(int n, long long hw, unsigned long long seed, const unsigned long long *__restrict__ seed_dev,
                                 long long *__restrict__ idx)
 {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     unsigned long long key = seed + (seed_dev ? *seed_dev : 0ull);
@@ -195,7 +198,7 @@ extern "C" int pslam_sample_pixels(int n, long long hw, unsigned long long seed,
 {
     PSLAM_CHECK_ARG(n > 0 && hw > 0 && idx, PSLAM_E_ARG, "sample_pixels: bad argument");
     PSLAM_CHECK_ARG((long long)n <= hw, PSLAM_E_RANGE, "sample_pixels: cannot draw %d distinct pixels out of %lld", n, hw);
-    k_sample_pixels<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(n, hw, seed, seed_dev, idx);
+    launch_chain(k_sample_pixels, dim3(ceil_div(n, 128)), dim3(128), 0, (cudaStream_t)stream, n, hw, seed, seed_dev, idx);
     PSLAM_CHECK_LAUNCH("sample_pixels");
     return 0;
 }
@@ -205,7 +208,7 @@ extern "C" int pslam_track_assemble(int n, const float *pose6, const long long *
 {
     PSLAM_CHECK_ARG(n > 0 && pose6 && idx && rays_d_cam && rays_o && rays_d, PSLAM_E_ARG, "track_assemble: bad argument");
     PSLAM_CHECK_ARG((rgb == nullptr || rgb_all) && (depth == nullptr || depth_all), PSLAM_E_ARG, "track_assemble: targets without their source");
-    k_track_assemble<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(n, pose6, idx, rays_d_cam, rgb_all, depth_all, rays_o, rays_d, rgb, depth);
+    launch_chain(k_track_assemble, dim3(ceil_div(n, 128)), dim3(128), 0, (cudaStream_t)stream, n, pose6, idx, rays_d_cam, rgb_all, depth_all, rays_o, rays_d, rgb, depth);
     PSLAM_CHECK_LAUNCH("track_assemble");
     return 0;
 }
@@ -216,7 +219,7 @@ extern "C" int pslam_track_pose_step(int n, float *pose6, const long long *idx, 
 {
     PSLAM_CHECK_ARG(n > 0 && pose6 && idx && rays_d_cam && g_rays_o && g_rays_d && exp_avg && exp_avg_sq && (step || step_value >= 1.0),
                     PSLAM_E_ARG, "track_pose_step: bad argument");
-    k_track_pose_step<<<1, 256, 0, (cudaStream_t)stream>>>(n, pose6, idx, rays_d_cam, g_rays_o, g_rays_d, exp_avg, exp_avg_sq, step, (float)lr,
+    launch_chain(k_track_pose_step, dim3(1), dim3(256), 0, (cudaStream_t)stream, n, pose6, idx, rays_d_cam, g_rays_o, g_rays_d, exp_avg, exp_avg_sq, step, (float)lr,
                                                            (float)beta1, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps, (float)step_value, grad_out);
     PSLAM_CHECK_LAUNCH("track_pose_step");
     return 0;

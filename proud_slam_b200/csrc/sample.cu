@@ -280,6 +280,7 @@ struct BufSink {
 __global__ void __launch_bounds__(kSampleThreads)
 k_sample_onepass(pslam_render_t p, unsigned long long *__restrict__ state)
 {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char s_raw[];   // hits [3][n_max][T], then samples [3][kSampleBuf][T]
     __shared__ int s_wsum[kSampleThreads / 32];
     __shared__ int s_base;
@@ -412,9 +413,8 @@ int launch_sample_fused(const pslam_render_t *p, cudaStream_t st)
             configured = true;
         }
         unsigned long long *state = reinterpret_cast<unsigned long long *>(block_counts + (((uintptr_t)block_counts & 7) ? 1 : 0));
-        cudaError_t e = cudaMemsetAsync(state, 0, (size_t)nb * sizeof(unsigned long long), st);
-        if (e != cudaSuccess) { set_error("sample: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
-        k_sample_onepass<<<nb, kSampleThreads, smem1, st>>>(*p, state);
+        // (the look-back state was cleared by k_compact_rays, the last kernel of the intersection stage)
+        launch_chain(k_sample_onepass, dim3(nb), dim3(kSampleThreads), smem1, st, *p, state);
         PSLAM_CHECK_LAUNCH("sample_onepass");
         return 0;
     }
