@@ -126,6 +126,9 @@ int pslam_debug_umma_gemm(const float *A, const float *B, float *D, int N, int K
  * weight-gradient form; K <= 64).  N in 16..144 step 16, K a multiple of 16. */
 int pslam_debug_umma_gemm_bf(const float *A, const float *B, float *D, int N, int K, int mode, pslam_stream_t stream);
 int pslam_debug_bf_trace(long long *dev_buf);
+/* Per-warp timeline of the one-pass sampling kernel: [block][warp][8] (globaltimer at entry, clock64 after staging+loop /
+ * scan / look-back / copy-out, globaltimer at exit, the warp's largest and total sample count).  NULL switches it off. */
+int pslam_debug_sample_trace(long long *dev_buf);
 
 /* ------------------------------------------------------------------------
  * Torch-level stages of render_rays (src/variations/render_helpers.py)

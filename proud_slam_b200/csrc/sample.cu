@@ -26,6 +26,19 @@ constexpr int kSampleThreads = 64;    // fused path: one ray per thread, 2 warps
 constexpr int kGroups = 200;      // voxel_helpers.py:300
 constexpr int kChunkRays = 800;   // voxel_helpers.py:331 (4*G)
 
+// optional per-warp timeline (pslam_debug_sample_trace): [block][warp][8] = globaltimer at entry / exit, clock64 after each phase
+__device__ long long *g_sample_trace = nullptr;
+__device__ __forceinline__ long long globaltimer_ns()
+{
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define SAMPLE_TRACE(slot, value)                                                                                  \
+    do {                                                                                                           \
+        if (g_sample_trace) { __syncwarp(); if ((threadIdx.x & 31) == 0) g_sample_trace[((blockIdx.x * (kSampleThreads / 32)) + (threadIdx.x >> 5)) * 8 + (slot)] = (value); } \
+    } while (0)
+
 // The sampling loop for ray j of a group with `num_rays` rays and P hit slots.
 template <class HitView, class Noise, class Sink>
 __device__ __forceinline__ int sample_ray(const HitView &hv, const Noise &noise, Sink &sink, int j, int num_rays, int P,
@@ -47,7 +60,7 @@ __device__ __forceinline__ int sample_ray(const HitView &hv, const Noise &noise,
             ++bin; ++s;
             if (bin >= P || hv.idx(j, bin) == -1) { done = true; break; }
             lo_d = hv.tmin(j, bin); hi_d = hv.tmax(j, bin);
-            lo_c = hi_c; hi_c = __fadd_rn(hi_c, hv.prob(j, bin));
+            lo_c = hi_c; hi_c = hv.next_cdf(hi_c, j, bin);
             z_low = lo_d;
         }
         if (done) break;
@@ -76,6 +89,7 @@ struct RefHits {
     __device__ __forceinline__ float tmin(int j, int b) const { return __ldg(min_ + j * P + b); }
     __device__ __forceinline__ float tmax(int j, int b) const { return __ldg(max_ + j * P + b); }
     __device__ __forceinline__ float prob(int j, int b) const { return __ldg(prob_ + j * P + b); }
+    __device__ __forceinline__ float next_cdf(float hi_c, int j, int b) const { return __fadd_rn(hi_c, prob(j, b)); }
 };
 struct RefNoise {
     const float *row; int max_steps;
@@ -144,6 +158,13 @@ struct FusedHits {
     {
         return __fdiv_rn(__fsub_rn(tmax(j, b), tmin(j, b)), total);  // voxel_helpers.py:639-643
     }
+    // running sum of the bin probabilities: the same left-to-right chain, taken once while the hit list is staged (s_cum)
+    // so that a bin change inside the divergent sampling loop costs a shared-memory read instead of an IEEE division
+    const float *s_cum;
+    __device__ __forceinline__ float next_cdf(float hi_c, int j, int b) const
+    {
+        return (s_cum && b < own_cnt) ? s_cum[b * kSampleThreads] : __fadd_rn(hi_c, prob(j, b));
+    }
 };
 
 // Counter-based uniform noise for production runs (no noise tensor in HBM): the (seed, rank) pair is mixed
@@ -187,7 +208,8 @@ struct CsrSink {
 // Everything one thread does for the ray of rank q: stage its hit list, rebuild the reference's group / chunk
 // indexing, run the sampling loop into `sink`.  Returns the number of emissions.
 template <class Sink>
-__device__ __forceinline__ int run_ray(const pslam_render_t &p, int q, int Rh, int P, int *s_idx, float *s_min, float *s_max, Sink &sink)
+__device__ __forceinline__ int run_ray(const pslam_render_t &p, int q, int Rh, int P, int *s_idx, float *s_min, float *s_max, Sink &sink,
+                                       float *s_cum = nullptr)
 {
     const int n = (Rh + kGroups - 1) / kGroups;
     const int g = q / n, jf = q % n;
@@ -211,6 +233,16 @@ __device__ __forceinline__ int run_ray(const pslam_render_t &p, int q, int Rh, i
     hv.total = total; hv.max_distance = p.max_distance;
     hv.own_j = j; hv.own_r = r; hv.own_cnt = cnt;
     hv.s_idx = s_idx; hv.s_min = s_min; hv.s_max = s_max;
+    hv.s_cum = s_cum;
+    if (s_cum) {
+        float c = 0.0f;
+        for (int b = 0; b < cnt; ++b) {
+            const float pr = hv.prob(0, b);
+            c = (b == 0) ? pr : __fadd_rn(c, pr);
+            s_cum[b * kSampleThreads] = c;
+        }
+    }
+    SAMPLE_TRACE(7, clock64());   // hit list staged
     const float prob0 = hv.prob(j, 0);
     if (p.noise) {
         TensorNoise nz{p.noise + (int64_t)q * p.noise_stride, p.noise_stride};
@@ -268,12 +300,13 @@ k_sample_fused(pslam_render_t p, int *__restrict__ block_counts)
 // 1 = this block's total, 2 = inclusive prefix -- value in the low word; zeroed before the launch), then every thread
 // copies its samples out.  A ray with more emissions than buffer slots simply reruns its loop straight into global memory.
 constexpr int kSampleBuf = 96;
+constexpr int kBufPitch = kSampleThreads + 1;   // [slot][thread] sample buffer, padded so that a column read is conflict-free too
 struct BufSink {
     int *vox; float *z, *dist; int last;
     __device__ __forceinline__ void operator()(int s, int v, float d, float zz)
     {
         last = v;
-        if (s < kSampleBuf) { vox[s * kSampleThreads] = v; z[s * kSampleThreads] = zz; dist[s * kSampleThreads] = fmaxf(d, 0.0f); }
+        if (s < kSampleBuf) { vox[s * kBufPitch] = v; z[s * kBufPitch] = zz; dist[s * kBufPitch] = fmaxf(d, 0.0f); }
     }
 };
 
@@ -281,7 +314,7 @@ __global__ void __launch_bounds__(kSampleThreads)
 k_sample_onepass(pslam_render_t p, unsigned long long *__restrict__ state)
 {
     pdl_enter();
-    extern __shared__ __align__(16) unsigned char s_raw[];   // hits [3][n_max][T], then samples [3][kSampleBuf][T]
+    extern __shared__ __align__(16) unsigned char s_raw[];   // hits [3][n_max][T], samples [3][kSampleBuf][T + 1], cumulative bin probabilities [n_max][T]
     __shared__ int s_wsum[kSampleThreads / 32];
     __shared__ int s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -289,17 +322,21 @@ k_sample_onepass(pslam_render_t p, unsigned long long *__restrict__ state)
     float *s_min = reinterpret_cast<float *>(s_raw) + (size_t)p.n_max * kSampleThreads + tid;
     float *s_max = s_min + (size_t)p.n_max * kSampleThreads;
     int *b_vox = reinterpret_cast<int *>(s_raw) + (size_t)3 * p.n_max * kSampleThreads + tid;
-    float *b_z = reinterpret_cast<float *>(b_vox) + kSampleBuf * kSampleThreads;
-    float *b_dist = b_z + kSampleBuf * kSampleThreads;
+    float *b_z = reinterpret_cast<float *>(b_vox) + kSampleBuf * kBufPitch;
+    float *b_dist = b_z + kSampleBuf * kBufPitch;
+    float *s_cum = b_dist + kSampleBuf * kBufPitch;   // [n_max][T] after the sample buffers: running sums of the bin probabilities
     const int Rh = p.counters[PSLAM_C_RH];
     const int P = p.counters[PSLAM_C_P];
     const int q = blockIdx.x * kSampleThreads + tid;
     int nsamp = 0;
+    SAMPLE_TRACE(0, globaltimer_ns());
+    SAMPLE_TRACE(1, clock64());
     if (q < Rh) {
         BufSink bs{b_vox, b_z, b_dist, 0};
-        const int s = run_ray(p, q, Rh, P, s_idx, s_min, s_max, bs);
+        const int s = run_ray(p, q, Rh, P, s_idx, s_min, s_max, bs, s_cum);
         nsamp = (s > 0 && bs.last == -1) ? s - 1 : s;   // a trailing -1 id (A-Q7) is not a sample and can only be the last emission
     }
+    SAMPLE_TRACE(2, clock64());
     // block scan of the counts
     int x = nsamp;
 #pragma unroll
@@ -344,6 +381,7 @@ k_sample_onepass(pslam_render_t p, unsigned long long *__restrict__ state)
         }
     }
     __syncthreads();
+    SAMPLE_TRACE(3, clock64());
     const int off_raw = s_base + excl;
     if (q < Rh) {
         p.samp_off[q] = off_raw;
@@ -353,21 +391,40 @@ k_sample_onepass(pslam_render_t p, unsigned long long *__restrict__ state)
             p.counters[PSLAM_C_NSAMP] = min(total, p.sample_cap);
             if (total > p.sample_cap) atomicOr(p.counters + PSLAM_C_OVERFLOW, 1);
         }
-        const int off = min(off_raw, p.sample_cap);
-        const int room = max(0, min(off_raw + nsamp, p.sample_cap) - off);
-        if (nsamp <= kSampleBuf) {
-            const int m = min(nsamp, room);
-            for (int k = 0; k < m; ++k) {
-                p.samp_vox[off + k] = b_vox[k * kSampleThreads];
-                p.samp_z[off + k] = b_z[k * kSampleThreads];
-                p.samp_dist[off + k] = b_dist[k * kSampleThreads];
-                p.samp_ray[off + k] = q;
-            }
-        } else {
-            CsrSink csr{p.samp_vox + off, p.samp_z + off, p.samp_dist + off, p.samp_ray + off, q, room};
-            run_ray(p, q, Rh, P, s_idx, s_min, s_max, csr);
+    }
+    const int off = min(off_raw, p.sample_cap);
+    const int room = max(0, min(off_raw + nsamp, p.sample_cap) - off);
+    // copy-out, one ray at a time by the whole warp: lane k takes the ray's k-th sample, so the stores of a ray are one
+    // contiguous run (the per-thread form wrote 32 different lines per store); the buffer pitch of T + 1 keeps both this
+    // column read and the sampling loop's row write free of bank conflicts
+    const int m = (q < Rh && nsamp <= kSampleBuf) ? min(nsamp, room) : 0;
+#pragma unroll 4
+    for (int L = 0; L < 32; ++L) {                      // (unrolled: the shared-memory reads of four rays are in flight together)
+        const int mL = __shfl_sync(0xffffffffu, m, L);
+        const int offL = __shfl_sync(0xffffffffu, off, L);
+        const int col = L - lane;                       // b_* already point at this thread's column
+        if (lane < mL) {
+            const int v = b_vox[lane * kBufPitch + col];
+            const float zz = b_z[lane * kBufPitch + col], dd = b_dist[lane * kBufPitch + col];
+            p.samp_vox[offL + lane] = v;
+            p.samp_z[offL + lane] = zz;
+            p.samp_dist[offL + lane] = dd;
+            p.samp_ray[offL + lane] = q + col;
+        }
+        for (int k = lane + 32; k < mL; k += 32) {      // rays with more than 32 samples
+            p.samp_vox[offL + k] = b_vox[k * kBufPitch + col];
+            p.samp_z[offL + k] = b_z[k * kBufPitch + col];
+            p.samp_dist[offL + k] = b_dist[k * kBufPitch + col];
+            p.samp_ray[offL + k] = q + col;
         }
     }
+    if (q < Rh && nsamp > kSampleBuf) {                 // a ray too long for the buffer reruns straight into global memory
+        CsrSink csr{p.samp_vox + off, p.samp_z + off, p.samp_dist + off, p.samp_ray + off, q, room};
+        run_ray(p, q, Rh, P, s_idx, s_min, s_max, csr, s_cum);
+    }
+    SAMPLE_TRACE(4, clock64());
+    SAMPLE_TRACE(5, globaltimer_ns());
+    SAMPLE_TRACE(6, (long long)warp_max_i(nsamp));
 }
 
 // counts -> exclusive offsets (block-local scan + scanned block bases); also writes off[R_h].
@@ -404,11 +461,11 @@ int launch_sample_fused(const pslam_render_t *p, cudaStream_t st)
     int *block_counts = p->scratch_i + scratch_i_sample_off(p->R);   // after intersect's block_hits; 2 ints per block
     const size_t smem = (size_t)p->n_max * kSampleThreads * 12;
     PSLAM_CHECK_ARG(smem <= 48 * 1024, PSLAM_E_RANGE, "n_max=%d: the per-block hit staging exceeds 48 KB of shared memory", p->n_max);
-    const size_t smem1 = smem + (size_t)kSampleBuf * kSampleThreads * 12;
-    if (smem1 <= 112 * 1024) {
+    const size_t smem1 = smem + (size_t)kSampleBuf * kBufPitch * 12 + (size_t)p->n_max * kSampleThreads * 4;
+    if (smem1 <= 160 * 1024) {
         static bool configured = false;
         if (!configured) {
-            cudaError_t e = cudaFuncSetAttribute(k_sample_onepass, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+            cudaError_t e = cudaFuncSetAttribute(k_sample_onepass, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
             if (e != cudaSuccess) { set_error("sample: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
             configured = true;
         }
@@ -474,6 +531,13 @@ __global__ void k_uniform_sampling_ref(int b, int num_rays, int max_hits, int ma
 }  // namespace pslam
 
 using namespace pslam;
+
+extern "C" int pslam_debug_sample_trace(long long *dev_buf)
+{
+    cudaError_t e = cudaMemcpyToSymbol(g_sample_trace, &dev_buf, sizeof(dev_buf));
+    if (e != cudaSuccess) { set_error("sample_trace: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
 
 extern "C" int pslam_inverse_cdf_sampling(int b, int num_rays, int max_hits, int max_steps, float fixed_step_size,
                                           const int *pts_idx, const float *min_depth, const float *max_depth,
