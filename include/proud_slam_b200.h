@@ -41,10 +41,10 @@ const char *pslam_last_error(void);
 int pslam_device_info(int *out3);
 /* Process-wide configuration.  PSLAM_OPT_DECODER selects the build of the width-128 decoder:
  * 0 = tcgen05 tensor cores with 3xTF32 operand splitting (fp32-equivalent), 1 = fp32 SIMT build,
- * 2 = tcgen05 tensor cores with 3xBF16 operand splitting (16-17 significant bits per operand,
- * <= ~1e-5 relative; inside the 1e-4 parity bound).  Width 256 always runs the SIMT build. */
+ * 2 = tcgen05 tensor cores with 3xF16 operand splitting and power-of-two operand scales (22 significant bits per
+ * operand, fp32-equivalent; default).  Width 256 always runs the SIMT build. */
 #define PSLAM_OPT_DECODER 1
-/* PSLAM_OPT_SAVE_ACT (3xBF16 build): 1 (default) = a forward that will be followed by a decoder-gradient
+/* PSLAM_OPT_SAVE_ACT (3xF16 build): 1 (default) = a forward that will be followed by a decoder-gradient
  * backward (PSLAM_F_GRAD_DEC with a wgrad workspace) spills its activations and ReLU masks, and that backward
  * runs the gradient chain only; 0 = the backward always recomputes the forward. */
 #define PSLAM_OPT_SAVE_ACT 2

@@ -53,8 +53,12 @@ __device__ __forceinline__ int sample_ray(const HitView &hv, const Noise &noise,
     bool done = false;
     if (fixed_step_size > 0.0f) step_size = fixed_step_size;
 
+    // One thread runs one ray, so a step is a chain of dependent latencies (hash, IEEE division) with nothing to hide them
+    // behind: the next step's cdf is computed ahead of the division.  (Taking two in-bin steps together was measured and
+    // dropped: the extra divergence between lanes on the one- and two-step paths cost more than the second division hid.)
+    float cdf_next = __fmul_rn(__fadd_rn(0.0f, noise(0)), step_size);
     for (int step = 0; step < total_steps; ++step) {
-        const float cdf = __fmul_rn(__fadd_rn((float)step, noise(step)), step_size);
+        const float cdf = cdf_next;
         while (cdf > hi_c) {
             sink(s, hv.idx(j, bin), __fsub_rn(hi_d, z_low), __fmul_rn(__fadd_rn(hi_d, z_low), 0.5f));
             ++bin; ++s;
@@ -64,6 +68,7 @@ __device__ __forceinline__ int sample_ray(const HitView &hv, const Noise &noise,
             z_low = lo_d;
         }
         if (done) break;
+        cdf_next = __fmul_rn(__fadd_rn((float)(step + 1), noise(step + 1)), step_size);   // independent of this step: overlaps the division
         const float u = __fdiv_rn(__fsub_rn(cdf, lo_c), __fsub_rn(hi_c, lo_c));
         const float z = __fmaf_rn(u, __fsub_rn(hi_d, lo_d), lo_d);
         sink(s, hv.idx(j, bin), __fsub_rn(z, z_low), __fmul_rn(__fadd_rn(z, z_low), 0.5f));
