@@ -128,9 +128,7 @@ extern "C" int pslam_render_sample(const pslam_render_t *p, pslam_stream_t strea
 {
     if (int rc = check_render(p)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(p->counters, 0, sizeof(int) * PSLAM_C_COUNT, st);
-    if (e != cudaSuccess) { set_error("memset counters: %s", cudaGetErrorString(e)); return (int)e; }
-    if (int rc = launch_intersect_fused(p, st)) return rc;
+    if (int rc = launch_intersect_fused(p, st)) return rc;   // (clears the step's counters first)
     return launch_sample_fused(p, st);
 }
 
@@ -191,11 +189,7 @@ extern "C" int pslam_render_stage(const pslam_render_t *p, int stage, pslam_stre
     if (int rc = check_render(p)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     switch (stage) {
-        case 0: {
-            cudaError_t e = cudaMemsetAsync(p->counters, 0, sizeof(int) * PSLAM_C_COUNT, st);
-            if (e != cudaSuccess) { set_error("memset counters: %s", cudaGetErrorString(e)); return (int)e; }
-            return launch_intersect_fused(p, st);
-        }
+        case 0: return launch_intersect_fused(p, st);
         case 1: return launch_sample_fused(p, st);
         case 2: if (int rc = check_render_field(p, false)) return rc; return launch_field_forward(p, st);
         case 3: if (int rc = check_render_field(p, false)) return rc; return launch_composite_forward(p, st);

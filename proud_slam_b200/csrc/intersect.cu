@@ -185,10 +185,12 @@ constexpr size_t kWideSmem = sizeof(int) * 3 * (kWideStack + kWideHits) * kWideR
 // Child records for the walk: rec[node][c] = (row id of child c or -1, centre of that child).  Expanding a node then
 // costs ONE dependent 16-byte load per lane instead of two (child id, then its centre): the walk is a chain of ~25
 // dependent expansions per ray and nothing but that chain's latency.
-__global__ void k_build_child_records(int N, const float *__restrict__ points, const int *__restrict__ children, int4 *__restrict__ rec)
+__global__ void k_build_child_records(int N, const float *__restrict__ points, const int *__restrict__ children, int4 *__restrict__ rec,
+                                      int *__restrict__ counters)
 {
     pdl_enter();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < PSLAM_C_COUNT) counters[t] = 0;   // first kernel of a step: the step's counters (instead of a memset node in front of the chain)
     if (t >= N * 8) return;
     const int node = t >> 3, c = t & 7;
     const int cid = __ldg(children + (int64_t)node * 9 + c);
@@ -357,9 +359,21 @@ __global__ void __launch_bounds__(1024) k_scan_partials(int *__restrict__ partia
 // rank of every hit ray (order-preserving compaction, render_helpers.py:390-398).
 __global__ void __launch_bounds__(kIntersectThreads)
 k_compact_rays(int R, const int *__restrict__ hit_count, const int *__restrict__ block_base, int *__restrict__ hit_ray,
-               int *__restrict__ ray_rank, int *__restrict__ zero, int zero_n)
+               int *__restrict__ ray_rank, int *__restrict__ zero, int zero_n, int *__restrict__ total_out)
 {
     pdl_enter();
+    __shared__ int s_base;
+    // total_out != NULL: block_base holds the raw per-block hit counts and every block sums its predecessors itself (a few
+    // hundred L2-resident ints: cheaper than a scan kernel in the chain); NULL: block_base was scanned by k_scan_partials
+    if (threadIdx.x < 32) {
+        int acc = 0;
+        if (total_out) {
+            for (int i = threadIdx.x; i < (int)blockIdx.x; i += 32) acc += block_base[i];
+            acc = warp_sum_i(acc);
+            if (threadIdx.x == 0 && blockIdx.x == gridDim.x - 1) *total_out = acc + block_base[blockIdx.x];
+        } else acc = block_base[blockIdx.x];
+        if (threadIdx.x == 0) s_base = acc;
+    }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < zero_n; i += gridDim.x * blockDim.x) zero[i] = 0;   // the sampling kernel's look-back state
     __shared__ int s_warp[kIntersectThreads / 32];   // launched with kWideRays threads per block (<= kIntersectThreads)
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -368,7 +382,7 @@ k_compact_rays(int R, const int *__restrict__ hit_count, const int *__restrict__
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) s_warp[warp] = __popc(ballot);
     __syncthreads();
-    int base = block_base[blockIdx.x];
+    int base = s_base;
     for (int w = 0; w < warp; ++w) base += s_warp[w];
     const int rank = base + __popc(ballot & ((1u << lane) - 1u));
     if (r < R) ray_rank[r] = hit ? rank : -1;
@@ -573,6 +587,8 @@ int launch_intersect_fused(const pslam_render_t *p, cudaStream_t st)
     const bool cached = p->node_cache && p->node_cache_bytes >= (int64_t)128 * p->N && ((uintptr_t)p->node_cache % 16 == 0) &&
                         (int64_t)p->N * 8 <= (int64_t)p->R * 256;
     if (!cached) {   // (building the record table reads both arrays and leaves the table in L2: no separate prefetch then)
+        cudaError_t e = cudaMemsetAsync(p->counters, 0, sizeof(int) * PSLAM_C_COUNT, st);   // (cached: k_build_child_records clears them)
+        if (e != cudaSuccess) { set_error("memset counters: %s", cudaGetErrorString(e)); return (int)e; }
         const size_t na = (size_t)p->N * 12, nbytes = (size_t)p->N * 36;
         k_prefetch_l2<<<(int)ceil_div64((int64_t)(nbytes / 128 + 1), 256), 256, 0, st>>>(reinterpret_cast<const char *>(p->centres), na,
                                                                                   reinterpret_cast<const char *>(p->structure), nbytes);
@@ -587,7 +603,7 @@ int launch_intersect_fused(const pslam_render_t *p, cudaStream_t st)
     }
     if (cached) {
         int4 *rec = static_cast<int4 *>(p->node_cache);
-        launch_chain(k_build_child_records, dim3((int)ceil_div64((int64_t)p->N * 8, 256)), dim3(256), 0, st, p->N, p->centres, p->structure, rec);
+        launch_chain(k_build_child_records, dim3((int)ceil_div64((int64_t)p->N * 8, 256)), dim3(256), 0, st, p->N, p->centres, p->structure, rec, p->counters);
         PSLAM_CHECK_LAUNCH("build_child_records");
         launch_chain(k_intersect_wide<true>, dim3(nb), dim3(kWideThreads), kWideSmem, st, p->R, (float)(p->voxel_size * 0.5), p->n_max, p->max_distance, p->rays_o,
                                                                    p->rays_d, p->centres, p->structure, rec, p->hit_idx, p->hit_min,
@@ -598,9 +614,10 @@ int launch_intersect_fused(const pslam_render_t *p, cudaStream_t st)
                                                                     p->hit_max, p->hit_count, block_hits, p->counters);
     }
     PSLAM_CHECK_LAUNCH("intersect_wide");
-    if (int rc = scan_partials(block_hits, nb, p->counters + PSLAM_C_RH, st)) return rc;
+    const bool own_scan = nb <= 1024;                   // beyond that the O(nb^2) sums lose to the scan kernel
+    if (!own_scan) { if (int rc = scan_partials(block_hits, nb, p->counters + PSLAM_C_RH, st)) return rc; }
     launch_chain(k_compact_rays, dim3(nb), dim3(kWideRays), 0, st, p->R, p->hit_count, block_hits, p->hit_ray, p->ray_rank,
-                 p->scratch_i + scratch_i_sample_off(p->R), 2 * scratch_i_sample_off(p->R));
+                 p->scratch_i + scratch_i_sample_off(p->R), 2 * scratch_i_sample_off(p->R), own_scan ? p->counters + PSLAM_C_RH : nullptr);
     PSLAM_CHECK_LAUNCH("compact_rays");
     return 0;
 }

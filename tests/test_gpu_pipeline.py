@@ -209,6 +209,38 @@ def test_saved_activations_equal_recompute(device):
         assert rel_err(a, b) < 1e-5
 
 
+def test_programmatic_launch_changes_nothing(device):
+    """PSLAM_OPT_PDL: launching the chain with programmatic stream serialization (every kernel starts with
+    griddepcontrol.wait) overlaps launch latency only -- samples and forward outputs are bit-identical to plain stream
+    order over repeated steps, gradients equal up to the order of the floating-point atomics."""
+    from proud_slam_b200 import _lib, scene as sc
+    s, ms = util.build_scene("replica_small")
+    dec = util.test_decoder(width=128, seed=3)
+    rays_o, rays_d, rgb, depth = sc.sample_batch(s, [0, 1], 1024, seed=9)
+    msd = util.to_device(ms, device)
+    msd["voxel_vertex_emb"] = msd["voxel_vertex_emb"].detach()
+    decd = [p.detach().to(device) for p in dec]
+    cw = (util.CRIT["rgb_weight"], util.CRIT["depth_weight"], util.CRIT["fs_weight"], util.CRIT["sdf_weight"])
+    res = []
+    try:
+        for pdl in (1, 0):
+            assert _lib.lib().pslam_set_option(3, pdl) == 0
+            for rep in range(3):                            # back-to-back steps: the chain also crosses step boundaries
+                pipe, g_emb, g_dec = _run_pipeline(
+                    device, rays_o.to(device), rays_d.to(device), rgb.to(device), depth.to(device), msd, decd, voxel_size=s.voxel_size,
+                    step_size=0.1 * s.voxel_size, truncation=util.CRIT["truncation"], max_distance=10.0, max_depth=util.CRIT["max_depth"],
+                    weights=cw, noise=None, tracking=False)
+            n = pipe.counts()["n_samples"]
+            res.append([pipe.samp_vox[:n].clone(), pipe.samp_z[:n].clone(), pipe.samp_out[:n].clone(), pipe.loss.clone(),
+                        g_emb.clone(), pipe.g_rays_o.clone(), pipe.g_rays_d.clone()] + [g.clone() for g in g_dec])
+    finally:
+        _lib.lib().pslam_set_option(3, 1)
+    for a, b in zip(res[0][:4], res[1][:4]):
+        assert torch.equal(a, b)
+    for a, b in zip(res[0][4:], res[1][4:]):
+        assert rel_err(a, b) < 1e-5
+
+
 def test_f16_operand_range_is_guarded(device):
     """3xF16 build: operands are kept in f16's window by fixed power-of-two scales; a decoder whose activations leave it
     (|16 x value| >= 32752) must be reported through the overflow counter, not silently clipped."""
