@@ -169,8 +169,19 @@ extern "C" int pslam_render_backward_ext(const pslam_render_t *p, const float *g
 
 extern "C" int pslam_render_step(const pslam_render_t *p, pslam_stream_t stream)
 {
-    if (int rc = pslam_render_sample(p, stream)) return rc;
-    if (int rc = pslam_render_forward(p, stream)) return rc;
+    if (int rc = check_render(p)) return rc;
+    if (int rc = check_render_field(p, false)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = launch_intersect_fused(p, st)) return rc;
+    cudaEvent_t packed = nullptr;                               // the decoder re-pack runs underneath the sampling kernel
+    if (int rc = fork_decoder_pack(p, st, &packed)) return rc;
+    if (int rc = launch_sample_fused(p, st)) return rc;
+    if (packed && cudaStreamWaitEvent(st, packed, 0) != cudaSuccess) {
+        set_error("render_step: cudaStreamWaitEvent: %s", cudaGetErrorString(cudaGetLastError()));
+        return PSLAM_E_ARG;
+    }
+    if (int rc = launch_field_forward(p, st, packed ? 4 : 0)) return rc;
+    if (int rc = launch_composite_forward(p, st)) return rc;
     if (p->flags & (PSLAM_F_FORWARD_ONLY | PSLAM_F_DEFER_LOSS)) return 0;
     return pslam_render_backward(p, stream);
 }

@@ -767,9 +767,30 @@ static FieldParams params_from_render(const pslam_render_t *p)
     return fp;
 }
 
+// The weight re-pack of a step depends on nothing the step computes: pslam_render_step forks it onto the side stream behind the
+// intersection stage (whose first kernel clears the counters the pack's range flag lives in), underneath the sampling kernel.
+// *packed = the event the forward must wait for, or NULL when the pack was not forked (other decoder builds, no side stream).
+int fork_decoder_pack(const pslam_render_t *p, cudaStream_t st, cudaEvent_t *packed)
+{
+    *packed = nullptr;
+    if (p->dec.width != 128 || decoder_mode() != 2) return 0;
+    const bool simt = (p->flags & PSLAM_F_GRAD_DEC) && !(p->wgrad_ws && (size_t)p->wgrad_ws_bytes >= (size_t)pslam_wgrad_ws_bytes(p->sample_cap));
+    SideStream *side = simt ? nullptr : side_stream();
+    if (!side) return 0;
+    if (cudaEventRecord(side->fork, st) != cudaSuccess || cudaStreamWaitEvent(side->stream, side->fork, 0) != cudaSuccess) {
+        set_error("decoder pack: stream fork: %s", cudaGetErrorString(cudaGetLastError()));
+        return PSLAM_E_ARG;
+    }
+    if (int rc = pack_decoder(p->dec, p->dec_ws, side->stream, false, p->counters + PSLAM_C_OVERFLOW)) return rc;
+    if (cudaEventRecord(side->join, side->stream) != cudaSuccess) { set_error("decoder pack: stream join: %s", cudaGetErrorString(cudaGetLastError())); return PSLAM_E_ARG; }
+    *packed = side->join;
+    return 0;
+}
+
 int launch_field_forward(const pslam_render_t *p, cudaStream_t st, int part)
 {
-    if (part != 3)   // part 3 (profiling): the decoder kernel alone, after a full forward of the same arguments
+    if (part == 4) part = 0;   // part 4: the weights were packed by fork_decoder_pack
+    else if (part != 3)        // part 3 (profiling): the decoder kernel alone, after a full forward of the same arguments
     {
         // the SIMT weights are only read by a SIMT backward: decoder gradients wanted without a large enough workspace
         const bool simt = (p->flags & PSLAM_F_GRAD_DEC) && !(p->wgrad_ws && (size_t)p->wgrad_ws_bytes >= (size_t)pslam_wgrad_ws_bytes(p->sample_cap));

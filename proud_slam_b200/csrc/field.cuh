@@ -60,5 +60,7 @@ int bf_launch_field_forward(const FieldParams &fp, int max_samples, cudaStream_t
 int bf_launch_field_backward(const FieldParams &fp, int max_samples, cudaStream_t st, int part = 0);
 size_t bf_wgrad_scratch_bytes(int max_samples);
 void bf_set_save_activations(int on);   // PSLAM_OPT_SAVE_ACT
+struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
+SideStream *side_stream();            // one non-blocking side stream + fork / join events per device (field_bf.cu)
 
 }  // namespace pslam

@@ -1298,8 +1298,7 @@ int bf_launch_field_forward(const FieldParams &fp_in, int max_samples, cudaStrea
 }
 
 // one non-blocking side stream + fork / join events per device (created on first use, never destroyed)
-struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
-static SideStream *side_stream()
+SideStream *side_stream()
 {
     static SideStream table[64] = {};
     static bool ready[64] = {};

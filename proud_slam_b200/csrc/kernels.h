@@ -17,6 +17,7 @@ int launch_intersect_fused(const pslam_render_t *p, cudaStream_t st);
 int launch_sample_fused(const pslam_render_t *p, cudaStream_t st);
 // field.cu (trilinear lookup + decoder MLP)
 int launch_field_forward(const pslam_render_t *p, cudaStream_t st, int part = 0);   // part 3: the decoder kernel only (profiling)
+int fork_decoder_pack(const pslam_render_t *p, cudaStream_t st, cudaEvent_t *packed);   // then launch_field_forward(..., part 4) after waiting for *packed
 int launch_field_backward(const pslam_render_t *p, cudaStream_t st, int part = 0);  // part 1/2: dgrad / wgrad stage only, 3: the dgrad kernel only
 // composite.cu (SDF->weights compositing + loss)
 int launch_composite_forward(const pslam_render_t *p, cudaStream_t st);
