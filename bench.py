@@ -405,7 +405,7 @@ def run_gpu(args):
                     "h2d_bytes_per_step": int(sum(t.numel() * 4 for t in host)), "d2h_bytes_per_step": 64},
             # our kernels per mapping iteration (3xF16 build): child records, intersect, compact | sample | pack, gather, decoder fwd |
             # composite fwd, loss reduce | prologue, composite bwd, decoder bwd, scatter, wgrad, wgrad finish = 15 (N > 1: + loss coeffs
-            # = 16; torch's gradient-buffer fill and NCCL not counted; profiles/r01_final_launches.csv predates the scan kernel's removal)
+            # = 16; torch's gradient-buffer fill and NCCL not counted; profiles/r01_final_launches.csv)
             "gpu_launches": args.steps * ((15 if world == 1 else 16) if build == 2 else 19),
             "clocks": clocks,
             "roofline": {"kernel": f"{kname} ({ktext}: " + (("5 layers, activations + ReLU masks spilled for the backward" if dom == "decoder_fwd_kernel" else "dgrad chain from the forward's saved ReLU masks, gradient operands spilled for the wgrad kernel") if build == 2 else "decoder recompute + dgrad, fused trilinear backward, wgrad spill") + ")", "bound": "tensor",
