@@ -56,6 +56,25 @@ def test_library_exports_every_declared_symbol():
     assert h.pslam_abi_version() == 2
 
 
+def test_process_wide_options_are_validated():
+    """pslam_set_option (no device work): the documented keys / values are accepted, anything else is an error with a message."""
+    from proud_slam_b200 import _lib
+    lib = _lib.lib()
+    hdr = open(os.path.join(ROOT, "include", "proud_slam_b200.h")).read()
+    keys = {name: int(val) for name, val in re.findall(r"#define (PSLAM_OPT_[A-Z_]+) (\d+)", hdr)}
+    assert keys == {"PSLAM_OPT_DECODER": 1, "PSLAM_OPT_SAVE_ACT": 2, "PSLAM_OPT_PDL": 3}
+    try:
+        for key, values in ((1, (0, 1, 2)), (2, (0, 1)), (3, (0, 1))):
+            for v in values:
+                assert lib.pslam_set_option(key, v) == 0
+            assert lib.pslam_set_option(key, 7) != 0
+            assert b"unknown option" in lib.pslam_last_error()
+        assert lib.pslam_set_option(99, 0) != 0
+    finally:
+        for key, v in ((1, 2), (2, 1), (3, 1)):              # the defaults
+            lib.pslam_set_option(key, v)
+
+
 def test_python_mirror_matches_header_and_struct():
     from proud_slam_b200 import _lib
     lib = _lib.lib()   # checks sizeof / offsetof of pslam_render_t against the ctypes mirror
