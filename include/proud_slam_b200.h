@@ -129,6 +129,9 @@ int pslam_debug_bf_trace(long long *dev_buf);
 /* Per-warp timeline of the one-pass sampling kernel: [block][warp][8] (globaltimer at entry, clock64 after staging+loop /
  * scan / look-back / copy-out, globaltimer at exit, the warp's largest and total sample count).  NULL switches it off. */
 int pslam_debug_sample_trace(long long *dev_buf);
+/* Same for the octree walk (k_intersect_wide, 16 warps of 4 rays per block): [block][warp][8] (globaltimer at entry, clock64 at
+ * entry / after the walk / after the sort / at exit, globaltimer at exit, loop trips of the warp, its largest hit count). */
+int pslam_debug_intersect_trace(long long *dev_buf);
 
 /* ------------------------------------------------------------------------
  * Torch-level stages of render_rays (src/variations/render_helpers.py)

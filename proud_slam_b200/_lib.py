@@ -69,6 +69,7 @@ _PROTOTYPES = {
     "pslam_track_pose_step": (C.c_int, [_I, _P, _P, _P, _P, _P, _P, _P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _P, _S]),
     "pslam_debug_bf_trace": (C.c_int, [_P]),
     "pslam_debug_sample_trace": (C.c_int, [_P]),
+    "pslam_debug_intersect_trace": (C.c_int, [_P]),
     "pslam_set_option": (C.c_int, [_I, _I]),
     "pslam_decoder_ws_count": (C.c_int64, [_I]),
     "pslam_trilinear_fwd": (C.c_int, [_I, _P, _P, _P, _P, _P, _F, _P, _S]),

@@ -203,6 +203,20 @@ __global__ void k_build_child_records(int N, const float *__restrict__ points, c
     rec[t] = r;
 }
 
+// optional per-warp timeline of the walk (pslam_debug_intersect_trace): [block][warp][8] = globaltimer at entry, clock64 at entry /
+// after the walk / after the sort / at exit, globaltimer at exit, expansions (loop trips of the warp), largest hit count
+__device__ long long *g_intersect_trace = nullptr;
+__device__ __forceinline__ void intersect_stamp(long long *tr, int slot, long long v)
+{
+    if (tr && (threadIdx.x & 31) == 0) tr[((size_t)blockIdx.x * (kWideThreads / 32) + (threadIdx.x >> 5)) * 8 + slot] = v;
+}
+__device__ __forceinline__ long long intersect_globaltimer()
+{
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 template <bool CACHED>
 __global__ void __launch_bounds__(kWideThreads)
 k_intersect_wide(int R, float half_voxel, int n_max, float max_distance, const float *__restrict__ ray_start,
@@ -211,6 +225,9 @@ k_intersect_wide(int R, float half_voxel, int n_max, float max_distance, const f
                  int *__restrict__ hit_count, int *__restrict__ block_hits, int *__restrict__ counters)
 {
     pdl_enter();
+    long long *const tr = g_intersect_trace;
+    if (tr) { intersect_stamp(tr, 0, intersect_globaltimer()); intersect_stamp(tr, 1, clock64()); }
+    int trips = 0;
     extern __shared__ int s_wide[];
     int *s_id = s_wide;                                                    // [kWideStack][kWideRays]: id | log2(side) << 26
     float *s_lo = reinterpret_cast<float *>(s_wide + kWideStack * kWideRays);
@@ -236,6 +253,7 @@ k_intersect_wide(int R, float half_voxel, int n_max, float max_distance, const f
         }
     }
     while (__any_sync(0xffffffffu, cur >= 0)) {
+        ++trips;
         bool hit = false;
         int cid = -1;
         float lo = 0.f, hi = 0.f;
@@ -276,6 +294,7 @@ k_intersect_wide(int R, float half_voxel, int n_max, float max_distance, const f
         if (cnt >= n_max) { cur = -1; top = -1; }   // intersect_gpu.cu:233: the walk stops at n_max hits
         __syncwarp();
     }
+    if (tr) intersect_stamp(tr, 2, clock64());
     int count = 0;
     if (valid && sub == 0) {
         // stable insertion sort by entry depth: ties keep DFS order (SURVEY A-Q3)
@@ -292,6 +311,7 @@ k_intersect_wide(int R, float half_voxel, int n_max, float max_distance, const f
         }
     }
     __syncwarp();   // outside any divergent region: a warp may hold valid and out-of-range rays
+    if (tr) intersect_stamp(tr, 3, clock64());
     if (valid) {
         // drop hits that start beyond max_distance (voxel_helpers.py:578)
         while (count < cnt && !(h_lo[count * kWideRays + rl] > max_distance)) ++count;
@@ -306,6 +326,10 @@ k_intersect_wide(int R, float half_voxel, int n_max, float max_distance, const f
     if (lane == 0 && wmax > 0) atomicMax(counters + PSLAM_C_P, wmax);
     if (overflow) atomicOr(counters + PSLAM_C_OVERFLOW, 2);
     if (threadIdx.x == 0) block_hits[blockIdx.x] = nhit;
+    if (tr) {
+        intersect_stamp(tr, 4, clock64()); intersect_stamp(tr, 5, intersect_globaltimer());
+        intersect_stamp(tr, 6, trips); intersect_stamp(tr, 7, wmax);
+    }
 }
 
 // Pulls the flattened octree into L2 before the latency-bound traversal: the DFS is a chain of ~70
@@ -559,6 +583,13 @@ extern "C" int pslam_triangle_intersect(int b, int n, int m, float cagesize, flo
     k_triangle_intersect_ref<<<blocks, 128, 0, (cudaStream_t)stream>>>(b, n, m, cagesize, blur, n_max, ray_start, ray_dir,
                                                                        face_points, idx, depth, uv);
     PSLAM_CHECK_LAUNCH("triangle_intersect");
+    return 0;
+}
+
+extern "C" int pslam_debug_intersect_trace(long long *dev_buf)
+{
+    cudaError_t e = cudaMemcpyToSymbol(g_intersect_trace, &dev_buf, sizeof(dev_buf));
+    if (e != cudaSuccess) { set_error("intersect_trace: %s", cudaGetErrorString(e)); return (int)e; }
     return 0;
 }
 
