@@ -51,6 +51,10 @@ int pslam_device_info(int *out3);
 /* PSLAM_OPT_PDL: 1 (default) = the kernels of the fused step are launched with programmatic stream serialization
  * (each starts with griddepcontrol.wait, so only launch latency overlaps, never data); 0 = plain stream order. */
 #define PSLAM_OPT_PDL 3
+/* PSLAM_OPT_TILES (3xF16 build): 2 (default) = two 128-sample tiles in flight per CTA, the epilogue of one under the MMAs of
+ * the other (csrc/field_pp.cu); 1 = one tile per CTA (csrc/field_bf.cu).  Results are identical up to the fp32 order of
+ * the sdf / colour heads. */
+#define PSLAM_OPT_TILES 4
 int pslam_set_option(int key, int value);
 
 /* ------------------------------------------------------------------------
@@ -126,6 +130,8 @@ int pslam_debug_umma_gemm(const float *A, const float *B, float *D, int N, int K
  * weight-gradient form; K <= 64).  N in 16..144 step 16, K a multiple of 16. */
 int pslam_debug_umma_gemm_bf(const float *A, const float *B, float *D, int N, int K, int mode, pslam_stream_t stream);
 int pslam_debug_bf_trace(long long *dev_buf);
+/* Same for the two-tiles-in-flight kernels (csrc/field_pp.cu): dev_buf[4 iterations][worker g0, worker g1, issuer g0, issuer g1][16]. */
+int pslam_debug_pp_trace(long long *dev_buf);
 /* Per-warp timeline of the one-pass sampling kernel: [block][warp][8] (globaltimer at entry, clock64 after staging+loop /
  * scan / look-back / copy-out, globaltimer at exit, the warp's largest and total sample count).  NULL switches it off. */
 int pslam_debug_sample_trace(long long *dev_buf);

@@ -68,6 +68,7 @@ _PROTOTYPES = {
     "pslam_track_assemble": (C.c_int, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _S]),
     "pslam_track_pose_step": (C.c_int, [_I, _P, _P, _P, _P, _P, _P, _P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _P, _S]),
     "pslam_debug_bf_trace": (C.c_int, [_P]),
+    "pslam_debug_pp_trace": (C.c_int, [_P]),
     "pslam_debug_sample_trace": (C.c_int, [_P]),
     "pslam_debug_intersect_trace": (C.c_int, [_P]),
     "pslam_set_option": (C.c_int, [_I, _I]),
@@ -131,6 +132,9 @@ def lib():
     pdl = os.environ.get("PSLAM_PDL")        # programmatic dependent launch on / off (PSLAM_OPT_PDL)
     if pdl is not None and handle.pslam_set_option(3, int(pdl)) != 0:
         raise RuntimeError(f"PSLAM_PDL={pdl}: " + handle.pslam_last_error().decode(errors="replace"))
+    tiles = os.environ.get("PSLAM_TILES")    # tiles in flight per CTA of the 3xF16 decoder (PSLAM_OPT_TILES)
+    if tiles is not None and handle.pslam_set_option(4, int(tiles)) != 0:
+        raise RuntimeError(f"PSLAM_TILES={tiles}: " + handle.pslam_last_error().decode(errors="replace"))
     _lib = handle
     return _lib
 

@@ -14,7 +14,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
-#include "field.cuh"
+#include "field_bf.cuh"
 
 namespace pslam {
 
@@ -99,6 +99,7 @@ extern "C" int pslam_set_option(int key, int value)
     if (key == PSLAM_OPT_DECODER && (value == 0 || value == 1 || value == 2)) { g_decoder_mode = value; return 0; }
     if (key == PSLAM_OPT_SAVE_ACT && (value == 0 || value == 1)) { bf_set_save_activations(value); return 0; }
     if (key == PSLAM_OPT_PDL && (value == 0 || value == 1)) { g_pdl = value; return 0; }
+    if (key == PSLAM_OPT_TILES && (value == 1 || value == 2)) { pp_set_enabled(value == 2); return 0; }
     set_error("unknown option %d=%d", key, value);
     return PSLAM_E_ARG;
 }

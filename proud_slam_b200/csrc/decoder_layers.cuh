@@ -28,7 +28,8 @@ static __device__ __forceinline__ float tc_weight(const pslam_decoder_t &d, int 
         case 6: return d.W4[k * 144 + n];                                                  // [g_t; g_f][n] = sum_k g_hc[k] W4[k][n]
         case 7: return k < 128 ? d.W3[(1 + k) * 128 + n] : (k == 128 ? d.W3[n] : 0.0f);    // g_h2[n] = sum_j g_o3[j] W3[j][n]
         case 8: return d.W2[k * 128 + n];
-        default: return d.W1[k * 16 + n];                                                  // g_f[n] = sum_k g_h1[k] W1[k][n]
+        case 9: return d.W1[k * 16 + n];                                                   // g_f[n] = sum_k g_h1[k] W1[k][n]
+        default: return d.W4[k * 144 + 128 + n];                                           // (3xF16 stream, layer 10) g_f[n] += sum_k g_hc[k] W4[k][128 + n]
     }
 }
 
