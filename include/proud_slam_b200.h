@@ -55,6 +55,10 @@ int pslam_device_info(int *out3);
  * the other (csrc/field_pp.cu); 1 = one tile per CTA (csrc/field_bf.cu).  Results are identical up to the fp32 order of
  * the sdf / colour heads. */
 #define PSLAM_OPT_TILES 4
+/* PSLAM_OPT_FUSED_WGRAD (3xF16 build, with PSLAM_OPT_TILES = 2): 1 (default) = the mapping backward runs the dgrad chain and the
+ * weight-gradient MMAs in one kernel (csrc/field_bw.cu; no gradient operand leaves the SM); 0 = chain kernel + k_wgrad_bf through
+ * the HBM scratch. */
+#define PSLAM_OPT_FUSED_WGRAD 5
 int pslam_set_option(int key, int value);
 
 /* ------------------------------------------------------------------------
@@ -132,6 +136,8 @@ int pslam_debug_umma_gemm_bf(const float *A, const float *B, float *D, int N, in
 int pslam_debug_bf_trace(long long *dev_buf);
 /* Same for the two-tiles-in-flight kernels (csrc/field_pp.cu): dev_buf[4 iterations][worker g0, worker g1, issuer g0, issuer g1][16]. */
 int pslam_debug_pp_trace(long long *dev_buf);
+/* Same for the fused backward (csrc/field_bw.cu): dev_buf[4 tiles][worker, issuer][16]. */
+int pslam_debug_bw_trace(long long *dev_buf);
 /* Per-warp timeline of the one-pass sampling kernel: [block][warp][8] (globaltimer at entry, clock64 after staging+loop /
  * scan / look-back / copy-out, globaltimer at exit, the warp's largest and total sample count).  NULL switches it off. */
 int pslam_debug_sample_trace(long long *dev_buf);

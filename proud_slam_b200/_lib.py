@@ -69,6 +69,7 @@ _PROTOTYPES = {
     "pslam_track_pose_step": (C.c_int, [_I, _P, _P, _P, _P, _P, _P, _P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _P, _S]),
     "pslam_debug_bf_trace": (C.c_int, [_P]),
     "pslam_debug_pp_trace": (C.c_int, [_P]),
+    "pslam_debug_bw_trace": (C.c_int, [_P]),
     "pslam_debug_sample_trace": (C.c_int, [_P]),
     "pslam_debug_intersect_trace": (C.c_int, [_P]),
     "pslam_set_option": (C.c_int, [_I, _I]),
@@ -135,6 +136,9 @@ def lib():
     tiles = os.environ.get("PSLAM_TILES")    # tiles in flight per CTA of the 3xF16 decoder (PSLAM_OPT_TILES)
     if tiles is not None and handle.pslam_set_option(4, int(tiles)) != 0:
         raise RuntimeError(f"PSLAM_TILES={tiles}: " + handle.pslam_last_error().decode(errors="replace"))
+    fw = os.environ.get("PSLAM_FUSED_WGRAD")  # dgrad chain + weight gradients in one kernel (PSLAM_OPT_FUSED_WGRAD)
+    if fw is not None and handle.pslam_set_option(5, int(fw)) != 0:
+        raise RuntimeError(f"PSLAM_FUSED_WGRAD={fw}: " + handle.pslam_last_error().decode(errors="replace"))
     _lib = handle
     return _lib
 

@@ -1209,6 +1209,8 @@ int bf_launch_field_forward(const FieldParams &fp_in, int max_samples, cudaStrea
     const bool pp = pp_enabled() && fp.feat != nullptr;   // two tiles in flight per CTA (field_pp.cu): reads feature rows only
     if (!save) return pp ? pp_launch(bf::kFwd, fp, max_samples, st) : launch_bf<bf::kFwd>(fp, max_samples, st);
     fp.act_masks = reinterpret_cast<uint32_t *>(scratch_finish(fp, max_samples) + bf::kFinishFloats * sizeof(float));
+    // the fused backward (field_bw.cu) accumulates M = G4^T H2 straight into the reduction block: the forward clears it
+    if (pp && fp.grad_dec) fp.finish_zero = reinterpret_cast<float *>(scratch_finish(fp, max_samples));
     if (int rc = pp ? pp_launch(bf::kFwdSave, fp, max_samples, st) : launch_bf<bf::kFwdSave>(fp, max_samples, st)) return rc;
     g_saved_scratch = fp.wg_scratch;
     g_saved_out = fp.out;
@@ -1239,6 +1241,7 @@ int bf_launch_field_backward(const FieldParams &fp_in, int max_samples, cudaStre
 {
     FieldParams fp = fp_in;
     cudaEvent_t joined = nullptr;
+    bool fused = false;
     if (!fp.grad_dec && !fp.paired) fp.wg_scratch = nullptr;
     fp.spill_ops = fp.grad_dec;
     // per-launch gradient scale: 4 bytes at the end of the weight-stream region (the f16 stream fills only its first half)
@@ -1265,7 +1268,11 @@ int bf_launch_field_backward(const FieldParams &fp_in, int max_samples, cudaStre
         }
         if (saved) {
             const bool pp = pp_enabled() && fp.feat != nullptr;
-            if (int rc = pp ? pp_launch(bf::kBwdSaved, fp, max_samples, st) : launch_bf<bf::kBwdSaved>(fp, max_samples, st)) return rc;
+            // decoder gradients wanted: chain + weight gradients in one kernel (nothing is spilled; the forward cleared the reduction block)
+            fused = pp && bw_enabled() && fp.grad_dec && fp.spill_ops && part != 1;
+            if (fused) {
+                if (int rc = bw_launch(fp, max_samples, reinterpret_cast<float *>(scratch_finish(fp, max_samples)), st)) return rc;
+            } else if (int rc = pp ? pp_launch(bf::kBwdSaved, fp, max_samples, st) : launch_bf<bf::kBwdSaved>(fp, max_samples, st)) return rc;
         } else {
             if (int rc = launch_bf<bf::kBwdRecompute>(fp, max_samples, st)) return rc;
         }
@@ -1299,12 +1306,14 @@ int bf_launch_field_backward(const FieldParams &fp_in, int max_samples, cudaStre
     const int tiles = ceil_div(max_samples > 0 ? max_samples : 1, 128);
     const int grid = tiles < num_sms() ? tiles : num_sms();
     float *finish = reinterpret_cast<float *>(scratch_finish(fp, max_samples));
-    if (!fp.finish_zero) {                              // the chain kernel did not clear the reduction block (part 2 on its own grid)
-        cudaError_t e = cudaMemsetAsync(finish, 0, bf::kFinishFloats * sizeof(float), st);
-        if (e != cudaSuccess) { set_error("wgrad_bf: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
+    if (!fused) {
+        if (!fp.finish_zero) {                          // the chain kernel did not clear the reduction block (part 2 on its own grid)
+            cudaError_t e = cudaMemsetAsync(finish, 0, bf::kFinishFloats * sizeof(float), st);
+            if (e != cudaSuccess) { set_error("wgrad_bf: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
+        }
+        launch_chain(k_wgrad_bf, dim3(grid), dim3(wgb::kThreads), wgb::kSmemBytes, st, fp, finish);
+        PSLAM_CHECK_LAUNCH("wgrad_bf");
     }
-    launch_chain(k_wgrad_bf, dim3(grid), dim3(wgb::kThreads), wgb::kSmemBytes, st, fp, finish);
-    PSLAM_CHECK_LAUNCH("wgrad_bf");
     static bool finish_configured = false;
     if (!finish_configured) {
         cudaError_t e2 = cudaFuncSetAttribute(k_wgrad_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinishSmem);

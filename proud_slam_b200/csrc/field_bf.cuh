@@ -100,6 +100,10 @@ __device__ __forceinline__ float grad_scale(const uint32_t *gscale)
 
 // launchers of the two-tiles-in-flight build (field_pp.cu); KIND = bf::kFwd / kBwdRecompute / kFwdSave / kBwdSaved
 int pp_launch(int kind, const FieldParams &fp, int max_samples, cudaStream_t st);
+// field_bw.cu: dgrad chain + weight gradients in one kernel (the forward must have saved masks and activations)
+int bw_launch(const FieldParams &fp, int max_samples, float *finish, cudaStream_t st);
+int bw_enabled();
+void bw_set_enabled(int on);
 int pp_enabled();
 void pp_set_enabled(int on);
 

@@ -289,7 +289,7 @@ k_field_pp(FieldParams p, const unsigned char *__restrict__ wstream)
         uint32_t done_uses = 0;
         float ymax = 0.0f;
         const float Sg = kIsFwd ? 1.0f : grad_scale(p.gscale), invSg = 1.0f / Sg;
-        if (!kIsFwd && p.finish_zero) {                // clear the wgrad kernel's reduction block
+        if (p.finish_zero) {                           // clear the reduction block of the weight-gradient kernels that follow
             for (int i = (int)blockIdx.x * (kPPThreads - 128) + (int)threadIdx.x - 128; i < (int)(kFinishFloats / 4); i += G * (kPPThreads - 128))
                 reinterpret_cast<float4 *>(p.finish_zero)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }

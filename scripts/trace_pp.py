@@ -25,7 +25,7 @@ for _ in range(3):
     pipe.step()
 torch.cuda.synchronize()
 print(pipe.counts())
-buf = torch.zeros(4 * 4 * 16, dtype=torch.int64, device=dev)
+buf = torch.zeros(1024, dtype=torch.int64, device=dev)
 
 
 def show(stage, nph, title):
@@ -37,7 +37,8 @@ def show(stage, nph, title):
     pipe.stage(stage)
     torch.cuda.synchronize()
     lib.pslam_debug_pp_trace(None)
-    t = buf.cpu().view(4, 4, 16)
+    span = buf.cpu()[256:256 + 296].view(148, 2)
+    t = buf.cpu()[:256].view(4, 4, 16)
     print("==", title)
     for it in (1, 2):
         t0 = int(t[it, 0, 0])
@@ -50,6 +51,10 @@ def show(stage, nph, title):
         print("  next iteration starts", int(t[it + 1, 0, 0]) - t0)
     clk, ns = int(t[3, 3, 13]) - int(t[3, 3, 12]), int(t[3, 3, 15]) - int(t[3, 3, 14])
     print(f"  CTA 0 worker span: {clk} clocks in {ns} ns = {clk / max(ns, 1):.3f} GHz")
+    t00 = int(span[:, 0].min())
+    st, en = (span[:, 0] - t00).tolist(), (span[:, 1] - t00).tolist()
+    print("  CTA entry ns: min %d max %d | exit ns: min %d median %d max %d | CTA 0: %d..%d, worker loop starts at %d"
+          % (min(st), max(st), min(en), sorted(en)[74], max(en), st[0], en[0], int(t[3, 3, 14]) - t00))
 
 
 def timed_stage(stage, reps=5):

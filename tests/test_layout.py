@@ -62,16 +62,16 @@ def test_process_wide_options_are_validated():
     lib = _lib.lib()
     hdr = open(os.path.join(ROOT, "include", "proud_slam_b200.h")).read()
     keys = {name: int(val) for name, val in re.findall(r"#define (PSLAM_OPT_[A-Z_]+) (\d+)", hdr)}
-    assert keys == {"PSLAM_OPT_DECODER": 1, "PSLAM_OPT_SAVE_ACT": 2, "PSLAM_OPT_PDL": 3, "PSLAM_OPT_TILES": 4}
+    assert keys == {"PSLAM_OPT_DECODER": 1, "PSLAM_OPT_SAVE_ACT": 2, "PSLAM_OPT_PDL": 3, "PSLAM_OPT_TILES": 4, "PSLAM_OPT_FUSED_WGRAD": 5}
     try:
-        for key, values in ((1, (0, 1, 2)), (2, (0, 1)), (3, (0, 1)), (4, (1, 2))):
+        for key, values in ((1, (0, 1, 2)), (2, (0, 1)), (3, (0, 1)), (4, (1, 2)), (5, (0, 1))):
             for v in values:
                 assert lib.pslam_set_option(key, v) == 0
             assert lib.pslam_set_option(key, 7) != 0
             assert b"unknown option" in lib.pslam_last_error()
         assert lib.pslam_set_option(99, 0) != 0
     finally:
-        for key, v in ((1, 2), (2, 1), (3, 1), (4, 2)):      # the defaults
+        for key, v in ((1, 2), (2, 1), (3, 1), (4, 2), (5, 1)):   # the defaults
             lib.pslam_set_option(key, v)
 
 
