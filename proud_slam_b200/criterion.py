@@ -1,68 +1,91 @@
-"""Drop-in for ``src/criterion.py``: colour L1 + depth L1 (optionally median-gated) + free-space and
-SDF L2 terms, on the dict ``render_rays`` returns.  Plain torch ops in the reference's order (this is
-the modular route; ``bundle_adjust_frames`` / ``track_frame`` use the fused CUDA loss instead)."""
+"""Drop-in for the reference's ``Criterion`` object (``src/criterion.py:8-116``) on the dict the drop-in ``render_rays`` returns.
+
+This is the *modular* route (``render_rays`` -> ``Criterion`` -> ``loss.backward()``); ``bundle_adjust_frames`` /
+``track_frame`` use the fused CUDA loss of ``pslam_render_step`` instead.  It is written the way the CUDA path computes the
+loss (``csrc/composite.cu``: raw sums first, then one closing step -- the same split that makes the loss shardable over
+GPUs, ``pslam_loss_finalize``), not as a transcription of the reference module: every term is a ratio of two sums over the
+padded ``[R_h, S]`` grid,
+
+    colour   = sum |c_gt - c| / (3 R_h)                                   (criterion.py:37-40)
+    depth    = sum_valid |d_gt - d| / #valid                              (:42-52; tracking: valid also needs
+                                                                             |d_gt - d| / sqrt(var) < 10 median, :45-49)
+    fs       = (1 - n_fs / (n_fs + n_sdf)) * sum_front (s - 1)^2 / (R_h S)          (:78-100)
+    sdf      = (1 - n_sdf / (n_fs + n_sdf)) * sum_band (z + tau s - d_gt)^2 / (R_h S) (:102-116)
+
+with front = z < d_gt - tau, band = not front, not (z > d_gt + tau), 0 < d_gt < max_depth.  Names of the constructor
+argument, the attributes (``max_dpeth`` sic, criterion.py:14) and the returned ``(loss, dict of floats)`` are the reference's.
+"""
 import torch
 import torch.nn as nn
+
+
+def raw_loss_sums(outputs, obs, truncation, max_depth, weight_depth_loss=False):
+    """The sums every loss term is made of (tensors, differentiable where the reference's terms are)."""
+    img, depth = obs
+    hit = outputs["ray_mask"]
+    d_gt, c_gt = depth[hit], img[hit]
+    z, s, d, c = outputs["z_vals"], outputs["sdf"], outputs["depth"], outputs["color"]
+    err_d = (d_gt - d).abs()
+    ok = (d_gt > 0.01) & (d_gt < max_depth)
+    if weight_depth_loss:
+        # median gate: a boolean mask only, no gradient flows through the variance (criterion.py:45-49)
+        var = (outputs["weights"] * (d[:, None] - z) ** 2).sum(-1)
+        ratio = err_d / (var + 1e-10).sqrt()
+        ok = ok & (ratio < 10 * ratio.median())
+    dg = d_gt[:, None]
+    front = z < dg - truncation
+    band = ~front & ~(z > dg + truncation) & ((dg > 0.0) & (dg < max_depth))
+    return {
+        "abs_color": (c_gt - c).abs().sum(), "n_color": float(c.numel()),
+        "abs_depth": err_d[ok].sum(), "n_depth": ok.sum(),
+        "sq_fs": ((s - 1.0) ** 2)[front].sum(), "n_fs": front.sum().float(),
+        "sq_sdf": ((z + truncation * s - dg) ** 2)[band].sum(), "n_sdf": band.sum().float(),
+        "n_elems": float(z.numel()),
+    }
 
 
 class Criterion(nn.Module):
     def __init__(self, args) -> None:
         super().__init__()
         self.args = args
-        self.rgb_weight = args.criteria["rgb_weight"]
-        self.depth_weight = args.criteria["depth_weight"]
-        self.sdf_weight = args.criteria["sdf_weight"]
-        self.fs_weight = args.criteria["fs_weight"]
-        self.truncation = args.criteria["sdf_truncation"]
-        self.max_dpeth = args.data_specs["max_depth"]   # (sic) attribute name of the reference, criterion.py:14
+        c = args.criteria
+        self.rgb_weight, self.depth_weight = c["rgb_weight"], c["depth_weight"]
+        self.sdf_weight, self.fs_weight = c["sdf_weight"], c["fs_weight"]
+        self.truncation = c["sdf_truncation"]
+        self.max_dpeth = args.data_specs["max_depth"]
 
     def weights(self):
         """(rgb, depth, fs, sdf) in the order of the C ABI."""
         return (self.rgb_weight, self.depth_weight, self.fs_weight, self.sdf_weight)
 
-    def forward(self, outputs, obs, use_color_loss=True, use_depth_loss=True, compute_sdf_loss=True,
-                weight_depth_loss=False):
-        img, depth = obs
-        loss, loss_dict = 0, {}
-        pred_depth, pred_color, pred_sdf = outputs["depth"], outputs["color"], outputs["sdf"]
-        z_vals, ray_mask, weights = outputs["z_vals"], outputs["ray_mask"], outputs["weights"]
-        gt_depth, gt_color = depth[ray_mask], img[ray_mask]
+    def forward(self, outputs, obs, use_color_loss=True, use_depth_loss=True, compute_sdf_loss=True, weight_depth_loss=False):
+        r = raw_loss_sums(outputs, obs, self.truncation, self.max_dpeth, weight_depth_loss)
+        terms = {}
         if use_color_loss:
-            color_loss = (gt_color - pred_color).abs().mean()
-            loss += self.rgb_weight * color_loss
-            loss_dict["color_loss"] = color_loss.item()
+            terms["color_loss"] = (self.rgb_weight, r["abs_color"] / r["n_color"])
         if use_depth_loss:
-            valid_depth = (gt_depth > 0.01) & (gt_depth < self.max_dpeth)
-            depth_loss = (gt_depth - pred_depth).abs()
-            if weight_depth_loss:
-                depth_var = torch.sum(weights * ((pred_depth.unsqueeze(-1) - z_vals) ** 2), -1)
-                tmp = depth_loss / torch.sqrt(depth_var + 1e-10)
-                valid_depth = (tmp < 10 * tmp.median()) & valid_depth
-            depth_loss = depth_loss[valid_depth].mean()
-            loss += self.depth_weight * depth_loss
-            loss_dict["depth_loss"] = depth_loss.item()
+            terms["depth_loss"] = (self.depth_weight, r["abs_depth"] / r["n_depth"])
         if compute_sdf_loss:
-            fs_loss, sdf_loss = self.get_sdf_loss(z_vals, gt_depth, pred_sdf, truncation=self.truncation)
-            loss += self.fs_weight * fs_loss
-            loss += self.sdf_weight * sdf_loss
-            loss_dict["fs_loss"] = fs_loss.item()
-            loss_dict["sdf_loss"] = sdf_loss.item()
-        loss_dict["loss"] = loss.item()
-        return loss, loss_dict
+            n_both = r["n_fs"] + r["n_sdf"]
+            terms["fs_loss"] = (self.fs_weight, (1.0 - r["n_fs"] / n_both) * r["sq_fs"] / r["n_elems"])
+            terms["sdf_loss"] = (self.sdf_weight, (1.0 - r["n_sdf"] / n_both) * r["sq_sdf"] / r["n_elems"])
+        loss = sum(w * t for w, t in terms.values())
+        report = {k: float(t.detach()) for k, (_, t) in terms.items()}
+        report["loss"] = float(loss.detach())
+        return loss, report
 
+    # the two helpers the reference exposes on the object (criterion.py:70-116), in terms of the same sums
     def get_masks(self, z_vals, depth, epsilon):
-        front_mask = torch.where(z_vals < (depth - epsilon), torch.ones_like(z_vals), torch.zeros_like(z_vals))
-        back_mask = torch.where(z_vals > (depth + epsilon), torch.ones_like(z_vals), torch.zeros_like(z_vals))
-        depth_mask = torch.where((depth > 0.0) & (depth < self.max_dpeth), torch.ones_like(depth), torch.zeros_like(depth))
-        sdf_mask = (1.0 - front_mask) * (1.0 - back_mask) * depth_mask
-        num_fs_samples = torch.count_nonzero(front_mask).float()
-        num_sdf_samples = torch.count_nonzero(sdf_mask).float()
-        num_samples = num_sdf_samples + num_fs_samples
-        return front_mask, sdf_mask, 1.0 - num_fs_samples / num_samples, 1.0 - num_sdf_samples / num_samples
+        front = z_vals < depth - epsilon
+        band = ~front & ~(z_vals > depth + epsilon) & ((depth > 0.0) & (depth < self.max_dpeth))
+        n_fs, n_sdf = front.sum().float(), band.sum().float()
+        return front.to(z_vals.dtype), band.to(z_vals.dtype), 1.0 - n_fs / (n_fs + n_sdf), 1.0 - n_sdf / (n_fs + n_sdf)
 
     def get_sdf_loss(self, z_vals, depth, predicted_sdf, truncation, loss_type="l2"):
-        d = depth.unsqueeze(-1).expand(*z_vals.shape)
-        front_mask, sdf_mask, fs_weight, sdf_weight = self.get_masks(z_vals, d, truncation)
-        fs_loss = torch.mean(torch.square(predicted_sdf * front_mask - torch.ones_like(predicted_sdf) * front_mask)) * fs_weight
-        sdf_loss = torch.mean(torch.square((z_vals + predicted_sdf * truncation) * sdf_mask - d * sdf_mask)) * sdf_weight
-        return fs_loss, sdf_loss
+        if loss_type != "l2":
+            raise NotImplementedError("only the l2 form is on the SLAM path (criterion.py:78)")
+        dg = depth[:, None].expand_as(z_vals)
+        front, band, w_fs, w_sdf = self.get_masks(z_vals, dg, truncation)
+        n = float(z_vals.numel())
+        return (w_fs * (front * (predicted_sdf - 1.0) ** 2).sum() / n,
+                w_sdf * (band * (z_vals + truncation * predicted_sdf - dg) ** 2).sum() / n)

@@ -105,4 +105,6 @@ if __name__ == "__main__":
     run_case("mapping_tiny", "tiny", 2, 192, 512, tracking=False)
     run_case("tracking_tiny", "tiny", 1, 256, 512, tracking=True)
     run_case("mapping_tiny_w256", "tiny", 2, 96, 512, tracking=False, width=256)
+    # BASELINE.json configs[0]: 2048-ray mapping step on the 0.2 m Replica-shaped octree, default-init decoder
+    run_case("mapping_replica_small", "replica_small", 2, 1024, 0, tracking=False)
     se3_kat()

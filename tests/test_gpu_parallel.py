@@ -51,6 +51,7 @@ def test_two_shards_close_to_one_padded_batch(device):
         P = int(out["_dbg"]["sample_mask"].sum())
         near = util.relu_near_samples(out, sh[0][None], sh[1][None], ms, dec, s.voxel_size, util.RELU_MARGIN["f16"])
         g_full.append(pipe.samp_gout[:P].clone())
+        assert float(near.float().mean()) < 0.02       # share of samples masked as ReLU near-ties
         pipe.samp_gout[:P][near.to(device)] = 0.0
         pipe.stage(5)
     torch.cuda.synchronize()

@@ -9,10 +9,12 @@ import pytest
 import torch
 
 from tests import util
-from tests.util import rel_err
+from tests.util import elem_err, rel_err
 
 pytestmark = pytest.mark.gpu
-TOL = 1e-4
+TOL = 1e-4        # norm-wise: max |a - b| / max |b|
+ELEM_TOL = 1e-4   # element-wise with a floor of 2 % of the largest entry (tests.util.elem_err)
+NEAR_TIE_MAX = 0.02   # largest share of samples whose upstream gradient may be zeroed as "a ReLU pre-activation within rounding of 0"
 
 
 def _run_pipeline(device, rays_o, rays_d, rgb, depth, ms, dec, *, voxel_size, step_size, truncation, max_distance,
@@ -40,7 +42,7 @@ def _run_pipeline(device, rays_o, rays_d, rgb, depth, ms, dec, *, voxel_size, st
 
 
 @pytest.mark.parametrize("build", ["f16", "f16-recompute", "tf32"])
-@pytest.mark.parametrize("name", ["mapping_tiny", "tracking_tiny", "mapping_tiny_w256"])
+@pytest.mark.parametrize("name", ["mapping_tiny", "tracking_tiny", "mapping_tiny_w256", "mapping_replica_small"])
 def test_step_matches_reference_golden(name, build, device):
     with util.decoder_build(build.split("-")[0], save_activations=not build.endswith("recompute")):
         _golden_step(name, device)
@@ -83,6 +85,12 @@ def _golden_step(name, device):
     R = g["rays_o"].reshape(-1, 3).shape[0]
     assert rel_err(pipe.g_rays_o[:R], g["g_rays_o"].reshape(-1, 3)) < TOL
     assert rel_err(pipe.g_rays_d[:R], g["g_rays_d"].reshape(-1, 3)) < TOL
+    # element-wise as well (entries above 2 % of the largest one by one; the rest to an absolute 2e-6 x max)
+    worst = max([elem_err(out["sdf"], g["out_sdf"]), elem_err(out["color"], g["out_color"]), elem_err(out["depth"], g["out_depth"]),
+                 elem_err(g_emb, g["g_emb"]), elem_err(pipe.g_rays_d[:R], g["g_rays_d"].reshape(-1, 3))]
+                + [elem_err(g_dec[i], g[f"g_dec_{i}"]) for i in range(10)])
+    print(f"{name}: worst element-wise error {worst:.2e}")
+    assert worst < ELEM_TOL
 
 
 @pytest.mark.parametrize("decoder_build", ["f16", "f16-recompute", "tf32", "simt"])
@@ -129,7 +137,9 @@ def test_step_matches_oracle(kind, frames, rays, tracking, width, decoder_build,
     decd = [p.detach().to(device) for p in dec]
     cw = (util.CRIT["rgb_weight"], util.CRIT["depth_weight"], util.CRIT["fs_weight"], util.CRIT["sdf_weight"])
     near = util.relu_near_samples(out, rays_o.detach(), rays_d.detach(), ms, dec, s.voxel_size, util.RELU_MARGIN[decoder_build.split("-")[0]])
-    assert float(near.float().mean()) < 0.5
+    near_frac = float(near.float().mean())
+    print(f"{kind}/{decoder_build}: {100 * near_frac:.3f} % of the samples masked as ReLU near-ties")
+    assert near_frac < NEAR_TIE_MAX
     with util.decoder_build(decoder_build.split("-")[0], save_activations=not decoder_build.endswith("recompute")):
         pipe, g_emb, g_dec = _run_pipeline(
             device, rays_o.detach().to(device), rays_d.detach().to(device), rgb.to(device), depth.to(device), msd, decd,
@@ -180,6 +190,11 @@ def test_step_matches_oracle(kind, frames, rays, tracking, width, decoder_build,
     assert rel_err(pipe.g_rays_d[:R], grads[2].reshape(-1, 3)) < TOL
     for i in range(10):
         assert rel_err(g_dec[i], grads[3 + i]) < TOL, f"decoder grad {i}"
+    worst = max([elem_err(so, torch.cat([out["_dbg"]["rgb_p"].detach(), out["_dbg"]["sdf_p"].detach()[:, None]], 1)),
+                 elem_err(g_emb, grads[0]), elem_err(pipe.g_rays_d[:R], grads[2].reshape(-1, 3))]
+                + [elem_err(g_dec[i], grads[3 + i]) for i in range(10)])
+    print(f"{kind}/{decoder_build}: worst element-wise error {worst:.2e}")
+    assert worst < ELEM_TOL
 
 
 def test_saved_activations_equal_recompute(device):

@@ -72,6 +72,16 @@ def rel_err(a, b):
     return float((a - b).abs().max() / denom)
 
 
+def elem_err(a, b, floor=0.02):
+    """Element-wise relative error with an absolute floor: max_i |a_i - b_i| / max(|b_i|, floor * max|b|).  Entries above
+    `floor` of the largest magnitude are held to the relative bound one by one; smaller ones (sums that cancel) to an
+    absolute bound of floor * tolerance * max|b|."""
+    a = torch.as_tensor(a, dtype=torch.float64).cpu()
+    b = torch.as_tensor(b, dtype=torch.float64).cpu()
+    denom = b.abs().clamp(min=float(floor) * float(b.abs().max().clamp(min=1e-30)))
+    return float(((a - b).abs() / denom).max())
+
+
 def oracle_step(rays_o, rays_d, rgb, depth, ms, dec, *, voxel_size, noise=None, tracking=False, inv_dir=None,
                 generator=None):
     """Oracle forward + loss + backward on CPU tensors.  Returns (outputs, loss, parts)."""
