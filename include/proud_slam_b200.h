@@ -11,8 +11,15 @@
  *     the failing launch.  Nothing aborts or exit()s (the reference's
  *     CUDA_CHECK_ERRORS does, sparse_voxels/include/cuda_utils.h:37-48);
  *     pslam_last_error() returns a thread-local message for the last failure.
- *   - all launches are asynchronous on `stream`; the library keeps no global
- *     mutable state and retains no pointer after return.
+ *   - all launches are asynchronous on `stream`; the library retains no caller
+ *     pointer after return.  What it does keep, per process: the options of
+ *     pslam_set_option (plain ints), the debug-trace pointers, and per DEVICE a
+ *     side stream + two events (forked work of one step), the "shared-memory
+ *     attribute already set" flags, and a mutex-guarded record of which
+ *     workspace holds the activations saved by the last forward.  Calls on
+ *     different devices are independent; two host threads may drive two
+ *     pipelines of one device, but one pslam_render_t / workspace belongs to
+ *     one stream at a time.
  *   - outputs and workspaces are caller-allocated (the reference allocates
  *     inside C++, intersect.cpp:98-106 / sample.cpp:80-89; the Python shim
  *     proud_slam_b200/grid.py does that allocation instead).
@@ -221,6 +228,10 @@ enum {
     PSLAM_C_OVERFLOW = 4, /* bit 0: sample_cap too small, bit 1: DFS stack overflow, bit 2: decoder operand outside the 3xF16 range */
     PSLAM_C_TILE = 5,     /* internal work counters */
     PSLAM_C_TILE2 = 6,
+    PSLAM_C_STICKY = 7,   /* OR of PSLAM_C_OVERFLOW over all steps since the caller last cleared it, | 8 if a step had no hit ray.
+                             The next step folds the previous step's flags in before it clears the counters, so a loop of
+                             pslam_render_step calls can be checked once at its end without a host sync per step. */
+    PSLAM_C_STEPS = 8,    /* steps started since the caller last cleared it */
     PSLAM_C_COUNT = 16
 };
 

@@ -46,7 +46,7 @@ class RenderT(C.Structure):
 
 # flags / counter slots / loss slots (include/proud_slam_b200.h)
 F_TRACKING, F_GRAD_EMB, F_GRAD_DEC, F_GRAD_RAYS, F_FORWARD_ONLY, F_DEFER_LOSS = 1, 2, 4, 8, 16, 32
-C_RH, C_P, C_NSAMP, C_S, C_OVERFLOW, C_COUNT = 0, 1, 2, 3, 4, 16
+C_RH, C_P, C_NSAMP, C_S, C_OVERFLOW, C_STICKY, C_STEPS, C_COUNT = 0, 1, 2, 3, 4, 7, 8, 16
 L_TOTAL, L_COLOR, L_DEPTH, L_FS, L_SDF, L_COUNT = 0, 1, 2, 3, 4, 16
 
 _I, _F, _P, _S = C.c_int, C.c_float, C.c_void_p, C.c_void_p

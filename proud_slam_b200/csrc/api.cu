@@ -41,7 +41,7 @@ int num_sms()
     return cached[dev];
 }
 
-static int g_decoder_mode = 2;   // tcgen05 3xBF16 (field_bf.cu)
+static int g_decoder_mode = 2;   // tcgen05 3xF16 (field_pp.cu / field_bw.cu / field_bf.cu)
 int decoder_mode() { return g_decoder_mode; }
 static int g_pdl = 1;             // programmatic dependent launch between the kernels of the fused step
 int pdl_enabled() { return g_pdl; }
@@ -62,14 +62,14 @@ static int check_render(const pslam_render_t *p)
     return 0;
 }
 
-static int check_render_field(const pslam_render_t *p, bool backward)
+static int check_render_field(const pslam_render_t *p, bool backward, bool need_targets = true)
 {
     PSLAM_CHECK_ARG(p->dec.width == 128 || p->dec.width == 256, PSLAM_E_RANGE, "decoder width %d not supported (128 or 256)", p->dec.width);
     PSLAM_CHECK_ARG(p->dec.W1 && p->dec.b1 && p->dec.W2 && p->dec.b2 && p->dec.W3 && p->dec.b3 && p->dec.W4 && p->dec.b4 && p->dec.W5 && p->dec.b5,
                     PSLAM_E_ARG, "null decoder parameter");
     PSLAM_CHECK_ARG(p->dec_ws && p->samp_out && p->ray_out && p->loss && p->loss_raw, PSLAM_E_ARG, "null forward buffer");
     PSLAM_CHECK_ARG((p->target_rgb == nullptr) == (p->target_depth == nullptr), PSLAM_E_ARG, "target_rgb and target_depth go together");
-    if (backward) PSLAM_CHECK_ARG(p->target_rgb && p->target_depth, PSLAM_E_ARG, "backward needs the Criterion targets (use pslam_render_backward_ext otherwise)");
+    if (backward && need_targets) PSLAM_CHECK_ARG(p->target_rgb && p->target_depth, PSLAM_E_ARG, "backward needs the Criterion targets (use pslam_render_backward_ext otherwise)");
     PSLAM_CHECK_ARG(((uintptr_t)p->dec.W1 | (uintptr_t)p->dec.W2 | (uintptr_t)p->dec.W3 | (uintptr_t)p->dec.W4 | (uintptr_t)p->dec_ws |
                      (uintptr_t)p->samp_out | (uintptr_t)p->emb) % 16 == 0,
                     PSLAM_E_ALIGN, "decoder weights, dec_ws, samp_out and emb must be 16-byte aligned");
@@ -163,7 +163,7 @@ extern "C" int pslam_render_backward_ext(const pslam_render_t *p, const float *g
                                          const float *g_weight, pslam_stream_t stream)
 {
     if (int rc = check_render(p)) return rc;
-    PSLAM_CHECK_ARG(p->dec_ws && p->samp_out && p->ray_out && p->samp_gout, PSLAM_E_ARG, "null forward buffer");
+    if (int rc = check_render_field(p, true, false)) return rc;   // decoder, alignment, gradient targets; no Criterion targets needed
     cudaStream_t st = (cudaStream_t)stream;
     if (int rc = launch_composite_backward_ext(p, g_color, g_depth, g_sdf, g_weight, st)) return rc;
     return launch_field_backward(p, st);

@@ -59,6 +59,15 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
 
 int num_sms();
 
+// "Done once per device": cudaFuncSetAttribute (the opt-in dynamic shared-memory size) and occupancy queries belong to a
+// (function, device) pair, so a process that drives several GPUs must repeat them on each.  Races set the same value twice.
+struct PerDevice { bool done[64]; int value[64]; };
+static inline int current_device()
+{
+    int dev = 0;
+    return (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) ? dev : 0;
+}
+
 // Programmatic dependent launch (PSLAM_OPT_PDL).  Every kernel of the fused step starts with pdl_wait() (all earlier grids
 // complete, their memory visible; a no-op for a plain launch) followed by pdl_trigger() (the next grid may be scheduled as
 // soon as every CTA of this one has started), so consecutive launches overlap their launch latency and prologue but never

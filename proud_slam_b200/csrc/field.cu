@@ -701,7 +701,8 @@ template <int W, bool BWD>
 static int launch_field_t(const FieldParams &fp, int max_samples, cudaStream_t st)
 {
     using C = FieldCfg<W>;
-    static bool configured = false;  // idempotent attribute; a race just sets it twice
+    static PerDevice once = {};
+    bool &configured = once.done[current_device()];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_field<W, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
         if (e != cudaSuccess) { set_error("field: cudaFuncSetAttribute(%zu B): %s", C::SMEM, cudaGetErrorString(e)); return (int)e; }

@@ -47,14 +47,15 @@ struct FieldParams {
 // field_tc.cu: tcgen05 build of the width-128 decoder (3xTF32, fp32-equivalent accuracy)
 constexpr int kTcPackFloats = 229376;   // forward + dgrad weight streams in UMMA operand order (hi, lo)
 // decoder build selection (PSLAM_OPT_DECODER), width 128: 0 = tcgen05 3xTF32 (fp32-equivalent), 1 = fp32 SIMT build,
-// 2 = tcgen05 3xBF16 (field_bf.cu, <= ~1e-5 relative); width 256 always runs the SIMT build
+// 2 = tcgen05 3xF16 with power-of-two operand scales (fp32-equivalent; field_pp.cu / field_bw.cu / field_bf.cu); width 256
+// always runs the SIMT build
 int decoder_mode();
 int tc_pack_decoder(const pslam_decoder_t &d, float *ws_tc, cudaStream_t st);
 int tc_launch_field_forward(const FieldParams &fp, int max_samples, cudaStream_t st);
 // part: 0 = dgrad kernel + wgrad kernel, 1 = dgrad kernel only, 2 = wgrad kernel only (profiling)
 int tc_launch_field_backward(const FieldParams &fp, int max_samples, cudaStream_t st, int part = 0);
 size_t tc_wgrad_scratch_bytes(int max_samples);
-// field_bf.cu: 3xBF16 build, same entry points; its weight stream (bf16 hi/lo) fits in the first half of the tc region
+// field_bf.cu: 3xF16 build, same entry points; its weight stream (f16 hi/lo) fits in the first half of the tc region
 int bf_pack_decoder(const pslam_decoder_t &d, float *ws_tc, cudaStream_t st, int *range_flag = nullptr);
 int bf_launch_field_forward(const FieldParams &fp, int max_samples, cudaStream_t st, int part = 0);
 int bf_launch_field_backward(const FieldParams &fp, int max_samples, cudaStream_t st, int part = 0);

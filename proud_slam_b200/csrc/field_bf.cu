@@ -1,23 +1,27 @@
-// Kernel 4 on the 5th-generation tensor cores, "3xBF16" build: the width-128 SDF/colour decoder
+// Kernel 4 on the 5th-generation tensor cores, 3xF16 build, one tile in flight per CTA: the width-128 SDF/colour decoder
 // (src/variations/nrgbd.py:116-135) fused with the trilinear corner-embedding lookup
 // (src/variations/render_helpers.py:105-156, 47-59), forward and backward.
 //
 // Same tile / role structure as field_tc.cu (tile = 128 samples = the 128 lanes of tensor memory, A operand
 // from tensor memory, weights streamed by multicast bulk TMA, persistent 2-CTA clusters), but every value is
-// split into TWO bf16 halves instead of two tf32 halves:
-//         x = hi + lo,  hi = rn_bf16(x), lo = rn_bf16(x - hi)        (16-17 significant bits)
+// split into TWO f16 halves kept in their precise window by power-of-two scales (field_bf.cuh, umma.cuh: h16_split2):
+//         x = hi + lo,  hi = rn_f16(x), lo = rn_f16(x - hi)          (22 significant bits)
 //         a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi                   (kind::f16 MMAs, fp32 accumulate in TMEM)
-// which is <= ~1e-5 relative per product (the reference's tolerance is 1e-4; field_tc.cu stays the
-// fp32-equivalent build).  What that buys:
-//   * one MMA covers K = 16 instead of 8: half the tcgen05.mma instructions, half the weight-stream bytes,
-//     half the tensor-memory columns and tcgen05.st traffic for the A operand (two values per 32-bit column);
+// which is fp32-equivalent (~2^-21 relative per product) at half the MMA count of 3xTF32.  (bf16 halves were built first
+// and rejected: 16 bits, 2e-4 on the rendered sdf.)  What K = 16 per MMA buys over 3xTF32:
+//   * half the tcgen05.mma instructions, half the weight-stream bytes, half the tensor-memory columns and tcgen05.st
+//     traffic for the A operand (two values per 32-bit column);
 //   * hi and lo of one value are 4 bytes together, so the wgrad scratch can hold the operands ALREADY SPLIT
 //     and in MMA order at the same 4 B/element as raw fp32.  The scratch is written in the MN-major
 //     (sample-major) core-matrix layout, so k_wgrad_bf is nothing but bulk-TMA loads feeding tcgen05.mma
 //     with both operands MN-major from shared memory: no transform warps, no transposition, no re-split.
 //   TMEM columns (k_field_bf): A_hi [0,72)  A_lo [72,144)  D0 [144,288)  D1 [288,432).
+// This file now serves the calls field_pp.cu / field_bw.cu do not take: the recomputing backward (pslam_decoder_bwd, and any
+// backward whose forward did not save), launches without feature rows, PSLAM_OPT_TILES = 1; and it owns k_wgrad_bf /
+// k_wgrad_finish, the trilinear kernels and the launch logic of the 3xF16 build.
 #include "field_bf.cuh"
 #include "kernels.h"
+#include <mutex>
 #include <type_traits>
 
 namespace pslam {
@@ -1154,21 +1158,50 @@ static unsigned char *scratch_finish(const FieldParams &fp, int max_samples)
 // Which scratch holds the activations + masks of the most recent saving forward of a fused pipeline (stream-ordered
 // with the backward that consumes them), together with the sample outputs it wrote.  Only `paired` launches (both
 // from one pslam_render_t) save / consume; any other launch that writes the same scratch clears the record.
-static const void *g_saved_scratch = nullptr, *g_saved_out = nullptr;
+// The record is per device and guarded by a mutex (two host threads may drive two pipelines); what it guards is only the
+// host-side decision "the backward may start from the saved masks", the data itself is stream-ordered.
+struct SavedRecord { const void *scratch, *out; };
+static SavedRecord g_saved[64] = {};
+static std::mutex g_saved_mutex;
 static int g_save_activations = 1;
-void bf_set_save_activations(int on) { g_save_activations = on ? 1 : 0; g_saved_scratch = nullptr; }
+void bf_set_save_activations(int on)
+{
+    std::lock_guard<std::mutex> lock(g_saved_mutex);
+    g_save_activations = on ? 1 : 0;
+    for (auto &r : g_saved) r = SavedRecord{nullptr, nullptr};
+}
+static void saved_set(const void *scratch, const void *out)
+{
+    std::lock_guard<std::mutex> lock(g_saved_mutex);
+    g_saved[current_device()] = SavedRecord{scratch, out};
+}
+// a launch is about to rewrite `scratch` and / or the sample outputs `out`: whatever was saved there is gone
+static void saved_invalidate(const void *scratch, const void *out)
+{
+    std::lock_guard<std::mutex> lock(g_saved_mutex);
+    SavedRecord &r = g_saved[current_device()];
+    if ((scratch && scratch == r.scratch) || (out && out == r.out)) r = SavedRecord{nullptr, nullptr};
+}
+static bool saved_matches(const void *scratch, const void *out)
+{
+    std::lock_guard<std::mutex> lock(g_saved_mutex);
+    const SavedRecord &r = g_saved[current_device()];
+    return scratch && scratch == r.scratch && out == r.out;
+}
 
 template <int KIND>
 static int launch_bf(const FieldParams &fp, int max_samples, cudaStream_t st)
 {
-    static bool configured = false;
+    static PerDevice once = {};
+    bool &configured = once.done[current_device()];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_field_bf<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, bf::Smem<KIND>::bytes);
         if (e != cudaSuccess) { set_error("field_bf: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         configured = true;
     }
     // persistent grid = as many whole clusters as can be resident at once (GPC boundaries may strand a few SMs)
-    static int max_clusters = 0;
+    static PerDevice clusters = {};
+    int &max_clusters = clusters.value[current_device()];
     if (max_clusters == 0) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(num_sms() / bf::kCluster * bf::kCluster);
@@ -1201,7 +1234,7 @@ int bf_launch_field_forward(const FieldParams &fp_in, int max_samples, cudaStrea
     const bool save = g_save_activations && fp.paired && (fp.grad_dec || fp.grad_emb || fp.grad_rays) && fp.wg_scratch &&
                       fp.wg_scratch_bytes >= bf_wgrad_scratch_bytes(max_samples);
     fp.spill_ops = fp.grad_dec;
-    if (fp.wg_scratch && fp.wg_scratch == g_saved_scratch) g_saved_scratch = nullptr;
+    saved_invalidate(fp.wg_scratch, fp.out);     // every forward rewrites its outputs (and, with a workspace, the feature rows)
     if (split_trilinear(fp, max_samples)) {
         if (part == 3) fp.feat = scratch_feat(fp, max_samples, 0);      // profiling: the rows of the previous full forward
         else if (int rc = launch_tri_gather(fp, max_samples, st)) return rc;
@@ -1212,8 +1245,7 @@ int bf_launch_field_forward(const FieldParams &fp_in, int max_samples, cudaStrea
     // the fused backward (field_bw.cu) accumulates M = G4^T H2 straight into the reduction block: the forward clears it
     if (pp && fp.grad_dec) fp.finish_zero = reinterpret_cast<float *>(scratch_finish(fp, max_samples));
     if (int rc = pp ? pp_launch(bf::kFwdSave, fp, max_samples, st) : launch_bf<bf::kFwdSave>(fp, max_samples, st)) return rc;
-    g_saved_scratch = fp.wg_scratch;
-    g_saved_out = fp.out;
+    saved_set(fp.wg_scratch, fp.out);
     return 0;
 }
 
@@ -1255,8 +1287,8 @@ int bf_launch_field_backward(const FieldParams &fp_in, int max_samples, cudaStre
             k_grad_scale<<<num_sms(), 256, 0, st>>>(reinterpret_cast<const float4 *>(fp.g_out), fp.nsamp, fp.nsamp_dev, fp.gscale);
             PSLAM_CHECK_LAUNCH("grad_scale");
         }
-        const bool saved = g_save_activations && fp.paired && fp.wg_scratch && fp.wg_scratch == g_saved_scratch && fp.out == g_saved_out;
-        if (!saved && fp.wg_scratch && fp.wg_scratch == g_saved_scratch) g_saved_scratch = nullptr;   // about to be overwritten
+        const bool saved = g_save_activations && fp.paired && saved_matches(fp.wg_scratch, fp.out);
+        if (!saved) saved_invalidate(fp.wg_scratch, nullptr);   // about to be overwritten
         fp.act_masks = fp.wg_scratch ? reinterpret_cast<uint32_t *>(scratch_finish(fp, max_samples) + bf::kFinishFloats * sizeof(float)) : nullptr;
         if (fp.grad_dec && fp.wg_scratch) fp.finish_zero = reinterpret_cast<float *>(scratch_finish(fp, max_samples));
         const bool split = split_trilinear(fp, max_samples);
@@ -1297,7 +1329,8 @@ int bf_launch_field_backward(const FieldParams &fp_in, int max_samples, cudaStre
         }
     }
     if (!fp.grad_dec || part == 1 || part == 3) return 0;
-    static bool configured = false;
+    static PerDevice once = {};
+    bool &configured = once.done[current_device()];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_wgrad_bf, cudaFuncAttributeMaxDynamicSharedMemorySize, wgb::kSmemBytes);
         if (e != cudaSuccess) { set_error("wgrad_bf: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
@@ -1314,7 +1347,8 @@ int bf_launch_field_backward(const FieldParams &fp_in, int max_samples, cudaStre
         launch_chain(k_wgrad_bf, dim3(grid), dim3(wgb::kThreads), wgb::kSmemBytes, st, fp, finish);
         PSLAM_CHECK_LAUNCH("wgrad_bf");
     }
-    static bool finish_configured = false;
+    static PerDevice finish_once = {};
+    bool &finish_configured = finish_once.done[current_device()];
     if (!finish_configured) {
         cudaError_t e2 = cudaFuncSetAttribute(k_wgrad_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinishSmem);
         if (e2 != cudaSuccess) { set_error("wgrad_finish: cudaFuncSetAttribute: %s", cudaGetErrorString(e2)); return (int)e2; }

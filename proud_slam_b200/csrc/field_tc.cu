@@ -887,14 +887,16 @@ size_t tc_wgrad_scratch_bytes(int max_samples) { return (size_t)ceil_div(max_sam
 template <bool BWD>
 static int launch_tc(const FieldParams &fp, int max_samples, cudaStream_t st)
 {
-    static bool configured = false;
+    static PerDevice once = {};
+    bool &configured = once.done[current_device()];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_field_tc<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Smem<BWD>::bytes);
         if (e != cudaSuccess) { set_error("field_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         configured = true;
     }
     // persistent grid = as many whole clusters as can be resident at once (GPC boundaries may strand a few SMs)
-    static int max_clusters = 0;
+    static PerDevice clusters = {};
+    int &max_clusters = clusters.value[current_device()];
     if (max_clusters == 0) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(num_sms() / tc::kCluster * tc::kCluster);
@@ -928,7 +930,8 @@ int tc_launch_field_backward(const FieldParams &fp_in, int max_samples, cudaStre
     if (part != 2)
         if (int rc = launch_tc<true>(fp, max_samples, st)) return rc;
     if (!fp.grad_dec || part == 1) return 0;
-    static bool configured = false;
+    static PerDevice once = {};
+    bool &configured = once.done[current_device()];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::kSmemBytes);
         if (e != cudaSuccess) { set_error("wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }

@@ -182,6 +182,22 @@ constexpr int kWideStack = 64;                   // 7 pending siblings per level
 constexpr int kWideHits = 50;                    // == n_max of the reference (voxel_helpers.py:561)
 constexpr size_t kWideSmem = sizeof(int) * 3 * (kWideStack + kWideHits) * kWideRays;
 
+// First warp of a step: folds the previous step's overflow flags (and "no ray hit") into the sticky slot, counts the step and
+// clears the per-step counters (include/proud_slam_b200.h: PSLAM_C_STICKY).
+__device__ __forceinline__ void step_begin_counters(int *__restrict__ counters, int t)
+{
+    const int old = t < PSLAM_C_COUNT ? counters[t] : 0;
+    const int ov = __shfl_sync(0xffffffffu, old, PSLAM_C_OVERFLOW), rh = __shfl_sync(0xffffffffu, old, PSLAM_C_RH);
+    const int steps = __shfl_sync(0xffffffffu, old, PSLAM_C_STEPS);
+    if (t < PSLAM_C_COUNT) {
+        int v = 0;
+        if (t == PSLAM_C_STICKY) v = old | ov | ((steps > 0 && rh == 0) ? 8 : 0);
+        if (t == PSLAM_C_STEPS) v = old + 1;
+        counters[t] = v;
+    }
+}
+__global__ void k_step_begin(int *__restrict__ counters) { step_begin_counters(counters, threadIdx.x); }
+
 // Child records for the walk: rec[node][c] = (row id of child c or -1, centre of that child).  Expanding a node then
 // costs ONE dependent 16-byte load per lane instead of two (child id, then its centre): the walk is a chain of ~25
 // dependent expansions per ray and nothing but that chain's latency.
@@ -190,7 +206,7 @@ __global__ void k_build_child_records(int N, const float *__restrict__ points, c
 {
     pdl_enter();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < PSLAM_C_COUNT) counters[t] = 0;   // first kernel of a step: the step's counters (instead of a memset node in front of the chain)
+    if (t < 32) step_begin_counters(counters, t);   // first kernel of a step: the step's counters (instead of a memset node in front of the chain)
     if (t >= N * 8) return;
     const int node = t >> 3, c = t & 7;
     const int cid = __ldg(children + (int64_t)node * 9 + c);
@@ -618,14 +634,15 @@ int launch_intersect_fused(const pslam_render_t *p, cudaStream_t st)
     const bool cached = p->node_cache && p->node_cache_bytes >= (int64_t)128 * p->N && ((uintptr_t)p->node_cache % 16 == 0) &&
                         (int64_t)p->N * 8 <= (int64_t)p->R * 256;
     if (!cached) {   // (building the record table reads both arrays and leaves the table in L2: no separate prefetch then)
-        cudaError_t e = cudaMemsetAsync(p->counters, 0, sizeof(int) * PSLAM_C_COUNT, st);   // (cached: k_build_child_records clears them)
-        if (e != cudaSuccess) { set_error("memset counters: %s", cudaGetErrorString(e)); return (int)e; }
+        k_step_begin<<<1, 32, 0, st>>>(p->counters);   // (cached: k_build_child_records does this)
+        PSLAM_CHECK_LAUNCH("step_begin");
         const size_t na = (size_t)p->N * 12, nbytes = (size_t)p->N * 36;
         k_prefetch_l2<<<(int)ceil_div64((int64_t)(nbytes / 128 + 1), 256), 256, 0, st>>>(reinterpret_cast<const char *>(p->centres), na,
                                                                                   reinterpret_cast<const char *>(p->structure), nbytes);
         PSLAM_CHECK_LAUNCH("prefetch_l2");
     }
-    static bool configured = false;
+    static PerDevice once = {};
+    bool &configured = once.done[current_device()];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_intersect_wide<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWideSmem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_intersect_wide<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWideSmem);

@@ -468,7 +468,8 @@ int launch_sample_fused(const pslam_render_t *p, cudaStream_t st)
     PSLAM_CHECK_ARG(smem <= 48 * 1024, PSLAM_E_RANGE, "n_max=%d: the per-block hit staging exceeds 48 KB of shared memory", p->n_max);
     const size_t smem1 = smem + (size_t)kSampleBuf * kBufPitch * 12 + (size_t)p->n_max * kSampleThreads * 4;
     if (smem1 <= 160 * 1024) {
-        static bool configured = false;
+        static PerDevice once = {};
+        bool &configured = once.done[current_device()];
         if (!configured) {
             cudaError_t e = cudaFuncSetAttribute(k_sample_onepass, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
             if (e != cudaSuccess) { set_error("sample: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }

@@ -78,6 +78,10 @@ class DataParallelStep:
         if self.world > 1:
             dist.all_reduce(self.grads.flat, group=self.group)
 
+    def check(self):
+        """Overflow / no-hit flags of all iterations since the last call (one host sync; ``RenderPipeline.check``)."""
+        return self.pipe.check() if hasattr(self.pipe, "check") else None
+
 
 class ChunkedStep:
     """One mapping iteration over a ray batch larger than one launch's workspace (the wgrad scratch is 3.2 kB per

@@ -224,6 +224,50 @@ class RenderPipeline:
             raise RuntimeError("octree traversal stack overflow (the reference asserts here, intersect_gpu.cu:235)")
         return dict(R_h=c[C_RH], P=c[C_P], n_samples=c[C_NSAMP], S=c[C_S])
 
+    # ------------------------------------------------------------------ flags of a whole loop of steps
+    def _raise_for(self, bits, steps):
+        if bits & 1:
+            raise RuntimeError(f"sample capacity exceeded ({self.sample_cap}) in one of the last {steps} steps: the tail of the batch was "
+                               "dropped; build the pipeline with a larger samples_per_ray")
+        if bits & 2:
+            raise RuntimeError("octree traversal stack overflow (the reference asserts here, intersect_gpu.cu:235)")
+        if bits & 8:
+            raise AssertionError("no ray hits the map")          # the reference's assert, render_helpers.py:388
+        if bits & 4:
+            # an operand left the f16 window of the default decoder build: its gradients saturated (satfinite, never NaN).
+            # Continue on the fp32-range 3xTF32 build instead of raising; the caller may redo the affected loop.
+            import warnings
+            _lib.check(self.lib.pslam_set_option(1, 0), "set_option")
+            warnings.warn("a decoder weight, activation or gradient left the range of the 3xF16 tensor-core build "
+                          "(|16 x value| >= 32752): switched this process to the 3xTF32 build (PSLAM_OPT_DECODER = 0)")
+            return "range"
+        return None
+
+    def check(self):
+        """Flags of every step since the last check (one host sync): raises for a dropped batch tail, a traversal stack
+        overflow or a step without hit rays; returns "range" after switching to the 3xTF32 decoder when the 3xF16 window was
+        left (see ``_raise_for``), else None.  The fused loops call this once per loop instead of syncing per step."""
+        c = self.counters.tolist()
+        bits, steps = c[_lib.C_STICKY] | c[C_OVERFLOW] | (8 if (c[_lib.C_STEPS] > 0 and c[C_RH] == 0) else 0), c[_lib.C_STEPS]
+        self.counters[_lib.C_STICKY: _lib.C_STEPS + 1] = 0
+        return self._raise_for(bits, steps)
+
+    def check_async(self):
+        """Non-blocking form: starts a copy of the counters into pinned memory and returns a callable that, once the copy has
+        landed (it waits if necessary), does what ``check`` does.  ``GraphTracker`` evaluates it at the next frame."""
+        host = torch.empty(_lib.C_COUNT, dtype=torch.int32, pin_memory=True)
+        host.copy_(self.counters, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.counters[_lib.C_STICKY: _lib.C_STEPS + 1] = 0
+
+        def finish():
+            ev.synchronize()
+            c = host.tolist()
+            bits = c[_lib.C_STICKY] | c[C_OVERFLOW] | (8 if (c[_lib.C_STEPS] > 0 and c[C_RH] == 0) else 0)
+            return self._raise_for(bits, c[_lib.C_STEPS])
+        return finish
+
     def losses(self):
         l = self.loss.tolist()
         return dict(loss=l[L_TOTAL], color_loss=l[L_COLOR], depth_loss=l[L_DEPTH], fs_loss=l[L_FS], sdf_loss=l[L_SDF])

@@ -352,6 +352,7 @@ def bundle_adjust_frames(keyframe_graph, map_states, sdf_network, resnet, loss_c
                                                      float(grp["lr"]), float(grp["betas"][0]), float(grp["betas"][1]), float(grp["eps"]),
                                                      None, _lib.stream_ptr(device)), "pslam_track_pose_step")
             off += n
+    it.pipe.check()      # capacity / stack / no-hit flags of every iteration above, one sync (the reference syncs >= 7 times per iteration)
 
 
 def track_frame(frame_pose, curr_frame, map_states, sdf_network, resnet, loss_criteria, voxel_size, N_rays=512, step_size=0.05,
@@ -415,6 +416,7 @@ def track_frame(frame_pose, curr_frame, map_states, sdf_network, resnet, loss_cr
             torch.autograd.backward([ray_start_iter, ray_dirs_iter], [it.pipe.g_rays_o[:R], it.pipe.g_rays_d[:R]])
             optim.step()
         hit_mask = it.pipe.hit_count[:R] > 0
+    it.pipe.check()      # flags of all iterations (one sync per frame)
     return init_pose, optim, hit_mask
 
 
@@ -522,6 +524,9 @@ class GraphTracker:
                     v.zero_()
 
     def track(self, init_pose, frame, num_iterations=30):
+        if getattr(self, "_pending_check", None) is not None:      # flags of the previous frame's iterations (copied without a sync)
+            pending, self._pending_check = self._pending_check, None
+            pending()
         self._reset(frame, init_pose)
         if self.graph is None:
             side = torch.cuda.Stream(device=self.device)
@@ -537,4 +542,11 @@ class GraphTracker:
             self._reset(frame, init_pose)
         for _ in range(num_iterations):
             self.graph.replay()
+        self._pending_check = self.it.pipe.check_async()
         return self.pose, self.optim, self.hit_mask
+
+    def finish(self):
+        """Evaluates the flags of the last tracked frame (``track`` checks each frame's flags when the next one starts)."""
+        if getattr(self, "_pending_check", None) is not None:
+            pending, self._pending_check = self._pending_check, None
+            pending()

@@ -283,3 +283,42 @@ def test_sample_pixels_distinct_uniform(hw, n, device):
     if n >= 1024 and n < hw:
         assert abs(float(sets[0].double().mean()) / hw - 0.5) < 0.05      # uniform over the range
     assert lib.pslam_sample_pixels(10, 5, 0, None, _lib.ptr(idx), _lib.stream_ptr(device)) != 0   # more pixels than there are
+
+
+def test_loop_flags_are_sticky_across_steps(device):
+    """A loop of pslam_render_step calls is checked ONCE at its end (RenderPipeline.check): each step folds the previous
+    step's overflow flags into counters[PSLAM_C_STICKY] before it clears the per-step counters, so a dropped batch tail
+    or a step without hit rays several iterations ago is still reported (the reference asserts / syncs in every call,
+    render_helpers.py:388)."""
+    from proud_slam_b200.pipeline import RenderPipeline
+    s, ms, msd, dec, rays_o, rays_d, rgb, depth = _setup(device, "replica_small", 300)
+    decd = [p.detach().to(device) for p in dec]
+    msd = {k: v.detach() for k, v in msd.items()}
+    kw = dict(voxel_size=s.voxel_size, step_size=0.1 * s.voxel_size, truncation=0.1, max_distance=10.0, target_rgb=rgb.to(device),
+              target_depth=depth.to(device), grad_rays=True)
+    R = rays_o.shape[1]
+    # (1) a clean loop reports nothing
+    pipe = RenderPipeline(R, device, samples_per_ray=96)
+    pipe.bind(rays_o.to(device), rays_d.to(device), msd, decd, seed=1, **kw)
+    for _ in range(3):
+        pipe.step()
+    assert pipe.check() is None
+    # (2) capacity exceeded in the FIRST of three steps (the later ones fit: fewer rays)
+    small = RenderPipeline(R, device, samples_per_ray=8)
+    small.bind(rays_o.to(device), rays_d.to(device), msd, decd, seed=1, **kw)
+    small.step()
+    few = slice(0, 20)
+    small.bind(rays_o[:, few].to(device).contiguous(), rays_d[:, few].to(device).contiguous(), msd, decd, seed=2,
+               **{**kw, "target_rgb": rgb[:, few].to(device).contiguous(), "target_depth": depth[:, few].to(device).contiguous()})
+    small.step()
+    small.step()
+    with pytest.raises(RuntimeError, match="capacity"):
+        small.check()
+    assert small.check() is None                                   # cleared by the check
+    # (3) a step whose rays all miss the map, followed by a good one
+    pipe.bind((rays_o + 500.0).to(device), rays_d.to(device), msd, decd, seed=3, **kw)
+    pipe.step()
+    pipe.bind(rays_o.to(device), rays_d.to(device), msd, decd, seed=4, **kw)
+    pipe.step()
+    with pytest.raises(AssertionError, match="no ray hits"):
+        pipe.check()
