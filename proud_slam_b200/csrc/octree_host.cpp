@@ -129,8 +129,7 @@ extern "C" int pslam_octree_has_voxel(void *h, int x, int y, int z)
 {
     if (!h) return -1;
     const Tree *t = static_cast<Tree *>(h);
-    const int n = t->find(x, y, z);
-    return n >= 0 && t->nodes[n].type == kSurface;
+    return t->find(x, y, z) >= 0;   // any leaf at that coordinate, SURFACE voxel or FEATURE corner (octree.cpp:441-473)
 }
 
 extern "C" int pslam_octree_flatten(void *h, float *voxels, float *children, int *features)

@@ -63,19 +63,35 @@ class Octree:
         return int(_lib.lib().pslam_octree_count_leaves(self._handle()))
 
     def has_voxel(self, pt):
+        """octree.cpp:441-473: true when a leaf exists at the coordinate -- a SURFACE voxel or a FEATURE corner."""
         x, y, z = [int(a) for a in torch.as_tensor(pt).view(-1)[:3]]
         return bool(_lib.lib().pslam_octree_has_voxel(self._handle(), x, y, z))
 
     def try_insert(self, pts):
-        """How many of the voxels are not in the tree yet (octree.cpp try_insert)."""
-        pts = torch.as_tensor(pts).int()
-        return int(sum(not self.has_voxel(p) for p in pts))
+        """octree.cpp:385-416: the share of the voxels' corner keys (8 per voxel, deduplicated) that are already in the tree,
+        as a double in [0, 1] (the reference intersects them with ``all_keys``, the corner keys of everything inserted)."""
+        pts = torch.as_tensor(pts)
+        if pts.dim() != 2 or pts.size(1) != 3:
+            return -1.0
+        v = pts.cpu().numpy().astype(np.int64)
+        corner = np.array([[(j >> 2) & 1, (j >> 1) & 1, j & 1] for j in range(8)], np.int64)
+        keys = np.unique((v[:, None, :] + corner[None]).reshape(-1, 3), axis=0)
+        if keys.shape[0] == 0:
+            return float("nan")                                   # 0 / 0 in the reference
+        present = sum(self.has_voxel(k) for k in keys)
+        return float(present) / float(keys.shape[0])
 
     def get_leaf_voxels(self):
+        """octree.cpp:480-511: float32 [n,3] coordinates of the SURFACE voxels in the reference's order (depth-first, children
+        0..7, child id = x bit + 2 y bit + 4 z bit per level)."""
         n = self.count_leaf_nodes()
         out = np.empty((max(n, 1), 3), np.int32)
         _lib.lib().pslam_octree_leaf_voxels(self._handle(), out.ctypes.data_as(C.c_void_p), n)
-        return torch.from_numpy(out[:n].copy())
+        v = out[:n].astype(np.int64)
+        key = np.zeros(n, np.int64)
+        for b in range(int(np.log2(self.grid_dim)) - 1, -1, -1):   # most significant level first: (z, y, x) bits
+            key = (key << 3) | ((((v[:, 2] >> b) & 1) << 2) | (((v[:, 1] >> b) & 1) << 1) | ((v[:, 0] >> b) & 1))
+        return torch.from_numpy(v[np.argsort(key, kind="stable")].astype(np.float32))
 
     def get_centres_and_children(self):
         """octree.cpp:561-687 -> (voxels f32[N,4], children f32[N,8], features i32[N,8],
