@@ -351,6 +351,25 @@ int pslam_track_pose_step(int n, float *pose6, const long long *idx, const float
                           double beta1, double beta2, double eps, float *grad_out, pslam_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * Optimizer step of the mapping loop (src/mapping.py:81-82: torch.optim.Adam over the embedding table and over the decoder,
+ * stepped at src/variations/render_helpers.py:667-676).  One launch for up to 16 tensors, in place on the tensors
+ * torch.optim.Adam owns; torch's arithmetic without weight decay / amsgrad.  row = 16 with row_active ([n / 16] bytes, zeroed
+ * by the caller once): rows that never received a gradient are skipped (exact: zero state and zero gradient give a zero
+ * update).  step: the optimizer's device-side count (capturable form), incremented here; NULL: the count lives on the host
+ * and step_value is its NEW value.  zero_grad != 0 clears the gradients in the same pass.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+    float *param, *grad, *exp_avg, *exp_avg_sq;   /* [n], 16-byte aligned */
+    float *step;                                  /* [1] or NULL */
+    unsigned char *row_active;                    /* [n / row] or NULL (dense) */
+    int64_t n;
+    int row;                                      /* 0 = dense, 16 = embedding rows */
+    float lr;
+} pslam_adam_tensor_t;
+int pslam_adam_step(const pslam_adam_tensor_t *tensors, int count, double step_value, double beta1, double beta2, double eps,
+                    int zero_grad, pslam_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * Host-side octree: torch.classes.svo.Octree,
  * third_party/sparse_octree/src/bindings.cpp:11-35 (init / insert /
  * get_centres_and_children / has_voxel / count_nodes / count_leaf_nodes /

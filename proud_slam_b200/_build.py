@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libproud_b200.so")
-SOURCES = ["api.cu", "intersect.cu", "sample.cu", "field.cu", "field_tc.cu", "field_bf.cu", "field_pp.cu", "field_bw.cu", "composite.cu", "pose.cu", "octree_host.cpp"]
+SOURCES = ["api.cu", "intersect.cu", "sample.cu", "field.cu", "field_tc.cu", "field_bf.cu", "field_pp.cu", "field_bw.cu", "composite.cu", "pose.cu", "optim.cu", "octree_host.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--compiler-options", "-fPIC", "-shared"]
 

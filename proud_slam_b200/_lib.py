@@ -26,6 +26,11 @@ class DecoderGradT(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("W1", "b1", "W2", "b2", "W3", "b3", "W4", "b4", "W5", "b5")]
 
 
+class AdamTensorT(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("param", "grad", "exp_avg", "exp_avg_sq", "step", "row_active")] + [("n", C.c_int64), ("row", C.c_int),
+                                                                                                         ("lr", C.c_float)]
+
+
 class RenderT(C.Structure):
     _fields_ = (
         [(n, C.c_int) for n in ("R", "N", "E", "n_max", "sample_cap", "flags")]
@@ -67,6 +72,7 @@ _PROTOTYPES = {
     "pslam_sample_pixels": (C.c_int, [_I, C.c_longlong, C.c_uint64, _P, _P, _S]),
     "pslam_track_assemble": (C.c_int, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _S]),
     "pslam_track_pose_step": (C.c_int, [_I, _P, _P, _P, _P, _P, _P, _P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _P, _S]),
+    "pslam_adam_step": (C.c_int, [_P, _I, C.c_double, C.c_double, C.c_double, C.c_double, _I, _S]),
     "pslam_debug_bf_trace": (C.c_int, [_P]),
     "pslam_debug_pp_trace": (C.c_int, [_P]),
     "pslam_debug_bw_trace": (C.c_int, [_P]),

@@ -195,8 +195,8 @@ extern "C" int pslam_render_offsetof_loss(void) { return (int)offsetof(pslam_ren
 /* Profiling hook: launches ONE stage of the step so that a benchmark can bracket a single kernel
  * with events.  0 intersect(+compaction) 1 sampling 2 field fwd 3 composite fwd(+loss) 4 composite bwd
  * 5 field bwd (6 / 7: only its dgrad / wgrad stage in the tcgen05 builds; 8 / 9: the forward / backward decoder kernel
- * alone, without the pack / gather / scale / scatter launches around it, 3xF16 build).  The preceding stages must have run
- * on the same argument block. */
+ * alone, without the pack / gather / scale / scatter launches around it, 3xF16 build; 10 / 11: the trilinear gather / scatter
+ * kernel alone).  The preceding stages must have run on the same argument block. */
 extern "C" int pslam_render_stage(const pslam_render_t *p, int stage, pslam_stream_t stream)
 {
     if (int rc = check_render(p)) return rc;
@@ -212,6 +212,8 @@ extern "C" int pslam_render_stage(const pslam_render_t *p, int stage, pslam_stre
         case 7: if (int rc = check_render_field(p, true)) return rc; return launch_field_backward(p, st, 2);
         case 8: if (int rc = check_render_field(p, false)) return rc; return launch_field_forward(p, st, 3);
         case 9: if (int rc = check_render_field(p, true)) return rc; return launch_field_backward(p, st, 3);
+        case 10: if (int rc = check_render_field(p, false)) return rc; return launch_field_forward(p, st, 5);
+        case 11: if (int rc = check_render_field(p, true)) return rc; return launch_field_backward(p, st, 4);
     }
     set_error("unknown stage %d", stage);
     return PSLAM_E_ARG;

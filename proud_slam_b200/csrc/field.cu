@@ -791,7 +791,7 @@ int fork_decoder_pack(const pslam_render_t *p, cudaStream_t st, cudaEvent_t *pac
 int launch_field_forward(const pslam_render_t *p, cudaStream_t st, int part)
 {
     if (part == 4) part = 0;   // part 4: the weights were packed by fork_decoder_pack
-    else if (part != 3)        // part 3 (profiling): the decoder kernel alone, after a full forward of the same arguments
+    else if (part != 3 && part != 5)   // part 3 / 5 (profiling): the decoder / gather kernel alone, after a full forward of the same arguments
     {
         // the SIMT weights are only read by a SIMT backward: decoder gradients wanted without a large enough workspace
         const bool simt = (p->flags & PSLAM_F_GRAD_DEC) && !(p->wgrad_ws && (size_t)p->wgrad_ws_bytes >= (size_t)pslam_wgrad_ws_bytes(p->sample_cap));

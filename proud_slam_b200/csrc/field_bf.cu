@@ -1238,6 +1238,7 @@ int bf_launch_field_forward(const FieldParams &fp_in, int max_samples, cudaStrea
     if (split_trilinear(fp, max_samples)) {
         if (part == 3) fp.feat = scratch_feat(fp, max_samples, 0);      // profiling: the rows of the previous full forward
         else if (int rc = launch_tri_gather(fp, max_samples, st)) return rc;
+        if (part == 5) return 0;                                        // profiling: the trilinear gather alone
     }
     const bool pp = pp_enabled() && fp.feat != nullptr;   // two tiles in flight per CTA (field_pp.cu): reads feature rows only
     if (!save) return pp ? pp_launch(bf::kFwd, fp, max_samples, st) : launch_bf<bf::kFwd>(fp, max_samples, st);
@@ -1280,6 +1281,12 @@ int bf_launch_field_backward(const FieldParams &fp_in, int max_samples, cudaStre
     fp.gscale = reinterpret_cast<uint32_t *>(const_cast<float *>(fp.ws_tc)) + kTcPackFloats - 4;
     const bool gmax_known = fp.paired && fp.gmax_ready;
     if (gmax_known) fp.gscale = fp.gmax_ready;          // k_composite_bwd published max |g_out| while it wrote g_out
+    if (part == 4) {   // profiling: the trilinear scatter alone, on the feature-gradient rows of the previous full backward
+        if (!split_trilinear(fp, max_samples) || !(fp.grad_emb || fp.grad_rays)) return 0;
+        k_tri_scatter<<<(int)ceil_div64((int64_t)(max_samples > 0 ? max_samples : 1) * 4, 256), 256, 0, st>>>(fp, scratch_feat(fp, max_samples, 1));
+        PSLAM_CHECK_LAUNCH("tri_scatter");
+        return 0;
+    }
     if (part != 2) {
         if (!gmax_known && part != 3) {   // part 3 (profiling): the chain kernel alone; the scale of the previous full backward is still there
             cudaError_t e = cudaMemsetAsync(fp.gscale, 0, sizeof(uint32_t), st);

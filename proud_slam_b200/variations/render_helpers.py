@@ -69,12 +69,14 @@ def decoder_params_of(sdf_network):
 def _device_states(map_states, device):
     """map_states tensors on the device with the dtypes the kernels take (the reference calls
     ``.cuda()`` on them at every use, render_helpers.py:108-110)."""
-    return {
+    out = {
         "voxel_center_xyz": map_states["voxel_center_xyz"].to(device, torch.float32).contiguous(),
-        "voxel_structure": map_states["voxel_structure"].to(device, torch.int32).contiguous(),
         "voxel_vertex_idx": map_states["voxel_vertex_idx"].to(device, torch.int32).contiguous(),
         "voxel_vertex_emb": map_states["voxel_vertex_emb"].to(device, torch.float32),
     }
+    if "voxel_structure" in map_states:      # (the meshing queries pass the three tables of the surface voxels only)
+        out["voxel_structure"] = map_states["voxel_structure"].to(device, torch.int32).contiguous()
+    return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -115,6 +117,115 @@ def get_features_vox(samples, map_states, voxel_size):
     idx = samples["sampled_point_voxel_idx"].to(torch.int32).contiguous()
     feats = _TrilinearFn.apply(xyz, ms["voxel_vertex_emb"], idx, ms["voxel_center_xyz"], ms["voxel_vertex_idx"], voxel_size)
     return {"dists": samples["sampled_point_distance"], "emb": feats}
+
+
+# ------------------------------------------------------------------------------------------
+# meshing / evaluation queries (render_helpers.py:243-328): the same two kernels (trilinear lookup + decoder), no gradients
+# ------------------------------------------------------------------------------------------
+def _field_values(sdf_network, ms, xyz, idx, voxel_size, chunk=1 << 20):
+    """(r, g, b, sdf) of arbitrary in-voxel points: ``pslam_trilinear_fwd`` + ``pslam_decoder_fwd`` over chunks of
+    ``chunk`` points (the reference goes through get_features_vox + get_values in chunks of 32 voxels)."""
+    lib = _lib.lib()
+    dev = xyz.device
+    dec = [p.detach().to(dev).contiguous() for p in decoder_params_of(sdf_network)]
+    from ..pipeline import _decoder_struct, check_decoder_params
+    import ctypes as C
+    width = check_decoder_params(dec)
+    ds = _decoder_struct(dec)
+    ws = torch.empty(int(lib.pslam_decoder_ws_count(width)), device=dev)
+    n = xyz.shape[0]
+    out = torch.empty(n, 4, device=dev)
+    centres, vidx, emb = ms["voxel_center_xyz"], ms["voxel_vertex_idx"], ms["voxel_vertex_emb"].detach().contiguous()
+    st = _lib.stream_ptr(dev)
+    feat = torch.empty(min(n, chunk), 16, device=dev)
+    for a in range(0, n, chunk):
+        b = min(a + chunk, n)
+        x, i = xyz[a:b].contiguous(), idx[a:b].contiguous()
+        _lib.check(lib.pslam_trilinear_fwd(b - a, _lib.ptr(x), _lib.ptr(i), _lib.ptr(centres), _lib.ptr(vidx), _lib.ptr(emb), float(voxel_size),
+                                           _lib.ptr(feat), st), "trilinear forward")
+        _lib.check(lib.pslam_decoder_fwd(b - a, C.byref(ds), _lib.ptr(feat), _lib.ptr(ws), _lib.ptr(out[a:b]), st), "decoder forward")
+    return out
+
+
+@torch.no_grad()
+def get_scores(sdf_network, map_states, voxel_size, bits=8):
+    """render_helpers.py:243-296: (r, g, b, sdf) on a ``bits``^3 lattice inside every row of the map, as a CPU tensor
+    ``[N, bits, bits, bits, 4]`` (what the mesher's marching cubes reads).  Rows must have their 8 vertex ids (surface voxels),
+    as in the reference, where ``F.embedding`` faults on -1."""
+    emb = map_states["voxel_vertex_emb"]
+    dev = emb.device if emb.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    ms = _device_states(map_states, dev)
+    res = int(bits)
+    n = ms["voxel_center_xyz"].shape[0]
+    if n == 0:
+        return torch.zeros(0, res, res, res, 4)
+    if bool((ms["voxel_vertex_idx"] < 0).any()):
+        raise RuntimeError("get_scores: every row needs its 8 vertex ids (pass the surface voxels, as the reference's mesher does)")
+    lin = torch.linspace(-0.5, 0.5, res, device=dev)
+    grid = torch.stack(torch.meshgrid(lin, lin, lin, indexing="ij"), -1).reshape(1, -1, 3) * voxel_size
+    xyz = (grid + ms["voxel_center_xyz"].unsqueeze(1)).reshape(-1, 3).float()
+    idx = torch.arange(n, device=dev, dtype=torch.int32).repeat_interleave(res ** 3)
+    vals = _field_values(sdf_network, ms, xyz, idx, voxel_size)
+    return vals.view(n, res, res, res, 4).cpu()
+
+
+@torch.no_grad()
+def eval_points(sdf_network, map_states, sampled_xyz, sampled_idx, voxel_size):
+    """render_helpers.py:299-328: colours of given points inside given voxels, CPU ``[p, 3]`` (``None`` for no points)."""
+    emb = map_states["voxel_vertex_emb"]
+    dev = emb.device if emb.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    ms = _device_states(map_states, dev)
+    xyz = sampled_xyz.reshape(-1, 3).to(dev).float()
+    if xyz.shape[0] == 0:
+        return None
+    idx = sampled_idx.reshape(-1).to(dev).to(torch.int32)
+    return _field_values(sdf_network, ms, xyz, idx, voxel_size)[:, :3].cpu()
+
+
+class SharedMap:
+    """Map hand-off between the mapping and the tracking loop without the reference's round trip through the host
+    (``Mapping.update_share_data``: deepcopy -> CPU -> manager -> ``.cuda()``, src/mapping.py:236-247, src/tracking.py:116-125).
+
+    Two device-resident slots; ``publish`` copies the map tensors and the decoder into the inactive slot on the publisher's
+    stream (device-to-device, no sync) and then flips a version word; ``acquire`` returns the tensors of the last complete
+    version after making the reader's stream wait for that copy.  The tensors are ordinary CUDA tensors, so they also travel
+    through ``torch.multiprocessing`` queues as CUDA IPC handles when mapping and tracking are separate processes, as in
+    the reference (src/voxslam.py:26)."""
+
+    KEYS = ("voxel_vertex_idx", "voxel_center_xyz", "voxel_structure", "voxel_vertex_emb")
+
+    def __init__(self, device=None):
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.slots = [None, None]
+        self.events = [torch.cuda.Event(), torch.cuda.Event()]
+        self.version = 0          # completed publishes; slot = (version - 1) & 1
+
+    def publish(self, map_states, sdf_network):
+        s = self.version & 1
+        dec = decoder_params_of(sdf_network)
+        cur = self.slots[s]
+        fresh = (cur is None or any(cur["map"][k].shape != map_states[k].shape for k in self.KEYS)
+                 or any(a.shape != b.shape for a, b in zip(cur["dec"], dec)))
+        if fresh:
+            cur = {"map": {k: torch.empty_like(map_states[k], device=self.device) for k in self.KEYS},
+                   "dec": [torch.empty_like(p, device=self.device) for p in dec]}
+            self.slots[s] = cur
+        for k in self.KEYS:
+            cur["map"][k].copy_(map_states[k].detach(), non_blocking=True)
+        for d, p in zip(cur["dec"], dec):
+            d.copy_(p.detach(), non_blocking=True)
+        self.events[s].record(torch.cuda.current_stream(self.device))
+        self.version += 1
+        return self.version
+
+    def acquire(self):
+        """(map_states dict, decoder parameter list, version) of the latest complete publish; ``None`` before the first."""
+        if self.version == 0:
+            return None
+        s = (self.version - 1) & 1
+        torch.cuda.current_stream(self.device).wait_event(self.events[s])
+        cur = self.slots[s]
+        return cur["map"], cur["dec"], self.version
 
 
 # ------------------------------------------------------------------------------------------

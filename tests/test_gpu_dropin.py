@@ -322,3 +322,81 @@ def test_loop_flags_are_sticky_across_steps(device):
     pipe.step()
     with pytest.raises(AssertionError, match="no ray hits"):
         pipe.check()
+
+
+@pytest.mark.parametrize("capturable", [True, False])
+def test_fused_adam_matches_torch_adam(capturable, device):
+    """pslam_adam_step (csrc/optim.cu) on the optimizers' own state against torch.optim.Adam over 6 steps: an embedding
+    table whose rows receive gradients sparsely (different rows per step) plus the ten decoder tensors, two learning rates."""
+    from proud_slam_b200.optim import FusedAdam
+    g = torch.Generator().manual_seed(0)
+    emb0 = torch.randn(3000, 16, generator=g) * 0.01
+    dec0 = [torch.randn(*s, generator=g) * 0.1 for s in [(128, 16), (128,), (128, 128), (128,), (129, 128), (129,), (128, 144), (128,), (3, 128), (3,)]]
+
+    def make():
+        emb = emb0.clone().to(device).requires_grad_(True)
+        dec = [p.clone().to(device).requires_grad_(True) for p in dec0]
+        return emb, dec, torch.optim.Adam([emb], lr=5e-3, capturable=capturable), torch.optim.Adam(dec, lr=1e-3, capturable=capturable)
+
+    emb_a, dec_a, oe_a, od_a = make()
+    emb_b, dec_b, oe_b, od_b = make()
+    fused = FusedAdam([oe_b, od_b], row_tensors=[emb_b])
+    assert fused.fused
+    for it in range(6):
+        rows = torch.randperm(3000, generator=g)[:300]
+        ge = torch.zeros(3000, 16)
+        ge[rows] = torch.randn(300, 16, generator=g)
+        gd = [torch.randn(*p.shape, generator=g) for p in dec0]
+        emb_a.grad = ge.to(device)
+        for p, q in zip(dec_a, gd):
+            p.grad = q.to(device)
+        oe_a.step(); od_a.step()
+        gb = {emb_b: ge.to(device).contiguous()}
+        gb.update({p: q.to(device).contiguous() for p, q in zip(dec_b, gd)})
+        assert fused.step(grads=gb, zero_grad=True)
+        assert all(float(t.abs().max()) == 0.0 for t in gb.values())          # cleared in the same pass
+    torch.cuda.synchronize()
+    assert rel_err(emb_b, emb_a) < 1e-6 and util.elem_err(emb_b.detach() - emb0.to(device), emb_a.detach() - emb0.to(device)) < 1e-4
+    for p, q in zip(dec_b, dec_a):
+        assert rel_err(p, q) < 1e-6
+    # the state the torch optimizer owns was advanced: its own next step continues from it
+    assert float(oe_b.state[emb_b]["step"]) == 6.0
+    untouched = (oe_a.state[emb_a]["exp_avg_sq"].amax(1) == 0)
+    assert torch.equal(emb_b[untouched], emb0.to(device)[untouched])            # never-touched rows: bit-identical, skipped
+
+
+def test_get_scores_eval_points_and_shared_map(device):
+    """Meshing queries (render_helpers.py:243-328) = trilinear lookup + decoder on a lattice inside the surface voxels,
+    against the oracle; and the device-side map hand-off (mapping.py:236-247 / tracking.py:116-125 without the host trip)."""
+    from proud_slam_b200.variations import render_helpers as rh
+    s, ms, msd, dec, rays_o, rays_d, rgb, depth = _setup(device, "tiny", 64)
+    surf = torch.nonzero((ms["voxel_vertex_idx"] >= 0).all(-1)).view(-1)
+    sub = {"voxel_vertex_idx": msd["voxel_vertex_idx"][surf.to(device)], "voxel_center_xyz": msd["voxel_center_xyz"][surf.to(device)],
+           "voxel_vertex_emb": msd["voxel_vertex_emb"]}
+    decd = [p.detach().to(device) for p in dec]
+    res = 4
+    scores = rh.get_scores(decd, sub, s.voxel_size, bits=res)
+    assert scores.shape == (surf.numel(), res, res, res, 4) and not scores.is_cuda
+    lin = torch.linspace(-0.5, 0.5, res)
+    grid = torch.stack(torch.meshgrid(lin, lin, lin, indexing="ij"), -1).reshape(1, -1, 3) * s.voxel_size
+    xyz = (grid + ms["voxel_center_xyz"].detach()[surf].unsqueeze(1)).reshape(-1, 3)
+    idx = surf.repeat_interleave(res ** 3)
+    f = ro.get_features_vox(xyz, idx, ms, s.voxel_size)
+    c, sd = ro.decoder_forward(dec, f)
+    ref = torch.cat([c, sd[:, None]], 1).detach().view(-1, res, res, res, 4)
+    assert rel_err(scores, ref) < 1e-4
+    cols = rh.eval_points(decd, msd, xyz[:1000].to(device), idx[:1000].to(device), s.voxel_size)
+    assert cols.shape == (1000, 3) and rel_err(cols, c.detach()[:1000]) < 1e-4
+    assert rh.eval_points(decd, msd, xyz[:0].to(device), idx[:0].to(device), s.voxel_size) is None
+    # hand-off: two publishes, the reader always sees a complete version; a later edit of the source does not leak in
+    shared = rh.SharedMap(device)
+    assert shared.acquire() is None
+    src = {k: v.clone() for k, v in msd.items()}
+    shared.publish(src, decd)
+    m1, d1, v1 = shared.acquire()
+    src["voxel_vertex_emb"].add_(1.0)
+    assert v1 == 1 and torch.equal(m1["voxel_vertex_emb"], msd["voxel_vertex_emb"].detach()) and torch.equal(d1[0], decd[0])
+    shared.publish(src, decd)
+    m2, d2, v2 = shared.acquire()
+    assert v2 == 2 and torch.equal(m2["voxel_vertex_emb"], src["voxel_vertex_emb"]) and m2["voxel_vertex_emb"].data_ptr() != m1["voxel_vertex_emb"].data_ptr()
+    assert torch.equal(m1["voxel_vertex_emb"], msd["voxel_vertex_emb"].detach())      # the first version is still intact
