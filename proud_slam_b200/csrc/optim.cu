@@ -11,6 +11,8 @@
 // state is zero and so is their gradient, for which the update above is exactly zero, so the result equals the dense step bit for
 // bit in what it changes; a byte per row remembers "has state".  The gradient can be cleared in the same pass (the kernels
 // of the next iteration accumulate into it), which replaces the zero_grad / fill launches.
+#include <math.h>
+
 #include "common.cuh"
 
 namespace pslam {
@@ -21,6 +23,7 @@ struct AdamTable {
     long long first_vec[kAdamMaxTensors + 1];   // prefix of float4 counts
     int count;
     float b1, b2, omb1, omb2, eps, step_value;
+    float host_step_size_scale, host_bc2s;   // host-side step count: 1 / (1 - b1^t) and sqrt(1 - b2^t) evaluated in double, like torch
     int zero_grad;
 };
 
@@ -66,9 +69,15 @@ __global__ void __launch_bounds__(256) k_adam_step(AdamTable tab)
         if (row_nz && !had && (lane & 3) == 0 && nval > 0) T.row_active[row] = 1;
     }
     if (!active) return;
-    const float t = T.step ? *T.step : tab.step_value;
-    const float bc1 = 1.0f - powf(tab.b1, t), bc2s = sqrtf(1.0f - powf(tab.b2, t));
-    const float step_size = T.lr / bc1;
+    float step_size, bc2s;
+    if (T.step) {                                  // capturable form: torch evaluates the corrections in fp32 tensor ops
+        const float t = *T.step;
+        step_size = T.lr / (1.0f - powf(tab.b1, t));
+        bc2s = sqrtf(1.0f - powf(tab.b2, t));
+    } else {
+        step_size = T.lr * tab.host_step_size_scale;
+        bc2s = tab.host_bc2s;
+    }
     float p[4], m1[4], m2[4];
     if (nval == 4) {
         const float4 a = *reinterpret_cast<const float4 *>(T.param + e0), b = *reinterpret_cast<const float4 *>(T.exp_avg + e0),
@@ -125,6 +134,10 @@ extern "C" int pslam_adam_step(const pslam_adam_tensor_t *tensors, int count, do
     tab.count = count;
     tab.b1 = (float)beta1; tab.b2 = (float)beta2; tab.omb1 = (float)(1.0 - beta1); tab.omb2 = (float)(1.0 - beta2);
     tab.eps = (float)eps; tab.step_value = (float)step_value; tab.zero_grad = zero_grad;
+    if (step_value >= 1.0) {
+        tab.host_step_size_scale = (float)(1.0 / (1.0 - pow(beta1, step_value)));
+        tab.host_bc2s = (float)sqrt(1.0 - pow(beta2, step_value));
+    }
     cudaStream_t st = (cudaStream_t)stream;
     launch_chain(k_adam_bump, dim3(1), dim3(32), 0, st, tab);
     PSLAM_CHECK_LAUNCH("adam_bump");

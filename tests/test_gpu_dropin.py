@@ -356,9 +356,10 @@ def test_fused_adam_matches_torch_adam(capturable, device):
         assert fused.step(grads=gb, zero_grad=True)
         assert all(float(t.abs().max()) == 0.0 for t in gb.values())          # cleared in the same pass
     torch.cuda.synchronize()
-    assert rel_err(emb_b, emb_a) < 1e-6 and util.elem_err(emb_b.detach() - emb0.to(device), emb_a.detach() - emb0.to(device)) < 1e-4
-    for p, q in zip(dec_b, dec_a):
-        assert rel_err(p, q) < 1e-6
+    # (the update itself is compared, not the parameter it is added to: 1e-4 of the largest total change)
+    assert util.elem_err(emb_b.detach() - emb0.to(device), emb_a.detach() - emb0.to(device)) < 1e-4
+    for p, q, p0 in zip(dec_b, dec_a, dec0):
+        assert rel_err(p.detach() - p0.to(device), q.detach() - p0.to(device)) < 1e-4
     # the state the torch optimizer owns was advanced: its own next step continues from it
     assert float(oe_b.state[emb_b]["step"]) == 6.0
     untouched = (oe_a.state[emb_a]["exp_avg_sq"].amax(1) == 0)
