@@ -329,6 +329,23 @@ def render_rays(rays_o, rays_d, map_states, sdf_network, resnet, step_size, voxe
 # ------------------------------------------------------------------------------------------
 # fused iteration used by the SLAM loops
 # ------------------------------------------------------------------------------------------
+def _frame_on_device(frame, device):
+    """Contiguous fp32 device copies of a frame's per-pixel tensors ([HW,3] camera rays, [HW,3] colour, [HW] depth), made
+    once per frame object (the reference indexes the frame's own tensors and calls ``.cuda()`` on the result per iteration,
+    render_helpers.py:621-640)."""
+    cached = getattr(frame, "_pslam_dev", None)
+    key = (frame.rays_d.data_ptr(), frame.rgb.data_ptr(), frame.depth.data_ptr(), str(device))
+    if cached is None or cached[0] != key:
+        t = (frame.rays_d.reshape(-1, 3).to(device, torch.float32).contiguous(), frame.rgb.reshape(-1, 3).to(device, torch.float32).contiguous(),
+             frame.depth.reshape(-1).to(device, torch.float32).contiguous())
+        cached = (key, t)
+        try:
+            frame._pslam_dev = cached
+        except Exception:
+            pass
+    return cached[1]
+
+
 def _criterion_cfg(loss_criteria):
     return dict(weights=(loss_criteria.rgb_weight, loss_criteria.depth_weight, loss_criteria.fs_weight, loss_criteria.sdf_weight),
                 truncation=loss_criteria.truncation, max_depth=loss_criteria.max_dpeth)
@@ -345,16 +362,19 @@ class FusedIteration:
         self.width = width
 
     def run(self, rays_o, rays_d, rgb, depth, ms, dec, crit, *, voxel_size, step_size, max_distance, tracking, grad_emb,
-            grad_dec, grad_rays, seed):
+            grad_dec, grad_rays, seed, zero_grads=True):
         if grad_emb and (self.g_emb is None or self.g_emb.shape != ms["voxel_vertex_emb"].shape):
             self.g_emb = torch.zeros_like(ms["voxel_vertex_emb"])
         if grad_dec and self.g_dec is None:
-            self.g_dec = [torch.zeros_like(p) for p in dec]
-        if grad_emb:
-            self.g_emb.zero_()
-        if grad_dec:
-            for g in self.g_dec:
-                g.zero_()
+            # one flat buffer: a single fill clears all ten gradients (and a caller may all-reduce it in one go)
+            from ..parallel import FlatGrads
+            self._flat = FlatGrads(torch.zeros(0, 16, device=dec[0].device), dec)
+            self.g_dec = self._flat.g_dec
+        if zero_grads:           # (the fused Adam of bundle_adjust_frames clears the gradients it consumed itself)
+            if grad_emb:
+                self.g_emb.zero_()
+            if grad_dec:
+                self._flat.flat.zero_()
         self.pipe.bind(rays_o, rays_d, ms, dec, voxel_size=voxel_size, step_size=step_size, truncation=crit["truncation"],
                        max_distance=max_distance, max_depth=crit["max_depth"], target_rgb=rgb, target_depth=depth, seed=seed,
                        weights=crit["weights"], tracking=tracking, g_emb=self.g_emb if grad_emb else None,
@@ -365,10 +385,12 @@ class FusedIteration:
 
 def bundle_adjust_frames(keyframe_graph, map_states, sdf_network, resnet, loss_criteria, voxel_size, step_size, N_rays=512,
                          num_iterations=10, truncation=0.1, max_voxel_hit=10, max_distance=10, learning_rate=[1e-2, 5e-3],
-                         embed_optim=None, model_optim=None, resnet_optim=None, update_pose=True):
-    """render_helpers.py:559-676.  Same loop; per iteration the rays of all keyframes are assembled as
-    in the reference (pose autograd kept in torch, se3pose.py), then ONE fused call produces the loss
-    and every gradient; ``.grad`` fields are filled and the caller's optimizers stepped."""
+                         embed_optim=None, model_optim=None, resnet_optim=None, update_pose=True, device_sampling=True):
+    """render_helpers.py:559-676.  Same loop and arguments; per iteration ONE fused call produces the loss and every gradient
+    and the caller's optimizers are stepped.  Around it, for keyframes whose pose is the 6-vector of se3pose.py with a plain
+    Adam: pixels are drawn and rays assembled on the device (``device_sampling``; uniform without replacement, like the
+    frame's own ``sample_rays``, but not its random stream), dL/dpose and the pose Adam are two kernels; the embedding / decoder
+    Adam is one launch on the optimizers' own state.  Any other frame or optimizer keeps the reference's torch route."""
     from .. import _lib
     lib = _lib.lib()
     emb = map_states["voxel_vertex_emb"]
@@ -394,11 +416,51 @@ def bundle_adjust_frames(keyframe_graph, map_states, sdf_network, resnet, loss_c
     dec_params = decoder_params_of(sdf_network)
     crit = _criterion_cfg(loss_criteria)
     crit["truncation"] = truncation
-    it = FusedIteration(N_rays * max(len(keyframe_graph), 1), device, int(dec_params[0].shape[0]))
-    for _ in range(num_iterations):
+    n_frames = max(len(keyframe_graph), 1)
+    it = FusedIteration(N_rays * n_frames, device, int(dec_params[0].shape[0]))
+    # Optimizer step of the embedding table and the decoder as one launch on the optimizers' own state (csrc/optim.cu) when
+    # they are plain fp32 CUDA Adams; it reads the fused step's gradient buffers directly and clears them in the same pass.
+    from ..optim import FusedAdam
+    fused_adam = None
+    if emb.is_cuda and embed_optim is not None:
+        fa = FusedAdam([embed_optim, model_optim], row_tensors=[emb])
+        if fa.fused and all(p.is_cuda for p in dec_params):
+            fused_adam = fa
+    torch_optimizers = [o for o in optimizers if fused_adam is None or (o is not embed_optim and o is not model_optim)]
+    # Device-side ray selection and assembly for the fused-pose frames: n distinct uniform pixels per
+    # frame and iteration from a keyed permutation (pslam_sample_pixels) instead of the frame's Gumbel top-k over all H*W pixels
+    # (src/utils/sample_util.py:4-20), and one gather + rotate kernel per frame (pslam_track_assemble) writing straight into
+    # the concatenated batch instead of three boolean-mask gathers and a torch.cat (render_helpers.py:620-646).
+    dev_frames = {}
+    if device_sampling:
+        for frame in keyframe_graph:
+            if id(frame) in fused and int(frame.rays_d.reshape(-1, 3).shape[0]) >= N_rays:
+                dev_frames[id(frame)] = _frame_on_device(frame, device)
+    R_all = N_rays * n_frames
+    buf_o, buf_d = torch.empty(R_all, 3, device=device), torch.empty(R_all, 3, device=device)
+    buf_rgb, buf_depth = torch.empty(R_all, 3, device=device), torch.empty(R_all, device=device)
+    buf_idx = torch.empty(R_all, dtype=torch.int64, device=device)
+    base_seed = _next_seed()
+    for iteration in range(num_iterations):
+        all_dev = len(dev_frames) == len(keyframe_graph) and len(keyframe_graph) > 0
         rays_o, rays_d, rgb_samples, depth_samples = [], [], [], []
         cam_dirs = []
-        for frame in keyframe_graph:
+        off = 0
+        for k, frame in enumerate(keyframe_graph):
+            if id(frame) in dev_frames:
+                cam_all, rgb_all, depth_all = dev_frames[id(frame)]
+                n = N_rays
+                idx = buf_idx[off:off + n]
+                _lib.check(lib.pslam_sample_pixels(n, cam_all.shape[0], (base_seed + 0x9E3779B97F4A7C15 * (iteration * n_frames + k + 1)) & 0xFFFFFFFFFFFFFFFF,
+                                                   None, _lib.ptr(idx), _lib.stream_ptr(device)), "pslam_sample_pixels")
+                o_k, d_k = buf_o[off:off + n], buf_d[off:off + n]
+                _lib.check(lib.pslam_track_assemble(n, _lib.ptr(frame.pose.data), _lib.ptr(idx), _lib.ptr(cam_all), _lib.ptr(rgb_all),
+                                                    _lib.ptr(depth_all), _lib.ptr(o_k), _lib.ptr(d_k), _lib.ptr(buf_rgb[off:off + n]),
+                                                    _lib.ptr(buf_depth[off:off + n]), _lib.stream_ptr(device)), "pslam_track_assemble")
+                cam_dirs += [(cam_all, idx)]
+                rays_o += [o_k]; rays_d += [d_k]; rgb_samples += [buf_rgb[off:off + n]]; depth_samples += [buf_depth[off:off + n]]
+                off += n
+                continue
             frame.sample_rays(N_rays)
             sample_mask = frame.sample_mask.to(device)
             sampled_rays_d = frame.rays_d.to(device)[sample_mask]
@@ -420,29 +482,40 @@ def bundle_adjust_frames(keyframe_graph, map_states, sdf_network, resnet, loss_c
                 rays_o += [pose[:3, 3].reshape(1, -1).expand_as(sampled_rays_d)]
             rgb_samples += [frame.rgb.to(device)[sample_mask]]
             depth_samples += [frame.depth.to(device)[sample_mask]]
+            off += rays_d[-1].shape[0]
         counts = [t.shape[0] for t in rays_d]
-        rays_d = torch.cat(rays_d, dim=0)
-        rays_o = torch.cat(rays_o, dim=0)
-        rgb_samples = torch.cat(rgb_samples, dim=0).float().contiguous()
-        depth_samples = torch.cat(depth_samples, dim=0).float().contiguous()
+        if all_dev:      # every frame wrote its slice of the batch buffers: nothing to concatenate
+            n_tot = sum(counts)
+            rays_o, rays_d, rgb_samples, depth_samples = buf_o[:n_tot], buf_d[:n_tot], buf_rgb[:n_tot], buf_depth[:n_tot]
+        else:
+            rays_d = torch.cat(rays_d, dim=0)
+            rays_o = torch.cat(rays_o, dim=0)
+            rgb_samples = torch.cat(rgb_samples, dim=0).float().contiguous()
+            depth_samples = torch.cat(depth_samples, dim=0).float().contiguous()
         torch_pose = rays_d.requires_grad or rays_o.requires_grad
         need_pose = torch_pose or (update_pose and any(id(f) in fused and f.stamp != 0 for f in keyframe_graph))
         ms["voxel_vertex_emb"] = emb.detach() if emb.is_cuda else emb.detach().to(device)
         dec = [p.detach() for p in dec_params]
         it.run(rays_o.detach().float().contiguous(), rays_d.detach().float().contiguous(), rgb_samples, depth_samples, ms, dec, crit,
                voxel_size=voxel_size, step_size=step_size, max_distance=max_distance, tracking=False, grad_emb=True,
-               grad_dec=model_optim is not None, grad_rays=need_pose, seed=_next_seed())
-        for optim in optimizers:
+               grad_dec=model_optim is not None, grad_rays=need_pose, seed=_next_seed(), zero_grads=fused_adam is None or iteration == 0)
+        for optim in torch_optimizers:
             optim.zero_grad()
-        emb.grad = it.g_emb if emb.is_cuda else it.g_emb.to(emb.device)
-        if model_optim is not None:
-            for p, g in zip(dec_params, it.g_dec):
-                p.grad = g.clone()
+        if fused_adam is None:
+            emb.grad = it.g_emb if emb.is_cuda else it.g_emb.to(emb.device)
+            if model_optim is not None:
+                for p, g in zip(dec_params, it.g_dec):
+                    p.grad = g.clone()
         if torch_pose:
             R = rays_o.shape[0]
             torch.autograd.backward([rays_o, rays_d], [it.pipe.g_rays_o[:R], it.pipe.g_rays_d[:R]])
-        for optim in optimizers:
+        for optim in torch_optimizers:
             optim.step()
+        if fused_adam is not None:
+            grads = {emb: it.g_emb}
+            if model_optim is not None:
+                grads.update({p: g for p, g in zip(dec_params, it.g_dec)})
+            fused_adam.step(grads=grads, zero_grad=True)
         off = 0
         for frame, cd, n in zip(keyframe_graph, cam_dirs, counts):
             if cd is not None and frame.stamp != 0 and update_pose and n > 0:

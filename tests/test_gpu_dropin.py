@@ -184,11 +184,17 @@ def test_tracking_and_mapping_loops_run_and_improve(device):
         return float(loss)
 
     before = eval_loss()
-    rh.bundle_adjust_frames(frames, ms, dec, None, crit, s.voxel_size, 0.1 * s.voxel_size, N_rays=512, num_iterations=30,
+    rh.bundle_adjust_frames(frames, ms, dec, None, crit, s.voxel_size, 0.1 * s.voxel_size, N_rays=512, num_iterations=100,
                             truncation=0.1, max_voxel_hit=10, max_distance=10.0, embed_optim=embed_optim, model_optim=model_optim,
                             update_pose=True)
     after = eval_loss()
     assert after < 0.7 * before, (before, after)
+    assert float(embed_optim.state[ms["voxel_vertex_emb"]]["step"]) == 100.0      # the fused Adam advanced the caller's optimizer state
+    # the reference's own route for ray selection (frame.sample_rays + mask gathers) still works and keeps improving
+    rh.bundle_adjust_frames(frames, ms, dec, None, crit, s.voxel_size, 0.1 * s.voxel_size, N_rays=512, num_iterations=3,
+                            truncation=0.1, max_voxel_hit=10, max_distance=10.0, embed_optim=embed_optim, model_optim=model_optim,
+                            update_pose=False, device_sampling=False)
+    assert eval_loss() < 0.7 * before
     # tracking: start 3 cm off, expect to end closer to the true pose
     true_t = frames[1].pose.translation().detach().clone()
     start = util.TestFrame(s, s.frames[1], stamp=1, device=device, perturb=(0.03, -0.02, 0.02), seed=9)
@@ -197,6 +203,8 @@ def test_tracking_and_mapping_loops_run_and_improve(device):
                                            N_rays=1024, step_size=0.1 * s.voxel_size, num_iterations=40, truncation=0.1,
                                            learning_rate=0.01, max_voxel_hit=10, max_distance=10.0, depth_variance=True)
     e1 = float((pose.translation().detach() - true_t).norm())
+    drift = float((true_t.cpu() - s.frames[1].pose[:3, 3]).norm())
+    print(f"BA loss {before:.4f} -> {after:.4f}; BA moved frame 1 by {drift:.4f} m; tracking error {e0:.4f} -> {e1:.4f} m")
     assert hit_mask.shape == (1024,) and hit_mask.dtype == torch.bool
     assert e1 < e0, (e0, e1)
     # the same optimisation as one CUDA graph per iteration
