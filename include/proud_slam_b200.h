@@ -145,11 +145,12 @@ int pslam_debug_bf_trace(long long *dev_buf);
 int pslam_debug_pp_trace(long long *dev_buf);
 /* Same for the fused backward (csrc/field_bw.cu): dev_buf[4 tiles][worker, issuer][16]. */
 int pslam_debug_bw_trace(long long *dev_buf);
-/* Per-warp timeline of the one-pass sampling kernel: [block][warp][8] (globaltimer at entry, clock64 after staging+loop /
- * scan / look-back / copy-out, globaltimer at exit, the warp's largest and total sample count).  NULL switches it off. */
+/* Per-warp timeline of the sampling kernel (k_sample_warp, 8 warps per block): [block][warp][8] (globaltimer at entry, clock64 at
+ * entry / hits staged / rays sampled / offsets known / copied out, globaltimer at exit, the warp's largest sample count).
+ * NULL switches it off. */
 int pslam_debug_sample_trace(long long *dev_buf);
-/* Same for the octree walk (k_intersect_wide, 16 warps of 4 rays per block): [block][warp][8] (globaltimer at entry, clock64 at
- * entry / after the walk / after the sort / at exit, globaltimer at exit, loop trips of the warp, its largest hit count). */
+/* Same for the octree walk (k_intersect_warp, 32 warps = 32 rays per block): [block][warp][8] (globaltimer at entry, clock64 at
+ * entry / after the walk / after ranking + write-out / at exit, globaltimer at exit, trips of the walk, the ray's hit count). */
 int pslam_debug_intersect_trace(long long *dev_buf);
 
 /* ------------------------------------------------------------------------
@@ -218,6 +219,10 @@ int pslam_decoder_bwd(int p, const pslam_decoder_t *dec, const float *feat,
 #define PSLAM_F_FORWARD_ONLY 16
 #define PSLAM_F_DEFER_LOSS 32   /* forward stops at this rank's raw loss sums (loss_raw); the
                                   caller exchanges them and calls pslam_loss_finalize */
+#define PSLAM_F_NODE_CACHE_VALID 64   /* node_cache already holds the child records of the bound map (built by an earlier step
+                                         on the same centres / structure, or by pslam_build_node_cache): the step does not
+                                         rebuild it.  The octree only changes when a keyframe is inserted
+                                         (src/mapping.py:258-295), the BA loop renders the same map ~10-50 times in between. */
 
 /* device-side counters written by the pipeline (int32 each) */
 enum {
@@ -291,9 +296,9 @@ typedef struct {
     float *g_emb;                          /* [E,16] += */
     pslam_decoder_grad_t g_dec;            /* += */
     float *g_rays_o, *g_rays_d;            /* [R,3] by ray id, overwritten */
-    /* optional traversal cache: [N,8] x 16 B child records (child row id + child centre), rebuilt by every
-     * pslam_render_sample from `structure` / `centres`; halves the dependent-load chain of the octree walk.
-     * NULL or node_cache_bytes < 128*N: the walk reads the two arrays directly. */
+    /* optional traversal cache: [N,8] x 16 B child records (child row id + child centre), built by pslam_render_sample /
+     * pslam_render_step from `structure` / `centres` unless PSLAM_F_NODE_CACHE_VALID is set; halves the dependent-load
+     * chain of the octree walk.  NULL or node_cache_bytes < 128*N: the walk reads the two arrays directly. */
     void *node_cache;
     int64_t node_cache_bytes;
 } pslam_render_t;
@@ -305,6 +310,9 @@ int pslam_render_offsetof_loss(void);
 /* Elements the caller must provide for scratch_i / scratch_f for a batch of R rays. */
 int64_t pslam_render_scratch_i_count(int R);
 int64_t pslam_render_scratch_f_count(int R);
+
+/* The traversal cache alone: node_cache [N,8] x 16 B from centres [N,3] / structure [N,9] (once per map generation). */
+int pslam_build_node_cache(int N, const float *centres, const int *structure, void *node_cache, pslam_stream_t stream);
 
 /* Stage 1: intersection, sort/trim, compaction, sampling (kernels 1-2 + a4-a6).
  * Fills hit_*, samp_* and counters.  No host sync. */

@@ -50,7 +50,7 @@ class RenderT(C.Structure):
 
 
 # flags / counter slots / loss slots (include/proud_slam_b200.h)
-F_TRACKING, F_GRAD_EMB, F_GRAD_DEC, F_GRAD_RAYS, F_FORWARD_ONLY, F_DEFER_LOSS = 1, 2, 4, 8, 16, 32
+F_TRACKING, F_GRAD_EMB, F_GRAD_DEC, F_GRAD_RAYS, F_FORWARD_ONLY, F_DEFER_LOSS, F_NODE_CACHE_VALID = 1, 2, 4, 8, 16, 32, 64
 C_RH, C_P, C_NSAMP, C_S, C_OVERFLOW, C_STICKY, C_STEPS, C_COUNT = 0, 1, 2, 3, 4, 7, 8, 16
 L_TOTAL, L_COLOR, L_DEPTH, L_FS, L_SDF, L_COUNT = 0, 1, 2, 3, 4, 16
 
@@ -89,6 +89,7 @@ _PROTOTYPES = {
     "pslam_render_offsetof_loss": (C.c_int, []),
     "pslam_render_scratch_i_count": (C.c_int64, [_I]),
     "pslam_render_scratch_f_count": (C.c_int64, [_I]),
+    "pslam_build_node_cache": (C.c_int, [_I, _P, _P, _P, _S]),
     "pslam_render_sample": (C.c_int, [C.POINTER(RenderT), _S]),
     "pslam_render_forward": (C.c_int, [C.POINTER(RenderT), _S]),
     "pslam_render_backward": (C.c_int, [C.POINTER(RenderT), _S]),

@@ -126,6 +126,12 @@ extern "C" int64_t pslam_render_scratch_i_count(int R)
 }
 extern "C" int64_t pslam_render_scratch_f_count(int R) { return 8 * (int64_t)ceil_div(R, 8) + 64; }
 
+extern "C" int pslam_build_node_cache(int N, const float *centres, const int *structure, void *node_cache, pslam_stream_t stream)
+{
+    PSLAM_CHECK_ARG(N > 0 && centres && structure && node_cache && ((uintptr_t)node_cache % 16 == 0), PSLAM_E_ARG, "build_node_cache: bad argument");
+    return launch_build_node_cache(N, centres, structure, node_cache, (cudaStream_t)stream);
+}
+
 extern "C" int pslam_render_sample(const pslam_render_t *p, pslam_stream_t stream)
 {
     if (int rc = check_render(p)) return rc;

@@ -17,6 +17,7 @@
 // octree is read once through the read-only path and stays L1/L2 resident.
 #include "common.cuh"
 #include "kernels.h"
+#include <stdlib.h>
 
 namespace pslam {
 
@@ -121,66 +122,31 @@ k_svo_intersect_ref(int b, int n, int m, float half_voxel, int n_max, const floa
 }
 
 // ---- fused layout: slot-major [n_max, R], sorted by entry depth, trimmed at max_distance ------
-// Does the work of voxel_helpers.py:571-588 (fill/sort/gather/trim) per ray in
-// the same kernel: a stable insertion sort over the (mean ~3.6) hits.
-__global__ void __launch_bounds__(kIntersectThreads)
-k_intersect_fused(int R, float half_voxel, int n_max, float max_distance, const float *__restrict__ ray_start,
-                  const float *__restrict__ ray_dir, const float *__restrict__ points,
-                  const int *__restrict__ children, int *__restrict__ hit_idx, float *__restrict__ hit_min,
-                  float *__restrict__ hit_max, int *__restrict__ hit_count, int *__restrict__ block_hits,
-                  int *__restrict__ counters)
-{
-    extern __shared__ int s_stack[];
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    int count = 0;
-    bool overflow = false;
-    if (r < R) {
-        const Ray ray = load_ray(ray_start, ray_dir, r);
-        int cnt = dfs(ray, points, children, half_voxel, n_max, s_stack, [&](int c, int k, float lo, float hi) {
-            const int64_t at = (int64_t)c * R + r;
-            hit_idx[at] = k; hit_min[at] = lo; hit_max[at] = hi;
-        });
-        if (cnt < 0) { overflow = true; cnt = -1 - cnt; }
-        // stable insertion sort by entry depth: ties keep DFS order (SURVEY A-Q3)
-        for (int i = 1; i < cnt; ++i) {
-            const int64_t ai = (int64_t)i * R + r;
-            const float kmin = hit_min[ai], kmax = hit_max[ai];
-            const int kidx = hit_idx[ai];
-            int j = i - 1;
-            while (j >= 0 && hit_min[(int64_t)j * R + r] > kmin) {
-                const int64_t from = (int64_t)j * R + r, to = from + R;
-                hit_min[to] = hit_min[from]; hit_max[to] = hit_max[from]; hit_idx[to] = hit_idx[from];
-                --j;
-            }
-            const int64_t to = (int64_t)(j + 1) * R + r;
-            hit_min[to] = kmin; hit_max[to] = kmax; hit_idx[to] = kidx;
-        }
-        // drop hits that start beyond max_distance (voxel_helpers.py:578)
-        while (count < cnt && !(hit_min[(int64_t)count * R + r] > max_distance)) ++count;
-        hit_count[r] = count;
-    }
-    const int nhit = __syncthreads_count(count > 0);
-    const int wmax = warp_max_i(count);
-    if ((threadIdx.x & 31) == 0 && wmax > 0) atomicMax(counters + PSLAM_C_P, wmax);
-    if (overflow) atomicOr(counters + PSLAM_C_OVERFLOW, 2);
-    if (threadIdx.x == 0) block_hits[blockIdx.x] = nhit;
-}
-
-// ---- fused layout, 8 lanes per ray -----------------------------------------------------------
-// The per-thread DFS above is a chain of ~70-200 dependent loads per ray (and a warp waits for its
-// slowest ray).  Here a ray owns 8 lanes: when an internal node is expanded, lane c loads child c, its
-// centre, and runs the slab test, so the dependent chain is one step per HIT INTERNAL node instead of
-// one per tested node, and leaves cost no extra round trip (their interval is computed when the
-// parent is expanded and waits on the stack).  Hit children are pushed in ascending child order, so
-// the pop order -- and with it the emission order and the n_max cut -- is the reference's
-// (children 0..7 pushed, 7 popped first, intersect_gpu.cu:259-265; misses contribute nothing there
-// either).  The child's box half-size is half_voxel * side with side = parent side / 2, the same
-// integer the reference reads from children[c*9+8].  Hits are collected and sorted in shared memory.
-constexpr int kWideRays = 64;                    // rays per block
-constexpr int kWideThreads = kWideRays * 8;
-constexpr int kWideStack = 64;                   // 7 pending siblings per level + 8: enough for 9 levels (grid 512)
-constexpr int kWideHits = 50;                    // == n_max of the reference (voxel_helpers.py:561)
-constexpr size_t kWideSmem = sizeof(int) * 3 * (kWideStack + kWideHits) * kWideRays;
+// Does the work of voxel_helpers.py:571-588 (fill/sort/gather/trim) per ray in the same kernel.
+//
+// ONE WARP PER RAY.  The reference's walk is a DFS: one node per step, a chain of dependent loads as long as the number of
+// nodes a ray tests.  What the rest of the pipeline consumes, though, is the SET of hit leaves -- sorted by entry depth, ties
+// in DFS order, cut to the first n_max in DFS order -- and the DFS order of two leaves is a static property of their paths:
+// children are pushed 0..7 and popped 7 first (intersect_gpu.cu:259-265), all leaves sit at the same depth, so leaf a is
+// emitted before leaf b iff its path of child indices is lexicographically LARGER.  Every hit carries that path as a key
+// (3 bits per level) and the walk is free to run in any order:
+//   * the four 8-lane groups of the warp expand up to four pending internal nodes per trip, lane c of a group loading child
+//     c's record (id + centre, one 16-byte load: k_build_child_records) and running the slab test -- a ray needs about one
+//     trip per octree level instead of one per hit internal node (8-10 instead of ~25 dependent round trips);
+//   * hit leaves go straight to the ray's hit list (ballot-compacted), hit internal nodes back on the pending stack;
+//   * more than n_max hit leaves: the list keeps the n_max largest keys (= the first n_max of the DFS), replacing its
+//     smallest key -- rare, taken one candidate at a time;
+//   * at the end every lane ranks its hits by (entry depth, then key descending) = the reference's stable sort of the DFS
+//     emission order, and stores them at their rank (hits entering beyond max_distance are the tail of that order and are
+//     dropped, voxel_helpers.py:578).
+// The slab arithmetic, the child's half size (half_voxel * side, side halving per level exactly like children[c*9+8]) and the
+// "depths.x > -1" acceptance are the reference's, so depths stay bit-identical.
+constexpr int kWarpRays = 8;                     // rays (= warps) per block
+constexpr int kRayThreads = kWarpRays * 32;
+constexpr int kCompactRays = 32;                 // rays per block of the compaction that follows (block_hits granularity)
+constexpr int kRayStack = 64;                    // pending internal nodes per ray
+constexpr int kRayHits = 50;                     // == n_max of the reference (voxel_helpers.py:561)
+constexpr size_t kRaySmem = (size_t)kWarpRays * (kRayStack * (4 + 8) + kRayHits * (4 + 4 + 4 + 8));   // x rays per warp
 
 // First warp of a step: folds the previous step's overflow flags (and "no ray hit") into the sticky slot, counts the step and
 // clears the per-step counters (include/proud_slam_b200.h: PSLAM_C_STICKY).
@@ -196,17 +162,23 @@ __device__ __forceinline__ void step_begin_counters(int *__restrict__ counters, 
         counters[t] = v;
     }
 }
-__global__ void k_step_begin(int *__restrict__ counters) { step_begin_counters(counters, threadIdx.x); }
+__global__ void k_step_begin(int *__restrict__ counters, int *__restrict__ block_hits, int nbh)
+{
+    pdl_enter();
+    if (threadIdx.x < 32) step_begin_counters(counters, threadIdx.x);
+    for (int i = threadIdx.x; i < nbh; i += blockDim.x) block_hits[i] = 0;   // hit-ray counts per kCompactRays rays (k_intersect_warp adds)
+}
 
 // Child records for the walk: rec[node][c] = (row id of child c or -1, centre of that child).  Expanding a node then
-// costs ONE dependent 16-byte load per lane instead of two (child id, then its centre): the walk is a chain of ~25
-// dependent expansions per ray and nothing but that chain's latency.
+// costs ONE dependent 16-byte load per lane instead of two (child id, then its centre); a node's eight records are one
+// 128-byte line.  Built once per map generation (PSLAM_F_NODE_CACHE_VALID tells the step that the table is current).
 __global__ void k_build_child_records(int N, const float *__restrict__ points, const int *__restrict__ children, int4 *__restrict__ rec,
-                                      int *__restrict__ counters)
+                                      int *__restrict__ counters, int *__restrict__ block_hits, int nbh)
 {
     pdl_enter();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < 32) step_begin_counters(counters, t);   // first kernel of a step: the step's counters (instead of a memset node in front of the chain)
+    if (t < 32 && counters) step_begin_counters(counters, t);   // first kernel of a step: the step's counters (instead of a memset node in front of the chain)
+    if (blockIdx.x == 0) for (int i = threadIdx.x; i < nbh; i += blockDim.x) block_hits[i] = 0;
     if (t >= N * 8) return;
     const int node = t >> 3, c = t & 7;
     const int cid = __ldg(children + (int64_t)node * 9 + c);
@@ -220,11 +192,11 @@ __global__ void k_build_child_records(int N, const float *__restrict__ points, c
 }
 
 // optional per-warp timeline of the walk (pslam_debug_intersect_trace): [block][warp][8] = globaltimer at entry, clock64 at entry /
-// after the walk / after the sort / at exit, globaltimer at exit, expansions (loop trips of the warp), largest hit count
+// after the walk / after the ranking + write-out / at exit, globaltimer at exit, trips of the walk, hit count
 __device__ long long *g_intersect_trace = nullptr;
 __device__ __forceinline__ void intersect_stamp(long long *tr, int slot, long long v)
 {
-    if (tr && (threadIdx.x & 31) == 0) tr[((size_t)blockIdx.x * (kWideThreads / 32) + (threadIdx.x >> 5)) * 8 + slot] = v;
+    if (tr && (threadIdx.x & 31) == 0) tr[((size_t)blockIdx.x * kWarpRays + (threadIdx.x >> 5)) * 8 + slot] = v;   // [block][warp][8]
 }
 __device__ __forceinline__ long long intersect_globaltimer()
 {
@@ -233,118 +205,196 @@ __device__ __forceinline__ long long intersect_globaltimer()
     return t;
 }
 
-template <bool CACHED>
-__global__ void __launch_bounds__(kWideThreads)
-k_intersect_wide(int R, float half_voxel, int n_max, float max_distance, const float *__restrict__ ray_start,
+// intersect_gpu.cu:75-140 without branches: the same operations in the same order; once a test has failed the later
+// updates of lo / hi are dead, so carrying them on changes nothing that is read.
+__device__ __forceinline__ bool slab_nb(const Ray &ray, float cx, float cy, float cz, float half, float &t_lo, float &t_hi)
+{
+    float lo = 0.0f, hi = 100000.0f;
+    bool ok = true;
+    const float c[3] = {cx, cy, cz};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float d_lo = __fmul_rn(__fsub_rn(__fsub_rn(c[a], half), ray.o[a]), ray.inv[a]);
+        float d_hi = __fmul_rn(__fsub_rn(__fadd_rn(c[a], half), ray.o[a]), ray.inv[a]);
+        const bool sw = d_hi < d_lo;
+        const float t0 = sw ? d_hi : d_lo, t1 = sw ? d_lo : d_hi;
+        ok = ok && !(t1 < lo) && !(t0 > hi);
+        lo = (t0 > lo) ? t0 : lo;
+        hi = (t1 < hi) ? t1 : hi;
+        ok = ok && !(lo > hi);
+    }
+    t_lo = lo; t_hi = hi;
+    return ok && lo > -1.0f;  // "depths.x > -1.0f", intersect_gpu.cu:247
+}
+
+// RPW rays per warp: a ray owns 32 / RPW lanes = 4 / RPW nodes per trip (RPW = 1: shortest dependent chain, for small batches;
+// RPW = 2 / 4: better lane utilisation near the root, where a ray has one or two pending nodes, for large ones).
+template <bool CACHED, int RPW>
+__global__ void __launch_bounds__(kRayThreads, 6)
+k_intersect_warp(int R, float half_voxel, int n_max, float max_distance, const float *__restrict__ ray_start,
                  const float *__restrict__ ray_dir, const float *__restrict__ points, const int *__restrict__ children,
                  const int4 *__restrict__ rec, int *__restrict__ hit_idx, float *__restrict__ hit_min, float *__restrict__ hit_max,
                  int *__restrict__ hit_count, int *__restrict__ block_hits, int *__restrict__ counters)
 {
     pdl_enter();
+    constexpr int SEG = 32 / RPW;                         // lanes of a ray
+    constexpr int NPT = SEG / 8;                          // nodes a ray expands per trip
+    constexpr int RAYS = kWarpRays * RPW;                 // rays of a block
     long long *const tr = g_intersect_trace;
     if (tr) { intersect_stamp(tr, 0, intersect_globaltimer()); intersect_stamp(tr, 1, clock64()); }
-    int trips = 0;
-    extern __shared__ int s_wide[];
-    int *s_id = s_wide;                                                    // [kWideStack][kWideRays]: id | log2(side) << 26
-    float *s_lo = reinterpret_cast<float *>(s_wide + kWideStack * kWideRays);
-    float *s_hi = s_lo + kWideStack * kWideRays;
-    int *h_id = s_wide + 3 * kWideStack * kWideRays;                       // [kWideHits][kWideRays]
-    float *h_lo = reinterpret_cast<float *>(h_id + kWideHits * kWideRays);
-    float *h_hi = h_lo + kWideHits * kWideRays;
+    extern __shared__ __align__(16) unsigned char s_ray[];
+    __shared__ int s_blockmax;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int seg = lane / SEG, sl = lane % SEG;          // ray of the warp, lane of the ray
+    const int grp = sl >> 3, sub = sl & 7;
+    const int slot = warp * RPW + seg;                    // ray of the block
+    unsigned long long *st_key = reinterpret_cast<unsigned long long *>(s_ray) + slot * kRayStack;          // [ray][kRayStack]
+    unsigned long long *h_key = reinterpret_cast<unsigned long long *>(s_ray) + RAYS * kRayStack + slot * kRayHits;
+    int *ibase = reinterpret_cast<int *>(s_ray + (size_t)RAYS * (kRayStack + kRayHits) * 8);
+    int *st_id = ibase + slot * kRayStack;                // id | log2(side) << 26
+    int *h_id = ibase + RAYS * kRayStack + slot * kRayHits;
+    float *h_lo = reinterpret_cast<float *>(ibase + RAYS * kRayStack + RAYS * kRayHits) + slot * kRayHits;
+    float *h_hi = h_lo + RAYS * kRayHits;
+    if (threadIdx.x == 0) s_blockmax = 0;
 
-    const int lane = threadIdx.x & 31, sub = threadIdx.x & 7, rl = threadIdx.x >> 3;
-    const int r = blockIdx.x * kWideRays + rl;
+    const int r = blockIdx.x * RAYS + slot;
     const bool valid = r < R;
-    Ray ray{};
-    if (valid) ray = load_ray(ray_start, ray_dir, r);
-    if (n_max > kWideHits) n_max = kWideHits;
-    int top = -1, cnt = 0, cur = -1, cur_side = 0;
+    if (n_max > kRayHits) n_max = kRayHits;
+    int top = 0, cnt = 0, trips = 0;
     bool overflow = false;
-    if (valid) {   // the root (row 0, intersect_gpu.cu:232)
+    Ray ray{};
+    if (valid) {
+        ray = load_ray(ray_start, ray_dir, r);
+        // the root (row 0, intersect_gpu.cu:232)
         const int side = __ldg(children + 8);
         float lo, hi;
         if (slab(ray, __ldg(points), __ldg(points + 1), __ldg(points + 2), __fmul_rn(half_voxel, (float)side), lo, hi)) {
-            if (side == 1) { h_id[rl] = 0; h_lo[rl] = lo; h_hi[rl] = hi; cnt = 1; }
-            else { cur = 0; cur_side = side; }
+            if (side == 1) {
+                if (sl == 0) { h_id[0] = 0; h_lo[0] = lo; h_hi[0] = hi; h_key[0] = 0ull; }
+                cnt = 1;
+            } else {
+                if (sl == 0) { st_id[0] = (31 - __clz(side)) << 26; st_key[0] = 0ull; }
+                top = 1;
+            }
         }
     }
-    while (__any_sync(0xffffffffu, cur >= 0)) {
+    __syncwarp();
+    const unsigned seg_mask = (SEG == 32) ? 0xffffffffu : (((1u << SEG) - 1u) << (seg * SEG));
+    const unsigned lt = ((1u << lane) - 1u) & seg_mask;    // earlier lanes of this ray
+    while (__any_sync(0xffffffffu, top > 0)) {
         ++trips;
+        const int take = min(top, NPT);
+        const bool have = grp < take;
+        int e = 0;
+        unsigned long long key = 0ull;
+        if (have) { e = st_id[top - 1 - grp]; key = st_key[top - 1 - grp]; }
+        top -= take;
+        __syncwarp();                                        // the slots just read may be overwritten below
+        const int level = e >> 26, cur = e & 0x3FFFFFF;
+        const int cside = (1 << level) >> 1;
         bool hit = false;
         int cid = -1;
         float lo = 0.f, hi = 0.f;
-        const int cside = cur_side >> 1;
-        if (cur >= 0) {
+        if (have) {
             if (CACHED) {
                 const int4 r4 = __ldg(rec + (int64_t)cur * 8 + sub);
                 cid = r4.x;
-                if (cid > -1)
-                    hit = slab(ray, __int_as_float(r4.y), __int_as_float(r4.z), __int_as_float(r4.w), __fmul_rn(half_voxel, (float)cside), lo, hi);
+                hit = slab_nb(ray, __int_as_float(r4.y), __int_as_float(r4.z), __int_as_float(r4.w), __fmul_rn(half_voxel, (float)cside), lo, hi) && cid > -1;
             } else {
                 cid = __ldg(children + (int64_t)cur * 9 + sub);
                 if (cid > -1)
-                    hit = slab(ray, __ldg(points + (int64_t)cid * 3), __ldg(points + (int64_t)cid * 3 + 1), __ldg(points + (int64_t)cid * 3 + 2),
-                               __fmul_rn(half_voxel, (float)cside), lo, hi);
+                    hit = slab_nb(ray, __ldg(points + (int64_t)cid * 3), __ldg(points + (int64_t)cid * 3 + 1), __ldg(points + (int64_t)cid * 3 + 2),
+                                  __fmul_rn(half_voxel, (float)cside), lo, hi);
             }
         }
-        const unsigned mine = (__ballot_sync(0xffffffffu, hit) >> (lane & ~7)) & 0xFFu;
-        if (hit) {
-            const int pos = top + 1 + __popc(mine & ((1u << sub) - 1u));
-            if (pos < kWideStack) {
-                s_id[pos * kWideRays + rl] = cid | ((31 - __clz(cside)) << 26);
-                s_lo[pos * kWideRays + rl] = lo; s_hi[pos * kWideRays + rl] = hi;
+        const bool leaf = hit && cside == 1, inner = hit && cside > 1;
+        const unsigned long long ckey = (key << 3) | (unsigned long long)sub;
+        const unsigned m_in = __ballot_sync(0xffffffffu, inner) & seg_mask, m_leaf = __ballot_sync(0xffffffffu, leaf) & seg_mask;
+        if (inner) {
+            const int pos = top + __popc(m_in & lt);
+            if (pos < kRayStack) {
+                st_id[pos] = cid | ((level - 1) << 26);
+                st_key[pos] = ckey;
+                if (CACHED) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + (int64_t)cid * 8));   // its records: one 128-byte line
             } else overflow = true;
         }
-        top = min(top + __popc(mine), kWideStack - 1);
-        __syncwarp();
-        // pop: leaves are emitted straight away, the first internal node becomes the next expansion
-        cur = -1;
-        while (top >= 0 && cnt < n_max) {
-            const int e = s_id[top * kWideRays + rl];
-            const int side = 1 << (e >> 26), id = e & 0x3FFFFFF;
-            if (side == 1) {
-                if (sub == 0) { h_id[cnt * kWideRays + rl] = id; h_lo[cnt * kWideRays + rl] = s_lo[top * kWideRays + rl]; h_hi[cnt * kWideRays + rl] = s_hi[top * kWideRays + rl]; }
-                ++cnt; --top;
-            } else { cur = id; cur_side = side; --top; break; }
+        top = min(top + __popc(m_in), kRayStack);
+        const int n_new = __popc(m_leaf);
+        const bool fits = cnt + n_new <= n_max;
+        if (fits) {
+            if (leaf) {
+                const int pos = cnt + __popc(m_leaf & lt);
+                h_id[pos] = cid; h_lo[pos] = lo; h_hi[pos] = hi; h_key[pos] = ckey;
+            }
+            cnt += n_new;
         }
-        if (cnt >= n_max) { cur = -1; top = -1; }   // intersect_gpu.cu:233: the walk stops at n_max hits
+        // more hit leaves than slots: keep the n_max largest keys = the first n_max leaves of the reference's DFS (rare; one
+        // candidate per ray and round, every lane of the warp takes part in the shuffles)
+        unsigned rest = fits ? 0u : m_leaf;
+        while (__any_sync(0xffffffffu, rest != 0u)) {
+            const bool act = rest != 0u;
+            const int src = act ? __ffs(rest) - 1 : lane;
+            rest &= rest - 1;
+            const int c_id = __shfl_sync(0xffffffffu, cid, src);
+            const float c_lo = __shfl_sync(0xffffffffu, lo, src), c_hi = __shfl_sync(0xffffffffu, hi, src);
+            const unsigned long long c_key = __shfl_sync(0xffffffffu, ckey, src);
+            unsigned long long mk = ~0ull;
+            int mi = -1;
+            if (act && cnt >= n_max) {
+                for (int i = sl; i < n_max; i += SEG) {
+                    const unsigned long long k2 = h_key[i];
+                    if (k2 < mk) { mk = k2; mi = i; }
+                }
+            }
+#pragma unroll
+            for (int o = SEG / 2; o > 0; o >>= 1) {
+                const unsigned long long ok = __shfl_xor_sync(0xffffffffu, mk, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+                if (ok < mk) { mk = ok; mi = oi; }               // keys of distinct leaves are distinct
+            }
+            if (act) {
+                if (cnt < n_max) {
+                    if (sl == 0) { h_id[cnt] = c_id; h_lo[cnt] = c_lo; h_hi[cnt] = c_hi; h_key[cnt] = c_key; }
+                    ++cnt;
+                } else if (c_key > mk && sl == 0) { h_id[mi] = c_id; h_lo[mi] = c_lo; h_hi[mi] = c_hi; h_key[mi] = c_key; }
+            }
+            __syncwarp();
+        }
         __syncwarp();
     }
     if (tr) intersect_stamp(tr, 2, clock64());
+    // rank = position in the stable sort by entry depth of the DFS emission order (SURVEY A-Q3), then the max_distance trim
     int count = 0;
-    if (valid && sub == 0) {
-        // stable insertion sort by entry depth: ties keep DFS order (SURVEY A-Q3)
-        for (int i = 1; i < cnt; ++i) {
-            const float kmin = h_lo[i * kWideRays + rl], kmax = h_hi[i * kWideRays + rl];
-            const int kidx = h_id[i * kWideRays + rl];
-            int j = i - 1;
-            while (j >= 0 && h_lo[j * kWideRays + rl] > kmin) {
-                h_lo[(j + 1) * kWideRays + rl] = h_lo[j * kWideRays + rl]; h_hi[(j + 1) * kWideRays + rl] = h_hi[j * kWideRays + rl];
-                h_id[(j + 1) * kWideRays + rl] = h_id[j * kWideRays + rl];
-                --j;
-            }
-            h_lo[(j + 1) * kWideRays + rl] = kmin; h_hi[(j + 1) * kWideRays + rl] = kmax; h_id[(j + 1) * kWideRays + rl] = kidx;
-        }
-    }
-    __syncwarp();   // outside any divergent region: a warp may hold valid and out-of-range rays
-    if (tr) intersect_stamp(tr, 3, clock64());
     if (valid) {
-        // drop hits that start beyond max_distance (voxel_helpers.py:578)
-        while (count < cnt && !(h_lo[count * kWideRays + rl] > max_distance)) ++count;
-        for (int i = sub; i < count; i += 8) {
-            const int64_t at = (int64_t)i * R + r;
-            hit_idx[at] = h_id[i * kWideRays + rl]; hit_min[at] = h_lo[i * kWideRays + rl]; hit_max[at] = h_hi[i * kWideRays + rl];
+        for (int i = sl; i < cnt; i += SEG) {
+            const float li = h_lo[i];
+            const unsigned long long ki = h_key[i];
+            int rank = 0;
+            for (int j = 0; j < cnt; ++j) {
+                const float lj = h_lo[j];
+                rank += (lj < li || (lj == li && h_key[j] > ki)) ? 1 : 0;
+            }
+            if (!(li > max_distance)) {       // (the dropped hits are the tail of the order: voxel_helpers.py:578)
+                const int64_t at = (int64_t)rank * R + r;
+                hit_idx[at] = h_id[i]; hit_min[at] = li; hit_max[at] = h_hi[i];
+                ++count;
+            }
         }
-        if (sub == 0) hit_count[r] = count;
     }
-    const int nhit = __syncthreads_count(sub == 0 && count > 0);
-    const int wmax = warp_max_i(count);
-    if (lane == 0 && wmax > 0) atomicMax(counters + PSLAM_C_P, wmax);
+#pragma unroll
+    for (int o = SEG / 2; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
+    if (valid && sl == 0) hit_count[r] = count;
+    if (tr) intersect_stamp(tr, 3, clock64());
+    if (sl == 0 && count > 0) atomicMax(&s_blockmax, count);
     if (overflow) atomicOr(counters + PSLAM_C_OVERFLOW, 2);
-    if (threadIdx.x == 0) block_hits[blockIdx.x] = nhit;
+    const int nhit = __syncthreads_count(sl == 0 && count > 0);
+    if (threadIdx.x == 0 && nhit > 0) {
+        atomicAdd(block_hits + (blockIdx.x * RAYS) / kCompactRays, nhit);   // (RAYS divides kCompactRays)
+        atomicMax(counters + PSLAM_C_P, s_blockmax);
+    }
     if (tr) {
         intersect_stamp(tr, 4, clock64()); intersect_stamp(tr, 5, intersect_globaltimer());
-        intersect_stamp(tr, 6, trips); intersect_stamp(tr, 7, wmax);
+        intersect_stamp(tr, 6, trips); intersect_stamp(tr, 7, warp_max_i(count));
     }
 }
 
@@ -415,7 +465,7 @@ k_compact_rays(int R, const int *__restrict__ hit_count, const int *__restrict__
         if (threadIdx.x == 0) s_base = acc;
     }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < zero_n; i += gridDim.x * blockDim.x) zero[i] = 0;   // the sampling kernel's look-back state
-    __shared__ int s_warp[kIntersectThreads / 32];   // launched with kWideRays threads per block (<= kIntersectThreads)
+    __shared__ int s_warp[kIntersectThreads / 32];   // launched with kCompactRays threads per block (<= kIntersectThreads)
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     const bool hit = (r < R) && hit_count[r] > 0;
     const unsigned ballot = __ballot_sync(0xffffffffu, hit);
@@ -628,45 +678,64 @@ int scan_partials(int *partials, int nb, int *total_out, cudaStream_t st)
 
 int launch_intersect_fused(const pslam_render_t *p, cudaStream_t st)
 {
-    const int nb = ceil_div(p->R, kWideRays);
+    const int nb = ceil_div(p->R, kCompactRays);
     int *block_hits = p->scratch_i;  // [nb]
-    // the record table costs a pass over the octree per call: worth it while the walk (about 64 node tests per ray) is the larger job
-    const bool cached = p->node_cache && p->node_cache_bytes >= (int64_t)128 * p->N && ((uintptr_t)p->node_cache % 16 == 0) &&
-                        (int64_t)p->N * 8 <= (int64_t)p->R * 256;
-    if (!cached) {   // (building the record table reads both arrays and leaves the table in L2: no separate prefetch then)
-        k_step_begin<<<1, 32, 0, st>>>(p->counters);   // (cached: k_build_child_records does this)
-        PSLAM_CHECK_LAUNCH("step_begin");
-        const size_t na = (size_t)p->N * 12, nbytes = (size_t)p->N * 36;
-        k_prefetch_l2<<<(int)ceil_div64((int64_t)(nbytes / 128 + 1), 256), 256, 0, st>>>(reinterpret_cast<const char *>(p->centres), na,
-                                                                                  reinterpret_cast<const char *>(p->structure), nbytes);
-        PSLAM_CHECK_LAUNCH("prefetch_l2");
+    // the record table costs a pass over the octree per map generation: worth it while the walk is the larger job
+    const bool cached = p->node_cache && p->node_cache_bytes >= (int64_t)128 * p->N && ((uintptr_t)p->node_cache % 16 == 0);
+    static int forced = -1;                                // PSLAM_INTERSECT_RPW=1|2|4: measurement override
+    if (forced < 0) {
+        const char *e = getenv("PSLAM_INTERSECT_RPW");
+        const int v = e ? atoi(e) : 0;
+        forced = (v == 1 || v == 2 || v == 4) ? v : 0;
     }
-    static PerDevice once = {};
-    bool &configured = once.done[current_device()];
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_intersect_wide<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWideSmem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_intersect_wide<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWideSmem);
-        if (e != cudaSuccess) { set_error("intersect: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-        configured = true;
-    }
-    if (cached) {
-        int4 *rec = static_cast<int4 *>(p->node_cache);
-        launch_chain(k_build_child_records, dim3((int)ceil_div64((int64_t)p->N * 8, 256)), dim3(256), 0, st, p->N, p->centres, p->structure, rec, p->counters);
+    // a ray per warp while every warp of the launch can be resident at once (the dependent chain is all there is: measured at
+    // 8192 rays 26.3 us against 28.5 / 31.7 for two / four rays per warp), more rays per warp beyond that (fewer instructions:
+    // near the root a ray has one or two pending nodes and most lanes of a whole warp would idle)
+    const int rpw = forced ? forced : (p->R <= 64 * num_sms() ? 1 : (p->R <= 256 * num_sms() ? 2 : 4));
+    int4 *rec = static_cast<int4 *>(p->node_cache);
+    if (cached && !(p->flags & PSLAM_F_NODE_CACHE_VALID)) {
+        // (building the record table reads both arrays and leaves the table in L2; it also opens the step: counters)
+        launch_chain(k_build_child_records, dim3((int)ceil_div64((int64_t)p->N * 8, 256)), dim3(256), 0, st, p->N, p->centres, p->structure, rec, p->counters, block_hits, nb);
         PSLAM_CHECK_LAUNCH("build_child_records");
-        launch_chain(k_intersect_wide<true>, dim3(nb), dim3(kWideThreads), kWideSmem, st, p->R, (float)(p->voxel_size * 0.5), p->n_max, p->max_distance, p->rays_o,
-                                                                   p->rays_d, p->centres, p->structure, rec, p->hit_idx, p->hit_min,
-                                                                   p->hit_max, p->hit_count, block_hits, p->counters);
     } else {
-        launch_chain(k_intersect_wide<false>, dim3(nb), dim3(kWideThreads), kWideSmem, st, p->R, (float)(p->voxel_size * 0.5), p->n_max, p->max_distance, p->rays_o,
-                                                                    p->rays_d, p->centres, p->structure, nullptr, p->hit_idx, p->hit_min,
-                                                                    p->hit_max, p->hit_count, block_hits, p->counters);
+        launch_chain(k_step_begin, dim3(1), dim3(256), 0, st, p->counters, block_hits, nb);
+        PSLAM_CHECK_LAUNCH("step_begin");
     }
-    PSLAM_CHECK_LAUNCH("intersect_wide");
+    const float half_voxel = (float)(p->voxel_size * 0.5);
+#define PSLAM_LAUNCH_INTERSECT(C, W)                                                                                                   \
+    do {                                                                                                                               \
+        static PerDevice once = {};                                                                                                    \
+        bool &configured = once.done[current_device()];                                                                                \
+        if (!configured) {                                                                                                             \
+            cudaError_t e = cudaFuncSetAttribute(k_intersect_warp<C, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRaySmem * W)); \
+            if (e != cudaSuccess) { set_error("intersect: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }          \
+            configured = true;                                                                                                         \
+        }                                                                                                                              \
+        launch_chain(k_intersect_warp<C, W>, dim3(ceil_div(p->R, kWarpRays * W)), dim3(kRayThreads), kRaySmem * W, st, p->R, half_voxel, p->n_max, \
+                     p->max_distance, p->rays_o, p->rays_d, p->centres, p->structure, (const int4 *)(C ? rec : nullptr), p->hit_idx, p->hit_min,       \
+                     p->hit_max, p->hit_count, block_hits, p->counters);                                                              \
+    } while (0)
+    if (cached) {
+        if (rpw == 1) PSLAM_LAUNCH_INTERSECT(true, 1); else if (rpw == 2) PSLAM_LAUNCH_INTERSECT(true, 2); else PSLAM_LAUNCH_INTERSECT(true, 4);
+    } else {
+        if (rpw == 1) PSLAM_LAUNCH_INTERSECT(false, 1); else if (rpw == 2) PSLAM_LAUNCH_INTERSECT(false, 2); else PSLAM_LAUNCH_INTERSECT(false, 4);
+    }
+#undef PSLAM_LAUNCH_INTERSECT
+    PSLAM_CHECK_LAUNCH("intersect_warp");
     const bool own_scan = nb <= 1024;                   // beyond that the O(nb^2) sums lose to the scan kernel
     if (!own_scan) { if (int rc = scan_partials(block_hits, nb, p->counters + PSLAM_C_RH, st)) return rc; }
-    launch_chain(k_compact_rays, dim3(nb), dim3(kWideRays), 0, st, p->R, p->hit_count, block_hits, p->hit_ray, p->ray_rank,
-                 p->scratch_i + scratch_i_sample_off(p->R), 2 * scratch_i_sample_off(p->R), own_scan ? p->counters + PSLAM_C_RH : nullptr);
+    launch_chain(k_compact_rays, dim3(nb), dim3(kCompactRays), 0, st, p->R, p->hit_count, block_hits, p->hit_ray, p->ray_rank,
+                 p->scratch_i + scratch_i_sample_off(p->R), scratch_i_sample_len(p->R), own_scan ? p->counters + PSLAM_C_RH : nullptr);
     PSLAM_CHECK_LAUNCH("compact_rays");
+    return 0;
+}
+
+// The child-record table alone (a caller that manages map generations itself: pslam_build_node_cache).
+int launch_build_node_cache(int N, const float *centres, const int *structure, void *node_cache, cudaStream_t st)
+{
+    launch_chain(k_build_child_records, dim3((int)ceil_div64((int64_t)N * 8, 256)), dim3(256), 0, st, N, centres, structure,
+                 static_cast<int4 *>(node_cache), (int *)nullptr, (int *)nullptr, 0);
+    PSLAM_CHECK_LAUNCH("build_child_records");
     return 0;
 }
 }  // namespace pslam

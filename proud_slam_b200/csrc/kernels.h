@@ -6,13 +6,15 @@
 
 namespace pslam {
 
-// scratch_i layout: [intersect block hits: R/64 + 8][sample block counts / look-back state: 2 x (R/64 + 8)][composite partials: 8 x R/8 + 64]
-static inline int scratch_i_sample_off(int R) { return (R + 63) / 64 + 8; }
-static inline int scratch_i_composite_off(int R) { return 3 * ((R + 63) / 64 + 8); }
+// scratch_i layout: [intersect block hits: R/32 + 8][sample look-back state (64-bit per block of >= 8 rays): 2 x (R/8 + 8)][composite partials: 8 x R/8 + 64]
+static inline int scratch_i_sample_off(int R) { return (R + 31) / 32 + 8; }
+static inline int scratch_i_sample_len(int R) { return 2 * ((R + 7) / 8 + 8); }
+static inline int scratch_i_composite_off(int R) { return scratch_i_sample_off(R) + scratch_i_sample_len(R); }
 
 // intersect.cu
 int scan_partials(int *partials, int nb, int *total_out, cudaStream_t st);
 int launch_intersect_fused(const pslam_render_t *p, cudaStream_t st);
+int launch_build_node_cache(int N, const float *centres, const int *structure, void *node_cache, cudaStream_t st);
 // sample.cu
 int launch_sample_fused(const pslam_render_t *p, cudaStream_t st);
 // field.cu (trilinear lookup + decoder MLP)

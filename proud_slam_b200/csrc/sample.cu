@@ -19,6 +19,7 @@
 //                 or nowhere for the counting pass)
 #include "common.cuh"
 #include "kernels.h"
+#include <stdlib.h>
 
 namespace pslam {
 
@@ -26,7 +27,7 @@ constexpr int kSampleThreads = 64;    // fused path: one ray per thread, 2 warps
 constexpr int kGroups = 200;      // voxel_helpers.py:300
 constexpr int kChunkRays = 800;   // voxel_helpers.py:331 (4*G)
 
-// optional per-warp timeline (pslam_debug_sample_trace): [block][warp][8] = globaltimer at entry / exit, clock64 after each phase
+// optional per-warp timeline of k_sample_warp (pslam_debug_sample_trace), see WARP_TRACE below
 __device__ long long *g_sample_trace = nullptr;
 __device__ __forceinline__ long long globaltimer_ns()
 {
@@ -34,11 +35,6 @@ __device__ __forceinline__ long long globaltimer_ns()
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-#define SAMPLE_TRACE(slot, value)                                                                                  \
-    do {                                                                                                           \
-        if (g_sample_trace) { __syncwarp(); if ((threadIdx.x & 31) == 0) g_sample_trace[((blockIdx.x * (kSampleThreads / 32)) + (threadIdx.x >> 5)) * 8 + (slot)] = (value); } \
-    } while (0)
-
 // The sampling loop for ray j of a group with `num_rays` rays and P hit slots.
 template <class HitView, class Noise, class Sink>
 __device__ __forceinline__ int sample_ray(const HitView &hv, const Noise &noise, Sink &sink, int j, int num_rays, int P,
@@ -247,7 +243,6 @@ __device__ __forceinline__ int run_ray(const pslam_render_t &p, int q, int Rh, i
             s_cum[b * kSampleThreads] = c;
         }
     }
-    SAMPLE_TRACE(7, clock64());   // hit list staged
     const float prob0 = hv.prob(j, 0);
     if (p.noise) {
         TensorNoise nz{p.noise + (int64_t)q * p.noise_stride, p.noise_stride};
@@ -300,136 +295,324 @@ k_sample_fused(pslam_render_t p, int *__restrict__ block_counts)
     }
 }
 
-// One-pass form: the sampling loop runs ONCE per ray into a shared-memory buffer ([slot][thread]); the CSR offsets
-// come from a block scan plus a decoupled look-back over the per-block totals (state[b]: flag in the high word --
-// 1 = this block's total, 2 = inclusive prefix -- value in the low word; zeroed before the launch), then every thread
-// copies its samples out.  A ray with more emissions than buffer slots simply reruns its loop straight into global memory.
-constexpr int kSampleBuf = 96;
-constexpr int kBufPitch = kSampleThreads + 1;   // [slot][thread] sample buffer, padded so that a column read is conflict-free too
+// One-pass form, ONE WARP PER RAY.  The reference's loop (sample_gpu.cu:176-222) looks serial -- every step's sample depends on
+// the previous one through z_low -- but each step's cdf is a closed form of (step, noise), so the warp takes 32 steps at a time:
+//   * lane k computes cdf_k and F(k) = the first bin whose cumulative probability is not below it; the loop's bin pointer never
+//     moves back, so bin(k) is the running maximum of F (a warp prefix-max), and z_k follows from the bin's (cum, min, max);
+//   * the in-bin sample of step k is emission number k + bin(k) (k earlier in-bin samples + one closing sample per bin left);
+//     its z_low is z_{k-1} when step k-1 sat in the same bin (one shuffle), else the bin's entry depth;
+//   * the closing samples of the bins crossed between steps k-1 and k are emitted by lane k (numbers k + b);
+//   * the first step whose bin runs past the ray's hits is the loop's `done` break: later lanes stay silent.
+// The arithmetic of every emission is the reference's, operation for operation (same _rn intrinsics), so samples stay
+// bit-identical; only the order in which they are produced changes.  The tail loop (sample_gpu.cu:224-237, the indexing quirk
+// SURVEY A-Q7) is short and data-dependent on other rays' hit lists: it runs as written, uniformly in all lanes.
+// A block stages the hit lists of its rays cooperatively (coalesced over rays), each warp then samples its rays into a
+// shared-memory buffer ([ray][slot]: lane = emission number, conflict-free), the CSR offsets come from a block scan plus a
+// decoupled look-back over the per-block totals (state[b]: flag in the high word -- 1 = this block's total, 2 = inclusive
+// prefix -- value in the low word; zeroed before the launch), and each warp copies its rays out as contiguous runs.  A ray with
+// more emissions than buffer slots reruns straight into global memory.
+constexpr int kWarpThreads = 256;               // 8 warps per block
+constexpr int kWarpBuf = 96;                    // buffered emissions per ray
 struct BufSink {
-    int *vox; float *z, *dist; int last;
+    int *vox; float *z, *dist;
     __device__ __forceinline__ void operator()(int s, int v, float d, float zz)
     {
-        last = v;
-        if (s < kSampleBuf) { vox[s * kBufPitch] = v; z[s * kBufPitch] = zz; dist[s * kBufPitch] = fmaxf(d, 0.0f); }
+        if (s < kWarpBuf) { vox[s] = v; z[s] = zz; dist[s] = fmaxf(d, 0.0f); }
     }
 };
 
-__global__ void __launch_bounds__(kSampleThreads)
-k_sample_onepass(pslam_render_t p, unsigned long long *__restrict__ state)
+// the hit list of one ray in shared memory + what the tail loop needs to reach other rays of its chunk
+struct WarpHits {
+    const int *idx; const float *tmin_, *tmax_, *cum;   // [cnt]
+    int cnt, P, own_j, chunk_base_rank, Rh, R;
+    float max_distance;
+    const int *hit_idx, *hit_count, *hit_ray;
+    __device__ __forceinline__ int own_idx(int b) const { return b < cnt ? idx[b] : -1; }
+    __device__ __forceinline__ float tmin(int b) const { return b < cnt ? tmin_[b] : max_distance; }
+    __device__ __forceinline__ float tmax(int b) const { return b < cnt ? tmax_[b] : max_distance; }
+    __device__ __forceinline__ int flat_idx(int f) const     // FusedHits::flat_idx
+    {
+        const int jj = f / P, b = f % P;
+        if (jj == own_j) return own_idx(b);
+        int q = chunk_base_rank + jj;
+        if (q >= Rh) q = 0;
+        const int r = __ldg(hit_ray + q);
+        return (b < __ldg(hit_count + r)) ? __ldg(hit_idx + (int64_t)b * R + r) : -1;
+    }
+};
+
+// All 32 lanes call this for the same ray.  Returns the number of emissions; `last` = voxel id of the final one.
+template <class Noise, class Sink>
+__device__ __forceinline__ int warp_sample_ray(const WarpHits &h, const Noise &noise, Sink &sink, int nc, float steps, int &last)
+{
+    const int lane = threadIdx.x & 31;
+    const int cnt = h.cnt;
+    const float step_size = __fdiv_rn(1.0f, steps);
+    const int T = (int)ceilf(steps);
+    // state handed to the tail loop
+    int s = 0, bin = 0;
+    float z_low = h.tmin(0), hi_d = h.tmax(0);
+    int carry_bin = 0;
+    float carry_z = 0.0f;
+    for (int base = 0; base < T; base += 32) {
+        const int k = base + lane;
+        const bool act = k < T;
+        float cdf = 0.0f;
+        int F = carry_bin;
+        if (act) {
+            cdf = __fmul_rn(__fadd_rn((float)k, noise(k)), step_size);
+            while (F < cnt && cdf > h.cum[F]) ++F;
+        }
+        int b_k = F;                                 // running maximum: the loop's bin pointer never moves back
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, b_k, o);
+            if (lane >= o) b_k = max(b_k, t);
+        }
+        int b_prev = __shfl_up_sync(0xffffffffu, b_k, 1);
+        if (lane == 0) b_prev = carry_bin;
+        float z = 0.0f;
+        if (act && b_k < cnt) {
+            const float lo_c = b_k == 0 ? 0.0f : h.cum[b_k - 1], hi_c = h.cum[b_k];
+            const float lo = h.tmin_[b_k], hi = h.tmax_[b_k];
+            const float u = __fdiv_rn(__fsub_rn(cdf, lo_c), __fsub_rn(hi_c, lo_c));
+            z = __fmaf_rn(u, __fsub_rn(hi, lo), lo);
+        }
+        float z_prev = __shfl_up_sync(0xffffffffu, z, 1);
+        if (lane == 0) z_prev = carry_z;
+        const bool has_prev = k >= 1;
+        const bool live = act && b_prev < cnt;       // no earlier step was the `done` step
+        if (live) {
+            const int bend = min(b_k, cnt);
+            for (int b = b_prev; b < bend; ++b) {    // closing samples of the bins left at this step
+                const float zl = (b == b_prev && has_prev) ? z_prev : h.tmin_[b];
+                const float hd = h.tmax_[b];
+                sink(k + b, h.idx[b], __fsub_rn(hd, zl), __fmul_rn(__fadd_rn(hd, zl), 0.5f));
+            }
+            if (b_k < cnt) {
+                const float zl = (b_k == b_prev && has_prev) ? z_prev : h.tmin_[b_k];
+                sink(k + b_k, h.idx[b_k], __fsub_rn(z, zl), __fmul_rn(__fadd_rn(z, zl), 0.5f));
+            }
+        }
+        const unsigned done_mask = __ballot_sync(0xffffffffu, live && b_k >= cnt);
+        if (done_mask) {                             // the loop's break: bins ran out at step kd
+            const int src = __ffs(done_mask) - 1;
+            const int kd = base + src;
+            const int bp = __shfl_sync(0xffffffffu, b_prev, src);
+            const float zp = __shfl_sync(0xffffffffu, z_prev, src);
+            s = kd + cnt; bin = cnt;
+            z_low = (bp == cnt - 1 && kd >= 1) ? zp : h.tmin_[cnt - 1];
+            hi_d = h.tmax_[cnt - 1];
+            break;
+        }
+        if (base + 32 >= T) {                        // ran out of steps inside bin(T-1)
+            const int src = T - 1 - base;
+            bin = __shfl_sync(0xffffffffu, b_k, src);
+            z_low = __shfl_sync(0xffffffffu, z, src);
+            s = T + bin;
+            hi_d = h.tmax_[bin];
+            break;
+        }
+        carry_bin = __shfl_sync(0xffffffffu, b_k, 31);
+        carry_z = __shfl_sync(0xffffffffu, z, 31);
+    }
+    // tail, sample_gpu.cu:224-237 (uniform in all lanes, lane 0 stores)
+    last = 0;
+    const int j = h.own_j, P = h.P;
+    while (z_low < hi_d && nc > j * P + bin) {
+        const int v = h.flat_idx(j * P + bin);
+        if (lane == 0) sink(s, v, __fsub_rn(hi_d, z_low), __fmul_rn(__fadd_rn(hi_d, z_low), 0.5f));
+        last = v;
+        ++bin; ++s;
+        if (bin >= P || h.flat_idx(bin) == -1) break;
+        hi_d = h.tmax(bin);
+        z_low = h.tmin(bin);
+    }
+    return s;
+}
+
+template <class Sink>
+__device__ __forceinline__ int warp_run_ray(const pslam_render_t &p, const WarpHits &h, int q, int nc, float total, Sink &sink, int &last)
+{
+    const float steps = __fdiv_rn(total, p.step_size);
+    if (p.noise) {
+        TensorNoise nz{p.noise + (int64_t)q * p.noise_stride, p.noise_stride};
+        return warp_sample_ray(h, nz, sink, nc, steps, last);
+    }
+    const HashNoise nz((p.seed + (p.seed_dev ? *p.seed_dev : 0ull)) ^ ((uint64_t)(uint32_t)q * 0xD1B54A32D192ED03ull));
+    return warp_sample_ray(h, nz, sink, nc, steps, last);
+}
+
+// optional per-warp timeline (pslam_debug_sample_trace): [block][warp][8] = globaltimer at entry, clock64 at entry / hits staged /
+// rays sampled / offsets known / copied out, globaltimer at exit, largest sample count of the warp's rays
+#define WARP_TRACE(slot, value)                                                                                                 \
+    do {                                                                                                                        \
+        if (g_sample_trace && (threadIdx.x & 31) == 0) g_sample_trace[((size_t)blockIdx.x * (kWarpThreads / 32) + (threadIdx.x >> 5)) * 8 + (slot)] = (value); \
+    } while (0)
+
+__global__ void __launch_bounds__(kWarpThreads)
+k_sample_warp(pslam_render_t p, unsigned long long *__restrict__ state, int rpb)
 {
     pdl_enter();
-    extern __shared__ __align__(16) unsigned char s_raw[];   // hits [3][n_max][T], samples [3][kSampleBuf][T + 1], cumulative bin probabilities [n_max][T]
-    __shared__ int s_wsum[kSampleThreads / 32];
-    __shared__ int s_base;
+    extern __shared__ __align__(16) unsigned char s_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int *s_idx = reinterpret_cast<int *>(s_raw) + tid;
-    float *s_min = reinterpret_cast<float *>(s_raw) + (size_t)p.n_max * kSampleThreads + tid;
-    float *s_max = s_min + (size_t)p.n_max * kSampleThreads;
-    int *b_vox = reinterpret_cast<int *>(s_raw) + (size_t)3 * p.n_max * kSampleThreads + tid;
-    float *b_z = reinterpret_cast<float *>(b_vox) + kSampleBuf * kBufPitch;
-    float *b_dist = b_z + kSampleBuf * kBufPitch;
-    float *s_cum = b_dist + kSampleBuf * kBufPitch;   // [n_max][T] after the sample buffers: running sums of the bin probabilities
     const int Rh = p.counters[PSLAM_C_RH];
     const int P = p.counters[PSLAM_C_P];
-    const int q = blockIdx.x * kSampleThreads + tid;
-    int nsamp = 0;
-    SAMPLE_TRACE(0, globaltimer_ns());
-    SAMPLE_TRACE(1, clock64());
-    if (q < Rh) {
-        BufSink bs{b_vox, b_z, b_dist, 0};
-        const int s = run_ray(p, q, Rh, P, s_idx, s_min, s_max, bs, s_cum);
-        nsamp = (s > 0 && bs.last == -1) ? s - 1 : s;   // a trailing -1 id (A-Q7) is not a sample and can only be the last emission
+    const int q0 = blockIdx.x * rpb;
+    if (q0 >= Rh) return;                                   // (no later block has rays either: nobody waits for this one)
+    WARP_TRACE(0, globaltimer_ns());
+    WARP_TRACE(1, clock64());
+    const int nm = p.n_max, pitch = nm | 1;                 // odd pitch: staging writes (ray varies fastest) are conflict-free
+    int *h_idx = reinterpret_cast<int *>(s_raw);            // [rpb][pitch]
+    float *h_min = reinterpret_cast<float *>(h_idx + rpb * pitch);
+    float *h_max = h_min + rpb * pitch;
+    float *h_cum = h_max + rpb * pitch;
+    float *w_pr = h_cum + rpb * pitch;                      // [warps][pitch]: bin probabilities of the ray a warp is preparing
+    int *b_vox = reinterpret_cast<int *>(w_pr + (kWarpThreads / 32) * pitch);   // [rpb][kWarpBuf]
+    float *b_z = reinterpret_cast<float *>(b_vox + rpb * kWarpBuf);
+    float *b_dist = b_z + rpb * kWarpBuf;
+    int *s_cnt = reinterpret_cast<int *>(b_dist + rpb * kWarpBuf);              // [rpb] hit count
+    int *s_ns = s_cnt + rpb;                                // [rpb] samples of the ray
+    int *s_off = s_ns + rpb;                                // [rpb] its CSR offset (unclamped)
+    float *s_total = reinterpret_cast<float *>(s_off + rpb);   // [rpb] summed segment length
+
+    // ---- phase 0: stage the hit lists (thread -> ray tid % rpb, slots tid / rpb, + blockDim / rpb, ...) ----
+    {
+        const int i = tid % rpb, q = q0 + i;
+        int cnt = 0, r = 0;
+        if (q < Rh) {
+            r = __ldg(p.hit_ray + q);
+            cnt = min(__ldg(p.hit_count + r), nm);
+        }
+        if (tid < rpb) s_cnt[i] = cnt;
+        for (int b = tid / rpb; b < cnt; b += kWarpThreads / rpb) {
+            h_idx[i * pitch + b] = __ldg(p.hit_idx + (int64_t)b * p.R + r);
+            h_min[i * pitch + b] = __ldg(p.hit_min + (int64_t)b * p.R + r);
+            h_max[i * pitch + b] = __ldg(p.hit_max + (int64_t)b * p.R + r);
+        }
     }
-    SAMPLE_TRACE(2, clock64());
-    // block scan of the counts
-    int x = nsamp;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(0xffffffffu, x, o);
-        if (lane >= o) x += y;
+    __syncthreads();
+    WARP_TRACE(2, clock64());
+    // ---- phase 1: every warp samples its rays ----
+    const int n = (Rh + kGroups - 1) / kGroups;
+    auto hits_of = [&](int i, int q) {
+        const int g = q / n, jf = q % n;
+        const int c = jf / kChunkRays;
+        WarpHits h;
+        h.idx = h_idx + i * pitch; h.tmin_ = h_min + i * pitch; h.tmax_ = h_max + i * pitch; h.cum = h_cum + i * pitch;
+        h.cnt = s_cnt[i]; h.P = P; h.own_j = jf % kChunkRays; h.chunk_base_rank = g * n + c * kChunkRays; h.Rh = Rh; h.R = p.R;
+        h.max_distance = p.max_distance;
+        h.hit_idx = p.hit_idx; h.hit_count = p.hit_count; h.hit_ray = p.hit_ray;
+        return h;
+    };
+    auto nc_of = [&](int q) { const int c = (q % n) / kChunkRays; return min(kChunkRays, n - c * kChunkRays); };
+    int wmax = 0;
+    for (int i = warp; i < rpb; i += kWarpThreads / 32) {
+        const int q = q0 + i;
+        int nsamp = 0;
+        if (q < Rh) {
+            WarpHits h = hits_of(i, q);
+            const int cnt = h.cnt;
+            // a5: dists, their sum (left to right), probs and their running sum (voxel_helpers.py:639-644): every lane runs the same
+            // chains on broadcast reads, lane b keeps element b
+            float total = 0.0f;
+            for (int b = 0; b < cnt; ++b) total = __fadd_rn(total, __fsub_rn(h.tmax_[b], h.tmin_[b]));
+            float *pr = w_pr + warp * pitch;
+            for (int b = lane; b < cnt; b += 32) pr[b] = __fdiv_rn(__fsub_rn(h.tmax_[b], h.tmin_[b]), total);
+            __syncwarp();
+            {
+                float c = 0.0f;
+                const int upto = ((cnt - 1 - lane) >= 0) ? lane + ((cnt - 1 - lane) / 32) * 32 : -1;   // last element this lane keeps
+                for (int b = 0; b <= upto; ++b) {
+                    c = (b == 0) ? pr[0] : __fadd_rn(c, pr[b]);
+                    if ((b & 31) == lane) h_cum[i * pitch + b] = c;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) s_total[i] = total;
+            BufSink bs{b_vox + i * kWarpBuf, b_z + i * kWarpBuf, b_dist + i * kWarpBuf};
+            int last = 0;
+            const int s = warp_run_ray(p, h, q, nc_of(q), total, bs, last);
+            nsamp = (s > 0 && last == -1) ? s - 1 : s;      // a trailing -1 id (A-Q7) is not a sample and can only be the last emission
+            __syncwarp();
+        }
+        if (lane == 0) s_ns[i] = nsamp;
+        wmax = max(wmax, nsamp);
     }
-    const int wmax = warp_max_i(nsamp);
-    if (lane == 31) s_wsum[warp] = x;
     if (lane == 0 && wmax > 0) atomicMax(p.counters + PSLAM_C_S, wmax);
     __syncthreads();
-    int excl = x - nsamp, btotal = 0;
-    for (int w = 0; w < kSampleThreads / 32; ++w) { if (w < warp) excl += s_wsum[w]; btotal += s_wsum[w]; }
-    // decoupled look-back (warp 0): exclusive prefix of this block over all earlier blocks
+    WARP_TRACE(3, clock64());
+    // ---- phase 2: CSR offsets = block scan + decoupled look-back (warp 0) ----
     if (warp == 0) {
+        const int v = lane < rpb ? s_ns[lane] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        const int btotal = __shfl_sync(0xffffffffu, x, 31);
         const int b = blockIdx.x;
         if (lane == 0) {
-            const unsigned long long v = ((unsigned long long)(b == 0 ? 2u : 1u) << 32) | (unsigned)btotal;
+            const unsigned long long sv = ((unsigned long long)(b == 0 ? 2u : 1u) << 32) | (unsigned)btotal;
             __threadfence();
-            atomicExch(state + b, v);
+            atomicExch(state + b, sv);
         }
         int base = 0;
         for (int hi_b = b - 1; hi_b >= 0; hi_b -= 32) {
             const int idx = hi_b - lane;                        // lane 0 looks at the nearest predecessor
-            unsigned long long v = 2ull << 32;                  // out of range: a zero prefix
+            unsigned long long sv = 2ull << 32;                 // out of range: a zero prefix
             if (idx >= 0) {
-                do { v = *reinterpret_cast<volatile unsigned long long *>(state + idx); } while ((v >> 32) == 0ull);
+                do { sv = *reinterpret_cast<volatile unsigned long long *>(state + idx); } while ((sv >> 32) == 0ull);
             }
-            const unsigned done = __ballot_sync(0xffffffffu, (v >> 32) == 2ull);
+            const unsigned done = __ballot_sync(0xffffffffu, (sv >> 32) == 2ull);
             const int stop = done ? __ffs(done) - 1 : 32;       // nearest lane that already has its inclusive prefix
-            int part = (lane <= stop) ? (int)(unsigned)(v & 0xffffffffull) : 0;
+            int part = (lane <= stop) ? (int)(unsigned)(sv & 0xffffffffull) : 0;
             part = warp_sum_i(part);
             base += part;
             if (done) break;
         }
-        if (lane == 0) {
-            s_base = base;
-            if (b > 0) {
-                __threadfence();
-                atomicExch(state + b, (2ull << 32) | (unsigned)(base + btotal));
-            }
+        if (lane == 0 && b > 0) {
+            __threadfence();
+            atomicExch(state + b, (2ull << 32) | (unsigned)(base + btotal));
         }
+        if (lane < rpb) s_off[lane] = base + x - v;
     }
     __syncthreads();
-    SAMPLE_TRACE(3, clock64());
-    const int off_raw = s_base + excl;
-    if (q < Rh) {
-        p.samp_off[q] = off_raw;
-        if (q == Rh - 1) {
-            const int total = off_raw + nsamp;
-            p.samp_off[Rh] = total;
-            p.counters[PSLAM_C_NSAMP] = min(total, p.sample_cap);
-            if (total > p.sample_cap) atomicOr(p.counters + PSLAM_C_OVERFLOW, 1);
+    WARP_TRACE(4, clock64());
+    // ---- phase 3: copy-out, a ray = one contiguous run per array ----
+    for (int i = warp; i < rpb; i += kWarpThreads / 32) {
+        const int q = q0 + i;
+        if (q >= Rh) break;
+        const int off_raw = s_off[i], nsamp = s_ns[i];
+        if (lane == 0) {
+            p.samp_off[q] = off_raw;
+            if (q == Rh - 1) {
+                const int total = off_raw + nsamp;
+                p.samp_off[Rh] = total;
+                p.counters[PSLAM_C_NSAMP] = min(total, p.sample_cap);
+                if (total > p.sample_cap) atomicOr(p.counters + PSLAM_C_OVERFLOW, 1);
+            }
+        }
+        const int off = min(off_raw, p.sample_cap);
+        const int room = max(0, min(off_raw + nsamp, p.sample_cap) - off);
+        if (nsamp <= kWarpBuf) {
+            for (int k = lane; k < min(nsamp, room); k += 32) {
+                p.samp_vox[off + k] = b_vox[i * kWarpBuf + k];
+                p.samp_z[off + k] = b_z[i * kWarpBuf + k];
+                p.samp_dist[off + k] = b_dist[i * kWarpBuf + k];
+                p.samp_ray[off + k] = q;
+            }
+        } else {                                            // too long for the buffer: once more, straight into global memory
+            WarpHits h = hits_of(i, q);
+            CsrSink csr{p.samp_vox + off, p.samp_z + off, p.samp_dist + off, p.samp_ray + off, q, room};
+            int last = 0;
+            warp_run_ray(p, h, q, nc_of(q), s_total[i], csr, last);
         }
     }
-    const int off = min(off_raw, p.sample_cap);
-    const int room = max(0, min(off_raw + nsamp, p.sample_cap) - off);
-    // copy-out, one ray at a time by the whole warp: lane k takes the ray's k-th sample, so the stores of a ray are one
-    // contiguous run (the per-thread form wrote 32 different lines per store); the buffer pitch of T + 1 keeps both this
-    // column read and the sampling loop's row write free of bank conflicts
-    const int m = (q < Rh && nsamp <= kSampleBuf) ? min(nsamp, room) : 0;
-#pragma unroll 4
-    for (int L = 0; L < 32; ++L) {                      // (unrolled: the shared-memory reads of four rays are in flight together)
-        const int mL = __shfl_sync(0xffffffffu, m, L);
-        const int offL = __shfl_sync(0xffffffffu, off, L);
-        const int col = L - lane;                       // b_* already point at this thread's column
-        if (lane < mL) {
-            const int v = b_vox[lane * kBufPitch + col];
-            const float zz = b_z[lane * kBufPitch + col], dd = b_dist[lane * kBufPitch + col];
-            p.samp_vox[offL + lane] = v;
-            p.samp_z[offL + lane] = zz;
-            p.samp_dist[offL + lane] = dd;
-            p.samp_ray[offL + lane] = q + col;
-        }
-        for (int k = lane + 32; k < mL; k += 32) {      // rays with more than 32 samples
-            p.samp_vox[offL + k] = b_vox[k * kBufPitch + col];
-            p.samp_z[offL + k] = b_z[k * kBufPitch + col];
-            p.samp_dist[offL + k] = b_dist[k * kBufPitch + col];
-            p.samp_ray[offL + k] = q + col;
-        }
-    }
-    if (q < Rh && nsamp > kSampleBuf) {                 // a ray too long for the buffer reruns straight into global memory
-        CsrSink csr{p.samp_vox + off, p.samp_z + off, p.samp_dist + off, p.samp_ray + off, q, room};
-        run_ray(p, q, Rh, P, s_idx, s_min, s_max, csr, s_cum);
-    }
-    SAMPLE_TRACE(4, clock64());
-    SAMPLE_TRACE(5, globaltimer_ns());
-    SAMPLE_TRACE(6, (long long)warp_max_i(nsamp));
+    WARP_TRACE(5, clock64());
+    WARP_TRACE(6, globaltimer_ns());
+    WARP_TRACE(7, (long long)wmax);
 }
 
 // counts -> exclusive offsets (block-local scan + scanned block bases); also writes off[R_h].
@@ -460,27 +643,46 @@ k_sample_offsets(pslam_render_t p, const int *__restrict__ block_base)
     }
 }
 
+// rays per block of the warp-per-ray kernel: 32 when that still gives every SM a block, else 16 / 8 (tracking batches)
+static int sample_rays_per_block(int R)
+{
+    static int forced = -1;                       // PSLAM_SAMPLE_RPB=8|16|32: measurement override
+    if (forced < 0) {
+        const char *e = getenv("PSLAM_SAMPLE_RPB");
+        const int v = e ? atoi(e) : 0;
+        forced = (v == 8 || v == 16 || v == 32) ? v : 0;
+    }
+    if (forced) return forced;
+    const int sms = num_sms();
+    if (ceil_div(R, 16) < sms) return 8;         // tracking batches: one ray per warp, every SM gets a block
+    if (ceil_div(R, 16) <= 8 * sms) return 16;   // measured at 8192 rays: 14.7 us (16) vs 19.8 (8) / 19.0 (32)
+    return 32;
+}
+
 int launch_sample_fused(const pslam_render_t *p, cudaStream_t st)
 {
-    const int nb = ceil_div(p->R, kSampleThreads);
-    int *block_counts = p->scratch_i + scratch_i_sample_off(p->R);   // after intersect's block_hits; 2 ints per block
-    const size_t smem = (size_t)p->n_max * kSampleThreads * 12;
-    PSLAM_CHECK_ARG(smem <= 48 * 1024, PSLAM_E_RANGE, "n_max=%d: the per-block hit staging exceeds 48 KB of shared memory", p->n_max);
-    const size_t smem1 = smem + (size_t)kSampleBuf * kBufPitch * 12 + (size_t)p->n_max * kSampleThreads * 4;
-    if (smem1 <= 160 * 1024) {
+    int *block_counts = p->scratch_i + scratch_i_sample_off(p->R);   // after intersect's block_hits: look-back state, 2 ints per block
+    const int rpb = sample_rays_per_block(p->R);
+    const int pitch = p->n_max | 1;
+    const size_t smem1 = sizeof(int) * ((size_t)4 * rpb * pitch + (size_t)(kWarpThreads / 32) * pitch + (size_t)3 * rpb * kWarpBuf + (size_t)4 * rpb);
+    if (smem1 <= 200 * 1024) {
         static PerDevice once = {};
         bool &configured = once.done[current_device()];
         if (!configured) {
-            cudaError_t e = cudaFuncSetAttribute(k_sample_onepass, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            cudaError_t e = cudaFuncSetAttribute(k_sample_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             if (e != cudaSuccess) { set_error("sample: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
             configured = true;
         }
         unsigned long long *state = reinterpret_cast<unsigned long long *>(block_counts + (((uintptr_t)block_counts & 7) ? 1 : 0));
         // (the look-back state was cleared by k_compact_rays, the last kernel of the intersection stage)
-        launch_chain(k_sample_onepass, dim3(nb), dim3(kSampleThreads), smem1, st, *p, state);
-        PSLAM_CHECK_LAUNCH("sample_onepass");
+        launch_chain(k_sample_warp, dim3(ceil_div(p->R, rpb)), dim3(kWarpThreads), smem1, st, *p, state, rpb);
+        PSLAM_CHECK_LAUNCH("sample_warp");
         return 0;
     }
+    // hit lists too long for the shared-memory staging of a block: count -> scan -> write, one thread per ray
+    const int nb = ceil_div(p->R, kSampleThreads);
+    const size_t smem = (size_t)p->n_max * kSampleThreads * 12;
+    PSLAM_CHECK_ARG(smem <= 48 * 1024, PSLAM_E_RANGE, "n_max=%d: the per-block hit staging exceeds 48 KB of shared memory", p->n_max);
     k_sample_fused<false><<<nb, kSampleThreads, smem, st>>>(*p, block_counts);
     PSLAM_CHECK_LAUNCH("sample_count");
     if (int rc = scan_partials(block_counts, nb, p->counters + PSLAM_C_TILE2, st)) return rc;

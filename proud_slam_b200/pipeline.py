@@ -86,6 +86,7 @@ class RenderPipeline:
         self.dec_ws = {w: torch.empty(int(self.lib.pslam_decoder_ws_count(w)), **f32) for w in (128, 256)}
         self.wgrad_ws = None   # allocated on first use (any backward through the tensor-core path)
         self.node_cache = None
+        self._map_key, self._map_built = None, False
         self.args = RenderT()
         self._keep = None      # tensors referenced by self.args
         self.R = 0
@@ -127,7 +128,6 @@ class RenderPipeline:
             flags |= F_FORWARD_ONLY
         if defer_loss:
             flags |= _lib.F_DEFER_LOSS
-        a.flags = flags
         a.voxel_size, a.step_size, a.truncation = float(voxel_size), float(step_size), float(truncation)
         a.max_distance, a.max_depth = float(max_distance), float(max_depth)
         a.w_rgb, a.w_depth, a.w_fs, a.w_sdf = [float(x) for x in weights]
@@ -143,11 +143,21 @@ class RenderPipeline:
                                                      emb.data_ptr())
         a.dec = _decoder_struct(dec_params)
         a.dec_ws = self.dec_ws[width].data_ptr()
-        # traversal cache of the octree walk: 128 B per octree row, rebuilt by every sample() from the bound map
+        # traversal cache of the octree walk: 128 B per octree row, built by the first sample() / step() on a map and reused
+        # until the map changes (new tensors, or an in-place edit that torch's version counters see; a caller that edits the
+        # map behind torch's back -- raw kernels -- calls invalidate_map())
         need = 128 * int(centres.shape[0])
         if self.node_cache is None or self.node_cache.numel() < need:
             self.node_cache = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._map_key = None
         a.node_cache, a.node_cache_bytes = self.node_cache.data_ptr(), self.node_cache.numel()
+        key = (centres.data_ptr(), structure.data_ptr(), int(centres.shape[0]), centres._version, structure._version,
+               map_states.get("generation") if hasattr(map_states, "get") else None)
+        if key == self._map_key and self._map_built:
+            flags |= _lib.F_NODE_CACHE_VALID
+        else:
+            self._map_key, self._map_built = key, False
+        a.flags = flags
         # width 128: the workspace holds the wgrad operands (decoder gradients) and, for any backward, the forward's ReLU
         # masks and the feature rows of the stand-alone trilinear kernels
         if (g_dec is not None or g_emb is not None or grad_rays) and width == 128 and not forward_only:
@@ -186,8 +196,20 @@ class RenderPipeline:
     def _call(self, fn, what):
         _lib.check(fn(C.byref(self.args), _lib.stream_ptr(self.device)), what)
 
+    def _map_cache_built(self):
+        # the launch just enqueued built the traversal cache of the bound map: later launches on this stream reuse it
+        if not self._map_built and self.args.node_cache:
+            self._map_built = True
+            self.args.flags |= _lib.F_NODE_CACHE_VALID
+
+    def invalidate_map(self):
+        """The bound map's octree arrays were edited in place outside torch: the next sample() rebuilds the traversal cache."""
+        self._map_key, self._map_built = None, False
+        self.args.flags &= ~_lib.F_NODE_CACHE_VALID
+
     def sample(self):
         self._call(self.lib.pslam_render_sample, "pslam_render_sample")
+        self._map_cache_built()
 
     def forward(self):
         self._call(self.lib.pslam_render_forward, "pslam_render_forward")
@@ -208,9 +230,12 @@ class RenderPipeline:
 
     def stage(self, i):
         _lib.check(self.lib.pslam_render_stage(C.byref(self.args), int(i), _lib.stream_ptr(self.device)), f"stage {i}")
+        if int(i) == 0:
+            self._map_cache_built()
 
     def step(self):
         self._call(self.lib.pslam_render_step, "pslam_render_step")
+        self._map_cache_built()
 
     # ------------------------------------------------------------------ results (synchronising)
     def counts(self):
