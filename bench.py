@@ -33,11 +33,28 @@ SCENE = "replica_20k"
 KEYFRAMES = 8
 RAYS_PER_FRAME = 1024
 CRIT_W = (0.5, 1.0, 10.0, 5000.0)      # rgb, depth, fs, sdf (configs/replica/replica.yaml:6-11)
-WIDTH = 128
+WIDTH = 128                            # configs/replica/replica.yaml; the ScanNet / ARKit configs use 256 (--width)
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r02_traffic.json")   # dram bytes per launch from the committed ncu --set full capture
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel at the bench workload (ncu --set full, profiles/*_summary.md)
-NCU_TRAFFIC = {0: 985.8e6, 2: 280.5e6}   # 3xF16: k_field_bf<kBwdSaved> 15.9 + 264.7 MB (kFwdSave: 12.8 + 261.3 MB), profiles/r01_final_kernels_full.csv
+def workload_string(scene, keyframes, rays_per_frame, R, n_oct, n_vox, voxel_size, E, width):
+    """config.workload -- the same string from both arms (the driver compares them)."""
+    return (f"{scene}: {keyframes} keyframes x {rays_per_frame} rays = {R} rays/iter per GPU, {n_oct} octants ({n_vox} voxels) at "
+            f"{voxel_size:g} m, {E}x16 embeddings, decoder width {width}, mapping fwd+bwd")
+
+
+def ncu_traffic(kernel, samples):
+    """dram__bytes_read.sum + dram__bytes_write.sum of `kernel` from the ncu --set full capture committed under profiles/
+    (scripts/ncu_traffic.py writes the file with the commit and workload it was taken on); None when there is no capture of
+    this workload (a different ray batch, scene or build)."""
+    try:
+        with open(TRAFFIC_FILE) as f:
+            t = json.load(f)
+        if abs(t["samples_per_iter"] - samples) > 0.02 * samples:
+            return None
+        return t["kernels"].get(kernel)
+    except Exception:
+        return None
 
 
 def macs_per_sample(w):
@@ -150,18 +167,30 @@ class ClockSampler:
                 "samples": len(sm), "source": "nvidia-smi -lms 20"}
 
 
-def build_workload(rank, rays_per_frame=RAYS_PER_FRAME, keyframes=KEYFRAMES, scene_kind=SCENE):
-    """Scene + map (product octree, no oracle) + this rank's ray batch, on CPU."""
-    from proud_slam_b200 import scene as sc, svo
+def build_workload(rank, rays_per_frame=RAYS_PER_FRAME, keyframes=KEYFRAMES, scene_kind=SCENE, oracle_tree=False):
+    """Scene + map + this rank's ray batch, on CPU.  The GPU arm builds the map with the product's octree (no oracle), the
+    reference arm with the oracle's (it never loads the product library); tests/test_octree.py holds the two equal."""
+    from proud_slam_b200 import scene as sc     # (pure Python / numpy: synthetic frames, no native code)
     s = sc.make_scene(scene_kind, pixel_stride=2)
-    tree = svo.Octree()
-    tree.init(s.grid_dim, 16, s.voxel_size, 8)
-    tree.insert(torch.from_numpy(s.voxels))
-    n_oct = tree.count_nodes()
-    ms = svo.build_map_states(tree, s.voxel_size, num_embeddings=max(20000, n_oct), device="cpu", seed=0)
+    if oracle_tree:
+        import oracle
+        tree = oracle.Octree(s.grid_dim)
+        tree.insert(s.voxels)
+        n_oct = tree.count()
+        v, c, f = tree.get_centres_and_children()
+        ms = sc.map_states_from_flat(v, c, f, s.voxel_size, num_embeddings=max(20000, n_oct), seed=0)
+        ms["voxel_vertex_emb"] = ms["voxel_vertex_emb"].detach()
+    else:
+        from proud_slam_b200 import svo
+        tree = svo.Octree()
+        tree.init(s.grid_dim, 16, s.voxel_size, 8)
+        tree.insert(torch.from_numpy(s.voxels))
+        n_oct = tree.count_nodes()
+        ms = svo.build_map_states(tree, s.voxel_size, num_embeddings=max(20000, n_oct), device="cpu", seed=0)
+    n_vox = int(s.voxels.shape[0])              # scene.voxels is unique: the surface voxels of the tree
     frames = [(rank * keyframes + i) % len(s.frames) for i in range(keyframes)]
     rays_o, rays_d, rgb, depth = sc.sample_batch(s, frames, rays_per_frame, seed=100 + rank)
-    return s, ms, (rays_o[0].contiguous(), rays_d[0].contiguous(), rgb[0].contiguous(), depth[0].contiguous()), n_oct, tree.count_leaf_nodes()
+    return s, ms, (rays_o[0].contiguous(), rays_d[0].contiguous(), rgb[0].contiguous(), depth[0].contiguous()), n_oct, n_vox
 
 
 def decoder_params(width, device):
@@ -175,29 +204,35 @@ def decoder_params(width, device):
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
+def oracle_iteration(s, ms_cpu, batch, width):
+    """One closure = one mapping iteration of the oracle port on CPU tensors (fwd + loss + bwd) on `batch`."""
+    import oracle  # noqa: F401  (test infrastructure; allowed here as the CPU baseline)
+    from tests import util
+    ms = {k: v.clone() for k, v in ms_cpu.items()}
+    ms["voxel_vertex_emb"].requires_grad_(True)
+    dec = [p.requires_grad_(True) for p in decoder_params(width, "cpu")]
+    rays_o, rays_d, rgb, depth = batch
+    ro_, rd_ = rays_o[None].clone().requires_grad_(True), rays_d[None].clone().requires_grad_(True)
+    gen = torch.Generator().manual_seed(0)
+    return lambda: util.oracle_step(ro_, rd_, rgb[None], depth[None], ms, dec, voxel_size=s.voxel_size, generator=gen)
+
+
 def run_reference(args):
     """`--impl reference`: the reference's CPU path for this workload.  /root/reference cannot travel
-    to the GPU box and its two native kernels have no CPU build, so this is the oracle PORT
-    (oracle/: C restatement of the kernels + the torch stages on CPU tensors), all host threads."""
+    to the GPU box (it does not exist there) and its two native kernels have no CPU build, so this is the oracle PORT
+    (oracle/: C restatement of the kernels + the torch stages on CPU tensors), all host threads, on the map the ORACLE's
+    octree builds -- this arm never loads the product library."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import oracle  # noqa: F401  (test infrastructure; allowed here as the CPU baseline)
-    from tests import util
-    from oracle import render_oracle as ro
     cores = os.cpu_count()
     torch.set_num_threads(cores)
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    s, ms, (rays_o, rays_d, rgb, depth), n_oct, n_vox = build_workload(0)
-    ms["voxel_vertex_emb"].requires_grad_(True)
-    dec = [p.requires_grad_(True) for p in decoder_params(WIDTH, "cpu")]
-    R = rays_o.shape[0]
-    ro_, rd_ = rays_o[None].clone().requires_grad_(True), rays_d[None].clone().requires_grad_(True)
-    gen = torch.Generator().manual_seed(0)
-
-    def one():
-        util.oracle_step(ro_, rd_, rgb[None], depth[None], ms, dec, voxel_size=s.voxel_size, generator=gen)
-
+    rpf = args.rays // args.keyframes
+    s, ms, batch, n_oct, n_vox = build_workload(0, rays_per_frame=rpf, keyframes=args.keyframes, scene_kind=args.workload, oracle_tree=True)
+    R = batch[0].shape[0]
+    E = ms["voxel_vertex_emb"].shape[0]
+    one = oracle_iteration(s, ms, batch, args.width)
     for _ in range(args.warmup):
         one()
     t0 = time.perf_counter()
@@ -209,8 +244,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{SCENE}: {KEYFRAMES} keyframes x {RAYS_PER_FRAME} rays = {R} rays/iter, {n_oct} octants "
-                               f"({n_vox} voxels) at 0.2 m, decoder width {WIDTH}, mapping fwd+bwd on CPU tensors"},
+        "config": {"workload": workload_string(args.workload, args.keyframes, rpf, R, n_oct, n_vox, s.voxel_size, E, args.width),
+                   "arm": "oracle port on CPU tensors (torch CPU + OpenMP C kernels); /root/reference is absent on the GPU box"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{args.steps} full iterations of the {R}-ray workload (oracle port, torch CPU + OpenMP C kernels)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -219,10 +254,23 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def algorithmic_bytes(R, Rh, P, hits, N, E_t):
+    """SURVEY 8(d) contract figures per HBM kernel (valid entries only, tables once per iteration), in bytes per launch."""
+    return {
+        "K1 intersect (k_step_begin + k_intersect_warp + k_compact_rays)": 24.0 * R + 12.0 * hits + 48.0 * N,
+        "K2 sample (k_sample_warp, counter-based noise: no noise tensor)": 12.0 * hits + 12.0 * P,
+        "K3 trilinear gather (k_tri_gather)": 8.0 * P + 44.0 * hits + 64.0 * P + 32.0 * N + 64.0 * E_t,
+        "K5 composite + loss (k_composite_fwd + k_loss_reduce)": 20.0 * P + 4.0 * P + 16.0 * Rh,
+        "K5' composite backward (k_composite_bwd)": 16.0 * Rh + 24.0 * P + 16.0 * P,
+        "K3' trilinear scatter (k_tri_scatter)": 64.0 * P + 8.0 * P + 44.0 * hits + 24.0 * Rh + 64.0 * E_t,
+    }
+
+
 def run_gpu(args):
     import torch.distributed as dist
     from proud_slam_b200 import _lib
     from proud_slam_b200.pipeline import RenderPipeline
+    from proud_slam_b200.parallel import FlatGrads, PeerExchange
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -234,24 +282,44 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
-    SCENE, RAYS_PER_FRAME = args.workload, args.rays // KEYFRAMES     # defaults = BASELINE.json configs[1]
-    s, ms_cpu, batch_cpu, n_oct, n_vox = build_workload(rank, rays_per_frame=RAYS_PER_FRAME, scene_kind=SCENE)
+    SCENE, WIDTH, KEYFRAMES = args.workload, args.width, args.keyframes     # defaults = BASELINE.json configs[1]
+    total_rays = args.rays
+    strong = args.strong and world > 1
+    rays_here = total_rays // world if strong else total_rays               # strong: the batch is fixed, every rank takes a share
+    RAYS_PER_FRAME = max(rays_here // KEYFRAMES, 1)
+    s, ms_cpu, batch_cpu, n_oct, n_vox = build_workload(rank, rays_per_frame=RAYS_PER_FRAME, keyframes=KEYFRAMES, scene_kind=SCENE)
     ms = {k: v.to(device).contiguous() for k, v in ms_cpu.items()}
     dec = decoder_params(WIDTH, device)
     R = batch_cpu[0].shape[0]
     E = ms["voxel_vertex_emb"].shape[0]
-    # one flat gradient buffer [E*16 | decoder]: the kernels scatter straight into what NCCL reduces
-    from proud_slam_b200.parallel import FlatGrads
-    fg = FlatGrads(ms["voxel_vertex_emb"], dec)
+    # one flat gradient buffer [E*16 | decoder]: the kernels scatter straight into what the all-reduce sums.  N > 1: peer-mapped
+    # (torch symmetric memory) so that both exchanges run inside pslam_render_step over NVLink; NCCL if that is unavailable
+    peer, transport = None, "single GPU"
+    if world > 1 and not args.nccl:
+        try:
+            peer = PeerExchange(FlatGrads.numel(ms["voxel_vertex_emb"], dec), device)
+            transport = "in-kernel exchanges over NVLink peer memory (csrc/peer.cu): loss closure inside k_loss_reduce, two-shot all-reduce"
+        except Exception as e:   # noqa: BLE001
+            peer, transport = None, f"NCCL all_gather + all_reduce (peer-mapped buffers unavailable: {type(e).__name__}: {e})"[:200]
+        ok = torch.tensor([1.0 if peer is not None else 0.0], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0.0:
+            peer = None
+    elif world > 1:
+        transport = "NCCL all_gather + all_reduce (--nccl)"
+    fg = FlatGrads(ms["voxel_vertex_emb"], dec, flat=None if peer is None else peer.flat)
     flat, g_emb, g_dec = fg.flat, fg.g_emb, fg.g_dec
     host = [t.pin_memory() for t in batch_cpu]                        # e2e: inputs start in pinned host memory
     dev_in = [torch.empty_like(t, device=device) for t in batch_cpu]
     for d, h in zip(dev_in, host):
         d.copy_(h)
-    pipe = RenderPipeline(R, device, samples_per_ray=64 if SCENE != "scannet_large" else 128)
+    spr = 64 if SCENE != "scannet_large" else 128
+    pipe = RenderPipeline(R, device, samples_per_ray=spr)
     pipe.bind(dev_in[0], dev_in[1], ms, dec, voxel_size=s.voxel_size, step_size=0.1 * s.voxel_size, truncation=0.1,
               max_distance=10.0, max_depth=10.0, target_rgb=dev_in[2], target_depth=dev_in[3], noise=None, seed=1,
-              weights=CRIT_W, g_emb=g_emb, g_dec=g_dec, grad_rays=True, defer_loss=(world > 1))
+              weights=CRIT_W, g_emb=g_emb, g_dec=g_dec, grad_rays=True, defer_loss=(world > 1 and peer is None))
+    if peer is not None:
+        peer.bind(pipe)
     rows = torch.zeros(world, 16, dtype=torch.float64, device=device)
     loss_host = torch.empty(16, pin_memory=True)
     flush = torch.empty(192 * 1024 * 1024 // 4, device=device)       # 192 MiB > 126 MB L2
@@ -259,8 +327,8 @@ def run_gpu(args):
     def step(seed):
         pipe.args.seed = seed
         flat.zero_()
-        if world == 1:
-            pipe.step()
+        if world == 1 or peer is not None:
+            pipe.step()                                               # N > 1: loss closure and gradient all-reduce happen inside
         else:
             pipe.sample()
             pipe.forward()                                            # stops at this rank's raw loss sums
@@ -298,6 +366,7 @@ def run_gpu(args):
         step(1000 + i)
     barrier()
     counts = pipe.counts()
+    pipe.check()
     sampler = ClockSampler(local)
     if rank == 0:
         clock_sampler = sampler
@@ -324,19 +393,69 @@ def run_gpu(args):
     clocks = sampler.stop() if rank == 0 else None
     loss_val = float(loss_host[0])
 
-    # dominant kernel alone (field backward = decoder dgrad+wgrad + embedding scatter), events around it
-    prof = {}
+    # ---- N > 1: the exchanges give the single-GPU answer.  Every rank renders rank 0's batch with the same seed: the global
+    # means are those of one copy, so the loss must equal the 1-GPU loss, every rank's gradient is 1/N of the 1-GPU gradient
+    # and their all-reduced sum must equal it (fp32 re-association apart); all ranks must hold bit-identical sums.
+    check = None
+    if world > 1:
+        b0 = [t.clone() for t in dev_in]
+        for t in b0:
+            dist.broadcast(t, 0)
+        pipe.bind(b0[0], b0[1], ms, dec, voxel_size=s.voxel_size, step_size=0.1 * s.voxel_size, truncation=0.1,
+                  max_distance=10.0, max_depth=10.0, target_rgb=b0[2], target_depth=b0[3], noise=None, seed=7,
+                  weights=CRIT_W, g_emb=g_emb, g_dec=g_dec, grad_rays=True, defer_loss=(peer is None))
+        step(7)
+        torch.cuda.synchronize()
+        multi_flat, multi_loss = flat.clone(), float(pipe.loss[0])
+        lo = multi_flat.clone()
+        hi = multi_flat.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        identical = bool(torch.equal(lo, hi))
+        saved_peer = _lib.PeerT()
+        import ctypes as C
+        C.memmove(C.byref(saved_peer), C.byref(pipe.args.peer), C.sizeof(saved_peer))
+        single = FlatGrads(ms["voxel_vertex_emb"], dec)
+        pipe.bind(b0[0], b0[1], ms, dec, voxel_size=s.voxel_size, step_size=0.1 * s.voxel_size, truncation=0.1,
+                  max_distance=10.0, max_depth=10.0, target_rgb=b0[2], target_depth=b0[3], noise=None, seed=7,
+                  weights=CRIT_W, g_emb=single.g_emb, g_dec=single.g_dec, grad_rays=True, defer_loss=False)
+        pipe.args.peer.world = 0                                      # a plain single-GPU step on the same batch
+        pipe.step()
+        torch.cuda.synchronize()
+        C.memmove(C.byref(pipe.args.peer), C.byref(saved_peer), C.sizeof(saved_peer))
+        ref_loss = float(pipe.loss[0])
+        gerr = float((multi_flat - single.flat).abs().max() / single.flat.abs().max().clamp(min=1e-30))
+        check = {"what": "every rank renders rank 0's batch: loss and all-reduced gradient vs one single-GPU step on that batch",
+                 "loss_rel_err": abs(multi_loss - ref_loss) / max(abs(ref_loss), 1e-30), "grad_rel_err": gerr,
+                 "ranks_bit_identical": identical, "ok": bool(abs(multi_loss - ref_loss) <= 1e-5 * abs(ref_loss) and gerr < 1e-4)}
+        # back to this rank's own batch for the stage timings below
+        pipe.bind(dev_in[0], dev_in[1], ms, dec, voxel_size=s.voxel_size, step_size=0.1 * s.voxel_size, truncation=0.1,
+                  max_distance=10.0, max_depth=10.0, target_rgb=dev_in[2], target_depth=dev_in[3], noise=None, seed=1,
+                  weights=CRIT_W, g_emb=g_emb, g_dec=g_dec, grad_rays=True, defer_loss=False)
+        pipe.args.peer.world = 0
+        flat.zero_()
+        pipe.step()
+        torch.cuda.synchronize()
+
+    # ---- every stage alone, events around it (pslam_render_stage): the dominant kernel and the HBM kernels of SURVEY 8(d)
+    prof, extra = {}, {}
+    build = int(os.environ.get("PSLAM_DECODER", "2"))   # include/proud_slam_b200.h: PSLAM_OPT_DECODER
+    tc = (WIDTH == 128 and build == 2)
     if rank == 0:
         pipe.args.flags = pipe.args.flags & ~_lib.F_DEFER_LOSS
-        stage_ms = []
-        for stage_id in range(10 if int(os.environ.get("PSLAM_DECODER", "2")) == 2 else 8):
+        names = ["intersect", "sample", "field_fwd", "composite_fwd", "composite_bwd", "field_bwd"]
+        ids = [0, 1, 2, 3, 4, 5]
+        if tc:
+            names += ["decoder_fwd_kernel", "decoder_bwd_kernel", "tri_gather_kernel", "tri_scatter_kernel"]
+            ids += [8, 9, 10, 11]
+        for name, stage_id in zip(names, ids):
             reps = []
             for it in range(max(3, min(args.steps, 10))):
                 flat.zero_()
                 for k in range(min(stage_id, 5)):        # bring the pipeline to this stage
                     pipe.stage(k)
-                if stage_id == 7:
-                    pipe.stage(6)                        # the wgrad kernel consumes what the dgrad kernel spilled
+                if stage_id == 11:
+                    pipe.stage(5)                        # the scatter consumes the feature-gradient rows of a full backward
                 flush.zero_()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
@@ -344,11 +463,32 @@ def run_gpu(args):
                 b.record()
                 torch.cuda.synchronize()
                 reps.append(a.elapsed_time(b))
-            stage_ms.append(sum(reps[1:]) / max(len(reps) - 1, 1))
-        # field_bwd_dgrad_kernel / _wgrad_kernel: the two halves of the backward stage (scale + chain kernel + scatter; memset +
-        # wgrad kernel + finish); decoder_fwd_kernel / decoder_bwd_kernel: k_field_bf<kFwdSave> / <kBwdSaved> alone
-        prof = dict(zip(["intersect", "sample", "field_fwd", "composite_fwd", "composite_bwd", "field_bwd", "field_bwd_dgrad_kernel",
-                         "field_bwd_wgrad_kernel", "decoder_fwd_kernel", "decoder_bwd_kernel"], stage_ms))
+            prof[name] = sum(reps[1:]) / max(len(reps) - 1, 1)
+        # fused optimizer step that follows the iteration in the mapping loop (reported separately, 8(d))
+        try:
+            from proud_slam_b200.optim import FusedAdam
+            emb_p = torch.nn.Parameter(ms["voxel_vertex_emb"].clone())
+            dec_p = [torch.nn.Parameter(p.clone()) for p in dec]
+            opts = [torch.optim.Adam([emb_p], lr=1e-2), torch.optim.Adam(dec_p, lr=1e-2)]
+            fa = FusedAdam(opts, row_tensors=[emb_p])
+            grads = {emb_p: g_emb, **{p: g for p, g in zip(dec_p, g_dec)}}
+            reps = []
+            for it in range(6):
+                flat.zero_()
+                pipe.step()
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fa.step(grads=grads, zero_grad=True)
+                b.record()
+                torch.cuda.synchronize()
+                reps.append(a.elapsed_time(b))
+            extra["optimizer_ms"] = sum(reps[1:]) / (len(reps) - 1)
+            extra["optimizer"] = ("pslam_adam_step: one launch for the [E,16] table (rows without gradient history skipped) + the 10 decoder "
+                                  "tensors, gradients cleared in the same pass; not part of `value` (SURVEY 8(d): reported separately)")
+        except Exception as e:   # noqa: BLE001
+            extra["optimizer_ms"] = None
+            extra["optimizer"] = f"not measured: {type(e).__name__}: {e}"[:160]
 
     if world > 1:
         t = torch.tensor([ms_step, ms_e2e], device=device, dtype=torch.float64)
@@ -362,68 +502,88 @@ def run_gpu(args):
 
     if rank == 0:
         peaks = measured_peaks()
-        P = counts["n_samples"]
-        build = int(os.environ.get("PSLAM_DECODER", "2"))   # include/proud_slam_b200.h: PSLAM_OPT_DECODER
-        kname, ktext, dtype = {
-            0: ("k_field_tc<bwd>", "tcgen05 3xTF32", "f32 (3xTF32 split, f32 accumulate)"),
-            1: ("k_field<128,bwd>", "fp32 SIMT", "f32"),
-            2: ("k_field_bf<kBwdSaved>", "tcgen05 3xF16", "f16x3 (f16 hi/lo split with power-of-two scales, f32 accumulate)")}[build]
-        # dominant kernel: k_field_tc<bwd> (forward recompute + dgrad chain + trilinear backward + scratch spill);
-        # algorithmic FLOPs = the dgrad GEMMs once (2 MACs P), neither the recompute nor the x3 of the TF32 split
-        flops_bwd = 2.0 * macs_per_sample(WIDTH) * P
-        dom = "decoder_bwd_kernel"
-        if build == 2 and prof["decoder_fwd_kernel"] > prof["decoder_bwd_kernel"]:
-            dom, kname = "decoder_fwd_kernel", "k_field_bf<kFwdSave>"
-        if build != 2:
-            dom = "field_bwd_dgrad_kernel"
-        t_k = prof[dom] * 1e-3
-        achieved = flops_bwd / t_k / 1e12
-        # the other kernels of the decoder, each against its own bound (same measured peaks)
-        others = []
-        if build == 2:
-            for name, key in (("k_field_bf<kFwdSave>", "decoder_fwd_kernel"), ("k_field_bf<kBwdSaved>", "decoder_bwd_kernel")):
-                a = flops_bwd / (prof[key] * 1e-3) / 1e12
-                others.append({"kernel": name, "bound": "tensor", "achieved": a, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                               "frac": a / peaks["bf16_tflops"], "kernel_ms": prof[key]})
-            wg_bytes = 409600.0 / 128.0 * P          # 3.2 kB of pre-split operands per sample
-            a = wg_bytes / (prof["field_bwd_wgrad_kernel"] * 1e-3) / 1e9
-            others.append({"kernel": "k_wgrad_bf (+ memset, k_wgrad_finish: the whole stage is timed)", "bound": "hbm", "achieved": a,
-                           "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": a / peaks["hbm_gbs"], "kernel_ms": prof["field_bwd_wgrad_kernel"],
-                           "traffic": 619.5e6 if (P > 190000 and P < 194000) else None})
+        P, Rh = counts["n_samples"], counts["R_h"]
+        macs = macs_per_sample(WIDTH)
+        ktext, dtype = {
+            0: ("tcgen05 3xTF32", "f32 (3xTF32 split, f32 accumulate)"),
+            1: ("fp32 SIMT", "f32"),
+            2: ("tcgen05 3xF16", "f16x3 (f16 hi/lo split with power-of-two scales, f32 accumulate)")}[build if WIDTH == 128 else 1]
+        hits = int(pipe.hit_count[:R].sum().item())
+        vox = torch.unique(pipe.samp_vox[:P].long())
+        E_t = int(torch.unique(ms["voxel_vertex_idx"][vox].long()).numel())
+        bytes_alg = algorithmic_bytes(R, Rh, P, hits, int(ms["voxel_center_xyz"].shape[0]), E_t)
+        kernels = []
+        if tc:
+            # decoder kernels: algorithmic FLOPs (2 MACs forward, 4 MACs backward = dgrad + wgrad; the 3 split MMAs
+            # per product are NOT counted, so frac <= 1/3 by construction)
+            for name, key, mult in (("k_field_bw (dgrad chain + weight-gradient MMAs, one kernel)", "decoder_bwd_kernel", 4.0),
+                                    ("k_field_pp<kFwdSave> (two tiles in flight)", "decoder_fwd_kernel", 2.0)):
+                fl = mult * macs * P
+                a = fl / (prof[key] * 1e-3) / 1e12
+                kernels.append({"kernel": name, "bound": "tensor", "achieved": a, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                                "frac": a / peaks["bf16_tflops"], "kernel_ms": prof[key], "algorithmic_flops_per_launch": fl,
+                                "traffic": ncu_traffic(name.split(" ")[0].split("<")[0], P)})
+        stage_of = {"K1": "intersect", "K2": "sample", "K3 ": "tri_gather_kernel" if tc else None, "K5 ": "composite_fwd", "K5'": "composite_bwd",
+                    "K3'": "tri_scatter_kernel" if tc else None}
+        hbm_time = 0.0
+        for name, nbytes in bytes_alg.items():
+            key = stage_of[name[:3]]
+            hbm_time += nbytes / (peaks["hbm_gbs"] * 1e9)
+            if key is None or key not in prof:
+                continue
+            a = nbytes / (prof[key] * 1e-3) / 1e9
+            kernels.append({"kernel": name, "bound": "hbm", "achieved": a, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": a / peaks["hbm_gbs"],
+                            "kernel_ms": prof[key], "algorithmic_bytes_per_launch": nbytes, "traffic": None})
+        flops_iter = 6.0 * macs * P
+        t_model = hbm_time + flops_iter / (peaks["bf16_tflops"] * 1e12)
+        dom = kernels[0] if tc else None
+        if dom is None:   # SIMT decoder (width 256 / PSLAM_DECODER=1): the backward stage is the dominant launch group
+            fl = 4.0 * macs * P
+            a = fl / (prof["field_bwd"] * 1e-3) / 1e12
+            dom = {"kernel": f"k_field<{WIDTH},bwd> stage (fp32 SIMT decoder backward + trilinear backward)", "bound": "tensor", "achieved": a,
+                   "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": a / peaks["bf16_tflops"], "kernel_ms": prof["field_bwd"],
+                   "algorithmic_flops_per_launch": fl, "traffic": None}
+        roofline = dict(dom)
+        roofline["peak_source"] = (peaks["source"] + ", dense bf16 burst (the kernel is timed alone); algorithmic FLOPs: every product of the "
+                                   "3xF16 split counted once, so frac <= 1/3 by construction" if tc else peaks["source"] + ", dense bf16 burst")
         value = world * R / (ms_step * 1e-3)
+        # our kernels per mapping iteration: step_begin, intersect, compact | sample | pack (side stream), gather, decoder fwd |
+        # composite fwd, loss reduce (+ backward prologue) | composite bwd, decoder bwd (+ wgrad), scatter (side stream), wgrad
+        # finish = 13 (N > 1 in-kernel exchanges: + all-reduce = 14; NCCL form: + prologue + loss coeffs = 15).  torch's
+        # gradient-buffer fill and NCCL's kernels are not counted; profiles/r02_launches.csv is the launch list.
+        per_step = (13 if world == 1 else (14 if peer is not None else 15)) if tc else 19
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": dtype,
             "data": "synthetic",
-            "config": {"workload": f"{SCENE}: {KEYFRAMES} keyframes x {RAYS_PER_FRAME} rays = {R} rays/iter per GPU, {n_oct} octants "
-                                   f"({n_vox} voxels) at {s.voxel_size:g} m, {E}x16 embeddings, decoder width {WIDTH} ({ktext}), mapping fwd+bwd",
-                       "rays_per_gpu": R, "hit_rays": counts["R_h"], "samples_per_iter_per_gpu": P, "max_samples_per_ray": counts["S"],
+            "config": {"workload": workload_string(SCENE, KEYFRAMES, RAYS_PER_FRAME, R, n_oct, n_vox, s.voxel_size, E, WIDTH),
+                       "decoder_build": ktext,
+                       "rays_per_gpu": R, "hit_rays": Rh, "samples_per_iter_per_gpu": P, "max_samples_per_ray": counts["S"],
+                       "mean_hits_per_ray": hits / max(Rh, 1), "mean_samples_per_ray": P / max(Rh, 1), "touched_embedding_rows": E_t,
                        "total_samples_all_gpus": total_samples, "l2": "flushed (192 MiB write) between timed iterations",
-                       "parallelism": f"dp{world} (rays sharded, map replicated, grads all-reduced)" if world > 1 else "single GPU",
+                       "parallelism": (f"dp{world} (rays sharded by keyframe, map replicated, " + transport + ")") if world > 1 else "single GPU",
                        "loss": loss_val},
             "e2e": {"value": world * R / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(sum(t.numel() * 4 for t in host)), "d2h_bytes_per_step": 64},
-            # our kernels per mapping iteration (3xF16 build): child records, intersect, compact | sample | pack, gather, decoder fwd |
-            # composite fwd, loss reduce | prologue, composite bwd, decoder bwd, scatter, wgrad, wgrad finish = 15 (N > 1: + loss coeffs
-            # = 16; torch's gradient-buffer fill and NCCL not counted; profiles/r01_final_launches.csv)
-            "gpu_launches": args.steps * ((15 if world == 1 else 16) if build == 2 else 19),
+            "gpu_launches": args.steps * per_step,
             "clocks": clocks,
-            "roofline": {"kernel": f"{kname} ({ktext}: " + (("5 layers, activations + ReLU masks spilled for the backward" if dom == "decoder_fwd_kernel" else "dgrad chain from the forward's saved ReLU masks, gradient operands spilled for the wgrad kernel") if build == 2 else "decoder recompute + dgrad, fused trilinear backward, wgrad spill") + ")", "bound": "tensor",
-                         "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
-                         "traffic": NCU_TRAFFIC.get(build) if (P > 190000 and P < 194000) else None,   # dram read+write per launch, ncu --set full (profiles/)
-                         "peak_source": peaks["source"] + ", dense bf16 burst; the kernel issues 3 split MMAs per product"
-                                        + (" (3 hardware FLOPs per algorithmic FLOP, so frac <= 1/3 by construction)" if build == 2 else
-                                           " and recomputes the forward (6 hardware FLOPs per algorithmic FLOP, so frac <= 1/6 by construction)"),
-                         "algorithmic_flops_per_launch": flops_bwd, "kernel_ms": prof[dom]},
-            "roofline_kernels": others,
+            "roofline": roofline,
+            "roofline_kernels": kernels,
+            "iteration_model": {"T_model_ms": t_model * 1e3, "T_measured_ms": ms_step, "ratio": t_model * 1e3 / ms_step,
+                                "algorithmic_flops": flops_iter, "algorithmic_hbm_bytes": sum(bytes_alg.values()),
+                                "note": "SURVEY 8(d): sum over the HBM kernels of bytes/BW + 6 MACs x samples / tensor peak (kernels are dependent)"},
             "stage_ms": prof,
         }
+        line.update(extra)
+        if check is not None:
+            line["exchange_check"] = check
         if world == 1 and not args.no_extras:
             line["tracking"] = tracking_bench(s, ms, dec, device)
         if not args.no_extras:
-            line["cpu_baseline"] = cpu_baseline(s, ms_cpu)
+            line["cpu_baseline"] = cpu_baseline(s, ms_cpu, batch_cpu, WIDTH)
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -497,30 +657,21 @@ def tracking_bench(scene, ms, dec, device, frames=5, iters=30, n_rays=1024):
                     "with the reference's per-iteration host loop; random-init map, so only the timing is meaningful"}
 
 
-def cpu_baseline(s, ms_cpu):
-    """Oracle port timed on the host cores on a bounded sample: BASELINE.json configs[0]-sized batches
-    (2048 rays) of the same scene, fwd + loss + bwd."""
-    import oracle  # noqa: F401
-    from proud_slam_b200 import scene as sc
-    from tests import util
+def cpu_baseline(s, ms_cpu, batch_cpu, width):
+    """Oracle port timed on the host cores on a bounded sample of the SAME workload: whole iterations (fwd + loss + bwd) on the
+    same ray batch, ~10 s."""
     cores = os.cpu_count()
     torch.set_num_threads(cores)
-    ms = {k: v.clone() for k, v in ms_cpu.items()}
-    ms["voxel_vertex_emb"].requires_grad_(True)
-    dec = [p.requires_grad_(True) for p in decoder_params(WIDTH, "cpu")]
-    rays_o, rays_d, rgb, depth = sc.sample_batch(s, [0, 1], 1024, seed=7)
-    rays_o.requires_grad_(True)
-    rays_d.requires_grad_(True)
-    gen = torch.Generator().manual_seed(0)
-    one = lambda: util.oracle_step(rays_o, rays_d, rgb, depth, ms, dec, voxel_size=s.voxel_size, generator=gen)
+    R = batch_cpu[0].shape[0]
+    one = oracle_iteration(s, ms_cpu, batch_cpu, width)
     one()
     n, t0 = 0, time.perf_counter()
     while n < 3 or (time.perf_counter() - t0 < 10.0 and n < 50):
         one()
         n += 1
     dt = (time.perf_counter() - t0) / n
-    return {"value": 2048 / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n} iterations x 2048 rays (2 keyframes x 1024) of the same scene, fwd+loss+bwd, {dt * 1e3:.1f} ms each"}
+    return {"value": R / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} whole iterations of the same {R}-ray batch (oracle port: torch CPU + OpenMP C kernels), {dt * 1e3:.1f} ms each"}
 
 
 def main():
@@ -531,7 +682,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     # sweeps (BASELINE.json configs[3], configs[4]); the defaults are the contract workload, configs[1]
     ap.add_argument("--workload", default=SCENE, choices=["replica_20k", "replica_small", "scannet_large"])
-    ap.add_argument("--rays", type=int, default=KEYFRAMES * RAYS_PER_FRAME, help="rays per GPU and iteration (multiple of 8)")
+    ap.add_argument("--rays", type=int, default=KEYFRAMES * RAYS_PER_FRAME, help="rays per GPU and iteration (with --strong: per iteration over all GPUs)")
+    ap.add_argument("--keyframes", type=int, default=KEYFRAMES, help="keyframes per GPU the rays are drawn from")
+    ap.add_argument("--width", type=int, default=WIDTH, choices=[128, 256], help="decoder width (configs/replica: 128, configs/scannet: 256)")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: --rays is the whole batch, every rank renders 1/N of it")
+    ap.add_argument("--nccl", action="store_true", help="N > 1: NCCL all_gather + all_reduce from the host instead of the in-kernel exchanges")
     ap.add_argument("--no-extras", action="store_true", help="skip the tracking and CPU-baseline legs (sweeps)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -230,7 +230,8 @@ enum {
     PSLAM_C_P = 1,        /* max hits per ray after trimming (P / H) */
     PSLAM_C_NSAMP = 2,    /* total valid samples */
     PSLAM_C_S = 3,        /* max samples per ray (S) */
-    PSLAM_C_OVERFLOW = 4, /* bit 0: sample_cap too small, bit 1: DFS stack overflow, bit 2: decoder operand outside the 3xF16 range */
+    PSLAM_C_OVERFLOW = 4, /* bit 0: sample_cap too small, bit 1: DFS stack overflow, bit 2: decoder operand outside the 3xF16 range,
+                             bit 4 (16): a peer rank did not arrive at a cross-GPU exchange */
     PSLAM_C_TILE = 5,     /* internal work counters */
     PSLAM_C_TILE2 = 6,
     PSLAM_C_STICKY = 7,   /* OR of PSLAM_C_OVERFLOW over all steps since the caller last cleared it, | 8 if a step had no hit ray.
@@ -245,6 +246,25 @@ enum {
     PSLAM_L_TOTAL = 0, PSLAM_L_COLOR = 1, PSLAM_L_DEPTH = 2, PSLAM_L_FS = 3, PSLAM_L_SDF = 4,
     PSLAM_L_COUNT = 16
 };
+
+/* Data-parallel mapping over the GPUs of one box (rays / keyframes sharded, map and decoder replicated; the
+ * reference is single GPU).  Every rank passes the same table: device pointers, valid on THIS device, to every rank's
+ * peer-mapped exchange area (`sync`, pslam_peer_sync_bytes() bytes, zeroed once by its owner) and flat gradient buffer
+ * (`flat`, [flat_count] floats, flat_count % 4 == 0; g_emb / g_dec of the step point into this rank's own copy).  With
+ * world >= 2, pslam_render_step closes the loss over all ranks' raw sums (peer stores + flags inside the loss kernel: no
+ * host-side collective between forward and backward) and, when `flat` is set, ends with a two-shot sum all-reduce of the
+ * flat buffers over NVLink peer memory (csrc/peer.cu).  Every rank must run the same sequence of steps. */
+#define PSLAM_MAX_PEERS 8
+typedef struct {
+    int world, rank;                     /* world <= 1: single GPU, everything below ignored */
+    void *sync[PSLAM_MAX_PEERS];
+    float *flat[PSLAM_MAX_PEERS];        /* all NULL: no gradient all-reduce inside the step */
+    int64_t flat_count;
+} pslam_peer_t;
+int64_t pslam_peer_sync_bytes(void);
+/* The all-reduce alone (sum over ranks, in place in every rank's `flat`); fail_flag: optional device int that gets bit 4
+ * (value 16) if a peer did not arrive within ~2 s. */
+int pslam_peer_allreduce(const pslam_peer_t *peer, int *fail_flag, pslam_stream_t stream);
 
 typedef struct {
     /* sizes */
@@ -301,6 +321,7 @@ typedef struct {
      * chain of the octree walk.  NULL or node_cache_bytes < 128*N: the walk reads the two arrays directly. */
     void *node_cache;
     int64_t node_cache_bytes;
+    pslam_peer_t peer;                     /* multi-GPU exchange tables (world <= 1: unused) */
 } pslam_render_t;
 
 /* sizeof(pslam_render_t) and offsetof(.., loss): lets a binding check its mirror of the struct. */

@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB_PATH = os.path.join(HERE, "libproud_b200.so")
 SOURCES = ["api.cu", "intersect.cu", "sample.cu", "field.cu", "field_tc.cu", "field_bf.cu", "field_pp.cu", "field_bw.cu", "field_w256.cu",
-           "composite.cu", "pose.cu", "optim.cu", "octree_dev.cu", "octree_host.cpp"]
+           "composite.cu", "peer.cu", "pose.cu", "optim.cu", "octree_dev.cu", "octree_host.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--compiler-options", "-fPIC"]
 

@@ -31,6 +31,15 @@ class AdamTensorT(C.Structure):
                                                                                                          ("lr", C.c_float)]
 
 
+MAX_PEERS = 8
+
+
+class PeerT(C.Structure):
+    """pslam_peer_t: every rank's peer-mapped exchange area and flat gradient buffer (include/proud_slam_b200.h)."""
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("sync", C.c_void_p * MAX_PEERS), ("flat", C.c_void_p * MAX_PEERS),
+                ("flat_count", C.c_int64)]
+
+
 class RenderT(C.Structure):
     _fields_ = (
         [(n, C.c_int) for n in ("R", "N", "E", "n_max", "sample_cap", "flags")]
@@ -45,7 +54,8 @@ class RenderT(C.Structure):
                                      "samp_off", "samp_vox", "samp_ray", "samp_z", "samp_dist", "samp_out",
                                      "samp_w", "samp_gout", "ray_out", "scratch_i", "scratch_f", "counters")]
         + [("loss_raw", C.c_void_p), ("loss", C.c_void_p), ("g_emb", C.c_void_p), ("g_dec", DecoderGradT),
-           ("g_rays_o", C.c_void_p), ("g_rays_d", C.c_void_p), ("node_cache", C.c_void_p), ("node_cache_bytes", C.c_int64)]
+           ("g_rays_o", C.c_void_p), ("g_rays_d", C.c_void_p), ("node_cache", C.c_void_p), ("node_cache_bytes", C.c_int64),
+           ("peer", PeerT)]
     )
 
 
@@ -90,6 +100,8 @@ _PROTOTYPES = {
     "pslam_render_scratch_i_count": (C.c_int64, [_I]),
     "pslam_render_scratch_f_count": (C.c_int64, [_I]),
     "pslam_build_node_cache": (C.c_int, [_I, _P, _P, _P, _S]),
+    "pslam_peer_sync_bytes": (C.c_int64, []),
+    "pslam_peer_allreduce": (C.c_int, [C.POINTER(PeerT), _P, _S]),
     "pslam_render_sample": (C.c_int, [C.POINTER(RenderT), _S]),
     "pslam_render_forward": (C.c_int, [C.POINTER(RenderT), _S]),
     "pslam_render_backward": (C.c_int, [C.POINTER(RenderT), _S]),

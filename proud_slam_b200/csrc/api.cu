@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "field_bf.cuh"
+#include "peer.cuh"
 
 namespace pslam {
 
@@ -59,6 +60,11 @@ static int check_render(const pslam_render_t *p)
                         p->samp_ray && p->samp_z && p->samp_dist && p->scratch_i && p->scratch_f && p->counters,
                     PSLAM_E_ARG, "null intermediate buffer");
     PSLAM_CHECK_ARG(p->noise == nullptr || p->noise_stride > 0, PSLAM_E_ARG, "noise_stride must be > 0 with an explicit noise tensor");
+    if (p->peer.world > 1) {
+        PSLAM_CHECK_ARG(p->peer.world <= PSLAM_MAX_PEERS && p->peer.rank >= 0 && p->peer.rank < p->peer.world, PSLAM_E_ARG,
+                        "peer table: world %d / rank %d", p->peer.world, p->peer.rank);
+        for (int q = 0; q < p->peer.world; ++q) PSLAM_CHECK_ARG(p->peer.sync[q], PSLAM_E_ARG, "peer table: null exchange area of rank %d", q);
+    }
     return 0;
 }
 
@@ -189,9 +195,15 @@ extern "C" int pslam_render_step(const pslam_render_t *p, pslam_stream_t stream)
         return PSLAM_E_ARG;
     }
     if (int rc = launch_field_forward(p, st, packed ? 4 : 0)) return rc;
-    if (int rc = launch_composite_forward(p, st)) return rc;
-    if (p->flags & (PSLAM_F_FORWARD_ONLY | PSLAM_F_DEFER_LOSS)) return 0;
-    return pslam_render_backward(p, stream);
+    const bool backward = !(p->flags & (PSLAM_F_FORWARD_ONLY | PSLAM_F_DEFER_LOSS));
+    const bool fold = backward && p->target_rgb && p->target_depth;   // (the loss kernel runs: it takes the backward's prologue along)
+    if (int rc = launch_composite_forward(p, st, fold ? 1 : 0)) return rc;
+    if (!backward) return 0;
+    if (int rc = check_render_field(p, true)) return rc;
+    if (int rc = launch_composite_backward(p, st, fold ? 1 : 0)) return rc;
+    if (int rc = launch_field_backward(p, st)) return rc;
+    if (p->peer.world > 1 && p->peer.flat[0]) return launch_peer_allreduce(&p->peer, p->counters + PSLAM_C_OVERFLOW, st);
+    return 0;
 }
 
 /* sizeof / field offsets so that language bindings can verify their struct mirrors */

@@ -17,6 +17,7 @@
 // gradient w.r.t. every sample's (r,g,b,sdf)).
 #include "common.cuh"
 #include "kernels.h"
+#include "peer.cuh"
 
 namespace pslam {
 
@@ -188,9 +189,14 @@ enum { RAW_COLOR = 0, RAW_FS, RAW_SDF, RAW_D0, RAW_D1, RAW_NFS, RAW_F0, RAW_F1, 
        RAW_DEPTH, RAW_NVALID, RAW_S, RAW_THRESH };
 
 __global__ void __launch_bounds__(1024)
-k_loss_reduce(pslam_render_t p, const float *__restrict__ part_f, const int *__restrict__ part_i, int nblocks)
+k_loss_reduce(pslam_render_t p, const float *__restrict__ part_f, const int *__restrict__ part_i, int nblocks, int prologue)
 {
     pdl_enter();
+    if (prologue) {   // the backward follows in the same step: its prologue (k_bwd_prologue) rides along here
+        if (threadIdx.x == 0) p.counters[PSLAM_C_TILE] = 0;
+        if (p.flags & PSLAM_F_GRAD_RAYS)
+            for (int i = threadIdx.x; i < p.R * 3; i += 1024) { p.g_rays_o[i] = 0.0f; p.g_rays_d[i] = 0.0f; }
+    }
     __shared__ double s_d[32 * 13], s_tot[13];
     __shared__ unsigned s_hist[256];
     __shared__ unsigned s_prefix, s_rank;
@@ -275,7 +281,31 @@ k_loss_reduce(pslam_render_t p, const float *__restrict__ part_f, const int *__r
         raw[RAW_RH] = (double)Rh; raw[RAW_DEPTH] = dsum; raw[RAW_NVALID] = nvalid;
         raw[RAW_S] = (double)p.counters[PSLAM_C_S]; raw[RAW_THRESH] = (double)thresh;
         // single rank: close the loss right here (stage B) instead of a launch of its own
-        if (!(p.flags & PSLAM_F_DEFER_LOSS)) loss_coeffs_body(p, raw, 1);
+        if (!(p.flags & PSLAM_F_DEFER_LOSS) && p.peer.world <= 1) loss_coeffs_body(p, raw, 1);
+    }
+    if (!(p.flags & PSLAM_F_DEFER_LOSS) && p.peer.world > 1) {
+        // all ranks: every rank's raw sums to every rank over NVLink peer memory, then the same closure everywhere (peer.cu)
+        __shared__ unsigned long long s_epoch;
+        __shared__ int s_fail;
+        const int world = p.peer.world, rank = p.peer.rank;
+        PeerSync *mine = static_cast<PeerSync *>(p.peer.sync[rank]);
+        if (tid == 0) { s_epoch = ld_acquire_sys(&mine->epoch_loss) + 1ull; s_fail = 0; __threadfence(); }
+        __syncthreads();
+        const unsigned long long e = s_epoch;
+        const int par = (int)(e & 1ull);
+        if (tid < world * 16) static_cast<PeerSync *>(p.peer.sync[tid >> 4])->rows[par][rank][tid & 15] = p.loss_raw[tid & 15];
+        __threadfence_system();
+        __syncthreads();
+        if (tid < world) {
+            st_release_sys(&static_cast<PeerSync *>(p.peer.sync[tid])->loss_flag[par][rank], e);
+            if (!spin_until(&mine->loss_flag[par][tid], e)) s_fail = 1;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (s_fail) { atomicOr(p.counters + PSLAM_C_OVERFLOW, 16); loss_coeffs_body(p, p.loss_raw, 1); }
+            else loss_coeffs_body(p, &mine->rows[par][0][0], world);
+            st_release_sys(&mine->epoch_loss, e);
+        }
     }
 }
 
@@ -444,7 +474,7 @@ __global__ void k_zero_f(float *__restrict__ a, int n)
     if (i < n) a[i] = 0.0f;
 }
 
-int launch_composite_forward(const pslam_render_t *p, cudaStream_t st)
+int launch_composite_forward(const pslam_render_t *p, cudaStream_t st, int fold_prologue)
 {
     const int nb = ceil_div(p->R, kCompWarps);
     float *part_f = p->scratch_f;                                // [nb,8]
@@ -452,7 +482,7 @@ int launch_composite_forward(const pslam_render_t *p, cudaStream_t st)
     launch_chain(k_composite_fwd, dim3(nb), dim3(kCompThreads), 0, st, *p, part_f, part_i);
     PSLAM_CHECK_LAUNCH("composite_fwd");
     if (p->target_depth && p->target_rgb) {
-        launch_chain(k_loss_reduce, dim3(1), dim3(1024), 0, st, *p, part_f, part_i, nb);
+        launch_chain(k_loss_reduce, dim3(1), dim3(1024), 0, st, *p, part_f, part_i, nb, fold_prologue);
         PSLAM_CHECK_LAUNCH("loss_reduce");
     }
     return 0;
@@ -475,10 +505,12 @@ int launch_composite_backward_ext(const pslam_render_t *p, const float *g_color,
     return 0;
 }
 
-int launch_composite_backward(const pslam_render_t *p, cudaStream_t st)
+int launch_composite_backward(const pslam_render_t *p, cudaStream_t st, int prologue_done)
 {
-    launch_chain(k_bwd_prologue, dim3((p->flags & PSLAM_F_GRAD_RAYS) ? ceil_div(p->R * 3, 256) : 1), dim3(256), 0, st, *p);
-    PSLAM_CHECK_LAUNCH("bwd_prologue");
+    if (!prologue_done) {
+        launch_chain(k_bwd_prologue, dim3((p->flags & PSLAM_F_GRAD_RAYS) ? ceil_div(p->R * 3, 256) : 1), dim3(256), 0, st, *p);
+        PSLAM_CHECK_LAUNCH("bwd_prologue");
+    }
     launch_chain(k_composite_bwd, dim3(ceil_div(p->R, kCompWarps)), dim3(kCompThreads), 0, st, *p);
     PSLAM_CHECK_LAUNCH("composite_bwd");
     return 0;

@@ -735,61 +735,143 @@ __device__ __forceinline__ void sample_position(const FieldParams &p, int s, int
     pz = __fadd_rn(__fdiv_rn(__fsub_rn(zz, __ldg(p.centres + (size_t)vox * 3 + 2)), p.voxel_size), 0.5f);
 }
 
+// A thread quad (one 16-byte quarter of the feature row per thread) walks kTriChunk CONSECUTIVE samples.  Samples are in
+// CSR order by ray and sorted by depth, so ~7 neighbours sit in the same voxel: the quad fetches the voxel's corner ids and
+// rows once per voxel change
+// (the scatter below aggregates the same way, across the lanes of a warp).
+constexpr int kTriChunk = 8;
+
 __global__ void __launch_bounds__(256) k_tri_gather(FieldParams p, float *__restrict__ feat)
 {
     pdl_enter();
     const int nsamp = p.nsamp_dev ? *p.nsamp_dev : p.nsamp;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int s = t >> 2, c = t & 3;
-    if (s >= nsamp) return;
-    int vox, ray;
-    float z, px, py, pz;
-    sample_position(p, s, vox, ray, z, px, py, pz);
-    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int s0 = (t >> 2) * kTriChunk, c = t & 3;
+    if (s0 >= nsamp) return;
+    int cur_vox = -1;
+    float4 v[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int row = __ldg(p.vertex_idx + (size_t)vox * 8 + i);
-        const float wx = (i & 4) ? px : 1.0f - px, wy = (i & 2) ? py : 1.0f - py, wz = (i & 1) ? pz : 1.0f - pz;
-        const float w = (wx * wy) * wz;
-        const float4 v = __ldg(reinterpret_cast<const float4 *>(p.emb + (size_t)row * 16 + c * 4));
-        f.x = fmaf(w, v.x, f.x); f.y = fmaf(w, v.y, f.y); f.z = fmaf(w, v.z, f.z); f.w = fmaf(w, v.w, f.w);
+    for (int i = 0; i < 8; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+    for (int k = 0; k < kTriChunk; ++k) {
+        const int s = s0 + k;
+        if (s >= nsamp) break;
+        int vox, ray;
+        float z, px, py, pz;
+        sample_position(p, s, vox, ray, z, px, py, pz);
+        if (vox != cur_vox) {
+            cur_vox = vox;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row = __ldg(p.vertex_idx + (size_t)vox * 8 + i);
+                v[i] = __ldg(reinterpret_cast<const float4 *>(p.emb + (size_t)row * 16 + c * 4));
+            }
+        }
+        float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float wx = (i & 4) ? px : 1.0f - px, wy = (i & 2) ? py : 1.0f - py, wz = (i & 1) ? pz : 1.0f - pz;
+            const float w = (wx * wy) * wz;
+            f.x = fmaf(w, v[i].x, f.x); f.y = fmaf(w, v[i].y, f.y); f.z = fmaf(w, v[i].z, f.z); f.w = fmaf(w, v[i].w, f.w);
+        }
+        *reinterpret_cast<float4 *>(feat + (size_t)s * 16 + c * 4) = f;
     }
-    *reinterpret_cast<float4 *>(feat + (size_t)s * 16 + c * 4) = f;
 }
 
-__global__ void __launch_bounds__(256) k_tri_scatter(FieldParams p, const float *__restrict__ g_feat)
+// Backward of the lookup with warp-aggregated reductions.  A warp takes 32 consecutive samples:
+//   phase 1  lane = sample: position, the 8 corner weights and the sample's feature-gradient row go to shared memory; with
+//            ray gradients, the lane also takes the 8 dot products <g, corner row> and the per-ray sums are reduced over the
+//            lanes of a ray (a segmented shuffle reduction: a ray's samples are consecutive) before they touch memory;
+//   phase 2  lane = (corner, quarter of the feature row): for every voxel fragment of the 32 samples (~7 consecutive samples
+//            share a voxel) the lane adds up w[k][corner] * g[k][quarter] over the fragment and issues ONE red.v4.
+// The kernel was bound by L2 reductions (32 red.v4 per sample, 6.1 M per mapping iteration); this issues ~5.6 per sample.
+constexpr int kScatWarps = 8, kScatWPitch = 9, kScatGPitch = 20;
+
+__global__ void __launch_bounds__(kScatWarps * 32) k_tri_scatter(FieldParams p, const float *__restrict__ g_feat)
 {
     pdl_enter();
+    __shared__ float s_w[kScatWarps][32 * kScatWPitch];
+    __shared__ __align__(16) float s_g[kScatWarps][32 * kScatGPitch];
     const int nsamp = p.nsamp_dev ? *p.nsamp_dev : p.nsamp;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int s = min(t >> 2, nsamp - 1), c = t & 3;
-    const bool live = (t >> 2) < nsamp;
-    if (nsamp <= 0 || __all_sync(0xffffffffu, !live)) return;     // whole warps leave; partial warps keep their shuffles converged
-    int vox, ray;
-    float z, px, py, pz;
-    sample_position(p, s, vox, ray, z, px, py, pz);
-    const float4 g = __ldg(reinterpret_cast<const float4 *>(g_feat + (size_t)s * 16 + c * 4));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int s0 = (blockIdx.x * kScatWarps + warp) * 32;
+    if (s0 >= nsamp) return;                                  // whole warps leave
+    const int s = s0 + lane;
+    const bool live = s < nsamp;
+    int vox = -1, ray = -1;
+    float z = 0.f, px = 0.f, py = 0.f, pz = 0.f;
+    float4 gq[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) gq[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
+        sample_position(p, s, vox, ray, z, px, py, pz);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) gq[j] = __ldg(reinterpret_cast<const float4 *>(g_feat + (size_t)s * 16 + j * 4));
+    }
+    float *w = s_w[warp], *g = s_g[warp];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) *reinterpret_cast<float4 *>(g + lane * kScatGPitch + j * 4) = gq[j];
     float gp[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const int row = __ldg(p.vertex_idx + (size_t)vox * 8 + i);
         const float wx = (i & 4) ? px : 1.0f - px, wy = (i & 2) ? py : 1.0f - py, wz = (i & 1) ? pz : 1.0f - pz;
-        const float w = (wx * wy) * wz;
-        if (p.grad_emb && live) red_add_v4(p.g_emb + (size_t)row * 16 + c * 4, w * g.x, w * g.y, w * g.z, w * g.w);
-        if (p.grad_rays) {
-            const float4 v = __ldg(reinterpret_cast<const float4 *>(p.emb + (size_t)row * 16 + c * 4));
-            float d = fmaf(g.w, v.w, fmaf(g.z, v.z, fmaf(g.y, v.y, g.x * v.x)));
-            d += __shfl_xor_sync(0xffffffffu, d, 1, 4);
-            d += __shfl_xor_sync(0xffffffffu, d, 2, 4);
+        w[lane * kScatWPitch + i] = (wx * wy) * wz;
+        if (p.grad_rays && live) {
+            const int row = __ldg(p.vertex_idx + (size_t)vox * 8 + i);
+            float d = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(p.emb + (size_t)row * 16 + j * 4));
+                d = fmaf(gq[j].w, v.w, fmaf(gq[j].z, v.z, fmaf(gq[j].y, v.y, fmaf(gq[j].x, v.x, d))));
+            }
             gp[0] += d * ((i & 4) ? 1.0f : -1.0f) * (wy * wz);
             gp[1] += d * ((i & 2) ? 1.0f : -1.0f) * (wx * wz);
             gp[2] += d * ((i & 1) ? 1.0f : -1.0f) * (wx * wy);
         }
     }
-    if (p.grad_rays && live && c < 3) {
-        const float gx = gp[c] / p.voxel_size;
-        atomicAdd(p.g_rays_o + ray * 3 + c, gx);
-        atomicAdd(p.g_rays_d + ray * 3 + c, z * gx);
+    if (p.grad_rays) {
+        // per-ray sums over the lanes of a ray: after the sweep the first lane of every ray fragment holds its total
+        float so[3], sd[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { so[a] = gp[a] / p.voxel_size; sd[a] = z * so[a]; }
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int r2 = __shfl_down_sync(0xffffffffu, ray, o);
+            const bool take = (lane + o < 32) && r2 == ray;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float x = __shfl_down_sync(0xffffffffu, so[a], o), y = __shfl_down_sync(0xffffffffu, sd[a], o);
+                if (take) { so[a] += x; sd[a] += y; }
+            }
+        }
+        const int rprev = __shfl_up_sync(0xffffffffu, ray, 1);
+        if (live && (lane == 0 || rprev != ray)) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                atomicAdd(p.g_rays_o + ray * 3 + a, so[a]);
+                atomicAdd(p.g_rays_d + ray * 3 + a, sd[a]);
+            }
+        }
+    }
+    if (!p.grad_emb) return;
+    const int vprev = __shfl_up_sync(0xffffffffu, vox, 1), rprev2 = __shfl_up_sync(0xffffffffu, ray, 1);
+    unsigned heads = __ballot_sync(0xffffffffu, live && (lane == 0 || vprev != vox || rprev2 != ray));
+    const int nlive = __popc(__ballot_sync(0xffffffffu, live));
+    __syncwarp();
+    const int ci = lane >> 2, cq = lane & 3;
+    while (heads) {
+        const int start = __ffs(heads) - 1;
+        heads &= heads - 1;
+        const int end = heads ? __ffs(heads) - 1 : nlive;
+        const int vf = __shfl_sync(0xffffffffu, vox, start);
+        const int row = __ldg(p.vertex_idx + (size_t)vf * 8 + ci);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = start; k < end; ++k) {
+            const float wk = w[k * kScatWPitch + ci];
+            const float4 gk = *reinterpret_cast<const float4 *>(g + k * kScatGPitch + cq * 4);
+            acc.x = fmaf(wk, gk.x, acc.x); acc.y = fmaf(wk, gk.y, acc.y); acc.z = fmaf(wk, gk.z, acc.z); acc.w = fmaf(wk, gk.w, acc.w);
+        }
+        red_add_v4(p.g_emb + (size_t)row * 16 + cq * 4, acc.x, acc.y, acc.z, acc.w);
     }
 }
 
@@ -1145,7 +1227,7 @@ static bool split_trilinear(const FieldParams &fp, int max_samples)
 static int launch_tri_gather(FieldParams &fp, int max_samples, cudaStream_t st)
 {
     float *feat = scratch_feat(fp, max_samples, 0);
-    launch_chain(k_tri_gather, dim3((int)ceil_div64((int64_t)(max_samples > 0 ? max_samples : 1) * 4, 256)), dim3(256), 0, st, fp, feat);
+    launch_chain(k_tri_gather, dim3((int)ceil_div64(ceil_div64(max_samples > 0 ? max_samples : 1, kTriChunk) * 4, 256)), dim3(256), 0, st, fp, feat);
     PSLAM_CHECK_LAUNCH("tri_gather");
     fp.feat = feat;
     return 0;
@@ -1283,7 +1365,7 @@ int bf_launch_field_backward(const FieldParams &fp_in, int max_samples, cudaStre
     if (gmax_known) fp.gscale = fp.gmax_ready;          // k_composite_bwd published max |g_out| while it wrote g_out
     if (part == 4) {   // profiling: the trilinear scatter alone, on the feature-gradient rows of the previous full backward
         if (!split_trilinear(fp, max_samples) || !(fp.grad_emb || fp.grad_rays)) return 0;
-        k_tri_scatter<<<(int)ceil_div64((int64_t)(max_samples > 0 ? max_samples : 1) * 4, 256), 256, 0, st>>>(fp, scratch_feat(fp, max_samples, 1));
+        k_tri_scatter<<<(int)ceil_div64(max_samples > 0 ? max_samples : 1, kScatWarps * 32), kScatWarps * 32, 0, st>>>(fp, scratch_feat(fp, max_samples, 1));
         PSLAM_CHECK_LAUNCH("tri_scatter");
         return 0;
     }
@@ -1327,7 +1409,7 @@ int bf_launch_field_backward(const FieldParams &fp_in, int max_samples, cudaStre
                 }
                 ss = side->stream;
             }
-            k_tri_scatter<<<(int)ceil_div64((int64_t)(max_samples > 0 ? max_samples : 1) * 4, 256), 256, 0, ss>>>(fps, fp.g_feat);
+            k_tri_scatter<<<(int)ceil_div64(max_samples > 0 ? max_samples : 1, kScatWarps * 32), kScatWarps * 32, 0, ss>>>(fps, fp.g_feat);
             PSLAM_CHECK_LAUNCH("tri_scatter");
             if (side) {
                 if (cudaEventRecord(side->join, side->stream) != cudaSuccess) { set_error("field_bf: stream join: %s", cudaGetErrorString(cudaGetLastError())); return PSLAM_E_ARG; }

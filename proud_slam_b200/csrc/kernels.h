@@ -22,8 +22,8 @@ int launch_field_forward(const pslam_render_t *p, cudaStream_t st, int part = 0)
 int fork_decoder_pack(const pslam_render_t *p, cudaStream_t st, cudaEvent_t *packed);   // then launch_field_forward(..., part 4) after waiting for *packed
 int launch_field_backward(const pslam_render_t *p, cudaStream_t st, int part = 0);  // part 1/2: dgrad / wgrad stage only, 3: the dgrad kernel only
 // composite.cu (SDF->weights compositing + loss)
-int launch_composite_forward(const pslam_render_t *p, cudaStream_t st);
-int launch_composite_backward(const pslam_render_t *p, cudaStream_t st);
+int launch_composite_forward(const pslam_render_t *p, cudaStream_t st, int fold_prologue = 0);   // fold_prologue: the loss kernel also does the backward's prologue
+int launch_composite_backward(const pslam_render_t *p, cudaStream_t st, int prologue_done = 0);
 int launch_composite_backward_ext(const pslam_render_t *p, const float *g_color, const float *g_depth, const float *g_sdf,
                                   const float *g_weight, cudaStream_t st);
 int launch_loss_coeffs(const pslam_render_t *p, const double *rows, int nrows, cudaStream_t st);

@@ -10,8 +10,12 @@ to one big batch (up to fp32 re-association):
 2. after backward, one sum-all-reduce of a single flat fp32 buffer ``[E*16 | decoder]`` that the
    kernels scattered their gradients straight into (no staging copy before the collective).
 
-``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests) is the plumbing.
+``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests) is the plumbing.  On the GPUs of one box both exchanges run
+inside ``pslam_render_step`` over NVLink peer memory (``PeerExchange`` below, ``csrc/peer.cu``): the loss kernel stores its raw
+sums into every peer and waits for theirs, and a two-shot kernel all-reduces the flat buffer -- no host-side collective in
+the iteration.  ``DataParallelStep`` is the NCCL form of the same protocol (any transport, also the gloo tests).
 """
+import ctypes as C
 from typing import List, Sequence
 
 import torch
@@ -41,10 +45,18 @@ def shard_rays(tensors: Sequence[torch.Tensor], rank: int, world: int):
 class FlatGrads:
     """One flat fp32 buffer ``[E*16 | decoder params]`` with views for the kernels to write into."""
 
-    def __init__(self, emb: torch.Tensor, dec_params: Sequence[torch.Tensor]):
+    @staticmethod
+    def numel(emb: torch.Tensor, dec_params: Sequence[torch.Tensor]) -> int:
+        pad4 = lambda k: (k + 3) // 4 * 4
+        return pad4(emb.numel()) + sum(pad4(p.numel()) for p in dec_params)
+
+    def __init__(self, emb: torch.Tensor, dec_params: Sequence[torch.Tensor], flat: torch.Tensor = None):
+        """``flat``: storage to use (e.g. ``PeerExchange.flat``, peer-mapped); allocated here when None."""
         pad4 = lambda k: (k + 3) // 4 * 4      # every segment starts 16-byte aligned (vector reductions)
-        n = pad4(emb.numel()) + sum(pad4(p.numel()) for p in dec_params)
-        self.flat = torch.zeros(n, dtype=torch.float32, device=emb.device)
+        n = self.numel(emb, dec_params)
+        if flat is not None and (flat.numel() != n or flat.dtype != torch.float32 or flat.device != emb.device):
+            raise RuntimeError(f"flat gradient buffer must hold {n} float32 on {emb.device}")
+        self.flat = torch.zeros(n, dtype=torch.float32, device=emb.device) if flat is None else flat
         self.g_emb = self.flat[: emb.numel()].view_as(emb)
         self.g_dec, off = [], pad4(emb.numel())
         for p in dec_params:
@@ -53,6 +65,53 @@ class FlatGrads:
 
     def zero_(self):
         self.flat.zero_()
+
+
+class PeerExchange:
+    """Peer-mapped buffers of one rank for the in-kernel exchanges (``pslam_peer_t``): the flat gradient buffer and the small
+    exchange area, allocated as torch symmetric memory (CUDA VMM allocations every rank of the group maps) and rendezvoused
+    over the process group.  ``bind(pipe)`` puts the table into a bound ``RenderPipeline``: from then on ``pipe.step()`` is a
+    whole data-parallel iteration.  Collective: every rank of ``group`` must construct it (same ``flat_numel``)."""
+
+    def __init__(self, flat_numel: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        group = dist.group.WORLD if group is None else group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > _lib.MAX_PEERS:
+            raise RuntimeError(f"PeerExchange supports up to {_lib.MAX_PEERS} ranks (one box)")
+        if flat_numel % 4:
+            raise RuntimeError("flat_numel must be a multiple of 4 (FlatGrads.numel pads its segments)")
+        lib = _lib.lib()
+        nsync = int(lib.pslam_peer_sync_bytes())
+        self.flat = symm_mem.empty(int(flat_numel), dtype=torch.float32, device=device)
+        self.sync = symm_mem.empty((nsync + 7) // 8, dtype=torch.int64, device=device)
+        self.flat.zero_()
+        self.sync.zero_()
+        torch.cuda.synchronize(device)
+        self._h_flat = symm_mem.rendezvous(self.flat, group)
+        self._h_sync = symm_mem.rendezvous(self.sync, group)
+        dist.barrier(group)                    # every rank's exchange area is zero before anybody raises a flag in it
+        self.table = _lib.PeerT()
+        self.table.world, self.table.rank, self.table.flat_count = self.world, self.rank, int(flat_numel)
+        for q in range(self.world):
+            self.table.sync[q] = int(self._h_sync.buffer_ptrs[q])
+            self.table.flat[q] = int(self._h_flat.buffer_ptrs[q])
+        self.fail = torch.zeros(1, dtype=torch.int32, device=device)
+        self._lib, self._stream_ptr, self.device = lib, _lib.stream_ptr, torch.device(device)
+
+    def bind(self, pipe, allreduce=True):
+        """Installs the table in ``pipe.args`` (after ``pipe.bind``); allreduce=False: loss closure only."""
+        C.memmove(C.byref(pipe.args.peer), C.byref(self.table), C.sizeof(self.table))
+        if not allreduce:
+            for q in range(self.world):
+                pipe.args.peer.flat[q] = None
+        return pipe
+
+    def allreduce(self):
+        """Sum of every rank's ``flat`` into every rank's ``flat`` (the kernel ``pslam_render_step`` ends with, on its own)."""
+        from . import _lib
+        _lib.check(self._lib.pslam_peer_allreduce(C.byref(self.table), _lib.ptr(self.fail), self._stream_ptr(self.device)), "pslam_peer_allreduce")
 
 
 class DataParallelStep:
