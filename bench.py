@@ -523,7 +523,7 @@ def run_gpu(args):
                 kernels.append({"kernel": name, "bound": "tensor", "achieved": a, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                                 "frac": a / peaks["bf16_tflops"], "kernel_ms": prof[key], "algorithmic_flops_per_launch": fl,
                                 "traffic": ncu_traffic(name.split(" ")[0].split("<")[0], P)})
-        stage_of = {"K1": "intersect", "K2": "sample", "K3 ": "tri_gather_kernel" if tc else None, "K5 ": "composite_fwd", "K5'": "composite_bwd",
+        stage_of = {"K1 ": "intersect", "K2 ": "sample", "K3 ": "tri_gather_kernel" if tc else None, "K5 ": "composite_fwd", "K5'": "composite_bwd",
                     "K3'": "tri_scatter_kernel" if tc else None}
         hbm_time = 0.0
         for name, nbytes in bytes_alg.items():

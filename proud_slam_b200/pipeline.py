@@ -247,6 +247,8 @@ class RenderPipeline:
                                "(|16 x value| >= 32752); select the 3xTF32 build: pslam_set_option(PSLAM_OPT_DECODER, 0)")
         if c[C_OVERFLOW] & 2:
             raise RuntimeError("octree traversal stack overflow (the reference asserts here, intersect_gpu.cu:235)")
+        if c[C_OVERFLOW] & 16:
+            raise RuntimeError("a peer rank did not arrive at a cross-GPU exchange (csrc/peer.cu)")
         return dict(R_h=c[C_RH], P=c[C_P], n_samples=c[C_NSAMP], S=c[C_S])
 
     # ------------------------------------------------------------------ flags of a whole loop of steps
@@ -256,6 +258,9 @@ class RenderPipeline:
                                "dropped; build the pipeline with a larger samples_per_ray")
         if bits & 2:
             raise RuntimeError("octree traversal stack overflow (the reference asserts here, intersect_gpu.cu:235)")
+        if bits & 16:
+            raise RuntimeError("a peer rank did not arrive at a cross-GPU exchange of one of the last steps (csrc/peer.cu gives up after "
+                               "~2 s): the ranks no longer run the same sequence of steps")
         if bits & 8:
             raise AssertionError("no ray hits the map")          # the reference's assert, render_helpers.py:388
         if bits & 4:
