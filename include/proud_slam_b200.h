@@ -202,6 +202,8 @@ int pslam_decoder_fwd(int p, const pslam_decoder_t *dec, const float *feat,
 /* wgrad_ws: pslam_wgrad_ws_bytes(p) bytes of scratch for the tensor-core weight-gradient kernel
  * (width 128), or NULL to run the SIMT build when parameter gradients are requested. */
 int64_t pslam_wgrad_ws_bytes(int max_samples);
+/* ... for a given decoder width (256: the workspace of csrc/field_w256.cu, 7.3 kB per sample) */
+int64_t pslam_wgrad_ws_bytes_w(int max_samples, int width);
 int pslam_decoder_bwd(int p, const pslam_decoder_t *dec, const float *feat,
                       float *ws, const float *g_out, float *g_feat,
                       const pslam_decoder_grad_t *grad, void *wgrad_ws, int64_t wgrad_ws_bytes,

@@ -95,6 +95,7 @@ _PROTOTYPES = {
     "pslam_decoder_fwd": (C.c_int, [_I, C.POINTER(DecoderT), _P, _P, _P, _S]),
     "pslam_decoder_bwd": (C.c_int, [_I, C.POINTER(DecoderT), _P, _P, _P, _P, C.POINTER(DecoderGradT), _P, C.c_int64, _S]),
     "pslam_wgrad_ws_bytes": (C.c_int64, [_I]),
+    "pslam_wgrad_ws_bytes_w": (C.c_int64, [_I, _I]),
     "pslam_render_sizeof": (C.c_int, []),
     "pslam_render_offsetof_loss": (C.c_int, []),
     "pslam_render_scratch_i_count": (C.c_int64, [_I]),

@@ -727,9 +727,11 @@ static int pack_decoder(const pslam_decoder_t &d, float *ws, cudaStream_t st, bo
     }
     if (d.width == 128 && decoder_mode() == 0) return tc_pack_decoder(d, ws + FieldCfg<128>::WS, st);
     if (d.width == 128 && decoder_mode() == 2) return bf_pack_decoder(d, ws + FieldCfg<128>::WS, st, range_flag);
+    if (d.width == 256 && decoder_mode() == 2) return w2_pack_decoder(d, ws + FieldCfg<256>::WS, st, range_flag);
     return 0;
 }
-static const float *tc_region(const pslam_decoder_t &d, const float *ws) { return d.width == 128 ? ws + FieldCfg<128>::WS : nullptr; }
+static_assert(FieldCfg<256>::WS == kSimt256Floats, "field.cuh: kSimt256Floats");
+static const float *tc_region(const pslam_decoder_t &d, const float *ws) { return ws + (d.width == 128 ? FieldCfg<128>::WS : FieldCfg<256>::WS); }
 
 static int launch_field(const FieldParams &fp, bool bwd, int max_samples, cudaStream_t st, int part = 0)
 {
@@ -745,6 +747,8 @@ static int launch_field(const FieldParams &fp, bool bwd, int max_samples, cudaSt
             return bf_launch_field_backward(fp, max_samples, st, part);
     }
     if (fp.dec.width == 128) return bwd ? launch_field_t<128, true>(fp, max_samples, st) : launch_field_t<128, false>(fp, max_samples, st);
+    if (decoder_mode() == 2 && w2_usable(fp, max_samples, bwd))
+        return bwd ? w2_launch_field_backward(fp, max_samples, st, part) : w2_launch_field_forward(fp, max_samples, st, part);
     return bwd ? launch_field_t<256, true>(fp, max_samples, st) : launch_field_t<256, false>(fp, max_samples, st);
 }
 
@@ -823,7 +827,7 @@ static int check_decoder(const pslam_decoder_t *dec)
 
 extern "C" int64_t pslam_decoder_ws_count(int width)
 {
-    return width == 128 ? FieldCfg<128>::WS + kTcPackFloats : width == 256 ? FieldCfg<256>::WS : -1;
+    return width == 128 ? FieldCfg<128>::WS + kTcPackFloats : width == 256 ? FieldCfg<256>::WS + kW2PackFloats : -1;
 }
 
 extern "C" int pslam_trilinear_fwd(int np, const float *xyz, const int *vox_idx, const float *centres, const int *vertex_idx,
@@ -861,6 +865,12 @@ extern "C" int pslam_decoder_fwd(int np, const pslam_decoder_t *dec, const float
     FieldParams fp{};
     fp.nsamp = np; fp.feat = feat; fp.dec = *dec; fp.ws = ws; fp.ws_tc = tc_region(*dec, ws); fp.out = out;
     return launch_field(fp, false, np, (cudaStream_t)stream);
+}
+
+extern "C" int64_t pslam_wgrad_ws_bytes_w(int max_samples, int width)
+{
+    if (width == 256) return (int64_t)w2_scratch_bytes(max_samples);
+    return pslam_wgrad_ws_bytes(max_samples);
 }
 
 extern "C" int64_t pslam_wgrad_ws_bytes(int max_samples)

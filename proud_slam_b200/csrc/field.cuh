@@ -61,6 +61,18 @@ int bf_launch_field_forward(const FieldParams &fp, int max_samples, cudaStream_t
 int bf_launch_field_backward(const FieldParams &fp, int max_samples, cudaStream_t st, int part = 0);
 size_t bf_wgrad_scratch_bytes(int max_samples);
 void bf_set_save_activations(int on);   // PSLAM_OPT_SAVE_ACT
+// stand-alone trilinear stages over feature rows [P,16] (field_bf.cu), shared with the width-256 build
+int launch_tri_gather_rows(const FieldParams &fp, float *feat, int max_samples, cudaStream_t st);
+int launch_tri_scatter_rows(const FieldParams &fp, const float *g_feat, int max_samples, cudaStream_t st);
+int launch_grad_scale(const FieldParams &fp, uint32_t *gscale, cudaStream_t st);
+// field_w256.cu: 3xF16 tcgen05 build of the width-256 decoder (forward, dgrad chain, weight gradients)
+constexpr int kSimt256Floats = 256 * 256 + 288 * 256;   // floats of the SIMT pack of the width-256 decoder (FieldCfg<256>::WS); the stream follows it
+constexpr int kW2PackFloats = 278528 + 16;              // f16 hi / lo weight stream of field_w256.cu
+int w2_pack_decoder(const pslam_decoder_t &d, float *ws_tc, cudaStream_t st, int *range_flag = nullptr);
+bool w2_usable(const FieldParams &fp, int max_samples, bool bwd);
+int w2_launch_field_forward(const FieldParams &fp, int max_samples, cudaStream_t st, int part = 0);
+int w2_launch_field_backward(const FieldParams &fp, int max_samples, cudaStream_t st, int part = 0);
+size_t w2_scratch_bytes(int max_samples);
 struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
 SideStream *side_stream();            // one non-blocking side stream + fork / join events per device (field_bf.cu)
 

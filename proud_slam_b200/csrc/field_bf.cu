@@ -1332,6 +1332,27 @@ int bf_launch_field_forward(const FieldParams &fp_in, int max_samples, cudaStrea
     return 0;
 }
 
+int launch_tri_gather_rows(const FieldParams &fp, float *feat, int max_samples, cudaStream_t st)
+{
+    launch_chain(k_tri_gather, dim3((int)ceil_div64(ceil_div64(max_samples > 0 ? max_samples : 1, kTriChunk) * 4, 256)), dim3(256), 0, st, fp, feat);
+    PSLAM_CHECK_LAUNCH("tri_gather");
+    return 0;
+}
+int launch_tri_scatter_rows(const FieldParams &fp, const float *g_feat, int max_samples, cudaStream_t st)
+{
+    k_tri_scatter<<<(int)ceil_div64(max_samples > 0 ? max_samples : 1, kScatWarps * 32), kScatWarps * 32, 0, st>>>(fp, g_feat);
+    PSLAM_CHECK_LAUNCH("tri_scatter");
+    return 0;
+}
+int launch_grad_scale(const FieldParams &fp, uint32_t *gscale, cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(gscale, 0, sizeof(uint32_t), st);
+    if (e != cudaSuccess) { set_error("grad_scale: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
+    k_grad_scale<<<num_sms(), 256, 0, st>>>(reinterpret_cast<const float4 *>(fp.g_out), fp.nsamp, fp.nsamp_dev, gscale);
+    PSLAM_CHECK_LAUNCH("grad_scale");
+    return 0;
+}
+
 // one non-blocking side stream + fork / join events per device (created on first use, never destroyed)
 SideStream *side_stream()
 {

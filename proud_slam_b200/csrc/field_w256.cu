@@ -17,6 +17,7 @@
 // column sums), each role walking its share of the tiles with its accumulators resident and flushing once with red.v4.
 #include "field_bf.cuh"
 #include "kernels.h"
+#include <mutex>
 #include <type_traits>
 
 namespace pslam {
@@ -55,7 +56,7 @@ constexpr int oHead = oW30 + 4 * 256;                          // [128 rows][4]:
 constexpr int kWSmem = oHead + 4 * 128 * 4;
 static_assert(kWSmem <= 232448, "shared memory budget");
 // scratch of one tile: 128-feature operand blocks of 64 kB in the order below, then F and G5 (8 kB each)
-constexpr int oH1 = 0, oH2 = 2, oHC = 4, oT = 6, oG1 = 7, oG2 = 9, oG4 = 11, oGt = 13, kBlocks = 14;
+constexpr int bH1 = 0, bH2 = 2, bHC = 4, bT = 6, bG1 = 7, bG2 = 9, bG4 = 11, bGt = 13, kBlocks = 14;
 constexpr size_t oFsm = (size_t)kBlocks * kOpBytes, oG5sm = oFsm + kSmallBytes, kWTile = oG5sm + kSmallBytes;
 constexpr int kWMaskBytes = 3 * 2 * 4 * 128 * 4;               // [layer h1, h2, hc][column half][32-column word][row]
 constexpr size_t kFeatTile = 128 * 16 * sizeof(float);
@@ -345,7 +346,7 @@ k_field_w256(FieldParams p, const unsigned char *__restrict__ wstream)
             auto stg_of = [&](int op) -> unsigned char * { return scr ? scr + (size_t)op * kOpBytes + rowoff_big : nullptr; };
             uint32_t *mk = (p.act_masks && real_tile) ? p.act_masks + (size_t)tile * (kWMaskBytes / 4) + h * 512 + m : nullptr;   // [layer][half][word][row]
             if constexpr (kIsFwd) {
-                uint32_t m1[4], m2[4], mc[4];
+                uint32_t m1[4] = {0u, 0u, 0u, 0u}, m2[4] = {0u, 0u, 0u, 0u}, mc[4] = {0u, 0u, 0u, 0u};
                 // ---- features -> shared-memory A operand (x16, hi / lo); the lead thread of a row does it ----
                 if (lead) {
                     float f[16];
@@ -383,8 +384,8 @@ k_field_w256(FieldParams p, const unsigned char *__restrict__ wstream)
                 for (int w = 0; w < 4; ++w) {
                     uint32_t mw = 0u;
                     const int f0 = 128 * h + 32 * w;
-                    w2_epi16<0, 0>(tg, f0, f0, sBias, mw, 0, stg_of(oH1 + h), 32 * w, ymax, nullptr, nullptr, 0.f);
-                    w2_epi16<0, 0>(tg, f0 + 16, f0 + 16, sBias, mw, 16, stg_of(oH1 + h), 32 * w + 16, ymax, nullptr, nullptr, 0.f);
+                    w2_epi16<0, 0>(tg, f0, f0, sBias, mw, 0, stg_of(bH1 + h), 32 * w, ymax, nullptr, nullptr, 0.f);
+                    w2_epi16<0, 0>(tg, f0 + 16, f0 + 16, sBias, mw, 16, stg_of(bH1 + h), 32 * w + 16, ymax, nullptr, nullptr, 0.f);
                     m1[0] = w == 0 ? mw : m1[0]; m1[1] = w == 1 ? mw : m1[1]; m1[2] = w == 2 ? mw : m1[2]; m1[3] = w == 3 ? mw : m1[3];
                 }
                 a_is_ready();
@@ -394,8 +395,8 @@ k_field_w256(FieldParams p, const unsigned char *__restrict__ wstream)
                 for (int w = 0; w < 4; ++w) {
                     uint32_t mw = 0u;
                     const int f0 = 128 * h + 32 * w;
-                    w2_epi16<0, 1>(tg, f0, f0, sBias + 256, mw, 0, stg_of(oH2 + h), 32 * w, ymax, sW30, sdf_acc, 0.f);
-                    w2_epi16<0, 1>(tg, f0 + 16, f0 + 16, sBias + 256, mw, 16, stg_of(oH2 + h), 32 * w + 16, ymax, sW30, sdf_acc, 0.f);
+                    w2_epi16<0, 1>(tg, f0, f0, sBias + 256, mw, 0, stg_of(bH2 + h), 32 * w, ymax, sW30, sdf_acc, 0.f);
+                    w2_epi16<0, 1>(tg, f0 + 16, f0 + 16, sBias + 256, mw, 16, stg_of(bH2 + h), 32 * w + 16, ymax, sW30, sdf_acc, 0.f);
                     m2[0] = w == 0 ? mw : m2[0]; m2[1] = w == 1 ? mw : m2[1]; m2[2] = w == 2 ? mw : m2[2]; m2[3] = w == 3 ? mw : m2[3];
                 }
                 a_is_ready();
@@ -404,8 +405,8 @@ k_field_w256(FieldParams p, const unsigned char *__restrict__ wstream)
 #pragma unroll 1
                 for (int w = 0; w < 2; ++w) {
                     const int f0 = 64 * h + 32 * w;
-                    w2_epi16<1, 0>(tg, f0, f0, sBias + 512, nomask, 0, stg_of(oT), f0, ymax, nullptr, nullptr, 0.f);
-                    w2_epi16<1, 0>(tg, f0 + 16, f0 + 16, sBias + 512, nomask, 0, stg_of(oT), f0 + 16, ymax, nullptr, nullptr, 0.f);
+                    w2_epi16<1, 0>(tg, f0, f0, sBias + 512, nomask, 0, stg_of(bT), f0, ymax, nullptr, nullptr, 0.f);
+                    w2_epi16<1, 0>(tg, f0 + 16, f0 + 16, sBias + 512, nomask, 0, stg_of(bT), f0 + 16, ymax, nullptr, nullptr, 0.f);
                 }
                 a_is_ready();
                 // ---- hc + colour head ----
@@ -414,8 +415,8 @@ k_field_w256(FieldParams p, const unsigned char *__restrict__ wstream)
                 for (int w = 0; w < 4; ++w) {
                     uint32_t mw = 0u;
                     const int f0 = 128 * h + 32 * w;
-                    w2_epi16<0, 2>(tg, f0, f0, sBias + 640, mw, 0, stg_of(oHC + h), 32 * w, ymax, sW5, head, 0.f);
-                    w2_epi16<0, 2>(tg, f0 + 16, f0 + 16, sBias + 640, mw, 16, stg_of(oHC + h), 32 * w + 16, ymax, sW5, head, 0.f);
+                    w2_epi16<0, 2>(tg, f0, f0, sBias + 640, mw, 0, stg_of(bHC + h), 32 * w, ymax, sW5, head, 0.f);
+                    w2_epi16<0, 2>(tg, f0 + 16, f0 + 16, sBias + 640, mw, 16, stg_of(bHC + h), 32 * w + 16, ymax, sW5, head, 0.f);
                     mc[0] = w == 0 ? mw : mc[0]; mc[1] = w == 1 ? mw : mc[1]; mc[2] = w == 2 ? mw : mc[2]; mc[3] = w == 3 ? mw : mc[3];
                 }
                 // the two threads of a row combine their head sums
@@ -464,7 +465,7 @@ k_field_w256(FieldParams p, const unsigned char *__restrict__ wstream)
                 }
                 {
                     // g_hc = mask_hc . (W5^T g5) on the CUDA cores -> A (+ G4 block h)
-                    unsigned char *stg = stg_of(oG4 + h);
+                    unsigned char *stg = stg_of(bG4 + h);
 #pragma unroll 1
                     for (int j = 0; j < 8; ++j) {
                         const int c0 = 128 * h + 16 * j;
@@ -505,8 +506,8 @@ k_field_w256(FieldParams p, const unsigned char *__restrict__ wstream)
 #pragma unroll 1
                 for (int w = 0; w < 2; ++w) {
                     const int f0 = 64 * h + 32 * w;
-                    w2_epi16<3, 0>(tg, 128 + f0, f0, nullptr, nomask, 0, stg_of(oGt), f0, ymax, nullptr, nullptr, 0.f);
-                    w2_epi16<3, 0>(tg, 128 + f0 + 16, f0 + 16, nullptr, nomask, 0, stg_of(oGt), f0 + 16, ymax, nullptr, nullptr, 0.f);
+                    w2_epi16<3, 0>(tg, 128 + f0, f0, nullptr, nomask, 0, stg_of(bGt), f0, ymax, nullptr, nullptr, 0.f);
+                    w2_epi16<3, 0>(tg, 128 + f0 + 16, f0 + 16, nullptr, nomask, 0, stg_of(bGt), f0 + 16, ymax, nullptr, nullptr, 0.f);
                 }
                 a_is_ready();
                 // ---- g_h2 (+ the sdf head's rank-1 term) ----
@@ -516,8 +517,8 @@ k_field_w256(FieldParams p, const unsigned char *__restrict__ wstream)
                     uint32_t mw = m2[0];
                     mw = w == 1 ? m2[1] : mw; mw = w == 2 ? m2[2] : mw; mw = w == 3 ? m2[3] : mw;
                     const int f0 = 128 * h + 32 * w;
-                    w2_epi16<2, 3>(tg, f0, f0, nullptr, mw, 0, stg_of(oG2 + h), 32 * w, ymax, sW30, nullptr, go.w);
-                    w2_epi16<2, 3>(tg, f0 + 16, f0 + 16, nullptr, mw, 16, stg_of(oG2 + h), 32 * w + 16, ymax, sW30, nullptr, go.w);
+                    w2_epi16<2, 3>(tg, f0, f0, nullptr, mw, 0, stg_of(bG2 + h), 32 * w, ymax, sW30, nullptr, go.w);
+                    w2_epi16<2, 3>(tg, f0 + 16, f0 + 16, nullptr, mw, 16, stg_of(bG2 + h), 32 * w + 16, ymax, sW30, nullptr, go.w);
                 }
                 a_is_ready();
                 // ---- g_h1 ----
@@ -527,8 +528,8 @@ k_field_w256(FieldParams p, const unsigned char *__restrict__ wstream)
                     uint32_t mw = m1[0];
                     mw = w == 1 ? m1[1] : mw; mw = w == 2 ? m1[2] : mw; mw = w == 3 ? m1[3] : mw;
                     const int f0 = 128 * h + 32 * w;
-                    w2_epi16<2, 0>(tg, f0, f0, nullptr, mw, 0, stg_of(oG1 + h), 32 * w, ymax, nullptr, nullptr, 0.f);
-                    w2_epi16<2, 0>(tg, f0 + 16, f0 + 16, nullptr, mw, 16, stg_of(oG1 + h), 32 * w + 16, ymax, nullptr, nullptr, 0.f);
+                    w2_epi16<2, 0>(tg, f0, f0, nullptr, mw, 0, stg_of(bG1 + h), 32 * w, ymax, nullptr, nullptr, 0.f);
+                    w2_epi16<2, 0>(tg, f0 + 16, f0 + 16, nullptr, mw, 16, stg_of(bG1 + h), 32 * w + 16, ymax, nullptr, nullptr, 0.f);
                 }
                 a_is_ready();
                 // ---- g_f: the part through W1 joins the part through W4's feature columns ----
@@ -555,3 +556,351 @@ k_field_w256(FieldParams p, const unsigned char *__restrict__ wstream)
     cluster_sync();
     if (warp == 0) tmem_dealloc(tmem, bf::kTmemCols);
 }
+
+// ------------------------------------------------------------------------------------------
+// Weight gradients of the width-256 decoder: dW[n][k] = sum over samples of G[s][n] * A[s][k], MMAs whose reduction dimension is
+// the SAMPLE index, both operands MN-major from shared memory straight out of the scratch (128-feature operand blocks, one
+// 64-sample half = 32 kB).  A CTA has a ROLE = a list of sub-steps per (tile, half); a sub-step loads up to three operand blocks
+// (+ F and G5) into a stage and issues up to four products into accumulators that stay in tensor memory for all the CTA's tiles:
+//   role 0  dW2 = G2^T H1                       (4 accumulators of 128 columns)
+//   role 1  dW3[1:] = Gt^T H2 ; dW4[:, :128] = G4^T T
+//   role 2  dW4[:, 128:] = G4^T F ; dW1 = G1^T F ; dW5 = (HC^T G5)[:, 0:3] ; dW3[0] = (H2^T G5)[:, 3] ; bias column sums of
+//           G4, G1, Gt, G2 (MMAs against a ones operand)
+// ------------------------------------------------------------------------------------------
+namespace wg2 {
+constexpr int kThreads = 192;                   // warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 drain
+constexpr int kStages = 2;
+constexpr int kHalf = 32768, kSmallHalf = 4096;
+constexpr int kStage = 3 * kHalf + 2 * kSmallHalf;          // 106 496
+constexpr int oOnes = kStages * kStage;         // 16 samples x 16 features of f16 1.0
+constexpr int oBars = oOnes + 512;              // full[2] free[2] all_done, tmem ptr
+constexpr int kSmem = oBars + 128;
+constexpr int kMaxProd = 6;
+// a product: accumulator columns [col, col + (n16 ? 16 : 128)) += X^T Y, X = stage slot x (always a 128-feature block),
+// Y = stage slot y (0..2), 3 = F, 4 = G5, 5 = ones
+struct Prod { short x, y, col, n16; };
+struct Sub { short op[3]; short small; short nprod; Prod prod[kMaxProd]; };   // op: scratch block per stage slot (-1: unused)
+struct Role { int nsub; Sub sub[5]; };
+using w2::bH1; using w2::bH2; using w2::bHC; using w2::bT; using w2::bG1; using w2::bG2; using w2::bG4; using w2::bGt;
+__device__ __constant__ Role cRoles[3] = {
+    {2, {{{bG2, bH1, bH1 + 1}, 0, 2, {{0, 1, 0, 0}, {0, 2, 128, 0}}},
+         {{bG2 + 1, bH1, bH1 + 1}, 0, 2, {{0, 1, 256, 0}, {0, 2, 384, 0}}}}},
+    {2, {{{bGt, bH2, bH2 + 1}, 0, 2, {{0, 1, 0, 0}, {0, 2, 128, 0}}},
+         {{bT, bG4, bG4 + 1}, 0, 2, {{1, 0, 256, 0}, {2, 0, 384, 0}}}}},
+    {5, {{{bG4, bG4 + 1, -1}, 1, 4, {{0, 3, 0, 1}, {1, 3, 16, 1}, {0, 5, 128, 1}, {1, 5, 144, 1}}},
+         {{bG1, bG1 + 1, -1}, 1, 4, {{0, 3, 32, 1}, {1, 3, 48, 1}, {0, 5, 160, 1}, {1, 5, 176, 1}}},
+         {{bHC, bHC + 1, -1}, 1, 2, {{0, 4, 64, 1}, {1, 4, 80, 1}}},
+         {{bH2, bH2 + 1, bGt}, 1, 3, {{0, 4, 96, 1}, {1, 4, 112, 1}, {2, 5, 192, 1}}},
+         {{bG2, bG2 + 1, -1}, 0, 2, {{0, 5, 208, 1}, {1, 5, 224, 1}}}}}};
+}  // namespace wg2
+
+__global__ void __launch_bounds__(wg2::kThreads, 1) k_wgrad_w256(FieldParams p, int n0, int n1)
+{
+    pdl_enter();
+    using namespace wg2;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + oBars);
+    uint64_t *freeb = full + kStages, *all_done = freeb + kStages;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(smem + oBars + 64);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nsamp = p.nsamp_dev ? *p.nsamp_dev : p.nsamp;
+    const int ntiles = (nsamp + 127) / 128;
+    // CTAs [0, n0) take role 0, [n0, n0 + n1) role 1, the rest role 2; inside a role, CTA j takes tiles j, j + group, ...
+    const int b = (int)blockIdx.x;
+    const int role = b < n0 ? 0 : (b < n0 + n1 ? 1 : 2);
+    const int j = role == 0 ? b : (role == 1 ? b - n0 : b - n0 - n1);
+    const int group = role == 0 ? n0 : (role == 1 ? n1 : (int)gridDim.x - n0 - n1);
+    const Role &R = cRoles[role];
+    if (tid == 0) {
+        for (int i = 0; i < kStages; ++i) { mbar_init(full + i, 1); mbar_init(freeb + i, 1); }
+        mbar_init(all_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, 512);
+    for (int i = tid; i < 128; i += kThreads) reinterpret_cast<uint32_t *>(smem + oOnes)[i] = 0x3C003C00u;   // f16 1.0 pairs
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = *tmem_ptr;
+    const int my_tiles = (j < ntiles) ? (ntiles - 1 - j) / group + 1 : 0;
+    const int nsteps = my_tiles * 2 * R.nsub;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        int tl = 0, h = 0, su = 0;
+        for (int g = 0; g < nsteps; ++g) {
+            const int rs = g % kStages, use = g / kStages;
+            const Sub &S = R.sub[su];
+            const unsigned char *tile = p.wg_scratch + (size_t)(j + (size_t)tl * group) * w2::kWTile;
+            if (use >= 1) mbar_wait(freeb + rs, (use - 1) & 1);
+            if (elect_one()) {
+                unsigned char *dst = smem + rs * kStage;
+                uint32_t bytes = 0;
+                for (int k = 0; k < 3; ++k) bytes += S.op[k] >= 0 ? kHalf : 0;
+                bytes += S.small ? 2 * kSmallHalf : 0;
+                mbar_arrive_expect_tx(full + rs, bytes);
+                for (int k = 0; k < 3; ++k)
+                    if (S.op[k] >= 0) bulk_g2s(dst + k * kHalf, tile + (size_t)S.op[k] * bf::kOpBytes + (size_t)h * kHalf, kHalf, full + rs);
+                if (S.small) {
+                    bulk_g2s(dst + 3 * kHalf, tile + w2::oFsm + (size_t)h * kSmallHalf, kSmallHalf, full + rs);
+                    bulk_g2s(dst + 3 * kHalf + kSmallHalf, tile + w2::oG5sm + (size_t)h * kSmallHalf, kSmallHalf, full + rs);
+                }
+            }
+            __syncwarp();
+            if (++su == R.nsub) { su = 0; if (++h == 2) { h = 0; ++tl; } }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t id128 = idesc_h16(128, 128, 1, 1), id16 = idesc_h16(128, 16, 1, 1);
+        const uint64_t ones = sdesc(smem_u32(smem + oOnes), 256, 128);
+        int su = 0;
+        for (int g = 0; g < nsteps; ++g) {
+            const int rs = g % kStages;
+            const Sub &S = R.sub[su];
+            mbar_wait(full + rs, (g / kStages) & 1);
+            fence_after_sync();
+            const uint32_t base = smem_u32(smem + rs * kStage);
+            if (elect_one()) {
+                for (int ks = 0; ks < 4; ++ks) {            // 16 samples = 2 kb blocks per MMA
+                    const uint32_t fresh = (g < R.nsub && ks == 0) ? 0u : 1u;   // first touch of this sub-step's accumulators
+                    for (int q = 0; q < S.nprod; ++q) {
+                        const Prod P = S.prod[q];
+                        const uint32_t xb = base + P.x * kHalf + ks * 4096;
+                        const uint64_t x_hi = sdesc(xb, 2048, 128), x_lo = sdesc(xb + 16384, 2048, 128);
+                        const uint32_t idesc = P.n16 ? id16 : id128;
+                        if (P.y == 5) {                     // column sums: X^T ones
+                            mma_h16_ss(tmem + P.col, x_hi, ones, id16, fresh);
+                            mma_h16_ss(tmem + P.col, x_lo, ones, id16, 1u);
+                            continue;
+                        }
+                        uint64_t y_hi, y_lo;
+                        if (P.y < 3) {
+                            const uint32_t yb = base + P.y * kHalf + ks * 4096;
+                            y_hi = sdesc(yb, 2048, 128); y_lo = sdesc(yb + 16384, 2048, 128);
+                        } else {
+                            const uint32_t yb = base + 3 * kHalf + (P.y - 3) * kSmallHalf + ks * 512;
+                            y_hi = sdesc(yb, 256, 128); y_lo = sdesc(yb + 2048, 256, 128);
+                        }
+                        mma_h16_ss(tmem + P.col, x_lo, y_hi, idesc, fresh);
+                        mma_h16_ss(tmem + P.col, x_hi, y_lo, idesc, 1u);
+                        mma_h16_ss(tmem + P.col, x_hi, y_hi, idesc, 1u);
+                    }
+                }
+                mma_commit(freeb + rs);
+                if (g == nsteps - 1) mma_commit(all_done);
+            }
+            __syncwarp();
+            if (++su == R.nsub) su = 0;
+        }
+    } else if (nsteps > 0) {
+        // ===================== drain: accumulators -> global gradients (warp & 3 = TMEM lane quarter) =====================
+        mbar_wait(all_done, 0);
+        fence_after_sync();
+        const int qd = warp & 3;
+        const int n = qd * 32 + lane;                            // accumulator row = TMEM lane = feature of the X block
+        const uint32_t trow = tmem + ((uint32_t)(qd * 32) << 16);
+        // accumulators hold 16 x Sg x (sum of products), the column sums Sg x (sum): both factors are powers of two
+        const float invSg = 1.0f / grad_scale(p.gscale), cW = bf::kInvScale * invSg;
+        auto flush = [&](int col0, int ncols, float *dst_row) {   // dst_row: &dW[row][0], ncols % 16 == 0
+            for (int c0 = 0; c0 < ncols; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(trow + col0 + c0, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    red_add_v4(dst_row + c0 + 4 * k, cW * __uint_as_float(v[4 * k]), cW * __uint_as_float(v[4 * k + 1]),
+                               cW * __uint_as_float(v[4 * k + 2]), cW * __uint_as_float(v[4 * k + 3]));
+            }
+        };
+        auto col0_of = [&](int col) { uint32_t v[8]; tmem_ld8(trow + col, v); tmem_wait_ld(); return __uint_as_float(v[0]); };
+        if (role == 0) {
+            flush(0, 128, p.g_dec.W2 + (size_t)n * 256);                  // G2 block 0 x H1 block 0
+            flush(128, 128, p.g_dec.W2 + (size_t)n * 256 + 128);
+            flush(256, 128, p.g_dec.W2 + (size_t)(128 + n) * 256);
+            flush(384, 128, p.g_dec.W2 + (size_t)(128 + n) * 256 + 128);
+        } else if (role == 1) {
+            flush(0, 128, p.g_dec.W3 + (size_t)(1 + n) * 256);            // Gt x H2 block 0 / 1
+            flush(128, 128, p.g_dec.W3 + (size_t)(1 + n) * 256 + 128);
+            flush(256, 128, p.g_dec.W4 + (size_t)n * 144);                // G4 block 0 / 1 x T
+            flush(384, 128, p.g_dec.W4 + (size_t)(128 + n) * 144);
+        } else {
+            flush(0, 16, p.g_dec.W4 + (size_t)n * 144 + 128);             // G4 x F
+            flush(16, 16, p.g_dec.W4 + (size_t)(128 + n) * 144 + 128);
+            flush(32, 16, p.g_dec.W1 + (size_t)n * 16);                   // G1 x F
+            flush(48, 16, p.g_dec.W1 + (size_t)(128 + n) * 16);
+            for (int blk = 0; blk < 2; ++blk) {
+                uint32_t v[8], w[8];
+                tmem_ld8(trow + 64 + 16 * blk, v);                        // HC^T G5: columns 0..2 = dW5 rows
+                tmem_ld8(trow + 96 + 16 * blk, w);                        // H2^T G5: column 3 = dW3 row 0
+                tmem_wait_ld();
+                atomicAdd(p.g_dec.W5 + 128 * blk + n, cW * __uint_as_float(v[0]));
+                atomicAdd(p.g_dec.W5 + 256 + 128 * blk + n, cW * __uint_as_float(v[1]));
+                atomicAdd(p.g_dec.W5 + 512 + 128 * blk + n, cW * __uint_as_float(v[2]));
+                atomicAdd(p.g_dec.W3 + 128 * blk + n, cW * __uint_as_float(w[3]));
+                atomicAdd(p.g_dec.b4 + 128 * blk + n, invSg * col0_of(128 + 16 * blk));
+                atomicAdd(p.g_dec.b1 + 128 * blk + n, invSg * col0_of(160 + 16 * blk));
+                atomicAdd(p.g_dec.b2 + 128 * blk + n, invSg * col0_of(208 + 16 * blk));
+            }
+            atomicAdd(p.g_dec.b3 + 1 + n, invSg * col0_of(192));
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+int w2_pack_decoder(const pslam_decoder_t &d, float *ws_tc, cudaStream_t st, int *range_flag)
+{
+    launch_chain(k_w2_pack, dim3(ceil_div(w2::kWStreamBytes / 4, 256)), dim3(256), 0, st, d, reinterpret_cast<uint16_t *>(ws_tc), range_flag);
+    PSLAM_CHECK_LAUNCH("w2_pack");
+    return 0;
+}
+
+// scratch = [tiles x kWTile operands][tiles x kWMaskBytes ReLU masks][tiles x 8 kB features][tiles x 8 kB feature gradients][gradient scale]
+size_t w2_scratch_bytes(int max_samples)
+{
+    return (size_t)ceil_div(max_samples > 0 ? max_samples : 1, 128) * (w2::kWTile + w2::kWMaskBytes + 2 * w2::kFeatTile) + 64;
+}
+static unsigned char *w2_masks(const FieldParams &fp, int max_samples)
+{
+    return fp.wg_scratch + (size_t)ceil_div(max_samples > 0 ? max_samples : 1, 128) * w2::kWTile;
+}
+static float *w2_feat(const FieldParams &fp, int max_samples, int which)
+{
+    const size_t tiles = (size_t)ceil_div(max_samples > 0 ? max_samples : 1, 128);
+    return reinterpret_cast<float *>(fp.wg_scratch + tiles * (w2::kWTile + w2::kWMaskBytes) + (size_t)which * tiles * w2::kFeatTile);
+}
+static uint32_t *w2_gscale(const FieldParams &fp, int max_samples)
+{
+    const size_t tiles = (size_t)ceil_div(max_samples > 0 ? max_samples : 1, 128);
+    return reinterpret_cast<uint32_t *>(fp.wg_scratch + tiles * (w2::kWTile + w2::kWMaskBytes + 2 * w2::kFeatTile));
+}
+
+struct W2DeviceState { bool configured[4]; int max_clusters[4]; bool wg_configured; };
+static W2DeviceState g_w2_state[64] = {};
+
+// Which workspace holds the masks (and operands) of the most recent saving forward, and for which sample outputs: a backward
+// may start from them only if nothing rewrote either since (same rule as field_bf.cu: the record is a host-side decision,
+// the data itself is stream-ordered).
+struct W2Saved { const void *scratch, *out; int spilled; };
+static W2Saved g_w2_saved[64] = {};
+static std::mutex g_w2_mutex;
+static void w2_saved_set(const void *scratch, const void *out, int spilled)
+{
+    std::lock_guard<std::mutex> lock(g_w2_mutex);
+    g_w2_saved[current_device()] = W2Saved{scratch, out, spilled};
+}
+static void w2_saved_invalidate(const void *scratch, const void *out)
+{
+    std::lock_guard<std::mutex> lock(g_w2_mutex);
+    W2Saved &r = g_w2_saved[current_device()];
+    if ((scratch && scratch == r.scratch) || (out && out == r.out)) r = W2Saved{nullptr, nullptr, 0};
+}
+static bool w2_saved_matches(const void *scratch, const void *out, int need_spill)
+{
+    std::lock_guard<std::mutex> lock(g_w2_mutex);
+    const W2Saved &r = g_w2_saved[current_device()];
+    return scratch && scratch == r.scratch && out == r.out && (!need_spill || r.spilled);
+}
+
+template <int KIND>
+static int launch_w2(const FieldParams &fp, int max_samples, cudaStream_t st)
+{
+    W2DeviceState &ds = g_w2_state[current_device()];
+    if (!ds.configured[KIND]) {      // per device: the attribute belongs to the function on the current device
+        cudaError_t e = cudaFuncSetAttribute(k_field_w256<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, w2::kWSmem);
+        if (e != cudaSuccess) { set_error("field_w256: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(num_sms() / bf::kCluster * bf::kCluster);
+        cfg.blockDim = dim3(w2::kWThreads);
+        cfg.dynamicSmemBytes = w2::kWSmem;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = bf::kCluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        int n = 0;
+        e = cudaOccupancyMaxActiveClusters(&n, k_field_w256<KIND>, &cfg);
+        if (e != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = num_sms() / bf::kCluster; }
+        ds.max_clusters[KIND] = n < num_sms() / bf::kCluster ? n : num_sms() / bf::kCluster;
+        ds.configured[KIND] = true;
+    }
+    const int tiles = ceil_div(max_samples > 0 ? max_samples : 1, 128);
+    int grid = ceil_div(tiles, bf::kCluster) * bf::kCluster;
+    if (grid > ds.max_clusters[KIND] * bf::kCluster) grid = ds.max_clusters[KIND] * bf::kCluster;
+    launch_chain(k_field_w256<KIND>, dim3(grid), dim3(w2::kWThreads), w2::kWSmem, st, fp, reinterpret_cast<const unsigned char *>(fp.ws_tc));
+    PSLAM_CHECK_LAUNCH("field_w256");
+    return 0;
+}
+
+// Can this call run on the tensor-core build?  The forward needs feature rows: given (stand-alone decoder) or gathered into
+// the workspace (fused pipeline); a backward needs the masks its forward saved there.
+bool w2_usable(const FieldParams &fp, int max_samples, bool bwd)
+{
+    const bool ws = fp.wg_scratch && fp.wg_scratch_bytes >= w2_scratch_bytes(max_samples);
+    if (!bwd) return fp.feat != nullptr || (fp.paired && ws);
+    return fp.paired && ws && w2_saved_matches(fp.wg_scratch, fp.out, fp.grad_dec);
+}
+
+int w2_launch_field_forward(const FieldParams &fp_in, int max_samples, cudaStream_t st, int part)
+{
+    FieldParams fp = fp_in;
+    const bool ws = fp.wg_scratch && fp.wg_scratch_bytes >= w2_scratch_bytes(max_samples);
+    if (!fp.feat) {
+        float *feat = w2_feat(fp, max_samples, 0);
+        if (part != 3) { if (int rc = launch_tri_gather_rows(fp, feat, max_samples, st)) return rc; }   // part 3 (profiling): the rows of the previous full forward
+        if (part == 5) return 0;
+        fp.feat = feat;
+    }
+    const bool save = fp.paired && ws && (fp.grad_dec || fp.grad_emb || fp.grad_rays);
+    fp.spill_ops = save && fp.grad_dec;
+    w2_saved_invalidate(fp.wg_scratch, fp.out);     // every forward rewrites its outputs (and, with a workspace, the feature rows)
+    if (!save) { fp.wg_scratch = nullptr; fp.act_masks = nullptr; return launch_w2<bf::kFwd>(fp, max_samples, st); }
+    fp.act_masks = reinterpret_cast<uint32_t *>(w2_masks(fp, max_samples));
+    if (int rc = launch_w2<bf::kFwdSave>(fp, max_samples, st)) return rc;
+    w2_saved_set(fp.wg_scratch, fp.out, fp.spill_ops);
+    return 0;
+}
+
+int w2_launch_field_backward(const FieldParams &fp_in, int max_samples, cudaStream_t st, int part)
+{
+    FieldParams fp = fp_in;
+    fp.spill_ops = fp.grad_dec;
+    fp.gscale = fp.gmax_ready ? fp.gmax_ready : w2_gscale(fp, max_samples);
+    float *g_feat = w2_feat(fp, max_samples, 1);
+    if (part == 4) {   // profiling: the trilinear scatter alone
+        if (fp.grad_emb || fp.grad_rays) return launch_tri_scatter_rows(fp, g_feat, max_samples, st);
+        return 0;
+    }
+    if (part != 2) {
+        if (!fp.gmax_ready && part != 3) { if (int rc = launch_grad_scale(fp, fp.gscale, st)) return rc; }
+        FieldParams fps = fp;                           // the scatter kernel wants the sample tables, not the feature rows
+        fp.act_masks = reinterpret_cast<uint32_t *>(w2_masks(fp, max_samples));
+        fp.feat = w2_feat(fp, max_samples, 0);
+        fp.g_feat = g_feat;
+        if (int rc = launch_w2<bf::kBwdSaved>(fp, max_samples, st)) return rc;
+        if ((fp.grad_emb || fp.grad_rays) && part != 3) { if (int rc = launch_tri_scatter_rows(fps, g_feat, max_samples, st)) return rc; }
+    }
+    if (!fp.grad_dec || part == 1 || part == 3) return 0;
+    W2DeviceState &ds = g_w2_state[current_device()];
+    if (!ds.wg_configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_wgrad_w256, cudaFuncAttributeMaxDynamicSharedMemorySize, wg2::kSmem);
+        if (e != cudaSuccess) { set_error("wgrad_w256: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+        ds.wg_configured = true;
+    }
+    // CTAs per role in proportion to the bytes a role reads per sample (3 : 3 : 5.6), never more roles' CTAs than tiles
+    const int tiles = ceil_div(max_samples > 0 ? max_samples : 1, 128);
+    const int sms = num_sms();
+    int n0 = sms * 3 / 12, n1 = n0, n2 = sms - n0 - n1;
+    if (n0 > tiles) n0 = tiles;
+    if (n1 > tiles) n1 = tiles;
+    if (n2 > tiles) n2 = tiles;
+    launch_chain(k_wgrad_w256, dim3(n0 + n1 + n2), dim3(wg2::kThreads), wg2::kSmem, st, fp, n0, n1);
+    PSLAM_CHECK_LAUNCH("wgrad_w256");
+    return 0;
+}
+
+}  // namespace pslam

@@ -158,12 +158,12 @@ class RenderPipeline:
         else:
             self._map_key, self._map_built = key, False
         a.flags = flags
-        # width 128: the workspace holds the wgrad operands (decoder gradients) and, for any backward, the forward's ReLU
-        # masks and the feature rows of the stand-alone trilinear kernels
-        if (g_dec is not None or g_emb is not None or grad_rays) and width == 128 and not forward_only:
-            if self.wgrad_ws is None:
-                self.wgrad_ws = torch.empty(int(self.lib.pslam_wgrad_ws_bytes(self.sample_cap)), dtype=torch.uint8,
-                                            device=self.device)
+        # the workspace holds the wgrad operands (decoder gradients) and, for any backward, the forward's ReLU masks and the
+        # feature rows of the stand-alone trilinear kernels (width 128: 3.3 kB per sample, width 256: 7.3 kB)
+        if (g_dec is not None or g_emb is not None or grad_rays) and not forward_only:
+            need_ws = int(self.lib.pslam_wgrad_ws_bytes_w(self.sample_cap, width))
+            if self.wgrad_ws is None or self.wgrad_ws.numel() < need_ws:
+                self.wgrad_ws = torch.empty(need_ws, dtype=torch.uint8, device=self.device)
             a.wgrad_ws, a.wgrad_ws_bytes = self.wgrad_ws.data_ptr(), self.wgrad_ws.numel()
         else:
             a.wgrad_ws, a.wgrad_ws_bytes = None, 0

@@ -124,8 +124,8 @@ def test_step_matches_oracle(kind, frames, rays, tracking, width, decoder_build,
          with the GPU's dL/d(sample outputs): 1e-4.
     """
     from proud_slam_b200 import _lib, scene as sc
-    if width == 256 and decoder_build != "simt":
-        pytest.skip("width 256 always runs the SIMT build")
+    if width == 256 and decoder_build in ("tf32", "f16-recompute"):
+        pytest.skip("width 256 has two builds: tcgen05 3xF16 (f16) and SIMT fp32")
     s, ms = util.build_scene(kind)
     dec = util.test_decoder(width=width, seed=1)
     rays_o, rays_d, rgb, depth = sc.sample_batch(s, list(range(frames)), rays, seed=5)
@@ -145,7 +145,7 @@ def test_step_matches_oracle(kind, frames, rays, tracking, width, decoder_build,
     near = util.relu_near_samples(out, rays_o.detach(), rays_d.detach(), ms, dec, s.voxel_size, util.RELU_MARGIN[decoder_build.split("-")[0]])
     near_frac = float(near.float().mean())
     print(f"{kind}/{decoder_build}: {100 * near_frac:.3f} % of the samples masked as ReLU near-ties")
-    assert near_frac < NEAR_TIE_MAX
+    assert near_frac < NEAR_TIE_MAX * width / 128          # (twice the ReLU units per sample at width 256)
     with util.decoder_build(decoder_build.split("-")[0], save_activations=not decoder_build.endswith("recompute")):
         pipe, g_emb, g_dec = _run_pipeline(
             device, rays_o.detach().to(device), rays_d.detach().to(device), rgb.to(device), depth.to(device), msd, decd,

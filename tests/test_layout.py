@@ -81,7 +81,7 @@ def test_python_mirror_matches_header_and_struct():
     declared = set(_header_functions())
     assert set(_lib.exported_symbols()) <= declared
     assert lib.pslam_decoder_ws_count(128) == 128 * 128 + 288 * 128 + 229376   # SIMT pack + tcgen05 weight stream
-    assert lib.pslam_decoder_ws_count(256) == 256 * 256 + 288 * 256
+    assert lib.pslam_decoder_ws_count(256) == 256 * 256 + 288 * 256 + 278528 + 16   # SIMT pack + the width-256 tcgen05 stream (field_w256.cu)
     assert lib.pslam_decoder_ws_count(7) == -1
     assert lib.pslam_render_scratch_i_count(8192) > 0
 
