@@ -440,7 +440,7 @@ def run_gpu(args):
     # ---- every stage alone, events around it (pslam_render_stage): the dominant kernel and the HBM kernels of SURVEY 8(d)
     prof, extra = {}, {}
     build = int(os.environ.get("PSLAM_DECODER", "2"))   # include/proud_slam_b200.h: PSLAM_OPT_DECODER
-    tc = (WIDTH == 128 and build == 2)
+    tc = build == 2                                      # tcgen05 3xF16 builds: field_pp / field_bw (width 128), field_w256 (width 256)
     if rank == 0:
         pipe.args.flags = pipe.args.flags & ~_lib.F_DEFER_LOSS
         names = ["intersect", "sample", "field_fwd", "composite_fwd", "composite_bwd", "field_bwd"]
@@ -448,6 +448,9 @@ def run_gpu(args):
         if tc:
             names += ["decoder_fwd_kernel", "decoder_bwd_kernel", "tri_gather_kernel", "tri_scatter_kernel"]
             ids += [8, 9, 10, 11]
+            if WIDTH == 256:
+                names.append("decoder_wgrad_kernel")
+                ids.append(7)
         for name, stage_id in zip(names, ids):
             reps = []
             for it in range(max(3, min(args.steps, 10))):
@@ -456,6 +459,8 @@ def run_gpu(args):
                     pipe.stage(k)
                 if stage_id == 11:
                     pipe.stage(5)                        # the scatter consumes the feature-gradient rows of a full backward
+                if stage_id == 7:
+                    pipe.stage(6)                        # the wgrad kernel consumes what the chain kernel spilled
                 flush.zero_()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
@@ -507,7 +512,7 @@ def run_gpu(args):
         ktext, dtype = {
             0: ("tcgen05 3xTF32", "f32 (3xTF32 split, f32 accumulate)"),
             1: ("fp32 SIMT", "f32"),
-            2: ("tcgen05 3xF16", "f16x3 (f16 hi/lo split with power-of-two scales, f32 accumulate)")}[build if WIDTH == 128 else 1]
+            2: ("tcgen05 3xF16", "f16x3 (f16 hi/lo split with power-of-two scales, f32 accumulate)")}[build if (WIDTH == 128 or build == 2) else 1]
         hits = int(pipe.hit_count[:R].sum().item())
         vox = torch.unique(pipe.samp_vox[:P].long())
         E_t = int(torch.unique(ms["voxel_vertex_idx"][vox].long()).numel())
@@ -516,8 +521,13 @@ def run_gpu(args):
         if tc:
             # decoder kernels: algorithmic FLOPs (2 MACs forward, 4 MACs backward = dgrad + wgrad; the 3 split MMAs
             # per product are NOT counted, so frac <= 1/3 by construction)
-            for name, key, mult in (("k_field_bw (dgrad chain + weight-gradient MMAs, one kernel)", "decoder_bwd_kernel", 4.0),
-                                    ("k_field_pp<kFwdSave> (two tiles in flight)", "decoder_fwd_kernel", 2.0)):
+            tck = ((("k_field_bw (dgrad chain + weight-gradient MMAs, one kernel)", "decoder_bwd_kernel", 4.0),
+                    ("k_field_pp<kFwdSave> (two tiles in flight)", "decoder_fwd_kernel", 2.0)) if WIDTH == 128 else
+                   (("k_field_w256<kFwdSave> (one tile per CTA: A 128+128 / D 256 TMEM columns)", "decoder_fwd_kernel", 2.0),
+                    ("k_field_w256<kBwdSaved> (dgrad chain)", "decoder_bwd_kernel", 2.0),
+                    ("k_wgrad_w256 (role-partitioned weight gradients from the spilled operands)", "decoder_wgrad_kernel", 2.0)))
+            tck = sorted(tck, key=lambda t: -prof[t[1]])          # the longest first: it becomes `roofline`
+            for name, key, mult in tck:
                 fl = mult * macs * P
                 a = fl / (prof[key] * 1e-3) / 1e12
                 kernels.append({"kernel": name, "bound": "tensor", "achieved": a, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",

@@ -43,13 +43,21 @@ k_peer_allreduce(pslam_peer_t peer, int *__restrict__ fail_flag)
     const int64_t n4 = peer.flat_count / 4;
     const int64_t lo = n4 * rank / world, hi = n4 * (rank + 1) / world;
     if (!s_fail) {
-        for (int64_t i = lo + (int64_t)b * kArThreads + tid; i < hi; i += (int64_t)gridDim.x * kArThreads) {
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int q = 0; q < world; ++q) {
-                const float4 v = ld_relaxed_sys_v4(reinterpret_cast<const float4 *>(peer.flat[q]) + i);
-                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-            }
-            for (int q = 0; q < world; ++q) reinterpret_cast<float4 *>(peer.flat[q])[i] = acc;
+        // every load of an element is in flight before the first is used: a remote load is a ~2 us NVLink round trip, and the
+        // launch gives a thread one or two elements, so the slice costs about one round trip
+        const int64_t stride = (int64_t)gridDim.x * kArThreads;
+        for (int64_t i = lo + (int64_t)b * kArThreads + tid; i < hi; i += stride) {
+            float4 v[PSLAM_MAX_PEERS];
+#pragma unroll
+            for (int q = 0; q < PSLAM_MAX_PEERS; ++q)
+                if (q < world) v[q] = ld_relaxed_sys_v4(reinterpret_cast<const float4 *>(peer.flat[q]) + i);
+            float4 acc = v[0];
+#pragma unroll
+            for (int q = 1; q < PSLAM_MAX_PEERS; ++q)
+                if (q < world) { acc.x += v[q].x; acc.y += v[q].y; acc.z += v[q].z; acc.w += v[q].w; }
+#pragma unroll
+            for (int q = 0; q < PSLAM_MAX_PEERS; ++q)
+                if (q < world) reinterpret_cast<float4 *>(peer.flat[q])[i] = acc;
         }
     }
     // ---- exit barrier: everybody's slice has landed in this rank's buffer ----
@@ -77,9 +85,9 @@ int launch_peer_allreduce(const pslam_peer_t *peer, int *fail_flag, cudaStream_t
     PSLAM_CHECK_ARG(peer->flat_count > 0 && peer->flat_count % 4 == 0, PSLAM_E_ARG, "peer_allreduce: flat_count must be a positive multiple of 4");
     for (int q = 0; q < peer->world; ++q)
         PSLAM_CHECK_ARG(peer->sync[q] && peer->flat[q] && ((uintptr_t)peer->flat[q] % 16 == 0), PSLAM_E_ARG, "peer_allreduce: null or misaligned peer pointer");
-    // one block per ~16 k float4 of this rank's slice, between 8 blocks (latency) and kArMaxBlocks
+    // one element (float4) of this rank's slice per thread up to kArMaxBlocks blocks, two or more beyond
     const int64_t slice4 = peer->flat_count / 4 / peer->world;
-    int blocks = (int)ceil_div64(slice4, 4 * kArThreads);
+    int blocks = (int)ceil_div64(slice4, kArThreads);
     blocks = blocks < 8 ? 8 : (blocks > kArMaxBlocks ? kArMaxBlocks : blocks);
     if (blocks > num_sms()) blocks = num_sms();      // every block spins on its peers: all of them must be resident
     launch_chain(k_peer_allreduce, dim3(blocks), dim3(kArThreads), 0, st, *peer, fail_flag);

@@ -362,7 +362,7 @@ class FusedIteration:
         self.width = width
 
     def run(self, rays_o, rays_d, rgb, depth, ms, dec, crit, *, voxel_size, step_size, max_distance, tracking, grad_emb,
-            grad_dec, grad_rays, seed, zero_grads=True):
+            grad_dec, grad_rays, seed, zero_grads=True, noise=None):
         if grad_emb and (self.g_emb is None or self.g_emb.shape != ms["voxel_vertex_emb"].shape):
             self.g_emb = torch.zeros_like(ms["voxel_vertex_emb"])
         if grad_dec and self.g_dec is None:
@@ -376,7 +376,7 @@ class FusedIteration:
             if grad_dec:
                 self._flat.flat.zero_()
         self.pipe.bind(rays_o, rays_d, ms, dec, voxel_size=voxel_size, step_size=step_size, truncation=crit["truncation"],
-                       max_distance=max_distance, max_depth=crit["max_depth"], target_rgb=rgb, target_depth=depth, seed=seed,
+                       max_distance=max_distance, max_depth=crit["max_depth"], target_rgb=rgb, target_depth=depth, seed=seed, noise=noise,
                        weights=crit["weights"], tracking=tracking, g_emb=self.g_emb if grad_emb else None,
                        g_dec=self.g_dec if grad_dec else None, grad_rays=grad_rays)
         self.pipe.step()
@@ -385,12 +385,14 @@ class FusedIteration:
 
 def bundle_adjust_frames(keyframe_graph, map_states, sdf_network, resnet, loss_criteria, voxel_size, step_size, N_rays=512,
                          num_iterations=10, truncation=0.1, max_voxel_hit=10, max_distance=10, learning_rate=[1e-2, 5e-3],
-                         embed_optim=None, model_optim=None, resnet_optim=None, update_pose=True, device_sampling=True):
+                         embed_optim=None, model_optim=None, resnet_optim=None, update_pose=True, device_sampling=True, noise_fn=None):
     """render_helpers.py:559-676.  Same loop and arguments; per iteration ONE fused call produces the loss and every gradient
     and the caller's optimizers are stepped.  Around it, for keyframes whose pose is the 6-vector of se3pose.py with a plain
     Adam: pixels are drawn and rays assembled on the device (``device_sampling``; uniform without replacement, like the
     frame's own ``sample_rays``, but not its random stream), dL/dpose and the pose Adam are two kernels; the embedding / decoder
-    Adam is one launch on the optimizers' own state.  Any other frame or optimizer keeps the reference's torch route."""
+    Adam is one launch on the optimizers' own state.  Any other frame or optimizer keeps the reference's torch route.
+    ``noise_fn(iteration)`` (optional, deterministic replay): the uniform sampling noise [>= R_h, M] of that iteration, in place of
+    the counter-based generator -- what the reference draws with ``torch.rand`` inside ``ray_sample`` (voxel_helpers.py:328)."""
     from .. import _lib
     lib = _lib.lib()
     emb = map_states["voxel_vertex_emb"]
@@ -498,7 +500,8 @@ def bundle_adjust_frames(keyframe_graph, map_states, sdf_network, resnet, loss_c
         dec = [p.detach() for p in dec_params]
         it.run(rays_o.detach().float().contiguous(), rays_d.detach().float().contiguous(), rgb_samples, depth_samples, ms, dec, crit,
                voxel_size=voxel_size, step_size=step_size, max_distance=max_distance, tracking=False, grad_emb=True,
-               grad_dec=model_optim is not None, grad_rays=need_pose, seed=_next_seed(), zero_grads=fused_adam is None or iteration == 0)
+               grad_dec=model_optim is not None, grad_rays=need_pose, seed=_next_seed(), zero_grads=fused_adam is None or iteration == 0,
+               noise=None if noise_fn is None else noise_fn(iteration))
         for optim in torch_optimizers:
             optim.zero_grad()
         if fused_adam is None:
@@ -541,9 +544,9 @@ def bundle_adjust_frames(keyframe_graph, map_states, sdf_network, resnet, loss_c
 
 def track_frame(frame_pose, curr_frame, map_states, sdf_network, resnet, loss_criteria, voxel_size, N_rays=512, step_size=0.05,
                 num_iterations=10, truncation=0.1, learning_rate=1e-3, max_voxel_hit=10, max_distance=10, profiler=None,
-                depth_variance=False):
+                depth_variance=False, noise_fn=None):
     """render_helpers.py:679-761: optimise the 6-vector pose of ``curr_frame`` against the fixed map.
-    Returns (pose, optim, hit_mask) like the reference."""
+    Returns (pose, optim, hit_mask) like the reference.  ``noise_fn``: see ``bundle_adjust_frames``."""
     device = torch.device("cuda", torch.cuda.current_device())
     init_pose = deepcopy(frame_pose).to(device)
     init_pose.requires_grad_(True)
@@ -569,7 +572,7 @@ def track_frame(frame_pose, curr_frame, map_states, sdf_network, resnet, loss_cr
     crit["truncation"] = truncation
     it = FusedIteration(N_rays, device, int(dec[0].shape[0]))
     hit_mask = None
-    for _ in range(num_iterations):
+    for iteration in range(num_iterations):
         curr_frame.sample_rays(N_rays)
         sample_mask = curr_frame.sample_mask.to(device)
         ray_dirs = curr_frame.rays_d.to(device)[sample_mask]
@@ -588,7 +591,7 @@ def track_frame(frame_pose, curr_frame, map_states, sdf_network, resnet, loss_cr
             ray_start_iter = init_pose.translation().reshape(1, -1).expand_as(ray_dirs_iter)
         it.run(ray_start_iter.detach().float().contiguous(), ray_dirs_iter.detach().float().contiguous(), rgb, depth, ms, dec, crit,
                voxel_size=voxel_size, step_size=step_size, max_distance=max_distance, tracking=depth_variance, grad_emb=False,
-               grad_dec=False, grad_rays=True, seed=_next_seed())
+               grad_dec=False, grad_rays=True, seed=_next_seed(), noise=None if noise_fn is None else noise_fn(iteration))
         R = ray_dirs_iter.shape[0]
         if fused_pose:
             _lib.check(lib.pslam_track_pose_step(R, _lib.ptr(init_pose.data), _lib.ptr(idx), _lib.ptr(ray_dirs), _lib.ptr(it.pipe.g_rays_o),
