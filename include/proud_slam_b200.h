@@ -416,6 +416,19 @@ int pslam_octree_has_voxel(void *tree, int x, int y, int z);
 int pslam_octree_flatten(void *tree, float *voxels, float *children, int *features);
 int pslam_octree_leaf_voxels(void *tree, int *out_xyz, int cap);
 
+/* ------------------------------------------------------------------------
+ * Device-side octree (csrc/octree_dev.cu): the same insert / get_centres_and_children with the same row ids (creation order
+ * of the sequential insertion, octree.h:41), built on the GPU from device tensors and flattened into device tensors -- the
+ * producer of `map_states` where the map is consumed (src/mapping.py:258-295, 301-406 re-flatten a host tree and upload it per
+ * keyframe).  vox [m,3] int32 ON THE DEVICE, 0 <= v < grid_dim - 1.  insert synchronises the stream once (array growth).
+ * ---------------------------------------------------------------------- */
+void *pslam_doctree_new(int grid_dim, int capacity_hint);
+void pslam_doctree_free(void *tree);
+int pslam_doctree_count(void *tree);
+int pslam_doctree_insert(void *tree, const int *vox_dev, int m, pslam_stream_t stream);
+int pslam_doctree_flatten(void *tree, float *voxels_dev, float *children_dev, int *features_dev, pslam_stream_t stream);
+int pslam_doctree_types(void *tree, int *types_dev_out, pslam_stream_t stream);   /* per row: -1 internal, 0 SURFACE voxel, 1 FEATURE corner */
+
 #ifdef __cplusplus
 }
 #endif

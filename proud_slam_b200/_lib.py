@@ -118,6 +118,12 @@ _PROTOTYPES = {
     "pslam_octree_has_voxel": (C.c_int, [_P, _I, _I, _I]),
     "pslam_octree_flatten": (C.c_int, [_P, _P, _P, _P]),
     "pslam_octree_leaf_voxels": (C.c_int, [_P, _P, _I]),
+    "pslam_doctree_new": (C.c_void_p, [_I, _I]),
+    "pslam_doctree_free": (None, [_P]),
+    "pslam_doctree_count": (C.c_int, [_P]),
+    "pslam_doctree_insert": (C.c_int, [_P, _P, _I, _S]),
+    "pslam_doctree_flatten": (C.c_int, [_P, _P, _P, _P, _S]),
+    "pslam_doctree_types": (C.c_int, [_P, _P, _S]),
 }
 
 _lib = None

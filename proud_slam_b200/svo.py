@@ -116,6 +116,74 @@ class Octree:
             self.insert(p)
 
 
+class DeviceOctree:
+    """The same octree on the GPU (``csrc/octree_dev.cu``): CUDA tensors in, CUDA tensors out, identical rows.  ``insert`` takes
+    int voxel coordinates [M,3] on the device (what ``Mapping.insert_points`` computes there, src/mapping.py:258-264, before the
+    reference copies them to the host tree); ``get_centres_and_children`` returns device tensors, so ``build_map_states`` needs
+    no upload.  Row ids equal the host tree's (creation order of the sequential insertion)."""
+
+    def __init__(self, device=None):
+        self._h = None
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.grid_dim, self.feat_dim, self.voxel_size, self.max_num = 256, 16, 0.2, 8
+
+    def init(self, grid_dim, feat_dim, voxel_size, max_num=8, capacity_hint=0):
+        self._free()
+        self.grid_dim, self.feat_dim, self.voxel_size, self.max_num = int(grid_dim), int(feat_dim), float(voxel_size), int(max_num)
+        with torch.cuda.device(self.device):
+            self._h = _lib.lib().pslam_doctree_new(self.grid_dim, int(capacity_hint))
+        if not self._h:
+            raise RuntimeError("device octree: " + _lib.lib().pslam_last_error().decode(errors="replace"))
+
+    def _free(self):
+        if self._h:
+            _lib.lib().pslam_doctree_free(C.c_void_p(self._h))
+            self._h = None
+
+    def __del__(self):
+        try:
+            self._free()
+        except Exception:
+            pass
+
+    def _handle(self):
+        if not self._h:
+            raise RuntimeError("Octree not initialized!")
+        return C.c_void_p(self._h)
+
+    def insert(self, pts, color=None, pcd=None):
+        pts = torch.as_tensor(pts)
+        if pts.dim() != 2 or pts.size(1) != 3:
+            raise RuntimeError(f"Point dimensions mismatch: inputs are {tuple(pts.shape)} expect [M,3]")
+        v = pts.to(self.device, torch.int32).contiguous()
+        if v.numel() and (bool((v < 0).any()) or bool((v >= self.grid_dim - 1).any())):
+            raise RuntimeError("voxel coordinates outside the octree grid")
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().pslam_doctree_insert(self._handle(), _lib.ptr(v), int(v.shape[0]), _lib.stream_ptr(self.device)), "device octree insert")
+
+    def count_nodes(self):
+        return int(_lib.lib().pslam_doctree_count(self._handle()))
+
+    def _types(self):
+        t = torch.empty(self.count_nodes(), dtype=torch.int32, device=self.device)
+        _lib.check(_lib.lib().pslam_doctree_types(self._handle(), _lib.ptr(t), _lib.stream_ptr(self.device)), "device octree types")
+        return t
+
+    def count_leaf_nodes(self):
+        return int((self._types() == 0).sum())
+
+    def get_centres_and_children(self):
+        """(voxels f32[N,4], children f32[N,8], features i32[N,8], pcd_xyz, pcd_color) on the device."""
+        n = self.count_nodes()
+        voxels = torch.empty(n, 4, dtype=torch.float32, device=self.device)
+        children = torch.empty(n, 8, dtype=torch.float32, device=self.device)
+        features = torch.empty(n, 8, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().pslam_doctree_flatten(self._handle(), _lib.ptr(voxels), _lib.ptr(children), _lib.ptr(features),
+                                                        _lib.stream_ptr(self.device)), "device octree flatten")
+        return (voxels, children, features, torch.zeros(n, self.max_num, 4, device=self.device), torch.zeros(n, self.max_num, 3, device=self.device))
+
+
 def build_map_states(octree, voxel_size, num_embeddings=20000, embed_dim=16, device="cuda", seed=None, emb=None):
     """``Mapping.update_grid_pcd_features`` (src/mapping.py:301-377): flatten the octree and build the
     ``map_states`` dict the render path reads."""
