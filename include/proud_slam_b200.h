@@ -66,6 +66,9 @@ int pslam_device_info(int *out3);
  * weight-gradient MMAs in one kernel (csrc/field_bw.cu; no gradient operand leaves the SM); 0 = chain kernel + k_wgrad_bf through
  * the HBM scratch. */
 #define PSLAM_OPT_FUSED_WGRAD 5
+/* PSLAM_OPT_FUSED_SCATTER (with PSLAM_OPT_FUSED_WGRAD): 1 = the trilinear backward (embedding scatter, ray gradients) of every
+ * finished tile runs in two otherwise idle warps of that kernel; 0 (default: measured faster) = as a kernel of its own behind it. */
+#define PSLAM_OPT_FUSED_SCATTER 6
 int pslam_set_option(int key, int value);
 
 /* ------------------------------------------------------------------------

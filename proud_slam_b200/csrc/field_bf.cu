@@ -21,6 +21,7 @@
 // k_wgrad_finish, the trilinear kernels and the launch logic of the 3xF16 build.
 #include "field_bf.cuh"
 #include "kernels.h"
+#include "trilinear.cuh"
 #include <mutex>
 #include <type_traits>
 
@@ -722,23 +723,9 @@ k_field_bf(FieldParams p, const unsigned char *__restrict__ wstream)
 // and the tensor-core kernels read / write plain [P,16] rows (64 B per sample, L2-resident at the mapping sizes).
 // Arithmetic and corner order are those of the fused path, so the features are bit-identical.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void sample_position(const FieldParams &p, int s, int &vox, int &ray, float &z, float &px, float &py, float &pz)
-{
-    vox = __ldg(p.samp_vox + s);
-    z = __ldg(p.samp_z + s);
-    ray = __ldg(p.hit_ray + __ldg(p.samp_ray + s));
-    const float x = __fadd_rn(__ldg(p.rays_o + ray * 3 + 0), __fmul_rn(__ldg(p.rays_d + ray * 3 + 0), z));
-    const float y = __fadd_rn(__ldg(p.rays_o + ray * 3 + 1), __fmul_rn(__ldg(p.rays_d + ray * 3 + 1), z));
-    const float zz = __fadd_rn(__ldg(p.rays_o + ray * 3 + 2), __fmul_rn(__ldg(p.rays_d + ray * 3 + 2), z));
-    px = __fadd_rn(__fdiv_rn(__fsub_rn(x, __ldg(p.centres + (size_t)vox * 3 + 0)), p.voxel_size), 0.5f);
-    py = __fadd_rn(__fdiv_rn(__fsub_rn(y, __ldg(p.centres + (size_t)vox * 3 + 1)), p.voxel_size), 0.5f);
-    pz = __fadd_rn(__fdiv_rn(__fsub_rn(zz, __ldg(p.centres + (size_t)vox * 3 + 2)), p.voxel_size), 0.5f);
-}
-
 // A thread quad (one 16-byte quarter of the feature row per thread) walks kTriChunk CONSECUTIVE samples.  Samples are in
 // CSR order by ray and sorted by depth, so ~7 neighbours sit in the same voxel: the quad fetches the voxel's corner ids and
-// rows once per voxel change
-// (the scatter below aggregates the same way, across the lanes of a warp).
+// rows once per voxel change (the scatter aggregates the same way, across the lanes of a warp: trilinear.cuh).
 constexpr int kTriChunk = 8;
 
 __global__ void __launch_bounds__(256) k_tri_gather(FieldParams p, float *__restrict__ feat)
@@ -778,101 +765,16 @@ __global__ void __launch_bounds__(256) k_tri_gather(FieldParams p, float *__rest
     }
 }
 
-// Backward of the lookup with warp-aggregated reductions.  A warp takes 32 consecutive samples:
-//   phase 1  lane = sample: position, the 8 corner weights and the sample's feature-gradient row go to shared memory; with
-//            ray gradients, the lane also takes the 8 dot products <g, corner row> and the per-ray sums are reduced over the
-//            lanes of a ray (a segmented shuffle reduction: a ray's samples are consecutive) before they touch memory;
-//   phase 2  lane = (corner, quarter of the feature row): for every voxel fragment of the 32 samples (~7 consecutive samples
-//            share a voxel) the lane adds up w[k][corner] * g[k][quarter] over the fragment and issues ONE red.v4.
-// The kernel was bound by L2 reductions (32 red.v4 per sample, 6.1 M per mapping iteration); this issues ~5.6 per sample.
-constexpr int kScatWarps = 8, kScatWPitch = 9, kScatGPitch = 20;
-
+// Backward of the lookup with warp-aggregated reductions: tri_scatter_warp (trilinear.cuh), 8 warps of 32 samples per block.
 __global__ void __launch_bounds__(kScatWarps * 32) k_tri_scatter(FieldParams p, const float *__restrict__ g_feat)
 {
     pdl_enter();
-    __shared__ float s_w[kScatWarps][32 * kScatWPitch];
-    __shared__ __align__(16) float s_g[kScatWarps][32 * kScatGPitch];
+    __shared__ __align__(16) float s_buf[kScatWarps][kScatWarpFloats];
     const int nsamp = p.nsamp_dev ? *p.nsamp_dev : p.nsamp;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warp = threadIdx.x >> 5;
     const int s0 = (blockIdx.x * kScatWarps + warp) * 32;
     if (s0 >= nsamp) return;                                  // whole warps leave
-    const int s = s0 + lane;
-    const bool live = s < nsamp;
-    int vox = -1, ray = -1;
-    float z = 0.f, px = 0.f, py = 0.f, pz = 0.f;
-    float4 gq[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) gq[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (live) {
-        sample_position(p, s, vox, ray, z, px, py, pz);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) gq[j] = __ldg(reinterpret_cast<const float4 *>(g_feat + (size_t)s * 16 + j * 4));
-    }
-    float *w = s_w[warp], *g = s_g[warp];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) *reinterpret_cast<float4 *>(g + lane * kScatGPitch + j * 4) = gq[j];
-    float gp[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float wx = (i & 4) ? px : 1.0f - px, wy = (i & 2) ? py : 1.0f - py, wz = (i & 1) ? pz : 1.0f - pz;
-        w[lane * kScatWPitch + i] = (wx * wy) * wz;
-        if (p.grad_rays && live) {
-            const int row = __ldg(p.vertex_idx + (size_t)vox * 8 + i);
-            float d = 0.f;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float4 v = __ldg(reinterpret_cast<const float4 *>(p.emb + (size_t)row * 16 + j * 4));
-                d = fmaf(gq[j].w, v.w, fmaf(gq[j].z, v.z, fmaf(gq[j].y, v.y, fmaf(gq[j].x, v.x, d))));
-            }
-            gp[0] += d * ((i & 4) ? 1.0f : -1.0f) * (wy * wz);
-            gp[1] += d * ((i & 2) ? 1.0f : -1.0f) * (wx * wz);
-            gp[2] += d * ((i & 1) ? 1.0f : -1.0f) * (wx * wy);
-        }
-    }
-    if (p.grad_rays) {
-        // per-ray sums over the lanes of a ray: after the sweep the first lane of every ray fragment holds its total
-        float so[3], sd[3];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) { so[a] = gp[a] / p.voxel_size; sd[a] = z * so[a]; }
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int r2 = __shfl_down_sync(0xffffffffu, ray, o);
-            const bool take = (lane + o < 32) && r2 == ray;
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                const float x = __shfl_down_sync(0xffffffffu, so[a], o), y = __shfl_down_sync(0xffffffffu, sd[a], o);
-                if (take) { so[a] += x; sd[a] += y; }
-            }
-        }
-        const int rprev = __shfl_up_sync(0xffffffffu, ray, 1);
-        if (live && (lane == 0 || rprev != ray)) {
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                atomicAdd(p.g_rays_o + ray * 3 + a, so[a]);
-                atomicAdd(p.g_rays_d + ray * 3 + a, sd[a]);
-            }
-        }
-    }
-    if (!p.grad_emb) return;
-    const int vprev = __shfl_up_sync(0xffffffffu, vox, 1), rprev2 = __shfl_up_sync(0xffffffffu, ray, 1);
-    unsigned heads = __ballot_sync(0xffffffffu, live && (lane == 0 || vprev != vox || rprev2 != ray));
-    const int nlive = __popc(__ballot_sync(0xffffffffu, live));
-    __syncwarp();
-    const int ci = lane >> 2, cq = lane & 3;
-    while (heads) {
-        const int start = __ffs(heads) - 1;
-        heads &= heads - 1;
-        const int end = heads ? __ffs(heads) - 1 : nlive;
-        const int vf = __shfl_sync(0xffffffffu, vox, start);
-        const int row = __ldg(p.vertex_idx + (size_t)vf * 8 + ci);
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int k = start; k < end; ++k) {
-            const float wk = w[k * kScatWPitch + ci];
-            const float4 gk = *reinterpret_cast<const float4 *>(g + k * kScatGPitch + cq * 4);
-            acc.x = fmaf(wk, gk.x, acc.x); acc.y = fmaf(wk, gk.y, acc.y); acc.z = fmaf(wk, gk.z, acc.z); acc.w = fmaf(wk, gk.w, acc.w);
-        }
-        red_add_v4(p.g_emb + (size_t)row * 16 + cq * 4, acc.x, acc.y, acc.z, acc.w);
-    }
+    tri_scatter_warp<false>(p, g_feat, s0, nsamp, s_buf[warp]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1377,7 +1279,7 @@ int bf_launch_field_backward(const FieldParams &fp_in, int max_samples, cudaStre
 {
     FieldParams fp = fp_in;
     cudaEvent_t joined = nullptr;
-    bool fused = false;
+    bool fused = false, scatter_fused = false;
     if (!fp.grad_dec && !fp.paired) fp.wg_scratch = nullptr;
     fp.spill_ops = fp.grad_dec;
     // per-launch gradient scale: 4 bytes at the end of the weight-stream region (the f16 stream fills only its first half)
@@ -1413,12 +1315,15 @@ int bf_launch_field_backward(const FieldParams &fp_in, int max_samples, cudaStre
             // decoder gradients wanted: chain + weight gradients in one kernel (nothing is spilled; the forward cleared the reduction block)
             fused = pp && bw_enabled() && fp.grad_dec && fp.spill_ops && part != 1;
             if (fused) {
-                if (int rc = bw_launch(fp, max_samples, reinterpret_cast<float *>(scratch_finish(fp, max_samples)), st)) return rc;
+                // the trilinear backward rides along in the kernel's idle warps (part 3 = the chain kernel alone for profiling: then
+                // the stand-alone scatter is simply not launched, as before)
+                scatter_fused = split && (fp.grad_emb || fp.grad_rays) && bw_fused_scatter();
+                if (int rc = bw_launch(fp, max_samples, reinterpret_cast<float *>(scratch_finish(fp, max_samples)), st, scatter_fused ? &fps : nullptr)) return rc;
             } else if (int rc = pp ? pp_launch(bf::kBwdSaved, fp, max_samples, st) : launch_bf<bf::kBwdSaved>(fp, max_samples, st)) return rc;
         } else {
             if (int rc = launch_bf<bf::kBwdRecompute>(fp, max_samples, st)) return rc;
         }
-        if (split && (fp.grad_emb || fp.grad_rays) && part != 3) {
+        if (split && (fp.grad_emb || fp.grad_rays) && part != 3 && !scatter_fused) {
             // the embedding / ray scatter and the weight-gradient kernels both depend on the kernel above only: the scatter
             // (L2 atomics, few threads per SM) runs on a side stream underneath the HBM-bound wgrad kernel
             cudaStream_t ss = st;

@@ -101,7 +101,9 @@ __device__ __forceinline__ float grad_scale(const uint32_t *gscale)
 // launchers of the two-tiles-in-flight build (field_pp.cu); KIND = bf::kFwd / kBwdRecompute / kFwdSave / kBwdSaved
 int pp_launch(int kind, const FieldParams &fp, int max_samples, cudaStream_t st);
 // field_bw.cu: dgrad chain + weight gradients in one kernel (the forward must have saved masks and activations)
-int bw_launch(const FieldParams &fp, int max_samples, float *finish, cudaStream_t st);
+int bw_launch(const FieldParams &fp, int max_samples, float *finish, cudaStream_t st, const FieldParams *scatter = nullptr);
+int bw_fused_scatter();              // PSLAM_OPT_FUSED_SCATTER
+void bw_set_fused_scatter(int on);
 int bw_enabled();
 void bw_set_enabled(int on);
 int pp_enabled();

@@ -21,6 +21,7 @@
 // gradients (64 B per sample).  k_wgrad_finish (field_bf.cu) still turns M into dW3 / dW4[:, :128].
 #include "field_bf.cuh"
 #include "kernels.h"
+#include "trilinear.cuh"
 #include <type_traits>
 
 namespace pslam {
@@ -48,7 +49,9 @@ constexpr int oBars = oOnes + 512;                             // full[4] empty[
 constexpr int oTmemPtr = oBars + 8 * (2 * kBWStages + 7);
 constexpr int oW5 = oTmemPtr + 16;                             // W5 [3][128] fp32
 constexpr int oW30 = oW5 + 4 * 3 * 128;                        // W3 row 0 [128] fp32
-constexpr int kSmemBytes = oW30 + 4 * 128;
+constexpr int oScat = (oW30 + 4 * 128 + 15) & ~15;                        // two warps x (weights [32][9] + gradient rows [32][16] + corner ids [32][8]) of the fused scatter
+constexpr int oScatDone = oScat + 2 * 4 * kScatWarpFloats;     // tiles whose feature-gradient rows are complete (x 128 lead threads)
+constexpr int kSmemBytes = oScatDone + 16;
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 __host__ __device__ constexpr int n_chunks(int l) { return 4; }                       // layers 10, 6, 7 (without its sdf chunk), 8, 9
 __host__ __device__ constexpr int chunk_bytes(int l) { return hN(l) * 32 * 4; }
@@ -129,7 +132,7 @@ __device__ long long *g_bw_trace = nullptr;
     } while (0)
 
 __global__ void __cluster_dims__(bf::kCluster, 1, 1) __launch_bounds__(bw::kBWThreads, 1)
-k_field_bw(FieldParams p, const unsigned char *__restrict__ wstream, float *__restrict__ finish)
+k_field_bw(FieldParams p, const unsigned char *__restrict__ wstream, float *__restrict__ finish, FieldParams ps, int fuse_scatter)
 {
     pdl_enter();
     using namespace bw;
@@ -153,7 +156,9 @@ k_field_bw(FieldParams p, const unsigned char *__restrict__ wstream, float *__re
     const int iters = (ntiles + G - 1) / G;
     const uint32_t crank = cluster_ctarank();
 
+    volatile int *scat_done = reinterpret_cast<volatile int *>(smem + oScatDone);
     if (threadIdx.x == 0) {
+        *scat_done = 0;
         for (int i = 0; i < kBWStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, kCluster); }
         mbar_init(a_ready, kBWWorkers);
         mbar_init(mma_done, 1);
@@ -405,6 +410,26 @@ k_field_bw(FieldParams p, const unsigned char *__restrict__ wstream, float *__re
                 __syncwarp();
                 if (lane == 0) BW_TRACE(it, 1, 14);
             }
+        } else if (fuse_scatter) {
+            // ===================== warps 2-3: the trilinear backward of every finished tile (embedding scatter, ray gradients) ============
+            // (PSLAM_OPT_FUSED_SCATTER, off by default.)  The chain leaves these warps and most issue slots idle and the stand-alone
+            // scatter kernel is the tail of the iteration (25 us after this kernel) -- but measured: two warps without an L1 to
+            // speak of (the kernel's 225 kB of shared memory leave none) take ~22 us for a tile's 128 samples, longer than the
+            // chain needs for the tile: the kernel went from 184 to 247 us.  Kept for batches where the chain is slower per tile.  The lead workers store a tile's feature-gradient rows, fence, and count themselves in;
+            // each of the two warps then takes 64 of the tile's samples in two passes of tri_scatter_warp (trilinear.cuh).
+            float *sw = reinterpret_cast<float *>(smem + oScat) + (warp - 2) * kScatWarpFloats;
+            int done = 0;
+            for (int it = 0; it < iters; ++it) {
+                const int tile_i = it * G + (int)blockIdx.x;
+                if (tile_i >= ntiles) break;
+                ++done;
+                while (*scat_done < 128 * done) __nanosleep(200);
+                __threadfence();
+                for (int pass = 0; pass < 2; ++pass) {
+                    const int s0 = tile_i * 128 + (warp - 2) * 64 + pass * 32;
+                    if (s0 < nsamp) tri_scatter_warp<true>(ps, p.g_feat, s0, nsamp, sw);
+                }
+            }
         }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsWorker));
@@ -562,6 +587,10 @@ k_field_bw(FieldParams p, const unsigned char *__restrict__ wstream, float *__re
                     for (int j = 0; j < 4; ++j)
                         *reinterpret_cast<float4 *>(p.g_feat + (size_t)s * 16 + 4 * j) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
                 }
+                if (fuse_scatter && real) {                 // this row of the tile is in place for warps 2-3
+                    __threadfence();
+                    atomicAdd(const_cast<int *>(scat_done), 1);
+                }
             } else if (real) {
                 uint32_t v[16], w[8], cs[8];
                 tmem_ld16(trow + cS0, v);
@@ -620,7 +649,9 @@ k_field_bw(FieldParams p, const unsigned char *__restrict__ wstream, float *__re
     if (warp == 0) tmem_dealloc(tmem, bf::kTmemCols);
 }
 
-static int g_bw_enabled = 1;
+static int g_bw_enabled = 1, g_bw_scatter = 0;   // fused scatter: measured slower (see the role's comment), off by default
+int bw_fused_scatter() { return g_bw_scatter; }
+void bw_set_fused_scatter(int on) { g_bw_scatter = on ? 1 : 0; }
 int bw_enabled() { return g_bw_enabled; }
 void bw_set_enabled(int on) { g_bw_enabled = on ? 1 : 0; }
 
@@ -629,7 +660,7 @@ static BWDeviceState g_bw_state[64] = {};
 
 // dgrad chain + weight gradients of the tiles whose forward saved masks and activations into fp.wg_scratch; `finish` = the
 // reduction block k_wgrad_finish consumes (cleared by this kernel's predecessor through fp.finish_zero or by the caller)
-int bw_launch(const FieldParams &fp, int max_samples, float *finish, cudaStream_t st)
+int bw_launch(const FieldParams &fp, int max_samples, float *finish, cudaStream_t st, const FieldParams *scatter)
 {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { set_error("field_bw: cudaGetDevice failed"); return PSLAM_E_ARG; }
@@ -654,7 +685,10 @@ int bw_launch(const FieldParams &fp, int max_samples, float *finish, cudaStream_
     const int tiles = ceil_div(max_samples > 0 ? max_samples : 1, 128);
     int grid = ceil_div(tiles, bf::kCluster) * bf::kCluster;
     if (grid > ds.max_clusters * bf::kCluster) grid = ds.max_clusters * bf::kCluster;
-    launch_chain(k_field_bw, dim3(grid), dim3(bw::kBWThreads), bw::kSmemBytes, st, fp, reinterpret_cast<const unsigned char *>(fp.ws_tc), finish);
+    // scatter != NULL: the trilinear backward runs inside the kernel (warps 2-3) on the feature-gradient rows fp.g_feat;
+    // *scatter = the parameters the stand-alone scatter kernel would get (sample tables, gradient targets)
+    launch_chain(k_field_bw, dim3(grid), dim3(bw::kBWThreads), bw::kSmemBytes, st, fp, reinterpret_cast<const unsigned char *>(fp.ws_tc), finish,
+                 scatter ? *scatter : fp, scatter ? 1 : 0);
     PSLAM_CHECK_LAUNCH("field_bw");
     return 0;
 }
