@@ -69,6 +69,9 @@ int pslam_device_info(int *out3);
 /* PSLAM_OPT_FUSED_SCATTER (with PSLAM_OPT_FUSED_WGRAD): 1 = the trilinear backward (embedding scatter, ray gradients) of every
  * finished tile runs in two otherwise idle warps of that kernel; 0 (default: measured faster) = as a kernel of its own behind it. */
 #define PSLAM_OPT_FUSED_SCATTER 6
+/* PSLAM_OPT_WALK: octree walk of the fused pipeline.  0 (default) = a warp per ray (k_intersect_warp), 1 = block-cooperative,
+ * one trip per octree level over a shared queue of slab tests (k_intersect_bfs).  Identical results. */
+#define PSLAM_OPT_WALK 7
 int pslam_set_option(int key, int value);
 
 /* ------------------------------------------------------------------------

@@ -108,6 +108,7 @@ extern "C" int pslam_set_option(int key, int value)
     if (key == PSLAM_OPT_TILES && (value == 1 || value == 2)) { pp_set_enabled(value == 2); return 0; }
     if (key == PSLAM_OPT_FUSED_WGRAD && (value == 0 || value == 1)) { bw_set_enabled(value); return 0; }
     if (key == PSLAM_OPT_FUSED_SCATTER && (value == 0 || value == 1)) { bw_set_fused_scatter(value); return 0; }
+    if (key == PSLAM_OPT_WALK && (value == 0 || value == 1)) { set_walk_mode(value); return 0; }
     set_error("unknown option %d=%d", key, value);
     return PSLAM_E_ARG;
 }

@@ -131,8 +131,9 @@ __device__ long long *g_bw_trace = nullptr;
         if (g_bw_trace && blockIdx.x == 0 && (it_) < 4) g_bw_trace[((it_) * 2 + (who_)) * 16 + (slot_)] = clock64(); \
     } while (0)
 
+template <bool SCATTER>     // SCATTER: the trilinear backward rides along in warps 2-3 (PSLAM_OPT_FUSED_SCATTER)
 __global__ void __cluster_dims__(bf::kCluster, 1, 1) __launch_bounds__(bw::kBWThreads, 1)
-k_field_bw(FieldParams p, const unsigned char *__restrict__ wstream, float *__restrict__ finish, FieldParams ps, int fuse_scatter)
+k_field_bw(FieldParams p, const unsigned char *__restrict__ wstream, float *__restrict__ finish, FieldParams ps)
 {
     pdl_enter();
     using namespace bw;
@@ -410,7 +411,7 @@ k_field_bw(FieldParams p, const unsigned char *__restrict__ wstream, float *__re
                 __syncwarp();
                 if (lane == 0) BW_TRACE(it, 1, 14);
             }
-        } else if (fuse_scatter) {
+        } else if constexpr (SCATTER) {
             // ===================== warps 2-3: the trilinear backward of every finished tile (embedding scatter, ray gradients) ============
             // (PSLAM_OPT_FUSED_SCATTER, off by default.)  The chain leaves these warps and most issue slots idle and the stand-alone
             // scatter kernel is the tail of the iteration (25 us after this kernel) -- but measured: two warps without an L1 to
@@ -587,7 +588,7 @@ k_field_bw(FieldParams p, const unsigned char *__restrict__ wstream, float *__re
                     for (int j = 0; j < 4; ++j)
                         *reinterpret_cast<float4 *>(p.g_feat + (size_t)s * 16 + 4 * j) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
                 }
-                if (fuse_scatter && real) {                 // this row of the tile is in place for warps 2-3
+                if (SCATTER && real) {                      // this row of the tile is in place for warps 2-3
                     __threadfence();
                     atomicAdd(const_cast<int *>(scat_done), 1);
                 }
@@ -656,6 +657,25 @@ int bw_enabled() { return g_bw_enabled; }
 void bw_set_enabled(int on) { g_bw_enabled = on ? 1 : 0; }
 
 struct BWDeviceState { bool configured; int max_clusters; };
+template <bool SCATTER>
+static cudaError_t bw_configure(int *max_clusters)
+{
+    cudaError_t e = cudaFuncSetAttribute(k_field_bw<SCATTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, bw::kSmemBytes);
+    if (e != cudaSuccess || !max_clusters) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(num_sms() / bf::kCluster * bf::kCluster);
+    cfg.blockDim = dim3(bw::kBWThreads);
+    cfg.dynamicSmemBytes = bw::kSmemBytes;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = bf::kCluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    int n = 0;
+    e = cudaOccupancyMaxActiveClusters(&n, k_field_bw<SCATTER>, &cfg);
+    if (e != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = num_sms() / bf::kCluster; }
+    *max_clusters = n < num_sms() / bf::kCluster ? n : num_sms() / bf::kCluster;
+    return cudaSuccess;
+}
 static BWDeviceState g_bw_state[64] = {};
 
 // dgrad chain + weight gradients of the tiles whose forward saved masks and activations into fp.wg_scratch; `finish` = the
@@ -666,20 +686,9 @@ int bw_launch(const FieldParams &fp, int max_samples, float *finish, cudaStream_
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { set_error("field_bw: cudaGetDevice failed"); return PSLAM_E_ARG; }
     BWDeviceState &ds = g_bw_state[dev];
     if (!ds.configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_field_bw, cudaFuncAttributeMaxDynamicSharedMemorySize, bw::kSmemBytes);
+        cudaError_t e = bw_configure<false>(&ds.max_clusters);
+        if (e == cudaSuccess) e = bw_configure<true>(nullptr);
         if (e != cudaSuccess) { set_error("field_bw: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(num_sms() / bf::kCluster * bf::kCluster);
-        cfg.blockDim = dim3(bw::kBWThreads);
-        cfg.dynamicSmemBytes = bw::kSmemBytes;
-        cudaLaunchAttribute attr;
-        attr.id = cudaLaunchAttributeClusterDimension;
-        attr.val.clusterDim.x = bf::kCluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-        cfg.attrs = &attr; cfg.numAttrs = 1;
-        int n = 0;
-        e = cudaOccupancyMaxActiveClusters(&n, k_field_bw, &cfg);
-        if (e != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = num_sms() / bf::kCluster; }
-        ds.max_clusters = n < num_sms() / bf::kCluster ? n : num_sms() / bf::kCluster;
         ds.configured = true;
     }
     const int tiles = ceil_div(max_samples > 0 ? max_samples : 1, 128);
@@ -687,8 +696,8 @@ int bw_launch(const FieldParams &fp, int max_samples, float *finish, cudaStream_
     if (grid > ds.max_clusters * bf::kCluster) grid = ds.max_clusters * bf::kCluster;
     // scatter != NULL: the trilinear backward runs inside the kernel (warps 2-3) on the feature-gradient rows fp.g_feat;
     // *scatter = the parameters the stand-alone scatter kernel would get (sample tables, gradient targets)
-    launch_chain(k_field_bw, dim3(grid), dim3(bw::kBWThreads), bw::kSmemBytes, st, fp, reinterpret_cast<const unsigned char *>(fp.ws_tc), finish,
-                 scatter ? *scatter : fp, scatter ? 1 : 0);
+    if (scatter) launch_chain(k_field_bw<true>, dim3(grid), dim3(bw::kBWThreads), bw::kSmemBytes, st, fp, reinterpret_cast<const unsigned char *>(fp.ws_tc), finish, *scatter);
+    else launch_chain(k_field_bw<false>, dim3(grid), dim3(bw::kBWThreads), bw::kSmemBytes, st, fp, reinterpret_cast<const unsigned char *>(fp.ws_tc), finish, fp);
     PSLAM_CHECK_LAUNCH("field_bw");
     return 0;
 }

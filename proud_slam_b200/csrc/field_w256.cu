@@ -26,7 +26,7 @@ using namespace umma;
 
 namespace w2 {
 using namespace bf;
-constexpr int kW = 256;
+
 constexpr int kWThreads = 384;            // warp 0 TMA producer, warp 1 MMA issuer, warps 2-3 idle, warps 4-11 workers
 constexpr int kWStages = 5;
 constexpr int kWStage = 32768;            // one chunk: 256 rows x 32 k x (hi, lo) x 2 B

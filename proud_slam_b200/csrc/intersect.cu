@@ -166,12 +166,13 @@ __global__ void k_step_begin(int *__restrict__ counters, int *__restrict__ block
 {
     pdl_enter();
     if (threadIdx.x < 32) step_begin_counters(counters, threadIdx.x);
-    for (int i = threadIdx.x; i < nbh; i += blockDim.x) block_hits[i] = 0;   // hit-ray counts per kCompactRays rays (k_intersect_warp adds)
+    for (int i = threadIdx.x; i < nbh; i += blockDim.x) block_hits[i] = 0;   // hit-ray counts per kCompactRays rays (k_intersect_* add)
 }
 
 // Child records for the walk: rec[node][c] = (row id of child c or -1, centre of that child).  Expanding a node then
 // costs ONE dependent 16-byte load per lane instead of two (child id, then its centre); a node's eight records are one
 // 128-byte line.  Built once per map generation (PSLAM_F_NODE_CACHE_VALID tells the step that the table is current).
+// The row id takes the low 24 bits of .x (the cached walks need N <= 2^24), the top 8 bits say which children the CHILD has.
 __global__ void k_build_child_records(int N, const float *__restrict__ points, const int *__restrict__ children, int4 *__restrict__ rec,
                                       int *__restrict__ counters, int *__restrict__ block_hits, int nbh)
 {
@@ -182,8 +183,13 @@ __global__ void k_build_child_records(int N, const float *__restrict__ points, c
     if (t >= N * 8) return;
     const int node = t >> 3, c = t & 7;
     const int cid = __ldg(children + (int64_t)node * 9 + c);
-    int4 r = make_int4(cid, 0, 0, 0);
+    int4 r = make_int4(-1, 0, 0, 0);
     if (cid > -1) {
+        // .x = child row (24 bits) | which of ITS children exist (8 bits): the level-synchronous walk queues existing children only
+        unsigned mask = 0u;
+        if (__ldg(children + (int64_t)cid * 9 + 8) > 1)
+            for (int k = 0; k < 8; ++k) mask |= (__ldg(children + (int64_t)cid * 9 + k) > -1 ? 1u : 0u) << k;
+        r.x = (int)((unsigned)cid | (mask << 24));
         r.y = __float_as_int(__ldg(points + (int64_t)cid * 3));
         r.z = __float_as_int(__ldg(points + (int64_t)cid * 3 + 1));
         r.w = __float_as_int(__ldg(points + (int64_t)cid * 3 + 2));
@@ -298,7 +304,7 @@ k_intersect_warp(int R, float half_voxel, int n_max, float max_distance, const f
         if (have) {
             if (CACHED) {
                 const int4 r4 = __ldg(rec + (int64_t)cur * 8 + sub);
-                cid = r4.x;
+                cid = r4.x == -1 ? -1 : (r4.x & 0xFFFFFF);
                 hit = slab_nb(ray, __int_as_float(r4.y), __int_as_float(r4.z), __int_as_float(r4.w), __fmul_rn(half_voxel, (float)cside), lo, hi) && cid > -1;
             } else {
                 cid = __ldg(children + (int64_t)cur * 9 + sub);
@@ -395,6 +401,279 @@ k_intersect_warp(int R, float half_voxel, int n_max, float max_distance, const f
     if (tr) {
         intersect_stamp(tr, 4, clock64()); intersect_stamp(tr, 5, intersect_globaltimer());
         intersect_stamp(tr, 6, trips); intersect_stamp(tr, 7, warp_max_i(count));
+    }
+}
+
+static int g_walk_mode = 0;
+int walk_mode() { return g_walk_mode; }
+void set_walk_mode(int m) { g_walk_mode = m ? 1 : 0; }
+
+// ---- block-cooperative level-synchronous walk (PSLAM_OPT_WALK = 1) ---------------------------------------------------------
+// The warp-per-ray walk above is bound by instruction issue: near the root a ray has one or two pending nodes, so most lanes of
+// its warp idle while the warp still pays the ~180 instructions of a trip.  With the DFS keys the walk can also run breadth
+// first for a whole block of rays: the slab tests of ALL its rays at one octree level sit in a shared queue -- one item per
+// EXISTING child of a node hit one level up (the child records carry each child's own child mask, so empty octants are never
+// tested: ~2.7 tests per expansion instead of 8) -- every lane a test; a hit internal child queues its existing children for
+// the next level (warp scan + one atomic per warp), a hit leaf goes to its ray's hit list (one shared-memory atomic for the
+// slot).  One trip per octree level for the block.
+// A ray with more than n_max hit leaves, or a queue overflow, falls back to the exact warp walk for those rays (walk_ray_warp32:
+// the n_max largest keys), so results are the same in every case.
+constexpr int kBfsRays = 16, kBfsThreads = 128, kBfsQueue = 1024;
+constexpr size_t kBfsSmem = sizeof(unsigned long long) * (2 * kBfsQueue + kBfsRays * kRayHits + (kBfsThreads / 32) * kRayStack) +
+                            sizeof(int) * (2 * kBfsQueue + 3 * kBfsRays * kRayHits + (kBfsThreads / 32) * kRayStack + kBfsRays * 8 + 16);
+
+// the exact walk of ONE ray by a whole warp (k_intersect_warp with one ray per warp) into the ray's hit arrays; returns the hit count
+template <bool CACHED>
+__device__ __forceinline__ int walk_ray_warp32(const Ray &ray, float half_voxel, int n_max, const float *__restrict__ points,
+                                               const int *__restrict__ children, const int4 *__restrict__ rec, int *st_id,
+                                               unsigned long long *st_key, int *h_id, float *h_lo, float *h_hi, unsigned long long *h_key,
+                                               bool &overflow)
+{
+    const int lane = threadIdx.x & 31, grp = lane >> 3, sub = lane & 7;
+    int top = 0, cnt = 0;
+    {
+        const int side = __ldg(children + 8);
+        float lo, hi;
+        if (slab(ray, __ldg(points), __ldg(points + 1), __ldg(points + 2), __fmul_rn(half_voxel, (float)side), lo, hi)) {
+            if (side == 1) {
+                if (lane == 0) { h_id[0] = 0; h_lo[0] = lo; h_hi[0] = hi; h_key[0] = 0ull; }
+                cnt = 1;
+            } else {
+                if (lane == 0) { st_id[0] = (31 - __clz(side)) << 26; st_key[0] = 0ull; }
+                top = 1;
+            }
+        }
+    }
+    __syncwarp();
+    const unsigned lt = (1u << lane) - 1u;
+    while (top > 0) {
+        const int take = min(top, 4);
+        const bool have = grp < take;
+        int e = 0;
+        unsigned long long key = 0ull;
+        if (have) { e = st_id[top - 1 - grp]; key = st_key[top - 1 - grp]; }
+        top -= take;
+        __syncwarp();
+        const int level = e >> 26, cur = e & 0x3FFFFFF;
+        const int cside = (1 << level) >> 1;
+        bool hit = false;
+        int cid = -1;
+        float lo = 0.f, hi = 0.f;
+        if (have) {
+            if (CACHED) {
+                const int4 r4 = __ldg(rec + (int64_t)cur * 8 + sub);
+                cid = r4.x == -1 ? -1 : (r4.x & 0xFFFFFF);
+                hit = slab_nb(ray, __int_as_float(r4.y), __int_as_float(r4.z), __int_as_float(r4.w), __fmul_rn(half_voxel, (float)cside), lo, hi) && cid > -1;
+            } else {
+                cid = __ldg(children + (int64_t)cur * 9 + sub);
+                if (cid > -1)
+                    hit = slab_nb(ray, __ldg(points + (int64_t)cid * 3), __ldg(points + (int64_t)cid * 3 + 1), __ldg(points + (int64_t)cid * 3 + 2),
+                                  __fmul_rn(half_voxel, (float)cside), lo, hi);
+            }
+        }
+        const bool leaf = hit && cside == 1, inner = hit && cside > 1;
+        const unsigned long long ckey = (key << 3) | (unsigned long long)sub;
+        const unsigned m_in = __ballot_sync(0xffffffffu, inner), m_leaf = __ballot_sync(0xffffffffu, leaf);
+        if (inner) {
+            const int pos = top + __popc(m_in & lt);
+            if (pos < kRayStack) { st_id[pos] = cid | ((level - 1) << 26); st_key[pos] = ckey; }
+            else overflow = true;
+        }
+        top = min(top + __popc(m_in), kRayStack);
+        unsigned rest = m_leaf;
+        while (rest) {                                        // (uniform: every lane holds the same mask)
+            const int src = __ffs(rest) - 1;
+            rest &= rest - 1;
+            const int c_id = __shfl_sync(0xffffffffu, cid, src);
+            const float c_lo = __shfl_sync(0xffffffffu, lo, src), c_hi = __shfl_sync(0xffffffffu, hi, src);
+            const unsigned long long c_key = __shfl_sync(0xffffffffu, ckey, src);
+            if (cnt < n_max) {
+                if (lane == 0) { h_id[cnt] = c_id; h_lo[cnt] = c_lo; h_hi[cnt] = c_hi; h_key[cnt] = c_key; }
+                ++cnt;
+            } else {
+                unsigned long long mk = ~0ull;
+                int mi = -1;
+                for (int i = lane; i < n_max; i += 32) {
+                    const unsigned long long k2 = h_key[i];
+                    if (k2 < mk) { mk = k2; mi = i; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const unsigned long long ok = __shfl_xor_sync(0xffffffffu, mk, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+                    if (ok < mk) { mk = ok; mi = oi; }
+                }
+                if (c_key > mk && lane == 0) { h_id[mi] = c_id; h_lo[mi] = c_lo; h_hi[mi] = c_hi; h_key[mi] = c_key; }
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+    }
+    return cnt;
+}
+
+template <bool CACHED>
+__global__ void __launch_bounds__(kBfsThreads)
+k_intersect_bfs(int R, float half_voxel, int n_max, float max_distance, const float *__restrict__ ray_start,
+                const float *__restrict__ ray_dir, const float *__restrict__ points, const int *__restrict__ children,
+                const int4 *__restrict__ rec, int *__restrict__ hit_idx, float *__restrict__ hit_min, float *__restrict__ hit_max,
+                int *__restrict__ hit_count, int *__restrict__ block_hits, int *__restrict__ counters)
+{
+    pdl_enter();
+    extern __shared__ __align__(16) unsigned char s_bfs[];
+    unsigned long long *q_key = reinterpret_cast<unsigned long long *>(s_bfs);                  // [2][kBfsQueue]
+    unsigned long long *h_key = q_key + 2 * kBfsQueue;                                           // [rays][kRayHits]
+    unsigned long long *f_key = h_key + kBfsRays * kRayHits;                                     // [warps][kRayStack] (fallback walk)
+    int *q_node = reinterpret_cast<int *>(f_key + (kBfsThreads / 32) * kRayStack);               // [2][kBfsQueue]: ray << 26 | node row
+    int *h_id = q_node + 2 * kBfsQueue;                                                          // [rays][kRayHits]
+    float *h_lo = reinterpret_cast<float *>(h_id + kBfsRays * kRayHits);
+    float *h_hi = h_lo + kBfsRays * kRayHits;
+    int *f_id = reinterpret_cast<int *>(h_hi + kBfsRays * kRayHits);                             // [warps][kRayStack]
+    float *s_ray = reinterpret_cast<float *>(f_id + (kBfsThreads / 32) * kRayStack);             // [rays][8]: o, inv
+    int *h_cnt = reinterpret_cast<int *>(s_ray + kBfsRays * 8);                                  // [rays] hits found (may exceed n_max)
+    __shared__ int s_misc[8];                                                                    // queue lengths [2], queue overflow, block max, hit rays
+    int *q_n = s_misc;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r0 = blockIdx.x * kBfsRays;
+    if (n_max > kRayHits) n_max = kRayHits;
+    if (tid < 8) s_misc[tid] = 0;
+    __syncthreads();
+    const int root_side = __ldg(children + 8);
+    int level = 31 - __clz(root_side);
+    // ---- rays and the root (row 0, intersect_gpu.cu:232): a hit internal root queues its existing children ----
+    // queue item = one slab test: ray (5 bits) | child index c (3 bits) | PARENT row (24 bits), with the key of the child
+    if (tid < kBfsRays) {
+        const int r = r0 + tid;
+        int cnt = 0;
+        if (r < R) {
+            const Ray ray = load_ray(ray_start, ray_dir, r);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { s_ray[tid * 8 + a] = ray.o[a]; s_ray[tid * 8 + 4 + a] = ray.inv[a]; }
+            float lo, hi;
+            if (slab(ray, __ldg(points), __ldg(points + 1), __ldg(points + 2), __fmul_rn(half_voxel, (float)root_side), lo, hi)) {
+                if (root_side == 1) {
+                    h_id[tid * kRayHits] = 0; h_lo[tid * kRayHits] = lo; h_hi[tid * kRayHits] = hi; h_key[tid * kRayHits] = 0ull;
+                    cnt = 1;
+                } else {
+                    for (int c = 0; c < 8; ++c) {
+                        if (__ldg(&rec[c].x) == -1) continue;
+                        const int at = atomicAdd(q_n, 1);
+                        q_node[at] = (tid << 27) | (c << 24);          // parent = row 0
+                        q_key[at] = (unsigned long long)c;
+                    }
+                }
+            }
+        }
+        h_cnt[tid] = cnt;
+    }
+    __syncthreads();
+    // ---- one trip per octree level: the items of a level are the existing children of the nodes hit one level up ----
+    int cur = 0;
+    for (; level >= 1; --level) {
+        const int nq = q_n[cur];
+        if (nq == 0) break;
+        const int cside = (1 << level) >> 1;
+        const float half = __fmul_rn(half_voxel, (float)cside);
+        int *qn_next = q_n + (cur ^ 1);
+        for (int base = 0; base < nq; base += kBfsThreads) {
+            const int t = base + tid;
+            bool hit = false;
+            int cid = -1, rl = 0;
+            unsigned cmask = 0u;
+            float lo = 0.f, hi = 0.f;
+            unsigned long long ckey = 0ull;
+            if (t < nq) {
+                const unsigned e = (unsigned)q_node[cur * kBfsQueue + t];
+                rl = (int)(e >> 27);
+                ckey = q_key[cur * kBfsQueue + t];
+                Ray ray;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) { ray.o[a] = s_ray[rl * 8 + a]; ray.inv[a] = s_ray[rl * 8 + 4 + a]; }
+                const int4 r4 = __ldg(rec + (int64_t)(e & 0xFFFFFFu) * 8 + ((e >> 24) & 7u));
+                cid = r4.x & 0xFFFFFF;
+                cmask = (unsigned)r4.x >> 24;
+                hit = slab_nb(ray, __int_as_float(r4.y), __int_as_float(r4.z), __int_as_float(r4.w), half, lo, hi);
+            }
+            if (cside == 1) {                                 // leaves: straight to the ray's hit list
+                if (hit) {
+                    const int slot = atomicAdd(h_cnt + rl, 1);
+                    if (slot < n_max) {
+                        h_id[rl * kRayHits + slot] = cid; h_lo[rl * kRayHits + slot] = lo; h_hi[rl * kRayHits + slot] = hi; h_key[rl * kRayHits + slot] = ckey;
+                    }
+                }
+            } else {                                          // a hit internal node queues its existing children (one atomic per warp)
+                const int n_push = hit ? __popc(cmask) : 0;
+                int x = n_push;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int y = __shfl_up_sync(0xffffffffu, x, o);
+                    if (lane >= o) x += y;
+                }
+                const int total = __shfl_sync(0xffffffffu, x, 31);
+                int at = 0;
+                if (lane == 31 && total) at = atomicAdd(qn_next, total);
+                at = __shfl_sync(0xffffffffu, at, 31) + x - n_push;
+                unsigned m = hit ? cmask : 0u;
+                while (m) {
+                    const int c = __ffs(m) - 1;
+                    m &= m - 1;
+                    if (at < kBfsQueue) {
+                        q_node[(cur ^ 1) * kBfsQueue + at] = (rl << 27) | (c << 24) | cid;
+                        q_key[(cur ^ 1) * kBfsQueue + at] = (ckey << 3) | (unsigned long long)c;
+                    } else s_misc[2] = 1;                     // queue overflow: every ray of the block takes the exact walk
+                    ++at;
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) { q_n[cur] = 0; if (q_n[cur ^ 1] > kBfsQueue) q_n[cur ^ 1] = kBfsQueue; }
+        cur ^= 1;
+        __syncthreads();
+    }
+    // ---- per ray: (exact re-walk where needed,) rank by (entry depth, key descending), trim, store ----
+    const bool all_exact = s_misc[2] != 0;
+    bool overflow = false;
+    for (int rl = warp; rl < kBfsRays; rl += kBfsThreads / 32) {
+        const int r = r0 + rl;
+        if (r >= R) break;
+        int *hi_ = h_id + rl * kRayHits;
+        float *hl = h_lo + rl * kRayHits, *hh = h_hi + rl * kRayHits;
+        unsigned long long *hk = h_key + rl * kRayHits;
+        int cnt = h_cnt[rl];
+        if (all_exact || cnt > n_max) {
+            Ray ray;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { ray.o[a] = s_ray[rl * 8 + a]; ray.inv[a] = s_ray[rl * 8 + 4 + a]; }
+            __syncwarp();
+            cnt = walk_ray_warp32<CACHED>(ray, half_voxel, n_max, points, children, rec, f_id + warp * kRayStack, f_key + warp * kRayStack, hi_, hl, hh, hk, overflow);
+            __syncwarp();
+        }
+        int count = 0;
+        for (int i = lane; i < cnt; i += 32) {
+            const float li = hl[i];
+            const unsigned long long ki = hk[i];
+            int rank = 0;
+            for (int j = 0; j < cnt; ++j) {
+                const float lj = hl[j];
+                rank += (lj < li || (lj == li && hk[j] > ki)) ? 1 : 0;
+            }
+            if (!(li > max_distance)) {       // (the dropped hits are the tail of the order: voxel_helpers.py:578)
+                const int64_t at = (int64_t)rank * R + r;
+                hit_idx[at] = hi_[i]; hit_min[at] = li; hit_max[at] = hh[i];
+                ++count;
+            }
+        }
+        count = warp_sum_i(count);
+        if (lane == 0) {
+            hit_count[r] = count;
+            if (count > 0) { atomicAdd(s_misc + 4, 1); atomicMax(s_misc + 3, count); }
+        }
+    }
+    if (overflow) atomicOr(counters + PSLAM_C_OVERFLOW, 2);
+    __syncthreads();
+    if (tid == 0 && s_misc[4] > 0) {
+        atomicAdd(block_hits + (blockIdx.x * kBfsRays) / kCompactRays, s_misc[4]);   // (kBfsRays divides kCompactRays)
+        atomicMax(counters + PSLAM_C_P, s_misc[3]);
     }
 }
 
@@ -681,7 +960,7 @@ int launch_intersect_fused(const pslam_render_t *p, cudaStream_t st)
     const int nb = ceil_div(p->R, kCompactRays);
     int *block_hits = p->scratch_i;  // [nb]
     // the record table costs a pass over the octree per map generation: worth it while the walk is the larger job
-    const bool cached = p->node_cache && p->node_cache_bytes >= (int64_t)128 * p->N && ((uintptr_t)p->node_cache % 16 == 0);
+    const bool cached = p->node_cache && p->node_cache_bytes >= (int64_t)128 * p->N && ((uintptr_t)p->node_cache % 16 == 0) && p->N <= (1 << 24);
     static int forced = -1;                                // PSLAM_INTERSECT_RPW=1|2|4: measurement override
     if (forced < 0) {
         const char *e = getenv("PSLAM_INTERSECT_RPW");
@@ -698,6 +977,8 @@ int launch_intersect_fused(const pslam_render_t *p, cudaStream_t st)
         launch_chain(k_build_child_records, dim3((int)ceil_div64((int64_t)p->N * 8, 256)), dim3(256), 0, st, p->N, p->centres, p->structure, rec, p->counters, block_hits, nb);
         PSLAM_CHECK_LAUNCH("build_child_records");
     } else {
+        // (an L2 prefetch of the child records / corner ids / embedding rows here was measured: no gain -- the walks are bound by
+        //  their dependent instruction chains, not by DRAM round trips)
         launch_chain(k_step_begin, dim3(1), dim3(256), 0, st, p->counters, block_hits, nb);
         PSLAM_CHECK_LAUNCH("step_begin");
     }
@@ -715,7 +996,21 @@ int launch_intersect_fused(const pslam_render_t *p, cudaStream_t st)
                      p->max_distance, p->rays_o, p->rays_d, p->centres, p->structure, (const int4 *)(C ? rec : nullptr), p->hit_idx, p->hit_min,       \
                      p->hit_max, p->hit_count, block_hits, p->counters);                                                              \
     } while (0)
-    if (cached) {
+    // PSLAM_OPT_WALK: 0 (default) = a warp per ray, 1 = the block-cooperative level-synchronous walk.  Measured at 8192 rays:
+    // 29 us against 31 us (26 us when it tested all eight child slots): with one trip per octree level and two block barriers per
+    // trip its few resident warps wait on their own dependent chains, so fewer instructions did not make it faster.
+    if (cached && walk_mode() == 1) {
+        static PerDevice bfs_once = {};
+        bool &bfs_configured = bfs_once.done[current_device()];
+        if (!bfs_configured) {
+            cudaError_t e = cudaFuncSetAttribute(k_intersect_bfs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBfsSmem);
+            if (e != cudaSuccess) { set_error("intersect: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+            bfs_configured = true;
+        }
+        launch_chain(k_intersect_bfs<true>, dim3(ceil_div(p->R, kBfsRays)), dim3(kBfsThreads), kBfsSmem, st, p->R, half_voxel, p->n_max, p->max_distance,
+                     p->rays_o, p->rays_d, p->centres, p->structure, (const int4 *)rec, p->hit_idx, p->hit_min, p->hit_max, p->hit_count, block_hits,
+                     p->counters);
+    } else if (cached) {
         if (rpw == 1) PSLAM_LAUNCH_INTERSECT(true, 1); else if (rpw == 2) PSLAM_LAUNCH_INTERSECT(true, 2); else PSLAM_LAUNCH_INTERSECT(true, 4);
     } else {
         if (rpw == 1) PSLAM_LAUNCH_INTERSECT(false, 1); else if (rpw == 2) PSLAM_LAUNCH_INTERSECT(false, 2); else PSLAM_LAUNCH_INTERSECT(false, 4);

@@ -14,6 +14,8 @@ static inline int scratch_i_composite_off(int R) { return scratch_i_sample_off(R
 // intersect.cu
 int scan_partials(int *partials, int nb, int *total_out, cudaStream_t st);
 int launch_intersect_fused(const pslam_render_t *p, cudaStream_t st);
+int walk_mode();
+void set_walk_mode(int m);   // PSLAM_OPT_WALK
 int launch_build_node_cache(int N, const float *centres, const int *structure, void *node_cache, cudaStream_t st);
 // sample.cu
 int launch_sample_fused(const pslam_render_t *p, cudaStream_t st);

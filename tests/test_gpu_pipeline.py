@@ -264,6 +264,44 @@ def test_programmatic_launch_changes_nothing(device):
         assert rel_err(a, b) < 1e-5
 
 
+@pytest.mark.parametrize("option,value", [(7, 1), (6, 1)])
+def test_optional_kernel_paths_change_nothing(option, value, device):
+    """PSLAM_OPT_WALK = 1 (block-cooperative level-synchronous octree walk) and PSLAM_OPT_FUSED_SCATTER = 1 (trilinear backward in
+    the idle warps of the fused backward kernel) against the defaults: hit lists, samples and forward outputs bit-identical,
+    gradients equal up to the order of the floating-point atomics."""
+    from proud_slam_b200 import _lib, scene as sc
+    s, ms = util.build_scene("replica_small")
+    dec = util.test_decoder(width=128, seed=3)
+    rays_o, rays_d, rgb, depth = sc.sample_batch(s, [0, 1, 2], 1024, seed=13)
+    msd = util.to_device(ms, device)
+    msd["voxel_vertex_emb"] = msd["voxel_vertex_emb"].detach()
+    decd = [p.detach().to(device) for p in dec]
+    cw = (util.CRIT["rgb_weight"], util.CRIT["depth_weight"], util.CRIT["fs_weight"], util.CRIT["sdf_weight"])
+    res = []
+    try:
+        for v in (0, value):
+            assert _lib.lib().pslam_set_option(option, v) == 0
+            pipe, g_emb, g_dec = _run_pipeline(
+                device, rays_o.to(device), rays_d.to(device), rgb.to(device), depth.to(device), msd, decd, voxel_size=s.voxel_size,
+                step_size=0.1 * s.voxel_size, truncation=util.CRIT["truncation"], max_distance=10.0, max_depth=util.CRIT["max_depth"],
+                weights=cw, noise=None, tracking=False)
+            n = pipe.counts()["n_samples"]
+            R = rays_o.shape[1]
+            res.append([pipe.hit_count[:R].clone(), pipe.hit_idx[: 50 * R].clone() * 0 + pipe.hit_idx[: 50 * R].clone(), pipe.samp_vox[:n].clone(),
+                        pipe.samp_z[:n].clone(), pipe.samp_out[:n].clone(), pipe.loss.clone(),
+                        g_emb.clone(), pipe.g_rays_o.clone(), pipe.g_rays_d.clone()] + [g.clone() for g in g_dec])
+    finally:
+        _lib.lib().pslam_set_option(option, 0)
+    cnt = res[0][0].long()
+    assert torch.equal(res[0][0], res[1][0])
+    valid = (torch.arange(50, device=device)[:, None] < cnt[None, :]).reshape(-1)      # slot-major [50, R]: only the valid slots are defined
+    assert torch.equal(res[0][1][valid], res[1][1][valid])
+    for a, b in zip(res[0][2:6], res[1][2:6]):
+        assert torch.equal(a, b)
+    for a, b in zip(res[0][6:], res[1][6:]):
+        assert rel_err(a, b) < 1e-5
+
+
 def test_f16_operand_range_is_guarded(device):
     """3xF16 build: operands are kept in f16's window by fixed power-of-two scales; a decoder whose activations leave it
     (|16 x value| >= 32752) must be reported through the overflow counter, not silently clipped."""

@@ -63,7 +63,7 @@ def test_process_wide_options_are_validated():
     hdr = open(os.path.join(ROOT, "include", "proud_slam_b200.h")).read()
     keys = {name: int(val) for name, val in re.findall(r"#define (PSLAM_OPT_[A-Z_]+) (\d+)", hdr)}
     assert keys == {"PSLAM_OPT_DECODER": 1, "PSLAM_OPT_SAVE_ACT": 2, "PSLAM_OPT_PDL": 3, "PSLAM_OPT_TILES": 4, "PSLAM_OPT_FUSED_WGRAD": 5,
-                    "PSLAM_OPT_FUSED_SCATTER": 6}
+                    "PSLAM_OPT_FUSED_SCATTER": 6, "PSLAM_OPT_WALK": 7}
     try:
         for key, values in ((1, (0, 1, 2)), (2, (0, 1)), (3, (0, 1)), (4, (1, 2)), (5, (0, 1))):
             for v in values:
