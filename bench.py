@@ -309,10 +309,16 @@ def run_gpu(args):
         transport = "NCCL all_gather + all_reduce (--nccl)"
     fg = FlatGrads(ms["voxel_vertex_emb"], dec, flat=None if peer is None else peer.flat)
     flat, g_emb, g_dec = fg.flat, fg.g_emb, fg.g_dec
-    host = [t.pin_memory() for t in batch_cpu]                        # e2e: inputs start in pinned host memory
-    dev_in = [torch.empty_like(t, device=device) for t in batch_cpu]
-    for d, h in zip(dev_in, host):
-        d.copy_(h)
+    # e2e: the step's inputs (rays_o, rays_d, rgb [R,3], depth [R]) start in ONE pinned host block and cross PCIe as one copy
+    sizes = [t.numel() for t in batch_cpu]
+    host_block = torch.empty(sum(sizes), dtype=torch.float32).pin_memory()
+    dev_block = torch.empty(sum(sizes), dtype=torch.float32, device=device)
+    host, dev_in, off = [], [], 0
+    for t, n in zip(batch_cpu, sizes):
+        host.append(host_block[off:off + n].view_as(t).copy_(t))
+        dev_in.append(dev_block[off:off + n].view_as(t))
+        off += n
+    dev_block.copy_(host_block)
     spr = 64 if SCENE != "scannet_large" else 128
     pipe = RenderPipeline(R, device, samples_per_ray=spr)
     pipe.bind(dev_in[0], dev_in[1], ms, dec, voxel_size=s.voxel_size, step_size=0.1 * s.voxel_size, truncation=0.1,
@@ -378,8 +384,7 @@ def run_gpu(args):
 
     # end to end through the public call with HOST buffers: H2D of the step's inputs, D2H of the loss
     def e2e_step(i):
-        for d, h in zip(dev_in, host):
-            d.copy_(h, non_blocking=True)
+        dev_block.copy_(host_block, non_blocking=True)
         step(i + 1)
         loss_host.copy_(pipe.loss, non_blocking=True)
 

@@ -10,6 +10,12 @@ to one big batch (up to fp32 re-association):
 2. after backward, one sum-all-reduce of a single flat fp32 buffer ``[E*16 | decoder]`` that the
    kernels scattered their gradients straight into (no staging copy before the collective).
 
+One known difference from ONE big padded batch: the reference's first-sign-change search runs over rows padded to the batch's
+longest ray with sdf = 1 (``render_helpers.py:510-545``).  A rank's (or chunk's) OWN longest ray has no pad locally, so if its
+last sdf is negative and it has no earlier sign change it keeps ``z_min = z[0]`` where the big batch (longer rows) would take its
+last sample; the loss closure itself uses the global row length.  At most one ray per rank and iteration; exchanging the row
+length before compositing would cost a third synchronisation point per step.
+
 ``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests) is the plumbing.  On the GPUs of one box both exchanges run
 inside ``pslam_render_step`` over NVLink peer memory (``PeerExchange`` below, ``csrc/peer.cu``): the loss kernel stores its raw
 sums into every peer and waits for theirs, and a two-shot kernel all-reduces the flat buffer -- no host-side collective in
