@@ -567,6 +567,8 @@ def run_gpu(args):
         # finish = 13 (N > 1 in-kernel exchanges: + all-reduce = 14; NCCL form: + prologue + loss coeffs = 15).  torch's
         # gradient-buffer fill and NCCL's kernels are not counted; profiles/r02_launches.csv is the launch list.
         per_step = (13 if world == 1 else (14 if peer is not None else 15)) if tc else 19
+        if tc and WIDTH == 256:       # width 256: two pack kernels (SIMT + tcgen05 stream), chain backward + k_wgrad_w256 instead of the fused kernel + finish
+            per_step += 1
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": dtype,
