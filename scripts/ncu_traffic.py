@@ -21,7 +21,7 @@ def main():
         h, u = rr[0], rr[1]
         ki, ri, wi = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
         for r in rr[2:]:
-            name = re.sub(r"^void ", "", r[ki]).split("(")[0]
+            name = re.sub(r"^void ", "", r[ki]).split("(")[0].split("<")[0]      # base name: bench.py looks kernels up without template arguments
             val = float(r[ri].replace(",", "")) * UNIT[u[ri]] + float(r[wi].replace(",", "")) * UNIT[u[wi]]
             kernels.setdefault(name, []).append(val)
     commit = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
