@@ -325,7 +325,7 @@ def run_gpu(args):
               max_distance=10.0, max_depth=10.0, target_rgb=dev_in[2], target_depth=dev_in[3], noise=None, seed=1,
               weights=CRIT_W, g_emb=g_emb, g_dec=g_dec, grad_rays=True, defer_loss=(world > 1 and peer is None))
     if peer is not None:
-        peer.bind(pipe)
+        peer.bind(pipe, allreduce=not args.no_allreduce)
     rows = torch.zeros(world, 16, dtype=torch.float64, device=device)
     loss_host = torch.empty(16, pin_memory=True)
     flush = torch.empty(192 * 1024 * 1024 // 4, device=device)       # 192 MiB > 126 MB L2
@@ -704,6 +704,7 @@ def main():
     ap.add_argument("--width", type=int, default=WIDTH, choices=[128, 256], help="decoder width (configs/replica: 128, configs/scannet: 256)")
     ap.add_argument("--strong", action="store_true", help="strong scaling: --rays is the whole batch, every rank renders 1/N of it")
     ap.add_argument("--nccl", action="store_true", help="N > 1: NCCL all_gather + all_reduce from the host instead of the in-kernel exchanges")
+    ap.add_argument("--no-allreduce", action="store_true", help="N > 1 (measurement only): loss closure across ranks but no gradient all-reduce")
     ap.add_argument("--no-extras", action="store_true", help="skip the tracking and CPU-baseline legs (sweeps)")
     args = ap.parse_args()
     if args.impl == "reference":

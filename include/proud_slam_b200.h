@@ -268,8 +268,12 @@ typedef struct {
     void *sync[PSLAM_MAX_PEERS];
     float *flat[PSLAM_MAX_PEERS];        /* all NULL: no gradient all-reduce inside the step */
     int64_t flat_count;
+    void *stage[PSLAM_MAX_PEERS];        /* optional: every rank's staging area of pslam_peer_stage_bytes(flat_count, world) bytes
+                                            (peer-mapped, zeroed once).  With it, buffers up to 4 MB take the low-latency
+                                            all-reduce: data and flag travel in the same 16-byte store, no barrier round trips. */
 } pslam_peer_t;
 int64_t pslam_peer_sync_bytes(void);
+int64_t pslam_peer_stage_bytes(int64_t flat_count, int world);
 /* The all-reduce alone (sum over ranks, in place in every rank's `flat`); fail_flag: optional device int that gets bit 4
  * (value 16) if a peer did not arrive within ~2 s. */
 int pslam_peer_allreduce(const pslam_peer_t *peer, int *fail_flag, pslam_stream_t stream);

@@ -37,7 +37,7 @@ MAX_PEERS = 8
 class PeerT(C.Structure):
     """pslam_peer_t: every rank's peer-mapped exchange area and flat gradient buffer (include/proud_slam_b200.h)."""
     _fields_ = [("world", C.c_int), ("rank", C.c_int), ("sync", C.c_void_p * MAX_PEERS), ("flat", C.c_void_p * MAX_PEERS),
-                ("flat_count", C.c_int64)]
+                ("flat_count", C.c_int64), ("stage", C.c_void_p * MAX_PEERS)]
 
 
 class RenderT(C.Structure):
@@ -102,6 +102,7 @@ _PROTOTYPES = {
     "pslam_render_scratch_f_count": (C.c_int64, [_I]),
     "pslam_build_node_cache": (C.c_int, [_I, _P, _P, _P, _S]),
     "pslam_peer_sync_bytes": (C.c_int64, []),
+    "pslam_peer_stage_bytes": (C.c_int64, [C.c_int64, _I]),
     "pslam_peer_allreduce": (C.c_int, [C.POINTER(PeerT), _P, _S]),
     "pslam_render_sample": (C.c_int, [C.POINTER(RenderT), _S]),
     "pslam_render_forward": (C.c_int, [C.POINTER(RenderT), _S]),

@@ -294,8 +294,7 @@ k_loss_reduce(pslam_render_t p, const float *__restrict__ part_f, const int *__r
         const unsigned long long e = s_epoch;
         const int par = (int)(e & 1ull);
         if (tid < world * 16) static_cast<PeerSync *>(p.peer.sync[tid >> 4])->rows[par][rank][tid & 15] = p.loss_raw[tid & 15];
-        __threadfence_system();
-        __syncthreads();
+        __syncthreads();               // (the flag threads' st.release.sys below is cumulative over what the barrier ordered before them)
         if (tid < world) {
             st_release_sys(&static_cast<PeerSync *>(p.peer.sync[tid])->loss_flag[par][rank], e);
             if (!spin_until(&mine->loss_flag[par][tid], e)) s_fail = 1;

@@ -92,17 +92,23 @@ class PeerExchange:
         nsync = int(lib.pslam_peer_sync_bytes())
         self.flat = symm_mem.empty(int(flat_numel), dtype=torch.float32, device=device)
         self.sync = symm_mem.empty((nsync + 7) // 8, dtype=torch.int64, device=device)
+        nstage = int(lib.pslam_peer_stage_bytes(int(flat_numel), self.world))
+        self.stage = symm_mem.empty((nstage + 15) // 16 * 4, dtype=torch.int32, device=device) if nstage > 0 else None
         self.flat.zero_()
         self.sync.zero_()
+        if self.stage is not None:
+            self.stage.zero_()
         torch.cuda.synchronize(device)
         self._h_flat = symm_mem.rendezvous(self.flat, group)
         self._h_sync = symm_mem.rendezvous(self.sync, group)
+        self._h_stage = symm_mem.rendezvous(self.stage, group) if self.stage is not None else None
         dist.barrier(group)                    # every rank's exchange area is zero before anybody raises a flag in it
         self.table = _lib.PeerT()
         self.table.world, self.table.rank, self.table.flat_count = self.world, self.rank, int(flat_numel)
         for q in range(self.world):
             self.table.sync[q] = int(self._h_sync.buffer_ptrs[q])
             self.table.flat[q] = int(self._h_flat.buffer_ptrs[q])
+            self.table.stage[q] = int(self._h_stage.buffer_ptrs[q]) if self._h_stage is not None else None
         self.fail = torch.zeros(1, dtype=torch.int32, device=device)
         self._lib, self._stream_ptr, self.device = lib, _lib.stream_ptr, torch.device(device)
 

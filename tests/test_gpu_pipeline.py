@@ -371,6 +371,49 @@ def test_ragged_batch_sizes_hit_lists(R, device):
     assert pipe.counts()["R_h"] == int(ref_hits.sum())
 
 
+@pytest.mark.parametrize("walk", [0, 1])
+@pytest.mark.parametrize("n_max", [1, 3, 6])
+def test_hit_cap_keeps_the_first_hits_of_the_reference_walk(n_max, walk, device):
+    """Rays that hit more leaves than the cap: the reference's DFS stops after n_max emissions (intersect_gpu.cu:233), i.e. it
+    keeps the FIRST n_max leaves of its walk order -- not the nearest.  The product's walks run in another order and keep the
+    n_max largest DFS keys instead; both walks (PSLAM_OPT_WALK 0 / 1) must reproduce the oracle's DFS, cut included."""
+    import oracle
+    from oracle import render_oracle as ro
+    from proud_slam_b200 import _lib, scene as sc
+    from proud_slam_b200.pipeline import RenderPipeline
+    s, ms = util.build_scene("replica_small")
+    dec = [p.detach().to(device) for p in ro.decoder_params(seed=1)]
+    rays_o, rays_d, rgb, depth = sc.sample_batch(s, [0, 3], 700, seed=21)
+    R = rays_o.shape[1]
+    inv = util.device_rcp(rays_d.reshape(-1, 3), device)
+    idx, tmin, tmax = oracle.svo_intersect(rays_o.reshape(1, R, 3).numpy(), rays_d.reshape(1, R, 3).numpy(),
+                                           ms["voxel_center_xyz"].detach().reshape(1, -1, 3).numpy(), ms["voxel_structure"].reshape(1, -1, 9).numpy(),
+                                           float(s.voxel_size), n_max, np.asarray(inv).reshape(1, R, 3))
+    idx, tmin, tmax = torch.from_numpy(idx)[0], torch.from_numpy(tmin)[0], torch.from_numpy(tmax)[0]
+    full, _ = ro.ray_intersect_vox(rays_o, rays_d, ms["voxel_center_xyz"].detach(), ms["voxel_structure"], s.voxel_size, 10, 10.0, inv_dir=inv)
+    assert int(full["intersected_voxel_idx"].ne(-1).sum(-1).max()) > n_max          # the cap really cuts
+    tmin = tmin.masked_fill(idx.eq(-1), 10.0)
+    tmin, order = tmin.sort(dim=-1, stable=True)
+    idx, tmax = idx.gather(-1, order), tmax.gather(-1, order)
+    idx[tmin > 10.0] = -1
+    msd = {k: v.detach().to(device) for k, v in ms.items()}
+    try:
+        assert _lib.lib().pslam_set_option(7, walk) == 0
+        pipe = RenderPipeline(R, device, n_max=n_max)
+        pipe.bind(rays_o.to(device), rays_d.to(device), msd, dec, voxel_size=s.voxel_size, step_size=0.1 * s.voxel_size, truncation=0.1,
+                  max_distance=10.0, seed=1, forward_only=True)
+        pipe.sample()
+        inter, hits = pipe.intersections()
+    finally:
+        _lib.lib().pslam_set_option(7, 0)
+    got, width = inter["intersected_voxel_idx"][0].cpu(), inter["intersected_voxel_idx"].shape[-1]
+    assert width == int(idx.ne(-1).sum(-1).max())
+    assert torch.equal(got, idx[:, :width])
+    valid = got.ne(-1)
+    assert torch.equal(inter["min_depth"][0].cpu()[valid], tmin[:, :width][valid])
+    assert torch.equal(inter["max_depth"][0].cpu()[valid], tmax[:, :width][valid])
+
+
 def test_large_ray_batch_properties(device):
     """configs[4] (ray-batch sweep): 2^17 rays in one launch on the configs[1] scene, checked through properties that do
     not need the oracle at that size: a ray's hit list does not depend on the batch it is in (bit-exact against a
