@@ -13,9 +13,9 @@ run() {
   tail -2 gpurun_out/${tag}_n${N}_last.err | grep -i -E "error|Traceback" 
 }
 run
-run --nccl
+[ -z "$SKIP_NCCL" ] && run --nccl
 run --workload scannet_large --width 256 --steps 10
-[ $N -lt 8 ] && run --workload scannet_large --width 256 --steps 10 --nccl
+[ $N -lt 8 ] && [ -z "$SKIP_NCCL" ] && run --workload scannet_large --width 256 --steps 10 --nccl
 shift 2
 for r in "$@"; do run --rays $r --steps 5; done
 run --rays 5120 --strong
