@@ -298,7 +298,8 @@ typedef struct {
     const float *emb;                      /* [E,16] voxel_vertex_emb */
     pslam_decoder_t dec;
     float *dec_ws;                         /* [pslam_decoder_ws_count(dec.width)] repacked weights */
-    void *wgrad_ws;                        /* pslam_wgrad_ws_bytes(sample_cap) bytes, or NULL (then SIMT wgrad) */
+    void *wgrad_ws;                        /* pslam_wgrad_ws_bytes_w(sample_cap, dec.width) bytes (wgrad operands, ReLU masks, feature rows),
+                                              or NULL: the fp32 SIMT build then serves any call that needs a backward */
     int64_t wgrad_ws_bytes;
     const float *noise;                    /* [>=R_h, noise_stride] uniform(0.001,0.999) or NULL */
     int noise_stride;
