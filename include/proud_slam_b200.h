@@ -388,9 +388,20 @@ int pslam_sample_pixels(int n, long long hw, unsigned long long seed, const unsi
                         pslam_stream_t stream);
 int pslam_track_assemble(int n, const float *pose6, const long long *idx, const float *rays_d_cam, const float *rgb_all,
                          const float *depth_all, float *rays_o, float *rays_d, float *rgb, float *depth, pslam_stream_t stream);
+/* pslam_sample_pixels + pslam_track_assemble in one launch (a captured tracking iteration): idx [n] receives the selection. */
+int pslam_track_sample_assemble(int n, long long hw, unsigned long long seed, const unsigned long long *seed_dev, const float *pose6,
+                                const float *rays_d_cam, const float *rgb_all, const float *depth_all, long long *idx, float *rays_o,
+                                float *rays_d, float *rgb, float *depth, pslam_stream_t stream);
 int pslam_track_pose_step(int n, float *pose6, const long long *idx, const float *rays_d_cam, const float *g_rays_o,
                           const float *g_rays_d, float *exp_avg, float *exp_avg_sq, float *step, double step_value, double lr,
                           double beta1, double beta2, double eps, float *grad_out, pslam_stream_t stream);
+/* The same step as the last kernel of a CAPTURED tracking iteration (device-side Adam count only), which also does the
+ * iteration's bookkeeping: hit_mask[i] = hit_count[i] > 0 (track_frame's third return value, render_helpers.py:741; both or
+ * neither) and *iter_counter += 1 (the device-side addend of the next iteration's pixel selection / sampling-noise seeds). */
+int pslam_track_pose_step_iter(int n, float *pose6, const long long *idx, const float *rays_d_cam, const float *g_rays_o,
+                               const float *g_rays_d, float *exp_avg, float *exp_avg_sq, float *step, double lr, double beta1,
+                               double beta2, double eps, unsigned long long *iter_counter, const int *hit_count,
+                               unsigned char *hit_mask, pslam_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * Optimizer step of the mapping loop (src/mapping.py:81-82: torch.optim.Adam over the embedding table and over the decoder,

@@ -81,7 +81,9 @@ _PROTOTYPES = {
     "pslam_debug_umma_gemm_bf": (C.c_int, [_P, _P, _P, _I, _I, _I, _S]),
     "pslam_sample_pixels": (C.c_int, [_I, C.c_longlong, C.c_uint64, _P, _P, _S]),
     "pslam_track_assemble": (C.c_int, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _S]),
+    "pslam_track_sample_assemble": (C.c_int, [_I, C.c_longlong, C.c_uint64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _S]),
     "pslam_track_pose_step": (C.c_int, [_I, _P, _P, _P, _P, _P, _P, _P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _P, _S]),
+    "pslam_track_pose_step_iter": (C.c_int, [_I, _P, _P, _P, _P, _P, _P, _P, _P, C.c_double, C.c_double, C.c_double, C.c_double, _P, _P, _P, _S]),
     "pslam_adam_step": (C.c_int, [_P, _I, C.c_double, C.c_double, C.c_double, C.c_double, _I, _S]),
     "pslam_debug_bf_trace": (C.c_int, [_P]),
     "pslam_debug_pp_trace": (C.c_int, [_P]),

@@ -79,9 +79,17 @@ __global__ void __launch_bounds__(256) k_track_pose_step(int n, float *__restric
                                                          const float *__restrict__ dirs, const float *__restrict__ g_o,
                                                          const float *__restrict__ g_d, float *__restrict__ exp_avg,
                                                          float *__restrict__ exp_avg_sq, float *__restrict__ step, float lr, float beta1,
-                                                         float beta2, float omb1, float omb2, float eps, float step_value, float *__restrict__ grad_out)
+                                                         float beta2, float omb1, float omb2, float eps, float step_value, float *__restrict__ grad_out,
+                                                         unsigned long long *__restrict__ iter_counter, const int *__restrict__ hit_count,
+                                                         unsigned char *__restrict__ hit_mask)
 {
     pdl_enter();
+    // end-of-iteration bookkeeping of a captured tracking iteration (instead of three torch launches): which rays hit the map
+    // (track_frame's third return value, render_helpers.py:741) and the device-side iteration count the next iteration's pixel
+    // selection and sampling noise are seeded with
+    if (hit_mask && hit_count)
+        for (int i = threadIdx.x; i < n; i += 256) hit_mask[i] = hit_count[i] > 0 ? 1 : 0;
+    if (iter_counter && threadIdx.x == 255) *iter_counter += 1ull;
     __shared__ float s_part[8][12];
     float acc[12];
 #pragma unroll
@@ -162,12 +170,10 @@ __device__ __forceinline__ uint32_t feistel_round(uint32_t x, uint32_t k)
     x ^= x >> 13;
     return x;
 }
-__global__ void k_sample_pixels(int n, long long hw, unsigned long long seed, const unsigned long long *__restrict__ seed_dev,
-                                long long *__restrict__ idx)
+// element i of a keyed permutation of [0, hw): a 4-round Feistel network over the smallest even bit width that covers hw, cycle-
+// walked back into range; (seed, seed_dev) pick the permutation
+__device__ __forceinline__ long long permuted_pixel(int i, long long hw, unsigned long long seed, const unsigned long long *__restrict__ seed_dev)
 {
-    pdl_enter();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
     unsigned long long key = seed + (seed_dev ? *seed_dev : 0ull);
     key ^= key >> 30; key *= 0xBF58476D1CE4E5B9ull;
     key ^= key >> 27; key *= 0x94D049BB133111EBull;
@@ -186,7 +192,40 @@ __global__ void k_sample_pixels(int n, long long hw, unsigned long long seed, co
         }
         x = ((unsigned long long)L << hb) | Rr;
     } while ((long long)x >= hw);
-    idx[i] = (long long)x;
+    return (long long)x;
+}
+
+__global__ void k_sample_pixels(int n, long long hw, unsigned long long seed, const unsigned long long *__restrict__ seed_dev,
+                                long long *__restrict__ idx)
+{
+    pdl_enter();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    idx[i] = permuted_pixel(i, hw, seed, seed_dev);
+}
+
+// pixel selection + ray assembly of a tracking iteration in one launch (k_sample_pixels + k_track_assemble)
+__global__ void k_track_sample_assemble(int n, long long hw, unsigned long long seed, const unsigned long long *__restrict__ seed_dev,
+                                        const float *__restrict__ pose, const float *__restrict__ dirs, const float *__restrict__ rgb_all,
+                                        const float *__restrict__ depth_all, long long *__restrict__ idx, float *__restrict__ rays_o,
+                                        float *__restrict__ rays_d, float *__restrict__ rgb, float *__restrict__ depth)
+{
+    pdl_enter();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long s = permuted_pixel(i, hw, seed, seed_dev);
+    idx[i] = s;
+    const float w[3] = {pose[3], pose[4], pose[5]};
+    float R[9];
+    rotation(w, R);
+    const float d0 = __ldg(dirs + s * 3), d1 = __ldg(dirs + s * 3 + 1), d2 = __ldg(dirs + s * 3 + 2);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        rays_d[i * 3 + a] = R[a * 3] * d0 + R[a * 3 + 1] * d1 + R[a * 3 + 2] * d2;
+        rays_o[i * 3 + a] = pose[a];
+    }
+    if (rgb) { rgb[i * 3] = __ldg(rgb_all + s * 3); rgb[i * 3 + 1] = __ldg(rgb_all + s * 3 + 1); rgb[i * 3 + 2] = __ldg(rgb_all + s * 3 + 2); }
+    if (depth) depth[i] = __ldg(depth_all + s);
 }
 
 }  // namespace pslam
@@ -213,6 +252,19 @@ extern "C" int pslam_track_assemble(int n, const float *pose6, const long long *
     return 0;
 }
 
+extern "C" int pslam_track_sample_assemble(int n, long long hw, unsigned long long seed, const unsigned long long *seed_dev, const float *pose6,
+                                           const float *rays_d_cam, const float *rgb_all, const float *depth_all, long long *idx, float *rays_o,
+                                           float *rays_d, float *rgb, float *depth, pslam_stream_t stream)
+{
+    PSLAM_CHECK_ARG(n > 0 && hw > 0 && pose6 && idx && rays_d_cam && rays_o && rays_d, PSLAM_E_ARG, "track_sample_assemble: bad argument");
+    PSLAM_CHECK_ARG((long long)n <= hw, PSLAM_E_RANGE, "track_sample_assemble: cannot draw %d distinct pixels out of %lld", n, hw);
+    PSLAM_CHECK_ARG((rgb == nullptr || rgb_all) && (depth == nullptr || depth_all), PSLAM_E_ARG, "track_sample_assemble: targets without their source");
+    launch_chain(k_track_sample_assemble, dim3(ceil_div(n, 128)), dim3(128), 0, (cudaStream_t)stream, n, hw, seed, seed_dev, pose6, rays_d_cam, rgb_all, depth_all,
+                 idx, rays_o, rays_d, rgb, depth);
+    PSLAM_CHECK_LAUNCH("track_sample_assemble");
+    return 0;
+}
+
 extern "C" int pslam_track_pose_step(int n, float *pose6, const long long *idx, const float *rays_d_cam, const float *g_rays_o,
                                      const float *g_rays_d, float *exp_avg, float *exp_avg_sq, float *step, double step_value, double lr,
                                      double beta1, double beta2, double eps, float *grad_out, pslam_stream_t stream)
@@ -220,7 +272,22 @@ extern "C" int pslam_track_pose_step(int n, float *pose6, const long long *idx, 
     PSLAM_CHECK_ARG(n > 0 && pose6 && idx && rays_d_cam && g_rays_o && g_rays_d && exp_avg && exp_avg_sq && (step || step_value >= 1.0),
                     PSLAM_E_ARG, "track_pose_step: bad argument");
     launch_chain(k_track_pose_step, dim3(1), dim3(256), 0, (cudaStream_t)stream, n, pose6, idx, rays_d_cam, g_rays_o, g_rays_d, exp_avg, exp_avg_sq, step, (float)lr,
-                                                           (float)beta1, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps, (float)step_value, grad_out);
+                                                           (float)beta1, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps, (float)step_value, grad_out,
+                                                           (unsigned long long *)nullptr, (const int *)nullptr, (unsigned char *)nullptr);
     PSLAM_CHECK_LAUNCH("track_pose_step");
+    return 0;
+}
+
+extern "C" int pslam_track_pose_step_iter(int n, float *pose6, const long long *idx, const float *rays_d_cam, const float *g_rays_o,
+                                          const float *g_rays_d, float *exp_avg, float *exp_avg_sq, float *step, double lr, double beta1,
+                                          double beta2, double eps, unsigned long long *iter_counter, const int *hit_count,
+                                          unsigned char *hit_mask, pslam_stream_t stream)
+{
+    PSLAM_CHECK_ARG(n > 0 && pose6 && idx && rays_d_cam && g_rays_o && g_rays_d && exp_avg && exp_avg_sq && step, PSLAM_E_ARG,
+                    "track_pose_step_iter: bad argument");
+    PSLAM_CHECK_ARG((hit_mask == nullptr) == (hit_count == nullptr), PSLAM_E_ARG, "track_pose_step_iter: hit_mask and hit_count go together");
+    launch_chain(k_track_pose_step, dim3(1), dim3(256), 0, (cudaStream_t)stream, n, pose6, idx, rays_d_cam, g_rays_o, g_rays_d, exp_avg, exp_avg_sq, step, (float)lr,
+                 (float)beta1, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps, 0.0f, (float *)nullptr, iter_counter, hit_count, hit_mask);
+    PSLAM_CHECK_LAUNCH("track_pose_step_iter");
     return 0;
 }

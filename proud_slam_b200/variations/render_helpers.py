@@ -659,14 +659,12 @@ class GraphTracker:
     def _iteration_fused(self):
         from .. import _lib
         lib, d = _lib.lib(), self.device
-        self.counter.add_(1)
         idx = self.idx          # distinct pixels, uniform, like the frame's own sample_rays (no replacement)
-        _lib.check(lib.pslam_sample_pixels(self.N, self.HW, self.base_seed ^ 0x5851F42D4C957F2D, _lib.ptr(self.counter), _lib.ptr(idx),
-                                           _lib.stream_ptr(d)), "pslam_sample_pixels")
         pose = self.pose.data
-        _lib.check(lib.pslam_track_assemble(self.N, _lib.ptr(pose), _lib.ptr(idx), _lib.ptr(self.rays_d_all), _lib.ptr(self.rgb_all),
-                                            _lib.ptr(self.depth_all), _lib.ptr(self.rays_o), _lib.ptr(self.rays_d), _lib.ptr(self.rgb),
-                                            _lib.ptr(self.depth), _lib.stream_ptr(d)), "pslam_track_assemble")
+        _lib.check(lib.pslam_track_sample_assemble(self.N, self.HW, self.base_seed ^ 0x5851F42D4C957F2D, _lib.ptr(self.counter), _lib.ptr(pose),
+                                                   _lib.ptr(self.rays_d_all), _lib.ptr(self.rgb_all), _lib.ptr(self.depth_all), _lib.ptr(idx),
+                                                   _lib.ptr(self.rays_o), _lib.ptr(self.rays_d), _lib.ptr(self.rgb), _lib.ptr(self.depth),
+                                                   _lib.stream_ptr(d)), "pslam_track_sample_assemble")
         pipe = self.it.pipe
         pipe.bind(self.rays_o, self.rays_d, self.ms, self.dec, voxel_size=self.cfg["voxel_size"], step_size=self.cfg["step_size"],
                   truncation=self.crit["truncation"], max_distance=self.cfg["max_distance"], max_depth=self.crit["max_depth"],
@@ -675,11 +673,13 @@ class GraphTracker:
         pipe.step()
         g = self.optim.param_groups[0]
         st = self.optim.state[pose]
-        _lib.check(lib.pslam_track_pose_step(self.N, _lib.ptr(pose), _lib.ptr(idx), _lib.ptr(self.rays_d_all), _lib.ptr(pipe.g_rays_o),
-                                             _lib.ptr(pipe.g_rays_d), _lib.ptr(st["exp_avg"]), _lib.ptr(st["exp_avg_sq"]),
-                                             _lib.ptr(st["step"]), 0.0, float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]),
-                                             float(g["eps"]), None, _lib.stream_ptr(d)), "pslam_track_pose_step")
-        self.hit_mask.copy_(pipe.hit_count[: self.N] > 0)
+        # the pose step is the iteration's last kernel: it also writes the hit mask and advances the iteration counter that seeds
+        # the next iteration's pixel selection and sampling noise (three torch launches per iteration otherwise)
+        _lib.check(lib.pslam_track_pose_step_iter(self.N, _lib.ptr(pose), _lib.ptr(idx), _lib.ptr(self.rays_d_all), _lib.ptr(pipe.g_rays_o),
+                                                  _lib.ptr(pipe.g_rays_d), _lib.ptr(st["exp_avg"]), _lib.ptr(st["exp_avg_sq"]),
+                                                  _lib.ptr(st["step"]), float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]),
+                                                  float(g["eps"]), _lib.ptr(self.counter), _lib.ptr(pipe.hit_count), _lib.ptr(self.hit_mask),
+                                                  _lib.stream_ptr(d)), "pslam_track_pose_step_iter")
 
     def _iteration(self):
         if self.fused_pose:
