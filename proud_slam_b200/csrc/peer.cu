@@ -19,12 +19,11 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "peer.cuh"
-#include <stdlib.h>
 
 namespace pslam {
 
 __global__ void __launch_bounds__(kArThreads)
-k_peer_allreduce(pslam_peer_t peer, int *__restrict__ fail_flag, int skip)
+k_peer_allreduce(pslam_peer_t peer, int *__restrict__ fail_flag)
 {
     pdl_enter();
     __shared__ unsigned long long s_epoch;
@@ -35,7 +34,7 @@ k_peer_allreduce(pslam_peer_t peer, int *__restrict__ fail_flag, int skip)
     __syncthreads();
     const unsigned long long e = s_epoch;
     // ---- entry barrier: every rank's kernel has started, i.e. its buffer is final (stream order on that rank) ----
-    if (tid < world && !(skip & 1)) {
+    if (tid < world) {
         st_release_sys(&static_cast<PeerSync *>(peer.sync[tid])->ar_flag[0][b][rank], e);
         if (!spin_until(&mine->ar_flag[0][b][tid], e)) s_fail = 1;
     }
@@ -43,7 +42,7 @@ k_peer_allreduce(pslam_peer_t peer, int *__restrict__ fail_flag, int skip)
     // ---- slice `rank` of the world's buffers: sum in rank order, store to everybody ----
     const int64_t n4 = peer.flat_count / 4;
     const int64_t lo = n4 * rank / world, hi = n4 * (rank + 1) / world;
-    if (!s_fail && !(skip & 2)) {
+    if (!s_fail) {
         // every load of an element is in flight before the first is used: a remote load is a ~2 us NVLink round trip, and the
         // launch gives a thread one or two elements, so the slice costs about one round trip
         const int64_t stride = (int64_t)gridDim.x * kArThreads;
@@ -64,9 +63,8 @@ k_peer_allreduce(pslam_peer_t peer, int *__restrict__ fail_flag, int skip)
     // ---- exit barrier: everybody's slice has landed in this rank's buffer ----
     // (no block-wide fence: the barrier orders the block's stores before the flag thread, whose st.release.sys is cumulative;
     //  512 threads x membar.sys was measured at 6.6 us of a 28 us kernel)
-    if (skip & 8) __threadfence_system();
     __syncthreads();
-    if (tid < world && !(skip & 4)) {
+    if (tid < world) {
         st_release_sys(&static_cast<PeerSync *>(peer.sync[tid])->ar_flag[1][b][rank], e);
         if (!spin_until(&mine->ar_flag[1][b][tid], e)) s_fail = 1;
     }
@@ -212,9 +210,7 @@ int launch_peer_allreduce(const pslam_peer_t *peer, int *fail_flag, cudaStream_t
     int blocks = (int)ceil_div64(slice4, kArThreads);
     blocks = blocks < 8 ? 8 : (blocks > kArMaxBlocks ? kArMaxBlocks : blocks);
     if (blocks > num_sms()) blocks = num_sms();      // every block spins on its peers: all of them must be resident
-    static int skip = -1;                            // PSLAM_AR_SKIP (measurement only): 1 no entry barrier, 2 no data, 4 no exit barrier, 8 no fence
-    if (skip < 0) { const char *e = getenv("PSLAM_AR_SKIP"); skip = e ? atoi(e) : 0; }
-    launch_chain(k_peer_allreduce, dim3(blocks), dim3(kArThreads), 0, st, *peer, fail_flag, skip);
+    launch_chain(k_peer_allreduce, dim3(blocks), dim3(kArThreads), 0, st, *peer, fail_flag);
     PSLAM_CHECK_LAUNCH("peer_allreduce");
     return 0;
 }

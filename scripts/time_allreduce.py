@@ -29,5 +29,5 @@ b.record(); torch.cuda.synchronize()
 t2 = torch.tensor([a.elapsed_time(b) / 200 * 1e3], device=dev)
 dist.all_reduce(t2, op=dist.ReduceOp.MAX)
 if rank == 0:
-    print(f"skip={os.environ.get('PSLAM_AR_SKIP', '0')} n={n} floats ({n * 4 / 1e6:.2f} MB) world={world}: peer all-reduce {t.item():.1f} us, NCCL all_reduce {t2.item():.1f} us, fail={int(px.fail.item())}")
+    print(f"n={n} floats ({n * 4 / 1e6:.2f} MB) world={world}: peer all-reduce {t.item():.1f} us, NCCL all_reduce {t2.item():.1f} us, fail={int(px.fail.item())}")
 dist.barrier(); dist.destroy_process_group()
