@@ -47,7 +47,7 @@ constexpr int oG5s = oFs + 2 * 4096;                           // G5 of the tile
 constexpr int oOnes = oG5s + 2 * 4096;                         // 16 samples x 16 features of f16 1.0
 constexpr int oBars = oOnes + 512;                             // full[4] empty[4] a_ready mma_done h_full[2] h_free[2] all_done
 constexpr int oTmemPtr = oBars + 8 * (2 * kBWStages + 7);
-constexpr int oW5 = oTmemPtr + 16;                             // W5 [3][128] fp32
+constexpr int oW5 = (oTmemPtr + 16 + 15) & ~15;                           // W5 [3][128] fp32
 constexpr int oW30 = oW5 + 4 * 3 * 128;                        // W3 row 0 [128] fp32
 constexpr int oScat = (oW30 + 4 * 128 + 15) & ~15;                        // two warps x (weights [32][9] + gradient rows [32][16] + corner ids [32][8]) of the fused scatter
 constexpr int oScatDone = oScat + 2 * 4 * kScatWarpFloats;     // tiles whose feature-gradient rows are complete (x 128 lead threads)
@@ -476,7 +476,53 @@ k_field_bw(FieldParams p, const unsigned char *__restrict__ wstream, float *__re
             po = in ? __ldg(reinterpret_cast<const float4 *>(p.out + (size_t)sn * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
             pgo = in ? __ldg(reinterpret_cast<const float4 *>(p.g_out + (size_t)sn * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
+        // The first epilogue of a tile (g_hc = mask_hc . (W5^T g5), on the CUDA cores: ~3.6k clocks of issue for the eight worker
+        // warps) is computed one tile AHEAD, while the workers would otherwise wait ~3k clocks for the small products of
+        // phase 4: the packed operand words wait in registers until the tile's last MMAs have completed, then only the stores
+        // remain at the top of the next tile.
+        uint32_t nhi[4][8], nlo[4][8];                    // next tile: g_hc, f16 hi / lo words of this thread's 64 columns
+        float ng5[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t nm1[2] = {0u, 0u}, nm2[2] = {0u, 0u};
+        auto compute_next = [&](int tn) {
+            const bool real_n = tn < ntiles;
+            nm1[0] = pm[0]; nm1[1] = pm[1]; nm2[0] = pm[2]; nm2[1] = pm[3];
+            const uint32_t mc[2] = {pm[4], pm[5]};
+            const float r = po.x, gg = po.y, b = po.z;    // (zeros outside the batch: prefetch_tile)
+            const float gx = pgo.x * Sg, gy = pgo.y * Sg, gz = pgo.z * Sg;
+            ng5[0] = gx * (1.0f - r) * r; ng5[1] = gy * (1.0f - gg) * gg; ng5[2] = gz * (1.0f - b) * b; ng5[3] = pgo.w * Sg;
+            if (lead) {
+                // bias gradients of the two heads: column sums of G5
+                const float s0 = warp_sum(ng5[0]), s1 = warp_sum(ng5[1]), s2 = warp_sum(ng5[2]), s3 = warp_sum(ng5[3]);
+                if (lane == 0 && real_n) {
+                    atomicAdd(p.g_dec.b5 + 0, s0 * invSg); atomicAdd(p.g_dec.b5 + 1, s1 * invSg); atomicAdd(p.g_dec.b5 + 2, s2 * invSg);
+                    atomicAdd(p.g_dec.b3, s3 * invSg);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c0 = col0 + 16 * j;
+                const uint32_t bits = mc[j >> 1] >> ((j & 1) * 16);
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {          // (128-bit broadcast loads: the tensor core's operand reads want the shared-memory cycles)
+                    const float4 w0 = *reinterpret_cast<const float4 *>(sW5 + c0 + 4 * qd);
+                    const float4 w1 = *reinterpret_cast<const float4 *>(sW5 + 128 + c0 + 4 * qd);
+                    const float4 w2 = *reinterpret_cast<const float4 *>(sW5 + 256 + c0 + 4 * qd);
+                    float y0 = fmaf(ng5[2], w2.x, fmaf(ng5[1], w1.x, ng5[0] * w0.x));
+                    float y1 = fmaf(ng5[2], w2.y, fmaf(ng5[1], w1.y, ng5[0] * w0.y));
+                    float y2 = fmaf(ng5[2], w2.z, fmaf(ng5[1], w1.z, ng5[0] * w0.z));
+                    float y3 = fmaf(ng5[2], w2.w, fmaf(ng5[1], w1.w, ng5[0] * w0.w));
+                    y0 = ((bits >> (4 * qd)) & 1u) ? y0 : 0.0f;
+                    y1 = ((bits >> (4 * qd + 1)) & 1u) ? y1 : 0.0f;
+                    y2 = ((bits >> (4 * qd + 2)) & 1u) ? y2 : 0.0f;
+                    y3 = ((bits >> (4 * qd + 3)) & 1u) ? y3 : 0.0f;
+                    ymax = fmaxf(ymax, fmaxf(fmaxf(fabsf(y0), fabsf(y1)), fmaxf(fabsf(y2), fabsf(y3))));
+                    h16_split2(y0, y1, nhi[j][2 * qd], nlo[j][2 * qd]);
+                    h16_split2(y2, y3, nhi[j][2 * qd + 1], nlo[j][2 * qd + 1]);
+                }
+            }
+        };
         prefetch_tile((int)blockIdx.x);
+        compute_next((int)blockIdx.x);
         for (int it = 0; it < iters; ++it) {
             const int tile = it * G + (int)blockIdx.x;
             const bool real = tile < ntiles;
@@ -484,54 +530,32 @@ k_field_bw(FieldParams p, const unsigned char *__restrict__ wstream, float *__re
             if (threadIdx.x == 128) BW_TRACE(tr_it, 0, tr_slot++);
             const int s = real ? tile * 128 + m : nsamp;
             const bool valid = s < nsamp;
-            const uint32_t m1[2] = {pm[0], pm[1]}, m2[2] = {pm[2], pm[3]}, mc[2] = {pm[4], pm[5]};
-            float4 go = valid ? pgo : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float r = valid ? po.x : 0.f, gg = valid ? po.y : 0.f, b = valid ? po.z : 0.f;
-            go.x *= Sg; go.y *= Sg; go.z *= Sg; go.w *= Sg;
-            const float g5[4] = {go.x * (1.0f - r) * r, go.y * (1.0f - gg) * gg, go.z * (1.0f - b) * b, go.w};
+            const uint32_t m1[2] = {nm1[0], nm1[1]}, m2[2] = {nm2[0], nm2[1]};
+            const float gow = ng5[3];
             if (lead) {
                 // G5 = (g5 r, g, b, g_sdf, 0 ...) as a 16-feature operand (second feature block zero: written once below)
                 uint32_t h0, l0, h1w, l1w;
-                h16_split2(g5[0], g5[1], h0, l0);
-                h16_split2(g5[2], g5[3], h1w, l1w);
+                h16_split2(ng5[0], ng5[1], h0, l0);
+                h16_split2(ng5[2], ng5[3], h1w, l1w);
                 *reinterpret_cast<uint4 *>(sG5row) = make_uint4(h0, h1w, 0u, 0u);
                 *reinterpret_cast<uint4 *>(sG5row + 4096) = make_uint4(l0, l1w, 0u, 0u);
                 if (it == 0) {
                     *reinterpret_cast<uint4 *>(sG5row + 128) = make_uint4(0u, 0u, 0u, 0u);
                     *reinterpret_cast<uint4 *>(sG5row + 4096 + 128) = make_uint4(0u, 0u, 0u, 0u);
                 }
-                // bias gradients of the two heads: column sums of G5
-                const float s0 = warp_sum(g5[0]), s1 = warp_sum(g5[1]), s2 = warp_sum(g5[2]), s3 = warp_sum(g5[3]);
-                if (lane == 0 && real) {
-                    atomicAdd(p.g_dec.b5 + 0, s0 * invSg); atomicAdd(p.g_dec.b5 + 1, s1 * invSg); atomicAdd(p.g_dec.b5 + 2, s2 * invSg);
-                    atomicAdd(p.g_dec.b3, s3 * invSg);
-                }
             }
-            {
-                // g_hc = mask_hc . (W5^T g5) on the CUDA cores -> A and the G buffer
+            // g_hc (computed during the previous tile) -> A and the G buffer
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int c0 = col0 + 16 * j;
-                    const uint32_t bits = mc[j >> 1] >> ((j & 1) * 16);
-                    uint32_t hi[8], lo[8];
+            for (int j = 0; j < 4; ++j) {
+                const int c0 = col0 + 16 * j;
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        float y0 = fmaf(g5[2], sW5[256 + c0 + 2 * e], fmaf(g5[1], sW5[128 + c0 + 2 * e], g5[0] * sW5[c0 + 2 * e]));
-                        float y1 = fmaf(g5[2], sW5[256 + c0 + 2 * e + 1], fmaf(g5[1], sW5[128 + c0 + 2 * e + 1], g5[0] * sW5[c0 + 2 * e + 1]));
-                        y0 = ((bits >> (2 * e)) & 1u) ? y0 : 0.0f;
-                        y1 = ((bits >> (2 * e + 1)) & 1u) ? y1 : 0.0f;
-                        ymax = fmaxf(ymax, fmaxf(fabsf(y0), fabsf(y1)));
-                        h16_split2(y0, y1, hi[e], lo[e]);
-                    }
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        unsigned char *dst = sGrow + (c0 / 8 + k) * 128;
-                        *reinterpret_cast<uint4 *>(dst) = make_uint4(hi[4 * k], hi[4 * k + 1], hi[4 * k + 2], hi[4 * k + 3]);
-                        *reinterpret_cast<uint4 *>(dst + kPlane) = make_uint4(lo[4 * k], lo[4 * k + 1], lo[4 * k + 2], lo[4 * k + 3]);
-                    }
-                    tmem_st8(trow + cHi + c0 / 2, hi);
-                    tmem_st8(trow + cLo + c0 / 2, lo);
+                for (int k = 0; k < 2; ++k) {
+                    unsigned char *dst = sGrow + (c0 / 8 + k) * 128;
+                    *reinterpret_cast<uint4 *>(dst) = make_uint4(nhi[j][4 * k], nhi[j][4 * k + 1], nhi[j][4 * k + 2], nhi[j][4 * k + 3]);
+                    *reinterpret_cast<uint4 *>(dst + kPlane) = make_uint4(nlo[j][4 * k], nlo[j][4 * k + 1], nlo[j][4 * k + 2], nlo[j][4 * k + 3]);
                 }
+                tmem_st8(trow + cHi + c0 / 2, nhi[j]);
+                tmem_st8(trow + cLo + c0 / 2, nlo[j]);
             }
             a_is_ready();
             // ---- phase 0 results: g_f part (lead) and the small products of G4 (second column half) ----
@@ -556,6 +580,7 @@ k_field_bw(FieldParams p, const unsigned char *__restrict__ wstream, float *__re
             fence_before_sync();
             mbar_arrive(a_ready);
             if (threadIdx.x == 128) BW_TRACE(tr_it, 0, tr_slot++);
+            prefetch_tile(tile + G);                      // per-row inputs of the next tile: in flight during phases 1-3
             // ---- phase 1: g_t -> A (not needed by the weight gradients: the G buffer keeps G4 for M += G4^T H2) ----
             layer_done();
             float nocs = 0.f;
@@ -566,14 +591,14 @@ k_field_bw(FieldParams p, const unsigned char *__restrict__ wstream, float *__re
             layer_done();
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                bw_epi16<2, true, true>(trow, col0 + 16 * j, m2[j >> 1], (j & 1) * 16, sGrow, ymax, sW30, go.w, db2[j], lane);
+                bw_epi16<2, true, true>(trow, col0 + 16 * j, m2[j >> 1], (j & 1) * 16, sGrow, ymax, sW30, gow, db2[j], lane);
             a_is_ready();
             // ---- phase 3: g_h1 -> A and the G buffer ----
             layer_done();
 #pragma unroll
             for (int j = 0; j < 4; ++j) bw_epi16<2, false, false>(trow, col0 + 16 * j, m1[j >> 1], (j & 1) * 16, sGrow, ymax, nullptr, 0.f, nocs, lane);
             a_is_ready();
-            prefetch_tile(tile + G);
+            compute_next(tile + G);                       // (under the MMAs of phase 4; its inputs were requested after phase 0)
             // ---- phase 4 results: g_f (lead) and the small products of G1 ----
             layer_done();
             if (lead) {
