@@ -319,11 +319,24 @@ def run_gpu(args):
         dev_in.append(dev_block[off:off + n].view_as(t))
         off += n
     dev_block.copy_(host_block)
-    spr = 64 if SCENE != "scannet_large" else 128
-    pipe = RenderPipeline(R, device, samples_per_ray=spr)
-    pipe.bind(dev_in[0], dev_in[1], ms, dec, voxel_size=s.voxel_size, step_size=0.1 * s.voxel_size, truncation=0.1,
-              max_distance=10.0, max_depth=10.0, target_rgb=dev_in[2], target_depth=dev_in[3], noise=None, seed=1,
-              weights=CRIT_W, g_emb=g_emb, g_dec=g_dec, grad_rays=True, defer_loss=(world > 1 and peer is None))
+    spr = args.samples_per_ray or (64 if SCENE != "scannet_large" else 128)
+    chunks = max(args.chunks, 1)
+    if chunks > 1 and (world > 1 or R % chunks):
+        raise SystemExit("--chunks needs one GPU and a ray count it divides")
+    Rc = R // chunks                                                  # rays per launch
+    pipe = RenderPipeline(Rc, device, samples_per_ray=spr)
+
+    def bind_chunk(k, seed=1, defer=(world > 1 and peer is None)):
+        lo, hi = k * Rc, (k + 1) * Rc
+        pipe.bind(dev_in[0][lo:hi], dev_in[1][lo:hi], ms, dec, voxel_size=s.voxel_size, step_size=0.1 * s.voxel_size, truncation=0.1,
+                  max_distance=10.0, max_depth=10.0, target_rgb=dev_in[2][lo:hi], target_depth=dev_in[3][lo:hi], noise=None,
+                  seed=seed, weights=CRIT_W, g_emb=g_emb, g_dec=g_dec, grad_rays=True, defer_loss=defer)
+
+    bind_chunk(0)
+    chunked, chunk_seed = None, [1]
+    if chunks > 1:
+        from proud_slam_b200.parallel import ChunkedStep
+        chunked = ChunkedStep(pipe, fg, chunks, lambda k: bind_chunk(k, seed=chunk_seed[0] * 64 + k, defer=True))
     if peer is not None:
         peer.bind(pipe, allreduce=not args.no_allreduce)
     rows = torch.zeros(world, 16, dtype=torch.float64, device=device)
@@ -331,6 +344,10 @@ def run_gpu(args):
     flush = torch.empty(192 * 1024 * 1024 // 4, device=device)       # 192 MiB > 126 MB L2
 
     def step(seed):
+        if chunked is not None:
+            chunk_seed[0] = seed
+            chunked()                                                 # (clears the gradients itself)
+            return
         pipe.args.seed = seed
         flat.zero_()
         if world == 1 or peer is not None:
@@ -442,6 +459,20 @@ def run_gpu(args):
         pipe.step()
         torch.cuda.synchronize()
 
+    iter_counts = dict(counts)
+    if chunked is not None:
+        iter_counts = {"n_samples": 0, "R_h": 0}
+        for k in reversed(range(chunks)):                             # ends on chunk 0: the stage timings below are ONE chunk's launches
+            bind_chunk(k, seed=1, defer=False)
+            flat.zero_()
+            pipe.step()
+            c = pipe.counts()
+            pipe.check()
+            iter_counts["n_samples"] += c["n_samples"]
+            iter_counts["R_h"] += c["R_h"]
+            counts = c
+        torch.cuda.synchronize()
+
     # ---- every stage alone, events around it (pslam_render_stage): the dominant kernel and the HBM kernels of SURVEY 8(d)
     prof, extra = {}, {}
     build = int(os.environ.get("PSLAM_DECODER", "2"))   # include/proud_slam_b200.h: PSLAM_OPT_DECODER
@@ -508,7 +539,7 @@ def run_gpu(args):
         dist.all_reduce(ns)
         total_samples = int(ns.item())
     else:
-        total_samples = counts["n_samples"]
+        total_samples = iter_counts["n_samples"]
 
     if rank == 0:
         peaks = measured_peaks()
@@ -518,10 +549,11 @@ def run_gpu(args):
             0: ("tcgen05 3xTF32", "f32 (3xTF32 split, f32 accumulate)"),
             1: ("fp32 SIMT", "f32"),
             2: ("tcgen05 3xF16", "f16x3 (f16 hi/lo split with power-of-two scales, f32 accumulate)")}[build if (WIDTH == 128 or build == 2) else 1]
-        hits = int(pipe.hit_count[:R].sum().item())
+        hits = int(pipe.hit_count[:Rc].sum().item())
         vox = torch.unique(pipe.samp_vox[:P].long())
         E_t = int(torch.unique(ms["voxel_vertex_idx"][vox].long()).numel())
-        bytes_alg = algorithmic_bytes(R, Rh, P, hits, int(ms["voxel_center_xyz"].shape[0]), E_t)
+        bytes_alg = algorithmic_bytes(Rc, Rh, P, hits, int(ms["voxel_center_xyz"].shape[0]), E_t)      # per launch (= per chunk)
+        iter_scale = iter_counts["n_samples"] / max(P, 1)             # launches' worth of work per iteration (1 without --chunks)
         kernels = []
         if tc:
             # decoder kernels: algorithmic FLOPs (2 MACs forward, 4 MACs backward = dgrad + wgrad; the 3 split MMAs
@@ -549,7 +581,8 @@ def run_gpu(args):
             a = nbytes / (prof[key] * 1e-3) / 1e9
             kernels.append({"kernel": name, "bound": "hbm", "achieved": a, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": a / peaks["hbm_gbs"],
                             "kernel_ms": prof[key], "algorithmic_bytes_per_launch": nbytes, "traffic": None})
-        flops_iter = 6.0 * macs * P
+        flops_iter = 6.0 * macs * P * iter_scale
+        hbm_time *= iter_scale
         t_model = hbm_time + flops_iter / (peaks["bf16_tflops"] * 1e12)
         dom = kernels[0] if tc else None
         if dom is None:   # SIMT decoder (width 256 / PSLAM_DECODER=1): the backward stage is the dominant launch group
@@ -569,13 +602,19 @@ def run_gpu(args):
         per_step = (13 if world == 1 else (14 if peer is not None else 15)) if tc else 19
         if tc and WIDTH == 256:       # width 256: two pack kernels (SIMT + tcgen05 stream), chain backward + k_wgrad_w256 instead of the fused kernel + finish
             per_step += 1
+        if chunks > 1:                # per chunk: a forward-only pass (9 launches), then forward + loss coefficients + prologue + backward
+            per_step = chunks * (9 + per_step + 2)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": dtype,
             "data": "synthetic",
             "config": {"workload": workload_string(SCENE, KEYFRAMES, RAYS_PER_FRAME, R, n_oct, n_vox, s.voxel_size, E, WIDTH),
                        "decoder_build": ktext,
-                       "rays_per_gpu": R, "hit_rays": Rh, "samples_per_iter_per_gpu": P, "max_samples_per_ray": counts["S"],
+                       "rays_per_gpu": R, "hit_rays": iter_counts["R_h"], "samples_per_iter_per_gpu": iter_counts["n_samples"],
+                       "max_samples_per_ray": counts["S"], "workspace_samples_per_ray": spr,
+                       **({"chunks": chunks, "rays_per_launch": Rc, "chunking": "parallel.ChunkedStep: every chunk is rendered twice (loss "
+                           "closure over all chunks between the passes); hits / samples / roofline_kernels / stage_ms are ONE chunk's launches"}
+                          if chunks > 1 else {}),
                        "mean_hits_per_ray": hits / max(Rh, 1), "mean_samples_per_ray": P / max(Rh, 1), "touched_embedding_rows": E_t,
                        "total_samples_all_gpus": total_samples, "l2": "flushed (192 MiB write) between timed iterations",
                        "parallelism": (f"dp{world} (rays sharded by keyframe, map replicated, " + transport + ")") if world > 1 else "single GPU",
@@ -587,7 +626,7 @@ def run_gpu(args):
             "roofline": roofline,
             "roofline_kernels": kernels,
             "iteration_model": {"T_model_ms": t_model * 1e3, "T_measured_ms": ms_step, "ratio": t_model * 1e3 / ms_step,
-                                "algorithmic_flops": flops_iter, "algorithmic_hbm_bytes": sum(bytes_alg.values()),
+                                "algorithmic_flops": flops_iter, "algorithmic_hbm_bytes": sum(bytes_alg.values()) * iter_scale,
                                 "note": "SURVEY 8(d): sum over the HBM kernels of bytes/BW + 6 MACs x samples / tensor peak (kernels are dependent)"},
             "stage_ms": prof,
         }
@@ -706,6 +745,10 @@ def main():
     ap.add_argument("--nccl", action="store_true", help="N > 1: NCCL all_gather + all_reduce from the host instead of the in-kernel exchanges")
     ap.add_argument("--no-allreduce", action="store_true", help="N > 1 (measurement only): loss closure across ranks but no gradient all-reduce")
     ap.add_argument("--no-extras", action="store_true", help="skip the tracking and CPU-baseline legs (sweeps)")
+    ap.add_argument("--samples-per-ray", type=int, default=0, help="workspace samples per ray (default 64; scannet_large 128): the "
+                    "forward's saved operands are 1.6 kB per sample of capacity, 2^21 rays fit one 180 GB GPU at 32")
+    ap.add_argument("--chunks", type=int, default=1, help="1 GPU: render the batch in this many chunks through parallel.ChunkedStep "
+                    "(batches beyond one launch's workspace, e.g. 2^22 rays = 2 x 2^21); costs one extra forward per chunk")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -155,8 +155,9 @@ class DataParallelStep:
 
 
 class ChunkedStep:
-    """One mapping iteration over a ray batch larger than one launch's workspace (the wgrad scratch is 3.2 kB per
-    sample: about 2^19 rays per 180 GB GPU).  The batch is cut into chunks that go through the same two-exchange
+    """One mapping iteration over a ray batch larger than one launch's workspace (``pslam_wgrad_ws_bytes_w`` is 4.2 kB per
+    sample of capacity, sized for either decoder build: 2^20 rays at 32 samples of capacity per ray fill 132 GiB of a
+    180 GB GPU; ``bench.py --chunks`` measures 2^21 / 2^22 rays this way).  The batch is cut into chunks that go through the same two-exchange
     protocol as the ranks of ``DataParallelStep``, as *virtual ranks* of one device:
 
     pass 1  every chunk is rendered with the loss deferred and leaves its 16 raw sums;
