@@ -13,10 +13,12 @@
 //     H2, H1, HC (and F) of the tile arrive from the forward's scratch by bulk TMA, one 64-sample half at a time;
 //   * the big products are issued right behind the chain layer that consumes the same operand, i.e. they execute while
 //     the workers run that layer's epilogue -- the tensor pipe idled there before;
-//   * the seven small products (16 / 8 output columns: dW4[:,128:], dW1, dW5, dW3[0], db4, db1) go to spare accumulator
-//     columns next to the two N = 16 layers at the ends of the chain, fresh for every tile; 128 worker threads read them
-//     with the chain's own results and keep the running sums in registers; db2 is a butterfly column sum of the g_h2
-//     epilogue.
+//   * the small products (16 / 8 output columns: dW4[:,128:], dW1, dW5, dW3[0]) go to spare accumulator columns next to
+//     the two N = 16 layers at the ends of the chain, fresh for every tile; 128 worker threads read them with the
+//     chain's own results and keep the running sums in registers.  Every one of these N = 16 MMAs re-reads a 4 kB A
+//     operand from shared memory (~45 clocks whatever N is) and they sit on the critical path, so the bias gradients
+//     db4 / db2 / db1 are NOT ones-operand products but butterfly column sums of the epilogues that produce G4 / G2 / G1;
+//   * the tile's first epilogue (g_hc, CUDA cores only) is computed one tile ahead, while the workers wait for phase 4.
 // DRAM traffic of the decoder backward: the forward's 1.6 kB per sample read once, nothing written but the feature
 // gradients (64 B per sample).  k_wgrad_finish (field_bf.cu) still turns M into dW3 / dW4[:, :128].
 #include "field_bf.cuh"
@@ -36,16 +38,16 @@ constexpr int kBWStages = 4;              // weight ring
 // tensor memory
 constexpr int cHi = 0, cLo = 64, cAcc = 128, cW2 = 256, cM = 384;
 // spare accumulator columns of the small products (inside D, next to the N = 16 layers that use D[0,16))
-constexpr int cS0 = cAcc + 16;            // at G4 time: [0,16) dW4[:,128:] = G4^T F   [16,32) H2^T G5   [32,48) column sums of G4
-                                          // at G1 time: [0,16) dW1 = G1^T F          [16,32) HC^T G5   [32,48) column sums of G1
+constexpr int cS0 = cAcc + 16;            // at G4 time: [0,16) dW4[:,128:] = G4^T F   [16,32) H2^T G5
+                                          // at G1 time: [0,16) dW1 = G1^T F          [16,32) HC^T G5
+                                          // (the bias gradients = column sums of G4 / G2 / G1 are butterfly sums of the epilogues)
 // shared memory
 constexpr int kPlane = 32768;             // one f16 plane of a 128 x 128 operand: [kb 16][fb 16][8 samples][8 features x 2 B]
 constexpr int oG = kBWStages * kStageBytes;                    // gradient operand of the current layer (hi plane | lo plane)
 constexpr int oH = oG + 2 * kPlane;                            // forward activation, two 64-sample halves of 32 kB ([plane 2][kb 8][fb 16][128 B])
 constexpr int oFs = oH + 2 * 32768;                            // features of the tile, two halves of 4 kB ([plane 2][kb 8][fb 2][128 B])
 constexpr int oG5s = oFs + 2 * 4096;                           // G5 of the tile: [plane 2][kb 16][fb 2][128 B]
-constexpr int oOnes = oG5s + 2 * 4096;                         // 16 samples x 16 features of f16 1.0
-constexpr int oBars = oOnes + 512;                             // full[4] empty[4] a_ready mma_done h_full[2] h_free[2] all_done
+constexpr int oBars = oG5s + 2 * 4096;                            // full[4] empty[4] a_ready mma_done h_full[2] h_free[2] all_done
 constexpr int oTmemPtr = oBars + 8 * (2 * kBWStages + 7);
 constexpr int oW5 = (oTmemPtr + 16 + 15) & ~15;                           // W5 [3][128] fp32
 constexpr int oW30 = oW5 + 4 * 3 * 128;                        // W3 row 0 [128] fp32
@@ -57,6 +59,33 @@ __host__ __device__ constexpr int n_chunks(int l) { return 4; }                 
 __host__ __device__ constexpr int chunk_bytes(int l) { return hN(l) * 32 * 4; }
 __host__ __device__ constexpr int chunk_offset(int l, int c) { return layer_offset(l) + c * hN(l) * 32 * 4; }
 }  // namespace bw
+
+// Butterfly column sums over the 32 rows of a warp: 16 values per lane -> 1 (lane pairs hold the same sum); the column a lane
+// ends up with is c0 + 8 b4 + 4 b3 + 2 b2 + b1 (b = bits of the lane index).  Clobbers y.
+__device__ __forceinline__ float colsum16(float (&y)[16], int lane)
+{
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float send = (lane & 16) ? y[i] : y[i + 8], keep = (lane & 16) ? y[i + 8] : y[i];
+        y[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = (lane & 8) ? y[i] : y[i + 4], keep = (lane & 8) ? y[i + 4] : y[i];
+        y[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = (lane & 4) ? y[i] : y[i + 2], keep = (lane & 4) ? y[i + 2] : y[i];
+        y[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    {
+        const float send = (lane & 2) ? y[0] : y[1], keep = (lane & 2) ? y[1] : y[0];
+        y[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    y[0] += __shfl_xor_sync(0xffffffffu, y[0], 1);
+    return y[0];
+}
 
 // 16 accumulator columns of this thread's row: D -> (scale / mask / rank-1 term) -> f16 hi / lo -> next A operand in tensor
 // memory and, with `stg`, the same packed words into the shared-memory gradient operand (MN-major core-matrix order).
@@ -95,31 +124,7 @@ __device__ __forceinline__ void bw_epi16(uint32_t trow, int c0, uint32_t mask, i
     }
     tmem_st8(trow + cHi + c0 / 2, hi);
     tmem_st8(trow + cLo + c0 / 2, lo);
-    if (COLSUM) {
-        // butterfly column sums over the 32 rows of this warp: 16 values per lane -> 1 (lane pairs hold the same sum);
-        // the column a lane ends up with is c0 + 8 b4 + 4 b3 + 2 b2 + b1 (b = bits of the lane index)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float send = (lane & 16) ? y[i] : y[i + 8], keep = (lane & 16) ? y[i + 8] : y[i];
-            y[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float send = (lane & 8) ? y[i] : y[i + 4], keep = (lane & 8) ? y[i + 4] : y[i];
-            y[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-        }
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const float send = (lane & 4) ? y[i] : y[i + 2], keep = (lane & 4) ? y[i + 2] : y[i];
-            y[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-        }
-        {
-            const float send = (lane & 2) ? y[0] : y[1], keep = (lane & 2) ? y[1] : y[0];
-            y[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-        }
-        y[0] += __shfl_xor_sync(0xffffffffu, y[0], 1);
-        colsum += y[0];
-    }
+    if (COLSUM) colsum += colsum16(y, lane);
 }
 
 // optional timeline of CTA 0 (pslam_debug_bw_trace): [tile < 4][worker | issuer][16] clock64 stamps
@@ -137,6 +142,7 @@ k_field_bw(FieldParams p, const unsigned char *__restrict__ wstream, float *__re
 {
     pdl_enter();
     using namespace bw;
+    if (threadIdx.x == 128) BW_TRACE(3, 0, 11);
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + oBars);
     uint64_t *empty = full + kBWStages;
@@ -152,10 +158,13 @@ k_field_bw(FieldParams p, const unsigned char *__restrict__ wstream, float *__re
     const int nsamp = p.nsamp_dev ? *p.nsamp_dev : p.nsamp;
     const int ntiles = (nsamp + 127) / 128;
     const int G = (int)gridDim.x;
-    // the CTAs of a cluster share one weight stream: same number of iterations everywhere, out-of-range tiles are dummies
-    // (no valid rows, no weight-gradient MMAs, nothing loaded or stored)
-    const int iters = (ntiles + G - 1) / G;
+    // the CTAs of a CLUSTER share one weight stream: same number of iterations for both, an out-of-range tile is a dummy (no
+    // valid rows, no weight-gradient MMAs, nothing loaded or stored).  Clusters without a tile in the last round stop one
+    // round early: their drain (128 kB of red.v4 per CTA, ~16 k clocks when all 148 CTAs flush at once) then runs under the
+    // last round of the others.
     const uint32_t crank = cluster_ctarank();
+    const int cbase = (int)blockIdx.x - (int)crank;
+    const int iters = cbase < ntiles ? (ntiles - 1 - cbase) / G + 1 : 1;
 
     volatile int *scat_done = reinterpret_cast<volatile int *>(smem + oScatDone);
     if (threadIdx.x == 0) {
@@ -170,7 +179,6 @@ k_field_bw(FieldParams p, const unsigned char *__restrict__ wstream, float *__re
     if (warp == 0) tmem_alloc(tmem_ptr, kTmemCols);
     for (int i = threadIdx.x; i < 3 * 128; i += kBWThreads) sW5[i] = p.dec.W5[i];
     for (int i = threadIdx.x; i < 128; i += kBWThreads) sW30[i] = p.dec.W3[i];
-    for (int i = threadIdx.x; i < 128; i += kBWThreads) reinterpret_cast<uint32_t *>(smem + oOnes)[i] = 0x3C003C00u;   // f16 1.0 pairs
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     fence_before_sync();
     __syncthreads();
@@ -232,7 +240,6 @@ k_field_bw(FieldParams p, const unsigned char *__restrict__ wstream, float *__re
             const uint32_t a_hi = tmem + cHi, a_lo = tmem + cLo, d = tmem + cAcc;
             const uint32_t id128 = idesc_h16(128, 128, 1, 1), id16 = idesc_h16(128, 16, 1, 1);
             const uint32_t sG = smem_u32(smem + oG), sH = smem_u32(smem + oH), sF = smem_u32(smem + oFs), sG5 = smem_u32(smem + oG5s);
-            const uint64_t ones = sdesc(smem_u32(smem + oOnes), 256, 128);
             // one chain layer (packed layer L, N output columns) from the A operand in tensor memory
             auto chain = [&](auto lc, auto nc, bool first_acc_fresh) {
                 constexpr int L = decltype(lc)::value, N = decltype(nc)::value;
@@ -297,8 +304,6 @@ k_field_bw(FieldParams p, const unsigned char *__restrict__ wstream, float *__re
                         for (int ks = 0; ks < 8; ++ks) {
                             const uint32_t fresh = ks == 0 ? 0u : 1u;
                             prod3(cS0, g_desc(ks, 0), g_desc(ks, 1), f_desc(ks, 0), f_desc(ks, 1), id16, fresh);        // dW4[:,128:] = G4^T F
-                            mma_h16_ss(tmem + cS0 + 32, g_desc(ks, 0), ones, id16, fresh);                               // column sums of G4
-                            mma_h16_ss(tmem + cS0 + 32, g_desc(ks, 1), ones, id16, 1u);
                             if (ks < 4) prod3(cS0 + 16, h_desc(ks, 0), h_desc(ks, 1), g5_desc(ks, 0), g5_desc(ks, 1), id16, fresh);   // H2^T G5
                         }
                     }
@@ -385,8 +390,6 @@ k_field_bw(FieldParams p, const unsigned char *__restrict__ wstream, float *__re
                         for (int ks = 0; ks < 8; ++ks) {
                             const uint32_t fresh = ks == 0 ? 0u : 1u;
                             prod3(cS0, g_desc(ks, 0), g_desc(ks, 1), f_desc(ks, 0), f_desc(ks, 1), id16, fresh);        // dW1 = G1^T F
-                            mma_h16_ss(tmem + cS0 + 32, g_desc(ks, 0), ones, id16, fresh);                               // column sums of G1
-                            mma_h16_ss(tmem + cS0 + 32, g_desc(ks, 1), ones, id16, 1u);
                         }
                     }
                     __syncwarp();
@@ -461,10 +464,11 @@ k_field_bw(FieldParams p, const unsigned char *__restrict__ wstream, float *__re
             if (threadIdx.x == 128) BW_TRACE(tr_it, 0, tr_slot++);
         };
         // running sums of the small products of this thread's accumulator row n = m (threads of the second column half hold them)
-        float acc_w4f[16], acc_w1[16], acc_h2g5 = 0.f, acc_hcg5[3] = {0.f, 0.f, 0.f}, acc_s4 = 0.f, acc_s1 = 0.f;
+        float acc_w4f[16], acc_w1[16], acc_h2g5 = 0.f, acc_hcg5[3] = {0.f, 0.f, 0.f};
 #pragma unroll
         for (int e = 0; e < 16; ++e) { acc_w4f[e] = 0.f; acc_w1[e] = 0.f; }
         float db2[4] = {0.f, 0.f, 0.f, 0.f};              // butterfly column sums of g_h2: one column per 16-column batch and lane pair
+        float db4[4] = {0.f, 0.f, 0.f, 0.f}, db1[4] = {0.f, 0.f, 0.f, 0.f};   // the same of g_hc (compute_next) and g_h1 (phase 3)
         // next tile's per-row inputs
         uint32_t pm[6] = {0u, 0u, 0u, 0u, 0u, 0u};
         float4 po = make_float4(0.f, 0.f, 0.f, 0.f), pgo = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -480,7 +484,7 @@ k_field_bw(FieldParams p, const unsigned char *__restrict__ wstream, float *__re
         // warps) is computed one tile AHEAD, while the workers would otherwise wait ~3k clocks for the small products of
         // phase 4: the packed operand words wait in registers until the tile's last MMAs have completed, then only the stores
         // remain at the top of the next tile.
-        uint32_t nhi[4][8], nlo[4][8];                    // next tile: g_hc, f16 hi / lo words of this thread's 64 columns
+        uint32_t nhi[4][8] = {}, nlo[4][8] = {};          // next tile: g_hc, f16 hi / lo words of this thread's 64 columns
         float ng5[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t nm1[2] = {0u, 0u}, nm2[2] = {0u, 0u};
         auto compute_next = [&](int tn) {
@@ -498,10 +502,15 @@ k_field_bw(FieldParams p, const unsigned char *__restrict__ wstream, float *__re
                     atomicAdd(p.g_dec.b3, s3 * invSg);
                 }
             }
-#pragma unroll
+            // (rolled: the kernel's code is refetched from L2 -- after an L2 flush from DRAM -- in every round, the instruction
+            // caches hold a third of it; the four 16-column batches share one body and the packed words rotate through the
+            // register arrays, 64 moves per batch)
+#pragma unroll 1
             for (int j = 0; j < 4; ++j) {
                 const int c0 = col0 + 16 * j;
-                const uint32_t bits = mc[j >> 1] >> ((j & 1) * 16);
+                const uint32_t bits = ((j & 2) ? mc[1] : mc[0]) >> ((j & 1) * 16);
+                float y[16];
+                uint32_t thi[8], tlo[8];
 #pragma unroll
                 for (int qd = 0; qd < 4; ++qd) {          // (128-bit broadcast loads: the tensor core's operand reads want the shared-memory cycles)
                     const float4 w0 = *reinterpret_cast<const float4 *>(sW5 + c0 + 4 * qd);
@@ -516,89 +525,107 @@ k_field_bw(FieldParams p, const unsigned char *__restrict__ wstream, float *__re
                     y2 = ((bits >> (4 * qd + 2)) & 1u) ? y2 : 0.0f;
                     y3 = ((bits >> (4 * qd + 3)) & 1u) ? y3 : 0.0f;
                     ymax = fmaxf(ymax, fmaxf(fmaxf(fabsf(y0), fabsf(y1)), fmaxf(fabsf(y2), fabsf(y3))));
-                    h16_split2(y0, y1, nhi[j][2 * qd], nlo[j][2 * qd]);
-                    h16_split2(y2, y3, nhi[j][2 * qd + 1], nlo[j][2 * qd + 1]);
+                    h16_split2(y0, y1, thi[2 * qd], tlo[2 * qd]);
+                    h16_split2(y2, y3, thi[2 * qd + 1], tlo[2 * qd + 1]);
+                    y[4 * qd] = y0; y[4 * qd + 1] = y1; y[4 * qd + 2] = y2; y[4 * qd + 3] = y3;
+                }
+                const float cs = colsum16(y, lane);       // bias gradient of layer 4 (here it costs nothing: the workers are waiting)
+                db4[0] += (j == 0) ? cs : 0.f; db4[1] += (j == 1) ? cs : 0.f; db4[2] += (j == 2) ? cs : 0.f; db4[3] += (j == 3) ? cs : 0.f;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {             // batch j ends up in n??[j] after the four rotations
+                    nhi[0][e] = nhi[1][e]; nhi[1][e] = nhi[2][e]; nhi[2][e] = nhi[3][e]; nhi[3][e] = thi[e];
+                    nlo[0][e] = nlo[1][e]; nlo[1][e] = nlo[2][e]; nlo[2][e] = nlo[3][e]; nlo[3][e] = tlo[e];
                 }
             }
         };
-        prefetch_tile((int)blockIdx.x);
-        compute_next((int)blockIdx.x);
-        for (int it = 0; it < iters; ++it) {
+        if (threadIdx.x == 128) BW_TRACE(3, 0, 12);
+        // round -1 is the look-ahead for the first tile alone (one call site: compute_next is a fifth of the worker code)
+        for (int it = -1; it < iters; ++it) {
             const int tile = it * G + (int)blockIdx.x;
-            const bool real = tile < ntiles;
-            tr_it = it; tr_slot = 0;
-            if (threadIdx.x == 128) BW_TRACE(tr_it, 0, tr_slot++);
+            const bool real = it >= 0 && tile < ntiles;
             const int s = real ? tile * 128 + m : nsamp;
             const bool valid = s < nsamp;
-            const uint32_t m1[2] = {nm1[0], nm1[1]}, m2[2] = {nm2[0], nm2[1]};
-            const float gow = ng5[3];
-            if (lead) {
-                // G5 = (g5 r, g, b, g_sdf, 0 ...) as a 16-feature operand (second feature block zero: written once below)
-                uint32_t h0, l0, h1w, l1w;
-                h16_split2(ng5[0], ng5[1], h0, l0);
-                h16_split2(ng5[2], ng5[3], h1w, l1w);
-                *reinterpret_cast<uint4 *>(sG5row) = make_uint4(h0, h1w, 0u, 0u);
-                *reinterpret_cast<uint4 *>(sG5row + 4096) = make_uint4(l0, l1w, 0u, 0u);
-                if (it == 0) {
-                    *reinterpret_cast<uint4 *>(sG5row + 128) = make_uint4(0u, 0u, 0u, 0u);
-                    *reinterpret_cast<uint4 *>(sG5row + 4096 + 128) = make_uint4(0u, 0u, 0u, 0u);
+            if (it < 0) {
+                prefetch_tile((int)blockIdx.x);
+            } else {
+                tr_it = it; tr_slot = 0;
+                if (threadIdx.x == 128) BW_TRACE(tr_it, 0, tr_slot++);
+                const uint32_t m1[2] = {nm1[0], nm1[1]}, m2[2] = {nm2[0], nm2[1]};
+                const float gow = ng5[3];
+                if (lead) {
+                    // G5 = (g5 r, g, b, g_sdf, 0 ...) as a 16-feature operand (second feature block zero: written once below)
+                    uint32_t h0, l0, h1w, l1w;
+                    h16_split2(ng5[0], ng5[1], h0, l0);
+                    h16_split2(ng5[2], ng5[3], h1w, l1w);
+                    *reinterpret_cast<uint4 *>(sG5row) = make_uint4(h0, h1w, 0u, 0u);
+                    *reinterpret_cast<uint4 *>(sG5row + 4096) = make_uint4(l0, l1w, 0u, 0u);
+                    if (it == 0) {
+                        *reinterpret_cast<uint4 *>(sG5row + 128) = make_uint4(0u, 0u, 0u, 0u);
+                        *reinterpret_cast<uint4 *>(sG5row + 4096 + 128) = make_uint4(0u, 0u, 0u, 0u);
+                    }
                 }
-            }
-            // g_hc (computed during the previous tile) -> A and the G buffer
+                // g_hc (computed during the previous tile) -> A and the G buffer
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int c0 = col0 + 16 * j;
+                for (int j = 0; j < 4; ++j) {
+                    const int c0 = col0 + 16 * j;
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    unsigned char *dst = sGrow + (c0 / 8 + k) * 128;
-                    *reinterpret_cast<uint4 *>(dst) = make_uint4(nhi[j][4 * k], nhi[j][4 * k + 1], nhi[j][4 * k + 2], nhi[j][4 * k + 3]);
-                    *reinterpret_cast<uint4 *>(dst + kPlane) = make_uint4(nlo[j][4 * k], nlo[j][4 * k + 1], nlo[j][4 * k + 2], nlo[j][4 * k + 3]);
+                    for (int k = 0; k < 2; ++k) {
+                        unsigned char *dst = sGrow + (c0 / 8 + k) * 128;
+                        *reinterpret_cast<uint4 *>(dst) = make_uint4(nhi[j][4 * k], nhi[j][4 * k + 1], nhi[j][4 * k + 2], nhi[j][4 * k + 3]);
+                        *reinterpret_cast<uint4 *>(dst + kPlane) = make_uint4(nlo[j][4 * k], nlo[j][4 * k + 1], nlo[j][4 * k + 2], nlo[j][4 * k + 3]);
+                    }
+                    tmem_st8(trow + cHi + c0 / 2, nhi[j]);
+                    tmem_st8(trow + cLo + c0 / 2, nlo[j]);
                 }
-                tmem_st8(trow + cHi + c0 / 2, nhi[j]);
-                tmem_st8(trow + cLo + c0 / 2, nlo[j]);
+                a_is_ready();
+                // ---- phase 0 results: g_f part (lead) and the small products of G4 (second column half) ----
+                layer_done();
+                if (lead) {                                   // (the lead threads keep no running sums: acc_w4f doubles as this tile's g_f part)
+                    uint32_t v[16];
+                    tmem_ld16(trow + cAcc, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) acc_w4f[e] = __uint_as_float(v[e]);
+                } else if (real) {
+                    uint32_t v[16], w[8];
+                    tmem_ld16(trow + cS0, v);
+                    tmem_ld8(trow + cS0 + 16, w);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) acc_w4f[e] += __uint_as_float(v[e]);
+                    acc_h2g5 += __uint_as_float(w[3]);        // H2^T G5, column 3 (g_sdf) -> dW3 row 0
+                }
+                fence_before_sync();
+                mbar_arrive(a_ready);
+                if (threadIdx.x == 128) BW_TRACE(tr_it, 0, tr_slot++);
+                prefetch_tile(tile + G);                      // per-row inputs of the next tile: in flight during phases 1-3
+                // ---- phase 1: g_t -> A (not needed by the weight gradients: the G buffer keeps G4 for M += G4^T H2) ----
+                layer_done();
+                float nocs = 0.f;
+#pragma unroll 1
+                for (int j = 0; j < 4; ++j) bw_epi16<3, false, false>(trow, col0 + 16 * j, 0u, 0, nullptr, ymax, nullptr, 0.f, nocs, lane);
+                a_is_ready();
+                // ---- phase 2: g_h2 -> A and the G buffer (+ rank-1 sdf term, + db2) ----
+                layer_done();
+#pragma unroll                                    // (unrolled: on the critical path, and the batches overlap each other's TMEM / shuffle latencies)
+                for (int j = 0; j < 4; ++j) {
+                    float cs = 0.f;
+                    bw_epi16<2, true, true>(trow, col0 + 16 * j, (j & 2) ? m2[1] : m2[0], (j & 1) * 16, sGrow, ymax, sW30, gow, cs, lane);
+                    db2[0] += (j == 0) ? cs : 0.f; db2[1] += (j == 1) ? cs : 0.f; db2[2] += (j == 2) ? cs : 0.f; db2[3] += (j == 3) ? cs : 0.f;
+                }
+                a_is_ready();
+                // ---- phase 3: g_h1 -> A and the G buffer ----
+                layer_done();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float cs = 0.f;
+                    bw_epi16<2, false, true>(trow, col0 + 16 * j, (j & 2) ? m1[1] : m1[0], (j & 1) * 16, sGrow, ymax, nullptr, 0.f, cs, lane);
+                    db1[0] += (j == 0) ? cs : 0.f; db1[1] += (j == 1) ? cs : 0.f; db1[2] += (j == 2) ? cs : 0.f; db1[3] += (j == 3) ? cs : 0.f;
+                }
+                a_is_ready();
             }
-            a_is_ready();
-            // ---- phase 0 results: g_f part (lead) and the small products of G4 (second column half) ----
-            layer_done();
-            if (lead) {                                   // (the lead threads keep no running sums: acc_w4f doubles as this tile's g_f part)
-                uint32_t v[16];
-                tmem_ld16(trow + cAcc, v);
-                tmem_wait_ld();
-#pragma unroll
-                for (int e = 0; e < 16; ++e) acc_w4f[e] = __uint_as_float(v[e]);
-            } else if (real) {
-                uint32_t v[16], w[8], cs[8];
-                tmem_ld16(trow + cS0, v);
-                tmem_ld8(trow + cS0 + 16, w);
-                tmem_ld8(trow + cS0 + 32, cs);
-                tmem_wait_ld();
-#pragma unroll
-                for (int e = 0; e < 16; ++e) acc_w4f[e] += __uint_as_float(v[e]);
-                acc_h2g5 += __uint_as_float(w[3]);        // H2^T G5, column 3 (g_sdf) -> dW3 row 0
-                acc_s4 += __uint_as_float(cs[0]);         // column sums of G4 (every column of the ones operand is the same)
-            }
-            fence_before_sync();
-            mbar_arrive(a_ready);
-            if (threadIdx.x == 128) BW_TRACE(tr_it, 0, tr_slot++);
-            prefetch_tile(tile + G);                      // per-row inputs of the next tile: in flight during phases 1-3
-            // ---- phase 1: g_t -> A (not needed by the weight gradients: the G buffer keeps G4 for M += G4^T H2) ----
-            layer_done();
-            float nocs = 0.f;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) bw_epi16<3, false, false>(trow, col0 + 16 * j, 0u, 0, nullptr, ymax, nullptr, 0.f, nocs, lane);
-            a_is_ready();
-            // ---- phase 2: g_h2 -> A and the G buffer (+ rank-1 sdf term, + db2) ----
-            layer_done();
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                bw_epi16<2, true, true>(trow, col0 + 16 * j, m2[j >> 1], (j & 1) * 16, sGrow, ymax, sW30, gow, db2[j], lane);
-            a_is_ready();
-            // ---- phase 3: g_h1 -> A and the G buffer ----
-            layer_done();
-#pragma unroll
-            for (int j = 0; j < 4; ++j) bw_epi16<2, false, false>(trow, col0 + 16 * j, m1[j >> 1], (j & 1) * 16, sGrow, ymax, nullptr, 0.f, nocs, lane);
-            a_is_ready();
             compute_next(tile + G);                       // (under the MMAs of phase 4; its inputs were requested after phase 0)
+            if (it < 0) continue;
             // ---- phase 4 results: g_f (lead) and the small products of G1 ----
             layer_done();
             if (lead) {
@@ -618,15 +645,13 @@ k_field_bw(FieldParams p, const unsigned char *__restrict__ wstream, float *__re
                     atomicAdd(const_cast<int *>(scat_done), 1);
                 }
             } else if (real) {
-                uint32_t v[16], w[8], cs[8];
+                uint32_t v[16], w[8];
                 tmem_ld16(trow + cS0, v);
                 tmem_ld8(trow + cS0 + 16, w);
-                tmem_ld8(trow + cS0 + 32, cs);
                 tmem_wait_ld();
 #pragma unroll
                 for (int e = 0; e < 16; ++e) acc_w1[e] += __uint_as_float(v[e]);
                 acc_hcg5[0] += __uint_as_float(w[0]); acc_hcg5[1] += __uint_as_float(w[1]); acc_hcg5[2] += __uint_as_float(w[2]);
-                acc_s1 += __uint_as_float(cs[0]);
             }
             // (the next tile's first epilogue writes A, the G buffer and G5: every MMA of this tile has completed -- mma_done above)
         }
@@ -634,6 +659,7 @@ k_field_bw(FieldParams p, const unsigned char *__restrict__ wstream, float *__re
         // ===================== drain: the big accumulators and this thread's running sums -> global gradients =====================
         mbar_wait(all_done, 0);
         fence_after_sync();
+        if (threadIdx.x == 128) BW_TRACE(3, 0, 13);
         const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / G + 1 : 0;
         if (my_tiles > 0) {
             const float cW = kInvScale * invSg;           // accumulators hold 16 x Sg x (sum of products), column sums Sg x (sum)
@@ -659,20 +685,24 @@ k_field_bw(FieldParams p, const unsigned char *__restrict__ wstream, float *__re
                 atomicAdd(p.g_dec.W5 + 128 + n, cW * acc_hcg5[1]);
                 atomicAdd(p.g_dec.W5 + 256 + n, cW * acc_hcg5[2]);
                 atomicAdd(p.g_dec.W3 + n, cW * acc_h2g5);
-                atomicAdd(finish + 128 * 128 + n, invSg * acc_s4);
-                atomicAdd(p.g_dec.b1 + n, invSg * acc_s1);
             }
-            if ((lane & 1) == 0) {                        // db2: lane pairs hold the same sums
+            if ((lane & 1) == 0) {                        // bias gradients: lane pairs hold the same column sums
                 const int cb = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) atomicAdd(p.g_dec.b2 + col0 + 16 * j + cb, invSg * db2[j]);
+                for (int j = 0; j < 4; ++j) {
+                    atomicAdd(p.g_dec.b2 + col0 + 16 * j + cb, invSg * db2[j]);
+                    atomicAdd(p.g_dec.b1 + col0 + 16 * j + cb, invSg * db1[j]);
+                    atomicAdd(finish + 128 * 128 + col0 + 16 * j + cb, invSg * db4[j]);
+                }
             }
         }
     }
+    if (threadIdx.x == 128) BW_TRACE(3, 0, 14);
     fence_before_sync();
     __syncthreads();
     cluster_sync();
     if (warp == 0) tmem_dealloc(tmem, bf::kTmemCols);
+    if (threadIdx.x == 128) BW_TRACE(3, 0, 15);
 }
 
 static int g_bw_enabled = 1, g_bw_scatter = 0;   // fused scatter: measured slower (see the role's comment), off by default

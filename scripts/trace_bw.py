@@ -33,7 +33,7 @@ pipe.stage(9)
 torch.cuda.synchronize()
 lib.pslam_debug_bw_trace(None)
 t = buf.cpu().view(4, 2, 16)
-for it in (1, 2):
+for it in (0, 1, 2):
     t0 = int(t[it, 0, 0])
     w = [int(x) - t0 for x in t[it, 0, :11]]
     i = [int(x) - t0 for x in t[it, 1, :15]]
@@ -42,3 +42,6 @@ for it in (1, 2):
         print(f"   phase {ph}: issuer saw operand {i[3 * ph]}, chain issued {i[3 * ph + 1]} | worker saw accumulators {w[2 + 2 * ph]}"
               + (f", epilogue published {w[3 + 2 * ph]}" if ph < 4 else ""))
     print(f"   issuer done with the tile {i[14]}; next tile starts {int(t[it + 1, 0, 0]) - t0}")
+e = [int(x) - int(t[3, 0, 11]) for x in t[3, 0, 11:16]]
+print(f"CTA 0: entry 0, worker loop starts {e[1]}, all MMAs done {e[2]}, drain done {e[3]}, cluster released {e[4]} clocks")
+print("tile starts of CTA 0 (clocks after entry):", [int(t[i, 0, 0]) - int(t[3, 0, 11]) for i in range(4)])
