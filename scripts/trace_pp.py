@@ -40,6 +40,7 @@ def show(stage, nph, title):
     span = buf.cpu()[256:256 + 296].view(148, 2)
     t = buf.cpu()[:256].view(4, 4, 16)
     print("==", title)
+    print("  iteration starts:", [int(t[i, 0, 0]) - int(t[0, 0, 0]) for i in range(4)])
     for it in (1, 2):
         t0 = int(t[it, 0, 0])
         for g in (0, 1):
