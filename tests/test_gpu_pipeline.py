@@ -302,6 +302,49 @@ def test_optional_kernel_paths_change_nothing(option, value, device):
         assert rel_err(a, b) < 1e-5
 
 
+@pytest.mark.parametrize("tiles", [1, 147, 148, 149, 150, 297, 445])
+def test_fused_backward_at_tile_count_boundaries(tiles, device):
+    """k_field_bw (dgrad + weight gradients in one kernel): its CTAs work in 2-CTA clusters that share one weight stream, clusters
+    run a per-cluster number of rounds and drain early when they have no tile in the last one.  The tile count is pinned through
+    the sample capacity (the batch has more samples; the tail is cut identically for both runs): fewer tiles than CTAs, exactly
+    one round, one tile more (a cluster with one real and one dummy tile), two, 2 rounds + 1, 3 rounds + 1.  Against the
+    unfused kernels (PSLAM_OPT_FUSED_WGRAD = 0: chain kernel + k_wgrad_bf)."""
+    from proud_slam_b200 import _lib, scene as sc
+    from proud_slam_b200.pipeline import RenderPipeline
+    s, ms = util.build_scene("replica_small")
+    dec = util.test_decoder(width=128, seed=3)
+    rays_o, rays_d, rgb, depth = sc.sample_batch(s, [0, 1, 2], 2048, seed=17)
+    msd = util.to_device(ms, device)
+    msd["voxel_vertex_emb"] = msd["voxel_vertex_emb"].detach()
+    decd = [p.detach().to(device) for p in dec]
+    cw = (util.CRIT["rgb_weight"], util.CRIT["depth_weight"], util.CRIT["fs_weight"], util.CRIT["sdf_weight"])
+    cap = 128 * tiles
+    R = min(rays_o.shape[0] * rays_o.shape[1], cap)
+    inp = [t.to(device).reshape(-1, 3)[:R].contiguous() for t in (rays_o, rays_d, rgb)] + [depth.to(device).reshape(-1)[:R].contiguous()]
+    spr = next(d for d in range(cap // R, 0, -1) if cap % d == 0)          # sample capacity = max_rays x samples_per_ray = cap exactly
+    res = []
+    try:
+        for fused in (1, 0):
+            assert _lib.lib().pslam_set_option(5, fused) == 0
+            pipe = RenderPipeline(cap // spr, device, samples_per_ray=spr)
+            assert pipe.sample_cap == cap
+            g_emb = torch.zeros_like(msd["voxel_vertex_emb"])
+            g_dec = [torch.zeros_like(p) for p in decd]
+            pipe.bind(inp[0], inp[1], msd, decd, voxel_size=s.voxel_size, step_size=0.1 * s.voxel_size, truncation=util.CRIT["truncation"],
+                      max_distance=10.0, max_depth=util.CRIT["max_depth"], target_rgb=inp[2], target_depth=inp[3], noise=None, weights=cw,
+                      tracking=False, g_emb=g_emb, g_dec=g_dec, grad_rays=True)
+            pipe.step()
+            torch.cuda.synchronize()
+            host = pipe.counters.cpu()
+            assert int(host[_lib.C_NSAMP]) >= cap and int(host[_lib.C_OVERFLOW]) & 1, "the batch must overfill the capacity: that pins the tile count"
+            res.append([g_emb, pipe.g_rays_o.clone(), pipe.g_rays_d.clone()] + g_dec)
+    finally:
+        _lib.lib().pslam_set_option(5, 1)
+    for a, b in zip(res[0], res[1]):
+        assert torch.isfinite(a).all()
+        assert rel_err(a, b) < 1e-5
+
+
 def test_f16_operand_range_is_guarded(device):
     """3xF16 build: operands are kept in f16's window by fixed power-of-two scales; a decoder whose activations leave it
     (|16 x value| >= 32752) must be reported through the overflow counter, not silently clipped."""
